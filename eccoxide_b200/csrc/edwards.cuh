@@ -1,0 +1,182 @@
+// edwards.cuh — edwards25519 group arithmetic (extended coordinates, a = -1) and the
+// curve25519 x-only ladder, device side.
+//
+// Group law = the reference's Point (src/curve/curve25519.rs:592-757): double_parts :604,
+// add :695 (HWCD complete addition with 2d), add_cached :715.  The batch path is free to
+// schedule the group operations differently (signed windows, precomputed affine "niels"
+// entries with Z = 1) because only canonical affine bytes are observable.
+#pragma once
+#include "fe25519.cuh"
+
+namespace ecb {
+
+typedef F25519 F;
+
+struct ge_p3 {
+    fe25519 X, Y, Z, T;
+};
+// affine precomputed point: (y+x, y-x, 2d*x*y)
+struct ge_niels {
+    fe25519 yp, ym, t2d;
+};
+// projective precomputed point: (Y+X, Y-X, Z, 2d*T)  (CachedPoint, curve25519.rs:994)
+struct ge_cached {
+    fe25519 yp, ym, Z, t2d;
+};
+
+ECB_DEV void ge_identity(ge_p3& r) {
+    F::set_zero(r.X);
+    F::set_one(r.Y);
+    F::set_one(r.Z);
+    F::set_zero(r.T);
+}
+ECB_DEV void ge_from_affine(ge_p3& r, const fe25519& x, const fe25519& y) {
+    F::copy(r.X, x);
+    F::copy(r.Y, y);
+    F::set_one(r.Z);
+    F::mul(r.T, x, y);
+}
+// a*x^2 + y^2 == 1 + d*x^2*y^2 (Point::from_coordinate, curve25519.rs:649)
+ECB_DEV u32 ge_on_curve(const fe25519& x, const fe25519& y) {
+    fe25519 xx, yy, l, r, d, one;
+    F::sqr(xx, x);
+    F::sqr(yy, y);
+    F::sub(l, yy, xx);
+    F::from_words(d, ED25519_D);
+    F::mul(r, xx, yy);
+    F::mul(r, r, d);
+    F::set_one(one);
+    F::add(r, r, one);
+    return F::eq(l, r);
+}
+
+// r = 2p. 4S + 3M (+1M when WITH_T)
+template <bool WITH_T>
+ECB_DEV void ge_double(ge_p3& r, const ge_p3& p) {
+    fe25519 A, B, C, E, G, Fv, H, t;
+    F::sqr(A, p.X);
+    F::sqr(B, p.Y);
+    F::sqr(C, p.Z);
+    F::dbl(C, C);
+    F::add(t, p.X, p.Y);
+    F::sqr(E, t);
+    F::add(H, A, B);      // A + B
+    F::sub(E, E, H);      // E = (X+Y)^2 - A - B
+    F::sub(G, B, A);      // G = D + B = B - A
+    F::sub(Fv, G, C);     // F = G - C
+    F::neg(H, H);         // H = D - B = -(A + B)
+    F::mul(r.X, E, Fv);
+    F::mul(r.Y, G, H);
+    F::mul(r.Z, Fv, G);
+    if (WITH_T) F::mul(r.T, E, H);
+}
+
+// r = p + q, q affine precomputed. 7M (6M when !WITH_T)
+template <bool WITH_T>
+ECB_DEV void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) {
+    fe25519 A, B, C, D, E, Fv, G, H;
+    F::sub(A, p.Y, p.X);
+    F::mul(A, A, q.ym);
+    F::add(B, p.Y, p.X);
+    F::mul(B, B, q.yp);
+    F::mul(C, p.T, q.t2d);
+    F::dbl(D, p.Z);
+    F::sub(E, B, A);
+    F::sub(Fv, D, C);
+    F::add(G, D, C);
+    F::add(H, B, A);
+    F::mul(r.X, E, Fv);
+    F::mul(r.Y, G, H);
+    F::mul(r.Z, Fv, G);
+    if (WITH_T) F::mul(r.T, E, H);
+}
+
+// r = p + q, q projective cached. 8M
+template <bool WITH_T>
+ECB_DEV void ge_add_cached(ge_p3& r, const ge_p3& p, const ge_cached& q) {
+    fe25519 A, B, C, D, E, Fv, G, H;
+    F::sub(A, p.Y, p.X);
+    F::mul(A, A, q.ym);
+    F::add(B, p.Y, p.X);
+    F::mul(B, B, q.yp);
+    F::mul(C, p.T, q.t2d);
+    F::mul(D, p.Z, q.Z);
+    F::dbl(D, D);
+    F::sub(E, B, A);
+    F::sub(Fv, D, C);
+    F::add(G, D, C);
+    F::add(H, B, A);
+    F::mul(r.X, E, Fv);
+    F::mul(r.Y, G, H);
+    F::mul(r.Z, Fv, G);
+    if (WITH_T) F::mul(r.T, E, H);
+}
+
+ECB_DEV void ge_to_cached(ge_cached& r, const ge_p3& p) {
+    fe25519 d2;
+    F::from_words(d2, ED25519_D2);
+    F::add(r.yp, p.Y, p.X);
+    F::sub(r.ym, p.Y, p.X);
+    F::copy(r.Z, p.Z);
+    F::mul(r.t2d, p.T, d2);
+}
+ECB_DEV void ge_cached_identity(ge_cached& r) {
+    F::set_one(r.yp);
+    F::set_one(r.ym);
+    F::set_one(r.Z);
+    F::set_zero(r.t2d);
+}
+// conditional negation: (yp, ym, Z, t2d) -> (ym, yp, Z, -t2d)
+ECB_DEV void ge_cached_cneg(ge_cached& r, u32 neg) {
+    F::cswap(neg, r.yp, r.ym);
+    fe25519 nt;
+    F::neg(nt, r.t2d);
+    F::select(r.t2d, neg, nt, r.t2d);
+}
+ECB_DEV void ge_niels_identity(ge_niels& r) {
+    F::set_one(r.yp);
+    F::set_one(r.ym);
+    F::set_zero(r.t2d);
+}
+ECB_DEV void ge_niels_cneg(ge_niels& r, u32 neg) {
+    F::cswap(neg, r.yp, r.ym);
+    fe25519 nt;
+    F::neg(nt, r.t2d);
+    F::select(r.t2d, neg, nt, r.t2d);
+}
+// affine (x, y) -> niels
+ECB_DEV void ge_niels_from_affine(ge_niels& r, const fe25519& x, const fe25519& y) {
+    fe25519 d2, t;
+    F::from_words(d2, ED25519_D2);
+    F::add(r.yp, y, x);
+    F::sub(r.ym, y, x);
+    F::mul(t, x, y);
+    F::mul(r.t2d, t, d2);
+}
+
+// Booth signed digit of width W for window i of the little-endian scalar words k[0..nw):
+// d = -2^(W-1) b_{Wi+W-1} + sum_{j<W-1} 2^j b_{Wi+j} + b_{Wi-1}.  Returns |d| in [0, 2^(W-1)]
+// and the sign.  sum_i d_i 2^(Wi) = k for ceil((bits+1)/W) windows.
+ECB_DEV u32 booth_digit(const u32* k, int nwords, int W, int i, u32& neg) {
+    int pos = W * i - 1;  // lowest bit of the (W+1)-bit view; -1 for i = 0
+    u32 view;
+    if (pos < 0) {
+        view = k[0] << 1;
+    } else {
+        int wd = pos >> 5, sh = pos & 31;
+        u32 lo = wd < nwords ? k[wd] : 0u;
+        u32 hi = (wd + 1) < nwords ? k[wd + 1] : 0u;
+        view = sh ? ((lo >> sh) | (hi << (32 - sh))) : lo;
+    }
+    view &= (2u << W) - 1u;  // W+1 bits
+    u32 s = view >> W;       // top bit = sign
+    u32 d = (view + 1u) >> 1;
+    // if sign: d = 2^W - d  (in units after the +1>>1 trick)
+    u32 dn = (1u << W) - d;
+    neg = s;
+    u32 r = s ? dn : d;
+    if (r == 0) neg = 0;
+    return r;
+}
+
+}  // namespace ecb

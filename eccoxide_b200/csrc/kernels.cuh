@@ -1,0 +1,521 @@
+// kernels.cuh — per-thread bodies of the batch kernels.
+//
+// Each body takes its global thread index explicitly; eccbatch.cu wraps them in __global__
+// launchers (one thread per scalar multiplication), tests/hostsim/ loops over them on the CPU.
+//
+// Data layout in HBM
+//   inputs / outputs : the reference's wire encodings, AoS, contiguous (32/48/56-byte elements)
+//   intermediates    : structure-of-arrays "planes": plane[limb * n + idx], so a warp reading limb
+//                      `l` of 32 consecutive elements touches one 128-byte line
+//   tables           : fixed-base comb tables as arrays of 96-byte niels entries (L2-resident)
+//                      per-thread window tables of variable-base kernels in a scratch arena,
+//                      one contiguous block per resident thread
+#pragma once
+#include "edwards.cuh"
+#include "weier.cuh"
+
+namespace ecb {
+
+// status word written with atomicMin: (index << 8) | code ; ~0 = no error
+enum { ST_NONCANONICAL_SCALAR = 1, ST_BAD_POINT = 2 };
+
+#ifdef ECB_HOSTSIM
+ECB_DEV void report_bad(unsigned long long* st, size_t idx, u32 code) {
+    unsigned long long v = ((unsigned long long)idx << 8) | code;
+    if (v < *st) *st = v;
+}
+ECB_DEV u32 bswap32(u32 x) { return __builtin_bswap32(x); }
+#else
+ECB_DEV void report_bad(unsigned long long* st, size_t idx, u32 code) {
+    atomicMin(st, ((unsigned long long)idx << 8) | code);
+}
+ECB_DEV u32 bswap32(u32 x) { return __byte_perm(x, 0, 0x0123); }
+#endif
+
+// ---- word movers -----------------------------------------------------------------------
+template <int NW>
+ECB_DEV void ld_words(u32* dst, const u32* src) {
+#ifndef ECB_HOSTSIM
+    if (NW % 4 == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        ECB_UNROLL
+        for (int i = 0; i < NW / 4; i++) {
+            uint4 v = __ldg(s4 + i);
+            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
+        }
+        return;
+    }
+    if (NW % 2 == 0) {
+        const uint2* s2 = reinterpret_cast<const uint2*>(src);
+        ECB_UNROLL
+        for (int i = 0; i < NW / 2; i++) {
+            uint2 v = __ldg(s2 + i);
+            dst[2 * i] = v.x; dst[2 * i + 1] = v.y;
+        }
+        return;
+    }
+#endif
+    ECB_UNROLL
+    for (int i = 0; i < NW; i++) dst[i] = src[i];
+}
+template <int NW>
+ECB_DEV void st_words(u32* dst, const u32* src) {
+#ifndef ECB_HOSTSIM
+    if (NW % 4 == 0) {
+        uint4* d4 = reinterpret_cast<uint4*>(dst);
+        ECB_UNROLL
+        for (int i = 0; i < NW / 4; i++) d4[i] = make_uint4(src[4 * i], src[4 * i + 1], src[4 * i + 2], src[4 * i + 3]);
+        return;
+    }
+    if (NW % 2 == 0) {
+        uint2* d2 = reinterpret_cast<uint2*>(dst);
+        ECB_UNROLL
+        for (int i = 0; i < NW / 2; i++) d2[i] = make_uint2(src[2 * i], src[2 * i + 1]);
+        return;
+    }
+#endif
+    ECB_UNROLL
+    for (int i = 0; i < NW; i++) dst[i] = src[i];
+}
+// big-endian wire bytes (NW words) <-> little-endian limbs
+template <int NW>
+ECB_DEV void ld_words_be(u32* dst, const u32* src) {
+    u32 t[NW];
+    ld_words<NW>(t, src);
+    ECB_UNROLL
+    for (int i = 0; i < NW; i++) dst[i] = bswap32(t[NW - 1 - i]);
+}
+template <int NW>
+ECB_DEV void st_words_be(u32* dst, const u32* src) {
+    u32 t[NW];
+    ECB_UNROLL
+    for (int i = 0; i < NW; i++) t[i] = bswap32(src[NW - 1 - i]);
+    st_words<NW>(dst, t);
+}
+template <int NW>
+ECB_DEV void plane_st(u32* plane, size_t n, size_t idx, const u32* v) {
+    ECB_UNROLL
+    for (int i = 0; i < NW; i++) plane[(size_t)i * n + idx] = v[i];
+}
+template <int NW>
+ECB_DEV void plane_ld(u32* v, const u32* plane, size_t n, size_t idx) {
+    ECB_UNROLL
+    for (int i = 0; i < NW; i++) v[i] = plane[(size_t)i * n + idx];
+}
+
+// l = 2^252 + 27742317777372353535851937790883648493 (curve25519.rs:46 ORDER_LIMBS)
+ECB_CONST u32 ED25519_L[8] = {0x5cf5d3edu, 0x5812631au, 0xa2f79cd6u, 0x14def9deu,
+                              0x00000000u, 0x00000000u, 0x00000000u, 0x10000000u};
+ECB_DEV u32 lt_words8(const u32* a, const u32* m) {  // a < m ?
+    u32 d = sub_cc(a[0], m[0]);
+    ECB_UNROLL
+    for (int i = 1; i < 8; i++) d = subc_cc(a[i], m[i]);
+    (void)d;
+    return subc(0, 0) & 1;
+}
+
+// =======================================================================================
+// Ed25519 fixed base: k*B from a signed-digit comb table  (replaces Point::mul_base,
+// curve25519.rs:840-869 + params/comb/curve25519.rs)
+//   table[(i * half + (j-1)) * 24 ..] = niels( j * 2^(W*i) * B ),  j = 1..half = 2^(W-1),
+//   i = 0..nwin-1, nwin = ceil(254 / W).
+// Writes projective X, Y, Z planes; the affine conversion is the batch-inversion kernel.
+// =======================================================================================
+ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin,
+                                   u32* planes, unsigned long long* status) {
+    u32 k[8];
+    ld_words<8>(k, scalars + idx * 8);
+    if (!lt_words8(k, ED25519_L)) {
+        report_bad(status, idx, ST_NONCANONICAL_SCALAR);
+        ECB_UNROLL
+        for (int i = 0; i < 8; i++) k[i] = 0;
+    }
+    const u32 half = 1u << (W - 1);
+    ge_p3 acc;
+    ge_identity(acc);
+    for (int i = 0; i < nwin; i++) {
+        u32 neg;
+        u32 d = booth_digit(k, 8, W, i, neg);
+        ge_niels e;
+        ge_niels_identity(e);
+        if (d != 0) {
+            const u32* src = table + ((size_t)i * half + (d - 1)) * 24;
+            ld_words<8>(e.yp.v, src);
+            ld_words<8>(e.ym.v, src + 8);
+            ld_words<8>(e.t2d.v, src + 16);
+        }
+        ge_niels_cneg(e, neg);
+        ge_madd<true>(acc, acc, e);
+    }
+    plane_st<8>(planes + 0 * 8 * n, n, idx, acc.X.v);
+    plane_st<8>(planes + 1 * 8 * n, n, idx, acc.Y.v);
+    plane_st<8>(planes + 2 * 8 * n, n, idx, acc.Z.v);
+}
+
+// comb-table builder: entry (i, j) = j * 2^(W*i) * B by plain double-and-add on the 256-bit
+// integer s = j << (W*i); output projective planes (4*8 words: X,Y,Z) over ntab entries.
+ECB_DEV void ed25519_table_point_body(size_t e, size_t ntab, int W, int nwin, u32* planes) {
+    const u32 half = 1u << (W - 1);
+    u32 i = (u32)(e / half), j = (u32)(e % half) + 1;
+    u32 s[9];
+    ECB_UNROLL
+    for (int t = 0; t < 9; t++) s[t] = 0;
+    int sh = W * (int)i;
+    int wd = sh >> 5, b = sh & 31;
+    // j < 2^16, may straddle two words
+    u32 lo = j << b, hi = b ? (j >> (32 - b)) : 0u;
+    for (int t = 0; t < 9; t++) {
+        if (t == wd) s[t] |= lo;
+        if (t == wd + 1) s[t] |= hi;
+    }
+    fe25519 bx, by;
+    F::from_words(bx, ED25519_BX);
+    F::from_words(by, ED25519_BY);
+    ge_niels nb;
+    ge_niels_from_affine(nb, bx, by);
+    ge_p3 acc;
+    ge_identity(acc);
+    for (int bit = W * nwin - 1; bit >= 0; bit--) {  // W*nwin <= 288 bits
+        ge_double<true>(acc, acc);
+        u32 wv = 0;
+        for (int t = 0; t < 9; t++)
+            if (t == (bit >> 5)) wv = s[t];
+        if ((wv >> (bit & 31)) & 1) ge_madd<true>(acc, acc, nb);
+    }
+    plane_st<8>(planes + 0 * 8 * ntab, ntab, e, acc.X.v);
+    plane_st<8>(planes + 1 * 8 * ntab, ntab, e, acc.Y.v);
+    plane_st<8>(planes + 2 * 8 * ntab, ntab, e, acc.Z.v);
+}
+
+// =======================================================================================
+// Ed25519 variable base: k*P, signed 4-bit Booth windows over a per-thread table of 8 cached
+// multiples (replaces &Point * &Scalar, curve25519.rs:746-760 / :1274).
+//   tbl : this thread's scratch, 8 entries x 32 words
+// =======================================================================================
+ECB_DEV void ed25519_mul_body(size_t idx, size_t n, const u32* scalars, const u32* points, u32* tbl, u32* planes,
+                              unsigned long long* status) {
+    u32 k[8], w[16];
+    ld_words<8>(k, scalars + idx * 8);
+    ld_words<16>(w, points + idx * 16);
+    u32 ok = 1;
+    if (!lt_words8(k, ED25519_L)) {
+        report_bad(status, idx, ST_NONCANONICAL_SCALAR);
+        ok = 0;
+    }
+    fe25519 x, y;
+    F::from_words(x, w);
+    F::from_words(y, w + 8);
+    if (ok && !(F::is_canonical_words(w) && F::is_canonical_words(w + 8) && ge_on_curve(x, y))) {
+        report_bad(status, idx, ST_BAD_POINT);
+        ok = 0;
+    }
+    if (!ok) {
+        // neutral inputs keep the arithmetic defined; the host discards the batch on error
+        ECB_UNROLL
+        for (int i = 0; i < 8; i++) k[i] = 0;
+        F::set_zero(x);
+        F::set_one(y);
+    }
+    ge_p3 P, acc;
+    ge_from_affine(P, x, y);
+    // table[j-1] = cached(j*P), j = 1..8
+    {
+        ge_cached c, c1;
+        ge_to_cached(c1, P);
+        st_words<8>(tbl + 0, c1.yp.v); st_words<8>(tbl + 8, c1.ym.v); st_words<8>(tbl + 16, c1.Z.v); st_words<8>(tbl + 24, c1.t2d.v);
+        ge_double<true>(acc, P);
+        for (int j = 2; j <= 8; j++) {
+            ge_to_cached(c, acc);
+            u32* d = tbl + (j - 1) * 32;
+            st_words<8>(d + 0, c.yp.v); st_words<8>(d + 8, c.ym.v); st_words<8>(d + 16, c.Z.v); st_words<8>(d + 24, c.t2d.v);
+            if (j < 8) ge_add_cached<true>(acc, acc, c1);
+        }
+    }
+    // k < 2^253: 64 Booth windows of width 4 cover 256 bits
+    ge_identity(acc);
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) {
+            ge_double<false>(acc, acc);
+            ge_double<false>(acc, acc);
+            ge_double<false>(acc, acc);
+            ge_double<true>(acc, acc);
+        }
+        u32 neg;
+        u32 d = booth_digit(k, 8, 4, i, neg);
+        ge_cached c;
+        ge_cached_identity(c);
+        if (d != 0) {
+            const u32* s = tbl + (d - 1) * 32;
+            ld_words<8>(c.yp.v, s); ld_words<8>(c.ym.v, s + 8); ld_words<8>(c.Z.v, s + 16); ld_words<8>(c.t2d.v, s + 24);
+        }
+        ge_cached_cneg(c, neg);
+        ge_add_cached<true>(acc, acc, c);
+    }
+    plane_st<8>(planes + 0 * 8 * n, n, idx, acc.X.v);
+    plane_st<8>(planes + 1 * 8 * n, n, idx, acc.Y.v);
+    plane_st<8>(planes + 2 * 8 * n, n, idx, acc.Z.v);
+}
+
+// =======================================================================================
+// X25519: the reference's ladder, step for step (protocol/x25519.rs:36-45, curve25519.rs:474-513):
+// clamp, mask bit 255 of u (no canonical check), 256 ladder steps MSB first, final cswap.
+// Writes x2 -> plane 0, z2 -> plane 2; u' = x2 * z2^-1 (0 for z2 = 0) is the batch inversion.
+// =======================================================================================
+ECB_DEV void x25519_body(size_t idx, size_t n, const u32* scalars, const u32* us, u32* planes) {
+    u32 k[8], uw[8];
+    ld_words<8>(k, scalars + idx * 8);
+    ld_words<8>(uw, us + idx * 8);
+    k[0] &= 0xfffffff8u;
+    k[7] = (k[7] & 0x7fffffffu) | 0x40000000u;
+    uw[7] &= 0x7fffffffu;
+    fe25519 x1, x2, z2, x3, z3;
+    F::from_words(x1, uw);
+    F::set_one(x2);
+    F::set_zero(z2);
+    F::copy(x3, x1);
+    F::set_one(z3);
+    u32 swap = 0;
+    for (int wi = 7; wi >= 0; wi--) {
+        u32 word = 0;
+        ECB_UNROLL
+        for (int t = 0; t < 8; t++)
+            if (t == wi) word = k[t];
+        for (int bi = 31; bi >= 0; bi--) {
+            u32 bit = (word >> bi) & 1u;
+            swap ^= bit;
+            F::cswap(swap, x2, x3);
+            F::cswap(swap, z2, z3);
+            swap = bit;
+            fe25519 a, aa, b, bb, e, c, d, da, cb, t;
+            F::add(a, x2, z2);
+            F::sqr(aa, a);
+            F::sub(b, x2, z2);
+            F::sqr(bb, b);
+            F::sub(e, aa, bb);
+            F::add(c, x3, z3);
+            F::sub(d, x3, z3);
+            F::mul(da, d, a);
+            F::mul(cb, c, b);
+            F::add(t, da, cb);
+            F::sqr(x3, t);
+            F::sub(t, da, cb);
+            F::sqr(t, t);
+            F::mul(z3, x1, t);
+            F::mul(x2, aa, bb);
+            F::mul_small(t, e, 121666u);
+            F::add(t, bb, t);
+            F::mul(z2, e, t);
+        }
+    }
+    F::cswap(swap, x2, x3);
+    F::cswap(swap, z2, z3);
+    plane_st<8>(planes + 0 * 8 * n, n, idx, x2.v);
+    plane_st<8>(planes + 2 * 8 * n, n, idx, z2.v);
+}
+
+// =======================================================================================
+// Batch inversion (Montgomery's trick) + affine finishing.
+//   thread t owns elements t, t+T, t+2T, ... ; prefix products go to the `pf` plane.
+//   Z == 0 is replaced by 1 and reported to the finisher (Weierstrass infinity,
+//   X25519 z2 = 0 -> output 0 as invert_or_zero does, curve25519.rs:191, :512).
+// Cost per element: 3 M + the finisher's (2 M for x,y), plus one inversion per thread.
+// =======================================================================================
+template <class FT, class FIN>
+ECB_DEV void batch_inv_body(size_t t, size_t T, size_t n, const u32* planes, u32* pf, FIN fin) {
+    typedef typename FT::el fe;
+    constexpr int N = FT::N;
+    if (t >= n) return;
+    const u32* zp = planes + 2 * (size_t)N * n;
+    fe acc, z, one;
+    FT::set_one(one);
+    FT::set_one(acc);
+    size_t last = t;
+    for (size_t idx = t; idx < n; idx += T) {
+        plane_ld<N>(z.v, zp, n, idx);
+        u32 zero = FT::is_zero(z);
+        FT::select(z, zero, one, z);
+        plane_st<N>(pf, n, idx, acc.v);
+        FT::mul(acc, acc, z);
+        last = idx;
+    }
+    fe inv;
+    FT::invert(inv, acc);
+    for (size_t idx = last;; idx -= T) {
+        plane_ld<N>(z.v, zp, n, idx);
+        u32 zero = FT::is_zero(z);
+        FT::select(z, zero, one, z);
+        fe p, zinv;
+        plane_ld<N>(p.v, pf, n, idx);
+        FT::mul(zinv, inv, p);
+        FT::mul(inv, inv, z);
+        fin(idx, zinv, zero);
+        if (idx == t) break;
+    }
+}
+
+// finishers ------------------------------------------------------------------------------
+struct FinEdXY {  // out: x_le || y_le, canonical (Point::to_affine + to_bytes_le)
+    const u32* planes; size_t n; u32* out;
+    ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
+        fe25519 X, Y, x, y;
+        plane_ld<8>(X.v, planes, n, idx);
+        plane_ld<8>(Y.v, planes + 8 * n, n, idx);
+        F::mul(x, X, zinv);
+        F::mul(y, Y, zinv);
+        F::freeze(x, x);
+        F::freeze(y, y);
+        st_words<8>(out + idx * 16, x.v);
+        st_words<8>(out + idx * 16 + 8, y.v);
+    }
+};
+struct FinEdCompressed {  // out: encode_point (protocol/ed25519.rs:27)
+    const u32* planes; size_t n; u32* out;
+    ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
+        fe25519 X, Y, x, y;
+        plane_ld<8>(X.v, planes, n, idx);
+        plane_ld<8>(Y.v, planes + 8 * n, n, idx);
+        F::mul(x, X, zinv);
+        F::mul(y, Y, zinv);
+        F::freeze(x, x);
+        F::freeze(y, y);
+        y.v[7] |= (x.v[0] & 1u) << 31;
+        st_words<8>(out + idx * 8, y.v);
+    }
+};
+struct FinEdNiels {  // out: comb-table entry (y+x, y-x, 2dxy), 24 words
+    const u32* planes; size_t n; u32* out;
+    ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
+        fe25519 X, Y, x, y;
+        plane_ld<8>(X.v, planes, n, idx);
+        plane_ld<8>(Y.v, planes + 8 * n, n, idx);
+        F::mul(x, X, zinv);
+        F::mul(y, Y, zinv);
+        ge_niels e;
+        ge_niels_from_affine(e, x, y);
+        F::freeze(e.yp, e.yp);
+        F::freeze(e.ym, e.ym);
+        F::freeze(e.t2d, e.t2d);
+        st_words<8>(out + idx * 24, e.yp.v);
+        st_words<8>(out + idx * 24 + 8, e.ym.v);
+        st_words<8>(out + idx * 24 + 16, e.t2d.v);
+    }
+};
+struct FinX25519 {  // out: u' = x2 / z2 little-endian canonical, 0 when z2 == 0
+    const u32* planes; size_t n; u32* out;
+    ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32 zero) const {
+        fe25519 X, x;
+        plane_ld<8>(X.v, planes, n, idx);
+        F::mul(x, X, zinv);
+        F::freeze(x, x);
+        u32 m = zero ? 0u : 0xffffffffu;
+        ECB_UNROLL
+        for (int i = 0; i < 8; i++) x.v[i] &= m;
+        st_words<8>(out + idx * 8, x.v);
+    }
+};
+
+// =======================================================================================
+// Weierstrass variable base: k*P with signed 4-bit Booth windows over a per-thread table of
+// 8 projective multiples and the complete RCB formulas (replaces &Point * &Scalar,
+// fiat/curve_macros.rs:321 -> projective.rs:871 scalar_mul_fixed_window_am3 / :842 _a0).
+//   scalars: n x SB bytes big-endian canonical (< group order)
+//   points : n x 2FB bytes big-endian affine (x, y), on the curve; inf_in (optional) marks
+//            identity inputs
+//   tbl    : this thread's scratch, 8 entries x 3N words
+// =======================================================================================
+template <class C>
+ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* points, const unsigned char* inf_in,
+                          u32* tbl, u32* planes, unsigned long long* status) {
+    typedef Wei<C> W;
+    typedef typename C::F FT;
+    typedef typename C::FN FNT;
+    typedef typename FT::el fe;
+    constexpr int N = FT::N;
+    constexpr int NS = C::SB / 4;
+    u32 k[NS + 1];
+    ld_words_be<NS>(k, scalars + idx * NS);
+    k[NS] = 0;
+    u32 ok = 1;
+    if (!FNT::is_canonical_words(k)) {
+        report_bad(status, idx, ST_NONCANONICAL_SCALAR);
+        ok = 0;
+    }
+    u32 xw[N], yw[N];
+    ld_words_be<N>(xw, points + idx * 2 * N);
+    ld_words_be<N>(yw, points + idx * 2 * N + N);
+    u32 is_inf = inf_in ? (inf_in[idx] ? 1u : 0u) : 0u;
+    typename W::pt P, acc;
+    FT::to_mont(P.X, xw);
+    FT::to_mont(P.Y, yw);
+    FT::set_one(P.Z);
+    if (ok && !is_inf && !(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(P.X, P.Y))) {
+        report_bad(status, idx, ST_BAD_POINT);
+        ok = 0;
+    }
+    if (!ok || is_inf) W::set_inf(P);
+    if (!ok) {
+        ECB_UNROLL
+        for (int i = 0; i < NS; i++) k[i] = 0;
+    }
+    // table[j-1] = j*P, j = 1..8
+    {
+        typename W::pt t;
+        st_words<N>(tbl, P.X.v); st_words<N>(tbl + N, P.Y.v); st_words<N>(tbl + 2 * N, P.Z.v);
+        W::dbl(t, P);
+        for (int j = 2; j <= 8; j++) {
+            u32* d = tbl + (j - 1) * 3 * N;
+            st_words<N>(d, t.X.v); st_words<N>(d + N, t.Y.v); st_words<N>(d + 2 * N, t.Z.v);
+            if (j < 8) W::add(t, t, P);
+        }
+    }
+    constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
+    W::set_inf(acc);
+    for (int i = NWIN - 1; i >= 0; i--) {
+        if (i != NWIN - 1) {
+            W::dbl(acc, acc);
+            W::dbl(acc, acc);
+            W::dbl(acc, acc);
+            W::dbl(acc, acc);
+        }
+        u32 neg;
+        u32 d = booth_digit(k, NS + 1, 4, i, neg);
+        typename W::pt s;
+        W::set_inf(s);
+        if (d != 0) {
+            const u32* src = tbl + (d - 1) * 3 * N;
+            ld_words<N>(s.X.v, src); ld_words<N>(s.Y.v, src + N); ld_words<N>(s.Z.v, src + 2 * N);
+        }
+        fe ny;
+        FT::neg(ny, s.Y);
+        FT::select(s.Y, neg, ny, s.Y);
+        W::add(acc, acc, s);
+    }
+    plane_st<N>(planes + 0 * (size_t)N * n, n, idx, acc.X.v);
+    plane_st<N>(planes + 1 * (size_t)N * n, n, idx, acc.Y.v);
+    plane_st<N>(planes + 2 * (size_t)N * n, n, idx, acc.Z.v);
+}
+
+template <class C>
+struct FinWeiXY {  // out: x_be || y_be (canonical, out of the Montgomery domain) + infinity flag
+    typedef typename C::F FT;
+    const u32* planes; size_t n; u32* out; unsigned char* inf_out;
+    ECB_DEV void operator()(size_t idx, const typename FT::el& zinv, u32 zero) const {
+        constexpr int N = FT::N;
+        typename FT::el X, Y, x, y;
+        plane_ld<N>(X.v, planes, n, idx);
+        plane_ld<N>(Y.v, planes + (size_t)N * n, n, idx);
+        FT::mul(x, X, zinv);
+        FT::mul(y, Y, zinv);
+        u32 xw[N], yw[N];
+        FT::from_mont(xw, x);
+        FT::from_mont(yw, y);
+        u32 m = zero ? 0u : 0xffffffffu;
+        ECB_UNROLL
+        for (int i = 0; i < N; i++) { xw[i] &= m; yw[i] &= m; }
+        st_words_be<N>(out + idx * 2 * N, xw);
+        st_words_be<N>(out + idx * 2 * N + N, yw);
+        if (inf_out) inf_out[idx] = (unsigned char)zero;
+    }
+};
+
+}  // namespace ecb

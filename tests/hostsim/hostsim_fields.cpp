@@ -1,0 +1,64 @@
+// Host simulation of the device field layer (tests only; never linked into libeccbatch.so).
+// Compiles the sm_100a headers with ECB_HOSTSIM (emulated carry flag) so the exact primitive
+// sequences can be checked on a machine without a GPU.
+#define ECB_HOSTSIM 1
+#include "../../eccoxide_b200/csrc/fe25519.cuh"
+#include "../../eccoxide_b200/csrc/mont.cuh"
+#include "../../eccoxide_b200/csrc/params_gen.cuh"
+#include <string.h>
+using namespace ecb;
+
+template <class P> static void mont_op(int op, const u32* a, const u32* b, u32* r) {
+    typedef Mont<P> F;
+    typename F::el x, y, z;
+    memcpy(x.v, a, 4 * P::N); memcpy(y.v, b, 4 * P::N);
+    switch (op) {
+        case 0: F::mul(z, x, y); break;
+        case 1: F::sqr(z, x); break;
+        case 2: F::add(z, x, y); break;
+        case 3: F::sub(z, x, y); break;
+        case 4: F::neg(z, x); break;
+        case 5: F::to_mont(z, a); break;
+        case 6: F::invert(z, x); break;
+        case 7: F::from_mont(z.v, x); break;
+    }
+    memcpy(r, z.v, 4 * P::N);
+}
+
+extern "C" {
+void hs_mul_full8(const u32* a, const u32* b, u32* t) { mul_full<8>(t, a, b); }
+void hs_sqr_full8(const u32* a, u32* t) { sqr_full<8>(t, a); }
+void hs_mul_full14(const u32* a, const u32* b, u32* t) { mul_full<14>(t, a, b); }
+void hs_sqr_full14(const u32* a, u32* t) { sqr_full<14>(t, a); }
+
+// op: 0 mul 1 sqr 2 add 3 sub 4 neg 5 freeze 6 invert 7 mul_small(b[0]) 8 pow_p58
+void hs_fe25519(int op, const u32* a, const u32* b, u32* r) {
+    fe25519 x, y, z;
+    memcpy(x.v, a, 32); memcpy(y.v, b, 32);
+    switch (op) {
+        case 0: F25519::mul(z, x, y); break;
+        case 1: F25519::sqr(z, x); break;
+        case 2: F25519::add(z, x, y); break;
+        case 3: F25519::sub(z, x, y); break;
+        case 4: F25519::neg(z, x); break;
+        case 5: F25519::freeze(z, x); break;
+        case 6: F25519::invert(z, x); break;
+        case 7: F25519::mul_small(z, x, b[0]); break;
+        case 8: F25519::pow_p58(z, x); break;
+    }
+    memcpy(r, z.v, 32);
+}
+u32 hs_fe25519_is_canonical(const u32* a) { return F25519::is_canonical_words(a); }
+
+// field: 0 P256_FP 1 P256_FN 2 P384_FP 3 P384_FN 4 BLS_FP 5 BLS_FR
+void hs_mont(int field, int op, const u32* a, const u32* b, u32* r) {
+    switch (field) {
+        case 0: mont_op<P256_FP>(op, a, b, r); break;
+        case 1: mont_op<P256_FN>(op, a, b, r); break;
+        case 2: mont_op<P384_FP>(op, a, b, r); break;
+        case 3: mont_op<P384_FN>(op, a, b, r); break;
+        case 4: mont_op<BLS_FP>(op, a, b, r); break;
+        case 5: mont_op<BLS_FR>(op, a, b, r); break;
+    }
+}
+}
