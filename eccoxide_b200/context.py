@@ -1,0 +1,198 @@
+"""Context: numpy-level access to the C ABI (host buffers in, host buffers out).
+
+All arrays are contiguous uint8 with one row per element in the reference's wire encodings
+(see include/eccbatch.h).  Every method is a single C-ABI call; nothing is computed in Python.
+"""
+import ctypes
+
+import numpy as np
+
+from . import _lib
+from ._lib import EccBatchError
+
+FIELD_BYTES = {_lib.CURVE_P256R1: 32, _lib.CURVE_P384R1: 48, _lib.CURVE_BLS12_381_G1: 48}
+SCALAR_BYTES = {_lib.CURVE_P256R1: 32, _lib.CURVE_P384R1: 48, _lib.CURVE_BLS12_381_G1: 32}
+CURVE_IDS = {"p256r1": _lib.CURVE_P256R1, "p384r1": _lib.CURVE_P384R1, "bls12_381_g1": _lib.CURVE_BLS12_381_G1}
+
+
+def _rows(a, width, name):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    if a.ndim == 1:
+        if a.size % width:
+            raise ValueError("%s: length %d is not a multiple of %d" % (name, a.size, width))
+        a = a.reshape(-1, width)
+    if a.ndim != 2 or a.shape[1] != width:
+        raise ValueError("%s: expected shape (n, %d), got %s" % (name, width, a.shape))
+    return a
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
+
+
+class Context:
+    """One libeccbatch context over `devices` (default: CUDA device 0)."""
+
+    def __init__(self, devices=None, ed25519_comb_w=None):
+        self._lib = _lib.load()
+        self._ctx = ctypes.c_void_p()
+        if devices is None:
+            rc = self._lib.ecb_init(None, 0, ctypes.byref(self._ctx))
+        else:
+            arr = (ctypes.c_int * len(devices))(*devices)
+            rc = self._lib.ecb_init(arr, len(devices), ctypes.byref(self._ctx))
+        if rc != _lib.ECB_OK:
+            self._ctx = None
+            raise EccBatchError(rc, "ecb_init failed (no CUDA device? there is no CPU fallback)")
+        if ed25519_comb_w is not None:
+            self.set_option("ed25519_comb_w", ed25519_comb_w)
+
+    def close(self):
+        if getattr(self, "_ctx", None):
+            self._lib.ecb_destroy(self._ctx)
+            self._ctx = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- plumbing ---------------------------------------------------------------------------
+    def _check(self, rc, bad=None):
+        if rc != _lib.ECB_OK:
+            msg = self._lib.ecb_last_error(self._ctx).decode()
+            raise EccBatchError(rc, msg, None if bad is None or bad.value == ctypes.c_size_t(-1).value else bad.value)
+
+    def set_option(self, key, value):
+        self._check(self._lib.ecb_set_option(self._ctx, key.encode(), int(value)))
+
+    @property
+    def handle(self):
+        return self._ctx
+
+    @property
+    def lib(self):
+        return self._lib
+
+    def launch_count(self):
+        return int(self._lib.ecb_launch_count(self._ctx))
+
+    def device_count(self):
+        return int(self._lib.ecb_device_count(self._ctx))
+
+    # -- edwards25519 -------------------------------------------------------------------------
+    def ed25519_mul_base(self, k_le, compressed=False):
+        k = _rows(k_le, 32, "k_le")
+        n = k.shape[0]
+        out = np.empty((n, 32 if compressed else 64), dtype=np.uint8)
+        bad = ctypes.c_size_t()
+        fn = self._lib.ecb_ed25519_mul_base_compressed if compressed else self._lib.ecb_ed25519_mul_base
+        self._check(fn(self._ctx, _p(k), n, _p(out), ctypes.byref(bad)), bad)
+        return out
+
+    def ed25519_mul(self, k_le, xy_le):
+        k = _rows(k_le, 32, "k_le")
+        p = _rows(xy_le, 64, "xy_le")
+        if k.shape[0] != p.shape[0]:
+            raise ValueError("scalar/point count mismatch")
+        n = k.shape[0]
+        out = np.empty((n, 64), dtype=np.uint8)
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_ed25519_mul(self._ctx, _p(k), _p(p), n, _p(out), ctypes.byref(bad)), bad)
+        return out
+
+    def ed25519_verify_prehashed(self, a_enc, r_enc, s_le, k_le):
+        a, r, s, k = (_rows(x, 32, nm) for x, nm in ((a_enc, "a_enc"), (r_enc, "r_enc"), (s_le, "s_le"), (k_le, "k_le")))
+        n = a.shape[0]
+        if not (r.shape[0] == s.shape[0] == k.shape[0] == n):
+            raise ValueError("count mismatch")
+        ok = np.empty(n, dtype=np.uint8)
+        self._check(self._lib.ecb_ed25519_verify_prehashed(self._ctx, _p(a), _p(r), _p(s), _p(k), n, _p(ok)))
+        return ok.astype(bool)
+
+    # -- X25519 / X448 ------------------------------------------------------------------------
+    def x25519(self, k, u):
+        k = _rows(k, 32, "k")
+        u = _rows(u, 32, "u")
+        if k.shape[0] != u.shape[0]:
+            raise ValueError("count mismatch")
+        n = k.shape[0]
+        out = np.empty((n, 32), dtype=np.uint8)
+        self._check(self._lib.ecb_x25519(self._ctx, _p(k), _p(u), n, _p(out)))
+        return out
+
+    def x448(self, k, u):
+        k = _rows(k, 56, "k")
+        u = _rows(u, 56, "u")
+        if k.shape[0] != u.shape[0]:
+            raise ValueError("count mismatch")
+        n = k.shape[0]
+        out = np.empty((n, 56), dtype=np.uint8)
+        self._check(self._lib.ecb_x448(self._ctx, _p(k), _p(u), n, _p(out)))
+        return out
+
+    # -- Weierstrass --------------------------------------------------------------------------
+    def wei_mul(self, curve, k_be, xy_be, inf_in=None):
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+        fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]
+        k = _rows(k_be, sb, "k_be")
+        p = _rows(xy_be, 2 * fb, "xy_be")
+        n = k.shape[0]
+        if p.shape[0] != n:
+            raise ValueError("count mismatch")
+        if inf_in is not None:
+            inf_in = np.ascontiguousarray(inf_in, dtype=np.uint8).reshape(n)
+        out = np.empty((n, 2 * fb), dtype=np.uint8)
+        inf = np.empty(n, dtype=np.uint8)
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_wei_mul(self._ctx, cid, _p(k), _p(p), _p(inf_in), n, _p(out), _p(inf), ctypes.byref(bad)), bad)
+        return out, inf.astype(bool)
+
+    def wei_mul_base(self, curve, k_be):
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+        fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]
+        k = _rows(k_be, sb, "k_be")
+        n = k.shape[0]
+        out = np.empty((n, 2 * fb), dtype=np.uint8)
+        inf = np.empty(n, dtype=np.uint8)
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_wei_mul_base(self._ctx, cid, _p(k), n, _p(out), _p(inf), ctypes.byref(bad)), bad)
+        return out, inf.astype(bool)
+
+    def ecdsa_verify_hashed(self, curve, q_xy_be, z_be, rs_be):
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+        fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]
+        q = _rows(q_xy_be, 2 * fb, "q_xy_be")
+        z = _rows(z_be, sb, "z_be")
+        rs = _rows(rs_be, 2 * sb, "rs_be")
+        n = q.shape[0]
+        if not (z.shape[0] == rs.shape[0] == n):
+            raise ValueError("count mismatch")
+        ok = np.empty(n, dtype=np.uint8)
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_ecdsa_verify_hashed(self._ctx, cid, _p(q), _p(z), _p(rs), n, _p(ok), ctypes.byref(bad)), bad)
+        return ok.astype(bool)
+
+    # -- measurement --------------------------------------------------------------------------
+    def imad_probe(self, variant, iters=4096, dev_index=0):
+        macs = ctypes.c_double()
+        ms = ctypes.c_double()
+        self._check(self._lib.ecb_imad_probe(self._ctx, dev_index, variant, iters, ctypes.byref(macs), ctypes.byref(ms)))
+        return macs.value, ms.value
+
+    def debug_ed25519_table(self, dev_index=0):
+        w = ctypes.c_int()
+        nwin = ctypes.c_int()
+        ntab = self._lib.ecb_debug_ed25519_table(self._ctx, dev_index, None, 0, ctypes.byref(w), ctypes.byref(nwin))
+        if ntab < 0:
+            self._check(int(ntab))
+        out = np.empty((ntab, 96), dtype=np.uint8)
+        self._lib.ecb_debug_ed25519_table(self._ctx, dev_index, _p(out), out.nbytes, ctypes.byref(w), ctypes.byref(nwin))
+        return out, w.value, nwin.value

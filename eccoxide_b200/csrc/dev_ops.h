@@ -1,0 +1,23 @@
+// dev_ops.h — device-level operations (enqueue on a stream, no synchronisation), one
+// translation unit per kernel family.  Called by the C ABI in eccbatch.cu.
+#pragma once
+#include "host_ctx.h"
+
+int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W);
+int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s);
+int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_out, cudaStream_t s);
+int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
+                       unsigned char* ok, cudaStream_t s);
+int dev_x25519(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_u, size_t n, u32* d_out, cudaStream_t s);
+int dev_x448(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_u, size_t n, u32* d_out, cudaStream_t s);
+int dev_wei_mul_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, const unsigned char* d_inf_in, size_t n,
+                     u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_mul_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, const unsigned char* d_inf_in, size_t n,
+                     u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_mul_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, const unsigned char* d_inf_in, size_t n,
+                    u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_ecdsa_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const u32* d_z, const u32* d_rs, size_t n, unsigned char* d_ok,
+                   cudaStream_t s);
+int dev_ecdsa_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const u32* d_z, const u32* d_rs, size_t n, unsigned char* d_ok,
+                   cudaStream_t s);
+int dev_imad_probe(ecb_ctx* ctx, DevCtx& d, int variant, int iters, double* macs_per_s, double* ms_out);

@@ -1,0 +1,356 @@
+// eccbatch.cu — the C ABI of include/eccbatch.h: context life cycle, sharding of a batch over the
+// devices of the context, chunking, host<->device copies.  All arithmetic lives in the kernel TUs
+// (tu_*.cu); there is no host arithmetic path in this library.
+#include "dev_ops.h"
+using namespace ecb;
+
+static int dev_wei_mul(ecb_ctx* ctx, DevCtx& d, int curve, const u32* d_k, const u32* d_p, const unsigned char* d_inf_in,
+                       size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s) {
+    switch (curve) {
+        case ECB_CURVE_P256R1: return dev_wei_mul_p256(ctx, d, d_k, d_p, d_inf_in, n, d_out, d_inf, s);
+        case ECB_CURVE_P384R1: return dev_wei_mul_p384(ctx, d, d_k, d_p, d_inf_in, n, d_out, d_inf, s);
+        case ECB_CURVE_BLS12_381_G1: return dev_wei_mul_bls(ctx, d, d_k, d_p, d_inf_in, n, d_out, d_inf, s);
+    }
+    return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
+}
+
+// =======================================================================================
+// C ABI
+// =======================================================================================
+extern "C" {
+
+int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out) {
+    if (!out) return ECB_ERR_INVALID_ARG;
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) return ECB_ERR_CUDA;  // no CPU fallback
+    ecb_ctx* ctx = new ecb_ctx();
+    int one = 0;
+    if (!device_ids || n_dev <= 0) {
+        device_ids = &one;
+        n_dev = 1;
+    }
+    for (int i = 0; i < n_dev; i++) {
+        if (device_ids[i] < 0 || device_ids[i] >= count) {
+            ecb_destroy(ctx);
+            return ECB_ERR_INVALID_ARG;
+        }
+        DevCtx* d = new DevCtx();
+        d->dev = device_ids[i];
+        ctx->devs.push_back(d);
+        if (cudaSetDevice(d->dev) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
+            cudaMalloc(&d->d_status, sizeof(unsigned long long)) != cudaSuccess ||
+            cudaMallocHost(&d->h_status, sizeof(unsigned long long)) != cudaSuccess ||
+            cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, d->dev) != cudaSuccess) {
+            ecb_destroy(ctx);
+            return ECB_ERR_CUDA;
+        }
+    }
+    const char* w = getenv("ECB_ED25519_COMB_W");
+    if (w) {
+        long v = atol(w);
+        if (v >= 4 && v <= 16) ctx->opt_ed_w = v;
+    }
+    *out = ctx;
+    return ECB_OK;
+}
+
+void ecb_destroy(ecb_ctx* ctx) {
+    if (!ctx) return;
+    for (DevCtx* d : ctx->devs) {
+        cudaSetDevice(d->dev);
+        if (d->stream) cudaStreamSynchronize(d->stream);
+        DevBuf* bufs[] = {&d->planes, &d->pf, &d->scratch, &d->aux, &d->in[0], &d->in[1], &d->in[2], &d->in[3], &d->out[0], &d->out[1]};
+        for (DevBuf* b : bufs)
+            if (b->p) cudaFree(b->p);
+        if (d->ed_table) cudaFree(d->ed_table);
+        if (d->d_status) cudaFree(d->d_status);
+        if (d->h_status) cudaFreeHost(d->h_status);
+        if (d->stream) cudaStreamDestroy(d->stream);
+        delete d;
+    }
+    delete ctx;
+}
+
+const char* ecb_last_error(ecb_ctx* ctx) { return ctx ? ctx->err.c_str() : "no context (no CUDA device?)"; }
+int ecb_device_count(ecb_ctx* ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+unsigned long long ecb_launch_count(ecb_ctx* ctx) { return ctx ? ctx->launches.load() : 0; }
+
+int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
+    if (!ctx || !key) return ECB_ERR_INVALID_ARG;
+    if (!strcmp(key, "ed25519_comb_w")) {
+        if (value < 4 || value > 16) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_comb_w must be in 4..16");
+        ctx->opt_ed_w = value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "chunk")) {
+        if (value < 1) return set_err(ctx, ECB_ERR_INVALID_ARG, "chunk must be >= 1");
+        ctx->opt_chunk = (size_t)value;
+        return ECB_OK;
+    }
+    return set_err(ctx, ECB_ERR_INVALID_ARG, std::string("unknown option ") + key);
+}
+
+void* ecb_alloc_pinned(size_t bytes) {
+    void* p = nullptr;
+    if (cudaMallocHost(&p, bytes ? bytes : 1) != cudaSuccess) return nullptr;
+    return p;
+}
+void ecb_free_pinned(void* p) {
+    if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"
+
+// ---- host-buffer plumbing: shard over devices, chunk, copy, run, copy back ---------------------
+struct HostArg {
+    const uint8_t* src;  // input (nullptr = absent)
+    size_t elem;         // bytes per element
+};
+struct HostOut {
+    uint8_t* dst;
+    size_t elem;
+};
+
+// op(d, stream, din[], dout[], n) enqueues the kernels for one chunk
+template <class OP>
+static int run_sharded(ecb_ctx* ctx, size_t n, const std::vector<HostArg>& ins, const std::vector<HostOut>& outs,
+                       bool has_status, size_t* bad_index, OP op) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (bad_index) *bad_index = (size_t)-1;
+    if (n == 0) return ECB_OK;
+    int nd = (int)ctx->devs.size();
+    std::vector<int> rc(nd, ECB_OK);
+    std::vector<unsigned long long> bad(nd, ~0ull);
+    auto worker = [&](int di) {
+        DevCtx& d = *ctx->devs[di];
+        size_t lo = n * (size_t)di / nd, hi = n * (size_t)(di + 1) / nd;
+        if (lo == hi) return;
+        std::lock_guard<std::mutex> g(d.mu);
+        auto body = [&]() -> int {
+            CU(cudaSetDevice(d.dev));
+            for (size_t c0 = lo; c0 < hi; c0 += ctx->opt_chunk) {
+                size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
+                const void* din[4] = {nullptr, nullptr, nullptr, nullptr};
+                void* dout[2] = {nullptr, nullptr};
+                for (size_t i = 0; i < ins.size(); i++) {
+                    if (!ins[i].src) continue;
+                    TRY(ensure(ctx, d.in[i], cn * ins[i].elem));
+                    CU(cudaMemcpyAsync(d.in[i].p, ins[i].src + c0 * ins[i].elem, cn * ins[i].elem, cudaMemcpyHostToDevice, d.stream));
+                    din[i] = d.in[i].p;
+                }
+                for (size_t i = 0; i < outs.size(); i++) {
+                    if (!outs[i].dst) continue;
+                    TRY(ensure(ctx, d.out[i], cn * outs[i].elem));
+                    dout[i] = d.out[i].p;
+                }
+                TRY(op(d, d.stream, din, dout, cn));
+                for (size_t i = 0; i < outs.size(); i++) {
+                    if (!outs[i].dst) continue;
+                    CU(cudaMemcpyAsync(outs[i].dst + c0 * outs[i].elem, d.out[i].p, cn * outs[i].elem, cudaMemcpyDeviceToHost, d.stream));
+                }
+                if (has_status) CU(cudaMemcpyAsync(d.h_status, d.d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
+                CU(cudaStreamSynchronize(d.stream));
+                if (has_status && *d.h_status != ~0ull) {
+                    unsigned long long v = *d.h_status;
+                    bad[di] = (((v >> 8) + c0) << 8) | (v & 0xff);
+                    return ECB_OK;
+                }
+            }
+            return ECB_OK;
+        };
+        rc[di] = body();
+    };
+    if (nd == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nd; i++) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < nd; i++)
+        if (rc[i] != ECB_OK) return rc[i];
+    unsigned long long first = ~0ull;
+    for (int i = 0; i < nd; i++)
+        if (bad[i] < first) first = bad[i];
+    if (first != ~0ull) {
+        if (bad_index) *bad_index = (size_t)(first >> 8);
+        int code = (first & 0xff) == ecb::ST_NONCANONICAL_SCALAR ? ECB_ERR_NONCANONICAL_SCALAR : ECB_ERR_POINT_NOT_ON_CURVE;
+        return set_err(ctx, code, code == ECB_ERR_NONCANONICAL_SCALAR ? "non-canonical scalar" : "point not on curve");
+    }
+    return ECB_OK;
+}
+
+static int curve_sizes(int curve, size_t& fb, size_t& sb) {
+    switch (curve) {
+        case ECB_CURVE_P256R1: fb = 32; sb = 32; return ECB_OK;
+        case ECB_CURVE_P384R1: fb = 48; sb = 48; return ECB_OK;
+        case ECB_CURVE_BLS12_381_G1: fb = 48; sb = 32; return ECB_OK;
+    }
+    return ECB_ERR_INVALID_ARG;
+}
+
+extern "C" {
+
+int ecb_ed25519_mul_base(ecb_ctx* ctx, const uint8_t* k_le, size_t n, uint8_t* xy_le, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k_le || !xy_le)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k_le, 32}}, {{xy_le, 64}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** out, size_t cn) {
+                           return dev_ed25519_mul_base(ctx, d, (const u32*)in[0], cn, (u32*)out[0], false, s);
+                       });
+}
+int ecb_ed25519_mul_base_compressed(ecb_ctx* ctx, const uint8_t* k_le, size_t n, uint8_t* enc, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k_le || !enc)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k_le, 32}}, {{enc, 32}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** out, size_t cn) {
+                           return dev_ed25519_mul_base(ctx, d, (const u32*)in[0], cn, (u32*)out[0], true, s);
+                       });
+}
+int ecb_ed25519_mul(ecb_ctx* ctx, const uint8_t* k_le, const uint8_t* xy_in, size_t n, uint8_t* xy_out, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k_le || !xy_in || !xy_out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k_le, 32}, {xy_in, 64}}, {{xy_out, 64}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** out, size_t cn) {
+                           return dev_ed25519_mul(ctx, d, (const u32*)in[0], (const u32*)in[1], cn, (u32*)out[0], s);
+                       });
+}
+int ecb_ed25519_verify_prehashed(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* r_enc, const uint8_t* s_le,
+                                 const uint8_t* k_le, size_t n, uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!a_enc || !r_enc || !s_le || !k_le || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{a_enc, 32}, {r_enc, 32}, {s_le, 32}, {k_le, 32}}, {{ok, 1}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** out, size_t cn) {
+                           return dev_ed25519_verify(ctx, d, (const u32*)in[0], (const u32*)in[1], (const u32*)in[2],
+                                                     (const u32*)in[3], cn, (unsigned char*)out[0], s);
+                       });
+}
+int ecb_x25519(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8_t* out) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k || !u || !out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k, 32}, {u, 32}}, {{out, 32}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_x25519(ctx, d, (const u32*)in[0], (const u32*)in[1], cn, (u32*)o[0], s);
+                       });
+}
+int ecb_x448(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8_t* out) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k || !u || !out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k, 56}, {u, 56}}, {{out, 56}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_x448(ctx, d, (const u32*)in[0], (const u32*)in[1], cn, (u32*)o[0], s);
+                       });
+}
+int ecb_wei_mul(ecb_ctx* ctx, int curve, const uint8_t* k_be, const uint8_t* xy_be, const uint8_t* inf_in, size_t n,
+                uint8_t* out_xy, uint8_t* out_inf, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb)) return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
+    if (n && (!k_be || !xy_be || !out_xy)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k_be, sb}, {xy_be, 2 * fb}, {inf_in, 1}}, {{out_xy, 2 * fb}, {out_inf, 1}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_wei_mul(ctx, d, curve, (const u32*)in[0], (const u32*)in[1], (const unsigned char*)in[2],
+                                              cn, (u32*)o[0], (unsigned char*)o[1], s);
+                       });
+}
+int ecb_wei_mul_base(ecb_ctx* ctx, int curve, const uint8_t* k_be, size_t n, uint8_t* out_xy, uint8_t* out_inf,
+                     size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb)) return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
+    if (n && (!k_be || !out_xy)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    // points == nullptr selects the generator inside the kernel
+    return run_sharded(ctx, n, {{k_be, sb}}, {{out_xy, 2 * fb}, {out_inf, 1}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_wei_mul(ctx, d, curve, (const u32*)in[0], nullptr, nullptr, cn, (u32*)o[0],
+                                              (unsigned char*)o[1], s);
+                       });
+}
+int ecb_ecdsa_verify_hashed(ecb_ctx* ctx, int curve, const uint8_t* q_xy, const uint8_t* z_be, const uint8_t* rs_be,
+                            size_t n, uint8_t* ok, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb)) return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
+    if (curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+    if (n && (!q_xy || !z_be || !rs_be || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{q_xy, 2 * fb}, {z_be, sb}, {rs_be, 2 * sb}}, {{ok, 1}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           if (curve == ECB_CURVE_P256R1)
+                               return dev_ecdsa_p256(ctx, d, (const u32*)in[0], (const u32*)in[1], (const u32*)in[2], cn,
+                                                             (unsigned char*)o[0], s);
+                           return dev_ecdsa_p384(ctx, d, (const u32*)in[0], (const u32*)in[1], (const u32*)in[2], cn,
+                                                         (unsigned char*)o[0], s);
+                       });
+}
+
+// ---- device-resident variants ---------------------------------------------------------------
+static DevCtx* get_dev(ecb_ctx* ctx, int i) { return (ctx && i >= 0 && i < (int)ctx->devs.size()) ? ctx->devs[i] : nullptr; }
+
+int ecb_ed25519_mul_base_dev(ecb_ctx* ctx, int di, const void* d_k, size_t n, void* d_xy, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_ed25519_mul_base(ctx, *d, (const u32*)d_k, n, (u32*)d_xy, false, (cudaStream_t)stream);
+}
+int ecb_ed25519_mul_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_xy_in, size_t n, void* d_xy_out, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_ed25519_mul(ctx, *d, (const u32*)d_k, (const u32*)d_xy_in, n, (u32*)d_xy_out, (cudaStream_t)stream);
+}
+int ecb_x25519_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_x25519(ctx, *d, (const u32*)d_k, (const u32*)d_u, n, (u32*)d_out, (cudaStream_t)stream);
+}
+int ecb_wei_mul_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, const void* d_xy, size_t n, void* d_out, void* d_inf,
+                    void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_wei_mul(ctx, *d, curve, (const u32*)d_k, (const u32*)d_xy, nullptr, n, (u32*)d_out, (unsigned char*)d_inf,
+                       (cudaStream_t)stream);
+}
+int ecb_dev_status(ecb_ctx* ctx, int di, size_t* bad_index) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    CU(cudaMemcpy(d->h_status, d->d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long v = *d->h_status;
+    if (bad_index) *bad_index = (size_t)-1;
+    if (v == ~0ull) return ECB_OK;
+    if (bad_index) *bad_index = (size_t)(v >> 8);
+    return (v & 0xff) == ecb::ST_NONCANONICAL_SCALAR ? ECB_ERR_NONCANONICAL_SCALAR : ECB_ERR_POINT_NOT_ON_CURVE;
+}
+
+int ecb_imad_probe(ecb_ctx* ctx, int di, int variant, int iters, double* macs_per_s, double* ms_out) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_imad_probe(ctx, *d, variant, iters, macs_per_s, ms_out);
+}
+
+long ecb_debug_ed25519_table(ecb_ctx* ctx, int di, uint8_t* out, size_t cap, int* w, int* nwin) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    std::lock_guard<std::mutex> g(d->mu);
+    if (cudaSetDevice(d->dev) != cudaSuccess) return ECB_ERR_CUDA;
+    if (!d->ed_table || d->ed_w != (int)ctx->opt_ed_w) {
+        int r = dev_ed25519_build_table(ctx, *d, (int)ctx->opt_ed_w);
+        if (r != ECB_OK) return r;
+    }
+    size_t ntab = (size_t)d->ed_nwin << (d->ed_w - 1);
+    if (w) *w = d->ed_w;
+    if (nwin) *nwin = d->ed_nwin;
+    size_t bytes = ntab * 96;
+    if (out) {
+        if (bytes > cap) bytes = cap - cap % 96;
+        if (cudaMemcpy(out, d->ed_table, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return ECB_ERR_CUDA;
+    }
+    return (long)ntab;
+}
+
+}  // extern "C"

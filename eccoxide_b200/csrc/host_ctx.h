@@ -1,0 +1,108 @@
+// host_ctx.h — per-device context, error plumbing and launch helpers shared by the translation
+// units of libeccbatch (one TU per kernel family so they compile in parallel).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/eccbatch.h"
+#include "limb.cuh"
+
+#define ECB_TPB 128
+using ecb::u32;
+
+// =======================================================================================
+// context
+// =======================================================================================
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+};
+
+struct DevCtx {
+    int dev = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;
+    DevBuf planes, pf, scratch, aux, in[4], out[2];
+    unsigned long long* d_status = nullptr;
+    unsigned long long* h_status = nullptr;  // pinned
+    u32* ed_table = nullptr;
+    int ed_w = 0, ed_nwin = 0;
+    std::mutex mu;
+};
+
+struct ecb_ctx {
+    std::vector<DevCtx*> devs;
+    std::string err;
+    std::mutex err_mu;
+    long opt_ed_w = 8;
+    size_t opt_chunk = (size_t)1 << 20;
+    std::atomic<unsigned long long> launches{0};
+};
+
+static inline int set_err(ecb_ctx* ctx, int code, const std::string& msg) {
+    if (ctx) {
+        std::lock_guard<std::mutex> g(ctx->err_mu);
+        ctx->err = msg;
+    }
+    return code;
+}
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess) {                                                                     \
+            int code_ = (e_ == cudaErrorMemoryAllocation) ? ECB_ERR_OOM : ECB_ERR_CUDA;              \
+            return set_err(ctx, code_, std::string(#call) + ": " + cudaGetErrorString(e_));          \
+        }                                                                                            \
+    } while (0)
+
+static inline int ensure(ecb_ctx* ctx, DevBuf& b, size_t bytes) {
+    if (b.cap >= bytes) return ECB_OK;
+    if (b.p) CU(cudaFree(b.p));
+    b.p = nullptr;
+    b.cap = 0;
+    size_t want = bytes + bytes / 8;
+    CU(cudaMalloc(&b.p, want));
+    b.cap = want;
+    return ECB_OK;
+}
+#define TRY(x)                 \
+    do {                       \
+        int r_ = (x);          \
+        if (r_ != ECB_OK) return r_; \
+    } while (0)
+
+static inline unsigned grid_for(size_t n) { return (unsigned)((n + ECB_TPB - 1) / ECB_TPB); }
+
+// number of threads for the batch inversion: ~16 elements per thread, but never fewer threads
+// than fill the machine once
+static inline size_t inv_threads(const DevCtx& d, size_t n) {
+    size_t T = (n + 15) / 16;
+    size_t fill = (size_t)d.sm_count * 256;
+    if (T < fill) T = fill;
+    if (T > n) T = n;
+    return T ? T : 1;
+}
+
+template <class K>
+static inline unsigned persistent_grid(const DevCtx& d, K kernel, size_t n) {
+    int per_sm = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, ECB_TPB, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
+    size_t g = (size_t)d.sm_count * per_sm;
+    size_t need = (n + ECB_TPB - 1) / ECB_TPB;
+    if (g > need) g = need;
+    return (unsigned)(g ? g : 1);
+}
+
+static inline int reset_status(ecb_ctx* ctx, DevCtx& d, cudaStream_t s) {
+    CU(cudaMemsetAsync(d.d_status, 0xff, sizeof(unsigned long long), s));
+    return ECB_OK;
+}
+

@@ -16,8 +16,6 @@
 
 namespace ecb {
 
-// status word written with atomicMin: (index << 8) | code ; ~0 = no error
-enum { ST_NONCANONICAL_SCALAR = 1, ST_BAD_POINT = 2 };
 
 #ifdef ECB_HOSTSIM
 ECB_DEV void report_bad(unsigned long long* st, size_t idx, u32 code) {
@@ -51,6 +49,24 @@ ECB_DEV void ld_words(u32* dst, const u32* src) {
         for (int i = 0; i < NW / 2; i++) {
             uint2 v = __ldg(s2 + i);
             dst[2 * i] = v.x; dst[2 * i + 1] = v.y;
+        }
+        return;
+    }
+#endif
+    ECB_UNROLL
+    for (int i = 0; i < NW; i++) dst[i] = src[i];
+}
+// coherent variant for memory written earlier by the same kernel (per-thread scratch tables):
+// ld.global.nc (__ldg) must not be used there.
+template <int NW>
+ECB_DEV void ld_words_rw(u32* dst, const u32* src) {
+#ifndef ECB_HOSTSIM
+    if (NW % 4 == 0) {
+        const uint4* s4 = reinterpret_cast<const uint4*>(src);
+        ECB_UNROLL
+        for (int i = 0; i < NW / 4; i++) {
+            uint4 v = s4[i];
+            dst[4 * i] = v.x; dst[4 * i + 1] = v.y; dst[4 * i + 2] = v.z; dst[4 * i + 3] = v.w;
         }
         return;
     }
@@ -222,9 +238,9 @@ ECB_DEV void ed25519_mul_body(size_t idx, size_t n, const u32* scalars, const u3
     {
         ge_cached c, c1;
         ge_to_cached(c1, P);
-        st_words<8>(tbl + 0, c1.yp.v); st_words<8>(tbl + 8, c1.ym.v); st_words<8>(tbl + 16, c1.Z.v); st_words<8>(tbl + 24, c1.t2d.v);
-        ge_double<true>(acc, P);
-        for (int j = 2; j <= 8; j++) {
+        acc = P;
+        ECB_NOUNROLL
+        for (int j = 1; j <= 8; j++) {  // the addition is complete, so 2P = P + P needs no doubling
             ge_to_cached(c, acc);
             u32* d = tbl + (j - 1) * 32;
             st_words<8>(d + 0, c.yp.v); st_words<8>(d + 8, c.ym.v); st_words<8>(d + 16, c.Z.v); st_words<8>(d + 24, c.t2d.v);
@@ -233,11 +249,11 @@ ECB_DEV void ed25519_mul_body(size_t idx, size_t n, const u32* scalars, const u3
     }
     // k < 2^253: 64 Booth windows of width 4 cover 256 bits
     ge_identity(acc);
+    ECB_NOUNROLL
     for (int i = 63; i >= 0; i--) {
         if (i != 63) {
-            ge_double<false>(acc, acc);
-            ge_double<false>(acc, acc);
-            ge_double<false>(acc, acc);
+            ECB_NOUNROLL
+            for (int r = 0; r < 3; r++) ge_double<false>(acc, acc);
             ge_double<true>(acc, acc);
         }
         u32 neg;
@@ -246,7 +262,7 @@ ECB_DEV void ed25519_mul_body(size_t idx, size_t n, const u32* scalars, const u3
         ge_cached_identity(c);
         if (d != 0) {
             const u32* s = tbl + (d - 1) * 32;
-            ld_words<8>(c.yp.v, s); ld_words<8>(c.ym.v, s + 8); ld_words<8>(c.Z.v, s + 16); ld_words<8>(c.t2d.v, s + 24);
+            ld_words_rw<8>(c.yp.v, s); ld_words_rw<8>(c.ym.v, s + 8); ld_words_rw<8>(c.Z.v, s + 16); ld_words_rw<8>(c.t2d.v, s + 24);
         }
         ge_cached_cneg(c, neg);
         ge_add_cached<true>(acc, acc, c);
@@ -440,18 +456,23 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
         report_bad(status, idx, ST_NONCANONICAL_SCALAR);
         ok = 0;
     }
-    u32 xw[N], yw[N];
-    ld_words_be<N>(xw, points + idx * 2 * N);
-    ld_words_be<N>(yw, points + idx * 2 * N + N);
     u32 is_inf = inf_in ? (inf_in[idx] ? 1u : 0u) : 0u;
     typename W::pt P, acc;
-    FT::to_mont(P.X, xw);
-    FT::to_mont(P.Y, yw);
-    FT::set_one(P.Z);
-    if (ok && !is_inf && !(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(P.X, P.Y))) {
-        report_bad(status, idx, ST_BAD_POINT);
-        ok = 0;
+    if (points) {
+        u32 xw[N], yw[N];
+        ld_words_be<N>(xw, points + idx * 2 * N);
+        ld_words_be<N>(yw, points + idx * 2 * N + N);
+        FT::to_mont(P.X, xw);
+        FT::to_mont(P.Y, yw);
+        if (ok && !is_inf && !(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(P.X, P.Y))) {
+            report_bad(status, idx, ST_BAD_POINT);
+            ok = 0;
+        }
+    } else {  // fixed base: the curve generator (Point::mul_base)
+        ECB_UNROLL
+        for (int i = 0; i < N; i++) { P.X.v[i] = C::gx(i); P.Y.v[i] = C::gy(i); }
     }
+    FT::set_one(P.Z);
     if (!ok || is_inf) W::set_inf(P);
     if (!ok) {
         ECB_UNROLL
@@ -459,10 +480,9 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
     }
     // table[j-1] = j*P, j = 1..8
     {
-        typename W::pt t;
-        st_words<N>(tbl, P.X.v); st_words<N>(tbl + N, P.Y.v); st_words<N>(tbl + 2 * N, P.Z.v);
-        W::dbl(t, P);
-        for (int j = 2; j <= 8; j++) {
+        typename W::pt t = P;
+        ECB_NOUNROLL
+        for (int j = 1; j <= 8; j++) {  // complete addition: 2P = P + P needs no doubling
             u32* d = tbl + (j - 1) * 3 * N;
             st_words<N>(d, t.X.v); st_words<N>(d + N, t.Y.v); st_words<N>(d + 2 * N, t.Z.v);
             if (j < 8) W::add(t, t, P);
@@ -470,12 +490,11 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
     }
     constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
     W::set_inf(acc);
+    ECB_NOUNROLL
     for (int i = NWIN - 1; i >= 0; i--) {
         if (i != NWIN - 1) {
-            W::dbl(acc, acc);
-            W::dbl(acc, acc);
-            W::dbl(acc, acc);
-            W::dbl(acc, acc);
+            ECB_NOUNROLL
+            for (int r = 0; r < 4; r++) W::dbl(acc, acc);
         }
         u32 neg;
         u32 d = booth_digit(k, NS + 1, 4, i, neg);
@@ -483,7 +502,7 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
         W::set_inf(s);
         if (d != 0) {
             const u32* src = tbl + (d - 1) * 3 * N;
-            ld_words<N>(s.X.v, src); ld_words<N>(s.Y.v, src + N); ld_words<N>(s.Z.v, src + 2 * N);
+            ld_words_rw<N>(s.X.v, src); ld_words_rw<N>(s.Y.v, src + N); ld_words_rw<N>(s.Z.v, src + 2 * N);
         }
         fe ny;
         FT::neg(ny, s.Y);

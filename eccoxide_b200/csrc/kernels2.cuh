@@ -1,0 +1,529 @@
+// kernels2.cuh — GF(2^448-2^224-1) + X448, batched ECDSA verification and batched Ed25519
+// verification (per-thread bodies; launchers in eccbatch.cu, host simulation in tests/hostsim/).
+#pragma once
+#include "kernels.cuh"
+
+namespace ecb {
+
+// =======================================================================================
+// GF(p448), p = 2^448 - 2^224 - 1, 14 saturated 32-bit limbs, any 448-bit value ("loose").
+// Replaces the 8x56-bit fiat backend src/curve/fiat/p448_solinas_64.rs as used by
+// src/curve/curve448.rs:45-122 (field) and :143-174 (pow_const Fermat inverse).
+// 2^448 = 2^224 + 1 (mod p): the fold is add-only.  mul = 196 IMAD.WIDE, sqr = 105.
+// =======================================================================================
+struct fe448 {
+    u32 v[14];
+};
+
+struct F448 {
+    typedef fe448 el;
+    static constexpr int N = 14;
+
+    ECB_DEV static void set_zero(el& r) {
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) r.v[i] = 0;
+    }
+    ECB_DEV static void set_one(el& r) {
+        set_zero(r);
+        r.v[0] = 1;
+    }
+    ECB_DEV static void copy(el& r, const el& a) {
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) r.v[i] = a.v[i];
+    }
+    // r (14 limbs) += c * (2^224 + 1), twice (the second time with the carry of the first)
+    ECB_DEV static void fold_top(u32* r, u32 c) {
+        ECB_UNROLL
+        for (int rep = 0; rep < 2; rep++) {
+            r[0] = add_cc(r[0], c);
+            ECB_UNROLL
+            for (int i = 1; i < 7; i++) r[i] = addc_cc(r[i], 0);
+            r[7] = addc_cc(r[7], c);
+            ECB_UNROLL
+            for (int i = 8; i < 14; i++) r[i] = addc_cc(r[i], 0);
+            c = addc(0, 0);
+        }
+    }
+    // reduce a 28-limb product
+    ECB_DEV static void reduce(el& r, const u32* t) {
+        const u32* lo = t;
+        const u32* hi = t + 14;
+        const u32* h0 = t + 14;
+        const u32* h1 = t + 21;
+        u32 A[14], S[7];
+        u32 c = add_n<14>(A, lo, hi);  // lo + hi
+        // A += h1 (limbs 0..6), propagate
+        A[0] = add_cc(A[0], h1[0]);
+        ECB_UNROLL
+        for (int i = 1; i < 7; i++) A[i] = addc_cc(A[i], h1[i]);
+        ECB_UNROLL
+        for (int i = 7; i < 14; i++) A[i] = addc_cc(A[i], 0);
+        c += addc(0, 0);
+        // S = h0 + h1 ; A += S << 224
+        c += add_n<7>(S, h0, h1);
+        A[7] = add_cc(A[7], S[0]);
+        ECB_UNROLL
+        for (int i = 1; i < 7; i++) A[7 + i] = addc_cc(A[7 + i], S[i]);
+        c += addc(0, 0);
+        fold_top(A, c);
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) r.v[i] = A[i];
+    }
+    ECB_DEV static void mul(el& r, const el& a, const el& b) {
+        u32 t[28];
+        mul_full<14>(t, a.v, b.v);
+        reduce(r, t);
+    }
+    ECB_DEV static void sqr(el& r, const el& a) {
+        u32 t[28];
+        sqr_full<14>(t, a.v);
+        reduce(r, t);
+    }
+    ECB_DEV static void mul_small(el& r, const el& a, u32 k) {  // k < 2^26
+        u32 R[16];
+        ECB_UNROLL
+        for (int i = 0; i < 16; i++) R[i] = 0;
+        mac_chain<7, true>(R, a.v, k);
+        mac_chain<7, false>(R + 1, a.v + 1, k);
+        fold_top(R, R[14]);
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) r.v[i] = R[i];
+    }
+    ECB_DEV static void add(el& r, const el& a, const el& b) {
+        u32 t[14];
+        u32 c = add_n<14>(t, a.v, b.v);
+        fold_top(t, c);
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) r.v[i] = t[i];
+    }
+    ECB_DEV static void sub(el& r, const el& a, const el& b) {
+        u32 t[14];
+        u32 c = sub_n<14>(t, a.v, b.v);
+        ECB_UNROLL
+        for (int rep = 0; rep < 2; rep++) {  // -2^448 = -(2^224 + 1)
+            t[0] = sub_cc(t[0], c);
+            ECB_UNROLL
+            for (int i = 1; i < 7; i++) t[i] = subc_cc(t[i], 0);
+            t[7] = subc_cc(t[7], c);
+            ECB_UNROLL
+            for (int i = 8; i < 14; i++) t[i] = subc_cc(t[i], 0);
+            c = subc(0, 0) & 1;
+        }
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) r.v[i] = t[i];
+    }
+    // canonical representative: subtract p iff a >= p  <=>  a + 2^224 + 1 carries out of 2^448
+    ECB_DEV static void freeze(el& r, const el& a) {
+        u32 s[14];
+        s[0] = add_cc(a.v[0], 1u);
+        ECB_UNROLL
+        for (int i = 1; i < 7; i++) s[i] = addc_cc(a.v[i], 0);
+        s[7] = addc_cc(a.v[7], 1u);
+        ECB_UNROLL
+        for (int i = 8; i < 14; i++) s[i] = addc_cc(a.v[i], 0);
+        u32 ge = addc(0, 0);
+        u32 m = 0u - ge;
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) r.v[i] = (s[i] & m) | (a.v[i] & ~m);
+    }
+    ECB_DEV static u32 is_zero(const el& a) {
+        el f;
+        freeze(f, a);
+        u32 o = 0;
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) o |= f.v[i];
+        return o == 0 ? 1u : 0u;
+    }
+    ECB_DEV static void select(el& r, u32 c, const el& a, const el& b) {
+        u32 m = 0u - c;
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) r.v[i] = (a.v[i] & m) | (b.v[i] & ~m);
+    }
+    ECB_DEV static void cswap(u32 c, el& a, el& b) {
+        u32 m = 0u - c;
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) {
+            u32 x = (a.v[i] ^ b.v[i]) & m;
+            a.v[i] ^= x;
+            b.v[i] ^= x;
+        }
+    }
+    ECB_DEV static void sqr_n(el& r, const el& a, int n) {
+        sqr(r, a);
+        for (int i = 1; i < n; i++) sqr(r, r);
+    }
+    // a^(p-2) = a^(2^448 - 2^224 - 3); 0 -> 0
+    ECB_DEV static void invert(el& r, const el& a) {
+        el x2, x3, x6, x12, x24, x27, x54, x108, x111, x222, x223, t;
+        sqr(t, a);           mul(x2, t, a);
+        sqr(t, x2);          mul(x3, t, a);
+        sqr_n(t, x3, 3);     mul(x6, t, x3);
+        sqr_n(t, x6, 6);     mul(x12, t, x6);
+        sqr_n(t, x12, 12);   mul(x24, t, x12);
+        sqr_n(t, x24, 3);    mul(x27, t, x3);
+        sqr_n(t, x27, 27);   mul(x54, t, x27);
+        sqr_n(t, x54, 54);   mul(x108, t, x54);
+        sqr_n(t, x108, 3);   mul(x111, t, x3);
+        sqr_n(t, x111, 111); mul(x222, t, x111);
+        sqr(t, x222);        mul(x223, t, a);
+        sqr_n(t, x223, 223); mul(t, t, x222);
+        sqr_n(t, t, 2);      mul(r, t, a);
+    }
+};
+
+// X448: the reference's ladder (src/curve/curve448.rs:263-302) behind protocol::x448::x448
+// (src/protocol/x448.rs:34-45): clamp k[0] &= 252, k[55] |= 128; u read as-is (implicitly
+// reduced); 448 steps MSB first; result x2 * z2^(p-2) (0 for z2 = 0).
+ECB_DEV void x448_body(size_t idx, size_t n, const u32* scalars, const u32* us, u32* planes) {
+    u32 k[14];
+    fe448 x1, x2, z2, x3, z3;
+    ld_words<14>(k, scalars + idx * 14);
+    ld_words<14>(x1.v, us + idx * 14);
+    k[0] &= 0xfffffffcu;
+    k[13] |= 0x80000000u;
+    F448::set_one(x2);
+    F448::set_zero(z2);
+    F448::copy(x3, x1);
+    F448::set_one(z3);
+    u32 swap = 0;
+    for (int wi = 13; wi >= 0; wi--) {
+        u32 word = 0;
+        ECB_UNROLL
+        for (int t = 0; t < 14; t++)
+            if (t == wi) word = k[t];
+        for (int bi = 31; bi >= 0; bi--) {
+            u32 bit = (word >> bi) & 1u;
+            swap ^= bit;
+            F448::cswap(swap, x2, x3);
+            F448::cswap(swap, z2, z3);
+            swap = bit;
+            fe448 a, aa, b, bb, e, c, d, da, cb, t;
+            F448::add(a, x2, z2);
+            F448::sqr(aa, a);
+            F448::sub(b, x2, z2);
+            F448::sqr(bb, b);
+            F448::sub(e, aa, bb);
+            F448::add(c, x3, z3);
+            F448::sub(d, x3, z3);
+            F448::mul(da, d, a);
+            F448::mul(cb, c, b);
+            F448::add(t, da, cb);
+            F448::sqr(x3, t);
+            F448::sub(t, da, cb);
+            F448::sqr(t, t);
+            F448::mul(z3, x1, t);
+            F448::mul(x2, aa, bb);
+            F448::mul_small(t, e, 39082u);
+            F448::add(t, bb, t);
+            F448::mul(z2, e, t);
+        }
+    }
+    F448::cswap(swap, x2, x3);
+    F448::cswap(swap, z2, z3);
+    plane_st<14>(planes + 0 * 14 * n, n, idx, x2.v);
+    plane_st<14>(planes + 2 * 14 * n, n, idx, z2.v);
+}
+struct FinX448 {
+    const u32* planes; size_t n; u32* out;
+    ECB_DEV void operator()(size_t idx, const fe448& zinv, u32 zero) const {
+        fe448 X, x;
+        plane_ld<14>(X.v, planes, n, idx);
+        F448::mul(x, X, zinv);
+        F448::freeze(x, x);
+        u32 m = zero ? 0u : 0xffffffffu;
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) x.v[i] &= m;
+        st_words<14>(out + idx * 14, x.v);
+    }
+};
+
+// =======================================================================================
+// ECDSA verify_hashed, batched (src/protocol/ecdsa.rs:205-222).
+//   prep : decode r || s (Signature::from_bytes :399 — zero or >= n is invalid), s -> Montgomery
+//          form in GF(n) into the "Z" plane of `sp` for the scalar-field batch inversion
+//   inv  : batch_inv_body<FN> + FinScalarInv  -> s^-1 (Montgomery) in plane 0 of `sp`
+//   main : u1 = z s^-1, u2 = r s^-1, R = u1*G + u2*Q (Straus, signed 4-bit windows, shared
+//          doublings, complete formulas), projective result to the point planes
+//   fin  : x = X/Z by batch inversion in GF(p); accept iff Z != 0 and x mod n == r
+// =======================================================================================
+template <class C>
+ECB_DEV void ecdsa_prep_body(size_t idx, size_t n, const u32* z_be, const u32* rs_be, u32* sp, unsigned char* valid) {
+    typedef typename C::FN FN;
+    constexpr int NS = FN::N;
+    u32 r[NS], s[NS];
+    ld_words_be<NS>(r, rs_be + idx * 2 * NS);
+    ld_words_be<NS>(s, rs_be + idx * 2 * NS + NS);
+    u32 rz = 0, sz = 0;
+    ECB_UNROLL
+    for (int i = 0; i < NS; i++) { rz |= r[i]; sz |= s[i]; }
+    u32 ok = (rz != 0) & (sz != 0) & FN::is_canonical_words(r) & FN::is_canonical_words(s);
+    if (!ok) {
+        ECB_UNROLL
+        for (int i = 0; i < NS; i++) s[i] = 0;
+        s[0] = 1;
+    }
+    typename FN::el sm;
+    FN::to_mont(sm, s);
+    plane_st<NS>(sp + 2 * (size_t)NS * n, n, idx, sm.v);
+    valid[idx] = (unsigned char)ok;
+    (void)z_be;
+}
+template <class C>
+struct FinScalarInv {
+    typedef typename C::FN FN;
+    u32* sp; size_t n;
+    ECB_DEV void operator()(size_t idx, const typename FN::el& zinv, u32) const { plane_st<FN::N>(sp, n, idx, zinv.v); }
+};
+
+template <class C>
+ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z_be, const u32* rs_be, const u32* sp,
+                             unsigned char* valid, u32* tbl, u32* planes, unsigned long long* status) {
+    typedef Wei<C> W;
+    typedef typename C::F FT;
+    typedef typename C::FN FN;
+    typedef typename FT::el fe;
+    constexpr int N = FT::N;
+    constexpr int NS = FN::N;
+    // public key
+    u32 xw[N], yw[N];
+    ld_words_be<N>(xw, q_be + idx * 2 * N);
+    ld_words_be<N>(yw, q_be + idx * 2 * N + N);
+    typename W::pt Q, G, acc;
+    FT::to_mont(Q.X, xw);
+    FT::to_mont(Q.Y, yw);
+    FT::set_one(Q.Z);
+    if (!(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(Q.X, Q.Y))) {
+        report_bad(status, idx, ST_BAD_POINT);
+        W::set_inf(Q);
+    }
+    // u1 = z * s^-1, u2 = r * s^-1 as plain integers: mont_mul(plain, mont) = plain product
+    typename FN::el sinv, zz, rr, u1e, u2e;
+    plane_ld<NS>(sinv.v, sp, n, idx);
+    ld_words_be<NS>(zz.v, z_be + idx * NS);
+    ld_words_be<NS>(rr.v, rs_be + idx * 2 * NS);
+    {   // z mod n: 2^(32 NS) < 2n, one conditional subtraction (digest_to_scalar, ecdsa.rs:340)
+        u32 d[NS];
+        d[0] = sub_cc(zz.v[0], FN::P_::mod(0));
+        ECB_UNROLL
+        for (int i = 1; i < NS; i++) d[i] = subc_cc(zz.v[i], FN::P_::mod(i));
+        u32 borrow = subc(0, 0) & 1;
+        ECB_UNROLL
+        for (int i = 0; i < NS; i++) zz.v[i] = borrow ? zz.v[i] : d[i];
+    }
+    if (!valid[idx]) {
+        ECB_UNROLL
+        for (int i = 0; i < NS; i++) rr.v[i] = 0;
+    }
+    FN::mul(u1e, zz, sinv);
+    FN::mul(u2e, rr, sinv);
+    u32 u1[NS + 1], u2[NS + 1];
+    ECB_UNROLL
+    for (int i = 0; i < NS; i++) { u1[i] = u1e.v[i]; u2[i] = u2e.v[i]; }
+    u1[NS] = 0;
+    u2[NS] = 0;
+    // tables: tbl[0..8) = j*Q, tbl[8..16) = j*G
+    ECB_UNROLL
+    for (int i = 0; i < N; i++) { G.X.v[i] = C::gx(i); G.Y.v[i] = C::gy(i); }
+    FT::set_one(G.Z);
+    ECB_NOUNROLL
+    for (int which = 0; which < 2; which++) {
+        typename W::pt B, t;
+        if (which == 0) B = Q; else B = G;
+        u32* base = tbl + which * 8 * 3 * N;
+        t = B;
+        ECB_NOUNROLL
+        for (int j = 1; j <= 8; j++) {  // complete addition: 2B = B + B
+            u32* d = base + (j - 1) * 3 * N;
+            st_words<N>(d, t.X.v); st_words<N>(d + N, t.Y.v); st_words<N>(d + 2 * N, t.Z.v);
+            if (j < 8) W::add(t, t, B);
+        }
+    }
+    constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
+    W::set_inf(acc);
+    ECB_NOUNROLL
+    for (int i = NWIN - 1; i >= 0; i--) {
+        if (i != NWIN - 1) {
+            ECB_NOUNROLL
+            for (int r = 0; r < 4; r++) W::dbl(acc, acc);
+        }
+        ECB_NOUNROLL
+        for (int which = 0; which < 2; which++) {
+            u32 neg;
+            u32 d = booth_digit(which == 0 ? u2 : u1, NS + 1, 4, i, neg);
+            if (d != 0) {  // skipping a zero digit: verification is variable time like mul_vartime
+                typename W::pt s;
+                const u32* src = tbl + (which * 8 + (d - 1)) * 3 * N;
+                ld_words_rw<N>(s.X.v, src); ld_words_rw<N>(s.Y.v, src + N); ld_words_rw<N>(s.Z.v, src + 2 * N);
+                fe ny;
+                FT::neg(ny, s.Y);
+                FT::select(s.Y, neg, ny, s.Y);
+                W::add(acc, acc, s);
+            }
+        }
+    }
+    plane_st<N>(planes + 0 * (size_t)N * n, n, idx, acc.X.v);
+    plane_st<N>(planes + 1 * (size_t)N * n, n, idx, acc.Y.v);
+    plane_st<N>(planes + 2 * (size_t)N * n, n, idx, acc.Z.v);
+}
+
+template <class C>
+struct FinEcdsa {  // x_mod_n(R) == r (ecdsa.rs:382, :218-221); identity => reject
+    typedef typename C::F FT;
+    typedef typename C::FN FN;
+    const u32* planes; size_t n; const u32* rs_be; unsigned char* ok;
+    ECB_DEV void operator()(size_t idx, const typename FT::el& zinv, u32 zero) const {
+        constexpr int N = FT::N;
+        constexpr int NS = FN::N;
+        typename FT::el X, x;
+        plane_ld<N>(X.v, planes, n, idx);
+        FT::mul(x, X, zinv);
+        u32 xw[N];
+        FT::from_mont(xw, x);
+        // field_to_scalar (ecdsa.rs:363): FB <= SB here, p < 2n: one conditional subtraction
+        u32 d[NS];
+        d[0] = sub_cc(xw[0], FN::P_::mod(0));
+        ECB_UNROLL
+        for (int i = 1; i < NS; i++) d[i] = subc_cc(xw[i], FN::P_::mod(i));
+        u32 borrow = subc(0, 0) & 1;
+        u32 r[NS];
+        ld_words_be<NS>(r, rs_be + idx * 2 * NS);
+        u32 diff = 0;
+        ECB_UNROLL
+        for (int i = 0; i < NS; i++) diff |= (borrow ? xw[i] : d[i]) ^ r[i];
+        ok[idx] = (unsigned char)((ok[idx] != 0) & (zero == 0) & (diff == 0));
+    }
+};
+
+// =======================================================================================
+// Ed25519 verification, batched (src/protocol/ed25519.rs:119-147) with k = H(R||A||M) mod l
+// supplied by the caller.  One kernel, no inversion: the final comparison is projective
+// exactly like Point::eq (curve25519.rs:1200).
+// =======================================================================================
+// decode_point (protocol/ed25519.rs:38-59) + Point::decompress (curve25519.rs:772) +
+// sqrt_div (curve25519.rs:258).  Returns 1 and (x, y) on success.
+ECB_DEV u32 ed25519_decode(fe25519& x, fe25519& y, const u32* enc) {
+    u32 w[8];
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) w[i] = enc[i];
+    u32 sign = w[7] >> 31;
+    w[7] &= 0x7fffffffu;
+    u32 ok = F::is_canonical_words(w);
+    F::from_words(y, w);
+    fe25519 one, u, v, v3, v7, r, chk, t, nu, d, sm1;
+    F::set_one(one);
+    // (x = 0, sign = 1) <=> y = +-1 with the sign bit set
+    {
+        fe25519 ny;
+        F::neg(ny, one);
+        u32 ypm1 = F::eq(y, one) | F::eq(y, ny);
+        ok &= (sign & ypm1) ^ 1u;
+    }
+    F::from_words(d, ED25519_D);
+    F::from_words(sm1, ED25519_SQRTM1);
+    F::sqr(t, y);
+    F::sub(u, t, one);
+    F::mul(v, t, d);
+    F::add(v, v, one);
+    F::sqr(v3, v);
+    F::mul(v3, v3, v);
+    F::sqr(v7, v3);
+    F::mul(v7, v7, v);
+    F::mul(t, u, v7);
+    F::pow_p58(t, t);
+    F::mul(r, u, v3);
+    F::mul(r, r, t);
+    F::sqr(chk, r);
+    F::mul(chk, chk, v);
+    F::neg(nu, u);
+    u32 correct = F::eq(chk, u);
+    u32 flipped = F::eq(chk, nu);
+    F::mul(t, r, sm1);
+    F::select(r, flipped, t, r);
+    ok &= (correct | flipped);
+    F::freeze(r, r);
+    u32 flip = (r.v[0] & 1u) ^ sign;
+    F::neg(t, r);
+    F::select(x, flip, t, r);
+    return ok;
+}
+
+ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u32* r_enc, const u32* s_le, const u32* k_le,
+                                 const u32* table, int W, int nwin, u32* tbl, unsigned char* out_ok) {
+    u32 aw[8], rw[8], s[8], k[8];
+    ld_words<8>(aw, a_enc + idx * 8);
+    ld_words<8>(rw, r_enc + idx * 8);
+    ld_words<8>(s, s_le + idx * 8);
+    ld_words<8>(k, k_le + idx * 8);
+    fe25519 ax, ay, rx, ry;
+    u32 ok = ed25519_decode(ax, ay, aw);
+    ok &= ed25519_decode(rx, ry, rw);
+    ok &= lt_words8(s, ED25519_L);
+    ok &= lt_words8(k, ED25519_L);
+    if (!ok) {
+        out_ok[idx] = 0;
+        return;
+    }
+    // [S]B from the comb
+    const u32 half = 1u << (W - 1);
+    ge_p3 sb;
+    ge_identity(sb);
+    for (int i = 0; i < nwin; i++) {
+        u32 neg;
+        u32 d = booth_digit(s, 8, W, i, neg);
+        if (d != 0) {
+            ge_niels e;
+            const u32* src = table + ((size_t)i * half + (d - 1)) * 24;
+            ld_words<8>(e.yp.v, src);
+            ld_words<8>(e.ym.v, src + 8);
+            ld_words<8>(e.t2d.v, src + 16);
+            ge_niels_cneg(e, neg);
+            ge_madd<true>(sb, sb, e);
+        }
+    }
+    // [k](-A): signed 4-bit windows over 8 cached multiples
+    ge_p3 P, acc;
+    {
+        fe25519 nax;
+        F::neg(nax, ax);
+        ge_from_affine(P, nax, ay);
+        ge_cached c, c1;
+        ge_to_cached(c1, P);
+        acc = P;
+        ECB_NOUNROLL
+        for (int j = 1; j <= 8; j++) {
+            ge_to_cached(c, acc);
+            u32* d = tbl + (j - 1) * 32;
+            st_words<8>(d + 0, c.yp.v); st_words<8>(d + 8, c.ym.v); st_words<8>(d + 16, c.Z.v); st_words<8>(d + 24, c.t2d.v);
+            if (j < 8) ge_add_cached<true>(acc, acc, c1);
+        }
+    }
+    ge_identity(acc);
+    ECB_NOUNROLL
+    for (int i = 63; i >= 0; i--) {
+        if (i != 63) {
+            ECB_NOUNROLL
+            for (int r = 0; r < 3; r++) ge_double<false>(acc, acc);
+            ge_double<true>(acc, acc);
+        }
+        u32 neg;
+        u32 d = booth_digit(k, 8, 4, i, neg);
+        if (d != 0) {
+            ge_cached c;
+            const u32* sp = tbl + (d - 1) * 32;
+            ld_words_rw<8>(c.yp.v, sp); ld_words_rw<8>(c.ym.v, sp + 8); ld_words_rw<8>(c.Z.v, sp + 16); ld_words_rw<8>(c.t2d.v, sp + 24);
+            ge_cached_cneg(c, neg);
+            ge_add_cached<true>(acc, acc, c);
+        }
+    }
+    // lhs = [S]B + [k](-A)
+    ge_cached cs;
+    ge_to_cached(cs, sb);
+    ge_add_cached<false>(acc, acc, cs);
+    // lhs == R  <=>  X = rx * Z and Y = ry * Z   (R has Z = 1)
+    fe25519 t1, t2;
+    F::mul(t1, rx, acc.Z);
+    F::mul(t2, ry, acc.Z);
+    out_ok[idx] = (unsigned char)(F::eq(t1, acc.X) & F::eq(t2, acc.Y));
+}
+
+}  // namespace ecb

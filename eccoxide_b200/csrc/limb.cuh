@@ -20,18 +20,23 @@
 #define ECB_DEV inline
 #define ECB_DEVNI inline
 #define ECB_UNROLL
+#define ECB_NOUNROLL
 #define ECB_CONST static const
 #else
 #define ECB_DEV __device__ __forceinline__
 #define ECB_DEVNI __device__ __noinline__
 #define ECB_UNROLL _Pragma("unroll")
-#define ECB_CONST __device__ __constant__ const
+#define ECB_NOUNROLL _Pragma("unroll 1")
+#define ECB_CONST static __device__ __constant__ const
 #endif
 
 namespace ecb {
 
 typedef uint32_t u32;
 typedef uint64_t u64;
+
+// per-batch status word written by kernels with atomicMin: (index << 8) | code ; ~0 = no error
+enum { ST_NONCANONICAL_SCALAR = 1, ST_BAD_POINT = 2 };
 
 #ifdef ECB_HOSTSIM
 // ---- emulated carry flag (tests only) ----

@@ -26,6 +26,7 @@ struct fe_mont {
 template <class P>
 struct Mont {
     static constexpr int N = P::N;
+    typedef P P_;
     typedef fe_mont<P::N> el;
 
     ECB_DEV static void set_zero(el& r) {

@@ -1,0 +1,4 @@
+// tu_ecdsa_p256.cu
+#define ECB_TU_CURVE CurveP256
+#define ECB_TU_FN dev_ecdsa_p256
+#include "tu_ecdsa.inc"

@@ -1,0 +1,4 @@
+// tu_ecdsa_p384.cu
+#define ECB_TU_CURVE CurveP384
+#define ECB_TU_FN dev_ecdsa_p384
+#include "tu_ecdsa.inc"

@@ -1,0 +1,87 @@
+// tu_ed25519.cu — edwards25519 kernels: fixed-base comb (+ table builder), variable base, verify.
+#include "tu_common.cuh"
+#include "dev_ops.h"
+
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul_base(size_t n, const u32* scalars, const u32* table, int W,
+                                                               int nwin, u32* planes, unsigned long long* status) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) ed25519_mul_base_body(idx, n, scalars, table, W, nwin, planes, status);
+}
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_table_points(size_t ntab, int W, int nwin, u32* planes) {
+    size_t e = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (e < ntab) ed25519_table_point_body(e, ntab, W, nwin, planes);
+}
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul(size_t n, const u32* scalars, const u32* points, u32* scratch,
+                                                          u32* planes, unsigned long long* status) {
+    size_t T = (size_t)gridDim.x * ECB_TPB, t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    u32* tbl = scratch + t * (8 * 32);
+    for (size_t idx = t; idx < n; idx += T) ed25519_mul_body(idx, n, scalars, points, tbl, planes, status);
+}
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_verify(size_t n, const u32* a_enc, const u32* r_enc, const u32* s_le,
+                                                             const u32* k_le, const u32* table, int W, int nwin,
+                                                             u32* scratch, unsigned char* ok) {
+    size_t T = (size_t)gridDim.x * ECB_TPB, t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    u32* tbl = scratch + t * (8 * 32);
+    for (size_t idx = t; idx < n; idx += T) ed25519_verify_body(idx, n, a_enc, r_enc, s_le, k_le, table, W, nwin, tbl, ok);
+}
+
+int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
+    int nwin = (254 + W - 1) / W;
+    size_t ntab = (size_t)nwin << (W - 1);
+    if (d.ed_table) CU(cudaFree(d.ed_table));
+    d.ed_table = nullptr;
+    CU(cudaMalloc(&d.ed_table, ntab * 24 * sizeof(u32)));
+    TRY(ensure(ctx, d.planes, ntab * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.pf, ntab * 8 * sizeof(u32)));
+    k_ed25519_table_points<<<grid_for(ntab), ECB_TPB, 0, d.stream>>>(ntab, W, nwin, (u32*)d.planes.p);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    FinEdNiels fin{(const u32*)d.planes.p, ntab, d.ed_table};
+    TRY((launch_batch_inv<F25519, FinEdNiels>(ctx, d, ntab, (const u32*)d.planes.p, (u32*)d.pf.p, fin, d.stream)));
+    CU(cudaStreamSynchronize(d.stream));
+    d.ed_w = W;
+    d.ed_nwin = nwin;
+    return ECB_OK;
+}
+
+int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s) {
+    if (!d.ed_table || d.ed_w != (int)ctx->opt_ed_w) TRY(dev_ed25519_build_table(ctx, d, (int)ctx->opt_ed_w));
+    TRY(ensure(ctx, d.planes, n * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.pf, n * 8 * sizeof(u32)));
+    TRY(reset_status(ctx, d, s));
+    u32* planes = (u32*)d.planes.p;
+    k_ed25519_mul_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, planes, d.d_status);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (compressed) {
+        FinEdCompressed fin{planes, n, d_out};
+        return launch_batch_inv<F25519, FinEdCompressed>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    }
+    FinEdXY fin{planes, n, d_out};
+    return launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+}
+
+int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_out, cudaStream_t s) {
+    TRY(ensure(ctx, d.planes, n * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.pf, n * 8 * sizeof(u32)));
+    unsigned g = persistent_grid(d, k_ed25519_mul, n);
+    TRY(ensure(ctx, d.scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
+    TRY(reset_status(ctx, d, s));
+    u32* planes = (u32*)d.planes.p;
+    k_ed25519_mul<<<g, ECB_TPB, 0, s>>>(n, d_k, d_p, (u32*)d.scratch.p, planes, d.d_status);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    FinEdXY fin{planes, n, d_out};
+    return launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+}
+
+int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
+                       unsigned char* ok, cudaStream_t s) {
+    if (!d.ed_table || d.ed_w != (int)ctx->opt_ed_w) TRY(dev_ed25519_build_table(ctx, d, (int)ctx->opt_ed_w));
+    unsigned g = persistent_grid(d, k_ed25519_verify, n);
+    TRY(ensure(ctx, d.scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
+    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, r, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, (u32*)d.scratch.p, ok);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ECB_OK;
+}

@@ -1,0 +1,89 @@
+// tu_probe.cu — integer-pipe (IMAD) peak probe: the denominator of every roofline fraction.
+#include "host_ctx.h"
+#include "dev_ops.h"
+using namespace ecb;
+
+// integer-pipe probe -----------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(256) k_imad_probe(u32* out, int iters) {
+    u32 tid = blockIdx.x * 256 + threadIdx.x;
+    u32 x[8], y = tid * 2654435761u + 12345u;
+    for (int i = 0; i < 8; i++) x[i] = (tid + i) * 2246822519u + 7u;
+    if (V == 0 || V == 3) {
+        u32 a[8];
+        for (int i = 0; i < 8; i++) a[i] = tid + i;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) {
+                    if (V == 0) asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(x[i]), "r"(y));
+                    else asm volatile("mad.hi.u32 %0, %1, %2, %0;" : "+r"(a[i]) : "r"(x[i] | 0x80000000u), "r"(y | 0x80000000u));
+                }
+            }
+        }
+        u32 s = 0;
+        for (int i = 0; i < 8; i++) s ^= a[i];
+        out[tid] = s;
+    } else if (V == 1) {
+        unsigned long long a[8];
+        for (int i = 0; i < 8; i++) a[i] = tid + i;
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+#pragma unroll
+                for (int i = 0; i < 8; i++) asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(x[i]), "r"(y));
+            }
+        }
+        unsigned long long s = 0;
+        for (int i = 0; i < 8; i++) s ^= a[i];
+        out[tid] = (u32)s ^ (u32)(s >> 32);
+    } else {
+        // two interleaved carry chains of 4 IMAD.WIDE.U32.X + capture: exactly one row of mul_full<8>
+        u32 E[10], O[10];
+        for (int i = 0; i < 10; i++) { E[i] = tid + i; O[i] = tid * 3 + i; }
+        for (int it = 0; it < iters; it++) {
+#pragma unroll
+            for (int u = 0; u < 8; u++) {
+                mac_chain<4, true>(E, x, y);
+                mac_chain<4, true>(O, x + 1, y);
+            }
+        }
+        u32 s = 0;
+        for (int i = 0; i < 10; i++) s ^= E[i] ^ O[i];
+        out[tid] = s;
+    }
+}
+
+
+int dev_imad_probe(ecb_ctx* ctx, DevCtx& dref, int variant, int iters, double* macs_per_s, double* ms_out) {
+    DevCtx* d = &dref;
+    if (variant < 0 || variant > 3 || iters < 1) return ECB_ERR_INVALID_ARG;
+    unsigned blocks = (unsigned)d->sm_count * 8;
+    TRY(ensure(ctx, d->aux, (size_t)blocks * 256 * sizeof(u32)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {  // first pass is warm-up
+        CU(cudaEventRecord(e0, d->stream));
+        switch (variant) {
+            case 0: k_imad_probe<0><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
+            case 1: k_imad_probe<1><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
+            case 2: k_imad_probe<2><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
+            case 3: k_imad_probe<3><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
+        }
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e1, d->stream));
+        CU(cudaEventSynchronize(e1));
+    }
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    double macs = (double)blocks * 256.0 * (double)iters * 64.0;
+    if (macs_per_s) *macs_per_s = macs / (ms * 1e-3);
+    if (ms_out) *ms_out = ms;
+    return ECB_OK;
+}
+

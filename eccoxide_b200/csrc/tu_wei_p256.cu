@@ -1,0 +1,4 @@
+// tu_wei_p256.cu
+#define ECB_TU_CURVE CurveP256
+#define ECB_TU_FN dev_wei_mul_p256
+#include "tu_wei.inc"

@@ -1,0 +1,128 @@
+/* eccbatch.h — C ABI of libeccbatch: batched elliptic-curve scalar multiplication on B200 (sm_100a).
+ *
+ * This is the drop-in boundary for the one data-parallel hot path of vincenthz/eccoxide: many
+ * independent scalar multiplications.  The reference has no FFI of its own (pure Rust, one element
+ * per call); each entry point below is the batch sibling of one public per-element function and
+ * reproduces that function's result byte for byte on every element.  File:line citations are
+ * relative to the reference tree.  The Rust shim that binds these is in bindings/rust/ and
+ * INTEGRATION.md.
+ *
+ * Conventions
+ *   - every function returns 0 (ECB_OK) or a negative ECB_ERR_* code; ecb_last_error() gives text
+ *   - all buffers are caller-owned, contiguous, array-of-structures, in the reference's own wire
+ *     encodings (curve25519: little-endian; Weierstrass curves: big-endian), element i at i*size
+ *   - host entry points copy host->device, run the kernels and copy back before returning
+ *     (blocking); *_dev entry points take device pointers on device `dev_index` of the context and
+ *     enqueue on `stream` (a cudaStream_t) without synchronising
+ *   - a batch is sharded by contiguous slice over the devices of the context; no collective
+ *   - input validation mirrors the reference's Option/CtOption results: a non-canonical scalar
+ *     (Scalar::from_bytes -> None, src/curve/fiat/field_macros.rs:645) or an off-curve /
+ *     non-canonical point (PointAffine::from_coordinate -> None, src/curve/affine.rs:77;
+ *     Point::from_coordinate, src/curve/curve25519.rs:649) fails the whole call with
+ *     ECB_ERR_NONCANONICAL_SCALAR / ECB_ERR_POINT_NOT_ON_CURVE and *bad_index = first offender
+ *   - there is no CPU fallback: without a CUDA device every call fails with ECB_ERR_CUDA
+ *   - NOT constant time (indexed table loads, data-dependent skips): meant for public data
+ *     (verification, public scalar multiplication); see DESIGN.md
+ */
+#ifndef ECCBATCH_H
+#define ECCBATCH_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ECB_OK 0
+#define ECB_ERR_CUDA (-1)
+#define ECB_ERR_INVALID_ARG (-2)
+#define ECB_ERR_NONCANONICAL_SCALAR (-3)
+#define ECB_ERR_POINT_NOT_ON_CURVE (-4)
+#define ECB_ERR_OOM (-5)
+
+/* Weierstrass curve ids (src/curve/sec2/p256r1.rs, p384r1.rs, src/curve/bls12_381/g1.rs) */
+#define ECB_CURVE_P256R1 0       /* field 32 B, scalar 32 B */
+#define ECB_CURVE_P384R1 1       /* field 48 B, scalar 48 B */
+#define ECB_CURVE_BLS12_381_G1 2 /* field 48 B, scalar 32 B */
+
+typedef struct ecb_ctx ecb_ctx;
+
+/* Create a context over `n_dev` CUDA devices (device_ids == NULL, n_dev == 0: device 0 only).
+ * Builds the per-device generator comb tables — the role of the reference's OnceLock'd
+ * generator_comb() (src/curve/curve25519.rs:881, src/curve/fiat/curve_macros.rs:168). */
+int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out);
+void ecb_destroy(ecb_ctx* ctx);
+const char* ecb_last_error(ecb_ctx* ctx);
+int ecb_device_count(ecb_ctx* ctx);
+/* tunables, before first use: "ed25519_comb_w" (window width of the fixed-base comb, 4..16),
+ * "chunk" (elements per device pass) */
+int ecb_set_option(ecb_ctx* ctx, const char* key, long value);
+/* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
+unsigned long long ecb_launch_count(ecb_ctx* ctx);
+
+void* ecb_alloc_pinned(size_t bytes);
+void ecb_free_pinned(void* p);
+
+/* ---- edwards25519 ---------------------------------------------------------------------- */
+
+/* Point::mul_base(&Scalar) -> to_affine   (src/curve/curve25519.rs:840, :663)
+ * k_le: n x 32 B canonical scalars (< l); xy_le: n x 64 B affine x || y, canonical. */
+int ecb_ed25519_mul_base(ecb_ctx* ctx, const uint8_t* k_le, size_t n, uint8_t* xy_le, size_t* bad_index);
+/* same, output = encode_point(mul_base(k)) (src/protocol/ed25519.rs:27), n x 32 B */
+int ecb_ed25519_mul_base_compressed(ecb_ctx* ctx, const uint8_t* k_le, size_t n, uint8_t* enc, size_t* bad_index);
+/* &Point * &Scalar -> to_affine   (src/curve/curve25519.rs:1274, :760)
+ * xy_le_in: n x 64 B affine points (must satisfy Point::from_coordinate). */
+int ecb_ed25519_mul(ecb_ctx* ctx, const uint8_t* k_le, const uint8_t* xy_le_in, size_t n, uint8_t* xy_le_out,
+                    size_t* bad_index);
+/* protocol::ed25519 verify with k = SHA-512(R||A||M) mod l computed by the caller
+ * (src/protocol/ed25519.rs:119-147).  a_enc, r_enc, s_le, k_le: n x 32 B; ok: n x 1 B (0/1). */
+int ecb_ed25519_verify_prehashed(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* r_enc, const uint8_t* s_le,
+                                 const uint8_t* k_le, size_t n, uint8_t* ok);
+
+/* ---- X25519 / X448 --------------------------------------------------------------------- */
+
+/* protocol::x25519::x25519(scalar, u)   (src/protocol/x25519.rs:36): clamps inside, masks bit 255
+ * of u, accepts non-canonical u, returns 0 for low-order inputs.  k, u, out: n x 32 B. */
+int ecb_x25519(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8_t* out);
+/* protocol::x448::x448(scalar, u)   (src/protocol/x448.rs:34).  k, u, out: n x 56 B. */
+int ecb_x448(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8_t* out);
+
+/* ---- short Weierstrass: p256r1, p384r1, bls12_381 G1 ------------------------------------ */
+
+/* &Point * &Scalar -> to_affine   (src/curve/fiat/curve_macros.rs:321 -> projective.rs:871/:842)
+ * k_be: n x SB canonical scalars; xy_be: n x 2FB affine x || y; inf_in: optional n x 1 B, non-zero
+ * marks an identity input (its xy is ignored); out_xy_be: n x 2FB (zeros for the identity);
+ * out_inf: n x 1 B, 1 when the result is the identity (to_affine() == None, projective.rs:666). */
+int ecb_wei_mul(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, const uint8_t* xy_be, const uint8_t* inf_in, size_t n,
+                uint8_t* out_xy_be, uint8_t* out_inf, size_t* bad_index);
+/* Point::mul_base(&Scalar) -> to_affine   (fiat/curve_macros.rs:55 -> projective.rs:965/:945) */
+int ecb_wei_mul_base(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, size_t n, uint8_t* out_xy_be, uint8_t* out_inf,
+                     size_t* bad_index);
+/* ecdsa::verify_hashed (src/protocol/ecdsa.rs:205-222) after Signature::from_bytes (:399).
+ * q_xy_be: n x 2FB public keys; z_be: n x SB message scalars (any value, reduced mod n as
+ * digest_to_scalar :340 does); rs_be: n x 2SB r || s (zero or >= n => ok = 0); ok: n x 1 B. */
+int ecb_ecdsa_verify_hashed(ecb_ctx* ctx, int curve_id, const uint8_t* q_xy_be, const uint8_t* z_be,
+                            const uint8_t* rs_be, size_t n, uint8_t* ok, size_t* bad_index);
+
+/* ---- device-resident variants (inputs/outputs already in HBM of device `dev_index`) ------ */
+int ecb_ed25519_mul_base_dev(ecb_ctx* ctx, int dev_index, const void* d_k_le, size_t n, void* d_xy_le, void* stream);
+int ecb_ed25519_mul_dev(ecb_ctx* ctx, int dev_index, const void* d_k_le, const void* d_xy_in, size_t n, void* d_xy_out,
+                        void* stream);
+int ecb_x25519_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);
+int ecb_wei_mul_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_k_be, const void* d_xy_be, size_t n,
+                    void* d_out_xy_be, void* d_out_inf, void* stream);
+/* after a *_dev call and a stream sync: 0, or the error of the first invalid element */
+int ecb_dev_status(ecb_ctx* ctx, int dev_index, size_t* bad_index);
+
+/* ---- measurement helpers ----------------------------------------------------------------- */
+/* Integer-pipe peak probe.  variant: 0 = IMAD (32-bit), 1 = IMAD.WIDE.U32, 2 = IMAD.WIDE.U32.X carry
+ * chains (the field kernels' instruction), 3 = IMAD.HI.U32.  Returns multiply-accumulates per second
+ * on device `dev_index` and the kernel time. */
+int ecb_imad_probe(ecb_ctx* ctx, int dev_index, int variant, int iters, double* macs_per_s, double* ms);
+/* debug: copy the device's Ed25519 comb table (niels entries, 96 B each) to host; returns entries */
+long ecb_debug_ed25519_table(ecb_ctx* ctx, int dev_index, uint8_t* out, size_t cap_bytes, int* w, int* nwin);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -81,3 +81,53 @@ extern "C" unsigned long long hs_wei_mul(int curve, const u32* k, const u32* pts
     }
     return 0;
 }
+
+// ---- kernels2: X448, ECDSA verify, Ed25519 verify ------------------------------------------
+#include "../../eccoxide_b200/csrc/kernels2.cuh"
+extern "C" {
+void hs_fe448(int op, const u32* a, const u32* b, u32* r) {
+    fe448 x, y, z;
+    memcpy(x.v, a, 56); memcpy(y.v, b, 56);
+    switch (op) {
+        case 0: F448::mul(z, x, y); break;
+        case 1: F448::sqr(z, x); break;
+        case 2: F448::add(z, x, y); break;
+        case 3: F448::sub(z, x, y); break;
+        case 5: F448::freeze(z, x); break;
+        case 6: F448::invert(z, x); break;
+        case 7: F448::mul_small(z, x, b[0]); break;
+    }
+    memcpy(r, z.v, 56);
+}
+void hs_x448(const u32* k, const u32* u, size_t n, u32* out) {
+    std::vector<u32> planes(3 * 14 * n), pf(14 * n);
+    for (size_t i = 0; i < n; i++) x448_body(i, n, k, u, planes.data());
+    size_t T = inv_threads(n);
+    FinX448 fin{planes.data(), n, out};
+    for (size_t t = 0; t < T; t++) batch_inv_body<F448>(t, T, n, planes.data(), pf.data(), fin);
+}
+void hs_ed25519_verify(const u32* a, const u32* r, const u32* s, const u32* k, size_t n, int W, const u32* table,
+                       unsigned char* ok) {
+    int nwin = (254 + W - 1) / W;
+    std::vector<u32> tbl(8 * 32);
+    for (size_t i = 0; i < n; i++) ed25519_verify_body(i, n, a, r, s, k, table, W, nwin, tbl.data(), ok);
+}
+}
+template <class C>
+static unsigned long long ecdsa_run(const u32* q, const u32* z, const u32* rs, size_t n, unsigned char* ok) {
+    constexpr int N = C::F::N, NS = C::FN::N;
+    std::vector<u32> planes(3 * N * n), pf((N > NS ? N : NS) * n), aux(3 * NS * n), tbl(16 * 3 * N);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) ecdsa_prep_body<C>(i, n, z, rs, aux.data(), ok);
+    size_t T = inv_threads(n);
+    FinScalarInv<C> f1{aux.data(), n};
+    for (size_t t = 0; t < T; t++) batch_inv_body<typename C::FN>(t, T, n, aux.data(), pf.data(), f1);
+    for (size_t i = 0; i < n; i++) ecdsa_main_body<C>(i, n, q, z, rs, aux.data(), ok, tbl.data(), planes.data(), &st);
+    FinEcdsa<C> f2{planes.data(), n, rs, ok};
+    for (size_t t = 0; t < T; t++) batch_inv_body<typename C::F>(t, T, n, planes.data(), pf.data(), f2);
+    return st;
+}
+extern "C" unsigned long long hs_ecdsa_verify(int curve, const u32* q, const u32* z, const u32* rs, size_t n, unsigned char* ok) {
+    if (curve == 0) return ecdsa_run<CurveP256>(q, z, rs, n, ok);
+    return ecdsa_run<CurveP384>(q, z, rs, n, ok);
+}
