@@ -1,0 +1,341 @@
+"""Pin the oracles (oracle/pyref.py, oracle/ecc_oracle.c) to the reference's own known-answer
+vectors (tests/golden/reference_vectors.json, extracted by tools/extract_reference_vectors.py) and
+to independent third-party implementations (libsodium via pynacl, OpenSSL via cryptography).
+
+CPU only.  These tests are what allows the `-m gpu` parity tests to treat the oracle as the
+reference: every vector the reference's tests hold for the hot path is checked here.
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from helpers import ed_edge_scalars, rng, rows, wei_edge_scalars
+from oracle import pyref as R
+
+H = bytes.fromhex
+CURVES = ("p256r1", "p384r1", "bls12_381_g1")
+
+
+# ---- domain parameters -------------------------------------------------------------------
+@pytest.mark.parametrize("curve", CURVES)
+def test_params_match_reference(golden, curve):
+    c, p = R.WCURVES[curve], golden["params"][curve]
+    assert c.p == int(p["p"], 16) and c.n == int(p["order"], 16) and c.b == int(p["b"], 16)
+    assert c.G == (int(p["gx"], 16), int(p["gy"], 16))
+    assert c.on_curve(c.G) and c.mul(c.n, c.G) is None
+
+
+# ---- comb tables (src/params/comb/*.rs) -----------------------------------------------------
+def test_comb_table_ed25519_matches_reference(golden, coracle):
+    t = golden["comb_tables"]["curve25519"]
+    raw = b"".join(coracle.ed25519_comb_entry(i, j) for i in range(t["windows"]) for j in range(1, 16))
+    assert hashlib.sha256(raw).hexdigest() == t["sha256"]
+    for key, val in t["samples"].items():
+        i, j = map(int, key.split(","))
+        x, y = R.ed_mul((j + 1) << (4 * i), R.ED_B)
+        assert (x.to_bytes(32, "little") + y.to_bytes(32, "little")).hex() == val
+    assert coracle.ed25519_comb_entry(3, 0) == (0).to_bytes(32, "little") + (1).to_bytes(32, "little")
+
+
+@pytest.mark.parametrize("curve,name", [("p256r1", "p256r1"), ("p384r1", "p384r1"), ("bls12_381_g1", "bls12_381")])
+def test_comb_table_weierstrass_matches_reference(golden, coracle, curve, name):
+    t, c = golden["comb_tables"][name], R.WCURVES[curve]
+    assert t["windows"] == 2 * c.sbytes
+    raw = b"".join(coracle.wei_comb_entry(curve, i, j) for i in range(t["windows"]) for j in range(1, 16))
+    assert hashlib.sha256(raw).hexdigest() == t["sha256"]
+    for key, val in t["samples"].items():
+        i, j = map(int, key.split(","))
+        assert c.enc(c.mul((j + 1) << (4 * i), c.G)).hex() == val
+
+
+# ---- NIST point-multiplication KATs (src/tests/kats.rs: &Point::GENERATOR * &k) -------------
+@pytest.mark.parametrize("curve,key", [("p256r1", "nist_p256"), ("p384r1", "nist_p384")])
+def test_nist_kats(golden, coracle, curve, key):
+    c = R.WCURVES[curve]
+    kats = golden[key]
+    assert len(kats) == 52
+    ks = rows([int(v["k"], 16).to_bytes(c.sbytes, "big") for v in kats])
+    exp = rows([int(v["x"], 16).to_bytes(c.fbytes, "big") + int(v["y"], 16).to_bytes(c.fbytes, "big") for v in kats])
+    g = np.tile(np.frombuffer(c.enc(c.G), dtype=np.uint8), (len(kats), 1))
+    for mode in (coracle.MODE_WINDOW, coracle.MODE_WNAF, coracle.MODE_COMB):
+        out, inf = coracle.wei_mul(curve, ks, g, mode=mode)
+        assert not inf.any() and np.array_equal(out, exp), mode
+    for i in (0, 1, 19, 25, 31, 51):
+        assert R.wei_mul(c, ks[i].tobytes(), g[i].tobytes()) == (exp[i].tobytes(), 0)
+
+
+# ---- X25519 / X448 (RFC 7748 vectors held by the reference) ----------------------------------
+def test_x25519_vectors(golden, coracle):
+    v = golden["x25519"]
+    ks, us, rs = [], [], []
+    for e in v["rfc7748_5_2"]:
+        ks.append(H(e["k"])); us.append(H(e["u"])); rs.append(H(e["r"]))
+    ks.append(H(v["iterated_once"]["k"])); us.append((9).to_bytes(32, "little")); rs.append(H(v["iterated_once"]["r"]))
+    a, b = H(v["dh_6_1"]["a"]), H(v["dh_6_1"]["b"])
+    a_pub, b_pub = R.x25519(a, (9).to_bytes(32, "little")), R.x25519(b, (9).to_bytes(32, "little"))
+    ks += [a, b]; us += [b_pub, a_pub]; rs += [H(v["dh_6_1"]["shared"])] * 2
+    for k, u, r in zip(ks, us, rs):
+        assert R.x25519(k, u) == r
+    assert np.array_equal(coracle.x25519(rows(ks), rows(us)), rows(rs))
+    # ladder KATs (curve25519.rs:1629-1643): unclamped small scalars on u = 9
+    for k, r in v["ladder_u9"].items():
+        assert R._ladder(R.P25519, 121666, 9, int(k), 256).to_bytes(32, "big") == H(r)  # fe() there parses big-endian
+
+
+def test_x25519_edge_inputs(coracle):
+    """decode_u masks bit 255 and accepts non-canonical u; low-order points give all-zero output."""
+    g = rng(7)
+    p = R.P25519
+    us = [0, 1, p - 1, p, p + 1, 2**255 - 1, 325606250916557431795983626356110631294008115727848805560023387167927233504]
+    us = [x.to_bytes(32, "little") for x in us] + [b"\xff" * 32, (9 | 1 << 255).to_bytes(32, "little")]
+    ks = [g.bytes(32) for _ in us]
+    out = coracle.x25519(rows(ks), rows(us))
+    for i, (k, u) in enumerate(zip(ks, us)):
+        assert out[i].tobytes() == R.x25519(k, u)
+    assert not out[0].any() and not out[1].any() and not out[3].any()
+
+
+def test_x448_vectors(golden, coracle):
+    v = golden["x448"]
+    ks, us, rs = [], [], []
+    for e in v["rfc7748_5_2"]:
+        ks.append(H(e["k"])); us.append(H(e["u"])); rs.append(H(e["r"]))
+    five = (5).to_bytes(56, "little")
+    d = v["dh_6_2"]
+    ks += [H(d["a"]), H(d["b"]), H(d["a"]), H(d["b"])]
+    us += [five, five, H(d["b_pub"]), H(d["a_pub"])]
+    rs += [H(d["a_pub"]), H(d["b_pub"]), H(d["shared"]), H(d["shared"])]
+    for k, u, r in zip(ks, us, rs):
+        assert R.x448(k, u) == r
+    assert np.array_equal(coracle.x448(rows(ks), rows(us)), rows(rs))
+
+
+# ---- Ed25519 (RFC 8032 vectors held by the reference) ----------------------------------------
+def _clamped_scalar(seed):
+    h = bytearray(hashlib.sha512(seed).digest()[:32])
+    h[0] &= 248; h[31] &= 127; h[31] |= 64
+    return (int.from_bytes(h, "little") % R.L25519).to_bytes(32, "little")
+
+
+def test_ed25519_rfc8032(golden, coracle):
+    A, Rr, S, K, ks = [], [], [], [], []
+    for v in golden["ed25519_rfc8032"]:
+        seed, pub, msg, sig = H(v["seed"]), H(v["public"]), H(v["message"]), H(v["signature"])
+        assert R.ed25519_public_from_seed(seed) == pub
+        assert R.ed25519_sign(seed, msg) == sig
+        assert R.ed25519_verify(pub, msg, sig)
+        ks.append(_clamped_scalar(seed))
+        for tamper in (False, True):
+            s2 = bytearray(sig)
+            if tamper:
+                s2[1] ^= 0x20
+            A.append(pub); Rr.append(bytes(s2[:32])); S.append(bytes(s2[32:])); K.append(R.ed25519_hash_k(bytes(s2[:32]), pub, msg))
+    xy = coracle.ed25519_mul_base(rows(ks))
+    for i, v in enumerate(golden["ed25519_rfc8032"]):
+        x, y = int.from_bytes(xy[i, :32].tobytes(), "little"), int.from_bytes(xy[i, 32:].tobytes(), "little")
+        assert R.ed_encode((x, y)) == H(v["public"])
+    ok = coracle.ed25519_verify_prehashed(rows(A), rows(Rr), rows(S), rows(K))
+    assert ok.tolist() == [True, False] * 3
+
+
+def test_ed25519_edge_scalars(golden, coracle):
+    vals = ed_edge_scalars(golden)
+    ks = rows([v.to_bytes(32, "little") for v in vals])
+    xy = coracle.ed25519_mul_base(ks)
+    g = np.tile(np.frombuffer(R.ED_BX.to_bytes(32, "little") + R.ED_BY.to_bytes(32, "little"), dtype=np.uint8), (len(vals), 1))
+    xy2 = coracle.ed25519_mul(ks, g)
+    for i, v in enumerate(vals):
+        assert xy[i].tobytes() == R.ed25519_mul_base_xy(ks[i].tobytes())
+    assert np.array_equal(xy, xy2)  # mul_base_matches_scale (curve25519.rs:1374)
+    assert xy[0].tobytes() == (0).to_bytes(32, "little") + (1).to_bytes(32, "little")
+
+
+def test_ed25519_invalid_inputs(coracle):
+    bad_k = rows([(1).to_bytes(32, "little"), R.L25519.to_bytes(32, "little")])
+    with pytest.raises(coracle.OracleInvalidInput) as e:
+        coracle.ed25519_mul_base(bad_k)
+    assert e.value.index == 1 and e.value.code == 1
+    pts = rows([R.ED_BX.to_bytes(32, "little") + R.ED_BY.to_bytes(32, "little"), (2).to_bytes(32, "little") + (3).to_bytes(32, "little")])
+    with pytest.raises(coracle.OracleInvalidInput) as e:
+        coracle.ed25519_mul(rows([(5).to_bytes(32, "little")] * 2), pts)
+    assert e.value.index == 1 and e.value.code == 2
+    # decode_point rejections (protocol/ed25519.rs:38-59): non-canonical y, x = 0 with sign bit
+    for enc in (R.P25519.to_bytes(32, "little"), (1 | 1 << 255).to_bytes(32, "little"), (2).to_bytes(32, "little")):
+        if R.ed_decode(enc) is None:
+            z = rows([enc])
+            assert not coracle.ed25519_verify_prehashed(z, z, rows([bytes(32)]), rows([bytes(32)]))[0]
+    assert R.ed_decode(R.P25519.to_bytes(32, "little")) is None
+    assert R.ed_decode((1 | 1 << 255).to_bytes(32, "little")) is None
+
+
+def test_ed25519_vs_libsodium(coracle):
+    nb = pytest.importorskip("nacl.bindings")
+    g = rng(11)
+    ks = [(int.from_bytes(g.bytes(40), "little") % (R.L25519 - 1) + 1).to_bytes(32, "little") for _ in range(64)]
+    xy = coracle.ed25519_mul_base(rows(ks))
+    for i, k in enumerate(ks):
+        x, y = int.from_bytes(xy[i, :32].tobytes(), "little"), int.from_bytes(xy[i, 32:].tobytes(), "little")
+        assert R.ed_encode((x, y)) == nb.crypto_scalarmult_ed25519_base_noclamp(k)
+    us = [g.bytes(32) for _ in ks]
+    out = coracle.x25519(rows(ks), rows(us))
+    for i in range(len(ks)):
+        u = bytearray(us[i])
+        try:
+            assert out[i].tobytes() == nb.crypto_scalarmult(ks[i], bytes(u))
+        except Exception as e:  # libsodium raises on all-zero output
+            assert "zero" in str(e).lower() or not out[i].any()
+
+
+# ---- ECDSA (RFC 6979 vectors held by the reference) -------------------------------------------
+@pytest.mark.parametrize("curve", ["p256r1", "p384r1"])
+def test_ecdsa_rfc6979(golden, coracle, curve):
+    c, v = R.WCURVES[curve], golden["ecdsa_rfc6979"][curve]
+    d, Q = int(v["d"], 16), (int(v["qx"], 16), int(v["qy"], 16))
+    assert c.mul(d, c.G) == Q
+    out, inf = coracle.wei_mul_base(curve, rows([d.to_bytes(c.sbytes, "big")]))
+    assert out[0].tobytes() == c.enc(Q) and not inf[0]
+    Qs, Zs, RSs, exp = [], [], [], []
+    for kat in v["kats"]:
+        z = R.ecdsa_digest_to_scalar(c, hashlib.new(kat["alg"], kat["message"].encode()).digest())
+        k, r, s = int(kat["k"], 16), int(kat["r"], 16), int(kat["s"], 16)
+        rs = r.to_bytes(c.sbytes, "big") + s.to_bytes(c.sbytes, "big")
+        assert R.ecdsa_sign_hashed(c, d, k, int.from_bytes(z, "big")) == rs
+        kg, _ = coracle.wei_mul_base(curve, rows([k.to_bytes(c.sbytes, "big")]))
+        assert int.from_bytes(kg[0, : c.fbytes].tobytes(), "big") % c.n == r
+        for tamper in range(3):
+            z2, rs2 = bytearray(z), bytearray(rs)
+            if tamper == 1:
+                z2[-1] ^= 1
+            if tamper == 2:
+                rs2[-1] ^= 1
+            Qs.append(c.enc(Q)); Zs.append(bytes(z2)); RSs.append(bytes(rs2)); exp.append(tamper == 0)
+            assert R.ecdsa_verify_hashed(c, c.enc(Q), bytes(z2), bytes(rs2)) == (tamper == 0)
+    ok = coracle.ecdsa_verify_hashed(curve, rows(Qs), rows(Zs), rows(RSs))
+    assert ok.tolist() == exp
+
+
+@pytest.mark.parametrize("curve", ["p256r1", "p384r1"])
+def test_ecdsa_zero_and_noncanonical_rejected(coracle, curve):
+    c = R.WCURVES[curve]
+    q = c.enc(c.G)
+    z = bytes(c.sbytes)
+    one = (1).to_bytes(c.sbytes, "big")
+    cases = [bytes(c.sbytes) + one, one + bytes(c.sbytes), c.n.to_bytes(c.sbytes, "big") + one, one + c.n.to_bytes(c.sbytes, "big")]
+    ok = coracle.ecdsa_verify_hashed(curve, rows([q] * 4), rows([z] * 4), rows(cases))
+    assert not ok.any()
+    assert not any(R.ecdsa_verify_hashed(c, q, z, cs) for cs in cases)
+
+
+def test_ecdsa_vs_openssl(coracle):
+    ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric.utils import decode_dss_signature
+
+    for curve, oc, hs in (("p256r1", ec.SECP256R1(), hashes.SHA256()), ("p384r1", ec.SECP384R1(), hashes.SHA384())):
+        c = R.WCURVES[curve]
+        Qs, Zs, RSs = [], [], []
+        for i in range(6):
+            key = ec.generate_private_key(oc)
+            msg = b"msg %d" % i
+            r, s = decode_dss_signature(key.sign(msg, ec.ECDSA(hs)))
+            pn = key.public_key().public_numbers()
+            Qs.append(c.enc((pn.x, pn.y)))
+            Zs.append(R.ecdsa_digest_to_scalar(c, hashlib.new(hs.name, msg).digest()))
+            RSs.append(r.to_bytes(c.sbytes, "big") + s.to_bytes(c.sbytes, "big"))
+            # OpenSSL k*G == oracle mul_base
+            d = key.private_numbers().private_value
+            out, _ = coracle.wei_mul_base(curve, rows([d.to_bytes(c.sbytes, "big")]))
+            assert out[0].tobytes() == Qs[-1]
+        assert coracle.ecdsa_verify_hashed(curve, rows(Qs), rows(Zs), rows(RSs)).all()
+
+
+# ---- BLS12-381 G1 (g1.rs serialization_kat) -----------------------------------------------------
+def _bls_compress(xy):
+    c = R.BLSG1
+    x, y = c.dec(xy)
+    b = bytearray(x.to_bytes(48, "big"))
+    b[0] |= 0x80
+    if y > (c.p - 1) // 2:
+        b[0] |= 0x20
+    return bytes(b)
+
+
+def test_bls_g1_kats(golden, coracle):
+    c = R.BLSG1
+    v = golden["bls12_381_g1"]
+    for ent in v["compressed"]:
+        k = ent["k"].to_bytes(32, "big")
+        for out, inf in (coracle.wei_mul_base("bls12_381_g1", rows([k])),
+                         coracle.wei_mul("bls12_381_g1", rows([k]), rows([c.enc(c.G)]))):
+            assert not inf[0] and _bls_compress(out[0].tobytes()).hex() == ent["bytes"]
+        assert _bls_compress(R.wei_mul_base(c, k)[0]).hex() == ent["bytes"]
+    for ent in v["uncompressed"]:
+        k = ent["k"].to_bytes(32, "big")
+        out, _ = coracle.wei_mul_base("bls12_381_g1", rows([k]))
+        assert out[0].tobytes().hex() == ent["bytes"]
+
+
+def test_bls_off_subgroup_points(coracle):
+    """Point::mul works on any curve point (g1.rs:375-377), not only the prime-order subgroup."""
+    c = R.BLSG1
+    pts = []
+    x = 1
+    while len(pts) < 3:
+        x += 1
+        rhs = (x**3 + 4) % c.p
+        y = pow(rhs, (c.p + 1) // 4, c.p)
+        if y * y % c.p == rhs and c.mul(c.n, (x, y)) is not None:
+            pts.append((x, y))
+    g = rng(5)
+    ks = [(int.from_bytes(g.bytes(40), "little") % c.n).to_bytes(32, "big") for _ in pts]
+    out, inf = coracle.wei_mul("bls12_381_g1", rows(ks), rows([c.enc(p) for p in pts]))
+    for i, p in enumerate(pts):
+        assert (out[i].tobytes(), int(inf[i])) == R.wei_mul(c, ks[i], c.enc(p))
+
+
+# ---- Weierstrass edge scalars, identity handling, cross-algorithm agreement ----------------------
+@pytest.mark.parametrize("curve", CURVES)
+def test_weierstrass_edge_scalars(golden, coracle, curve):
+    c = R.WCURVES[curve]
+    vals = wei_edge_scalars(golden, c.n)
+    ks = rows([v.to_bytes(c.sbytes, "big") for v in vals])
+    g = rng(3)
+    P = c.mul(int.from_bytes(g.bytes(16), "little"), c.G)
+    pts = np.tile(np.frombuffer(c.enc(P), dtype=np.uint8), (len(vals), 1))
+    ref = [R.wei_mul(c, ks[i].tobytes(), pts[i].tobytes()) for i in range(len(vals))]
+    for mode in (coracle.MODE_WINDOW, coracle.MODE_WNAF):
+        out, inf = coracle.wei_mul(curve, ks, pts, mode=mode)
+        assert [(out[i].tobytes(), int(inf[i])) for i in range(len(vals))] == ref
+    assert ref[0] == (bytes(2 * c.fbytes), 1)  # k = 0 -> identity
+    outb, infb = coracle.wei_mul_base(curve, ks)
+    outg, infg = coracle.wei_mul(curve, ks, np.tile(np.frombuffer(c.enc(c.G), dtype=np.uint8), (len(vals), 1)))
+    assert np.array_equal(outb, outg) and np.array_equal(infb, infg)  # mul_base_matches_generic
+    # identity input (inf_in) stays the identity
+    out, inf = coracle.wei_mul(curve, ks[:4], pts[:4], inf_in=np.ones(4, dtype=np.uint8))
+    assert inf.all() and not out.any()
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_weierstrass_invalid_inputs(coracle, curve):
+    c = R.WCURVES[curve]
+    good = c.enc(c.G)
+    bad_pt = bytearray(good); bad_pt[-1] ^= 1
+    with pytest.raises(coracle.OracleInvalidInput) as e:
+        coracle.wei_mul(curve, rows([(1).to_bytes(c.sbytes, "big")] * 2), rows([good, bytes(bad_pt)]))
+    assert (e.value.index, e.value.code) == (1, 2)
+    with pytest.raises(coracle.OracleInvalidInput) as e:
+        coracle.wei_mul(curve, rows([c.n.to_bytes(c.sbytes, "big")]), rows([good]))
+    assert (e.value.index, e.value.code) == (0, 1)
+
+
+def test_p256_vs_openssl_ecdh(coracle):
+    ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
+    c = R.P256
+    for _ in range(4):
+        a, b = ec.generate_private_key(ec.SECP256R1()), ec.generate_private_key(ec.SECP256R1())
+        pn = b.public_key().public_numbers()
+        shared = a.exchange(ec.ECDH(), b.public_key())
+        k = a.private_numbers().private_value.to_bytes(32, "big")
+        out, _ = coracle.wei_mul("p256r1", rows([k]), rows([c.enc((pn.x, pn.y))]))
+        assert out[0, :32].tobytes() == shared
