@@ -49,6 +49,10 @@ SIGNATURES = {
     "ecb_ed25519_mul_dev": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_x25519_dev": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_wei_mul_dev": (_int, [_vp, _int, _int, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "ecb_x448_dev": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
+    "ecb_ed25519_verify_prehashed_dev": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ecb_ecdsa_verify_hashed_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ecb_profile_collect": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_int)]),
     "ecb_dev_status": (_int, [_vp, _int, _szp]),
     "ecb_imad_probe": (_int, [_vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "ecb_debug_ed25519_table": (ctypes.c_long, [_vp, _int, _vp, _sz, ctypes.POINTER(_int), ctypes.POINTER(_int)]),

@@ -30,6 +30,15 @@ def _p(a):
     return None if a is None else a.ctypes.data_as(ctypes.c_void_p)
 
 
+def _out(out, shape):
+    """Caller-provided output (e.g. pinned memory) or a fresh array."""
+    if out is None:
+        return np.empty(shape, dtype=np.uint8)
+    if out.dtype != np.uint8 or not out.flags["C_CONTIGUOUS"] or out.size != int(np.prod(shape)):
+        raise ValueError("out: expected contiguous uint8 array of %d bytes" % int(np.prod(shape)))
+    return out.reshape(shape)
+
+
 class Context:
     """One libeccbatch context over `devices` (default: CUDA device 0)."""
 
@@ -88,58 +97,58 @@ class Context:
         return int(self._lib.ecb_device_count(self._ctx))
 
     # -- edwards25519 -------------------------------------------------------------------------
-    def ed25519_mul_base(self, k_le, compressed=False):
+    def ed25519_mul_base(self, k_le, compressed=False, out=None):
         k = _rows(k_le, 32, "k_le")
         n = k.shape[0]
-        out = np.empty((n, 32 if compressed else 64), dtype=np.uint8)
+        out = _out(out, (n, 32 if compressed else 64))
         bad = ctypes.c_size_t()
         fn = self._lib.ecb_ed25519_mul_base_compressed if compressed else self._lib.ecb_ed25519_mul_base
         self._check(fn(self._ctx, _p(k), n, _p(out), ctypes.byref(bad)), bad)
         return out
 
-    def ed25519_mul(self, k_le, xy_le):
+    def ed25519_mul(self, k_le, xy_le, out=None):
         k = _rows(k_le, 32, "k_le")
         p = _rows(xy_le, 64, "xy_le")
         if k.shape[0] != p.shape[0]:
             raise ValueError("scalar/point count mismatch")
         n = k.shape[0]
-        out = np.empty((n, 64), dtype=np.uint8)
+        out = _out(out, (n, 64))
         bad = ctypes.c_size_t()
         self._check(self._lib.ecb_ed25519_mul(self._ctx, _p(k), _p(p), n, _p(out), ctypes.byref(bad)), bad)
         return out
 
-    def ed25519_verify_prehashed(self, a_enc, r_enc, s_le, k_le):
+    def ed25519_verify_prehashed(self, a_enc, r_enc, s_le, k_le, out=None):
         a, r, s, k = (_rows(x, 32, nm) for x, nm in ((a_enc, "a_enc"), (r_enc, "r_enc"), (s_le, "s_le"), (k_le, "k_le")))
         n = a.shape[0]
         if not (r.shape[0] == s.shape[0] == k.shape[0] == n):
             raise ValueError("count mismatch")
-        ok = np.empty(n, dtype=np.uint8)
+        ok = _out(out, (n,))
         self._check(self._lib.ecb_ed25519_verify_prehashed(self._ctx, _p(a), _p(r), _p(s), _p(k), n, _p(ok)))
         return ok.astype(bool)
 
     # -- X25519 / X448 ------------------------------------------------------------------------
-    def x25519(self, k, u):
+    def x25519(self, k, u, out=None):
         k = _rows(k, 32, "k")
         u = _rows(u, 32, "u")
         if k.shape[0] != u.shape[0]:
             raise ValueError("count mismatch")
         n = k.shape[0]
-        out = np.empty((n, 32), dtype=np.uint8)
+        out = _out(out, (n, 32))
         self._check(self._lib.ecb_x25519(self._ctx, _p(k), _p(u), n, _p(out)))
         return out
 
-    def x448(self, k, u):
+    def x448(self, k, u, out=None):
         k = _rows(k, 56, "k")
         u = _rows(u, 56, "u")
         if k.shape[0] != u.shape[0]:
             raise ValueError("count mismatch")
         n = k.shape[0]
-        out = np.empty((n, 56), dtype=np.uint8)
+        out = _out(out, (n, 56))
         self._check(self._lib.ecb_x448(self._ctx, _p(k), _p(u), n, _p(out)))
         return out
 
     # -- Weierstrass --------------------------------------------------------------------------
-    def wei_mul(self, curve, k_be, xy_be, inf_in=None):
+    def wei_mul(self, curve, k_be, xy_be, inf_in=None, out=None, out_inf=None):
         cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
         fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]
         k = _rows(k_be, sb, "k_be")
@@ -149,24 +158,24 @@ class Context:
             raise ValueError("count mismatch")
         if inf_in is not None:
             inf_in = np.ascontiguousarray(inf_in, dtype=np.uint8).reshape(n)
-        out = np.empty((n, 2 * fb), dtype=np.uint8)
-        inf = np.empty(n, dtype=np.uint8)
+        out = _out(out, (n, 2 * fb))
+        inf = _out(out_inf, (n,))
         bad = ctypes.c_size_t()
         self._check(self._lib.ecb_wei_mul(self._ctx, cid, _p(k), _p(p), _p(inf_in), n, _p(out), _p(inf), ctypes.byref(bad)), bad)
         return out, inf.astype(bool)
 
-    def wei_mul_base(self, curve, k_be):
+    def wei_mul_base(self, curve, k_be, out=None, out_inf=None):
         cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
         fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]
         k = _rows(k_be, sb, "k_be")
         n = k.shape[0]
-        out = np.empty((n, 2 * fb), dtype=np.uint8)
-        inf = np.empty(n, dtype=np.uint8)
+        out = _out(out, (n, 2 * fb))
+        inf = _out(out_inf, (n,))
         bad = ctypes.c_size_t()
         self._check(self._lib.ecb_wei_mul_base(self._ctx, cid, _p(k), n, _p(out), _p(inf), ctypes.byref(bad)), bad)
         return out, inf.astype(bool)
 
-    def ecdsa_verify_hashed(self, curve, q_xy_be, z_be, rs_be):
+    def ecdsa_verify_hashed(self, curve, q_xy_be, z_be, rs_be, out=None):
         cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
         fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]
         q = _rows(q_xy_be, 2 * fb, "q_xy_be")
@@ -175,10 +184,25 @@ class Context:
         n = q.shape[0]
         if not (z.shape[0] == rs.shape[0] == n):
             raise ValueError("count mismatch")
-        ok = np.empty(n, dtype=np.uint8)
+        ok = _out(out, (n,))
         bad = ctypes.c_size_t()
         self._check(self._lib.ecb_ecdsa_verify_hashed(self._ctx, cid, _p(q), _p(z), _p(rs), n, _p(ok), ctypes.byref(bad)), bad)
         return ok.astype(bool)
+
+    # -- device-resident variants (raw device pointers, enqueue on `stream`, no sync) -----------
+    def dev_call(self, name, *args):
+        """Call a *_dev entry point: args are ints (device pointers, sizes, ids) in ABI order after ctx."""
+        self._check(getattr(self._lib, name)(self._ctx, *args))
+
+    def dev_status(self, dev_index=0):
+        bad = ctypes.c_size_t()
+        rc = self._lib.ecb_dev_status(self._ctx, dev_index, ctypes.byref(bad))
+        return rc, (None if bad.value == ctypes.c_size_t(-1).value else bad.value)
+
+    def profile_collect(self, dev_index=0):
+        m, f, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_int()
+        self._check(self._lib.ecb_profile_collect(self._ctx, dev_index, ctypes.byref(m), ctypes.byref(f), ctypes.byref(c)))
+        return m.value, f.value, c.value
 
     # -- measurement --------------------------------------------------------------------------
     def imad_probe(self, variant, iters=4096, dev_index=0):

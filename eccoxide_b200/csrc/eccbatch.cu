@@ -64,6 +64,7 @@ void ecb_destroy(ecb_ctx* ctx) {
         DevBuf* bufs[] = {&d->planes, &d->pf, &d->scratch, &d->aux, &d->in[0], &d->in[1], &d->in[2], &d->in[3], &d->out[0], &d->out[1]};
         for (DevBuf* b : bufs)
             if (b->p) cudaFree(b->p);
+        for (auto& r : d->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); cudaEventDestroy(r.c); }
         if (d->ed_table) cudaFree(d->ed_table);
         if (d->d_status) cudaFree(d->d_status);
         if (d->h_status) cudaFreeHost(d->h_status);
@@ -87,6 +88,10 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "chunk")) {
         if (value < 1) return set_err(ctx, ECB_ERR_INVALID_ARG, "chunk must be >= 1");
         ctx->opt_chunk = (size_t)value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "profile")) {
+        ctx->opt_profile = value ? 1 : 0;
         return ECB_OK;
     }
     return set_err(ctx, ECB_ERR_INVALID_ARG, std::string("unknown option ") + key);
@@ -313,6 +318,55 @@ int ecb_wei_mul_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, const void
     CU(cudaSetDevice(d->dev));
     return dev_wei_mul(ctx, *d, curve, (const u32*)d_k, (const u32*)d_xy, nullptr, n, (u32*)d_out, (unsigned char*)d_inf,
                        (cudaStream_t)stream);
+}
+int ecb_x448_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_x448(ctx, *d, (const u32*)d_k, (const u32*)d_u, n, (u32*)d_out, (cudaStream_t)stream);
+}
+int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int di, const void* d_a, const void* d_r, const void* d_s, const void* d_k,
+                                     size_t n, void* d_ok, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_ed25519_verify(ctx, *d, (const u32*)d_a, (const u32*)d_r, (const u32*)d_s, (const u32*)d_k, n,
+                              (unsigned char*)d_ok, (cudaStream_t)stream);
+}
+int ecb_ecdsa_verify_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_q, const void* d_z, const void* d_rs, size_t n,
+                                void* d_ok, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    if (curve == ECB_CURVE_P256R1)
+        return dev_ecdsa_p256(ctx, *d, (const u32*)d_q, (const u32*)d_z, (const u32*)d_rs, n, (unsigned char*)d_ok, (cudaStream_t)stream);
+    if (curve == ECB_CURVE_P384R1)
+        return dev_ecdsa_p384(ctx, *d, (const u32*)d_q, (const u32*)d_z, (const u32*)d_rs, n, (unsigned char*)d_ok, (cudaStream_t)stream);
+    return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+}
+int ecb_profile_collect(ecb_ctx* ctx, int di, double* main_ms, double* fin_ms, int* calls) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    double m = 0, f = 0;
+    int c = 0;
+    for (auto& r : d->prof) {
+        float t1 = 0, t2 = 0;
+        CU(cudaEventSynchronize(r.c));
+        CU(cudaEventElapsedTime(&t1, r.a, r.b));
+        CU(cudaEventElapsedTime(&t2, r.b, r.c));
+        m += t1;
+        f += t2;
+        c++;
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+        cudaEventDestroy(r.c);
+    }
+    d->prof.clear();
+    if (main_ms) *main_ms = m;
+    if (fin_ms) *fin_ms = f;
+    if (calls) *calls = c;
+    return ECB_OK;
 }
 int ecb_dev_status(ecb_ctx* ctx, int di, size_t* bad_index) {
     DevCtx* d = get_dev(ctx, di);

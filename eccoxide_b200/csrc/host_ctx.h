@@ -36,6 +36,10 @@ struct DevCtx {
     u32* ed_table = nullptr;
     int ed_w = 0, ed_nwin = 0;
     std::mutex mu;
+    // optional per-kernel timing (ecb_set_option "profile"): events recorded on the launching stream
+    // around the scalar-mult kernel(s) [a,b] and the batch-inversion finisher [b,c] of every call
+    struct ProfRec { cudaEvent_t a, b, c; };
+    std::vector<ProfRec> prof;
 };
 
 struct ecb_ctx {
@@ -44,6 +48,7 @@ struct ecb_ctx {
     std::mutex err_mu;
     long opt_ed_w = 8;
     size_t opt_chunk = (size_t)1 << 20;
+    long opt_profile = 0;
     std::atomic<unsigned long long> launches{0};
 };
 
@@ -106,3 +111,19 @@ static inline int reset_status(ecb_ctx* ctx, DevCtx& d, cudaStream_t s) {
     return ECB_OK;
 }
 
+
+// profiling marks: call prof_begin before the main kernel(s), prof_mid between them and the
+// finisher, prof_end after it.  No-ops unless the "profile" option is set.
+static inline void prof_mark(ecb_ctx* ctx, DevCtx& d, cudaStream_t s, int which) {
+    if (!ctx->opt_profile) return;
+    if (which == 0) {
+        DevCtx::ProfRec r;
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventCreate(&r.c);
+        d.prof.push_back(r);
+        cudaEventRecord(r.a, s);
+    } else if (!d.prof.empty()) {
+        cudaEventRecord(which == 1 ? d.prof.back().b : d.prof.back().c, s);
+    }
+}

@@ -50,15 +50,21 @@ int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32*
     TRY(ensure(ctx, d.pf, n * 8 * sizeof(u32)));
     TRY(reset_status(ctx, d, s));
     u32* planes = (u32*)d.planes.p;
+    prof_mark(ctx, d, s, 0);
     k_ed25519_mul_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, planes, d.d_status);
     ctx->launches++;
     CU(cudaGetLastError());
+    prof_mark(ctx, d, s, 1);
+    int rc;
     if (compressed) {
         FinEdCompressed fin{planes, n, d_out};
-        return launch_batch_inv<F25519, FinEdCompressed>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+        rc = launch_batch_inv<F25519, FinEdCompressed>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    } else {
+        FinEdXY fin{planes, n, d_out};
+        rc = launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
     }
-    FinEdXY fin{planes, n, d_out};
-    return launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    prof_mark(ctx, d, s, 2);
+    return rc;
 }
 
 int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_out, cudaStream_t s) {
@@ -68,11 +74,15 @@ int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, siz
     TRY(ensure(ctx, d.scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
     TRY(reset_status(ctx, d, s));
     u32* planes = (u32*)d.planes.p;
+    prof_mark(ctx, d, s, 0);
     k_ed25519_mul<<<g, ECB_TPB, 0, s>>>(n, d_k, d_p, (u32*)d.scratch.p, planes, d.d_status);
     ctx->launches++;
     CU(cudaGetLastError());
+    prof_mark(ctx, d, s, 1);
     FinEdXY fin{planes, n, d_out};
-    return launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    int rc = launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    prof_mark(ctx, d, s, 2);
+    return rc;
 }
 
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
@@ -80,8 +90,11 @@ int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, cons
     if (!d.ed_table || d.ed_w != (int)ctx->opt_ed_w) TRY(dev_ed25519_build_table(ctx, d, (int)ctx->opt_ed_w));
     unsigned g = persistent_grid(d, k_ed25519_verify, n);
     TRY(ensure(ctx, d.scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
+    prof_mark(ctx, d, s, 0);
     k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, r, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, (u32*)d.scratch.p, ok);
     ctx->launches++;
     CU(cudaGetLastError());
+    prof_mark(ctx, d, s, 1);
+    prof_mark(ctx, d, s, 2);
     return ECB_OK;
 }

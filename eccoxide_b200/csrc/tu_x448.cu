@@ -11,9 +11,13 @@ int dev_x448(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_u, size_t n, 
     TRY(ensure(ctx, d.planes, n * 3 * 14 * sizeof(u32)));
     TRY(ensure(ctx, d.pf, n * 14 * sizeof(u32)));
     u32* planes = (u32*)d.planes.p;
+    prof_mark(ctx, d, s, 0);
     k_x448<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d_u, planes);
     ctx->launches++;
     CU(cudaGetLastError());
+    prof_mark(ctx, d, s, 1);
     FinX448 fin{planes, n, d_out};
-    return launch_batch_inv<F448, FinX448>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    int rc = launch_batch_inv<F448, FinX448>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    prof_mark(ctx, d, s, 2);
+    return rc;
 }

@@ -55,7 +55,8 @@ void ecb_destroy(ecb_ctx* ctx);
 const char* ecb_last_error(ecb_ctx* ctx);
 int ecb_device_count(ecb_ctx* ctx);
 /* tunables, before first use: "ed25519_comb_w" (window width of the fixed-base comb, 4..16),
- * "chunk" (elements per device pass) */
+ * "chunk" (elements per device pass), "profile" (1: record CUDA events around the kernels of
+ * every call on the launching stream, read back with ecb_profile_collect) */
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 unsigned long long ecb_launch_count(ecb_ctx* ctx);
@@ -111,14 +112,22 @@ int ecb_ed25519_mul_dev(ecb_ctx* ctx, int dev_index, const void* d_k_le, const v
 int ecb_x25519_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);
 int ecb_wei_mul_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_k_be, const void* d_xy_be, size_t n,
                     void* d_out_xy_be, void* d_out_inf, void* stream);
+int ecb_x448_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);
+int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int dev_index, const void* d_a_enc, const void* d_r_enc, const void* d_s_le,
+                                     const void* d_k_le, size_t n, void* d_ok, void* stream);
+int ecb_ecdsa_verify_hashed_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_q_xy_be, const void* d_z_be,
+                                const void* d_rs_be, size_t n, void* d_ok, void* stream);
 /* after a *_dev call and a stream sync: 0, or the error of the first invalid element */
 int ecb_dev_status(ecb_ctx* ctx, int dev_index, size_t* bad_index);
 
 /* ---- measurement helpers ----------------------------------------------------------------- */
 /* Integer-pipe peak probe.  variant: 0 = IMAD (32-bit), 1 = IMAD.WIDE.U32, 2 = IMAD.WIDE.U32.X carry
- * chains (the field kernels' instruction), 3 = IMAD.HI.U32.  Returns multiply-accumulates per second
+ * chains (the field kernels' instruction), 3 = IMAD.HI.U32, 4 = DFMA, 5 = integer add/logic.  Returns multiply-accumulates per second
  * on device `dev_index` and the kernel time. */
 int ecb_imad_probe(ecb_ctx* ctx, int dev_index, int variant, int iters, double* macs_per_s, double* ms);
+/* with option "profile" = 1: sum over the calls since the last collect of the device time (ms) of
+ * the scalar-multiplication kernel(s) and of the batch-inversion / encoding kernel; synchronises. */
+int ecb_profile_collect(ecb_ctx* ctx, int dev_index, double* main_ms, double* finish_ms, int* calls);
 /* debug: copy the device's Ed25519 comb table (niels entries, 96 B each) to host; returns entries */
 long ecb_debug_ed25519_table(ecb_ctx* ctx, int dev_index, uint8_t* out, size_t cap_bytes, int* w, int* nwin);
 

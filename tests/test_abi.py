@@ -1,0 +1,62 @@
+"""The drop-in boundary: libeccbatch.so loads and exports exactly what include/eccbatch.h declares.
+
+CPU only — no compute calls (there is no CPU fallback to call).
+"""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+    src = open(os.path.join(ROOT, "include", "eccbatch.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(ecb_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_documented_surface():
+    fns = header_functions()
+    for must in ("ecb_init", "ecb_destroy", "ecb_ed25519_mul_base", "ecb_ed25519_mul", "ecb_x25519", "ecb_x448", "ecb_wei_mul",
+                 "ecb_wei_mul_base", "ecb_ecdsa_verify_hashed", "ecb_ed25519_verify_prehashed", "ecb_ed25519_mul_base_dev"):
+        assert must in fns
+
+
+def test_library_exports_every_declared_symbol():
+    from eccoxide_b200 import _lib
+
+    if not os.path.exists(_lib.LIB_PATH):
+        pytest.fail("libeccbatch.so not built: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in header_functions():
+        assert hasattr(lib, name), "missing export %s" % name
+
+
+def test_python_binding_covers_the_header_exactly():
+    from eccoxide_b200 import _lib
+
+    assert sorted(_lib.SIGNATURES) == header_functions()
+    _lib.load()
+
+
+def test_no_cuda_device_means_error_not_fallback():
+    """Without a GPU every entry point must fail loudly (ECB_ERR_CUDA); nothing is computed on the host."""
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    from eccoxide_b200 import Context, EccBatchError
+
+    with pytest.raises(EccBatchError):
+        Context()
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "eccoxide_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
+                txt = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in txt.replace("test oracle", "").lower() or f in (), "%s mentions the oracle" % f

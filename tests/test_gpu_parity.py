@@ -1,0 +1,471 @@
+"""Parity of the CUDA path with the reference (through the oracle), all through the C ABI.
+
+Every test calls libeccbatch.so via eccoxide_b200.Context (ctypes, one C-ABI call per method) on
+cuda:0 and compares byte for byte with
+  - the reference's golden vectors (tests/golden/reference_vectors.json),
+  - oracle/ecc_oracle.c / oracle/pyref.py on the same seeded inputs (small sizes),
+  - size-independent properties at BASELINE.json's full batch sizes (sampled oracle check,
+    homomorphism, DH commutativity, fixed-base == variable-base on the generator).
+Bar: bit-exact (integer / byte work).
+"""
+import hashlib
+
+import numpy as np
+import pytest
+
+from helpers import (SEEDS, ecdsa_batch, ed25519_sig_batch, ed_edge_scalars, ed_points, rand_bytes, rng, rows, scalars_mod,
+                     wei_edge_scalars, wei_points)
+from oracle import pyref as R
+
+pytestmark = pytest.mark.gpu
+H = bytes.fromhex
+CURVES = ("p256r1", "p384r1", "bls12_381_g1")
+NT = None
+
+
+def threads(coracle):
+    return coracle.default_threads()
+
+
+# ---- library / device sanity -----------------------------------------------------------------
+def test_native_library_is_loaded_and_counts_launches(ctx):
+    import eccoxide_b200._lib as L
+
+    assert L._lib is not None and L.LIB_PATH.endswith("libeccbatch.so")
+    before = ctx.launch_count()
+    ctx.ed25519_mul_base(rows([(5).to_bytes(32, "little")]))
+    assert ctx.launch_count() >= before + 2  # scalar-mult kernel + batch inversion
+
+
+def test_imad_probe_reports_a_plausible_peak(ctx):
+    lo, _ = ctx.imad_probe(0, 512)
+    wide, _ = ctx.imad_probe(2, 512)
+    assert 5e12 < lo < 40e12 and 2e12 < wide < 40e12
+
+
+# ---- Ed25519 fixed base (config 1) --------------------------------------------------------------
+def test_ed25519_mul_base_golden_and_edges(ctx, golden, coracle):
+    ks = []
+    for v in golden["ed25519_rfc8032"]:
+        h = bytearray(hashlib.sha512(H(v["seed"])).digest()[:32])
+        h[0] &= 248; h[31] &= 127; h[31] |= 64
+        ks.append((int.from_bytes(h, "little") % R.L25519).to_bytes(32, "little"))
+    enc = ctx.ed25519_mul_base(rows(ks), compressed=True)
+    assert [enc[i].tobytes().hex() for i in range(3)] == [v["public"] for v in golden["ed25519_rfc8032"]]
+    vals = ed_edge_scalars(golden)
+    kb = rows([v.to_bytes(32, "little") for v in vals])
+    got = ctx.ed25519_mul_base(kb)
+    assert np.array_equal(got, coracle.ed25519_mul_base(kb))
+    assert got[0].tobytes() == (0).to_bytes(32, "little") + (1).to_bytes(32, "little")
+    for i in (1, 5, len(vals) - 1):
+        assert got[i].tobytes() == R.ed25519_mul_base_xy(kb[i].tobytes())
+
+
+@pytest.mark.parametrize("w", [4, 5, 8, 11])
+def test_ed25519_mul_base_every_comb_width(w, coracle, golden):
+    """The comb width is a tunable of the GPU schedule; results must not depend on it."""
+    from eccoxide_b200 import Context
+
+    g = rng(SEEDS["ed25519"] + w)
+    kb = np.concatenate([scalars_mod(g, 600, R.L25519, 32, "little"), rows([v.to_bytes(32, "little") for v in ed_edge_scalars(golden)])])
+    with Context(ed25519_comb_w=w) as c:
+        assert np.array_equal(c.ed25519_mul_base(kb), coracle.ed25519_mul_base(kb, threads(coracle)))
+        table, tw, nwin = c.debug_ed25519_table()
+        assert tw == w and table.shape[0] == nwin << (w - 1)
+        # table entry (i, j) = niels(j * 2^(w i) * B): check a few against the big-int oracle
+        for (i, j) in ((0, 1), (1, 2), (nwin - 1, 1), (2, 1 << (w - 1))):
+            x, y = R.ed_mul(j << (w * i), R.ED_B)
+            p = R.P25519
+            exp = ((y + x) % p).to_bytes(32, "little") + ((y - x) % p).to_bytes(32, "little") + (2 * R.ED_D * x * y % p).to_bytes(32, "little")
+            assert table[i * (1 << (w - 1)) + j - 1].tobytes() == exp
+
+
+def test_ed25519_mul_base_config1_full_batch(ctx, coracle):
+    """Config 1 at full size (2^16 random scalars): 100 % against the C oracle, plus libsodium sample."""
+    g = rng(SEEDS["ed25519"])
+    kb = scalars_mod(g, 1 << 16, R.L25519, 32, "little")
+    got = ctx.ed25519_mul_base(kb)
+    assert np.array_equal(got, coracle.ed25519_mul_base(kb, threads(coracle)))
+    enc = ctx.ed25519_mul_base(kb[:2048], compressed=True)
+    nb = pytest.importorskip("nacl.bindings")
+    for i in range(0, 2048, 64):
+        if any(kb[i]):
+            assert enc[i].tobytes() == nb.crypto_scalarmult_ed25519_base_noclamp(kb[i].tobytes())
+    # compressed == encode(affine)
+    for i in range(0, 2048, 97):
+        x = int.from_bytes(got[i, :32].tobytes(), "little"); y = int.from_bytes(got[i, 32:].tobytes(), "little")
+        assert enc[i].tobytes() == R.ed_encode((x, y))
+
+
+def test_ed25519_mul_base_large_batch_properties(ctx, coracle):
+    """2^20 scalars: sampled oracle check + homomorphism (a+b)B = aB + bB on the outputs."""
+    g = rng(SEEDS["ed25519"] + 1)
+    n = 1 << 20
+    kb = rand_bytes(g, n, 32)
+    kb[:, 31] &= 0x0F
+    got = ctx.ed25519_mul_base(kb)
+    idx = g.integers(0, n, size=4096)
+    assert np.array_equal(got[idx], coracle.ed25519_mul_base(kb[idx], threads(coracle)))
+    for i in range(0, 64, 2):
+        a, b = int.from_bytes(kb[i].tobytes(), "little"), int.from_bytes(kb[i + 1].tobytes(), "little")
+        pa = (int.from_bytes(got[i, :32].tobytes(), "little"), int.from_bytes(got[i, 32:].tobytes(), "little"))
+        pb = (int.from_bytes(got[i + 1, :32].tobytes(), "little"), int.from_bytes(got[i + 1, 32:].tobytes(), "little"))
+        assert R.ed_add(pa, pb) == R.ed_mul((a + b) % R.L25519, R.ED_B)
+
+
+def test_ed25519_noncanonical_scalar_is_reported(ctx):
+    from eccoxide_b200 import EccBatchError
+
+    kb = rows([(7).to_bytes(32, "little")] * 300)
+    kb = kb.copy()
+    kb[123] = np.frombuffer(R.L25519.to_bytes(32, "little"), dtype=np.uint8)
+    kb[200] = 0xFF
+    with pytest.raises(EccBatchError) as e:
+        ctx.ed25519_mul_base(kb)
+    assert e.value.code == -3 and e.value.bad_index == 123
+
+
+def test_empty_batches(ctx):
+    assert ctx.ed25519_mul_base(np.zeros((0, 32), dtype=np.uint8)).shape == (0, 64)
+    assert ctx.x25519(np.zeros((0, 32), dtype=np.uint8), np.zeros((0, 32), dtype=np.uint8)).shape == (0, 32)
+    out, inf = ctx.wei_mul("p256r1", np.zeros((0, 32), dtype=np.uint8), np.zeros((0, 64), dtype=np.uint8))
+    assert out.shape == (0, 64) and inf.shape == (0,)
+
+
+@pytest.mark.parametrize("n", [1, 2, 31, 33, 127, 129, 1000])
+def test_ragged_batch_sizes(ctx, coracle, n):
+    g = rng(n)
+    kb = scalars_mod(g, n, R.L25519, 32, "little")
+    assert np.array_equal(ctx.ed25519_mul_base(kb), coracle.ed25519_mul_base(kb))
+    k, u = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
+    assert np.array_equal(ctx.x25519(k, u), coracle.x25519(k, u))
+
+
+# ---- Ed25519 variable base ------------------------------------------------------------------------
+def test_ed25519_mul_variable_base(ctx, golden, coracle):
+    g = rng(SEEDS["ed25519"] + 2)
+    vals = ed_edge_scalars(golden)
+    kb = np.concatenate([rows([v.to_bytes(32, "little") for v in vals]), scalars_mod(g, 1000, R.L25519, 32, "little")])
+    pts = ed_points(g, kb.shape[0])
+    # a few special points: identity, the order-2 point (0,-1), an order-4 point (sqrt(-1), 0), an order-8 point
+    special = [(0, 1), (0, R.P25519 - 1), (R.SQRT_M1, 0)]
+    for i, (x, y) in enumerate(special):
+        pts[i] = np.frombuffer(x.to_bytes(32, "little") + y.to_bytes(32, "little"), dtype=np.uint8)
+    got = ctx.ed25519_mul(kb, pts)
+    assert np.array_equal(got, coracle.ed25519_mul(kb, pts, threads(coracle)))
+    for i in (0, 1, 2, 30, 500):
+        assert got[i].tobytes() == R.ed25519_mul_xy(kb[i].tobytes(), pts[i].tobytes())
+    # mul_base_matches_scale (curve25519.rs:1374)
+    gpt = np.tile(np.frombuffer(R.ED_BX.to_bytes(32, "little") + R.ED_BY.to_bytes(32, "little"), dtype=np.uint8), (kb.shape[0], 1))
+    assert np.array_equal(ctx.ed25519_mul(kb, gpt), ctx.ed25519_mul_base(kb))
+
+
+def test_ed25519_mul_rejects_bad_points(ctx):
+    from eccoxide_b200 import EccBatchError
+
+    good = R.ED_BX.to_bytes(32, "little") + R.ED_BY.to_bytes(32, "little")
+    pts = rows([good] * 50).copy()
+    pts[17, 0] ^= 1
+    with pytest.raises(EccBatchError) as e:
+        ctx.ed25519_mul(rows([(3).to_bytes(32, "little")] * 50), pts)
+    assert e.value.code == -4 and e.value.bad_index == 17
+    # non-canonical coordinate (x + p) is rejected like FieldElement::from_bytes does
+    pts = rows([good] * 4).copy()
+    pts[2, :32] = np.frombuffer((R.ED_BX + R.P25519).to_bytes(32, "little"), dtype=np.uint8)
+    with pytest.raises(EccBatchError) as e:
+        ctx.ed25519_mul(rows([(3).to_bytes(32, "little")] * 4), pts)
+    assert e.value.bad_index == 2
+
+
+# ---- X25519 (config 2) ------------------------------------------------------------------------------
+def test_x25519_golden_and_edges(ctx, golden, coracle):
+    v = golden["x25519"]
+    ks = [H(e["k"]) for e in v["rfc7748_5_2"]] + [H(v["iterated_once"]["k"])]
+    us = [H(e["u"]) for e in v["rfc7748_5_2"]] + [(9).to_bytes(32, "little")]
+    rs = [H(e["r"]) for e in v["rfc7748_5_2"]] + [H(v["iterated_once"]["r"])]
+    nine = (9).to_bytes(32, "little")
+    a, b = H(v["dh_6_1"]["a"]), H(v["dh_6_1"]["b"])
+    pubs = ctx.x25519(rows([a, b]), rows([nine, nine]))
+    ks += [a, b]; us += [pubs[1].tobytes(), pubs[0].tobytes()]; rs += [H(v["dh_6_1"]["shared"])] * 2
+    assert np.array_equal(ctx.x25519(rows(ks), rows(us)), rows(rs))
+    p = R.P25519
+    g = rng(1)
+    eus = [0, 1, p - 1, p, p + 1, 2**255 - 1, 2**256 - 1, 9 | 1 << 255,
+           325606250916557431795983626356110631294008115727848805560023387167927233504,
+           39382357235489614581723060781553021112529911719440698176882885853963445705823]
+    eus = rows([x.to_bytes(32, "little") for x in eus])
+    eks = rand_bytes(g, eus.shape[0], 32)
+    got = ctx.x25519(eks, eus)
+    assert np.array_equal(got, coracle.x25519(eks, eus))
+    assert not got[0].any() and not got[1].any() and not got[3].any()  # low-order inputs -> zero output
+
+
+def test_x25519_config2_full_batch(ctx, coracle):
+    """Config 2 at full size (2^20 pairs): sampled 2^14 oracle check, libsodium sample, DH commutativity."""
+    g = rng(SEEDS["x25519"])
+    n = 1 << 20
+    k, u = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
+    got = ctx.x25519(k, u)
+    idx = np.concatenate([np.arange(4096), g.integers(0, n, size=12288)])
+    assert np.array_equal(got[idx], coracle.x25519(k[idx], u[idx], threads(coracle)))
+    nb = pytest.importorskip("nacl.bindings")
+    for i in range(0, 2048, 32):
+        try:
+            assert got[i].tobytes() == nb.crypto_scalarmult(k[i].tobytes(), u[i].tobytes())
+        except Exception:
+            assert not got[i].any()
+    # DH: x25519(a, x25519(b, 9)) == x25519(b, x25519(a, 9))
+    m = 1 << 12
+    nine = np.tile(np.frombuffer((9).to_bytes(32, "little"), dtype=np.uint8), (m, 1))
+    pa, pb = ctx.x25519(k[:m], nine), ctx.x25519(u[:m], nine)
+    assert np.array_equal(ctx.x25519(k[:m], pb), ctx.x25519(u[:m], pa))
+
+
+def test_x448(ctx, golden, coracle):
+    v = golden["x448"]
+    ks = [H(e["k"]) for e in v["rfc7748_5_2"]]
+    us = [H(e["u"]) for e in v["rfc7748_5_2"]]
+    rs = [H(e["r"]) for e in v["rfc7748_5_2"]]
+    d = v["dh_6_2"]
+    five = (5).to_bytes(56, "little")
+    ks += [H(d["a"]), H(d["b"]), H(d["a"])]; us += [five, five, H(d["b_pub"])]; rs += [H(d["a_pub"]), H(d["b_pub"]), H(d["shared"])]
+    assert np.array_equal(ctx.x448(rows(ks), rows(us)), rows(rs))
+    g = rng(SEEDS["sweep"])
+    n = 3000
+    k, u = rand_bytes(g, n, 56), rand_bytes(g, n, 56)
+    u[0] = 0; u[1] = 0xFF; u[2] = np.frombuffer(R.P448.to_bytes(56, "little"), dtype=np.uint8)
+    u[3] = np.frombuffer((1).to_bytes(56, "little"), dtype=np.uint8)
+    assert np.array_equal(ctx.x448(k, u), coracle.x448(k, u, threads(coracle)))
+
+
+# ---- Weierstrass variable base (configs 3a, 4, 5) -----------------------------------------------------
+@pytest.mark.parametrize("curve,key", [("p256r1", "nist_p256"), ("p384r1", "nist_p384")])
+def test_wei_nist_kats(ctx, golden, curve, key):
+    c = R.WCURVES[curve]
+    kats = golden[key]
+    ks = rows([int(v["k"], 16).to_bytes(c.sbytes, "big") for v in kats])
+    exp = rows([int(v["x"], 16).to_bytes(c.fbytes, "big") + int(v["y"], 16).to_bytes(c.fbytes, "big") for v in kats])
+    gpt = np.tile(np.frombuffer(c.enc(c.G), dtype=np.uint8), (len(kats), 1))
+    out, inf = ctx.wei_mul(curve, ks, gpt)
+    assert not inf.any() and np.array_equal(out, exp)
+    out, inf = ctx.wei_mul_base(curve, ks)
+    assert not inf.any() and np.array_equal(out, exp)
+
+
+def test_bls_g1_kats(ctx, golden):
+    c = R.BLSG1
+    for ent in golden["bls12_381_g1"]["uncompressed"]:
+        out, inf = ctx.wei_mul_base("bls12_381_g1", rows([ent["k"].to_bytes(32, "big")]))
+        assert out[0].tobytes().hex() == ent["bytes"] and not inf[0]
+    for ent in golden["bls12_381_g1"]["compressed"]:
+        out, _ = ctx.wei_mul("bls12_381_g1", rows([ent["k"].to_bytes(32, "big")]), rows([c.enc(c.G)]))
+        x, y = c.dec(out[0].tobytes())
+        b = bytearray(x.to_bytes(48, "big")); b[0] |= 0x80 | (0x20 if y > (c.p - 1) // 2 else 0)
+        assert bytes(b).hex() == ent["bytes"]
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_wei_mul_random_and_edges(ctx, golden, coracle, curve):
+    c = R.WCURVES[curve]
+    g = rng(SEEDS["p256"] + len(curve))
+    vals = wei_edge_scalars(golden, c.n)
+    kb = np.concatenate([rows([v.to_bytes(c.sbytes, "big") for v in vals]), scalars_mod(g, 1500, c.n, c.sbytes, "big")])
+    pts = wei_points(curve, g, kb.shape[0])
+    got, inf = ctx.wei_mul(curve, kb, pts)
+    exp, einf = coracle.wei_mul(curve, kb, pts, nthreads=threads(coracle))
+    assert np.array_equal(got, exp) and np.array_equal(inf, einf)
+    assert inf[0] and not got[0].any()  # k = 0 -> identity flag, zero bytes
+    for i in (1, 17, 40):
+        assert (got[i].tobytes(), int(inf[i])) == R.wei_mul(c, kb[i].tobytes(), pts[i].tobytes())
+    # fixed base == variable base on the generator (mul_base_matches_generic, completeness.rs:97)
+    gb, gi = ctx.wei_mul_base(curve, kb)
+    gv, gvi = ctx.wei_mul(curve, kb, np.tile(np.frombuffer(c.enc(c.G), dtype=np.uint8), (kb.shape[0], 1)))
+    assert np.array_equal(gb, gv) and np.array_equal(gi, gvi)
+    eb, ebi = coracle.wei_mul_base(curve, kb[:200], threads(coracle))
+    assert np.array_equal(gb[:200], eb) and np.array_equal(gi[:200], ebi)
+    # identity inputs
+    out, oinf = ctx.wei_mul(curve, kb[:64], pts[:64], inf_in=np.ones(64, dtype=np.uint8))
+    assert oinf.all() and not out.any()
+    # k = n - 1 gives -P
+    km1 = rows([(c.n - 1).to_bytes(c.sbytes, "big")] * 8)
+    out, _ = ctx.wei_mul(curve, km1, pts[:8])
+    for i in range(8):
+        x, y = c.dec(pts[i].tobytes())
+        assert out[i].tobytes() == c.enc((x, (-y) % c.p))
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_wei_mul_rejects_bad_inputs(ctx, curve):
+    from eccoxide_b200 import EccBatchError
+
+    c = R.WCURVES[curve]
+    good = c.enc(c.G)
+    one = (1).to_bytes(c.sbytes, "big")
+    pts = rows([good] * 40).copy()
+    pts[9, -1] ^= 1
+    with pytest.raises(EccBatchError) as e:
+        ctx.wei_mul(curve, rows([one] * 40), pts)
+    assert e.value.code == -4 and e.value.bad_index == 9
+    ks = rows([one] * 40).copy()
+    ks[33] = np.frombuffer(c.n.to_bytes(c.sbytes, "big"), dtype=np.uint8)
+    with pytest.raises(EccBatchError) as e:
+        ctx.wei_mul(curve, ks, rows([good] * 40))
+    assert e.value.code == -3 and e.value.bad_index == 33
+    # x >= p is non-canonical
+    pts = rows([good] * 3).copy()
+    pts[1, : c.fbytes] = np.frombuffer((c.p + 1).to_bytes(c.fbytes, "big"), dtype=np.uint8) if c.p + 1 < 1 << (8 * c.fbytes) else pts[1, : c.fbytes]
+    if c.p + 1 < 1 << (8 * c.fbytes):
+        with pytest.raises(EccBatchError):
+            ctx.wei_mul(curve, rows([one] * 3), pts)
+
+
+def test_bls_off_subgroup_points(ctx, coracle):
+    c = R.BLSG1
+    pts, x = [], 1
+    while len(pts) < 6:
+        x += 1
+        rhs = (x**3 + 4) % c.p
+        y = pow(rhs, (c.p + 1) // 4, c.p)
+        if y * y % c.p == rhs:
+            pts.append((x, y))
+    g = rng(5)
+    kb = scalars_mod(g, len(pts), c.n, 32, "big")
+    pb = rows([c.enc(p) for p in pts])
+    got, inf = ctx.wei_mul("bls12_381_g1", kb, pb)
+    exp, einf = coracle.wei_mul("bls12_381_g1", kb, pb)
+    assert np.array_equal(got, exp) and np.array_equal(inf, einf)
+
+
+def test_p256_config3a_large_batch(ctx, coracle):
+    """Config 3a at 2^18 (CI-sized; bench.py runs 2^20): sampled oracle + OpenSSL ECDH + distributivity."""
+    c = R.P256
+    g = rng(SEEDS["p256"])
+    n = 1 << 18
+    kb = rand_bytes(g, n, 32)
+    kb[:, 0] &= 0x7F
+    uniq, _ = ctx.wei_mul_base("p256r1", kb[:4096])
+    pts = np.tile(uniq, (n // 4096, 1))
+    got, inf = ctx.wei_mul("p256r1", kb, pts)
+    idx = g.integers(0, n, size=2048)
+    exp, einf = coracle.wei_mul("p256r1", kb[idx], pts[idx], nthreads=threads(coracle))
+    assert np.array_equal(got[idx], exp) and np.array_equal(inf[idx], einf)
+    # k*(t*G) == (k*t mod n)*G
+    for i in range(8):
+        k, t = int.from_bytes(kb[i].tobytes(), "big"), int.from_bytes(kb[i % 4096].tobytes(), "big")
+        assert got[i].tobytes() == c.enc(c.mul(k * t % c.n, c.G))
+    ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
+    for i in range(4):
+        priv = ec.derive_private_key(int.from_bytes(kb[i].tobytes(), "big"), ec.SECP256R1())
+        x, y = c.dec(pts[i].tobytes())
+        peer = ec.EllipticCurvePublicNumbers(x, y, ec.SECP256R1()).public_key()
+        assert priv.exchange(ec.ECDH(), peer) == got[i, :32].tobytes()
+
+
+# ---- ECDSA verify (config 3b) ------------------------------------------------------------------------
+@pytest.mark.parametrize("curve", ["p256r1", "p384r1"])
+def test_ecdsa_rfc6979_and_synthetic(ctx, golden, coracle, curve):
+    c, v = R.WCURVES[curve], golden["ecdsa_rfc6979"][curve]
+    Q = c.enc((int(v["qx"], 16), int(v["qy"], 16)))
+    Qs, Zs, RSs, exp = [], [], [], []
+    for kat in v["kats"]:
+        z = R.ecdsa_digest_to_scalar(c, hashlib.new(kat["alg"], kat["message"].encode()).digest())
+        rs = int(kat["r"], 16).to_bytes(c.sbytes, "big") + int(kat["s"], 16).to_bytes(c.sbytes, "big")
+        for tamper in range(3):
+            z2, rs2 = bytearray(z), bytearray(rs)
+            if tamper == 1:
+                z2[-1] ^= 1
+            if tamper == 2:
+                rs2[-1] ^= 1
+            Qs.append(Q); Zs.append(bytes(z2)); RSs.append(bytes(rs2)); exp.append(tamper == 0)
+    assert ctx.ecdsa_verify_hashed(curve, rows(Qs), rows(Zs), rows(RSs)).tolist() == exp
+    g = rng(SEEDS["p256"] + 7)
+    q, z, rs = ecdsa_batch(curve, g, 600)
+    got = ctx.ecdsa_verify_hashed(curve, q, z, rs)
+    want = coracle.ecdsa_verify_hashed(curve, q, z, rs, threads(coracle))
+    assert np.array_equal(got, want)
+    assert got.sum() > 300 and (~got).sum() > 100
+    for i in (0, 1, 5, 7, 11, 13):
+        assert bool(got[i]) == R.ecdsa_verify_hashed(c, q[i].tobytes(), z[i].tobytes(), rs[i].tobytes())
+
+
+def test_ecdsa_p256_openssl_signatures(ctx):
+    ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric.utils import decode_dss_signature
+
+    c = R.P256
+    Qs, Zs, RSs, exp = [], [], [], []
+    for i in range(48):
+        key = ec.generate_private_key(ec.SECP256R1())
+        msg = b"block %d" % i
+        r, s = decode_dss_signature(key.sign(msg, ec.ECDSA(hashes.SHA256())))
+        pn = key.public_key().public_numbers()
+        z = bytearray(hashlib.sha256(msg).digest())
+        if i % 6 == 5:
+            z[0] ^= 0x80
+        Qs.append(c.enc((pn.x, pn.y))); Zs.append(bytes(z)); RSs.append(r.to_bytes(32, "big") + s.to_bytes(32, "big")); exp.append(i % 6 != 5)
+    assert ctx.ecdsa_verify_hashed("p256r1", rows(Qs), rows(Zs), rows(RSs)).tolist() == exp
+
+
+def test_ecdsa_off_curve_key_fails_the_call(ctx):
+    from eccoxide_b200 import EccBatchError
+
+    c = R.P256
+    q = rows([c.enc(c.G)] * 10).copy()
+    q[4, 5] ^= 2
+    one = (1).to_bytes(32, "big")
+    with pytest.raises(EccBatchError) as e:
+        ctx.ecdsa_verify_hashed("p256r1", q, rows([one] * 10), rows([one + one] * 10))
+    assert e.value.code == -4 and e.value.bad_index == 4
+
+
+# ---- Ed25519 verify -------------------------------------------------------------------------------------
+def test_ed25519_verify(ctx, golden, coracle):
+    A, Rr, S, K, exp = [], [], [], [], []
+    for v in golden["ed25519_rfc8032"]:
+        pub, msg, sig = H(v["public"]), H(v["message"]), H(v["signature"])
+        for tamper in (False, True):
+            s2 = bytearray(sig)
+            if tamper:
+                s2[33] ^= 1
+            A.append(pub); Rr.append(bytes(s2[:32])); S.append(bytes(s2[32:])); K.append(R.ed25519_hash_k(bytes(s2[:32]), pub, msg)); exp.append(not tamper)
+    assert ctx.ed25519_verify_prehashed(rows(A), rows(Rr), rows(S), rows(K)).tolist() == exp
+    g = rng(99)
+    a, r, s, k = ed25519_sig_batch(g, 400)
+    # decode_point rejections: non-canonical y, x = 0 with sign bit, not on curve
+    a = a.copy(); r = r.copy()
+    a[20] = np.frombuffer(R.P25519.to_bytes(32, "little"), dtype=np.uint8)
+    a[21] = np.frombuffer((1 | 1 << 255).to_bytes(32, "little"), dtype=np.uint8)
+    r[22] = np.frombuffer((2).to_bytes(32, "little"), dtype=np.uint8)
+    got = ctx.ed25519_verify_prehashed(a, r, s, k)
+    want = coracle.ed25519_verify_prehashed(a, r, s, k, threads(coracle))
+    assert np.array_equal(got, want)
+    assert got.sum() > 100 and (~got).sum() > 100 and not got[20] and not got[21] and not got[9]
+    for i in (0, 1, 2, 3, 9, 20):
+        assert bool(got[i]) == R.ed25519_verify_prehashed(a[i].tobytes(), r[i].tobytes(), s[i].tobytes(), k[i].tobytes())
+
+
+# ---- device-resident entry points ---------------------------------------------------------------------
+def test_device_resident_entry_points_match_host_entry_points(ctx):
+    torch = pytest.importorskip("torch")
+    g = rng(4242)
+    n = 5000
+    kb = scalars_mod(g, n, R.L25519, 32, "little")
+    d_k = torch.from_numpy(kb).cuda()
+    d_out = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), n, d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert ctx.dev_status(0) == (0, None)
+    assert np.array_equal(d_out.cpu().numpy(), ctx.ed25519_mul_base(kb))
+    k, u = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
+    d_o = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
+    ctx.dev_call("ecb_x25519_dev", 0, torch.from_numpy(k).cuda().data_ptr(), torch.from_numpy(u).cuda().data_ptr(), n, d_o.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert np.array_equal(d_o.cpu().numpy(), ctx.x25519(k, u))
+    # invalid element is reported through ecb_dev_status
+    kb2 = kb.copy(); kb2[77] = 0xFF
+    d_k2 = torch.from_numpy(kb2).cuda()
+    ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k2.data_ptr(), n, d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert ctx.dev_status(0) == (-3, 77)

@@ -1,0 +1,164 @@
+"""Host simulation of the device code (CPU only): the very same .cuh headers that nvcc compiles for
+sm_100a are compiled with g++ and an emulated carry flag (ECB_HOSTSIM) and run thread by thread,
+then compared with the oracle.  This checks the primitive sequences (carry chains, reductions,
+formulas, recoding, batch inversion) without a GPU; the `-m gpu` tests check the real thing."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from helpers import ed_edge_scalars, rand_bytes, rng, rows, scalars_mod, wei_edge_scalars, wei_points, ecdsa_batch, ed25519_sig_batch
+from oracle import pyref as R
+
+HS = os.path.join(os.path.dirname(os.path.abspath(__file__)), "hostsim")
+VP = ctypes.c_void_p
+
+
+@pytest.fixture(scope="module")
+def hs():
+    subprocess.check_call(["make", "-s", "-j4", "-C", HS])
+    f = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_fields.so"))
+    k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
+    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul", "hs_wei_mul", "hs_ecdsa_verify"):
+        getattr(k, fn).restype = ctypes.c_ulonglong
+    return f, k
+
+
+def p(a):
+    return None if a is None else a.ctypes.data_as(VP)
+
+
+def words(x, n):
+    return np.array([(x >> (32 * i)) & 0xFFFFFFFF for i in range(n)], dtype=np.uint32)
+
+
+def val(a):
+    return sum(int(w) << (32 * i) for i, w in enumerate(a))
+
+
+def test_fe25519_ops(hs):
+    f, _ = hs
+    g = rng(1)
+    P = R.P25519
+    cases = [(0, 0), (1, P - 1), (P, P), (2**256 - 1, 2**256 - 1), (2**255 + 18, 19), (P + 5, 2**256 - 39)]
+    cases += [(int.from_bytes(g.bytes(32), "little"), int.from_bytes(g.bytes(32), "little")) for _ in range(200)]
+    r = np.zeros(8, dtype=np.uint32)
+    for a, b in cases:
+        aw, bw = words(a, 8), words(b, 8)
+        for op, exp in ((0, a * b), (1, a * a), (2, a + b), (3, a - b), (4, -a)):
+            f.hs_fe25519(op, p(aw), p(bw), p(r))
+            assert val(r) % P == exp % P, (op, a, b)
+        f.hs_fe25519(5, p(aw), p(bw), p(r))
+        assert val(r) == a % P
+        assert f.hs_fe25519_is_canonical(p(aw)) == (1 if a < P else 0)
+    for a, _ in cases[:20]:
+        aw = words(a, 8)
+        f.hs_fe25519(6, p(aw), p(aw), p(r))
+        assert val(r) % P == pow(a, P - 2, P)
+        f.hs_fe25519(8, p(aw), p(aw), p(r))
+        assert val(r) % P == pow(a, (P - 5) // 8, P)
+
+
+@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (1, R.P256.n, 8), (2, R.P384.p, 12), (3, R.P384.n, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
+def test_montgomery_fields(hs, field, mod, n):
+    f, _ = hs
+    g = rng(field)
+    Rm = 1 << (32 * n)
+    Ri = pow(Rm, -1, mod)
+    r = np.zeros(n, dtype=np.uint32)
+    cases = [(0, 0), (1, mod - 1), (mod - 1, mod - 1), (Rm % mod, 1)]
+    cases += [(int.from_bytes(g.bytes(48), "little") % mod, int.from_bytes(g.bytes(48), "little") % mod) for _ in range(100)]
+    for a, b in cases:
+        aw, bw = words(a, n), words(b, n)
+        for op, exp in ((0, a * b * Ri), (1, a * a * Ri), (2, a + b), (3, a - b), (4, -a), (5, a * Rm), (7, a * Ri)):
+            f.hs_mont(field, op, p(aw), p(bw), p(r))
+            assert val(r) == exp % mod, (field, op)
+    a = cases[5][0]
+    f.hs_mont(field, 6, p(words(a * Rm % mod, n)), p(words(0, n)), p(r))
+    assert val(r) == pow(a, -1, mod) * Rm % mod
+
+
+def test_ed25519_mul_base_and_table(hs, golden, coracle):
+    _, k = hs
+    g = rng(2)
+    kb = np.concatenate([rows([v.to_bytes(32, "little") for v in ed_edge_scalars(golden)]), scalars_mod(g, 40, R.L25519, 32, "little")])
+    n = kb.shape[0]
+    exp = coracle.ed25519_mul_base(kb)
+    for W in (4, 7):
+        ntab = k.hs_ed25519_table_entries(W)
+        table = np.zeros((ntab, 24), dtype=np.uint32)
+        k.hs_ed25519_build_table(W, p(table))
+        out = np.zeros((n, 64), dtype=np.uint8)
+        st = k.hs_ed25519_mul_base(p(kb), ctypes.c_size_t(n), W, p(table), p(out), 0)
+        assert st == 2**64 - 1 and np.array_equal(out, exp)
+    bad = kb.copy()
+    bad[3] = np.frombuffer(R.L25519.to_bytes(32, "little"), dtype=np.uint8)
+    st = k.hs_ed25519_mul_base(p(bad), ctypes.c_size_t(n), W, p(table), p(out), 0)
+    assert st == (3 << 8) | 1
+
+
+def test_ed25519_mul_x25519_x448(hs, coracle):
+    _, k = hs
+    g = rng(3)
+    n = 24
+    kb = scalars_mod(g, n, R.L25519, 32, "little")
+    from helpers import ed_points
+
+    pts = ed_points(g, n)
+    out = np.zeros((n, 64), dtype=np.uint8)
+    assert k.hs_ed25519_mul(p(kb), p(pts), ctypes.c_size_t(n), p(out)) == 2**64 - 1
+    assert np.array_equal(out, coracle.ed25519_mul(kb, pts))
+    ks, us = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
+    us[0] = 0; us[1] = 0xFF
+    o = np.zeros((n, 32), dtype=np.uint8)
+    k.hs_x25519(p(ks), p(us), ctypes.c_size_t(n), p(o))
+    assert np.array_equal(o, coracle.x25519(ks, us))
+    n = 6
+    ks, us = rand_bytes(g, n, 56), rand_bytes(g, n, 56)
+    us[0] = 0xFF
+    o = np.zeros((n, 56), dtype=np.uint8)
+    k.hs_x448(p(ks), p(us), ctypes.c_size_t(n), p(o))
+    assert np.array_equal(o, coracle.x448(ks, us))
+
+
+@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1"), (2, "bls12_381_g1")])
+def test_wei_mul(hs, golden, coracle, cid, curve):
+    _, k = hs
+    c = R.WCURVES[curve]
+    g = rng(10 + cid)
+    kb = np.concatenate([rows([v.to_bytes(c.sbytes, "big") for v in wei_edge_scalars(golden, c.n)[:12]]), scalars_mod(g, 12, c.n, c.sbytes, "big")])
+    n = kb.shape[0]
+    pts = wei_points(curve, g, n)
+    out = np.zeros((n, 2 * c.fbytes), dtype=np.uint8)
+    inf = np.zeros(n, dtype=np.uint8)
+    assert k.hs_wei_mul(cid, p(kb), p(pts), None, ctypes.c_size_t(n), p(out), p(inf)) == 2**64 - 1
+    exp, einf = coracle.wei_mul(curve, kb, pts)
+    assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
+    # fixed base: points == NULL
+    assert k.hs_wei_mul(cid, p(kb), None, None, ctypes.c_size_t(n), p(out), p(inf)) == 2**64 - 1
+    exp, einf = coracle.wei_mul_base(curve, kb)
+    assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
+
+
+@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1")])
+def test_ecdsa(hs, coracle, cid, curve):
+    _, k = hs
+    g = rng(20 + cid)
+    q, z, rs = ecdsa_batch(curve, g, 24)
+    ok = np.zeros(24, dtype=np.uint8)
+    assert k.hs_ecdsa_verify(cid, p(q), p(z), p(rs), ctypes.c_size_t(24), p(ok)) == 2**64 - 1
+    assert np.array_equal(ok.astype(bool), coracle.ecdsa_verify_hashed(curve, q, z, rs))
+
+
+def test_ed25519_verify(hs, coracle):
+    _, k = hs
+    g = rng(30)
+    a, r, s, kk = ed25519_sig_batch(g, 20)
+    W = 5
+    table = np.zeros((k.hs_ed25519_table_entries(W), 24), dtype=np.uint32)
+    k.hs_ed25519_build_table(W, p(table))
+    ok = np.zeros(20, dtype=np.uint8)
+    k.hs_ed25519_verify(p(a), p(r), p(s), p(kk), ctypes.c_size_t(20), W, p(table), p(ok))
+    assert np.array_equal(ok.astype(bool), coracle.ed25519_verify_prehashed(a, r, s, kk))
