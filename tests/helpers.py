@@ -13,7 +13,7 @@ def rng(seed):
 
 
 def rows(lst, width=None):
-    a = np.frombuffer(b"".join(lst), dtype=np.uint8)
+    a = np.frombuffer(b"".join(lst), dtype=np.uint8).copy()  # writable
     return a.reshape(len(lst), -1) if width is None else a.reshape(-1, width)
 
 

@@ -146,7 +146,7 @@ def test_ed25519_mul_variable_base(ctx, golden, coracle):
     g = rng(SEEDS["ed25519"] + 2)
     vals = ed_edge_scalars(golden)
     kb = np.concatenate([rows([v.to_bytes(32, "little") for v in vals]), scalars_mod(g, 1000, R.L25519, 32, "little")])
-    pts = ed_points(g, kb.shape[0])
+    pts = ed_points(g, kb.shape[0]).copy()
     # a few special points: identity, the order-2 point (0,-1), an order-4 point (sqrt(-1), 0), an order-8 point
     special = [(0, 1), (0, R.P25519 - 1), (R.SQRT_M1, 0)]
     for i, (x, y) in enumerate(special):
