@@ -39,13 +39,19 @@ int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out) {
         DevCtx* d = new DevCtx();
         d->dev = device_ids[i];
         ctx->devs.push_back(d);
-        if (cudaSetDevice(d->dev) != cudaSuccess || cudaStreamCreateWithFlags(&d->stream, cudaStreamNonBlocking) != cudaSuccess ||
-            cudaMalloc(&d->d_status, sizeof(unsigned long long)) != cudaSuccess ||
-            cudaMallocHost(&d->h_status, sizeof(unsigned long long)) != cudaSuccess ||
-            cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, d->dev) != cudaSuccess) {
+        bool ok = cudaSetDevice(d->dev) == cudaSuccess &&
+                  cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, d->dev) == cudaSuccess;
+        for (int s = 0; ok && s < ECB_NSLOT; s++) {
+            Slot& sl = d->slots[s];
+            ok = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
+                 cudaMalloc(&sl.d_status, sizeof(unsigned long long)) == cudaSuccess &&
+                 cudaMallocHost(&sl.h_status, sizeof(unsigned long long)) == cudaSuccess;
+        }
+        if (!ok) {
             ecb_destroy(ctx);
             return ECB_ERR_CUDA;
         }
+        d->stream = d->slots[0].stream;
     }
     const char* w = getenv("ECB_ED25519_COMB_W");
     if (w) {
@@ -60,15 +66,17 @@ void ecb_destroy(ecb_ctx* ctx) {
     if (!ctx) return;
     for (DevCtx* d : ctx->devs) {
         cudaSetDevice(d->dev);
-        if (d->stream) cudaStreamSynchronize(d->stream);
-        DevBuf* bufs[] = {&d->planes, &d->pf, &d->scratch, &d->aux, &d->in[0], &d->in[1], &d->in[2], &d->in[3], &d->out[0], &d->out[1]};
-        for (DevBuf* b : bufs)
-            if (b->p) cudaFree(b->p);
+        for (Slot& sl : d->slots) {
+            if (sl.stream) cudaStreamSynchronize(sl.stream);
+            DevBuf* bufs[] = {&sl.planes, &sl.pf, &sl.scratch, &sl.aux, &sl.in[0], &sl.in[1], &sl.in[2], &sl.in[3], &sl.out[0], &sl.out[1]};
+            for (DevBuf* b : bufs)
+                if (b->p) cudaFree(b->p);
+            if (sl.d_status) cudaFree(sl.d_status);
+            if (sl.h_status) cudaFreeHost(sl.h_status);
+            if (sl.stream) cudaStreamDestroy(sl.stream);
+        }
         for (auto& r : d->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); cudaEventDestroy(r.c); }
         if (d->ed_table) cudaFree(d->ed_table);
-        if (d->d_status) cudaFree(d->d_status);
-        if (d->h_status) cudaFreeHost(d->h_status);
-        if (d->stream) cudaStreamDestroy(d->stream);
         delete d;
     }
     delete ctx;
@@ -135,35 +143,57 @@ static int run_sharded(ecb_ctx* ctx, size_t n, const std::vector<HostArg>& ins, 
         std::lock_guard<std::mutex> g(d.mu);
         auto body = [&]() -> int {
             CU(cudaSetDevice(d.dev));
-            for (size_t c0 = lo; c0 < hi; c0 += ctx->opt_chunk) {
+            // retire the chunk in flight on `sl`: wait, then look at its status word
+            auto retire = [&](Slot& sl) -> int {
+                if (!sl.busy) return ECB_OK;
+                sl.busy = false;
+                CU(cudaStreamSynchronize(sl.stream));
+                if (has_status && *sl.h_status != ~0ull) {
+                    unsigned long long v = *sl.h_status;
+                    unsigned long long w = (((v >> 8) + sl.c0) << 8) | (v & 0xff);
+                    if (w < bad[di]) bad[di] = w;
+                }
+                return ECB_OK;
+            };
+            int rcb = ECB_OK;
+            size_t ci = 0;
+            for (size_t c0 = lo; c0 < hi && rcb == ECB_OK && bad[di] == ~0ull; c0 += ctx->opt_chunk, ci++) {
                 size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
-                const void* din[4] = {nullptr, nullptr, nullptr, nullptr};
-                void* dout[2] = {nullptr, nullptr};
-                for (size_t i = 0; i < ins.size(); i++) {
-                    if (!ins[i].src) continue;
-                    TRY(ensure(ctx, d.in[i], cn * ins[i].elem));
-                    CU(cudaMemcpyAsync(d.in[i].p, ins[i].src + c0 * ins[i].elem, cn * ins[i].elem, cudaMemcpyHostToDevice, d.stream));
-                    din[i] = d.in[i].p;
-                }
-                for (size_t i = 0; i < outs.size(); i++) {
-                    if (!outs[i].dst) continue;
-                    TRY(ensure(ctx, d.out[i], cn * outs[i].elem));
-                    dout[i] = d.out[i].p;
-                }
-                TRY(op(d, d.stream, din, dout, cn));
-                for (size_t i = 0; i < outs.size(); i++) {
-                    if (!outs[i].dst) continue;
-                    CU(cudaMemcpyAsync(outs[i].dst + c0 * outs[i].elem, d.out[i].p, cn * outs[i].elem, cudaMemcpyDeviceToHost, d.stream));
-                }
-                if (has_status) CU(cudaMemcpyAsync(d.h_status, d.d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, d.stream));
-                CU(cudaStreamSynchronize(d.stream));
-                if (has_status && *d.h_status != ~0ull) {
-                    unsigned long long v = *d.h_status;
-                    bad[di] = (((v >> 8) + c0) << 8) | (v & 0xff);
+                Slot& sl = d.slots[ci % ECB_NSLOT];
+                auto one = [&]() -> int {
+                    TRY(retire(sl));
+                    d.cur = &sl;
+                    const void* din[4] = {nullptr, nullptr, nullptr, nullptr};
+                    void* dout[2] = {nullptr, nullptr};
+                    for (size_t i = 0; i < ins.size(); i++) {
+                        if (!ins[i].src) continue;
+                        TRY(ensure(ctx, sl.in[i], cn * ins[i].elem));
+                        CU(cudaMemcpyAsync(sl.in[i].p, ins[i].src + c0 * ins[i].elem, cn * ins[i].elem, cudaMemcpyHostToDevice, sl.stream));
+                        din[i] = sl.in[i].p;
+                    }
+                    for (size_t i = 0; i < outs.size(); i++) {
+                        if (!outs[i].dst) continue;
+                        TRY(ensure(ctx, sl.out[i], cn * outs[i].elem));
+                        dout[i] = sl.out[i].p;
+                    }
+                    TRY(op(d, sl.stream, din, dout, cn));
+                    for (size_t i = 0; i < outs.size(); i++) {
+                        if (!outs[i].dst) continue;
+                        CU(cudaMemcpyAsync(outs[i].dst + c0 * outs[i].elem, sl.out[i].p, cn * outs[i].elem, cudaMemcpyDeviceToHost, sl.stream));
+                    }
+                    if (has_status) CU(cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.stream));
+                    sl.busy = true;
+                    sl.c0 = c0;
                     return ECB_OK;
-                }
+                };
+                rcb = one();
             }
-            return ECB_OK;
+            for (Slot& sl : d.slots) {
+                int r2 = retire(sl);
+                if (rcb == ECB_OK) rcb = r2;
+            }
+            d.cur = &d.slots[0];
+            return rcb;
         };
         rc[di] = body();
     };
@@ -372,8 +402,9 @@ int ecb_dev_status(ecb_ctx* ctx, int di, size_t* bad_index) {
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
-    CU(cudaMemcpy(d->h_status, d->d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    unsigned long long v = *d->h_status;
+    Slot& sl = d->slots[0];
+    CU(cudaMemcpy(sl.h_status, sl.d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    unsigned long long v = *sl.h_status;
     if (bad_index) *bad_index = (size_t)-1;
     if (v == ~0ull) return ECB_OK;
     if (bad_index) *bad_index = (size_t)(v >> 8);

@@ -432,22 +432,73 @@ struct FinX25519 {  // out: u' = x2 / z2 little-endian canonical, 0 when z2 == 0
 
 // =======================================================================================
 // Weierstrass variable base: k*P with signed 4-bit Booth windows over a per-thread table of
-// 8 projective multiples and the complete RCB formulas (replaces &Point * &Scalar,
-// fiat/curve_macros.rs:321 -> projective.rs:871 scalar_mul_fixed_window_am3 / :842 _a0).
+// 8 Jacobian multiples (replaces &Point * &Scalar, fiat/curve_macros.rs:321 ->
+// projective.rs:871 scalar_mul_fixed_window_am3 / :842 _a0: same group element, different
+// coordinates and window recoding — only the canonical affine result is observable).
 //   scalars: n x SB bytes big-endian canonical (< group order)
 //   points : n x 2FB bytes big-endian affine (x, y), on the curve; inf_in (optional) marks
-//            identity inputs
-//   tbl    : this thread's scratch, 8 entries x 3N words
+//            identity inputs; points == NULL selects the generator (Point::mul_base)
+//   tbl    : this thread's scratch, 8 entries x 5N words (X, Y, Z, Z^2, Z^3)
 // =======================================================================================
+template <class C>
+ECB_DEV void wei_store_cached(u32* d, const typename WeiJ<C>::cached& c) {
+    constexpr int N = C::F::N;
+    st_words<N>(d, c.X.v); st_words<N>(d + N, c.Y.v); st_words<N>(d + 2 * N, c.Z.v);
+    st_words<N>(d + 3 * N, c.ZZ.v); st_words<N>(d + 4 * N, c.ZZZ.v);
+}
+template <class C>
+ECB_DEV void wei_load_cached(typename WeiJ<C>::cached& c, const u32* s) {
+    constexpr int N = C::F::N;
+    ld_words_rw<N>(c.X.v, s); ld_words_rw<N>(c.Y.v, s + N); ld_words_rw<N>(c.Z.v, s + 2 * N);
+    ld_words_rw<N>(c.ZZ.v, s + 3 * N); ld_words_rw<N>(c.ZZZ.v, s + 4 * N);
+}
+// tbl[j-1] = cached(j * (x, y)), j = 1..8: 4 doublings + 3 additions.  Entries are written to
+// the table as soon as they exist and re-read when needed, so a single point is live at a time.
+template <class C>
+ECB_DEV void wei_store_pt_cached(u32* d, const typename WeiJ<C>::pt& p) {
+    typedef typename C::F FT;
+    constexpr int N = FT::N;
+    typename FT::el zz, zzz;
+    FT::sqr_ni(zz, p.Z);
+    FT::mul_ni(zzz, zz, p.Z);
+    st_words<N>(d, p.X.v); st_words<N>(d + N, p.Y.v); st_words<N>(d + 2 * N, p.Z.v);
+    st_words<N>(d + 3 * N, zz.v); st_words<N>(d + 4 * N, zzz.v);
+}
+template <class C>
+ECB_DEV void wei_build_table8(u32* tbl, const typename C::F::el& x, const typename C::F::el& y) {
+    typedef WeiJ<C> J;
+    typedef typename C::F FT;
+    constexpr int N = FT::N;
+    constexpr int ES = 5 * N;
+    auto ld = [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); };
+    typename J::pt cur;
+    FT::copy(cur.X, x); FT::copy(cur.Y, y); FT::set_one(cur.Z);
+    st_words<N>(tbl, cur.X.v); st_words<N>(tbl + N, cur.Y.v);
+    st_words<N>(tbl + 2 * N, cur.Z.v); st_words<N>(tbl + 3 * N, cur.Z.v); st_words<N>(tbl + 4 * N, cur.Z.v);
+    J::dbl(cur, cur);                                   // 2P
+    wei_store_pt_cached<C>(tbl + 1 * ES, cur);
+    ECB_NOUNROLL
+    for (int j = 2; j <= 6; j += 2) {                   // (j+1)P = jP + P ; (j+2)P = 2 * ((j+2)/2)P
+        J::add_mem(cur, cur, tbl, 0u, ld);
+        wei_store_pt_cached<C>(tbl + j * ES, cur);
+        const u32* h = tbl + (j / 2) * ES;              // ((j+2)/2) P sits in slot (j+2)/2 - 1 = j/2
+        ld(cur.X.v, h); ld(cur.Y.v, h + N); ld(cur.Z.v, h + 2 * N);
+        J::dbl(cur, cur);
+        wei_store_pt_cached<C>(tbl + (j + 1) * ES, cur);
+    }
+}
+
 template <class C>
 ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* points, const unsigned char* inf_in,
                           u32* tbl, u32* planes, unsigned long long* status) {
+    typedef WeiJ<C> J;
     typedef Wei<C> W;
     typedef typename C::F FT;
     typedef typename C::FN FNT;
     typedef typename FT::el fe;
     constexpr int N = FT::N;
     constexpr int NS = C::SB / 4;
+    constexpr int ES = 5 * N;
     u32 k[NS + 1];
     ld_words_be<NS>(k, scalars + idx * NS);
     k[NS] = 0;
@@ -457,57 +508,36 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
         ok = 0;
     }
     u32 is_inf = inf_in ? (inf_in[idx] ? 1u : 0u) : 0u;
-    typename W::pt P, acc;
+    fe px, py;
     if (points) {
         u32 xw[N], yw[N];
         ld_words_be<N>(xw, points + idx * 2 * N);
         ld_words_be<N>(yw, points + idx * 2 * N + N);
-        FT::to_mont(P.X, xw);
-        FT::to_mont(P.Y, yw);
-        if (ok && !is_inf && !(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(P.X, P.Y))) {
+        FT::to_mont(px, xw);
+        FT::to_mont(py, yw);
+        if (ok && !is_inf && !(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(px, py))) {
             report_bad(status, idx, ST_BAD_POINT);
             ok = 0;
         }
     } else {  // fixed base: the curve generator (Point::mul_base)
         ECB_UNROLL
-        for (int i = 0; i < N; i++) { P.X.v[i] = C::gx(i); P.Y.v[i] = C::gy(i); }
+        for (int i = 0; i < N; i++) { px.v[i] = C::gx(i); py.v[i] = C::gy(i); }
     }
-    FT::set_one(P.Z);
-    if (!ok || is_inf) W::set_inf(P);
-    if (!ok) {
-        ECB_UNROLL
-        for (int i = 0; i < NS; i++) k[i] = 0;
-    }
-    // table[j-1] = j*P, j = 1..8
-    {
-        typename W::pt t = P;
+    typename J::pt acc;
+    J::set_inf(acc);
+    if (ok && !is_inf) {
+        wei_build_table8<C>(tbl, px, py);
+        constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
         ECB_NOUNROLL
-        for (int j = 1; j <= 8; j++) {  // complete addition: 2P = P + P needs no doubling
-            u32* d = tbl + (j - 1) * 3 * N;
-            st_words<N>(d, t.X.v); st_words<N>(d + N, t.Y.v); st_words<N>(d + 2 * N, t.Z.v);
-            if (j < 8) W::add(t, t, P);
+        for (int i = NWIN - 1; i >= 0; i--) {
+            if (i != NWIN - 1) {
+                ECB_NOUNROLL
+                for (int r = 0; r < 4; r++) J::dbl(acc, acc);
+            }
+            u32 neg;
+            u32 d = booth_digit(k, NS + 1, 4, i, neg);
+            if (d != 0) J::add_mem(acc, acc, tbl + (d - 1) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
         }
-    }
-    constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
-    W::set_inf(acc);
-    ECB_NOUNROLL
-    for (int i = NWIN - 1; i >= 0; i--) {
-        if (i != NWIN - 1) {
-            ECB_NOUNROLL
-            for (int r = 0; r < 4; r++) W::dbl(acc, acc);
-        }
-        u32 neg;
-        u32 d = booth_digit(k, NS + 1, 4, i, neg);
-        typename W::pt s;
-        W::set_inf(s);
-        if (d != 0) {
-            const u32* src = tbl + (d - 1) * 3 * N;
-            ld_words_rw<N>(s.X.v, src); ld_words_rw<N>(s.Y.v, src + N); ld_words_rw<N>(s.Z.v, src + 2 * N);
-        }
-        fe ny;
-        FT::neg(ny, s.Y);
-        FT::select(s.Y, neg, ny, s.Y);
-        W::add(acc, acc, s);
     }
     plane_st<N>(planes + 0 * (size_t)N * n, n, idx, acc.X.v);
     plane_st<N>(planes + 1 * (size_t)N * n, n, idx, acc.Y.v);
@@ -523,8 +553,11 @@ struct FinWeiXY {  // out: x_be || y_be (canonical, out of the Montgomery domain
         typename FT::el X, Y, x, y;
         plane_ld<N>(X.v, planes, n, idx);
         plane_ld<N>(Y.v, planes + (size_t)N * n, n, idx);
-        FT::mul(x, X, zinv);
-        FT::mul(y, Y, zinv);
+        typename FT::el zi2;
+        FT::sqr(zi2, zinv);          // Jacobian: x = X / Z^2, y = Y / Z^3
+        FT::mul(x, X, zi2);
+        FT::mul(zi2, zi2, zinv);
+        FT::mul(y, Y, zi2);
         u32 xw[N], yw[N];
         FT::from_mont(xw, x);
         FT::from_mont(yw, y);

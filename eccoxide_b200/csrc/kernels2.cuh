@@ -279,22 +279,24 @@ template <class C>
 ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z_be, const u32* rs_be, const u32* sp,
                              unsigned char* valid, u32* tbl, u32* planes, unsigned long long* status) {
     typedef Wei<C> W;
+    typedef WeiJ<C> J;
     typedef typename C::F FT;
     typedef typename C::FN FN;
     typedef typename FT::el fe;
     constexpr int N = FT::N;
     constexpr int NS = FN::N;
+    constexpr int ES = 5 * N;
     // public key
     u32 xw[N], yw[N];
     ld_words_be<N>(xw, q_be + idx * 2 * N);
     ld_words_be<N>(yw, q_be + idx * 2 * N + N);
-    typename W::pt Q, G, acc;
-    FT::to_mont(Q.X, xw);
-    FT::to_mont(Q.Y, yw);
-    FT::set_one(Q.Z);
-    if (!(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(Q.X, Q.Y))) {
+    fe qx, qy, gx, gy;
+    FT::to_mont(qx, xw);
+    FT::to_mont(qy, yw);
+    u32 q_ok = 1;
+    if (!(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(qx, qy))) {
         report_bad(status, idx, ST_BAD_POINT);
-        W::set_inf(Q);
+        q_ok = 0;
     }
     // u1 = z * s^-1, u2 = r * s^-1 as plain integers: mont_mul(plain, mont) = plain product
     typename FN::el sinv, zz, rr, u1e, u2e;
@@ -310,54 +312,34 @@ ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z
         ECB_UNROLL
         for (int i = 0; i < NS; i++) zz.v[i] = borrow ? zz.v[i] : d[i];
     }
-    if (!valid[idx]) {
+    typename J::pt acc;
+    J::set_inf(acc);
+    if (valid[idx] && q_ok) {
+        FN::mul(u1e, zz, sinv);
+        FN::mul(u2e, rr, sinv);
+        u32 u1[NS + 1], u2[NS + 1];
         ECB_UNROLL
-        for (int i = 0; i < NS; i++) rr.v[i] = 0;
-    }
-    FN::mul(u1e, zz, sinv);
-    FN::mul(u2e, rr, sinv);
-    u32 u1[NS + 1], u2[NS + 1];
-    ECB_UNROLL
-    for (int i = 0; i < NS; i++) { u1[i] = u1e.v[i]; u2[i] = u2e.v[i]; }
-    u1[NS] = 0;
-    u2[NS] = 0;
-    // tables: tbl[0..8) = j*Q, tbl[8..16) = j*G
-    ECB_UNROLL
-    for (int i = 0; i < N; i++) { G.X.v[i] = C::gx(i); G.Y.v[i] = C::gy(i); }
-    FT::set_one(G.Z);
-    ECB_NOUNROLL
-    for (int which = 0; which < 2; which++) {
-        typename W::pt B, t;
-        if (which == 0) B = Q; else B = G;
-        u32* base = tbl + which * 8 * 3 * N;
-        t = B;
+        for (int i = 0; i < NS; i++) { u1[i] = u1e.v[i]; u2[i] = u2e.v[i]; }
+        u1[NS] = 0;
+        u2[NS] = 0;
+        // tables: tbl[0..8) = j*Q, tbl[8..16) = j*G  (Jacobian, cached Z powers)
+        ECB_UNROLL
+        for (int i = 0; i < N; i++) { gx.v[i] = C::gx(i); gy.v[i] = C::gy(i); }
+        wei_build_table8<C>(tbl, qx, qy);
+        wei_build_table8<C>(tbl + 8 * ES, gx, gy);
+        constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
         ECB_NOUNROLL
-        for (int j = 1; j <= 8; j++) {  // complete addition: 2B = B + B
-            u32* d = base + (j - 1) * 3 * N;
-            st_words<N>(d, t.X.v); st_words<N>(d + N, t.Y.v); st_words<N>(d + 2 * N, t.Z.v);
-            if (j < 8) W::add(t, t, B);
-        }
-    }
-    constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
-    W::set_inf(acc);
-    ECB_NOUNROLL
-    for (int i = NWIN - 1; i >= 0; i--) {
-        if (i != NWIN - 1) {
+        for (int i = NWIN - 1; i >= 0; i--) {
+            if (i != NWIN - 1) {
+                ECB_NOUNROLL
+                for (int r = 0; r < 4; r++) J::dbl(acc, acc);
+            }
             ECB_NOUNROLL
-            for (int r = 0; r < 4; r++) W::dbl(acc, acc);
-        }
-        ECB_NOUNROLL
-        for (int which = 0; which < 2; which++) {
-            u32 neg;
-            u32 d = booth_digit(which == 0 ? u2 : u1, NS + 1, 4, i, neg);
-            if (d != 0) {  // skipping a zero digit: verification is variable time like mul_vartime
-                typename W::pt s;
-                const u32* src = tbl + (which * 8 + (d - 1)) * 3 * N;
-                ld_words_rw<N>(s.X.v, src); ld_words_rw<N>(s.Y.v, src + N); ld_words_rw<N>(s.Z.v, src + 2 * N);
-                fe ny;
-                FT::neg(ny, s.Y);
-                FT::select(s.Y, neg, ny, s.Y);
-                W::add(acc, acc, s);
+            for (int which = 0; which < 2; which++) {
+                u32 neg;
+                u32 d = booth_digit(which == 0 ? u2 : u1, NS + 1, 4, i, neg);
+                // skipping a zero digit: verification is variable time like mul_vartime
+                if (d != 0) J::add_mem(acc, acc, tbl + (which * 8 + (d - 1)) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
             }
         }
     }
@@ -376,7 +358,9 @@ struct FinEcdsa {  // x_mod_n(R) == r (ecdsa.rs:382, :218-221); identity => reje
         constexpr int NS = FN::N;
         typename FT::el X, x;
         plane_ld<N>(X.v, planes, n, idx);
-        FT::mul(x, X, zinv);
+        typename FT::el zi2;
+        FT::sqr(zi2, zinv);          // Jacobian: x = X / Z^2
+        FT::mul(x, X, zi2);
         u32 xw[N];
         FT::from_mont(xw, x);
         // field_to_scalar (ecdsa.rs:363): FB <= SB here, p < 2n: one conditional subtraction

@@ -20,6 +20,15 @@ struct fe_mont {
     u32 v[N_];
 };
 
+// Per-prime reduction strategy.  kind 0 = generic CIOS (2 N^2 IMAD.WIDE per product).
+// kind 1 = p256: -p^-1 = 1 (mod 2^96) and p = 2^256 - 2^224 + 2^192 + 2^96 - 1, so the Montgomery
+// reduction of a 512-bit product is three rounds of shifted additions / subtractions of
+// m = T mod 2^96 — no multiplication at all; product = N^2, square = N(N+1)/2 IMAD.WIDE.
+template <class P>
+struct MontKind {
+    static constexpr int kind = 0;
+};
+
 // P supplies: N, INV (= -p^-1 mod 2^32) and accessors mod(i), r1(i) (= R mod p, "one"),
 // r2(i) (= R^2 mod p) over little-endian 32-bit limbs held in `__constant__ const`
 // arrays; with the loops unrolled the limbs fold to immediates.
@@ -56,7 +65,80 @@ struct Mont {
         for (int i = 0; i < N; i++) r.v[i] = (d[i] & m) | (t[i] & ~m);
     }
 
+    // ---- p256: one round of T += m * p * 2^(32 O), m = T[O .. O+ML) (ML = 3, or 2 in the last
+    // round); limbs O .. O+ML-1 become zero and are simply skipped.
+    //   m*p = m*2^256 - m*2^224 + m*2^192 + m*2^96 - m
+    template <int O, int ML>
+    ECB_DEV static void p256_round(u32* T) {
+        const u32 m0 = T[O], m1 = T[O + 1], m2 = (ML == 3) ? T[O + 2] : 0u;
+        // U = m * (2^96 + 2^192 + 2^256), relative limbs 3..11 (3..7 are plain copies of m)
+        u32 U8 = add_cc(m2, m0);
+        u32 U9 = addc_cc(m1, 0u);
+        u32 U10 = addc_cc(m2, 0u);
+        u32 U11 = addc(0u, 0u);
+        // V = U - m * 2^224 (relative limbs 7..11); V >= 0
+        u32 V7 = sub_cc(m1, m0);
+        u32 V8 = subc_cc(U8, m1);
+        u32 V9 = subc_cc(U9, m2);
+        u32 V10 = subc_cc(U10, 0u);
+        u32 V11 = subc(U11, 0u);
+        T[O + 3] = add_cc(T[O + 3], m0);
+        T[O + 4] = addc_cc(T[O + 4], m1);
+        T[O + 5] = addc_cc(T[O + 5], m2);
+        T[O + 6] = addc_cc(T[O + 6], m0);
+        T[O + 7] = addc_cc(T[O + 7], V7);
+        T[O + 8] = addc_cc(T[O + 8], V8);
+        T[O + 9] = addc_cc(T[O + 9], V9);
+        T[O + 10] = addc_cc(T[O + 10], V10);
+        if (O + 11 <= 16) T[O + 11] = addc_cc(T[O + 11], V11);
+        ECB_UNROLL
+        for (int j = O + 12; j <= 16; j++) T[j] = addc_cc(T[j], 0u);
+        (void)addc(0u, 0u);
+    }
+    // T: 17 limbs, T[16] = 0 on entry, value < p^2.  r = T / 2^256 mod p, canonical.
+    ECB_DEV static void p256_reduce(el& r, u32* T) {
+        p256_round<0, 3>(T);
+        p256_round<3, 3>(T);
+        p256_round<6, 2>(T);
+        // T[8..16] < 2^256 + p: fold the carry word by adding 2^256 - p once; the result is < 2^256
+        // ("loose": congruent, not necessarily < p — see the representation note above add())
+        fold_carry(r, T + 8, T[16]);
+    }
+    // r = t + c * (2^256 - p) mod 2^256 for c in {0, 1};  2^256 - p = 2^224 - 2^192 - 2^96 + 1
+    ECB_DEV static u32 fold_carry(el& r, const u32* t, u32 c) {
+        const u32 m = 0u - c;
+        r.v[0] = add_cc(t[0], c);
+        r.v[1] = addc_cc(t[1], 0u);
+        r.v[2] = addc_cc(t[2], 0u);
+        r.v[3] = addc_cc(t[3], m);
+        r.v[4] = addc_cc(t[4], m);
+        r.v[5] = addc_cc(t[5], m);
+        r.v[6] = addc_cc(t[6], m << 1);
+        r.v[7] = addc_cc(t[7], 0u);
+        return addc(0u, 0u);
+    }
+    // r = t - c * (2^256 - p) mod 2^256 ; returns the borrow
+    ECB_DEV static u32 fold_borrow(el& r, const u32* t, u32 c) {
+        const u32 m = 0u - c;
+        r.v[0] = sub_cc(t[0], c);
+        r.v[1] = subc_cc(t[1], 0u);
+        r.v[2] = subc_cc(t[2], 0u);
+        r.v[3] = subc_cc(t[3], m);
+        r.v[4] = subc_cc(t[4], m);
+        r.v[5] = subc_cc(t[5], m);
+        r.v[6] = subc_cc(t[6], m << 1);
+        r.v[7] = subc_cc(t[7], 0u);
+        return subc(0u, 0u) & 1u;
+    }
+
     ECB_DEV static void mul(el& r, const el& a, const el& b) {
+        if constexpr (MontKind<P>::kind == 1) {
+            u32 T[17];
+            mul_full<N>(T, a.v, b.v);
+            T[16] = 0;
+            p256_reduce(r, T);
+            return;
+        }
         // ev[k] sits on (relative) limb k, od[k] on limb k+1; L is a single word on limb 0
         u32 ev[N + 2], od[N + 2];
         ECB_UNROLL
@@ -101,16 +183,58 @@ struct Mont {
         for (int k = 1; k <= N; k++) t[k] = addc_cc(ev[k], od[k - 1]);
         final_sub(r, t, t[N]);
     }
-    ECB_DEV static void sqr(el& r, const el& a) { mul(r, a, a); }
+    ECB_DEV static void sqr(el& r, const el& a) {
+        if constexpr (MontKind<P>::kind == 1) {
+            u32 T[17];
+            sqr_full<N>(T, a.v);
+            T[16] = 0;
+            p256_reduce(r, T);
+            return;
+        }
+        mul(r, a, a);
+    }
 
+    // out-of-line copies for the big Weierstrass kernels: one body of each instead of one per call
+    // site keeps the window loop inside the instruction cache (ncu: stall_no_instruction was the top
+    // stall with everything inlined)
+    // (operands and result by value: the ABI then keeps them in registers; by reference they
+    // would be forced into local memory)
+    ECB_DEVNI static el mul_v(el a, el b) {
+        el r;
+        mul(r, a, b);
+        return r;
+    }
+    ECB_DEVNI static el sqr_v(el a) {
+        el r;
+        sqr(r, a);
+        return r;
+    }
+    ECB_DEV static void mul_ni(el& r, const el& a, const el& b) { r = mul_v(a, b); }
+    ECB_DEV static void sqr_ni(el& r, const el& a) { r = sqr_v(a); }
+
+    // Representation.  kind 0: canonical, every value < p (as the fiat code).  kind 1 (p256): "loose",
+    // every value < 2^256 and congruent to the element; since 2^256 < 2p a loose value is x or x + p.
+    // Carries / borrows out of 2^256 are folded with 2^256 = 2^256 - p (mod p); a second fold is
+    // needed only when both operands sit within 2^224 of 2^256, which is handled by a (practically
+    // never taken) branch.  from_mont() and is_zero()/eq() canonicalise, so nothing observable changes.
     ECB_DEV static void add(el& r, const el& a, const el& b) {
         u32 t[N];
         u32 c = add_n<N>(t, a.v, b.v);
+        if constexpr (MontKind<P>::kind == 1) {
+            u32 c2 = fold_carry(r, t, c);
+            if (c2) fold_carry(r, r.v, 1u);
+            return;
+        }
         final_sub(r, t, c);
     }
     ECB_DEV static void sub(el& r, const el& a, const el& b) {
         u32 t[N];
         u32 bw = sub_n<N>(t, a.v, b.v);
+        if constexpr (MontKind<P>::kind == 1) {
+            u32 b2 = fold_borrow(r, t, bw);
+            if (b2) fold_borrow(r, r.v, 1u);
+            return;
+        }
         u32 m = 0u - bw;
         r.v[0] = add_cc(t[0], P::mod(0) & m);
         ECB_UNROLL
@@ -127,9 +251,20 @@ struct Mont {
         u32 o = 0;
         ECB_UNROLL
         for (int i = 0; i < N; i++) o |= a.v[i];
+        if constexpr (MontKind<P>::kind == 1) {  // loose: 0 or p
+            u32 q = 0;
+            ECB_UNROLL
+            for (int i = 0; i < N; i++) q |= a.v[i] ^ P::mod(i);
+            return (o == 0 || q == 0) ? 1u : 0u;
+        }
         return o == 0 ? 1u : 0u;
     }
     ECB_DEV static u32 eq(const el& a, const el& b) {
+        if constexpr (MontKind<P>::kind == 1) {
+            el d;
+            sub(d, a, b);
+            return is_zero(d);
+        }
         u32 o = 0;
         ECB_UNROLL
         for (int i = 0; i < N; i++) o |= a.v[i] ^ b.v[i];
@@ -153,6 +288,7 @@ struct Mont {
         set_zero(one);
         one.v[0] = 1;
         mul(t, a, one);
+        if constexpr (MontKind<P>::kind == 1) final_sub(t, t.v, 0u);  // canonical representative
         ECB_UNROLL
         for (int i = 0; i < N; i++) w[i] = t.v[i];
     }

@@ -1,0 +1,13 @@
+// mont_kinds.cuh — which primes get a dedicated Montgomery reduction (see MontKind in mont.cuh).
+#pragma once
+#include "mont.cuh"
+#include "params_gen.cuh"
+
+namespace ecb {
+
+template <>
+struct MontKind<P256_FP> {
+    static constexpr int kind = 1;
+};
+
+}  // namespace ecb

@@ -31,13 +31,13 @@ int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
     if (d.ed_table) CU(cudaFree(d.ed_table));
     d.ed_table = nullptr;
     CU(cudaMalloc(&d.ed_table, ntab * 24 * sizeof(u32)));
-    TRY(ensure(ctx, d.planes, ntab * 3 * 8 * sizeof(u32)));
-    TRY(ensure(ctx, d.pf, ntab * 8 * sizeof(u32)));
-    k_ed25519_table_points<<<grid_for(ntab), ECB_TPB, 0, d.stream>>>(ntab, W, nwin, (u32*)d.planes.p);
+    TRY(ensure(ctx, d.cur->planes, ntab * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->pf, ntab * 8 * sizeof(u32)));
+    k_ed25519_table_points<<<grid_for(ntab), ECB_TPB, 0, d.stream>>>(ntab, W, nwin, (u32*)d.cur->planes.p);
     ctx->launches++;
     CU(cudaGetLastError());
-    FinEdNiels fin{(const u32*)d.planes.p, ntab, d.ed_table};
-    TRY((launch_batch_inv<F25519, FinEdNiels>(ctx, d, ntab, (const u32*)d.planes.p, (u32*)d.pf.p, fin, d.stream)));
+    FinEdNiels fin{(const u32*)d.cur->planes.p, ntab, d.ed_table};
+    TRY((launch_batch_inv<F25519, FinEdNiels>(ctx, d, ntab, (const u32*)d.cur->planes.p, (u32*)d.cur->pf.p, fin, d.stream)));
     CU(cudaStreamSynchronize(d.stream));
     d.ed_w = W;
     d.ed_nwin = nwin;
@@ -46,41 +46,41 @@ int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
 
 int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s) {
     if (!d.ed_table || d.ed_w != (int)ctx->opt_ed_w) TRY(dev_ed25519_build_table(ctx, d, (int)ctx->opt_ed_w));
-    TRY(ensure(ctx, d.planes, n * 3 * 8 * sizeof(u32)));
-    TRY(ensure(ctx, d.pf, n * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
     TRY(reset_status(ctx, d, s));
-    u32* planes = (u32*)d.planes.p;
+    u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
-    k_ed25519_mul_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, planes, d.d_status);
+    k_ed25519_mul_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, planes, d.cur->d_status);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);
     int rc;
     if (compressed) {
         FinEdCompressed fin{planes, n, d_out};
-        rc = launch_batch_inv<F25519, FinEdCompressed>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+        rc = launch_batch_inv<F25519, FinEdCompressed>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     } else {
         FinEdXY fin{planes, n, d_out};
-        rc = launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+        rc = launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     }
     prof_mark(ctx, d, s, 2);
     return rc;
 }
 
 int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_out, cudaStream_t s) {
-    TRY(ensure(ctx, d.planes, n * 3 * 8 * sizeof(u32)));
-    TRY(ensure(ctx, d.pf, n * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
     unsigned g = persistent_grid(d, k_ed25519_mul, n);
-    TRY(ensure(ctx, d.scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
     TRY(reset_status(ctx, d, s));
-    u32* planes = (u32*)d.planes.p;
+    u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
-    k_ed25519_mul<<<g, ECB_TPB, 0, s>>>(n, d_k, d_p, (u32*)d.scratch.p, planes, d.d_status);
+    k_ed25519_mul<<<g, ECB_TPB, 0, s>>>(n, d_k, d_p, (u32*)d.cur->scratch.p, planes, d.cur->d_status);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);
     FinEdXY fin{planes, n, d_out};
-    int rc = launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    int rc = launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     prof_mark(ctx, d, s, 2);
     return rc;
 }
@@ -89,9 +89,9 @@ int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, cons
                        unsigned char* ok, cudaStream_t s) {
     if (!d.ed_table || d.ed_w != (int)ctx->opt_ed_w) TRY(dev_ed25519_build_table(ctx, d, (int)ctx->opt_ed_w));
     unsigned g = persistent_grid(d, k_ed25519_verify, n);
-    TRY(ensure(ctx, d.scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
     prof_mark(ctx, d, s, 0);
-    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, r, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, (u32*)d.scratch.p, ok);
+    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, r, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, (u32*)d.cur->scratch.p, ok);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);

@@ -85,19 +85,19 @@ int dev_imad_probe(ecb_ctx* ctx, DevCtx& dref, int variant, int iters, double* m
     DevCtx* d = &dref;
     if (variant < 0 || variant > 5 || iters < 1) return ECB_ERR_INVALID_ARG;
     unsigned blocks = (unsigned)d->sm_count * 8;
-    TRY(ensure(ctx, d->aux, (size_t)blocks * 256 * sizeof(u32)));
+    TRY(ensure(ctx, d->cur->aux, (size_t)blocks * 256 * sizeof(u32)));
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     for (int rep = 0; rep < 2; rep++) {  // first pass is warm-up
         CU(cudaEventRecord(e0, d->stream));
         switch (variant) {
-            case 0: k_imad_probe<0><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
-            case 1: k_imad_probe<1><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
-            case 2: k_imad_probe<2><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
-            case 3: k_imad_probe<3><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
-            case 4: k_imad_probe<4><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
-            case 5: k_imad_probe<5><<<blocks, 256, 0, d->stream>>>((u32*)d->aux.p, iters); break;
+            case 0: k_imad_probe<0><<<blocks, 256, 0, d->stream>>>((u32*)d->cur->aux.p, iters); break;
+            case 1: k_imad_probe<1><<<blocks, 256, 0, d->stream>>>((u32*)d->cur->aux.p, iters); break;
+            case 2: k_imad_probe<2><<<blocks, 256, 0, d->stream>>>((u32*)d->cur->aux.p, iters); break;
+            case 3: k_imad_probe<3><<<blocks, 256, 0, d->stream>>>((u32*)d->cur->aux.p, iters); break;
+            case 4: k_imad_probe<4><<<blocks, 256, 0, d->stream>>>((u32*)d->cur->aux.p, iters); break;
+            case 5: k_imad_probe<5><<<blocks, 256, 0, d->stream>>>((u32*)d->cur->aux.p, iters); break;
         }
         ctx->launches++;
         CU(cudaGetLastError());

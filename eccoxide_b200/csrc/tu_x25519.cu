@@ -8,16 +8,16 @@ static __global__ void __launch_bounds__(ECB_TPB) k_x25519(size_t n, const u32* 
 }
 
 int dev_x25519(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_u, size_t n, u32* d_out, cudaStream_t s) {
-    TRY(ensure(ctx, d.planes, n * 3 * 8 * sizeof(u32)));
-    TRY(ensure(ctx, d.pf, n * 8 * sizeof(u32)));
-    u32* planes = (u32*)d.planes.p;
+    TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
+    u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
     k_x25519<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d_u, planes);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);
     FinX25519 fin{planes, n, d_out};
-    int rc = launch_batch_inv<F25519, FinX25519>(ctx, d, n, planes, (u32*)d.pf.p, fin, s);
+    int rc = launch_batch_inv<F25519, FinX25519>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     prof_mark(ctx, d, s, 2);
     return rc;
 }

@@ -6,8 +6,7 @@
 // :544 double_a0); INFINITY = (0:1:0) (:152).  The formulas are complete on odd-order curves
 // (P-256, P-384, BLS12-381 E(Fp)), so there are no exceptional inputs.
 #pragma once
-#include "mont.cuh"
-#include "params_gen.cuh"
+#include "mont_kinds.cuh"
 
 namespace ecb {
 
@@ -164,24 +163,24 @@ struct Wei {
         fe t0, t1, t2, t3, X3, Y3, Z3, b;
         if (C::A_M3) {
             get_b(b);
-            F::sqr(t0, p.X);
-            F::sqr(t1, p.Y);
-            F::sqr(t2, p.Z);
-            F::mul(t3, p.X, p.Y);
+            F::sqr_ni(t0, p.X);
+            F::sqr_ni(t1, p.Y);
+            F::sqr_ni(t2, p.Z);
+            F::mul_ni(t3, p.X, p.Y);
             F::dbl(t3, t3);
-            F::mul(Z3, p.X, p.Z);
+            F::mul_ni(Z3, p.X, p.Z);
             F::dbl(Z3, Z3);
-            F::mul(Y3, b, t2);
+            F::mul_ni(Y3, b, t2);
             F::sub(Y3, Y3, Z3);
             F::dbl(X3, Y3);
             F::add(Y3, X3, Y3);
             F::sub(X3, t1, Y3);
             F::add(Y3, t1, Y3);
-            F::mul(Y3, X3, Y3);
-            F::mul(X3, X3, t3);
+            F::mul_ni(Y3, X3, Y3);
+            F::mul_ni(X3, X3, t3);
             F::dbl(t3, t2);
             F::add(t2, t2, t3);
-            F::mul(Z3, b, Z3);
+            F::mul_ni(Z3, b, Z3);
             F::sub(Z3, Z3, t2);
             F::sub(Z3, Z3, t0);
             F::dbl(t3, Z3);
@@ -189,39 +188,272 @@ struct Wei {
             F::dbl(t3, t0);
             F::add(t0, t3, t0);
             F::sub(t0, t0, t2);
-            F::mul(t0, t0, Z3);
+            F::mul_ni(t0, t0, Z3);
             F::add(Y3, Y3, t0);
-            F::mul(t0, p.Y, p.Z);
+            F::mul_ni(t0, p.Y, p.Z);
             F::dbl(t0, t0);
-            F::mul(Z3, t0, Z3);
+            F::mul_ni(Z3, t0, Z3);
             F::sub(X3, X3, Z3);
-            F::mul(Z3, t0, t1);
+            F::mul_ni(Z3, t0, t1);
             F::dbl(Z3, Z3);
             F::dbl(Z3, Z3);
         } else {
             get_b3(b);
-            F::sqr(t0, p.Y);
+            F::sqr_ni(t0, p.Y);
             F::dbl(Z3, t0);
             F::dbl(Z3, Z3);
             F::dbl(Z3, Z3);
-            F::mul(t1, p.Y, p.Z);
-            F::sqr(t2, p.Z);
-            F::mul(t2, b, t2);
-            F::mul(X3, t2, Z3);
+            F::mul_ni(t1, p.Y, p.Z);
+            F::sqr_ni(t2, p.Z);
+            F::mul_ni(t2, b, t2);
+            F::mul_ni(X3, t2, Z3);
             F::add(Y3, t0, t2);
-            F::mul(Z3, t1, Z3);
+            F::mul_ni(Z3, t1, Z3);
             F::dbl(t1, t2);
             F::add(t2, t1, t2);
             F::sub(t0, t0, t2);
-            F::mul(Y3, t0, Y3);
+            F::mul_ni(Y3, t0, Y3);
             F::add(Y3, X3, Y3);
-            F::mul(t1, p.X, p.Y);
-            F::mul(X3, t0, t1);
+            F::mul_ni(t1, p.X, p.Y);
+            F::mul_ni(X3, t0, t1);
             F::dbl(X3, X3);
         }
         F::copy(r.X, X3);
         F::copy(r.Y, Y3);
         F::copy(r.Z, Z3);
+    }
+};
+
+
+// =======================================================================================
+// Jacobian coordinates (X : Y : Z), x = X/Z^2, y = Y/Z^3, infinity <=> Z = 0.
+//
+// The batch kernels use these instead of the complete projective formulas above: only the
+// canonical affine result is observable, the group law is the same, and a doubling
+// costs 3M + 5S (a = -3) / 2M + 5S (a = 0) instead of 8M + 3S + 2 m_b — fewer passes through the
+// integer-multiply pipe, which is what bounds these kernels.  The addition formulas are not
+// complete, so the exceptional inputs (P = Q, P = -Q, either operand at infinity) are detected and
+// handled explicitly; the kernels are variable-time anyway (public data).
+// =======================================================================================
+template <class C>
+struct WeiJ {
+    typedef typename C::F F;
+    typedef typename F::el fe;
+    static constexpr int N = F::N;
+    struct pt {
+        fe X, Y, Z;
+    };
+    // table entry: (X, Y, Z, Z^2, Z^3); AFF entries have Z = 1 and only X, Y are meaningful
+    struct cached {
+        fe X, Y, Z, ZZ, ZZZ;
+    };
+
+    ECB_DEV static void set_inf(pt& r) {
+        F::set_one(r.X);
+        F::set_one(r.Y);
+        F::set_zero(r.Z);
+    }
+    ECB_DEV static u32 is_inf(const pt& p) { return F::is_zero(p.Z); }
+
+    // dbl-2001-b (a = -3): 3M + 5S ; dbl-2009-l (a = 0): 2M + 5S.  Z = 0 stays Z = 0.
+    ECB_DEV static void dbl(pt& r, const pt& p) {
+        if (C::A_M3) {
+            fe delta, gamma, beta, alpha, t0, t1, X3, Y3, Z3;
+            F::sqr_ni(delta, p.Z);
+            F::sqr_ni(gamma, p.Y);
+            F::mul_ni(beta, p.X, gamma);
+            F::sub(t0, p.X, delta);
+            F::add(t1, p.X, delta);
+            F::mul_ni(t0, t0, t1);
+            F::dbl(alpha, t0);
+            F::add(alpha, alpha, t0);   // 3 (X - delta)(X + delta)
+            F::add(t1, p.Y, p.Z);
+            F::sqr_ni(Z3, t1);
+            F::sub(Z3, Z3, gamma);
+            F::sub(Z3, Z3, delta);      // (Y + Z)^2 - gamma - delta
+            F::sqr_ni(X3, alpha);
+            F::dbl(t0, beta);
+            F::dbl(t0, t0);             // 4 beta
+            F::dbl(t1, t0);             // 8 beta
+            F::sub(X3, X3, t1);
+            F::sub(t0, t0, X3);
+            F::mul_ni(Y3, alpha, t0);
+            F::sqr_ni(t1, gamma);
+            F::dbl(t1, t1);
+            F::dbl(t1, t1);
+            F::dbl(t1, t1);             // 8 gamma^2
+            F::sub(Y3, Y3, t1);
+            F::copy(r.X, X3);
+            F::copy(r.Y, Y3);
+            F::copy(r.Z, Z3);
+        } else {
+            fe A, B, Cc, D, E, Fv, t, X3, Y3, Z3;
+            F::sqr_ni(A, p.X);
+            F::sqr_ni(B, p.Y);
+            F::sqr_ni(Cc, B);
+            F::add(t, p.X, B);
+            F::sqr_ni(D, t);
+            F::sub(D, D, A);
+            F::sub(D, D, Cc);
+            F::dbl(D, D);               // 2((X + B)^2 - A - C)
+            F::dbl(E, A);
+            F::add(E, E, A);            // 3A
+            F::sqr_ni(Fv, E);
+            F::dbl(t, D);
+            F::sub(X3, Fv, t);
+            F::mul_ni(Z3, p.Y, p.Z);
+            F::dbl(Z3, Z3);
+            F::sub(t, D, X3);
+            F::mul_ni(Y3, E, t);
+            F::dbl(Cc, Cc);
+            F::dbl(Cc, Cc);
+            F::dbl(Cc, Cc);             // 8C
+            F::sub(Y3, Y3, Cc);
+            F::copy(r.X, X3);
+            F::copy(r.Y, Y3);
+            F::copy(r.Z, Z3);
+        }
+    }
+    ECB_DEV static void to_cached(cached& c, const pt& p) {
+        F::copy(c.X, p.X);
+        F::copy(c.Y, p.Y);
+        F::copy(c.Z, p.Z);
+        F::sqr_ni(c.ZZ, p.Z);
+        F::mul_ni(c.ZZZ, c.ZZ, p.Z);
+    }
+    ECB_DEV static void cached_from_affine(cached& c, const fe& x, const fe& y) {
+        F::copy(c.X, x);
+        F::copy(c.Y, y);
+        F::set_one(c.Z);
+        F::set_one(c.ZZ);
+        F::set_one(c.ZZZ);
+    }
+    // r = p + q, q a finite table entry (never infinity).  add-2007-bl with the Z2 powers cached:
+    // 10M + 4S; QAFF (Z2 = 1): 7M + 4S (madd-2007-bl).
+    template <bool QAFF>
+    ECB_DEV static void add(pt& r, const pt& p, const cached& q) {
+        if (F::is_zero(p.Z)) {  // infinity + q
+            F::copy(r.X, q.X);
+            F::copy(r.Y, q.Y);
+            if (QAFF) F::set_one(r.Z); else F::copy(r.Z, q.Z);
+            return;
+        }
+        fe Z1Z1, U1, U2, S1, S2, H, I, J, rr, V, t, X3, Y3, Z3;
+        F::sqr_ni(Z1Z1, p.Z);
+        if (QAFF) F::copy(U1, p.X); else F::mul_ni(U1, p.X, q.ZZ);
+        F::mul_ni(U2, q.X, Z1Z1);
+        if (QAFF) F::copy(S1, p.Y); else F::mul_ni(S1, p.Y, q.ZZZ);
+        F::mul_ni(t, p.Z, Z1Z1);
+        F::mul_ni(S2, q.Y, t);
+        F::sub(H, U2, U1);
+        F::sub(rr, S2, S1);
+        if (F::is_zero(H)) {
+            if (F::is_zero(rr)) {  // p == q: double
+                dbl(r, p);
+            } else {               // p == -q
+                set_inf(r);
+            }
+            return;
+        }
+        fe HH;
+        F::dbl(rr, rr);             // r = 2 (S2 - S1)
+        F::sqr_ni(HH, H);
+        F::dbl(I, HH);
+        F::dbl(I, I);               // I = 4 H^2
+        F::mul_ni(J, H, I);
+        F::mul_ni(V, U1, I);
+        F::sqr_ni(X3, rr);
+        F::sub(X3, X3, J);
+        F::sub(X3, X3, V);
+        F::sub(X3, X3, V);
+        F::sub(t, V, X3);
+        F::mul_ni(Y3, rr, t);
+        F::mul_ni(t, S1, J);
+        F::dbl(t, t);
+        F::sub(Y3, Y3, t);
+        if (QAFF) {
+            F::add(t, p.Z, H);      // Z3 = (Z1 + H)^2 - Z1Z1 - HH = 2 Z1 H
+            F::sqr_ni(Z3, t);
+            F::sub(Z3, Z3, Z1Z1);
+            F::sub(Z3, Z3, HH);
+        } else {
+            F::add(t, p.Z, q.Z);
+            F::sqr_ni(Z3, t);
+            F::sub(Z3, Z3, Z1Z1);
+            F::sub(Z3, Z3, q.ZZ);
+            F::mul_ni(Z3, Z3, H);
+        }
+        F::copy(r.X, X3);
+        F::copy(r.Y, Y3);
+        F::copy(r.Z, Z3);
+    }
+    // r = p + (neg ? -q : q) with q = the cached entry stored at `e` (5N words: X, Y, Z, Z^2, Z^3).
+    // Same formulas as add<false>; the entry's fields are loaded where they are consumed so that
+    // only one of them is live at a time (the whole entry would cost 5N registers).
+    template <class LD>
+    ECB_DEV static void add_mem(pt& r, const pt& p, const u32* e, u32 neg, LD ld) {
+        fe q;
+        if (F::is_zero(p.Z)) {  // infinity + q
+            ld(r.X.v, e);
+            ld(q.v, e + N);
+            F::neg(r.Y, q);
+            F::select(r.Y, neg, r.Y, q);
+            ld(r.Z.v, e + 2 * N);
+            return;
+        }
+        fe Z1Z1, U1, U2, S1, S2, H, I, J, rr, V, t, X3, Y3, Z3, HH;
+        F::sqr_ni(Z1Z1, p.Z);
+        ld(q.v, e + 3 * N);                 // Z2^2
+        F::mul_ni(U1, p.X, q);
+        ld(q.v, e);                         // X2
+        F::mul_ni(U2, q, Z1Z1);
+        F::sub(H, U2, U1);
+        ld(q.v, e + 4 * N);                 // Z2^3
+        F::mul_ni(S1, p.Y, q);
+        F::mul_ni(t, p.Z, Z1Z1);
+        ld(q.v, e + N);                     // Y2
+        F::mul_ni(S2, q, t);
+        F::neg(t, S2);
+        F::select(S2, neg, t, S2);
+        F::sub(rr, S2, S1);
+        if (F::is_zero(H)) {
+            if (F::is_zero(rr)) {
+                dbl(r, p);
+            } else {
+                set_inf(r);
+            }
+            return;
+        }
+        F::dbl(rr, rr);
+        F::sqr_ni(HH, H);
+        F::dbl(I, HH);
+        F::dbl(I, I);
+        F::mul_ni(J, H, I);
+        F::mul_ni(V, U1, I);
+        F::sqr_ni(X3, rr);
+        F::sub(X3, X3, J);
+        F::sub(X3, X3, V);
+        F::sub(X3, X3, V);
+        F::sub(t, V, X3);
+        F::mul_ni(Y3, rr, t);
+        F::mul_ni(t, S1, J);
+        F::dbl(t, t);
+        F::sub(Y3, Y3, t);
+        ld(q.v, e + 2 * N);                 // Z2
+        F::add(t, p.Z, q);
+        F::sqr_ni(Z3, t);
+        F::sub(Z3, Z3, Z1Z1);
+        ld(q.v, e + 3 * N);                 // Z2^2 again
+        F::sub(Z3, Z3, q);
+        F::mul_ni(Z3, Z3, H);
+        F::copy(r.X, X3);
+        F::copy(r.Y, Y3);
+        F::copy(r.Z, Z3);
+    }
+    ECB_DEV static void cached_cneg(cached& c, u32 neg) {
+        fe ny;
+        F::neg(ny, c.Y);
+        F::select(c.Y, neg, ny, c.Y);
     }
 };
 

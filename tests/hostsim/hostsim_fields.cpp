@@ -3,8 +3,7 @@
 // sequences can be checked on a machine without a GPU.
 #define ECB_HOSTSIM 1
 #include "../../eccoxide_b200/csrc/fe25519.cuh"
-#include "../../eccoxide_b200/csrc/mont.cuh"
-#include "../../eccoxide_b200/csrc/params_gen.cuh"
+#include "../../eccoxide_b200/csrc/mont_kinds.cuh"
 #include <string.h>
 using namespace ecb;
 

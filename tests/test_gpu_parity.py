@@ -460,7 +460,8 @@ def test_device_resident_entry_points_match_host_entry_points(ctx):
     assert np.array_equal(d_out.cpu().numpy(), ctx.ed25519_mul_base(kb))
     k, u = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
     d_o = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
-    ctx.dev_call("ecb_x25519_dev", 0, torch.from_numpy(k).cuda().data_ptr(), torch.from_numpy(u).cuda().data_ptr(), n, d_o.data_ptr(), st)
+    d_kk, d_u = torch.from_numpy(k).cuda(), torch.from_numpy(u).cuda()  # keep alive: the allocator reuses freed blocks
+    ctx.dev_call("ecb_x25519_dev", 0, d_kk.data_ptr(), d_u.data_ptr(), n, d_o.data_ptr(), st)
     torch.cuda.synchronize()
     assert np.array_equal(d_o.cpu().numpy(), ctx.x25519(k, u))
     # invalid element is reported through ecb_dev_status

@@ -70,14 +70,23 @@ def test_montgomery_fields(hs, field, mod, n):
     r = np.zeros(n, dtype=np.uint32)
     cases = [(0, 0), (1, mod - 1), (mod - 1, mod - 1), (Rm % mod, 1)]
     cases += [(int.from_bytes(g.bytes(48), "little") % mod, int.from_bytes(g.bytes(48), "little") % mod) for _ in range(100)]
+    loose = field == 0  # p256 field elements are kept "loose" (< 2^256, congruent): see mont.cuh
+    if loose:  # any 256-bit value is a valid operand, including the ones that need a second fold
+        cases += [(Rm - 1, Rm - 1), (Rm - 1, mod), (mod, mod), (Rm - 2**200, Rm - 5), (0, Rm - 1), (3, Rm - 2), (mod + 1, 2)]
+        cases += [(int.from_bytes(g.bytes(32), "little"), int.from_bytes(g.bytes(32), "little")) for _ in range(100)]
     for a, b in cases:
         aw, bw = words(a, n), words(b, n)
         for op, exp in ((0, a * b * Ri), (1, a * a * Ri), (2, a + b), (3, a - b), (4, -a), (5, a * Rm), (7, a * Ri)):
+            if op == 5 and a >= mod:
+                continue  # to_mont takes canonical wire values
             f.hs_mont(field, op, p(aw), p(bw), p(r))
-            assert val(r) == exp % mod, (field, op)
+            if loose and op != 7:
+                assert val(r) % mod == exp % mod and val(r) < Rm, (field, op, a, b)
+            else:
+                assert val(r) == exp % mod, (field, op)
     a = cases[5][0]
     f.hs_mont(field, 6, p(words(a * Rm % mod, n)), p(words(0, n)), p(r))
-    assert val(r) == pow(a, -1, mod) * Rm % mod
+    assert val(r) % mod == pow(a, -1, mod) * Rm % mod
 
 
 def test_ed25519_mul_base_and_table(hs, golden, coracle):
@@ -128,7 +137,7 @@ def test_wei_mul(hs, golden, coracle, cid, curve):
     _, k = hs
     c = R.WCURVES[curve]
     g = rng(10 + cid)
-    kb = np.concatenate([rows([v.to_bytes(c.sbytes, "big") for v in wei_edge_scalars(golden, c.n)[:12]]), scalars_mod(g, 12, c.n, c.sbytes, "big")])
+    kb = np.concatenate([rows([v.to_bytes(c.sbytes, "big") for v in wei_edge_scalars(golden, c.n)] + [(c.n - j).to_bytes(c.sbytes, "big") for j in range(1, 21)]), scalars_mod(g, 6, c.n, c.sbytes, "big")])
     n = kb.shape[0]
     pts = wei_points(curve, g, n)
     out = np.zeros((n, 2 * c.fbytes), dtype=np.uint8)
