@@ -36,6 +36,8 @@ sys.path.insert(0, ROOT)
 WORK = {
     "ed25519_mul_base": 41688,
     "ed25519_mul": 284888,
+    "p256_mul_base": 896 * 64 + 3 * 64,      # reference comb: 64 complete additions x 14 M + affine share
+    "bls12_381_g1_mul_base": 896 * 300 + 3 * 300,
     "x25519": 155864,
     "p256_mul": 261420,
     "p256_ecdsa_verify": 296900,
@@ -54,6 +56,8 @@ WORKLOADS = {
     "p384_mul": (18, 144, 97, "configs[4] sweep member"),
     "x448": (18, 112, 56, "configs[4] sweep member (X448 stands in for edwards448)"),
     "ed25519_mul": (18, 96, 64, "north star: variable-base Ed25519 Point::mul"),
+    "p256_mul_base": (20, 32, 65, "north star: fixed-base p256r1 Point::mul_base (comb)"),
+    "bls12_381_g1_mul_base": (20, 32, 97, "north star: fixed-base BLS12-381 G1 Point::mul_base (comb)"),
 }
 HEADLINE = "ed25519_mul_base"
 EXTRA_DEFAULT = ["ed25519_mul_base_2p16", "x25519", "p256_mul", "p256_ecdsa_verify", "bls12_381_g1_mul"]
@@ -93,6 +97,10 @@ def make_inputs(name, n, ctx, seed):
         pts, inf = ctx.wei_mul_base(curve, rand_scalars(g, uniq, sb, clr, "big"))
         assert not inf.any()
         return [rand_scalars(g, n, sb, clr, "big"), tile(pts)]
+    if base == "p256_mul_base":
+        return [rand_scalars(g, n, 32, 1, "big")]
+    if base == "bls12_381_g1_mul_base":
+        return [rand_scalars(g, n, 32, 2, "big")]
     if base == "p256_ecdsa_verify":
         from oracle import pyref as R
 
@@ -122,6 +130,7 @@ def make_inputs(name, n, ctx, seed):
 OUT_SHAPES = {
     "ed25519_mul_base": [64], "ed25519_mul": [64], "x25519": [32], "x448": [56],
     "p256_mul": [64, 1], "p384_mul": [96, 1], "bls12_381_g1_mul": [96, 1], "p256_ecdsa_verify": [1],
+    "p256_mul_base": [64, 1], "bls12_381_g1_mul_base": [96, 1],
 }
 
 
@@ -141,6 +150,8 @@ def dev_launch(ctx, name, ins, outs, n, stream):
     elif base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
         cid = {"p256_mul": 0, "p384_mul": 1, "bls12_381_g1_mul": 2}[base]
         ctx.dev_call("ecb_wei_mul_dev", 0, cid, p[0], p[1], n, o[0], o[1], stream)
+    elif base in ("p256_mul_base", "bls12_381_g1_mul_base"):
+        ctx.dev_call("ecb_wei_mul_base_dev", 0, 0 if base == "p256_mul_base" else 2, p[0], n, o[0], o[1], stream)
     elif base == "p256_ecdsa_verify":
         ctx.dev_call("ecb_ecdsa_verify_hashed_dev", 0, 0, p[0], p[1], p[2], n, o[0], stream)
     else:
@@ -162,6 +173,8 @@ def host_call(ctx, name, ins, outs=None):
     if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
         curve = {"p256_mul": "p256r1", "p384_mul": "p384r1", "bls12_381_g1_mul": "bls12_381_g1"}[base]
         return list(ctx.wei_mul(curve, ins[0], ins[1], out=o[0], out_inf=o[1]))
+    if base in ("p256_mul_base", "bls12_381_g1_mul_base"):
+        return list(ctx.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], out=o[0], out_inf=o[1]))
     if base == "p256_ecdsa_verify":
         return [ctx.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], out=o[0])]
     raise ValueError(name)
@@ -180,6 +193,8 @@ def oracle_call(C, name, ins, nthreads):
     if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
         curve = {"p256_mul": "p256r1", "p384_mul": "p384r1", "bls12_381_g1_mul": "bls12_381_g1"}[base]
         return list(C.wei_mul(curve, ins[0], ins[1], nthreads=nthreads))
+    if base in ("p256_mul_base", "bls12_381_g1_mul_base"):
+        return list(C.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], nthreads))
     if base == "p256_ecdsa_verify":
         return [C.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], nthreads)]
     raise ValueError(name)
@@ -392,10 +407,12 @@ def main():
     ap.add_argument("--extra", default=",".join(EXTRA_DEFAULT), help="comma list of further workloads reported under 'workloads' ('' = none)")
     ap.add_argument("--extra-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--profile-run", action="store_true", help="1 warm-up + 1 step per workload, for ncu captures only (numbers are not bench values)")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--comb-w", type=int, default=None)
+    ap.add_argument("--opt", action="append", default=[], help="library option key=value (ecb_set_option)")
     args = ap.parse_args()
-    if args.warmup < 3:
+    if args.warmup < 3 and not args.profile_run:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -418,6 +435,9 @@ def main():
     ctx = Context(devices=[local])
     if args.comb_w:
         ctx.set_option("ed25519_comb_w", args.comb_w)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        ctx.set_option(key, int(val))
 
     # IMAD peak, measured live: a 32x32->64 multiply-accumulate is two passes of the 32-bit multiplier
     # (IMAD.WIDE or IMAD.LO + IMAD.HI); take the best of the three ways of issuing it
@@ -440,7 +460,7 @@ def main():
     clocks = sampler.summary(r["t0"], r["t1"]) if sampler else None
     ops_s = world * n / (r["ms_per_step"] * 1e-3)
     W = work_of(name)
-    e2e_s, e2e_out = measure_e2e(torch, ctx, name, n, max(3, min(args.steps, 10)), args.warmup, r["ins_h"], dist)
+    e2e_s, e2e_out = measure_e2e(torch, ctx, name, n, 1 if args.profile_run else max(3, min(args.steps, 10)), args.warmup, r["ins_h"], dist)
 
     line = None
     if rank == 0:
@@ -486,7 +506,7 @@ def main():
     for x in extras:
         nx = 1 << WORKLOADS[x][0]
         try:
-            rx = measure_device(torch, ctx, x, nx, args.extra_steps, 3, 0xECC00002 + rank, dist)
+            rx = measure_device(torch, ctx, x, nx, args.extra_steps, 1 if args.profile_run else 3, 0xECC00002 + rank, dist)
             v = world * nx / (rx["ms_per_step"] * 1e-3)
             wl[x] = {"value": v, "ms_per_step": rx["ms_per_step"], "batch_per_gpu": nx, "mac32_per_op": work_of(x),
                      "roofline_frac": (nx * work_of(x) / (rx["ms_per_step"] * 1e-3) / 1e12) / peak if peak else None,

@@ -49,6 +49,7 @@ SIGNATURES = {
     "ecb_ed25519_mul_dev": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_x25519_dev": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_wei_mul_dev": (_int, [_vp, _int, _int, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "ecb_wei_mul_base_dev": (_int, [_vp, _int, _int, _vp, _sz, _vp, _vp, _vp]),
     "ecb_x448_dev": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ed25519_verify_prehashed_dev": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_verify_hashed_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp]),

@@ -16,6 +16,13 @@ int dev_wei_mul_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, co
                      u32* d_out, unsigned char* d_inf, cudaStream_t s);
 int dev_wei_mul_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, const unsigned char* d_inf_in, size_t n,
                     u32* d_out, unsigned char* d_inf, cudaStream_t s);
+// fixed base (comb): d_out / d_inf as dev_wei_mul_*; *_table makes sure the device comb exists
+int dev_wei_mul_base_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_mul_base_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_mul_base_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_table_p256(ecb_ctx* ctx, DevCtx& d);
+int dev_wei_table_p384(ecb_ctx* ctx, DevCtx& d);
+int dev_wei_table_bls(ecb_ctx* ctx, DevCtx& d);
 int dev_ecdsa_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const u32* d_z, const u32* d_rs, size_t n, unsigned char* d_ok,
                    cudaStream_t s);
 int dev_ecdsa_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const u32* d_z, const u32* d_rs, size_t n, unsigned char* d_ok,

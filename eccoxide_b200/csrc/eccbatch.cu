@@ -77,6 +77,8 @@ void ecb_destroy(ecb_ctx* ctx) {
         }
         for (auto& r : d->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); cudaEventDestroy(r.c); }
         if (d->ed_table) cudaFree(d->ed_table);
+        for (u32* t : d->wei_table)
+            if (t) cudaFree(t);
         delete d;
     }
     delete ctx;
@@ -91,6 +93,16 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "ed25519_comb_w")) {
         if (value < 4 || value > 16) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_comb_w must be in 4..16");
         ctx->opt_ed_w = value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "p256r1_comb_w") || !strcmp(key, "p384r1_comb_w") || !strcmp(key, "bls12_381_g1_comb_w")) {
+        if (value < 4 || value > 16) return set_err(ctx, ECB_ERR_INVALID_ARG, "comb width must be in 4..16");
+        ctx->opt_wei_w[key[1] == '2' ? 0 : (key[1] == '3' ? 1 : 2)] = value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "inv_per_thread")) {
+        if (value < 1 || value > 4096) return set_err(ctx, ECB_ERR_INVALID_ARG, "inv_per_thread must be in 1..4096");
+        for (DevCtx* d : ctx->devs) d->inv_per_thread = (size_t)value;
         return ECB_OK;
     }
     if (!strcmp(key, "chunk")) {
@@ -217,6 +229,16 @@ static int run_sharded(ecb_ctx* ctx, size_t n, const std::vector<HostArg>& ins, 
     return ECB_OK;
 }
 
+static int dev_wei_mul_base(ecb_ctx* ctx, DevCtx& d, int curve, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf,
+                            cudaStream_t s) {
+    switch (curve) {
+        case ECB_CURVE_P256R1: return dev_wei_mul_base_p256(ctx, d, d_k, n, d_out, d_inf, s);
+        case ECB_CURVE_P384R1: return dev_wei_mul_base_p384(ctx, d, d_k, n, d_out, d_inf, s);
+        case ECB_CURVE_BLS12_381_G1: return dev_wei_mul_base_bls(ctx, d, d_k, n, d_out, d_inf, s);
+    }
+    return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
+}
+
 static int curve_sizes(int curve, size_t& fb, size_t& sb) {
     switch (curve) {
         case ECB_CURVE_P256R1: fb = 32; sb = 32; return ECB_OK;
@@ -296,11 +318,9 @@ int ecb_wei_mul_base(ecb_ctx* ctx, int curve, const uint8_t* k_be, size_t n, uin
     size_t fb, sb;
     if (curve_sizes(curve, fb, sb)) return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
     if (n && (!k_be || !out_xy)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
-    // points == nullptr selects the generator inside the kernel
     return run_sharded(ctx, n, {{k_be, sb}}, {{out_xy, 2 * fb}, {out_inf, 1}}, true, bad_index,
                        [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
-                           return dev_wei_mul(ctx, d, curve, (const u32*)in[0], nullptr, nullptr, cn, (u32*)o[0],
-                                              (unsigned char*)o[1], s);
+                           return dev_wei_mul_base(ctx, d, curve, (const u32*)in[0], cn, (u32*)o[0], (unsigned char*)o[1], s);
                        });
 }
 int ecb_ecdsa_verify_hashed(ecb_ctx* ctx, int curve, const uint8_t* q_xy, const uint8_t* z_be, const uint8_t* rs_be,
@@ -348,6 +368,12 @@ int ecb_wei_mul_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, const void
     CU(cudaSetDevice(d->dev));
     return dev_wei_mul(ctx, *d, curve, (const u32*)d_k, (const u32*)d_xy, nullptr, n, (u32*)d_out, (unsigned char*)d_inf,
                        (cudaStream_t)stream);
+}
+int ecb_wei_mul_base_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, size_t n, void* d_out, void* d_inf, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_wei_mul_base(ctx, *d, curve, (const u32*)d_k, n, (u32*)d_out, (unsigned char*)d_inf, (cudaStream_t)stream);
 }
 int ecb_x448_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);

@@ -44,9 +44,12 @@ struct DevCtx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;            // = slots[0].stream: table builds, probes
     Slot slots[ECB_NSLOT];
+    size_t inv_per_thread = 32;               // batch-inversion chain length (option "inv_per_thread"; 8: 0.31 ms, 16: 0.24, 32: 0.20, 64: 0.20 at n = 2^20)
     Slot* cur = &slots[0];                    // slot whose buffers the dev_* functions use (calls are serialised by `mu`)
     u32* ed_table = nullptr;
     int ed_w = 0, ed_nwin = 0;
+    u32* wei_table[3] = {nullptr, nullptr, nullptr};  // generator combs of p256r1, p384r1, bls12_381 G1
+    int wei_w[3] = {0, 0, 0}, wei_nwin[3] = {0, 0, 0};
     std::mutex mu;
     // optional per-kernel timing (ecb_set_option "profile"): events recorded on the launching stream
     // around the scalar-mult kernel(s) [a,b] and the batch-inversion finisher [b,c] of every call
@@ -58,8 +61,9 @@ struct ecb_ctx {
     std::vector<DevCtx*> devs;
     std::string err;
     std::mutex err_mu;
+    long opt_wei_w[3] = {16, 14, 16};  // comb widths: 36 MB, 22 MB, 50 MB tables
     long opt_ed_w = 16;  // 16 windows x 2^15 niels entries (50 MB, L2-resident): measured best on B200
-    size_t opt_chunk = (size_t)1 << 18;  // elements per pipeline chunk (3 slots in flight per device)
+    size_t opt_chunk = (size_t)1 << 17;  // elements per pipeline chunk (3 slots in flight per device; measured best of 2^16..2^19)
     long opt_profile = 0;
     std::atomic<unsigned long long> launches{0};
 };
@@ -101,7 +105,8 @@ static inline unsigned grid_for(size_t n) { return (unsigned)((n + ECB_TPB - 1) 
 // number of threads for the batch inversion: ~16 elements per thread, but never fewer threads
 // than fill the machine once
 static inline size_t inv_threads(const DevCtx& d, size_t n) {
-    size_t T = (n + 15) / 16;
+    size_t per = d.inv_per_thread ? d.inv_per_thread : 32;
+    size_t T = (n + per - 1) / per;
     size_t fill = (size_t)d.sm_count * 256;
     if (T < fill) T = fill;
     if (T > n) T = n;

@@ -544,6 +544,112 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
     plane_st<N>(planes + 2 * (size_t)N * n, n, idx, acc.Z.v);
 }
 
+// =======================================================================================
+// Weierstrass fixed base: k*G from a signed-digit comb (replaces Point::mul_base,
+// fiat/curve_macros.rs:55 -> projective.rs:965 mul_base_table_am3 / :945 _a0 and the tables of
+// src/params/comb/{p256r1,p384r1,bls12_381}.rs — regenerated on the device, wider windows):
+//   table[(i * half + (j-1)) * 2N ..] = (x, y) of j * 2^(W i) * G in the Montgomery domain,
+//   j = 1..half = 2^(W-1), i = 0..nwin-1, nwin = ceil((SBITS + 1) / W).
+// One mixed Jacobian addition (7M + 4S) per window, no doublings.
+// =======================================================================================
+template <class C>
+ECB_DEV void wei_comb_accumulate(typename WeiJ<C>::pt& acc, const u32* k, int nwords, const u32* table, int W, int nwin) {
+    typedef WeiJ<C> J;
+    typedef typename C::F FT;
+    constexpr int N = FT::N;
+    const u32 half = 1u << (W - 1);
+    ECB_NOUNROLL
+    for (int i = 0; i < nwin; i++) {
+        u32 neg;
+        u32 d = booth_digit(k, nwords, W, i, neg);
+        if (d != 0) {
+            typename J::cached e;
+            const u32* src = table + ((size_t)i * half + (d - 1)) * 2 * N;
+            ld_words<N>(e.X.v, src);
+            ld_words<N>(e.Y.v, src + N);
+            J::cached_cneg(e, neg);
+            J::template add<true>(acc, acc, e);
+        }
+    }
+}
+template <class C>
+ECB_DEV void wei_mul_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin, u32* planes,
+                               unsigned long long* status) {
+    typedef WeiJ<C> J;
+    typedef typename C::FN FNT;
+    constexpr int N = C::F::N;
+    constexpr int NS = C::SB / 4;
+    u32 k[NS + 1];
+    ld_words_be<NS>(k, scalars + idx * NS);
+    k[NS] = 0;
+    if (!FNT::is_canonical_words(k)) {
+        report_bad(status, idx, ST_NONCANONICAL_SCALAR);
+        ECB_UNROLL
+        for (int i = 0; i < NS; i++) k[i] = 0;
+    }
+    typename J::pt acc;
+    J::set_inf(acc);
+    wei_comb_accumulate<C>(acc, k, NS + 1, table, W, nwin);
+    plane_st<N>(planes + 0 * (size_t)N * n, n, idx, acc.X.v);
+    plane_st<N>(planes + 1 * (size_t)N * n, n, idx, acc.Y.v);
+    plane_st<N>(planes + 2 * (size_t)N * n, n, idx, acc.Z.v);
+}
+// comb-table builder: entry (i, j) = j * 2^(W i) * G by double-and-add on s = j << (W i)
+template <class C>
+ECB_DEV void wei_table_point_body(size_t e, size_t ntab, int W, int nwin, u32* planes) {
+    typedef WeiJ<C> J;
+    typedef typename C::F FT;
+    constexpr int N = FT::N;
+    constexpr int SW = 14;  // scalar words: W * nwin <= 448 bits
+    const u32 half = 1u << (W - 1);
+    u32 i = (u32)(e / half), j = (u32)(e % half) + 1;
+    u32 s[SW];
+    ECB_UNROLL
+    for (int t = 0; t < SW; t++) s[t] = 0;
+    int sh = W * (int)i;
+    int wd = sh >> 5, b = sh & 31;
+    u32 lo = j << b, hi = b ? (j >> (32 - b)) : 0u;
+    for (int t = 0; t < SW; t++) {
+        if (t == wd) s[t] |= lo;
+        if (t == wd + 1) s[t] |= hi;
+    }
+    typename J::cached g;
+    ECB_UNROLL
+    for (int t = 0; t < N; t++) { g.X.v[t] = C::gx(t); g.Y.v[t] = C::gy(t); }
+    typename J::pt acc;
+    J::set_inf(acc);
+    ECB_NOUNROLL
+    for (int bit = W * nwin - 1; bit >= 0; bit--) {
+        J::dbl(acc, acc);
+        u32 wv = 0;
+        for (int t = 0; t < SW; t++)
+            if (t == (bit >> 5)) wv = s[t];
+        if ((wv >> (bit & 31)) & 1) J::template add<true>(acc, acc, g);
+    }
+    plane_st<N>(planes + 0 * (size_t)N * ntab, ntab, e, acc.X.v);
+    plane_st<N>(planes + 1 * (size_t)N * ntab, ntab, e, acc.Y.v);
+    plane_st<N>(planes + 2 * (size_t)N * ntab, ntab, e, acc.Z.v);
+}
+template <class C>
+struct FinWeiTable {  // out: comb-table entry (x, y), Montgomery domain, canonical, 2N words
+    typedef typename C::F FT;
+    const u32* planes; size_t n; u32* out;
+    ECB_DEV void operator()(size_t idx, const typename FT::el& zinv, u32) const {
+        constexpr int N = FT::N;
+        typename FT::el X, Y, x, y, zi2;
+        plane_ld<N>(X.v, planes, n, idx);
+        plane_ld<N>(Y.v, planes + (size_t)N * n, n, idx);
+        FT::sqr(zi2, zinv);
+        FT::mul(x, X, zi2);
+        FT::mul(zi2, zi2, zinv);
+        FT::mul(y, Y, zi2);
+        FT::canon(x, x);
+        FT::canon(y, y);
+        st_words<N>(out + idx * 2 * N, x.v);
+        st_words<N>(out + idx * 2 * N + N, y.v);
+    }
+};
+
 template <class C>
 struct FinWeiXY {  // out: x_be || y_be (canonical, out of the Montgomery domain) + infinity flag
     typedef typename C::F FT;

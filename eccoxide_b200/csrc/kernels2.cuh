@@ -277,8 +277,9 @@ struct FinScalarInv {
 
 template <class C>
 ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z_be, const u32* rs_be, const u32* sp,
-                             unsigned char* valid, u32* tbl, u32* planes, unsigned long long* status) {
-    typedef Wei<C> W;
+                             unsigned char* valid, u32* tbl, const u32* gtable, int W, int nwin, u32* planes,
+                             unsigned long long* status) {
+    typedef Wei<C> WP;
     typedef WeiJ<C> J;
     typedef typename C::F FT;
     typedef typename C::FN FN;
@@ -290,11 +291,11 @@ ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z
     u32 xw[N], yw[N];
     ld_words_be<N>(xw, q_be + idx * 2 * N);
     ld_words_be<N>(yw, q_be + idx * 2 * N + N);
-    fe qx, qy, gx, gy;
+    fe qx, qy;
     FT::to_mont(qx, xw);
     FT::to_mont(qy, yw);
     u32 q_ok = 1;
-    if (!(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(qx, qy))) {
+    if (!(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && WP::on_curve(qx, qy))) {
         report_bad(status, idx, ST_BAD_POINT);
         q_ok = 0;
     }
@@ -322,11 +323,8 @@ ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z
         for (int i = 0; i < NS; i++) { u1[i] = u1e.v[i]; u2[i] = u2e.v[i]; }
         u1[NS] = 0;
         u2[NS] = 0;
-        // tables: tbl[0..8) = j*Q, tbl[8..16) = j*G  (Jacobian, cached Z powers)
-        ECB_UNROLL
-        for (int i = 0; i < N; i++) { gx.v[i] = C::gx(i); gy.v[i] = C::gy(i); }
+        // u2*Q: signed 4-bit windows over tbl[0..8) = j*Q (Jacobian, cached Z powers)
         wei_build_table8<C>(tbl, qx, qy);
-        wei_build_table8<C>(tbl + 8 * ES, gx, gy);
         constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
         ECB_NOUNROLL
         for (int i = NWIN - 1; i >= 0; i--) {
@@ -334,13 +332,19 @@ ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z
                 ECB_NOUNROLL
                 for (int r = 0; r < 4; r++) J::dbl(acc, acc);
             }
-            ECB_NOUNROLL
-            for (int which = 0; which < 2; which++) {
-                u32 neg;
-                u32 d = booth_digit(which == 0 ? u2 : u1, NS + 1, 4, i, neg);
-                // skipping a zero digit: verification is variable time like mul_vartime
-                if (d != 0) J::add_mem(acc, acc, tbl + (which * 8 + (d - 1)) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
-            }
+            u32 neg;
+            u32 d = booth_digit(u2, NS + 1, 4, i, neg);
+            // skipping a zero digit: verification is variable time like mul_vartime
+            if (d != 0) J::add_mem(acc, acc, tbl + (d - 1) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
+        }
+        // u1*G from the generator comb (Point::mul_base), then one general addition
+        typename J::pt accg;
+        J::set_inf(accg);
+        wei_comb_accumulate<C>(accg, u1, NS + 1, gtable, W, nwin);
+        if (!J::is_inf(accg)) {
+            typename J::cached cg;
+            J::to_cached(cg, accg);
+            J::template add<false>(acc, acc, cg);
         }
     }
     plane_st<N>(planes + 0 * (size_t)N * n, n, idx, acc.X.v);

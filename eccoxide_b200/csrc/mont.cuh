@@ -24,6 +24,8 @@ struct fe_mont {
 // kind 1 = p256: -p^-1 = 1 (mod 2^96) and p = 2^256 - 2^224 + 2^192 + 2^96 - 1, so the Montgomery
 // reduction of a 512-bit product is three rounds of shifted additions / subtractions of
 // m = T mod 2^96 — no multiplication at all; product = N^2, square = N(N+1)/2 IMAD.WIDE.
+// kind 2 = p384: -p^-1 = 1 + 2^32 + 2^64 (mod 2^96) and p = 2^384 - 2^128 - 2^96 + 2^32 - 1: four
+// rounds of 96 bits, each a handful of shifted additions / subtractions of m — again no multiply.
 template <class P>
 struct MontKind {
     static constexpr int kind = 0;
@@ -131,7 +133,72 @@ struct Mont {
         return subc(0u, 0u) & 1u;
     }
 
+    // ---- p384: one round at limb offset O.  t = T[O..O+3); m = t (1 + 2^32 + 2^64) mod 2^96;
+    // T += m p 2^(32 O) with m p = m 2^384 - m 2^128 - m 2^96 + m (2^32 - 1).
+    // t + (m (2^32 - 1) mod 2^96) = k 2^96 with k = [t != 0], so limbs O..O+2 vanish and the rest is
+    //   V = (hi32(m (2^32 - 1)) + k) + m 2^(32*9) - m (1 + 2^32)        (relative limbs 3..14, V >= 0;
+    //   m (1 + 2^32) has five limbs)
+    template <int O>
+    ECB_DEV static void p384_round(u32* T) {
+        const u32 t0 = T[O], t1 = T[O + 1], t2 = T[O + 2];
+        const u32 m0 = t0;
+        const u32 m1 = add_cc(t1, t0);
+        const u32 a2 = addc(t2, t1);
+        const u32 m2 = a2 + t0;
+        const u32 k = (t0 | t1 | t2) ? 1u : 0u;
+        // d3 = top limb of m (2^32 - 1) = [0, m0, m1, m2] - [m0, m1, m2, 0]
+        (void)sub_cc(0u, m0);
+        (void)subc_cc(m0, m1);
+        (void)subc_cc(m1, m2);
+        const u32 d3 = subc(m2, 0u);
+        const u32 e3 = add_cc(d3, k);
+        const u32 ce = addc(0u, 0u);
+        // Neg = m (1 + 2^32): 4 limbs
+        const u32 n1 = add_cc(m1, m0);
+        const u32 n2 = addc_cc(m2, m1);
+        const u32 n3 = addc_cc(m2, 0u);
+        const u32 n4 = addc(0u, 0u);
+        // V = [e3, ce, 0, 0, 0.., m0, m1, m2 at rel 12..14] - [m0, n1, n2, n3, n4]
+        const u32 v3 = sub_cc(e3, m0);
+        const u32 v4 = subc_cc(ce, n1);
+        const u32 v5 = subc_cc(0u, n2);
+        const u32 v6 = subc_cc(0u, n3);
+        const u32 v7 = subc_cc(0u, n4);
+        const u32 vm = subc_cc(0u, 0u);   // rel 8..11: 0 - borrow, the borrow rides through unchanged
+        const u32 v12 = subc_cc(m0, 0u);
+        const u32 v13 = subc_cc(m1, 0u);
+        const u32 v14 = subc(m2, 0u);
+        T[O + 3] = add_cc(T[O + 3], v3);
+        T[O + 4] = addc_cc(T[O + 4], v4);
+        T[O + 5] = addc_cc(T[O + 5], v5);
+        T[O + 6] = addc_cc(T[O + 6], v6);
+        T[O + 7] = addc_cc(T[O + 7], v7);
+        ECB_UNROLL
+        for (int j = 8; j <= 11; j++) T[O + j] = addc_cc(T[O + j], vm);
+        T[O + 12] = addc_cc(T[O + 12], v12);
+        T[O + 13] = addc_cc(T[O + 13], v13);
+        T[O + 14] = addc_cc(T[O + 14], v14);
+        ECB_UNROLL
+        for (int j = O + 15; j <= 24; j++) T[j] = addc_cc(T[j], 0u);
+        (void)addc(0u, 0u);
+    }
+    // T: 25 limbs, T[24] = 0 on entry, value < p^2.  r = T / 2^384 mod p, canonical.
+    ECB_DEV static void p384_reduce(el& r, u32* T) {
+        p384_round<0>(T);
+        p384_round<3>(T);
+        p384_round<6>(T);
+        p384_round<9>(T);
+        final_sub(r, T + 12, T[24]);
+    }
+
     ECB_DEV static void mul(el& r, const el& a, const el& b) {
+        if constexpr (MontKind<P>::kind == 2) {
+            u32 T[25];
+            mul_full<N>(T, a.v, b.v);
+            T[24] = 0;
+            p384_reduce(r, T);
+            return;
+        }
         if constexpr (MontKind<P>::kind == 1) {
             u32 T[17];
             mul_full<N>(T, a.v, b.v);
@@ -184,6 +251,13 @@ struct Mont {
         final_sub(r, t, t[N]);
     }
     ECB_DEV static void sqr(el& r, const el& a) {
+        if constexpr (MontKind<P>::kind == 2) {
+            u32 T[25];
+            sqr_full<N>(T, a.v);
+            T[24] = 0;
+            p384_reduce(r, T);
+            return;
+        }
         if constexpr (MontKind<P>::kind == 1) {
             u32 T[17];
             sqr_full<N>(T, a.v);
@@ -212,11 +286,6 @@ struct Mont {
     ECB_DEV static void mul_ni(el& r, const el& a, const el& b) { r = mul_v(a, b); }
     ECB_DEV static void sqr_ni(el& r, const el& a) { r = sqr_v(a); }
 
-    // Representation.  kind 0: canonical, every value < p (as the fiat code).  kind 1 (p256): "loose",
-    // every value < 2^256 and congruent to the element; since 2^256 < 2p a loose value is x or x + p.
-    // Carries / borrows out of 2^256 are folded with 2^256 = 2^256 - p (mod p); a second fold is
-    // needed only when both operands sit within 2^224 of 2^256, which is handled by a (practically
-    // never taken) branch.  from_mont() and is_zero()/eq() canonicalise, so nothing observable changes.
     ECB_DEV static void add(el& r, const el& a, const el& b) {
         u32 t[N];
         u32 c = add_n<N>(t, a.v, b.v);
@@ -244,6 +313,14 @@ struct Mont {
         el z;
         set_zero(z);
         sub(r, z, a);
+    }
+    // canonical representative (< p) of a possibly loose value
+    ECB_DEV static void canon(el& r, const el& a) {
+        if constexpr (MontKind<P>::kind == 1) {
+            final_sub(r, a.v, 0u);
+            return;
+        }
+        copy(r, a);
     }
     ECB_DEV static void dbl(el& r, const el& a) { add(r, a, a); }
 

@@ -10,4 +10,9 @@ struct MontKind<P256_FP> {
     static constexpr int kind = 1;
 };
 
+template <>
+struct MontKind<P384_FP> {
+    static constexpr int kind = 2;
+};
+
 }  // namespace ecb

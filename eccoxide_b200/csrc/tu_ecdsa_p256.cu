@@ -1,4 +1,6 @@
 // tu_ecdsa_p256.cu
 #define ECB_TU_CURVE CurveP256
 #define ECB_TU_FN dev_ecdsa_p256
+#define ECB_TU_CURVE_INDEX 0
+#define ECB_TU_TABLE_FN dev_wei_table_p256
 #include "tu_ecdsa.inc"

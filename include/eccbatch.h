@@ -55,7 +55,8 @@ void ecb_destroy(ecb_ctx* ctx);
 const char* ecb_last_error(ecb_ctx* ctx);
 int ecb_device_count(ecb_ctx* ctx);
 /* tunables, before first use: "ed25519_comb_w" (window width of the fixed-base comb, 4..16),
- * "chunk" (elements per device pass), "profile" (1: record CUDA events around the kernels of
+ * "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w" (generator combs of the Weierstrass curves),
+ * "chunk" (elements per pipeline chunk), "inv_per_thread" (batch-inversion chain length), "profile" (1: record CUDA events around the kernels of
  * every call on the launching stream, read back with ecb_profile_collect) */
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
@@ -112,6 +113,8 @@ int ecb_ed25519_mul_dev(ecb_ctx* ctx, int dev_index, const void* d_k_le, const v
 int ecb_x25519_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);
 int ecb_wei_mul_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_k_be, const void* d_xy_be, size_t n,
                     void* d_out_xy_be, void* d_out_inf, void* stream);
+int ecb_wei_mul_base_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_k_be, size_t n, void* d_out_xy_be,
+                         void* d_out_inf, void* stream);
 int ecb_x448_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);
 int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int dev_index, const void* d_a_enc, const void* d_r_enc, const void* d_s_le,
                                      const void* d_k_le, size_t n, void* d_ok, void* stream);

@@ -114,15 +114,49 @@ void hs_ed25519_verify(const u32* a, const u32* r, const u32* s, const u32* k, s
 }
 }
 template <class C>
+static std::vector<u32> wei_build_comb(int W, int nwin) {
+    constexpr int N = C::F::N;
+    size_t ntab = (size_t)nwin << (W - 1);
+    std::vector<u32> planes(3 * N * ntab), pf(N * ntab), table(2 * N * ntab);
+    for (size_t e = 0; e < ntab; e++) wei_table_point_body<C>(e, ntab, W, nwin, planes.data());
+    size_t T = inv_threads(ntab);
+    FinWeiTable<C> fin{planes.data(), ntab, table.data()};
+    for (size_t t = 0; t < T; t++) batch_inv_body<typename C::F>(t, T, ntab, planes.data(), pf.data(), fin);
+    return table;
+}
+template <class C>
+static unsigned long long wei_mul_base_run(const u32* k, size_t n, int W, u32* out, unsigned char* inf) {
+    constexpr int N = C::F::N;
+    int nwin = (C::SBITS + 1 + W - 1) / W;
+    std::vector<u32> table = wei_build_comb<C>(W, nwin);
+    std::vector<u32> planes(3 * N * n), pf(N * n);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) wei_mul_base_body<C>(i, n, k, table.data(), W, nwin, planes.data(), &st);
+    size_t T = inv_threads(n);
+    FinWeiXY<C> fin{planes.data(), n, out, inf};
+    for (size_t t = 0; t < T; t++) batch_inv_body<typename C::F>(t, T, n, planes.data(), pf.data(), fin);
+    return st;
+}
+extern "C" unsigned long long hs_wei_mul_base(int curve, const u32* k, size_t n, int W, u32* out, unsigned char* inf) {
+    switch (curve) {
+        case 0: return wei_mul_base_run<CurveP256>(k, n, W, out, inf);
+        case 1: return wei_mul_base_run<CurveP384>(k, n, W, out, inf);
+        case 2: return wei_mul_base_run<CurveBLSG1>(k, n, W, out, inf);
+    }
+    return 0;
+}
+template <class C>
 static unsigned long long ecdsa_run(const u32* q, const u32* z, const u32* rs, size_t n, unsigned char* ok) {
     constexpr int N = C::F::N, NS = C::FN::N;
-    std::vector<u32> planes(3 * N * n), pf((N > NS ? N : NS) * n), aux(3 * NS * n), tbl(16 * 5 * N);
+    std::vector<u32> planes(3 * N * n), pf((N > NS ? N : NS) * n), aux(3 * NS * n), tbl(8 * 5 * N);
     unsigned long long st = ~0ull;
     for (size_t i = 0; i < n; i++) ecdsa_prep_body<C>(i, n, z, rs, aux.data(), ok);
     size_t T = inv_threads(n);
     FinScalarInv<C> f1{aux.data(), n};
     for (size_t t = 0; t < T; t++) batch_inv_body<typename C::FN>(t, T, n, aux.data(), pf.data(), f1);
-    for (size_t i = 0; i < n; i++) ecdsa_main_body<C>(i, n, q, z, rs, aux.data(), ok, tbl.data(), planes.data(), &st);
+    const int W = 5, nwin = (C::SBITS + 1 + W - 1) / W;
+    std::vector<u32> gtab = wei_build_comb<C>(W, nwin);
+    for (size_t i = 0; i < n; i++) ecdsa_main_body<C>(i, n, q, z, rs, aux.data(), ok, tbl.data(), gtab.data(), W, nwin, planes.data(), &st);
     FinEcdsa<C> f2{planes.data(), n, rs, ok};
     for (size_t t = 0; t < T; t++) batch_inv_body<typename C::F>(t, T, n, planes.data(), pf.data(), f2);
     return st;

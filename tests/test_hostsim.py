@@ -21,7 +21,7 @@ def hs():
     subprocess.check_call(["make", "-s", "-j4", "-C", HS])
     f = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_fields.so"))
     k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
-    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul", "hs_wei_mul", "hs_ecdsa_verify"):
+    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_ecdsa_verify"):
         getattr(k, fn).restype = ctypes.c_ulonglong
     return f, k
 
@@ -145,10 +145,11 @@ def test_wei_mul(hs, golden, coracle, cid, curve):
     assert k.hs_wei_mul(cid, p(kb), p(pts), None, ctypes.c_size_t(n), p(out), p(inf)) == 2**64 - 1
     exp, einf = coracle.wei_mul(curve, kb, pts)
     assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
-    # fixed base: points == NULL
-    assert k.hs_wei_mul(cid, p(kb), None, None, ctypes.c_size_t(n), p(out), p(inf)) == 2**64 - 1
+    # fixed base: the signed-digit generator comb, two window widths
     exp, einf = coracle.wei_mul_base(curve, kb)
-    assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
+    for W in (4, 5):
+        assert k.hs_wei_mul_base(cid, p(kb), ctypes.c_size_t(n), W, p(out), p(inf)) == 2**64 - 1
+        assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
 
 
 @pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1")])
@@ -171,3 +172,49 @@ def test_ed25519_verify(hs, coracle):
     ok = np.zeros(20, dtype=np.uint8)
     k.hs_ed25519_verify(p(a), p(r), p(s), p(kk), ctypes.c_size_t(20), W, p(table), p(ok))
     assert np.array_equal(ok.astype(bool), coracle.ed25519_verify_prehashed(a, r, s, kk))
+
+
+def _structured(g, n):
+    """Operands made of the limb values that break carry handling: 0, 1, ff..f, ff..e and random."""
+    choices = [0, 1, 0xFFFFFFFF, 0xFFFFFFFE]
+    return sum(int(choices[int(c)] if c < 4 else int(g.integers(0, 1 << 32))) << (32 * i) for i, c in enumerate(g.integers(0, 5, size=n)))
+
+
+@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (1, R.P256.n, 8), (2, R.P384.p, 12), (3, R.P384.n, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
+def test_montgomery_fields_structured_operands(hs, field, mod, n):
+    """A dropped top carry in the p384 reduction only showed with limbs like (1, 1, ff..f): random
+    operands never hit it.  Every field gets the structured stress."""
+    f, _ = hs
+    g = rng(100 + field)
+    Rm = 1 << (32 * n)
+    Ri = pow(Rm, -1, mod)
+    loose = field == 0
+    r = np.zeros(n, dtype=np.uint32)
+    for _ in range(1500):
+        a = _structured(g, n) % (Rm if loose else mod)
+        b = _structured(g, n) % (Rm if loose else mod)
+        for op, exp, bb in ((0, a * b * Ri, b), (1, a * a * Ri, a), (2, a + b, b), (3, a - b, b)):
+            f.hs_mont(field, op, p(words(a, n)), p(words(bb, n)), p(r))
+            if loose:
+                assert val(r) % mod == exp % mod and val(r) < Rm, (field, op, hex(a), hex(b))
+            else:
+                assert val(r) == exp % mod, (field, op, hex(a), hex(b))
+
+
+def test_fe25519_and_fe448_structured_operands(hs):
+    f, k = hs
+    g = rng(200)
+    r8, r14 = np.zeros(8, dtype=np.uint32), np.zeros(14, dtype=np.uint32)
+    for _ in range(1500):
+        a, b = _structured(g, 8), _structured(g, 8)
+        for op, exp in ((0, a * b), (1, a * a), (2, a + b), (3, a - b)):
+            f.hs_fe25519(op, p(words(a, 8)), p(words(b, 8)), p(r8))
+            assert val(r8) % R.P25519 == exp % R.P25519, (op, hex(a), hex(b))
+        f.hs_fe25519(5, p(words(a, 8)), p(words(b, 8)), p(r8))
+        assert val(r8) == a % R.P25519
+        a, b = _structured(g, 14), _structured(g, 14)
+        for op, exp in ((0, a * b), (1, a * a), (2, a + b), (3, a - b)):
+            k.hs_fe448(op, p(words(a, 14)), p(words(b, 14)), p(r14))
+            assert val(r14) % R.P448 == exp % R.P448, (op, hex(a), hex(b))
+        k.hs_fe448(5, p(words(a, 14)), p(words(b, 14)), p(r14))
+        assert val(r14) == a % R.P448
