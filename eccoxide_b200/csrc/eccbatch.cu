@@ -73,10 +73,12 @@ void ecb_destroy(ecb_ctx* ctx) {
                 if (b->p) cudaFree(b->p);
             if (sl.d_status) cudaFree(sl.d_status);
             if (sl.h_status) cudaFreeHost(sl.h_status);
+            if (sl.ev_join) cudaEventDestroy(sl.ev_join);
             if (sl.stream) cudaStreamDestroy(sl.stream);
         }
         for (auto& r : d->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); cudaEventDestroy(r.c); }
         if (d->ed_table) cudaFree(d->ed_table);
+        if (d->ev_fork) cudaEventDestroy(d->ev_fork);
         for (u32* t : d->wei_table)
             if (t) cudaFree(t);
         delete d;
@@ -108,6 +110,10 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "chunk")) {
         if (value < 1) return set_err(ctx, ECB_ERR_INVALID_ARG, "chunk must be >= 1");
         ctx->opt_chunk = (size_t)value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "dev_split")) {
+        ctx->opt_dev_split = value ? 1 : 0;
         return ECB_OK;
     }
     if (!strcmp(key, "profile")) {
@@ -239,6 +245,39 @@ static int dev_wei_mul_base(ecb_ctx* ctx, DevCtx& d, int curve, const u32* d_k, 
     return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
 }
 
+// Large device-resident batches of the fixed-base operations are cut into ECB_NSLOT sub-batches that
+// run on the context's slot streams, forked from and joined back to the caller's stream with events:
+// the batch-inversion kernel of one sub-batch (a long dependent chain per thread, latency-bound)
+// then overlaps the scalar-multiplication kernel of the next (integer-pipe-bound).
+// op(first, count, stream) enqueues one sub-batch using the buffers of d.cur.
+template <class OP>
+static int dev_forkjoin(ecb_ctx* ctx, DevCtx& d, size_t n, cudaStream_t s, OP op) {
+    const size_t min_split = (size_t)3 << 16;
+    if (!ctx->opt_dev_split || n < min_split) {
+        d.cur = &d.slots[0];
+        d.slots[0].c0 = 0;
+        d.dev_slots_used = 1;
+        return op((size_t)0, n, s);
+    }
+    if (!d.ev_fork) CU(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
+    CU(cudaEventRecord(d.ev_fork, s));
+    int rc = ECB_OK;
+    for (int k = 0; k < ECB_NSLOT && rc == ECB_OK; k++) {
+        Slot& sl = d.slots[k];
+        if (!sl.ev_join) CU(cudaEventCreateWithFlags(&sl.ev_join, cudaEventDisableTiming));
+        CU(cudaStreamWaitEvent(sl.stream, d.ev_fork, 0));
+        size_t lo = n * (size_t)k / ECB_NSLOT, hi = n * (size_t)(k + 1) / ECB_NSLOT;
+        d.cur = &sl;
+        sl.c0 = lo;
+        rc = op(lo, hi - lo, sl.stream);
+        CU(cudaEventRecord(sl.ev_join, sl.stream));
+        CU(cudaStreamWaitEvent(s, sl.ev_join, 0));
+    }
+    d.cur = &d.slots[0];
+    d.dev_slots_used = ECB_NSLOT;
+    return rc;
+}
+
 static int curve_sizes(int curve, size_t& fb, size_t& sb) {
     switch (curve) {
         case ECB_CURVE_P256R1: fb = 32; sb = 32; return ECB_OK;
@@ -341,24 +380,33 @@ int ecb_ecdsa_verify_hashed(ecb_ctx* ctx, int curve, const uint8_t* q_xy, const 
 }
 
 // ---- device-resident variants ---------------------------------------------------------------
+static inline void single_slot(DevCtx* d) {  // *_dev calls that do not fork: only slot 0's status word is live
+    d->cur = &d->slots[0];
+    d->slots[0].c0 = 0;
+    d->dev_slots_used = 1;
+}
 static DevCtx* get_dev(ecb_ctx* ctx, int i) { return (ctx && i >= 0 && i < (int)ctx->devs.size()) ? ctx->devs[i] : nullptr; }
 
 int ecb_ed25519_mul_base_dev(ecb_ctx* ctx, int di, const void* d_k, size_t n, void* d_xy, void* stream) {
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
-    return dev_ed25519_mul_base(ctx, *d, (const u32*)d_k, n, (u32*)d_xy, false, (cudaStream_t)stream);
+    return dev_forkjoin(ctx, *d, n, (cudaStream_t)stream, [&](size_t lo, size_t cnt, cudaStream_t st) {
+        return dev_ed25519_mul_base(ctx, *d, (const u32*)d_k + lo * 8, cnt, (u32*)d_xy + lo * 16, false, st);
+    });
 }
 int ecb_ed25519_mul_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_xy_in, size_t n, void* d_xy_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
+    single_slot(d);
     return dev_ed25519_mul(ctx, *d, (const u32*)d_k, (const u32*)d_xy_in, n, (u32*)d_xy_out, (cudaStream_t)stream);
 }
 int ecb_x25519_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
+    single_slot(d);
     return dev_x25519(ctx, *d, (const u32*)d_k, (const u32*)d_u, n, (u32*)d_out, (cudaStream_t)stream);
 }
 int ecb_wei_mul_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, const void* d_xy, size_t n, void* d_out, void* d_inf,
@@ -366,6 +414,7 @@ int ecb_wei_mul_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, const void
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
+    single_slot(d);
     return dev_wei_mul(ctx, *d, curve, (const u32*)d_k, (const u32*)d_xy, nullptr, n, (u32*)d_out, (unsigned char*)d_inf,
                        (cudaStream_t)stream);
 }
@@ -373,12 +422,18 @@ int ecb_wei_mul_base_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, size_
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
-    return dev_wei_mul_base(ctx, *d, curve, (const u32*)d_k, n, (u32*)d_out, (unsigned char*)d_inf, (cudaStream_t)stream);
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb)) return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
+    return dev_forkjoin(ctx, *d, n, (cudaStream_t)stream, [&](size_t lo, size_t cnt, cudaStream_t st) {
+        return dev_wei_mul_base(ctx, *d, curve, (const u32*)d_k + lo * (sb / 4), cnt, (u32*)d_out + lo * (fb / 2),
+                                d_inf ? (unsigned char*)d_inf + lo : nullptr, st);
+    });
 }
 int ecb_x448_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
+    single_slot(d);
     return dev_x448(ctx, *d, (const u32*)d_k, (const u32*)d_u, n, (u32*)d_out, (cudaStream_t)stream);
 }
 int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int di, const void* d_a, const void* d_r, const void* d_s, const void* d_k,
@@ -386,6 +441,7 @@ int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int di, const void* d_a, cons
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
+    single_slot(d);
     return dev_ed25519_verify(ctx, *d, (const u32*)d_a, (const u32*)d_r, (const u32*)d_s, (const u32*)d_k, n,
                               (unsigned char*)d_ok, (cudaStream_t)stream);
 }
@@ -394,6 +450,7 @@ int ecb_ecdsa_verify_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_q
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
+    single_slot(d);
     if (curve == ECB_CURVE_P256R1)
         return dev_ecdsa_p256(ctx, *d, (const u32*)d_q, (const u32*)d_z, (const u32*)d_rs, n, (unsigned char*)d_ok, (cudaStream_t)stream);
     if (curve == ECB_CURVE_P384R1)
@@ -428,9 +485,14 @@ int ecb_dev_status(ecb_ctx* ctx, int di, size_t* bad_index) {
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
-    Slot& sl = d->slots[0];
-    CU(cudaMemcpy(sl.h_status, sl.d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-    unsigned long long v = *sl.h_status;
+    unsigned long long v = ~0ull;
+    for (int k = 0; k < d->dev_slots_used; k++) {
+        Slot& sl = d->slots[k];
+        CU(cudaMemcpy(sl.h_status, sl.d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        if (*sl.h_status == ~0ull) continue;
+        unsigned long long w = (((*sl.h_status >> 8) + sl.c0) << 8) | (*sl.h_status & 0xff);
+        if (w < v) v = w;
+    }
     if (bad_index) *bad_index = (size_t)-1;
     if (v == ~0ull) return ECB_OK;
     if (bad_index) *bad_index = (size_t)(v >> 8);

@@ -36,6 +36,7 @@ struct Slot {
     unsigned long long* d_status = nullptr;
     unsigned long long* h_status = nullptr;  // pinned
     bool busy = false;
+    cudaEvent_t ev_join = nullptr;            // device-resident fork/join (see dev_forkjoin)
     size_t c0 = 0;                            // first element of the chunk in flight
 };
 
@@ -44,6 +45,8 @@ struct DevCtx {
     int sm_count = 0;
     cudaStream_t stream = nullptr;            // = slots[0].stream: table builds, probes
     Slot slots[ECB_NSLOT];
+    cudaEvent_t ev_fork = nullptr;
+    int dev_slots_used = 1;                   // slots whose status words the last *_dev call wrote
     size_t inv_per_thread = 32;               // batch-inversion chain length (option "inv_per_thread"; 8: 0.31 ms, 16: 0.24, 32: 0.20, 64: 0.20 at n = 2^20)
     Slot* cur = &slots[0];                    // slot whose buffers the dev_* functions use (calls are serialised by `mu`)
     u32* ed_table = nullptr;
@@ -65,6 +68,8 @@ struct ecb_ctx {
     long opt_ed_w = 16;  // 16 windows x 2^15 niels entries (50 MB, L2-resident): measured best on B200
     size_t opt_chunk = (size_t)1 << 17;  // elements per pipeline chunk (3 slots in flight per device; measured best of 2^16..2^19)
     long opt_profile = 0;
+    long opt_dev_split = 0;                   // 1: split large device-resident batches over the slot streams (measured: no gain, the
+                                              // shorter inversion chains cost what the overlap saves; kept as an option)
     std::atomic<unsigned long long> launches{0};
 };
 

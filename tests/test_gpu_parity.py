@@ -470,3 +470,68 @@ def test_device_resident_entry_points_match_host_entry_points(ctx):
     ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k2.data_ptr(), n, d_out.data_ptr(), st)
     torch.cuda.synchronize()
     assert ctx.dev_status(0) == (-3, 77)
+
+
+def test_device_resident_large_batch_is_split_over_streams_and_stays_exact(ctx, coracle):
+    """With option dev_split, n >= 3 * 2^16 takes the fork/join path (three sub-batches on the slot streams)."""
+    torch = pytest.importorskip("torch")
+    g = rng(777)
+    n = (1 << 18) + 12345
+    kb = rand_bytes(g, n, 32)
+    kb[:, 31] &= 0x0F
+    d_k = torch.from_numpy(kb).cuda()
+    d_out = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    ctx.set_option("dev_split", 1)
+    ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), n, d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert ctx.dev_status(0) == (0, None)
+    got = d_out.cpu().numpy()
+    idx = np.concatenate([np.arange(64), np.arange(n // 3 - 32, n // 3 + 32), np.arange(2 * n // 3 - 32, 2 * n // 3 + 32), np.arange(n - 64, n),
+                          g.integers(0, n, size=2048)])
+    assert np.array_equal(got[idx], coracle.ed25519_mul_base(kb[idx], threads(coracle)))
+    ctx.set_option("dev_split", 0)
+    d_out2 = torch.empty_like(d_out)
+    ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), n, d_out2.data_ptr(), st)
+    torch.cuda.synchronize()
+    ctx.set_option("dev_split", 1)
+    assert torch.equal(d_out, d_out2)
+    # an invalid scalar in the last sub-batch is reported with its absolute index
+    bad = n - 1000
+    kb2 = kb.copy(); kb2[bad] = 0xFF
+    d_k2 = torch.from_numpy(kb2).cuda()
+    ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k2.data_ptr(), n, d_out.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert ctx.dev_status(0) == (-3, bad)
+    # p256 fixed base through the same path
+    kp = rand_bytes(g, n, 32); kp[:, 0] &= 0x7F
+    d_kp = torch.from_numpy(kp).cuda()
+    d_xy = torch.empty((n, 64), dtype=torch.uint8, device="cuda"); d_inf = torch.empty((n,), dtype=torch.uint8, device="cuda")
+    ctx.dev_call("ecb_wei_mul_base_dev", 0, 0, d_kp.data_ptr(), n, d_xy.data_ptr(), d_inf.data_ptr(), st)
+    torch.cuda.synchronize()
+    assert ctx.dev_status(0) == (0, None)
+    sel = g.integers(0, n, size=1024)
+    exp, einf = coracle.wei_mul_base("p256r1", kp[sel], threads(coracle))
+    assert np.array_equal(d_xy.cpu().numpy()[sel], exp) and np.array_equal(d_inf.cpu().numpy()[sel].astype(bool), einf)
+    ctx.set_option("dev_split", 0)
+
+
+def test_context_over_all_visible_devices_shards_by_contiguous_slice(coracle):
+    """ecb_init over every visible GPU: one host thread + streams per device, slice [g n/G, (g+1) n/G)."""
+    torch = pytest.importorskip("torch")
+    from eccoxide_b200 import Context, EccBatchError
+
+    ndev = torch.cuda.device_count()
+    g = rng(31337)
+    n = 100003
+    with Context(devices=list(range(ndev))) as c:
+        assert c.device_count() == ndev
+        kb = scalars_mod(g, n, R.L25519, 32, "little")
+        assert np.array_equal(c.ed25519_mul_base(kb), coracle.ed25519_mul_base(kb, threads(coracle)))
+        k, u = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
+        assert np.array_equal(c.x25519(k, u), coracle.x25519(k, u, threads(coracle)))
+        kb[n - 7] = 0xFF  # first offender reported with its global index whichever device owns it
+        kb[n // 2 + 1] = 0xFF
+        with pytest.raises(EccBatchError) as e:
+            c.ed25519_mul_base(kb)
+        assert e.value.code == -3 and e.value.bad_index == n // 2 + 1
