@@ -113,6 +113,16 @@ ECB_DEV void plane_st(u32* plane, size_t n, size_t idx, const u32* v) {
     ECB_UNROLL
     for (int i = 0; i < NW; i++) plane[(size_t)i * n + idx] = v[i];
 }
+// hint: bring the NW lines of element idx (one per limb plane) towards the SM; no registers held
+template <int NW>
+ECB_DEV void plane_prefetch(const u32* plane, size_t n, size_t idx) {
+#ifndef ECB_HOSTSIM
+    ECB_UNROLL
+    for (int i = 0; i < NW; i++) asm volatile("prefetch.global.L2 [%0];" ::"l"(plane + (size_t)i * n + idx));
+#else
+    (void)plane; (void)n; (void)idx;
+#endif
+}
 template <int NW>
 ECB_DEV void plane_ld(u32* v, const u32* plane, size_t n, size_t idx) {
     ECB_UNROLL
@@ -342,36 +352,87 @@ ECB_DEV void batch_inv_body(size_t t, size_t T, size_t n, const u32* planes, u32
     constexpr int N = FT::N;
     if (t >= n) return;
     const u32* zp = planes + 2 * (size_t)N * n;
-    fe acc, z, one;
+    // Two interleaved chains per thread (elements t, t+2T, ... and t+T, t+3T, ...): the two
+    // running products are independent, so the long dependent multiplication chains overlap
+    // (the kernel is latency-bound: few warps, each a serial chain); one inversion serves both.
+    fe accA, accB, zA, zB, one;
     FT::set_one(one);
-    FT::set_one(acc);
-    size_t last = t;
-    for (size_t idx = t; idx < n; idx += T) {
-        plane_ld<N>(z.v, zp, n, idx);
-        u32 zero = FT::is_zero(z);
-        FT::select(z, zero, one, z);
-        plane_st<N>(pf, n, idx, acc.v);
-        FT::mul(acc, acc, z);
-        last = idx;
+    FT::set_one(accA);
+    FT::set_one(accB);
+    size_t cnt = (n - t + T - 1) / T;            // elements owned by this thread
+    size_t pairs = cnt / 2;
+    for (size_t j = 0; j < pairs; j++) {
+        size_t ia = t + (2 * j) * T, ib = ia + T;
+        if (ib + 2 * T < n) {                    // the loop is bound by DRAM latency without this
+            plane_prefetch<N>(zp, n, ia + 2 * T);
+            plane_prefetch<N>(zp, n, ib + 2 * T);
+        }
+        plane_ld<N>(zA.v, zp, n, ia);
+        plane_ld<N>(zB.v, zp, n, ib);
+        u32 zeroA = FT::is_zero(zA), zeroB = FT::is_zero(zB);
+        FT::select(zA, zeroA, one, zA);
+        FT::select(zB, zeroB, one, zB);
+        plane_st<N>(pf, n, ia, accA.v);
+        plane_st<N>(pf, n, ib, accB.v);
+        FT::mul(accA, accA, zA);
+        FT::mul(accB, accB, zB);
     }
-    fe inv;
-    FT::invert(inv, acc);
-    for (size_t idx = last;; idx -= T) {
-        plane_ld<N>(z.v, zp, n, idx);
-        u32 zero = FT::is_zero(z);
-        FT::select(z, zero, one, z);
+    if (cnt & 1) {                               // odd leftover goes to chain A
+        size_t ia = t + (cnt - 1) * T;
+        plane_ld<N>(zA.v, zp, n, ia);
+        u32 zeroA = FT::is_zero(zA);
+        FT::select(zA, zeroA, one, zA);
+        plane_st<N>(pf, n, ia, accA.v);
+        FT::mul(accA, accA, zA);
+    }
+    fe inv, invA, invB;
+    FT::mul(inv, accA, accB);
+    FT::invert(inv, inv);
+    FT::mul(invA, inv, accB);
+    FT::mul(invB, inv, accA);
+    if (cnt & 1) {
+        size_t ia = t + (cnt - 1) * T;
+        plane_ld<N>(zA.v, zp, n, ia);
+        u32 zeroA = FT::is_zero(zA);
+        FT::select(zA, zeroA, one, zA);
         fe p, zinv;
-        plane_ld<N>(p.v, pf, n, idx);
-        FT::mul(zinv, inv, p);
-        FT::mul(inv, inv, z);
-        fin(idx, zinv, zero);
-        if (idx == t) break;
+        plane_ld<N>(p.v, pf, n, ia);
+        FT::mul(zinv, invA, p);
+        FT::mul(invA, invA, zA);
+        fin(ia, zinv, zeroA);
+    }
+    for (size_t j = pairs; j-- > 0;) {
+        size_t ia = t + (2 * j) * T, ib = ia + T;
+        if (j > 0) {
+            size_t pa = ia - 2 * T, pb = ib - 2 * T;
+            plane_prefetch<N>(zp, n, pa);
+            plane_prefetch<N>(zp, n, pb);
+            plane_prefetch<N>(pf, n, pa);
+            plane_prefetch<N>(pf, n, pb);
+            fin.pre(pa);
+            fin.pre(pb);
+        }
+        plane_ld<N>(zA.v, zp, n, ia);
+        plane_ld<N>(zB.v, zp, n, ib);
+        u32 zeroA = FT::is_zero(zA), zeroB = FT::is_zero(zB);
+        FT::select(zA, zeroA, one, zA);
+        FT::select(zB, zeroB, one, zB);
+        fe pA, pB, zinvA, zinvB;
+        plane_ld<N>(pA.v, pf, n, ia);
+        plane_ld<N>(pB.v, pf, n, ib);
+        FT::mul(zinvA, invA, pA);
+        FT::mul(zinvB, invB, pB);
+        FT::mul(invA, invA, zA);
+        FT::mul(invB, invB, zB);
+        fin(ia, zinvA, zeroA);
+        fin(ib, zinvB, zeroB);
     }
 }
 
 // finishers ------------------------------------------------------------------------------
 struct FinEdXY {  // out: x_le || y_le, canonical (Point::to_affine + to_bytes_le)
     const u32* planes; size_t n; u32* out;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<8>(planes, n, idx); plane_prefetch<8>(planes + 8 * n, n, idx); }
     ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
         fe25519 X, Y, x, y;
         plane_ld<8>(X.v, planes, n, idx);
@@ -386,6 +447,7 @@ struct FinEdXY {  // out: x_le || y_le, canonical (Point::to_affine + to_bytes_l
 };
 struct FinEdCompressed {  // out: encode_point (protocol/ed25519.rs:27)
     const u32* planes; size_t n; u32* out;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<8>(planes, n, idx); plane_prefetch<8>(planes + 8 * n, n, idx); }
     ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
         fe25519 X, Y, x, y;
         plane_ld<8>(X.v, planes, n, idx);
@@ -400,6 +462,7 @@ struct FinEdCompressed {  // out: encode_point (protocol/ed25519.rs:27)
 };
 struct FinEdNiels {  // out: comb-table entry (y+x, y-x, 2dxy), 24 words
     const u32* planes; size_t n; u32* out;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<8>(planes, n, idx); plane_prefetch<8>(planes + 8 * n, n, idx); }
     ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
         fe25519 X, Y, x, y;
         plane_ld<8>(X.v, planes, n, idx);
@@ -418,6 +481,7 @@ struct FinEdNiels {  // out: comb-table entry (y+x, y-x, 2dxy), 24 words
 };
 struct FinX25519 {  // out: u' = x2 / z2 little-endian canonical, 0 when z2 == 0
     const u32* planes; size_t n; u32* out;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<8>(planes, n, idx); }
     ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32 zero) const {
         fe25519 X, x;
         plane_ld<8>(X.v, planes, n, idx);
@@ -634,6 +698,7 @@ template <class C>
 struct FinWeiTable {  // out: comb-table entry (x, y), Montgomery domain, canonical, 2N words
     typedef typename C::F FT;
     const u32* planes; size_t n; u32* out;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<FT::N>(planes, n, idx); plane_prefetch<FT::N>(planes + (size_t)FT::N * n, n, idx); }
     ECB_DEV void operator()(size_t idx, const typename FT::el& zinv, u32) const {
         constexpr int N = FT::N;
         typename FT::el X, Y, x, y, zi2;
@@ -654,6 +719,7 @@ template <class C>
 struct FinWeiXY {  // out: x_be || y_be (canonical, out of the Montgomery domain) + infinity flag
     typedef typename C::F FT;
     const u32* planes; size_t n; u32* out; unsigned char* inf_out;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<FT::N>(planes, n, idx); plane_prefetch<FT::N>(planes + (size_t)FT::N * n, n, idx); }
     ECB_DEV void operator()(size_t idx, const typename FT::el& zinv, u32 zero) const {
         constexpr int N = FT::N;
         typename FT::el X, Y, x, y;

@@ -225,6 +225,7 @@ ECB_DEV void x448_body(size_t idx, size_t n, const u32* scalars, const u32* us, 
 }
 struct FinX448 {
     const u32* planes; size_t n; u32* out;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<14>(planes, n, idx); }
     ECB_DEV void operator()(size_t idx, const fe448& zinv, u32 zero) const {
         fe448 X, x;
         plane_ld<14>(X.v, planes, n, idx);
@@ -272,6 +273,7 @@ template <class C>
 struct FinScalarInv {
     typedef typename C::FN FN;
     u32* sp; size_t n;
+    ECB_DEV void pre(size_t) const {}
     ECB_DEV void operator()(size_t idx, const typename FN::el& zinv, u32) const { plane_st<FN::N>(sp, n, idx, zinv.v); }
 };
 
@@ -357,6 +359,7 @@ struct FinEcdsa {  // x_mod_n(R) == r (ecdsa.rs:382, :218-221); identity => reje
     typedef typename C::F FT;
     typedef typename C::FN FN;
     const u32* planes; size_t n; const u32* rs_be; unsigned char* ok;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<FT::N>(planes, n, idx); }
     ECB_DEV void operator()(size_t idx, const typename FT::el& zinv, u32 zero) const {
         constexpr int N = FT::N;
         constexpr int NS = FN::N;
