@@ -327,6 +327,24 @@ def measure_e2e(torch, ctx, name, n, steps, warmup, ins_h, dist=None):
     return dt / steps, out
 
 
+def pcie_bandwidth(torch, nbytes=64 << 20):
+    """Plain pinned-memory copies, GB/s each direction: what bounds e2e for the fixed-base operations."""
+    h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    out = {}
+    for nm, src, dst in (("h2d_gbs", h, d), ("d2h_gbs", d, h)):
+        dst.copy_(src, non_blocking=True)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(4):
+            dst.copy_(src, non_blocking=True)
+        e1.record()
+        torch.cuda.synchronize()
+        out[nm] = 4 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    return out
+
+
 def cpu_baseline(name, ins_h, target_s, threads):
     """Time the C oracle (reference algorithms) on a bounded sample of the same inputs."""
     from oracle import coracle as C
@@ -483,6 +501,11 @@ def main():
         if not args.no_cpu:
             cpu, _, _ = cpu_baseline(name, r["ins_h"], 12.0, os.cpu_count() or 1)
         achieved = n * W / (r["ms_per_step"] * 1e-3) / 1e12
+        try:
+            static = json.load(open(os.path.join(ROOT, "profiles", "ncu_static.json"))).get(name) or {}
+        except Exception:
+            static = {}
+        traffic = (static.get("dram_read_bytes") or 0) + (static.get("dram_write_bytes") or 0) or None
         line = {
             "metric": "scalar-mults/s", "value": ops_s, "unit": "scalar-mults/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -492,10 +515,14 @@ def main():
                            r["nbuf"], r["nbuf"] * r["in_bytes"] / 1e6, n * 4 * 32 / 1e6),
                        "parallelism": "%d x contiguous batch slice, no collective" % world},
             "e2e": {"value": world * n / e2e_s, "unit": "scalar-mults/s", "h2d_bytes_per_step": r["in_bytes"], "d2h_bytes_per_step": r["out_bytes"],
-                    "path": "ecb_* host entry point, pinned host buffers"},
+                    "path": "ecb_* host entry point, pinned host buffers, chunks pipelined over 3 streams",
+                    "pcie": pcie_bandwidth(torch)},
             "gpu_launches": int(r["launches"]),
             "roofline": {"bound": "imad", "achieved": achieved, "peak": peak, "unit": "T MAC32/s (32x32->64 multiply-accumulates)", "frac": achieved / peak if peak else None,
-                         "traffic": None, "mac32_per_op": W, "peak_source": "live probe kernels on this GPU (T/s): %s; a MAC32 is two passes of the 32-bit multiplier" % json.dumps({k: (round(v, 3) if v else v) for k, v in probes.items()}),
+                         "traffic": traffic, "mac32_per_op": W,
+                         "pipe_util_ncu": {"kernel": static.get("kernel"), "fmaheavy_pct": static.get("fmaheavy_pct"), "alu_pct": static.get("alu_pct"),
+                                           "issue_pct": static.get("issue_pct"), "source": static.get("source")},
+                         "note": "frac uses the reference algorithm's MAC32 count (SURVEY 8d); the kernels execute fewer (wider comb, mixed additions), so frac can exceed 1 while pipe_util_ncu (the integer-multiply pipe's busy cycles) stays below 100 %", "peak_source": "live probe kernels on this GPU (T/s): %s; a MAC32 is two passes of the 32-bit multiplier" % json.dumps({k: (round(v, 3) if v else v) for k, v in probes.items()}),
                          "kernels_ms": {"scalar_mult": r["main_ms"], "batch_inversion_encode": r["fin_ms"]},
                          "hbm_gbs": (r["in_bytes"] + r["out_bytes"]) / (r["ms_per_step"] * 1e-3) / 1e9},
             "cpu_baseline": cpu, "clocks": clocks, "parity_check": check,

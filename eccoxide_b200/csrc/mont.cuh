@@ -250,7 +250,59 @@ struct Mont {
         for (int k = 1; k <= N; k++) t[k] = addc_cc(ev[k], od[k - 1]);
         final_sub(r, t, t[N]);
     }
+    // Montgomery reduction of a full 2N-limb product T (generic prime): the CIOS reduction rows of
+    // mul() on their own — per row m = w0 * INV, window += m * p, shift one limb, pull in the next
+    // limb of T at the top.  N^2 IMAD.WIDE; with sqr_full this makes a square N(N+1)/2 + N^2 instead
+    // of the 2 N^2 of mul(a, a).
+    ECB_DEV static void redc_full(el& r, const u32* T) {
+        u32 ev[N + 2], od[N + 2];
+        ECB_UNROLL
+        for (int i = 0; i < N; i++) { ev[i] = T[i]; od[i] = 0; }
+        ev[N] = ev[N + 1] = od[N] = od[N + 1] = 0;
+        u32 L = 0;
+        u32 pm[N];
+        ECB_UNROLL
+        for (int i = 0; i < N; i++) pm[i] = P::mod(i);
+        ECB_UNROLL
+        for (int i = 0; i < N; i++) {
+            ev[0] = add_cc(ev[0], L);            // its carry enters the odd chain (limb 1)
+            u32 m = ev[0] * P::INV;
+            od[0] = madc_lo_cc(pm[1], m, od[0]);
+            od[1] = madc_hi_cc(pm[1], m, od[1]);
+            ECB_UNROLL
+            for (int k = 1; k < N / 2; k++) {
+                od[2 * k] = madc_lo_cc(pm[2 * k + 1], m, od[2 * k]);
+                od[2 * k + 1] = madc_hi_cc(pm[2 * k + 1], m, od[2 * k + 1]);
+            }
+            od[N] = addc(od[N], 0);
+            mac_chain<N / 2, true>(ev, pm, m);
+            L = ev[1];
+            u32 nev[N + 2], nod[N + 2];
+            ECB_UNROLL
+            for (int k = 0; k < N + 2; k++) nev[k] = od[k];
+            ECB_UNROLL
+            for (int k = 0; k < N; k++) nod[k] = ev[k + 2];
+            nod[N] = 0;
+            nod[N + 1] = 0;
+            ECB_UNROLL
+            for (int k = 0; k < N + 2; k++) { ev[k] = nev[k]; od[k] = nod[k]; }
+            ev[N - 1] = add_cc(ev[N - 1], T[N + i]);   // next limb of T enters at the top of the window
+            ev[N] = addc(ev[N], 0);
+        }
+        u32 t[N + 1];
+        t[0] = add_cc(ev[0], L);
+        ECB_UNROLL
+        for (int k = 1; k <= N; k++) t[k] = addc_cc(ev[k], od[k - 1]);
+        final_sub(r, t, t[N]);
+    }
+
     ECB_DEV static void sqr(el& r, const el& a) {
+        if constexpr (MontKind<P>::kind == 0) {
+            u32 T[2 * N];
+            sqr_full<N>(T, a.v);
+            redc_full(r, T);
+            return;
+        }
         if constexpr (MontKind<P>::kind == 2) {
             u32 T[25];
             sqr_full<N>(T, a.v);
