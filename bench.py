@@ -36,6 +36,9 @@ sys.path.insert(0, ROOT)
 WORK = {
     "ed25519_mul_base": 41688,
     "ed25519_mul": 284888,
+    # Ed25519 verify as the reference does it: 2 x decode_point (sqrt-ratio exponentiation, ~254 S + 20 M each)
+    # + double_scalar_mul_base_vartime (~253 doublings of 3 M + 4 S, ~70 cached additions of 8 M)
+    "ed25519_verify": 2 * (254 * 44 + 20 * 72) + 253 * (3 * 72 + 4 * 44) + 70 * 8 * 72,
     "p256_mul_base": 896 * 64 + 3 * 64,      # reference comb: 64 complete additions x 14 M + affine share
     "bls12_381_g1_mul_base": 896 * 300 + 3 * 300,
     "x25519": 155864,
@@ -56,6 +59,7 @@ WORKLOADS = {
     "p384_mul": (18, 144, 97, "configs[4] sweep member"),
     "x448": (18, 112, 56, "configs[4] sweep member (X448 stands in for edwards448)"),
     "ed25519_mul": (18, 96, 64, "north star: variable-base Ed25519 Point::mul"),
+    "ed25519_verify": (20, 128, 1, "north star: batched ed25519 verify (k = SHA-512(R||A||M) mod l precomputed by the caller)"),
     "p256_mul_base": (20, 32, 65, "north star: fixed-base p256r1 Point::mul_base (comb)"),
     "bls12_381_g1_mul_base": (20, 32, 97, "north star: fixed-base BLS12-381 G1 Point::mul_base (comb)"),
 }
@@ -97,6 +101,24 @@ def make_inputs(name, n, ctx, seed):
         pts, inf = ctx.wei_mul_base(curve, rand_scalars(g, uniq, sb, clr, "big"))
         assert not inf.any()
         return [rand_scalars(g, n, sb, clr, "big"), tile(pts)]
+    if base == "ed25519_verify":
+        # synthetic signatures: R = r*B and A = a*B from the library's own fixed-base path, S = r + k*a mod l
+        # computed on the host for `uniq` triples with an arbitrary (synthetic) challenge k; 1/16 corrupted
+        from oracle import pyref as R
+
+        L = R.L25519
+        a_s = rand_scalars(g, uniq, 32, 4, "little")
+        r_s = rand_scalars(g, uniq, 32, 4, "little")
+        k_s = rand_scalars(g, uniq, 32, 4, "little")
+        A = ctx.ed25519_mul_base(a_s, compressed=True)
+        Rr = ctx.ed25519_mul_base(r_s, compressed=True)
+        S = np.empty((uniq, 32), dtype=np.uint8)
+        for i in range(uniq):
+            a, r, k = (int.from_bytes(x[i].tobytes(), "little") for x in (a_s, r_s, k_s))
+            S[i] = np.frombuffer(((r + k * a) % L).to_bytes(32, "little"), dtype=np.uint8)
+            if i % 16 == 5:
+                S[i, 3] ^= 1
+        return [tile(A), tile(Rr), tile(S), tile(k_s)]
     if base == "p256_mul_base":
         return [rand_scalars(g, n, 32, 1, "big")]
     if base == "bls12_381_g1_mul_base":
@@ -130,7 +152,7 @@ def make_inputs(name, n, ctx, seed):
 OUT_SHAPES = {
     "ed25519_mul_base": [64], "ed25519_mul": [64], "x25519": [32], "x448": [56],
     "p256_mul": [64, 1], "p384_mul": [96, 1], "bls12_381_g1_mul": [96, 1], "p256_ecdsa_verify": [1],
-    "p256_mul_base": [64, 1], "bls12_381_g1_mul_base": [96, 1],
+    "p256_mul_base": [64, 1], "bls12_381_g1_mul_base": [96, 1], "ed25519_verify": [1],
 }
 
 
@@ -150,6 +172,8 @@ def dev_launch(ctx, name, ins, outs, n, stream):
     elif base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
         cid = {"p256_mul": 0, "p384_mul": 1, "bls12_381_g1_mul": 2}[base]
         ctx.dev_call("ecb_wei_mul_dev", 0, cid, p[0], p[1], n, o[0], o[1], stream)
+    elif base == "ed25519_verify":
+        ctx.dev_call("ecb_ed25519_verify_prehashed_dev", 0, p[0], p[1], p[2], p[3], n, o[0], stream)
     elif base in ("p256_mul_base", "bls12_381_g1_mul_base"):
         ctx.dev_call("ecb_wei_mul_base_dev", 0, 0 if base == "p256_mul_base" else 2, p[0], n, o[0], o[1], stream)
     elif base == "p256_ecdsa_verify":
@@ -173,6 +197,8 @@ def host_call(ctx, name, ins, outs=None):
     if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
         curve = {"p256_mul": "p256r1", "p384_mul": "p384r1", "bls12_381_g1_mul": "bls12_381_g1"}[base]
         return list(ctx.wei_mul(curve, ins[0], ins[1], out=o[0], out_inf=o[1]))
+    if base == "ed25519_verify":
+        return [ctx.ed25519_verify_prehashed(ins[0], ins[1], ins[2], ins[3], out=o[0])]
     if base in ("p256_mul_base", "bls12_381_g1_mul_base"):
         return list(ctx.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], out=o[0], out_inf=o[1]))
     if base == "p256_ecdsa_verify":
@@ -193,6 +219,8 @@ def oracle_call(C, name, ins, nthreads):
     if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
         curve = {"p256_mul": "p256r1", "p384_mul": "p384r1", "bls12_381_g1_mul": "bls12_381_g1"}[base]
         return list(C.wei_mul(curve, ins[0], ins[1], nthreads=nthreads))
+    if base == "ed25519_verify":
+        return [C.ed25519_verify_prehashed(ins[0], ins[1], ins[2], ins[3], nthreads)]
     if base in ("p256_mul_base", "bls12_381_g1_mul_base"):
         return list(C.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], nthreads))
     if base == "p256_ecdsa_verify":

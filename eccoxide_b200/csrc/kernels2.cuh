@@ -438,83 +438,103 @@ ECB_DEV u32 ed25519_decode(fe25519& x, fe25519& y, const u32* enc) {
     return ok;
 }
 
-ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u32* r_enc, const u32* s_le, const u32* k_le,
-                                 const u32* table, int W, int nwin, u32* tbl, unsigned char* out_ok) {
-    u32 aw[8], rw[8], s[8], k[8];
+ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,
+                                 const u32* table, int W, int nwin, u32* tbl, u32* planes, unsigned char* out_ok) {
+    u32 aw[8], s[8], k[8];
     ld_words<8>(aw, a_enc + idx * 8);
-    ld_words<8>(rw, r_enc + idx * 8);
     ld_words<8>(s, s_le + idx * 8);
     ld_words<8>(k, k_le + idx * 8);
-    fe25519 ax, ay, rx, ry;
+    fe25519 ax, ay;
     u32 ok = ed25519_decode(ax, ay, aw);
-    ok &= ed25519_decode(rx, ry, rw);
     ok &= lt_words8(s, ED25519_L);
     ok &= lt_words8(k, ED25519_L);
-    if (!ok) {
-        out_ok[idx] = 0;
-        return;
-    }
-    // [S]B from the comb
-    const u32 half = 1u << (W - 1);
-    ge_p3 sb;
-    ge_identity(sb);
-    for (int i = 0; i < nwin; i++) {
-        u32 neg;
-        u32 d = booth_digit(s, 8, W, i, neg);
-        if (d != 0) {
-            ge_niels e;
-            const u32* src = table + ((size_t)i * half + (d - 1)) * 24;
-            ld_words<8>(e.yp.v, src);
-            ld_words<8>(e.ym.v, src + 8);
-            ld_words<8>(e.t2d.v, src + 16);
-            ge_niels_cneg(e, neg);
-            ge_madd<true>(sb, sb, e);
-        }
-    }
-    // [k](-A): signed 4-bit windows over 8 cached multiples
-    ge_p3 P, acc;
-    {
-        fe25519 nax;
-        F::neg(nax, ax);
-        ge_from_affine(P, nax, ay);
-        ge_cached c, c1;
-        ge_to_cached(c1, P);
-        acc = P;
-        ECB_NOUNROLL
-        for (int j = 1; j <= 8; j++) {
-            ge_to_cached(c, acc);
-            u32* d = tbl + (j - 1) * 32;
-            st_words<8>(d + 0, c.yp.v); st_words<8>(d + 8, c.ym.v); st_words<8>(d + 16, c.Z.v); st_words<8>(d + 24, c.t2d.v);
-            if (j < 8) ge_add_cached<true>(acc, acc, c1);
-        }
-    }
+    ge_p3 acc;
     ge_identity(acc);
-    ECB_NOUNROLL
-    for (int i = 63; i >= 0; i--) {
-        if (i != 63) {
+    if (ok) {
+        // [S]B from the comb
+        const u32 half = 1u << (W - 1);
+        ge_p3 sb;
+        ge_identity(sb);
+        for (int i = 0; i < nwin; i++) {
+            u32 neg;
+            u32 d = booth_digit(s, 8, W, i, neg);
+            if (d != 0) {
+                ge_niels e;
+                const u32* src = table + ((size_t)i * half + (d - 1)) * 24;
+                ld_words<8>(e.yp.v, src);
+                ld_words<8>(e.ym.v, src + 8);
+                ld_words<8>(e.t2d.v, src + 16);
+                ge_niels_cneg(e, neg);
+                ge_madd<true>(sb, sb, e);
+            }
+        }
+        // [k](-A): signed 4-bit windows over 8 cached multiples
+        ge_p3 P;
+        {
+            fe25519 nax;
+            F::neg(nax, ax);
+            ge_from_affine(P, nax, ay);
+            ge_cached c, c1;
+            ge_to_cached(c1, P);
+            acc = P;
             ECB_NOUNROLL
-            for (int r = 0; r < 3; r++) ge_double<false>(acc, acc);
-            ge_double<true>(acc, acc);
+            for (int j = 1; j <= 8; j++) {
+                ge_to_cached(c, acc);
+                u32* d = tbl + (j - 1) * 32;
+                st_words<8>(d + 0, c.yp.v); st_words<8>(d + 8, c.ym.v); st_words<8>(d + 16, c.Z.v); st_words<8>(d + 24, c.t2d.v);
+                if (j < 8) ge_add_cached<true>(acc, acc, c1);
+            }
         }
-        u32 neg;
-        u32 d = booth_digit(k, 8, 4, i, neg);
-        if (d != 0) {
-            ge_cached c;
-            const u32* sp = tbl + (d - 1) * 32;
-            ld_words_rw<8>(c.yp.v, sp); ld_words_rw<8>(c.ym.v, sp + 8); ld_words_rw<8>(c.Z.v, sp + 16); ld_words_rw<8>(c.t2d.v, sp + 24);
-            ge_cached_cneg(c, neg);
-            ge_add_cached<true>(acc, acc, c);
+        ge_identity(acc);
+        ECB_NOUNROLL
+        for (int i = 63; i >= 0; i--) {
+            if (i != 63) {
+                ECB_NOUNROLL
+                for (int r = 0; r < 3; r++) ge_double<false>(acc, acc);
+                ge_double<true>(acc, acc);
+            }
+            u32 neg;
+            u32 d = booth_digit(k, 8, 4, i, neg);
+            if (d != 0) {
+                ge_cached c;
+                const u32* sp = tbl + (d - 1) * 32;
+                ld_words_rw<8>(c.yp.v, sp); ld_words_rw<8>(c.ym.v, sp + 8); ld_words_rw<8>(c.Z.v, sp + 16); ld_words_rw<8>(c.t2d.v, sp + 24);
+                ge_cached_cneg(c, neg);
+                ge_add_cached<true>(acc, acc, c);
+            }
         }
+        // lhs = [S]B + [k](-A)
+        ge_cached cs;
+        ge_to_cached(cs, sb);
+        ge_add_cached<false>(acc, acc, cs);
     }
-    // lhs = [S]B + [k](-A)
-    ge_cached cs;
-    ge_to_cached(cs, sb);
-    ge_add_cached<false>(acc, acc, cs);
-    // lhs == R  <=>  X = rx * Z and Y = ry * Z   (R has Z = 1)
-    fe25519 t1, t2;
-    F::mul(t1, rx, acc.Z);
-    F::mul(t2, ry, acc.Z);
-    out_ok[idx] = (unsigned char)(F::eq(t1, acc.X) & F::eq(t2, acc.Y));
+    out_ok[idx] = (unsigned char)ok;
+    plane_st<8>(planes + 0 * 8 * n, n, idx, acc.X.v);
+    plane_st<8>(planes + 1 * 8 * n, n, idx, acc.Y.v);
+    plane_st<8>(planes + 2 * 8 * n, n, idx, acc.Z.v);
 }
+// lhs == R  <=>  encode_point(lhs) == the signature's R bytes: decode_point (protocol/ed25519.rs:38)
+// accepts exactly the canonical encodings of curve points and encode_point is its inverse, so a
+// non-canonical / off-curve / (x = 0, sign = 1) R can never equal an encoding and is rejected just as
+// the reference's decode step rejects it — without paying a second square-root exponentiation.
+struct FinEdVerify {
+    const u32* planes; size_t n; const u32* r_enc; unsigned char* ok;
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<8>(planes, n, idx); plane_prefetch<8>(planes + 8 * n, n, idx); }
+    ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
+        fe25519 X, Y, x, y;
+        plane_ld<8>(X.v, planes, n, idx);
+        plane_ld<8>(Y.v, planes + 8 * n, n, idx);
+        F::mul(x, X, zinv);
+        F::mul(y, Y, zinv);
+        F::freeze(x, x);
+        F::freeze(y, y);
+        y.v[7] |= (x.v[0] & 1u) << 31;
+        u32 rw[8], diff = 0;
+        ld_words<8>(rw, r_enc + idx * 8);
+        ECB_UNROLL
+        for (int i = 0; i < 8; i++) diff |= rw[i] ^ y.v[i];
+        ok[idx] = (unsigned char)((ok[idx] != 0) & (diff == 0));
+    }
+};
 
 }  // namespace ecb

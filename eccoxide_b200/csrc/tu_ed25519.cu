@@ -17,12 +17,12 @@ static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul(size_t n, const 
     u32* tbl = scratch + t * (8 * 32);
     for (size_t idx = t; idx < n; idx += T) ed25519_mul_body(idx, n, scalars, points, tbl, planes, status);
 }
-static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_verify(size_t n, const u32* a_enc, const u32* r_enc, const u32* s_le,
-                                                             const u32* k_le, const u32* table, int W, int nwin,
-                                                             u32* scratch, unsigned char* ok) {
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_verify(size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,
+                                                             const u32* table, int W, int nwin, u32* scratch, u32* planes,
+                                                             unsigned char* ok) {
     size_t T = (size_t)gridDim.x * ECB_TPB, t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
     u32* tbl = scratch + t * (8 * 32);
-    for (size_t idx = t; idx < n; idx += T) ed25519_verify_body(idx, n, a_enc, r_enc, s_le, k_le, table, W, nwin, tbl, ok);
+    for (size_t idx = t; idx < n; idx += T) ed25519_verify_body(idx, n, a_enc, s_le, k_le, table, W, nwin, tbl, planes, ok);
 }
 
 int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
@@ -88,13 +88,19 @@ int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, siz
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
                        unsigned char* ok, cudaStream_t s) {
     if (!d.ed_table || d.ed_w != (int)ctx->opt_ed_w) TRY(dev_ed25519_build_table(ctx, d, (int)ctx->opt_ed_w));
+    TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
     unsigned g = persistent_grid(d, k_ed25519_verify, n);
     TRY(ensure(ctx, d.cur->scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
+    u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
-    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, r, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, (u32*)d.cur->scratch.p, ok);
+    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, (u32*)d.cur->scratch.p, planes, ok);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);
+    // affine + encode_point + comparison with the signature's R bytes
+    FinEdVerify fin{planes, n, r, ok};
+    int rc = launch_batch_inv<F25519, FinEdVerify>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     prof_mark(ctx, d, s, 2);
-    return ECB_OK;
+    return rc;
 }

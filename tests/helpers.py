@@ -132,3 +132,21 @@ def sha(alg, msg):
 
 def checksum(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def ed25519_identity_r_cases(g):
+    """Prehashed triples whose R is the identity: S = k a mod l makes [S]B - [k]A = (0, 1).
+    Returns (A, R, S, K) rows: the canonical encoding of the identity (accepted), the same with the
+    sign bit set (x = 0, sign = 1: decode_point rejects), and y = 1 + p (non-canonical: rejected)."""
+    L = R.L25519
+    A, Rr, S, K = [], [], [], []
+    ident = (1).to_bytes(32, "little")
+    encs = [ident, (1 | 1 << 255).to_bytes(32, "little"), (1 + R.P25519).to_bytes(32, "little")]
+    for enc in encs:
+        a = int.from_bytes(g.bytes(40), "little") % (L - 1) + 1
+        k = int.from_bytes(g.bytes(40), "little") % L
+        A.append(R.ed_encode(R.ed_mul(a, R.ED_B)))
+        Rr.append(enc)
+        S.append((k * a % L).to_bytes(32, "little"))
+        K.append(k.to_bytes(32, "little"))
+    return rows(A), rows(Rr), rows(S), rows(K)

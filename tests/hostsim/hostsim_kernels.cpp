@@ -109,8 +109,11 @@ void hs_x448(const u32* k, const u32* u, size_t n, u32* out) {
 void hs_ed25519_verify(const u32* a, const u32* r, const u32* s, const u32* k, size_t n, int W, const u32* table,
                        unsigned char* ok) {
     int nwin = (254 + W - 1) / W;
-    std::vector<u32> tbl(8 * 32);
-    for (size_t i = 0; i < n; i++) ed25519_verify_body(i, n, a, r, s, k, table, W, nwin, tbl.data(), ok);
+    std::vector<u32> tbl(8 * 32), planes(3 * 8 * n), pf(8 * n);
+    for (size_t i = 0; i < n; i++) ed25519_verify_body(i, n, a, s, k, table, W, nwin, tbl.data(), planes.data(), ok);
+    size_t T = inv_threads(n);
+    FinEdVerify fin{planes.data(), n, r, ok};
+    for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
 }
 }
 template <class C>

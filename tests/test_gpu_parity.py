@@ -443,6 +443,13 @@ def test_ed25519_verify(ctx, golden, coracle):
     assert got.sum() > 100 and (~got).sum() > 100 and not got[20] and not got[21] and not got[9]
     for i in (0, 1, 2, 3, 9, 20):
         assert bool(got[i]) == R.ed25519_verify_prehashed(a[i].tobytes(), r[i].tobytes(), s[i].tobytes(), k[i].tobytes())
+    # R = identity in its canonical encoding / with the sign bit / non-canonical: the kernel compares
+    # encode_point(lhs) with R's bytes instead of decoding R — same three answers as decode + compare
+    from helpers import ed25519_identity_r_cases
+
+    a, r, s, k = ed25519_identity_r_cases(g)
+    assert ctx.ed25519_verify_prehashed(a, r, s, k).tolist() == [True, False, False]
+    assert coracle.ed25519_verify_prehashed(a, r, s, k).tolist() == [True, False, False]
 
 
 # ---- device-resident entry points ---------------------------------------------------------------------

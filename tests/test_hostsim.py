@@ -172,6 +172,16 @@ def test_ed25519_verify(hs, coracle):
     ok = np.zeros(20, dtype=np.uint8)
     k.hs_ed25519_verify(p(a), p(r), p(s), p(kk), ctypes.c_size_t(20), W, p(table), p(ok))
     assert np.array_equal(ok.astype(bool), coracle.ed25519_verify_prehashed(a, r, s, kk))
+    # R = identity: canonical encoding accepted, (x = 0, sign = 1) and non-canonical y rejected — the
+    # kernel compares encodings instead of decoding R, which must give the same three answers
+    from helpers import ed25519_identity_r_cases
+
+    a, r, s, kk = ed25519_identity_r_cases(g)
+    ok = np.zeros(3, dtype=np.uint8)
+    k.hs_ed25519_verify(p(a), p(r), p(s), p(kk), ctypes.c_size_t(3), W, p(table), p(ok))
+    assert ok.tolist() == [1, 0, 0]
+    assert coracle.ed25519_verify_prehashed(a, r, s, kk).tolist() == [True, False, False]
+    assert [R.ed25519_verify_prehashed(a[i].tobytes(), r[i].tobytes(), s[i].tobytes(), kk[i].tobytes()) for i in range(3)] == [True, False, False]
 
 
 def _structured(g, n):
