@@ -43,7 +43,12 @@ int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out) {
                   cudaDeviceGetAttribute(&d->sm_count, cudaDevAttrMultiProcessorCount, d->dev) == cudaSuccess;
         for (int s = 0; ok && s < ECB_NSLOT; s++) {
             Slot& sl = d->slots[s];
-            ok = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking) == cudaSuccess &&
+            int lo_p = 0, hi_p = 0;
+            cudaDeviceGetStreamPriorityRange(&lo_p, &hi_p);
+            ok = cudaStreamCreateWithPriority(&sl.stream, cudaStreamNonBlocking, lo_p) == cudaSuccess &&
+                 cudaStreamCreateWithPriority(&sl.hi, cudaStreamNonBlocking, hi_p) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&sl.ev_a, cudaEventDisableTiming) == cudaSuccess &&
+                 cudaEventCreateWithFlags(&sl.ev_b, cudaEventDisableTiming) == cudaSuccess &&
                  cudaMalloc(&sl.d_status, sizeof(unsigned long long)) == cudaSuccess &&
                  cudaMallocHost(&sl.h_status, sizeof(unsigned long long)) == cudaSuccess;
         }
@@ -74,6 +79,9 @@ void ecb_destroy(ecb_ctx* ctx) {
             if (sl.d_status) cudaFree(sl.d_status);
             if (sl.h_status) cudaFreeHost(sl.h_status);
             if (sl.ev_join) cudaEventDestroy(sl.ev_join);
+            if (sl.ev_a) cudaEventDestroy(sl.ev_a);
+            if (sl.ev_b) cudaEventDestroy(sl.ev_b);
+            if (sl.hi) cudaStreamDestroy(sl.hi);
             if (sl.stream) cudaStreamDestroy(sl.stream);
         }
         for (auto& r : d->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); cudaEventDestroy(r.c); }
@@ -110,6 +118,10 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "chunk")) {
         if (value < 1) return set_err(ctx, ECB_ERR_INVALID_ARG, "chunk must be >= 1");
         ctx->opt_chunk = (size_t)value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "inv_hi")) {
+        ctx->opt_inv_hi = value ? 1 : 0;
         return ECB_OK;
     }
     if (!strcmp(key, "dev_split")) {

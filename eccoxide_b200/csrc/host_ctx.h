@@ -28,8 +28,9 @@ struct DevBuf {
 
 // One pipeline slot: a stream with its own staging and work buffers.  The host entry points cut a
 // device's slice into chunks and rotate them over ECB_NSLOT slots, so the H2D copy of chunk i+1, the
-// kernels of chunk i and the D2H copy of chunk i-1 overlap (two copy engines + SMs).
-#define ECB_NSLOT 3
+// kernels of chunk i and the D2H copy of chunk i-1 overlap (two copy engines + SMs); measured e2e at n = 2^20:
+// 3 slots 491 M/s, 4 slots 500 M/s (Ed25519 mul_base).
+#define ECB_NSLOT 4
 struct Slot {
     cudaStream_t stream = nullptr;
     DevBuf planes, pf, scratch, aux, in[4], out[2];
@@ -37,6 +38,8 @@ struct Slot {
     unsigned long long* h_status = nullptr;  // pinned
     bool busy = false;
     cudaEvent_t ev_join = nullptr;            // device-resident fork/join (see dev_forkjoin)
+    cudaStream_t hi = nullptr;                // high-priority side stream for the batch-inversion kernel
+    cudaEvent_t ev_a = nullptr, ev_b = nullptr;
     size_t c0 = 0;                            // first element of the chunk in flight
 };
 
@@ -66,8 +69,9 @@ struct ecb_ctx {
     std::mutex err_mu;
     long opt_wei_w[3] = {16, 14, 16};  // comb widths: 36 MB, 22 MB, 50 MB tables
     long opt_ed_w = 16;  // 16 windows x 2^15 niels entries (50 MB, L2-resident): measured best on B200
-    size_t opt_chunk = (size_t)1 << 17;  // elements per pipeline chunk (3 slots in flight per device; measured best of 2^16..2^19)
+    size_t opt_chunk = 189440;  // elements per pipeline chunk = 148 SMs x 1280 (ECB_NSLOT chunks in flight per device; measured best of 2^16..2^19)
     long opt_profile = 0;
+    long opt_inv_hi = 1;                      // run batch inversions on the slot's high-priority side stream
     long opt_dev_split = 0;                   // 1: split large device-resident batches over the slot streams (measured: no gain, the
                                               // shorter inversion chains cost what the overlap saves; kept as an option)
     std::atomic<unsigned long long> launches{0};
