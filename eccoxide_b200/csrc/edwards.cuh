@@ -71,6 +71,28 @@ ECB_DEV void ge_double(ge_p3& r, const ge_p3& p) {
     if (WITH_T) F::mul(r.T, E, H);
 }
 
+// Same doubling with the T product behind a (warp-uniform) run-time flag: the window loops of the
+// variable-base kernels keep ONE copy of the doubling in a 4-iteration loop instead of two inlined
+// instances, which keeps the loop body inside the instruction cache.
+ECB_DEV void ge_double_rt(ge_p3& r, const ge_p3& p, u32 with_t) {
+    fe25519 A, B, C, E, G, Fv, H, t;
+    F::sqr(A, p.X);
+    F::sqr(B, p.Y);
+    F::sqr(C, p.Z);
+    F::dbl(C, C);
+    F::add(t, p.X, p.Y);
+    F::sqr(E, t);
+    F::add(H, A, B);
+    F::sub(E, E, H);
+    F::sub(G, B, A);
+    F::sub(Fv, G, C);
+    F::neg(H, H);
+    F::mul(r.X, E, Fv);
+    F::mul(r.Y, G, H);
+    F::mul(r.Z, Fv, G);
+    if (with_t) F::mul(r.T, E, H);
+}
+
 // r = p + q, q affine precomputed. 7M (6M when !WITH_T)
 template <bool WITH_T>
 ECB_DEV void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) {

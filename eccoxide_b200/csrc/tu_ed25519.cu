@@ -17,7 +17,7 @@ static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul(size_t n, const 
     u32* tbl = scratch + t * (8 * 32);
     for (size_t idx = t; idx < n; idx += T) ed25519_mul_body(idx, n, scalars, points, tbl, planes, status);
 }
-static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_verify(size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,
+static __global__ void __launch_bounds__(ECB_TPB, 3) k_ed25519_verify(size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,
                                                              const u32* table, int W, int nwin, u32* scratch, u32* planes,
                                                              unsigned char* ok) {
     size_t T = (size_t)gridDim.x * ECB_TPB, t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
