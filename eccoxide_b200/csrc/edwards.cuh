@@ -74,23 +74,26 @@ ECB_DEV void ge_double(ge_p3& r, const ge_p3& p) {
 // Same doubling with the T product behind a (warp-uniform) run-time flag: the window loops of the
 // variable-base kernels keep ONE copy of the doubling in a 4-iteration loop instead of two inlined
 // instances, which keeps the loop body inside the instruction cache.
+// NI: field products through the out-of-line by-value copies (smaller loop body; pays off in the
+// verification kernel, which is the largest, and costs ~9 % in the plain variable-base kernel).
+template <bool NI>
 ECB_DEV void ge_double_rt(ge_p3& r, const ge_p3& p, u32 with_t) {
     fe25519 A, B, C, E, G, Fv, H, t;
-    F::sqr(A, p.X);
-    F::sqr(B, p.Y);
-    F::sqr(C, p.Z);
+    if (NI) F::sqr_ni(A, p.X); else F::sqr(A, p.X);
+    if (NI) F::sqr_ni(B, p.Y); else F::sqr(B, p.Y);
+    if (NI) F::sqr_ni(C, p.Z); else F::sqr(C, p.Z);
     F::dbl(C, C);
     F::add(t, p.X, p.Y);
-    F::sqr(E, t);
+    if (NI) F::sqr_ni(E, t); else F::sqr(E, t);
     F::add(H, A, B);
     F::sub(E, E, H);
     F::sub(G, B, A);
     F::sub(Fv, G, C);
     F::neg(H, H);
-    F::mul(r.X, E, Fv);
-    F::mul(r.Y, G, H);
-    F::mul(r.Z, Fv, G);
-    if (with_t) F::mul(r.T, E, H);
+    if (NI) F::mul_ni(r.X, E, Fv); else F::mul(r.X, E, Fv);
+    if (NI) F::mul_ni(r.Y, G, H); else F::mul(r.Y, G, H);
+    if (NI) F::mul_ni(r.Z, Fv, G); else F::mul(r.Z, Fv, G);
+    if (with_t) { if (NI) F::mul_ni(r.T, E, H); else F::mul(r.T, E, H); }
 }
 
 // r = p + q, q affine precomputed. 7M (6M when !WITH_T)
@@ -114,24 +117,24 @@ ECB_DEV void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) {
 }
 
 // r = p + q, q projective cached. 8M
-template <bool WITH_T>
+template <bool WITH_T, bool NI = false>
 ECB_DEV void ge_add_cached(ge_p3& r, const ge_p3& p, const ge_cached& q) {
     fe25519 A, B, C, D, E, Fv, G, H;
     F::sub(A, p.Y, p.X);
-    F::mul(A, A, q.ym);
+    if (NI) F::mul_ni(A, A, q.ym); else F::mul(A, A, q.ym);
     F::add(B, p.Y, p.X);
-    F::mul(B, B, q.yp);
-    F::mul(C, p.T, q.t2d);
-    F::mul(D, p.Z, q.Z);
+    if (NI) F::mul_ni(B, B, q.yp); else F::mul(B, B, q.yp);
+    if (NI) F::mul_ni(C, p.T, q.t2d); else F::mul(C, p.T, q.t2d);
+    if (NI) F::mul_ni(D, p.Z, q.Z); else F::mul(D, p.Z, q.Z);
     F::dbl(D, D);
     F::sub(E, B, A);
     F::sub(Fv, D, C);
     F::add(G, D, C);
     F::add(H, B, A);
-    F::mul(r.X, E, Fv);
-    F::mul(r.Y, G, H);
-    F::mul(r.Z, Fv, G);
-    if (WITH_T) F::mul(r.T, E, H);
+    if (NI) F::mul_ni(r.X, E, Fv); else F::mul(r.X, E, Fv);
+    if (NI) F::mul_ni(r.Y, G, H); else F::mul(r.Y, G, H);
+    if (NI) F::mul_ni(r.Z, Fv, G); else F::mul(r.Z, Fv, G);
+    if (WITH_T) { if (NI) F::mul_ni(r.T, E, H); else F::mul(r.T, E, H); }
 }
 
 ECB_DEV void ge_to_cached(ge_cached& r, const ge_p3& p) {

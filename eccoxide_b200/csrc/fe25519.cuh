@@ -67,6 +67,20 @@ struct F25519 {
         sqr_full<8>(t, a.v);
         fold(r, t);
     }
+    // out-of-line copies (operands by value, so they stay in registers) for the kernels whose window
+    // loop would not fit the instruction cache with every product inlined
+    ECB_DEVNI static el mul_v(el a, el b) {
+        el r;
+        mul(r, a, b);
+        return r;
+    }
+    ECB_DEVNI static el sqr_v(el a) {
+        el r;
+        sqr(r, a);
+        return r;
+    }
+    ECB_DEV static void mul_ni(el& r, const el& a, const el& b) { r = mul_v(a, b); }
+    ECB_DEV static void sqr_ni(el& r, const el& a) { r = sqr_v(a); }
     // r = a * k for a small constant k (< 2^26)
     ECB_DEV static void mul_small(el& r, const el& a, u32 k) {
         u32 R[10];

@@ -263,7 +263,7 @@ ECB_DEV void ed25519_mul_body(size_t idx, size_t n, const u32* scalars, const u3
     for (int i = 63; i >= 0; i--) {
         if (i != 63) {
             ECB_NOUNROLL
-            for (int r = 0; r < 4; r++) ge_double_rt(acc, acc, r == 3 ? 1u : 0u);
+            for (int r = 0; r < 4; r++) ge_double_rt<false>(acc, acc, r == 3 ? 1u : 0u);
         }
         u32 neg;
         u32 d = booth_digit(k, 8, 4, i, neg);

@@ -490,7 +490,7 @@ ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u
         for (int i = 63; i >= 0; i--) {
             if (i != 63) {
                 ECB_NOUNROLL
-                for (int r = 0; r < 4; r++) ge_double_rt(acc, acc, r == 3 ? 1u : 0u);
+                for (int r = 0; r < 4; r++) ge_double_rt<true>(acc, acc, r == 3 ? 1u : 0u);
             }
             u32 neg;
             u32 d = booth_digit(k, 8, 4, i, neg);
@@ -499,7 +499,7 @@ ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u
                 const u32* sp = tbl + (d - 1) * 32;
                 ld_words_rw<8>(c.yp.v, sp); ld_words_rw<8>(c.ym.v, sp + 8); ld_words_rw<8>(c.Z.v, sp + 16); ld_words_rw<8>(c.t2d.v, sp + 24);
                 ge_cached_cneg(c, neg);
-                ge_add_cached<true>(acc, acc, c);
+                ge_add_cached<true, true>(acc, acc, c);
             }
         }
         // lhs = [S]B + [k](-A)
