@@ -230,25 +230,76 @@ def oracle_call(C, name, ins, nthreads):
 
 # ---- clocks --------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock, power and throttle reasons sampled DURING the timed region.  NVML is polled from a
+    thread of this process every ~2 ms (the timed region of the fixed-base workloads is only tens of
+    milliseconds, far shorter than nvidia-smi's loop period); nvidia-smi is the fallback."""
+
+    REASONS = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.th, self.stop_flag, self.max_mhz = index, [], None, None, False, None
+        self.nvml = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            import pynvml
+
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[self.index]) if vis and vis.split(",")[self.index].isdigit() else self.index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+            self.th = threading.Thread(target=self._poll, daemon=True)
+            self.th.start()
+            return
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
         except Exception:
             self.proc = None
 
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                except Exception:
+                    pw = None
+                self.rows.append((time.time(), mhz, mask, pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
+
     def _read(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for line in self.proc.stdout:
-            self.rows.append((time.time(), line.strip()))
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                mask = 0
+                for nm, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        mask |= self.REASONS[nm]
+                self.max_mhz = max(self.max_mhz or 0, int(float(f[1])))
+                self.rows.append((time.time(), int(float(f[0])), mask, float(f[2])))
+            except ValueError:
+                continue
 
     def stop(self):
+        self.stop_flag = True
         if self.proc:
             self.proc.terminate()
             try:
@@ -257,24 +308,19 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self, t0, t1):
-        sm, mx, reasons, pw = [], 0, set(), []
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for t, line in self.rows:
-            f = [x.strip() for x in line.split(",")]
-            if len(f) < 7:
-                continue
-            try:
-                mx = max(mx, int(float(f[1])))
-                if t0 <= t <= t1:
-                    sm.append(int(float(f[0])))
-                    pw.append(float(f[2]))
-                    for nm, v in zip(names, f[3:7]):
-                        if v.lower().startswith("active"):
-                            reasons.add(nm)
-            except ValueError:
-                continue
-        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+        inside = [r for r in self.rows if t0 <= r[0] <= t1]
+        scope = "timed region"
+        if not inside:  # region shorter than the sampling period: fall back to everything seen so far
+            inside, scope = list(self.rows), "whole run (timed region shorter than the sampling period)"
+        reasons = set()
+        for _, _, mask, _ in inside:
+            for nm, bit in self.REASONS.items():
+                if mask & bit:
+                    reasons.add(nm)
+        sm = [r[1] for r in inside]
+        pw = [r[3] for r in inside if r[3] is not None]
+        return {"sm_mhz": int(np.median(sm)) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw) if pw else None, "scope": scope, "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 # ---- measurement ---------------------------------------------------------------------------------
@@ -446,7 +492,7 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
@@ -526,7 +572,7 @@ def main():
             exp2 = oracle_call(C, name, [a[:m] for a in r["ins_h"]], os.cpu_count() or 1)
             check = check and all(np.array_equal(np.asarray(g[:m]).astype(np.uint8).reshape(m, -1), np.asarray(e).astype(np.uint8).reshape(m, -1)) for g, e in zip(e2e_out, exp2))
         cpu = None
-        if not args.no_cpu:
+        if not args.no_cpu and world == 1:  # CPU baseline: rank 0 at N = 1 only
             cpu, _, _ = cpu_baseline(name, r["ins_h"], 12.0, os.cpu_count() or 1)
         achieved = n * W / (r["ms_per_step"] * 1e-3) / 1e12
         try:
@@ -543,7 +589,7 @@ def main():
                            r["nbuf"], r["nbuf"] * r["in_bytes"] / 1e6, n * 4 * 32 / 1e6),
                        "parallelism": "%d x contiguous batch slice, no collective" % world},
             "e2e": {"value": world * n / e2e_s, "unit": "scalar-mults/s", "h2d_bytes_per_step": r["in_bytes"], "d2h_bytes_per_step": r["out_bytes"],
-                    "path": "ecb_* host entry point, pinned host buffers, chunks pipelined over 3 streams",
+                    "path": "ecb_* host entry point, pinned host buffers, chunks pipelined over 4 stream slots",
                     "pcie": pcie_bandwidth(torch)},
             "gpu_launches": int(r["launches"]),
             "roofline": {"bound": "imad", "achieved": achieved, "peak": peak, "unit": "T MAC32/s (32x32->64 multiply-accumulates)", "frac": achieved / peak if peak else None,

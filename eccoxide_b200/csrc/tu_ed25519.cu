@@ -92,6 +92,7 @@ int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, cons
     TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
     unsigned g = persistent_grid(d, k_ed25519_verify, n);
     TRY(ensure(ctx, d.cur->scratch, (size_t)g * ECB_TPB * 8 * 32 * sizeof(u32)));
+    TRY(reset_status(ctx, d, s));
     u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
     k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, (u32*)d.cur->scratch.p, planes, ok);

@@ -10,6 +10,7 @@ static __global__ void __launch_bounds__(ECB_TPB) k_x25519(size_t n, const u32* 
 int dev_x25519(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_u, size_t n, u32* d_out, cudaStream_t s) {
     TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
+    TRY(reset_status(ctx, d, s));  // these kernels report no per-element errors; keep the word clean for ecb_dev_status
     u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
     k_x25519<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d_u, planes);
