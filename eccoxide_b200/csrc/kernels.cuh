@@ -500,21 +500,9 @@ struct FinX25519 {  // out: u' = x2 / z2 little-endian canonical, 0 when z2 == 0
 // coordinates and window recoding — only the canonical affine result is observable).
 //   scalars: n x SB bytes big-endian canonical (< group order)
 //   points : n x 2FB bytes big-endian affine (x, y), on the curve; inf_in (optional) marks
-//            identity inputs; points == NULL selects the generator (Point::mul_base)
+//            identity inputs
 //   tbl    : this thread's scratch, 8 entries x 5N words (X, Y, Z, Z^2, Z^3)
 // =======================================================================================
-template <class C>
-ECB_DEV void wei_store_cached(u32* d, const typename WeiJ<C>::cached& c) {
-    constexpr int N = C::F::N;
-    st_words<N>(d, c.X.v); st_words<N>(d + N, c.Y.v); st_words<N>(d + 2 * N, c.Z.v);
-    st_words<N>(d + 3 * N, c.ZZ.v); st_words<N>(d + 4 * N, c.ZZZ.v);
-}
-template <class C>
-ECB_DEV void wei_load_cached(typename WeiJ<C>::cached& c, const u32* s) {
-    constexpr int N = C::F::N;
-    ld_words_rw<N>(c.X.v, s); ld_words_rw<N>(c.Y.v, s + N); ld_words_rw<N>(c.Z.v, s + 2 * N);
-    ld_words_rw<N>(c.ZZ.v, s + 3 * N); ld_words_rw<N>(c.ZZZ.v, s + 4 * N);
-}
 // tbl[j-1] = cached(j * (x, y)), j = 1..8: 4 doublings + 3 additions.  Entries are written to
 // the table as soon as they exist and re-read when needed, so a single point is live at a time.
 template <class C>
@@ -572,7 +560,7 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
     }
     u32 is_inf = inf_in ? (inf_in[idx] ? 1u : 0u) : 0u;
     fe px, py;
-    if (points) {
+    {
         u32 xw[N], yw[N];
         ld_words_be<N>(xw, points + idx * 2 * N);
         ld_words_be<N>(yw, points + idx * 2 * N + N);
@@ -582,9 +570,6 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
             report_bad(status, idx, ST_BAD_POINT);
             ok = 0;
         }
-    } else {  // fixed base: the curve generator (Point::mul_base)
-        ECB_UNROLL
-        for (int i = 0; i < N; i++) { px.v[i] = C::gx(i); py.v[i] = C::gy(i); }
     }
     typename J::pt acc;
     J::set_inf(acc);

@@ -1,10 +1,10 @@
-// weier.cuh — short-Weierstrass homogeneous projective arithmetic with the complete
-// Renes–Costello–Batina formulas (eprint 2015/1060), a = -3 (Alg. 4/5/6) and a = 0 (Alg. 7/8/9).
+// weier.cuh — short-Weierstrass curves of the batch path (p256r1, p384r1, BLS12-381 G1): curve
+// descriptions, the on-curve check and Jacobian point arithmetic.
 //
-// Same group law as the reference's generic projective::Point<FE>
-// (src/curve/projective.rs:340 add_different_am3, :586 double_am3, :268 add_different_a0,
-// :544 double_a0); INFINITY = (0:1:0) (:152).  The formulas are complete on odd-order curves
-// (P-256, P-384, BLS12-381 E(Fp)), so there are no exceptional inputs.
+// The reference's generic projective::Point<FE> uses homogeneous coordinates with the complete
+// Renes–Costello–Batina formulas (src/curve/projective.rs:340 add_different_am3, :586 double_am3,
+// :268 add_different_a0, :544 double_a0; INFINITY = (0:1:0) :152).  The kernels compute the same
+// group law in Jacobian coordinates (see WeiJ below): only canonical affine results are observable.
 #pragma once
 #include "mont_kinds.cuh"
 
@@ -87,143 +87,7 @@ struct Wei {
         return F::eq(l, r);
     }
 
-    // complete addition
-    ECB_DEV static void add(pt& r, const pt& p, const pt& q) {
-        fe t0, t1, t2, t3, t4, X3, Y3, Z3, b;
-        F::mul(t0, p.X, q.X);
-        F::mul(t1, p.Y, q.Y);
-        F::mul(t2, p.Z, q.Z);
-        F::add(t3, p.X, p.Y);
-        F::add(t4, q.X, q.Y);
-        F::mul(t3, t3, t4);
-        F::add(t4, t0, t1);
-        F::sub(t3, t3, t4);
-        F::add(t4, p.Y, p.Z);
-        F::add(X3, q.Y, q.Z);
-        F::mul(t4, t4, X3);
-        F::add(X3, t1, t2);
-        F::sub(t4, t4, X3);
-        F::add(X3, p.X, p.Z);
-        F::add(Y3, q.X, q.Z);
-        F::mul(X3, X3, Y3);
-        F::add(Y3, t0, t2);
-        F::sub(Y3, X3, Y3);
-        if (C::A_M3) {
-            get_b(b);
-            F::mul(Z3, b, t2);
-            F::sub(X3, Y3, Z3);
-            F::dbl(Z3, X3);
-            F::add(X3, X3, Z3);
-            F::sub(Z3, t1, X3);
-            F::add(X3, t1, X3);
-            F::mul(Y3, b, Y3);
-            F::dbl(t1, t2);
-            F::add(t2, t1, t2);
-            F::sub(Y3, Y3, t2);
-            F::sub(Y3, Y3, t0);
-            F::dbl(t1, Y3);
-            F::add(Y3, t1, Y3);
-            F::dbl(t1, t0);
-            F::add(t0, t1, t0);
-            F::sub(t0, t0, t2);
-            F::mul(t1, t4, Y3);
-            F::mul(t2, t0, Y3);
-            F::mul(Y3, X3, Z3);
-            F::add(Y3, Y3, t2);
-            F::mul(X3, t3, X3);
-            F::sub(X3, X3, t1);
-            F::mul(Z3, t4, Z3);
-            F::mul(t1, t3, t0);
-            F::add(Z3, Z3, t1);
-        } else {
-            get_b3(b);
-            F::dbl(X3, t0);
-            F::add(t0, X3, t0);
-            F::mul(t2, b, t2);
-            F::add(Z3, t1, t2);
-            F::sub(t1, t1, t2);
-            F::mul(Y3, b, Y3);
-            F::mul(X3, t4, Y3);
-            F::mul(t2, t3, t1);
-            F::sub(X3, t2, X3);
-            F::mul(Y3, Y3, t0);
-            F::mul(t1, t1, Z3);
-            F::add(Y3, t1, Y3);
-            F::mul(t0, t0, t3);
-            F::mul(Z3, Z3, t4);
-            F::add(Z3, Z3, t0);
-        }
-        F::copy(r.X, X3);
-        F::copy(r.Y, Y3);
-        F::copy(r.Z, Z3);
-    }
-
-    // complete doubling
-    ECB_DEV static void dbl(pt& r, const pt& p) {
-        fe t0, t1, t2, t3, X3, Y3, Z3, b;
-        if (C::A_M3) {
-            get_b(b);
-            F::sqr_ni(t0, p.X);
-            F::sqr_ni(t1, p.Y);
-            F::sqr_ni(t2, p.Z);
-            F::mul_ni(t3, p.X, p.Y);
-            F::dbl(t3, t3);
-            F::mul_ni(Z3, p.X, p.Z);
-            F::dbl(Z3, Z3);
-            F::mul_ni(Y3, b, t2);
-            F::sub(Y3, Y3, Z3);
-            F::dbl(X3, Y3);
-            F::add(Y3, X3, Y3);
-            F::sub(X3, t1, Y3);
-            F::add(Y3, t1, Y3);
-            F::mul_ni(Y3, X3, Y3);
-            F::mul_ni(X3, X3, t3);
-            F::dbl(t3, t2);
-            F::add(t2, t2, t3);
-            F::mul_ni(Z3, b, Z3);
-            F::sub(Z3, Z3, t2);
-            F::sub(Z3, Z3, t0);
-            F::dbl(t3, Z3);
-            F::add(Z3, Z3, t3);
-            F::dbl(t3, t0);
-            F::add(t0, t3, t0);
-            F::sub(t0, t0, t2);
-            F::mul_ni(t0, t0, Z3);
-            F::add(Y3, Y3, t0);
-            F::mul_ni(t0, p.Y, p.Z);
-            F::dbl(t0, t0);
-            F::mul_ni(Z3, t0, Z3);
-            F::sub(X3, X3, Z3);
-            F::mul_ni(Z3, t0, t1);
-            F::dbl(Z3, Z3);
-            F::dbl(Z3, Z3);
-        } else {
-            get_b3(b);
-            F::sqr_ni(t0, p.Y);
-            F::dbl(Z3, t0);
-            F::dbl(Z3, Z3);
-            F::dbl(Z3, Z3);
-            F::mul_ni(t1, p.Y, p.Z);
-            F::sqr_ni(t2, p.Z);
-            F::mul_ni(t2, b, t2);
-            F::mul_ni(X3, t2, Z3);
-            F::add(Y3, t0, t2);
-            F::mul_ni(Z3, t1, Z3);
-            F::dbl(t1, t2);
-            F::add(t2, t1, t2);
-            F::sub(t0, t0, t2);
-            F::mul_ni(Y3, t0, Y3);
-            F::add(Y3, X3, Y3);
-            F::mul_ni(t1, p.X, p.Y);
-            F::mul_ni(X3, t0, t1);
-            F::dbl(X3, X3);
-        }
-        F::copy(r.X, X3);
-        F::copy(r.Y, Y3);
-        F::copy(r.Z, Z3);
-    }
 };
-
 
 // =======================================================================================
 // Jacobian coordinates (X : Y : Z), x = X/Z^2, y = Y/Z^3, infinity <=> Z = 0.

@@ -542,3 +542,38 @@ def test_context_over_all_visible_devices_shards_by_contiguous_slice(coracle):
         with pytest.raises(EccBatchError) as e:
             c.ed25519_mul_base(kb)
         assert e.value.code == -3 and e.value.bad_index == n // 2 + 1
+
+
+def test_host_entry_points_across_pipeline_chunks(ctx, coracle):
+    """A batch spanning several pipeline chunks (default 189 440 elements, 4 stream slots): exact
+    results at the chunk borders and the first offender reported with its global index."""
+    from eccoxide_b200 import EccBatchError
+
+    g = rng(2718)
+    n = 3 * 189440 + 777
+    kb = rand_bytes(g, n, 32)
+    kb[:, 31] &= 0x0F
+    got = ctx.ed25519_mul_base(kb)
+    idx = np.concatenate([np.arange(32)] + [np.arange(c * 189440 - 16, c * 189440 + 16) for c in (1, 2, 3)] + [np.arange(n - 32, n)])
+    assert np.array_equal(got[idx], coracle.ed25519_mul_base(kb[idx], threads(coracle)))
+    kb[2 * 189440 + 5] = 0xFF
+    kb[3 * 189440 + 9] = 0xFF
+    with pytest.raises(EccBatchError) as e:
+        ctx.ed25519_mul_base(kb)
+    assert e.value.code == -3 and e.value.bad_index == 2 * 189440 + 5
+    # a small chunk size exercises slot reuse many times
+    ctx.set_option("chunk", 1000)
+    try:
+        k, u = rand_bytes(g, 25000, 32), rand_bytes(g, 25000, 32)
+        assert np.array_equal(ctx.x25519(k, u), coracle.x25519(k, u, threads(coracle)))
+    finally:
+        ctx.set_option("chunk", 189440)
+
+
+def test_options_are_validated(ctx):
+    from eccoxide_b200 import EccBatchError
+
+    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 17), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0)):
+        with pytest.raises(EccBatchError) as e:
+            ctx.set_option(key, val)
+        assert e.value.code == -2
