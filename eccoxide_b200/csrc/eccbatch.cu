@@ -62,7 +62,7 @@ int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out) {
     const char* w = getenv("ECB_ED25519_COMB_W");
     if (w) {
         long v = atol(w);
-        if (v >= 4 && v <= 16) ctx->opt_ed_w = v;
+        if (v >= 4 && v <= 24) ctx->opt_ed_w = v;
     }
     *out = ctx;
     return ECB_OK;
@@ -102,12 +102,12 @@ unsigned long long ecb_launch_count(ecb_ctx* ctx) { return ctx ? ctx->launches.l
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return ECB_ERR_INVALID_ARG;
     if (!strcmp(key, "ed25519_comb_w")) {
-        if (value < 4 || value > 16) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_comb_w must be in 4..16");
+        if (value < 4 || value > 24) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_comb_w must be in 4..24");
         ctx->opt_ed_w = value;
         return ECB_OK;
     }
     if (!strcmp(key, "p256r1_comb_w") || !strcmp(key, "p384r1_comb_w") || !strcmp(key, "bls12_381_g1_comb_w")) {
-        if (value < 4 || value > 16) return set_err(ctx, ECB_ERR_INVALID_ARG, "comb width must be in 4..16");
+        if (value < 4 || value > 22) return set_err(ctx, ECB_ERR_INVALID_ARG, "comb width must be in 4..22");
         ctx->opt_wei_w[key[1] == '2' ? 0 : (key[1] == '3' ? 1 : 2)] = value;
         return ECB_OK;
     }
@@ -524,8 +524,8 @@ long ecb_debug_ed25519_table(ecb_ctx* ctx, int di, uint8_t* out, size_t cap, int
     if (!d) return ECB_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
     if (cudaSetDevice(d->dev) != cudaSuccess) return ECB_ERR_CUDA;
-    if (!d->ed_table || d->ed_w != (int)ctx->opt_ed_w) {
-        int r = dev_ed25519_build_table(ctx, *d, (int)ctx->opt_ed_w);
+    if (!d->ed_table || (ctx->opt_ed_w && d->ed_w != (int)ctx->opt_ed_w)) {
+        int r = dev_ed25519_build_table(ctx, *d, ctx->opt_ed_w ? (int)ctx->opt_ed_w : 16);
         if (r != ECB_OK) return r;
     }
     size_t ntab = (size_t)d->ed_nwin << (d->ed_w - 1);

@@ -67,8 +67,12 @@ struct ecb_ctx {
     std::vector<DevCtx*> devs;
     std::string err;
     std::mutex err_mu;
-    long opt_wei_w[3] = {16, 14, 16};  // comb widths: 36 MB, 22 MB, 50 MB tables
-    long opt_ed_w = 16;  // 16 windows x 2^15 niels entries (50 MB, L2-resident): measured best on B200
+    long opt_wei_w[3] = {20, 18, 20};  // generator comb widths: 13 / 22 / 13 windows, 436 MB / 277 MB / 654 MB tables
+    // Ed25519 comb width; 0 = pick by free device memory (24: 11 windows, 8.9 GB table; 20: 13 windows, 0.65 GB;
+    // 16: 16 windows, 50 MB).  Measured at n = 2^20: w=16 772 M/s, 20 907, 22 969, 24 1041 M/s — the kernel is
+    // integer-pipe-bound, so time follows the window count; the random table reads (96 B per window) stay
+    // far below HBM bandwidth.
+    long opt_ed_w = 0;
     size_t opt_chunk = 189440;  // elements per pipeline chunk = 148 SMs x 1280 (ECB_NSLOT chunks in flight per device; measured best of 2^16..2^19)
     long opt_profile = 0;
     long opt_inv_hi = 1;                      // run batch inversions on the slot's high-priority side stream

@@ -25,6 +25,16 @@ static __global__ void __launch_bounds__(ECB_TPB, 3) k_ed25519_verify(size_t n, 
     for (size_t idx = t; idx < n; idx += T) ed25519_verify_body(idx, n, a_enc, s_le, k_le, table, W, nwin, tbl, planes, ok);
 }
 
+// comb width actually used on this device: the option, or (option 0) the widest whose table and
+// transient build buffers (~2.5x the table) fit comfortably in the free memory
+static int ed_pick_w(ecb_ctx* ctx) {
+    if (ctx->opt_ed_w) return (int)ctx->opt_ed_w;
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 16;
+    if (free_b > ((size_t)64 << 30)) return 24;
+    if (free_b > ((size_t)8 << 30)) return 20;
+    return 16;
+}
 int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
     int nwin = (254 + W - 1) / W;
     size_t ntab = (size_t)nwin << (W - 1);
@@ -39,13 +49,20 @@ int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
     FinEdNiels fin{(const u32*)d.cur->planes.p, ntab, d.ed_table};
     TRY((launch_batch_inv<F25519, FinEdNiels>(ctx, d, ntab, (const u32*)d.cur->planes.p, (u32*)d.cur->pf.p, fin, d.stream)));
     CU(cudaStreamSynchronize(d.stream));
+    if (ntab * 96 > ((size_t)256 << 20)) {  // give the build buffers of a large table back
+        for (DevBuf* b : {&d.cur->planes, &d.cur->pf}) {
+            if (b->p) CU(cudaFree(b->p));
+            b->p = nullptr;
+            b->cap = 0;
+        }
+    }
     d.ed_w = W;
     d.ed_nwin = nwin;
     return ECB_OK;
 }
 
 int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s) {
-    if (!d.ed_table || d.ed_w != (int)ctx->opt_ed_w) TRY(dev_ed25519_build_table(ctx, d, (int)ctx->opt_ed_w));
+    if (!d.ed_table || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
     TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
     TRY(reset_status(ctx, d, s));
@@ -87,7 +104,7 @@ int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, siz
 
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
                        unsigned char* ok, cudaStream_t s) {
-    if (!d.ed_table || d.ed_w != (int)ctx->opt_ed_w) TRY(dev_ed25519_build_table(ctx, d, (int)ctx->opt_ed_w));
+    if (!d.ed_table || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
     TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
     unsigned g = persistent_grid(d, k_ed25519_verify, n);

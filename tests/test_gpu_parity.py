@@ -573,7 +573,7 @@ def test_host_entry_points_across_pipeline_chunks(ctx, coracle):
 def test_options_are_validated(ctx):
     from eccoxide_b200 import EccBatchError
 
-    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 17), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0)):
+    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 25), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0)):
         with pytest.raises(EccBatchError) as e:
             ctx.set_option(key, val)
         assert e.value.code == -2
