@@ -42,6 +42,7 @@ WORK = {
     "p256_mul_base": 896 * 64 + 3 * 64,      # reference comb: 64 complete additions x 14 M + affine share
     "bls12_381_g1_mul_base": 896 * 300 + 3 * 300,
     "x25519": 155864,
+    "x25519_base": 155864,                     # the reference computes x25519_base as the full ladder on u = 9
     "p256_mul": 261420,
     "p256_ecdsa_verify": 296900,
     "p384_mul": 864666,
@@ -53,6 +54,7 @@ WORKLOADS = {
     "ed25519_mul_base": (20, 32, 64, "configs[0] op (Ed25519 Point::mul_base) at the 2^20 batch of configs[1..3]"),
     "ed25519_mul_base_2p16": (16, 32, 64, "configs[0] exactly: 2^16 scalars"),
     "x25519": (20, 64, 32, "configs[1]"),
+    "x25519_base": (20, 32, 32, "x25519_base (public keys): fixed-base comb instead of the ladder"),
     "p256_mul": (20, 96, 65, "configs[2] variable-base Point::mul"),
     "p256_ecdsa_verify": (20, 160, 1, "configs[2] ecdsa verify_batch"),
     "bls12_381_g1_mul": (20, 128, 97, "configs[3]"),
@@ -91,6 +93,8 @@ def make_inputs(name, n, ctx, seed):
         return [rand_scalars(g, n, 32, 4, "little")]
     if base == "x25519":
         return [g.integers(0, 256, size=(n, 32), dtype=np.uint8), g.integers(0, 256, size=(n, 32), dtype=np.uint8)]
+    if base == "x25519_base":
+        return [g.integers(0, 256, size=(n, 32), dtype=np.uint8)]
     if base == "x448":
         return [g.integers(0, 256, size=(n, 56), dtype=np.uint8), g.integers(0, 256, size=(n, 56), dtype=np.uint8)]
     if base == "ed25519_mul":
@@ -150,7 +154,7 @@ def make_inputs(name, n, ctx, seed):
 
 
 OUT_SHAPES = {
-    "ed25519_mul_base": [64], "ed25519_mul": [64], "x25519": [32], "x448": [56],
+    "ed25519_mul_base": [64], "ed25519_mul": [64], "x25519": [32], "x25519_base": [32], "x448": [56],
     "p256_mul": [64, 1], "p384_mul": [96, 1], "bls12_381_g1_mul": [96, 1], "p256_ecdsa_verify": [1],
     "p256_mul_base": [64, 1], "bls12_381_g1_mul_base": [96, 1], "ed25519_verify": [1],
 }
@@ -167,6 +171,8 @@ def dev_launch(ctx, name, ins, outs, n, stream):
         ctx.dev_call("ecb_ed25519_mul_dev", 0, p[0], p[1], n, o[0], stream)
     elif base == "x25519":
         ctx.dev_call("ecb_x25519_dev", 0, p[0], p[1], n, o[0], stream)
+    elif base == "x25519_base":
+        ctx.dev_call("ecb_x25519_base_dev", 0, p[0], n, o[0], stream)
     elif base == "x448":
         ctx.dev_call("ecb_x448_dev", 0, p[0], p[1], n, o[0], stream)
     elif base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
@@ -192,6 +198,8 @@ def host_call(ctx, name, ins, outs=None):
         return [ctx.ed25519_mul(ins[0], ins[1], out=o[0])]
     if base == "x25519":
         return [ctx.x25519(ins[0], ins[1], out=o[0])]
+    if base == "x25519_base":
+        return [ctx.x25519_base(ins[0], out=o[0])]
     if base == "x448":
         return [ctx.x448(ins[0], ins[1], out=o[0])]
     if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
@@ -214,6 +222,9 @@ def oracle_call(C, name, ins, nthreads):
         return [C.ed25519_mul(ins[0], ins[1], nthreads)]
     if base == "x25519":
         return [C.x25519(ins[0], ins[1], nthreads)]
+    if base == "x25519_base":
+        nine = np.tile(np.frombuffer((9).to_bytes(32, "little"), dtype=np.uint8), (len(ins[0]), 1))
+        return [C.x25519(ins[0], nine, nthreads)]
     if base == "x448":
         return [C.x448(ins[0], ins[1], nthreads)]
     if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):

@@ -33,6 +33,7 @@ extern "C" {
     pub fn ecb_ed25519_mul(ctx: *mut ecb_ctx, k_le: *const u8, xy_in: *const u8, n: usize, xy_out: *mut u8, bad_index: *mut usize) -> c_int;
     pub fn ecb_ed25519_verify_prehashed(ctx: *mut ecb_ctx, a_enc: *const u8, r_enc: *const u8, s_le: *const u8, k_le: *const u8, n: usize, ok: *mut u8) -> c_int;
     pub fn ecb_x25519(ctx: *mut ecb_ctx, k: *const u8, u: *const u8, n: usize, out: *mut u8) -> c_int;
+    pub fn ecb_x25519_base(ctx: *mut ecb_ctx, k: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn ecb_x448(ctx: *mut ecb_ctx, k: *const u8, u: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn ecb_wei_mul(ctx: *mut ecb_ctx, curve_id: c_int, k_be: *const u8, xy_be: *const u8, inf_in: *const u8, n: usize,
                        out_xy_be: *mut u8, out_inf: *mut u8, bad_index: *mut usize) -> c_int;

@@ -41,6 +41,8 @@ SIGNATURES = {
     "ecb_ed25519_mul": (_int, [_vp, _vp, _vp, _sz, _vp, _szp]),
     "ecb_ed25519_verify_prehashed": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ecb_x25519": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ecb_x25519_base": (_int, [_vp, _vp, _sz, _vp]),
+    "ecb_x25519_base_dev": (_int, [_vp, _int, _vp, _sz, _vp, _vp]),
     "ecb_x448": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "ecb_wei_mul": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _vp, _szp]),
     "ecb_wei_mul_base": (_int, [_vp, _int, _vp, _sz, _vp, _vp, _szp]),

@@ -137,6 +137,14 @@ class Context:
         self._check(self._lib.ecb_x25519(self._ctx, _p(k), _p(u), n, _p(out)))
         return out
 
+    def x25519_base(self, k, out=None):
+        """x25519::x25519_base: public keys of `k` (n x 32 raw secret bytes, clamped inside)."""
+        k = _rows(k, 32, "k")
+        n = k.shape[0]
+        out = _out(out, (n, 32))
+        self._check(self._lib.ecb_x25519_base(self._ctx, _p(k), n, _p(out)))
+        return out
+
     def x448(self, k, u, out=None):
         k = _rows(k, 56, "k")
         u = _rows(u, 56, "u")

@@ -344,6 +344,14 @@ int ecb_x25519(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8
                            return dev_x25519(ctx, d, (const u32*)in[0], (const u32*)in[1], cn, (u32*)o[0], s);
                        });
 }
+int ecb_x25519_base(ecb_ctx* ctx, const uint8_t* k, size_t n, uint8_t* out) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k || !out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k, 32}}, {{out, 32}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_x25519_base(ctx, d, (const u32*)in[0], cn, (u32*)o[0], s);
+                       });
+}
 int ecb_x448(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8_t* out) {
     if (!ctx) return ECB_ERR_CUDA;
     if (n && (!k || !u || !out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
@@ -421,6 +429,13 @@ int ecb_x25519_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_
     CU(cudaSetDevice(d->dev));
     single_slot(d);
     return dev_x25519(ctx, *d, (const u32*)d_k, (const u32*)d_u, n, (u32*)d_out, (cudaStream_t)stream);
+}
+int ecb_x25519_base_dev(ecb_ctx* ctx, int di, const void* d_k, size_t n, void* d_out, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    single_slot(d);
+    return dev_x25519_base(ctx, *d, (const u32*)d_k, n, (u32*)d_out, (cudaStream_t)stream);
 }
 int ecb_wei_mul_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, const void* d_xy, size_t n, void* d_out, void* d_inf,
                     void* stream) {

@@ -147,11 +147,18 @@ ECB_DEV u32 lt_words8(const u32* a, const u32* m) {  // a < m ?
 //   i = 0..nwin-1, nwin = ceil(254 / W).
 // Writes projective X, Y, Z planes; the affine conversion is the batch-inversion kernel.
 // =======================================================================================
+// CLAMP: the scalar is an X25519 secret (protocol/x25519.rs:15 clamp, :49 x25519_base): any 32 bytes,
+// clamped here, up to 255 bits — the comb covers W * nwin >= 256 bits and k*B = (k mod l)*B.
+template <bool CLAMP>
 ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin,
                                    u32* planes, unsigned long long* status) {
-    u32 k[8];
+    u32 k[9];
     ld_words<8>(k, scalars + idx * 8);
-    if (!lt_words8(k, ED25519_L)) {
+    k[8] = 0;
+    if (CLAMP) {
+        k[0] &= 0xfffffff8u;
+        k[7] = (k[7] & 0x7fffffffu) | 0x40000000u;
+    } else if (!lt_words8(k, ED25519_L)) {
         report_bad(status, idx, ST_NONCANONICAL_SCALAR);
         ECB_UNROLL
         for (int i = 0; i < 8; i++) k[i] = 0;
@@ -161,7 +168,7 @@ ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, con
     ge_identity(acc);
     for (int i = 0; i < nwin; i++) {
         u32 neg;
-        u32 d = booth_digit(k, 8, W, i, neg);
+        u32 d = booth_digit(k, 9, W, i, neg);
         ge_niels e;
         ge_niels_identity(e);
         if (d != 0) {
@@ -176,6 +183,22 @@ ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, con
     plane_st<8>(planes + 0 * 8 * n, n, idx, acc.X.v);
     plane_st<8>(planes + 1 * 8 * n, n, idx, acc.Y.v);
     plane_st<8>(planes + 2 * 8 * n, n, idx, acc.Z.v);
+}
+
+// X25519 against the base point (protocol/x25519.rs:49 x25519_base = x25519(k, 9)): the ladder on
+// u = 9 equals the u-coordinate of clamp(k) * B on the birationally equivalent edwards25519
+// (u = (1 + y) / (1 - y), curve25519.rs:1668 tests this map), so the fixed-base comb replaces 255
+// ladder steps.  Writes Z + Y -> plane 0, Z - Y -> plane 2; FinEdMontU divides (0 when Z = Y, as the
+// ladder's z2 = 0 case gives).
+ECB_DEV void x25519_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin, u32* planes) {
+    ed25519_mul_base_body<true>(idx, n, scalars, table, W, nwin, planes, nullptr);
+    fe25519 Y, Z, s, d;
+    plane_ld<8>(Y.v, planes + 1 * 8 * n, n, idx);
+    plane_ld<8>(Z.v, planes + 2 * 8 * n, n, idx);
+    F::add(s, Z, Y);
+    F::sub(d, Z, Y);
+    plane_st<8>(planes + 0 * 8 * n, n, idx, s.v);
+    plane_st<8>(planes + 2 * 8 * n, n, idx, d.v);
 }
 
 // comb-table builder: entry (i, j) = j * 2^(W*i) * B by plain double-and-add on the 256-bit
@@ -457,6 +480,20 @@ struct FinEdCompressed {  // out: encode_point (protocol/ed25519.rs:27)
         F::freeze(y, y);
         y.v[7] |= (x.v[0] & 1u) << 31;
         st_words<8>(out + idx * 8, y.v);
+    }
+};
+struct FinEdMontU {  // out: u = (1 + y) / (1 - y) = (Z + Y) / (Z - Y), little-endian canonical; 0 for the identity
+    const u32* planes; size_t n; u32* out;   // the "Z" plane holds Z - Y (see ed25519_to_montgomery_planes)
+    ECB_DEV void pre(size_t idx) const { plane_prefetch<8>(planes, n, idx); }
+    ECB_DEV void operator()(size_t idx, const fe25519& dinv, u32 zero) const {
+        fe25519 N_, u;
+        plane_ld<8>(N_.v, planes, n, idx);
+        F::mul(u, N_, dinv);
+        F::freeze(u, u);
+        u32 m = zero ? 0u : 0xffffffffu;
+        ECB_UNROLL
+        for (int i = 0; i < 8; i++) u.v[i] &= m;
+        st_words<8>(out + idx * 8, u.v);
     }
 };
 struct FinEdNiels {  // out: comb-table entry (y+x, y-x, 2dxy), 24 words

@@ -5,7 +5,7 @@
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul_base(size_t n, const u32* scalars, const u32* table, int W,
                                                                int nwin, u32* planes, unsigned long long* status) {
     size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
-    if (idx < n) ed25519_mul_base_body(idx, n, scalars, table, W, nwin, planes, status);
+    if (idx < n) ed25519_mul_base_body<false>(idx, n, scalars, table, W, nwin, planes, status);
 }
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_table_points(size_t ntab, int W, int nwin, u32* planes) {
     size_t e = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
@@ -80,6 +80,29 @@ int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32*
         FinEdXY fin{planes, n, d_out};
         rc = launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     }
+    prof_mark(ctx, d, s, 2);
+    return rc;
+}
+
+static __global__ void __launch_bounds__(ECB_TPB) k_x25519_base(size_t n, const u32* scalars, const u32* table, int W, int nwin,
+                                                          u32* planes) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) x25519_base_body(idx, n, scalars, table, W, nwin, planes);
+}
+int dev_x25519_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, cudaStream_t s) {
+    if (!d.ed_table || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
+    if (d.ed_w * d.ed_nwin < 256) return set_err(ctx, ECB_ERR_INVALID_ARG, "x25519_base needs a comb covering 256 bits (ed25519_comb_w)");
+    TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
+    TRY(reset_status(ctx, d, s));
+    u32* planes = (u32*)d.cur->planes.p;
+    prof_mark(ctx, d, s, 0);
+    k_x25519_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, planes);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    prof_mark(ctx, d, s, 1);
+    FinEdMontU fin{planes, n, d_out};
+    int rc = launch_batch_inv<F25519, FinEdMontU>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     prof_mark(ctx, d, s, 2);
     return rc;
 }

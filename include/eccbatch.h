@@ -86,6 +86,10 @@ int ecb_ed25519_verify_prehashed(ecb_ctx* ctx, const uint8_t* a_enc, const uint8
 /* protocol::x25519::x25519(scalar, u)   (src/protocol/x25519.rs:36): clamps inside, masks bit 255
  * of u, accepts non-canonical u, returns 0 for low-order inputs.  k, u, out: n x 32 B. */
 int ecb_x25519(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8_t* out);
+/* protocol::x25519::x25519_base(scalar) = x25519(scalar, 9)   (src/protocol/x25519.rs:49; SecretKey::public_key
+ * :75): public-key generation.  Same bytes as ecb_x25519 with u = 9, computed with the fixed-base
+ * comb instead of the ladder.  k, out: n x 32 B. */
+int ecb_x25519_base(ecb_ctx* ctx, const uint8_t* k, size_t n, uint8_t* out);
 /* protocol::x448::x448(scalar, u)   (src/protocol/x448.rs:34).  k, u, out: n x 56 B. */
 int ecb_x448(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8_t* out);
 
@@ -110,6 +114,7 @@ int ecb_ecdsa_verify_hashed(ecb_ctx* ctx, int curve_id, const uint8_t* q_xy_be, 
 int ecb_ed25519_mul_base_dev(ecb_ctx* ctx, int dev_index, const void* d_k_le, size_t n, void* d_xy_le, void* stream);
 int ecb_ed25519_mul_dev(ecb_ctx* ctx, int dev_index, const void* d_k_le, const void* d_xy_in, size_t n, void* d_xy_out,
                         void* stream);
+int ecb_x25519_base_dev(ecb_ctx* ctx, int dev_index, const void* d_k, size_t n, void* d_out, void* stream);
 int ecb_x25519_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);
 int ecb_wei_mul_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_k_be, const void* d_xy_be, size_t n,
                     void* d_out_xy_be, void* d_out_inf, void* stream);

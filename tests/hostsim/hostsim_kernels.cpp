@@ -28,7 +28,7 @@ unsigned long long hs_ed25519_mul_base(const u32* k, size_t n, int W, const u32*
     int nwin = (254 + W - 1) / W;
     std::vector<u32> planes(3 * 8 * n), pf(8 * n);
     unsigned long long st = ~0ull;
-    for (size_t i = 0; i < n; i++) ed25519_mul_base_body(i, n, k, table, W, nwin, planes.data(), &st);
+    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, k, table, W, nwin, planes.data(), &st);
     size_t T = inv_threads(n);
     if (compressed) {
         FinEdCompressed fin{planes.data(), n, out};
@@ -38,6 +38,15 @@ unsigned long long hs_ed25519_mul_base(const u32* k, size_t n, int W, const u32*
         for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
     }
     return st;
+}
+
+void hs_x25519_base(const u32* k, size_t n, int W, const u32* table, u32* out) {
+    int nwin = (254 + W - 1) / W;
+    std::vector<u32> planes(3 * 8 * n), pf(8 * n);
+    for (size_t i = 0; i < n; i++) x25519_base_body(i, n, k, table, W, nwin, planes.data());
+    size_t T = inv_threads(n);
+    FinEdMontU fin{planes.data(), n, out};
+    for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
 }
 
 unsigned long long hs_ed25519_mul(const u32* k, const u32* pts, size_t n, u32* out) {

@@ -221,6 +221,26 @@ def test_x25519_config2_full_batch(ctx, coracle):
     assert np.array_equal(ctx.x25519(k[:m], pb), ctx.x25519(u[:m], pa))
 
 
+def test_x25519_base_public_keys(ctx, golden, coracle):
+    """x25519_base (x25519.rs:49): fixed-base comb + Montgomery map == the ladder on u = 9, byte for byte."""
+    v = golden["x25519"]
+    g = rng(SEEDS["x25519"] + 9)
+    n = 1 << 16
+    ks = rand_bytes(g, n, 32)
+    ks[0] = 0; ks[1] = 0xFF
+    ks[2] = np.frombuffer(H(v["iterated_once"]["k"]), dtype=np.uint8)
+    ks[3] = np.frombuffer(H(v["dh_6_1"]["a"]), dtype=np.uint8)
+    ks[4] = np.frombuffer(H(v["dh_6_1"]["b"]), dtype=np.uint8)
+    got = ctx.x25519_base(ks)
+    assert got[2].tobytes() == H(v["iterated_once"]["r"])
+    nine = np.tile(np.frombuffer((9).to_bytes(32, "little"), dtype=np.uint8), (n, 1))
+    assert np.array_equal(got, ctx.x25519(ks, nine))                       # the ladder kernel, 100 %
+    assert np.array_equal(got[:4096], coracle.x25519(ks[:4096], nine[:4096], threads(coracle)))
+    # RFC 7748 6.1: shared secret from the two public keys
+    shared = ctx.x25519(ks[3:5], got[[4, 3]])
+    assert shared[0].tobytes() == shared[1].tobytes() == H(v["dh_6_1"]["shared"])
+
+
 def test_x448(ctx, golden, coracle):
     v = golden["x448"]
     ks = [H(e["k"]) for e in v["rfc7748_5_2"]]

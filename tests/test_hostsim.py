@@ -108,6 +108,26 @@ def test_ed25519_mul_base_and_table(hs, golden, coracle):
     assert st == (3 << 8) | 1
 
 
+def test_x25519_base_via_comb(hs, golden, coracle):
+    """x25519_base(k) = x25519(k, 9) computed as the Montgomery u of clamp(k) * B on edwards25519."""
+    _, k = hs
+    g = rng(77)
+    n = 40
+    ks = rand_bytes(g, n, 32)
+    ks[0] = 0; ks[1] = 0xFF
+    ks[2] = np.frombuffer(bytes.fromhex(golden["x25519"]["iterated_once"]["k"]), dtype=np.uint8)
+    ks[3] = np.frombuffer(bytes.fromhex(golden["x25519"]["dh_6_1"]["a"]), dtype=np.uint8)
+    nine = np.tile(np.frombuffer((9).to_bytes(32, "little"), dtype=np.uint8), (n, 1))
+    exp = coracle.x25519(ks, nine)
+    assert exp[2].tobytes().hex() == golden["x25519"]["iterated_once"]["r"]
+    for W in (4, 7):
+        table = np.zeros((k.hs_ed25519_table_entries(W), 24), dtype=np.uint32)
+        k.hs_ed25519_build_table(W, p(table))
+        out = np.zeros((n, 32), dtype=np.uint8)
+        k.hs_x25519_base(p(ks), ctypes.c_size_t(n), W, p(table), p(out))
+        assert np.array_equal(out, exp)
+
+
 def test_ed25519_mul_x25519_x448(hs, coracle):
     _, k = hs
     g = rng(3)
