@@ -40,6 +40,7 @@ SIGNATURES = {
     "ecb_ed25519_mul_base_compressed": (_int, [_vp, _vp, _sz, _vp, _szp]),
     "ecb_ed25519_mul": (_int, [_vp, _vp, _vp, _sz, _vp, _szp]),
     "ecb_ed25519_verify_prehashed": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ecb_ed25519_verify": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ecb_x25519": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "ecb_x25519_base": (_int, [_vp, _vp, _sz, _vp]),
     "ecb_x25519_base_dev": (_int, [_vp, _int, _vp, _sz, _vp, _vp]),

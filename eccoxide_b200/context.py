@@ -126,6 +126,21 @@ class Context:
         self._check(self._lib.ecb_ed25519_verify_prehashed(self._ctx, _p(a), _p(r), _p(s), _p(k), n, _p(ok)))
         return ok.astype(bool)
 
+    def ed25519_verify(self, a_enc, msgs, sigs, out=None):
+        """ed25519 PublicKey::verify on raw messages: `msgs` is a sequence of bytes objects (ragged);
+        the challenge hash SHA-512(R || A || M) mod l runs on the device."""
+        a = _rows(a_enc, 32, "a_enc")
+        s = _rows(sigs, 64, "sigs")
+        n = a.shape[0]
+        if s.shape[0] != n or len(msgs) != n:
+            raise ValueError("count mismatch")
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(bytes(m) for m in msgs) + b"\0", dtype=np.uint8)
+        ok = _out(out, (n,))
+        self._check(self._lib.ecb_ed25519_verify(self._ctx, _p(a), _p(blob), _p(off), _p(s), n, _p(ok)))
+        return ok.astype(bool)
+
     # -- X25519 / X448 ------------------------------------------------------------------------
     def x25519(self, k, u, out=None):
         k = _rows(k, 32, "k")

@@ -8,6 +8,8 @@ int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32*
 int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_out, cudaStream_t s);
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
                        unsigned char* ok, cudaStream_t s);
+int dev_ed25519_verify_msgs(ecb_ctx* ctx, DevCtx& d, const unsigned char* a, const unsigned char* sig, const unsigned char* d_msgs,
+                            const unsigned long long* d_off, size_t n, unsigned char* ok, cudaStream_t s);
 int dev_x25519_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, cudaStream_t s);
 int dev_x25519(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_u, size_t n, u32* d_out, cudaStream_t s);
 int dev_x448(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_u, size_t n, u32* d_out, cudaStream_t s);

@@ -344,6 +344,72 @@ int ecb_x25519(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8
                            return dev_x25519(ctx, d, (const u32*)in[0], (const u32*)in[1], cn, (u32*)o[0], s);
                        });
 }
+// Ed25519 verification on raw messages (ragged input): same device sharding and slot rotation as
+// run_sharded, with the message bytes of a chunk copied as one contiguous range.
+int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* sig,
+                       size_t n, uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!a_enc || !msg_off || !sig || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    if (n == 0) return ECB_OK;
+    for (size_t i = 0; i < n; i++)
+        if (msg_off[i + 1] < msg_off[i]) return set_err(ctx, ECB_ERR_INVALID_ARG, "message offsets must be non-decreasing");
+    if (msg_off[n] > msg_off[0] && !msgs) return set_err(ctx, ECB_ERR_INVALID_ARG, "null message buffer");
+    int nd = (int)ctx->devs.size();
+    std::vector<int> rc(nd, ECB_OK);
+    auto worker = [&](int di) {
+        DevCtx& d = *ctx->devs[di];
+        size_t lo = n * (size_t)di / nd, hi = n * (size_t)(di + 1) / nd;
+        if (lo == hi) return;
+        std::lock_guard<std::mutex> g(d.mu);
+        auto body = [&]() -> int {
+            CU(cudaSetDevice(d.dev));
+            size_t ci = 0;
+            for (size_t c0 = lo; c0 < hi; c0 += ctx->opt_chunk, ci++) {
+                size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
+                Slot& sl = d.slots[ci % ECB_NSLOT];
+                if (sl.busy) {
+                    sl.busy = false;
+                    CU(cudaStreamSynchronize(sl.stream));
+                }
+                d.cur = &sl;
+                size_t mbytes = (size_t)(msg_off[c0 + cn] - msg_off[c0]);
+                TRY(ensure(ctx, sl.in[0], cn * 32));
+                TRY(ensure(ctx, sl.in[1], cn * 64));
+                TRY(ensure(ctx, sl.in[2], (cn + 1) * sizeof(uint64_t)));
+                TRY(ensure(ctx, sl.in[3], mbytes + 16));
+                TRY(ensure(ctx, sl.out[0], cn));
+                CU(cudaMemcpyAsync(sl.in[0].p, a_enc + c0 * 32, cn * 32, cudaMemcpyHostToDevice, sl.stream));
+                CU(cudaMemcpyAsync(sl.in[1].p, sig + c0 * 64, cn * 64, cudaMemcpyHostToDevice, sl.stream));
+                CU(cudaMemcpyAsync(sl.in[2].p, msg_off + c0, (cn + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, sl.stream));
+                if (mbytes) CU(cudaMemcpyAsync(sl.in[3].p, msgs + msg_off[c0], mbytes, cudaMemcpyHostToDevice, sl.stream));
+                // the offsets stay absolute: rebase the message pointer instead
+                const unsigned char* d_msgs = (const unsigned char*)sl.in[3].p - msg_off[c0];
+                TRY(dev_ed25519_verify_msgs(ctx, d, (const unsigned char*)sl.in[0].p, (const unsigned char*)sl.in[1].p, d_msgs,
+                                            (const unsigned long long*)sl.in[2].p, cn, (unsigned char*)sl.out[0].p, sl.stream));
+                CU(cudaMemcpyAsync(ok + c0, sl.out[0].p, cn, cudaMemcpyDeviceToHost, sl.stream));
+                sl.busy = true;
+            }
+            for (Slot& sl : d.slots) {
+                if (!sl.busy) continue;
+                sl.busy = false;
+                CU(cudaStreamSynchronize(sl.stream));
+            }
+            d.cur = &d.slots[0];
+            return ECB_OK;
+        };
+        rc[di] = body();
+    };
+    if (nd == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nd; i++) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < nd; i++)
+        if (rc[i] != ECB_OK) return rc[i];
+    return ECB_OK;
+}
 int ecb_x25519_base(ecb_ctx* ctx, const uint8_t* k, size_t n, uint8_t* out) {
     if (!ctx) return ECB_ERR_CUDA;
     if (n && (!k || !out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");

@@ -2,6 +2,7 @@
 // verification (per-thread bodies; launchers in eccbatch.cu, host simulation in tests/hostsim/).
 #pragma once
 #include "kernels.cuh"
+#include "sha512.cuh"
 
 namespace ecb {
 
@@ -436,6 +437,44 @@ ECB_DEV u32 ed25519_decode(fe25519& x, fe25519& y, const u32* enc) {
     F::neg(t, r);
     F::select(x, flip, t, r);
     return ok;
+}
+
+// =======================================================================================
+// k = reduce_wide_le(SHA-512(R || A || M))  (src/protocol/ed25519.rs:21 reduce_wide_le, :139) and the
+// split of the 64-byte signature into R and S: the prologue of verification on raw messages.
+//   sig : n x 64 bytes R || S ; a_enc : n x 32 ; msgs + off : concatenated messages, message i is
+//   bytes [off[i], off[i+1]) ; outputs r_out, s_out, k_out : n x 32 bytes each
+// The 512-bit digest d = d_lo + 2^256 d_hi (little-endian) is reduced with three Montgomery products
+// in GF(l): d_hi 2^256 = mont(d_hi, R^2), d_lo = mont(mont(d_lo, R^2), 1) — CIOS accepts any 256-bit
+// first operand.
+// =======================================================================================
+ECB_DEV void ed25519_hash_k_body(size_t idx, const unsigned char* a_enc, const unsigned char* sig, const unsigned char* msgs,
+                                 const unsigned long long* off, u32* r_out, u32* s_out, u32* k_out) {
+    typedef Mont<ED_FN> FL;
+    const unsigned char* R = sig + idx * 64;
+    const unsigned char* A = a_enc + idx * 32;
+    const unsigned char* M = msgs + off[idx];
+    size_t mlen = (size_t)(off[idx + 1] - off[idx]);
+    unsigned char dg[64];
+    sha512_bytes(dg, 64 + mlen, [&](size_t pos) -> unsigned char { return pos < 32 ? R[pos] : (pos < 64 ? A[pos - 32] : M[pos - 64]); });
+    FL::el lo, hi, r2, one, t;
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        lo.v[i] = (u32)dg[4 * i] | ((u32)dg[4 * i + 1] << 8) | ((u32)dg[4 * i + 2] << 16) | ((u32)dg[4 * i + 3] << 24);
+        hi.v[i] = (u32)dg[32 + 4 * i] | ((u32)dg[32 + 4 * i + 1] << 8) | ((u32)dg[32 + 4 * i + 2] << 16) | ((u32)dg[32 + 4 * i + 3] << 24);
+        r2.v[i] = ED_FN::r2(i);
+        one.v[i] = i == 0 ? 1u : 0u;
+    }
+    FL::mul(hi, hi, r2);       // d_hi * 2^256 mod l
+    FL::mul(t, lo, r2);        // d_lo * 2^256 mod l
+    FL::mul(lo, t, one);       // d_lo mod l
+    FL::add(t, lo, hi);
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        k_out[idx * 8 + i] = t.v[i];
+        r_out[idx * 8 + i] = (u32)R[4 * i] | ((u32)R[4 * i + 1] << 8) | ((u32)R[4 * i + 2] << 16) | ((u32)R[4 * i + 3] << 24);
+        s_out[idx * 8 + i] = (u32)R[32 + 4 * i] | ((u32)R[32 + 4 * i + 1] << 8) | ((u32)R[32 + 4 * i + 2] << 16) | ((u32)R[32 + 4 * i + 3] << 24);
+    }
 }
 
 ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,

@@ -1,0 +1,82 @@
+// sha512.cuh — SHA-512 (FIPS 180-4) for the Ed25519 challenge k = SHA-512(R || A || M) mod l.
+//
+// Replaces, for the batched verification path, the reference's use of cryptoxide's SHA-512
+// (src/protocol/ed25519.rs:8, :11-23 hash + reduce_wide_le, :139 in verify).  One thread hashes one
+// message: the state is eight 64-bit words, the schedule a rolling window of 16; message bytes are
+// fetched by a callback so the caller can concatenate R, A and a ragged message without copying.
+#pragma once
+#include "params_gen.cuh"
+
+namespace ecb {
+
+typedef unsigned long long w64;  // (limb.cuh's w64 is uint64_t: unsigned long on LP64)
+
+ECB_DEV w64 rotr64(w64 x, int n) { return (x >> n) | (x << (64 - n)); }
+
+struct Sha512 {
+    w64 h[8];
+    ECB_DEV void init() {
+        ECB_UNROLL
+        for (int i = 0; i < 8; i++) h[i] = SHA512_H0[i];
+    }
+    // one 128-byte block given as 16 big-endian words
+    ECB_DEV void compress(w64* w) {
+        w64 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        ECB_NOUNROLL
+        for (int t = 0; t < 80; t++) {
+            w64 wt;
+            if (t < 16) {
+                wt = w[t];
+            } else {
+                w64 w15 = w[(t - 15) & 15], w2 = w[(t - 2) & 15];
+                w64 s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
+                w64 s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
+                wt = w[t & 15] + s0 + w[(t - 7) & 15] + s1;
+                w[t & 15] = wt;
+            }
+            w64 S1 = rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41);
+            w64 ch = (e & f) ^ (~e & g);
+            w64 t1 = hh + S1 + ch + SHA512_K[t] + wt;
+            w64 S0 = rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39);
+            w64 mj = (a & b) ^ (a & c) ^ (b & c);
+            w64 t2 = S0 + mj;
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+};
+
+// digest[0..64) = SHA-512 of the `len` bytes byte_at(0) .. byte_at(len-1)
+template <class BYTE_AT>
+ECB_DEV void sha512_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at) {
+    Sha512 st;
+    st.init();
+    w64 w[16];
+    size_t nblocks = (len + 17 + 127) / 128;  // 0x80 marker + 16-byte length field
+    ECB_NOUNROLL
+    for (size_t blk = 0; blk < nblocks; blk++) {
+        ECB_NOUNROLL
+        for (int i = 0; i < 16; i++) {
+            w64 v = 0;
+            ECB_NOUNROLL
+            for (int j = 0; j < 8; j++) {
+                size_t pos = blk * 128 + (size_t)i * 8 + j;
+                unsigned b = pos < len ? (unsigned)byte_at(pos) : (pos == len ? 0x80u : 0u);
+                v = (v << 8) | b;
+            }
+            w[i] = v;
+        }
+        if (blk == nblocks - 1) {
+            w[14] = (w64)(len >> 61);        // bit length, 128-bit big-endian
+            w[15] = (w64)len << 3;
+        }
+        st.compress(w);
+    }
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        ECB_UNROLL
+        for (int j = 0; j < 8; j++) digest[8 * i + j] = (unsigned char)(st.h[i] >> (56 - 8 * j));
+    }
+}
+
+}  // namespace ecb

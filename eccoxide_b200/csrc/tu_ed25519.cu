@@ -125,6 +125,26 @@ int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, siz
     return rc;
 }
 
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_hash_k(size_t n, const unsigned char* a_enc, const unsigned char* sig,
+                                                             const unsigned char* msgs, const unsigned long long* off,
+                                                             u32* r_out, u32* s_out, u32* k_out) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) ed25519_hash_k_body(idx, a_enc, sig, msgs, off, r_out, s_out, k_out);
+}
+// verification on raw messages: k = SHA-512(R || A || M) mod l on the device, then the prehashed path.
+// d_msgs is addressed as d_msgs[off[i] .. off[i+1]) (the caller may pass a pointer already rebased).
+int dev_ed25519_verify_msgs(ecb_ctx* ctx, DevCtx& d, const unsigned char* a, const unsigned char* sig, const unsigned char* d_msgs,
+                            const unsigned long long* d_off, size_t n, unsigned char* ok, cudaStream_t s) {
+    TRY(ensure(ctx, d.cur->aux, n * 3 * 32));
+    u32* r = (u32*)d.cur->aux.p;
+    u32* sl = r + n * 8;
+    u32* kl = sl + n * 8;
+    k_ed25519_hash_k<<<grid_for(n), ECB_TPB, 0, s>>>(n, a, sig, d_msgs, d_off, r, sl, kl);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return dev_ed25519_verify(ctx, d, (const u32*)a, r, sl, kl, n, ok, s);
+}
+
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
                        unsigned char* ok, cudaStream_t s) {
     if (!d.ed_table || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));

@@ -81,6 +81,13 @@ int ecb_ed25519_mul(ecb_ctx* ctx, const uint8_t* k_le, const uint8_t* xy_le_in, 
 int ecb_ed25519_verify_prehashed(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* r_enc, const uint8_t* s_le,
                                  const uint8_t* k_le, size_t n, uint8_t* ok);
 
+/* ed25519::PublicKey::verify(msg, sig)   (src/protocol/ed25519.rs:119-147, :200) on raw messages:
+ * k = reduce_wide_le(SHA-512(R || A || M)) (:21, :139) is computed on the device.
+ * a_enc: n x 32 B public keys; sig: n x 64 B R || S; message i = msgs[msg_off[i] .. msg_off[i+1])
+ * (msg_off: n + 1 non-decreasing byte offsets); ok: n x 1 B. */
+int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, const uint64_t* msg_off, const uint8_t* sig,
+                       size_t n, uint8_t* ok);
+
 /* ---- X25519 / X448 --------------------------------------------------------------------- */
 
 /* protocol::x25519::x25519(scalar, u)   (src/protocol/x25519.rs:36): clamps inside, masks bit 255

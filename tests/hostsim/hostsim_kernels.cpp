@@ -115,6 +115,13 @@ void hs_x448(const u32* k, const u32* u, size_t n, u32* out) {
     FinX448 fin{planes.data(), n, out};
     for (size_t t = 0; t < T; t++) batch_inv_body<F448>(t, T, n, planes.data(), pf.data(), fin);
 }
+void hs_sha512(const unsigned char* msg, size_t len, unsigned char* digest) {
+    sha512_bytes(digest, len, [&](size_t pos) -> unsigned char { return msg[pos]; });
+}
+void hs_ed25519_hash_k(const unsigned char* a, const unsigned char* sig, const unsigned char* msgs, const unsigned long long* off,
+                       size_t n, u32* r, u32* s, u32* k) {
+    for (size_t i = 0; i < n; i++) ed25519_hash_k_body(i, a, sig, msgs, off, r, s, k);
+}
 void hs_ed25519_verify(const u32* a, const u32* r, const u32* s, const u32* k, size_t n, int W, const u32* table,
                        unsigned char* ok) {
     int nwin = (254 + W - 1) / W;

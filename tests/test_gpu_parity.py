@@ -472,6 +472,40 @@ def test_ed25519_verify(ctx, golden, coracle):
     assert coracle.ed25519_verify_prehashed(a, r, s, k).tolist() == [True, False, False]
 
 
+def test_ed25519_verify_raw_messages(ctx, golden, coracle):
+    """PublicKey::verify(msg, sig) with the challenge hash on the device (SHA-512 + reduction mod l)."""
+    pubs, msgs, sigs, exp = [], [], [], []
+    for v in golden["ed25519_rfc8032"]:
+        pub, msg, sig = H(v["public"]), H(v["message"]), H(v["signature"])
+        pubs += [pub, pub, pub]; sigs += [sig, sig, bytes([sig[0] ^ 1]) + sig[1:]]; msgs += [msg, msg + b"!", msg]; exp += [True, False, False]
+    assert ctx.ed25519_verify(rows(pubs), msgs, rows(sigs)).tolist() == exp
+    g = rng(8032)
+    n = 3000
+    lens = [0, 1, 47, 48, 63, 64, 65, 111, 112, 175, 176, 177, 239, 240, 1000] + [int(x) for x in g.integers(0, 300, size=n - 15)]
+    pubs, msgs, sigs = [], [], []
+    seeds = [g.bytes(32) for _ in range(16)]
+    keys = [(s, R.ed25519_public_from_seed(s)) for s in seeds]
+    for i, ln in enumerate(lens):
+        seed, pub = keys[i % 16]
+        msg = g.bytes(ln) if ln else b""
+        sig = bytearray(R.ed25519_sign(seed, msg)) if i < 400 else None
+        if sig is None:  # signing in Python is slow: reuse a signature on a different message (invalid) for the bulk
+            sig = bytearray(sigs[i % 400])
+        if i % 7 == 3:
+            sig[5] ^= 0x10
+        pubs.append(pub); msgs.append(msg); sigs.append(bytes(sig))
+    got = ctx.ed25519_verify(rows(pubs), msgs, rows(sigs))
+    ks = rows([R.ed25519_hash_k(s[:32], p_, m) for p_, m, s in zip(pubs, msgs, sigs)])
+    sg = rows(sigs)
+    want = coracle.ed25519_verify_prehashed(rows(pubs), sg[:, :32].copy(), sg[:, 32:].copy(), ks, threads(coracle))
+    assert np.array_equal(got, want)
+    assert got[:400].sum() > 300 and not got[400:].any()
+    for i in (0, 1, 2, 3, 14, 399):
+        assert bool(got[i]) == R.ed25519_verify(pubs[i], msgs[i], sigs[i])
+    # same answers as the prehashed entry point
+    assert np.array_equal(got, ctx.ed25519_verify_prehashed(rows(pubs), sg[:, :32].copy(), sg[:, 32:].copy(), ks))
+
+
 # ---- device-resident entry points ---------------------------------------------------------------------
 def test_device_resident_entry_points_match_host_entry_points(ctx):
     torch = pytest.importorskip("torch")

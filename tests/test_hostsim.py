@@ -248,3 +248,30 @@ def test_fe25519_and_fe448_structured_operands(hs):
             assert val(r14) % R.P448 == exp % R.P448, (op, hex(a), hex(b))
         k.hs_fe448(5, p(words(a, 14)), p(words(b, 14)), p(r14))
         assert val(r14) == a % R.P448
+
+
+def test_sha512_and_ed25519_challenge(hs):
+    """Device SHA-512 and k = SHA-512(R || A || M) mod l against hashlib / the big-int oracle."""
+    import hashlib
+
+    _, k = hs
+    g = rng(512)
+    dg = np.zeros(64, dtype=np.uint8)
+    for ln in list(range(0, 20)) + [55, 56, 63, 64, 110, 111, 112, 113, 127, 128, 129, 239, 240, 241, 255, 256, 300, 1000]:
+        m = np.frombuffer(g.bytes(ln) if ln else b"", dtype=np.uint8).copy() if ln else np.zeros(0, dtype=np.uint8)
+        buf = np.concatenate([m, np.zeros(1, dtype=np.uint8)])  # non-empty buffer for ctypes
+        k.hs_sha512(p(buf), ctypes.c_size_t(ln), p(dg))
+        assert dg.tobytes() == hashlib.sha512(m.tobytes()).digest(), ln
+    n = 40
+    lens = [0, 1, 47, 48, 63, 64, 65, 111, 112, 175, 176, 177, 300] + [int(x) for x in g.integers(0, 400, size=n - 13)]
+    msgs = [g.bytes(l) if l else b"" for l in lens]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    blob = np.frombuffer(b"".join(msgs) + b"\0", dtype=np.uint8).copy()
+    a = rand_bytes(g, n, 32)
+    sig = rand_bytes(g, n, 64)
+    r = np.zeros((n, 32), dtype=np.uint8); s = np.zeros((n, 32), dtype=np.uint8); kk = np.zeros((n, 32), dtype=np.uint8)
+    k.hs_ed25519_hash_k(p(a), p(sig), p(blob), p(off), ctypes.c_size_t(n), p(r), p(s), p(kk))
+    for i in range(n):
+        assert kk[i].tobytes() == R.ed25519_hash_k(sig[i, :32].tobytes(), a[i].tobytes(), msgs[i]), i
+    assert np.array_equal(r, sig[:, :32]) and np.array_equal(s, sig[:, 32:])
