@@ -32,6 +32,9 @@ extern "C" {
     pub fn ecb_ed25519_mul_base_compressed(ctx: *mut ecb_ctx, k_le: *const u8, n: usize, enc: *mut u8, bad_index: *mut usize) -> c_int;
     pub fn ecb_ed25519_mul(ctx: *mut ecb_ctx, k_le: *const u8, xy_in: *const u8, n: usize, xy_out: *mut u8, bad_index: *mut usize) -> c_int;
     pub fn ecb_ed25519_verify_prehashed(ctx: *mut ecb_ctx, a_enc: *const u8, r_enc: *const u8, s_le: *const u8, k_le: *const u8, n: usize, ok: *mut u8) -> c_int;
+    pub fn ecb_ed25519_verify(ctx: *mut ecb_ctx, a_enc: *const u8, msgs: *const u8, msg_off: *const u64, sig: *const u8, n: usize, ok: *mut u8) -> c_int;
+    pub fn ecb_ecdsa_verify(ctx: *mut ecb_ctx, curve_id: c_int, hash: c_int, q_xy_be: *const u8, msgs: *const u8, msg_off: *const u64,
+                            rs_be: *const u8, n: usize, ok: *mut u8, bad_index: *mut usize) -> c_int;
     pub fn ecb_x25519(ctx: *mut ecb_ctx, k: *const u8, u: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn ecb_x25519_base(ctx: *mut ecb_ctx, k: *const u8, n: usize, out: *mut u8) -> c_int;
     pub fn ecb_x448(ctx: *mut ecb_ctx, k: *const u8, u: *const u8, n: usize, out: *mut u8) -> c_int;

@@ -48,6 +48,7 @@ SIGNATURES = {
     "ecb_wei_mul": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _vp, _szp]),
     "ecb_wei_mul_base": (_int, [_vp, _int, _vp, _sz, _vp, _vp, _szp]),
     "ecb_ecdsa_verify_hashed": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _szp]),
+    "ecb_ecdsa_verify": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp, _szp]),
     "ecb_ed25519_mul_base_dev": (_int, [_vp, _int, _vp, _sz, _vp, _vp]),
     "ecb_ed25519_mul_dev": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_x25519_dev": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),

@@ -212,6 +212,23 @@ class Context:
         self._check(self._lib.ecb_ecdsa_verify_hashed(self._ctx, cid, _p(q), _p(z), _p(rs), n, _p(ok), ctypes.byref(bad)), bad)
         return ok.astype(bool)
 
+    def ecdsa_verify(self, curve, hash_bits, q_xy_be, msgs, rs_be, out=None):
+        """ecdsa::verify on raw messages (ragged `msgs`); hash_bits in (256, 384, 512) selects SHA-2."""
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+        fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]
+        q = _rows(q_xy_be, 2 * fb, "q_xy_be")
+        rs = _rows(rs_be, 2 * sb, "rs_be")
+        n = q.shape[0]
+        if rs.shape[0] != n or len(msgs) != n:
+            raise ValueError("count mismatch")
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(bytes(m) for m in msgs) + b"\0", dtype=np.uint8)
+        ok = _out(out, (n,))
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_ecdsa_verify(self._ctx, cid, int(hash_bits), _p(q), _p(blob), _p(off), _p(rs), n, _p(ok), ctypes.byref(bad)), bad)
+        return ok.astype(bool)
+
     # -- device-resident variants (raw device pointers, enqueue on `stream`, no sync) -----------
     def dev_call(self, name, *args):
         """Call a *_dev entry point: args are ints (device pointers, sizes, ids) in ABI order after ctx."""

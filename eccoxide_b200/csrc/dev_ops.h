@@ -30,4 +30,8 @@ int dev_ecdsa_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const u32* d_z, cons
                    cudaStream_t s);
 int dev_ecdsa_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const u32* d_z, const u32* d_rs, size_t n, unsigned char* d_ok,
                    cudaStream_t s);
+int dev_ecdsa_msgs_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const unsigned char* d_msgs, const unsigned long long* d_off, int hash,
+                        const u32* d_rs, size_t n, unsigned char* d_ok, cudaStream_t s);
+int dev_ecdsa_msgs_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const unsigned char* d_msgs, const unsigned long long* d_off, int hash,
+                        const u32* d_rs, size_t n, unsigned char* d_ok, cudaStream_t s);
 int dev_imad_probe(ecb_ctx* ctx, DevCtx& d, int variant, int iters, double* macs_per_s, double* ms_out);

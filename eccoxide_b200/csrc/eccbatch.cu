@@ -410,6 +410,96 @@ int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, 
         if (rc[i] != ECB_OK) return rc[i];
     return ECB_OK;
 }
+// ECDSA verification on raw messages (ragged input); layout of a chunk in the slot buffers:
+// in[0] = Q, in[1] = r || s, in[2] = offsets, aux2 (in[3]) = z, message bytes in `scratch2` (out[1]).
+int ecb_ecdsa_verify(ecb_ctx* ctx, int curve, int hash, const uint8_t* q_xy, const uint8_t* msgs, const uint64_t* msg_off,
+                     const uint8_t* rs_be, size_t n, uint8_t* ok, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (bad_index) *bad_index = (size_t)-1;
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb) || curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+    if (hash != 256 && hash != 384 && hash != 512) return set_err(ctx, ECB_ERR_INVALID_ARG, "hash must be 256, 384 or 512 (SHA-2)");
+    if (n && (!q_xy || !msg_off || !rs_be || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    if (n == 0) return ECB_OK;
+    for (size_t i = 0; i < n; i++)
+        if (msg_off[i + 1] < msg_off[i]) return set_err(ctx, ECB_ERR_INVALID_ARG, "message offsets must be non-decreasing");
+    if (msg_off[n] > msg_off[0] && !msgs) return set_err(ctx, ECB_ERR_INVALID_ARG, "null message buffer");
+    int nd = (int)ctx->devs.size();
+    std::vector<int> rc(nd, ECB_OK);
+    std::vector<unsigned long long> bad(nd, ~0ull);
+    auto worker = [&](int di) {
+        DevCtx& d = *ctx->devs[di];
+        size_t lo = n * (size_t)di / nd, hi = n * (size_t)(di + 1) / nd;
+        if (lo == hi) return;
+        std::lock_guard<std::mutex> g(d.mu);
+        auto retire = [&](Slot& sl) -> int {
+            if (!sl.busy) return ECB_OK;
+            sl.busy = false;
+            CU(cudaStreamSynchronize(sl.stream));
+            if (*sl.h_status != ~0ull) {
+                unsigned long long v = *sl.h_status, w = (((v >> 8) + sl.c0) << 8) | (v & 0xff);
+                if (w < bad[di]) bad[di] = w;
+            }
+            return ECB_OK;
+        };
+        auto body = [&]() -> int {
+            CU(cudaSetDevice(d.dev));
+            size_t ci = 0;
+            for (size_t c0 = lo; c0 < hi && bad[di] == ~0ull; c0 += ctx->opt_chunk, ci++) {
+                size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
+                Slot& sl = d.slots[ci % ECB_NSLOT];
+                TRY(retire(sl));
+                d.cur = &sl;
+                size_t mbytes = (size_t)(msg_off[c0 + cn] - msg_off[c0]);
+                TRY(ensure(ctx, sl.in[0], cn * 2 * fb));
+                TRY(ensure(ctx, sl.in[1], cn * 2 * sb));
+                TRY(ensure(ctx, sl.in[2], (cn + 1) * sizeof(uint64_t)));
+                TRY(ensure(ctx, sl.out[1], mbytes + 16));
+                TRY(ensure(ctx, sl.out[0], cn));
+                CU(cudaMemcpyAsync(sl.in[0].p, q_xy + c0 * 2 * fb, cn * 2 * fb, cudaMemcpyHostToDevice, sl.stream));
+                CU(cudaMemcpyAsync(sl.in[1].p, rs_be + c0 * 2 * sb, cn * 2 * sb, cudaMemcpyHostToDevice, sl.stream));
+                CU(cudaMemcpyAsync(sl.in[2].p, msg_off + c0, (cn + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, sl.stream));
+                if (mbytes) CU(cudaMemcpyAsync(sl.out[1].p, msgs + msg_off[c0], mbytes, cudaMemcpyHostToDevice, sl.stream));
+                const unsigned char* d_msgs = (const unsigned char*)sl.out[1].p - msg_off[c0];
+                if (curve == ECB_CURVE_P256R1)
+                    TRY(dev_ecdsa_msgs_p256(ctx, d, (const u32*)sl.in[0].p, d_msgs, (const unsigned long long*)sl.in[2].p, hash,
+                                            (const u32*)sl.in[1].p, cn, (unsigned char*)sl.out[0].p, sl.stream));
+                else
+                    TRY(dev_ecdsa_msgs_p384(ctx, d, (const u32*)sl.in[0].p, d_msgs, (const unsigned long long*)sl.in[2].p, hash,
+                                            (const u32*)sl.in[1].p, cn, (unsigned char*)sl.out[0].p, sl.stream));
+                CU(cudaMemcpyAsync(ok + c0, sl.out[0].p, cn, cudaMemcpyDeviceToHost, sl.stream));
+                CU(cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.stream));
+                sl.busy = true;
+                sl.c0 = c0;
+            }
+            int r2 = ECB_OK;
+            for (Slot& sl : d.slots) {
+                int r3 = retire(sl);
+                if (r2 == ECB_OK) r2 = r3;
+            }
+            d.cur = &d.slots[0];
+            return r2;
+        };
+        rc[di] = body();
+    };
+    if (nd == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nd; i++) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < nd; i++)
+        if (rc[i] != ECB_OK) return rc[i];
+    unsigned long long first = ~0ull;
+    for (int i = 0; i < nd; i++)
+        if (bad[i] < first) first = bad[i];
+    if (first != ~0ull) {
+        if (bad_index) *bad_index = (size_t)(first >> 8);
+        return set_err(ctx, ECB_ERR_POINT_NOT_ON_CURVE, "public key not on curve");
+    }
+    return ECB_OK;
+}
 int ecb_x25519_base(ecb_ctx* ctx, const uint8_t* k, size_t n, uint8_t* out) {
     if (!ctx) return ECB_ERR_CUDA;
     if (n && (!k || !out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");

@@ -248,6 +248,26 @@ struct FinX448 {
 //          doublings, complete formulas), projective result to the point planes
 //   fin  : x = X/Z by batch inversion in GF(p); accept iff Z != 0 and x mod n == r
 // =======================================================================================
+// z = digest_to_scalar(H(message)) before the reduction mod n (src/protocol/ecdsa.rs:288 hash_to_scalar,
+// :340 digest_to_scalar = SEC1 bits2int: the leftmost min(8 len, qlen) bits; for p256r1 / p384r1 the
+// order fills whole bytes, so that is "left-pad a short digest, keep the first SB bytes of a long one").
+// hash: 256 / 384 / 512.  z_out: n x SB bytes big-endian (reduced mod n later, in ecdsa_main_body).
+ECB_DEV void ecdsa_hash_z_body(size_t idx, const unsigned char* msgs, const unsigned long long* off, int hash, int SB,
+                               unsigned char* z_out) {
+    const unsigned char* M = msgs + off[idx];
+    size_t mlen = (size_t)(off[idx + 1] - off[idx]);
+    unsigned char dg[64];
+    int dlen = hash / 8;
+    auto at = [&](size_t pos) -> unsigned char { return M[pos]; };
+    if (hash == 256) sha256_bytes(dg, mlen, at);
+    else sha512_bytes(dg, mlen, at, hash == 384);
+    unsigned char* z = z_out + idx * (size_t)SB;
+    for (int i = 0; i < SB; i++) {
+        int j = dlen <= SB ? i - (SB - dlen) : i;   // left-pad, or keep the leading SB bytes
+        z[i] = (j >= 0 && j < dlen) ? dg[j] : 0;
+    }
+}
+
 template <class C>
 ECB_DEV void ecdsa_prep_body(size_t idx, size_t n, const u32* z_be, const u32* rs_be, u32* sp, unsigned char* valid) {
     typedef typename C::FN FN;

@@ -15,9 +15,9 @@ ECB_DEV w64 rotr64(w64 x, int n) { return (x >> n) | (x << (64 - n)); }
 
 struct Sha512 {
     w64 h[8];
-    ECB_DEV void init() {
+    ECB_DEV void init(bool sha384 = false) {
         ECB_UNROLL
-        for (int i = 0; i < 8; i++) h[i] = SHA512_H0[i];
+        for (int i = 0; i < 8; i++) h[i] = sha384 ? SHA384_H0[i] : SHA512_H0[i];
     }
     // one 128-byte block given as 16 big-endian words
     ECB_DEV void compress(w64* w) {
@@ -46,11 +46,12 @@ struct Sha512 {
     }
 };
 
-// digest[0..64) = SHA-512 of the `len` bytes byte_at(0) .. byte_at(len-1)
+// digest[0..64) = SHA-512 of the `len` bytes byte_at(0) .. byte_at(len-1); with sha384 the SHA-384
+// initial value is used and the caller keeps the first 48 bytes
 template <class BYTE_AT>
-ECB_DEV void sha512_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at) {
+ECB_DEV void sha512_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at, bool sha384 = false) {
     Sha512 st;
-    st.init();
+    st.init(sha384);
     w64 w[16];
     size_t nblocks = (len + 17 + 127) / 128;  // 0x80 marker + 16-byte length field
     ECB_NOUNROLL
@@ -76,6 +77,63 @@ ECB_DEV void sha512_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at) {
     for (int i = 0; i < 8; i++) {
         ECB_UNROLL
         for (int j = 0; j < 8; j++) digest[8 * i + j] = (unsigned char)(st.h[i] >> (56 - 8 * j));
+    }
+}
+
+// ---- SHA-256 (ECDSA over p256r1: src/protocol/ecdsa.rs:288-292 hash_to_scalar) --------------------
+ECB_DEV u32 rotr32(u32 x, int n) { return (x >> n) | (x << (32 - n)); }
+template <class BYTE_AT>
+ECB_DEV void sha256_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at) {
+    u32 h[8], w[16];
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) h[i] = SHA256_H0[i];
+    size_t nblocks = (len + 9 + 63) / 64;
+    ECB_NOUNROLL
+    for (size_t blk = 0; blk < nblocks; blk++) {
+        ECB_NOUNROLL
+        for (int i = 0; i < 16; i++) {
+            u32 v = 0;
+            ECB_NOUNROLL
+            for (int j = 0; j < 4; j++) {
+                size_t pos = blk * 64 + (size_t)i * 4 + j;
+                unsigned b = pos < len ? (unsigned)byte_at(pos) : (pos == len ? 0x80u : 0u);
+                v = (v << 8) | b;
+            }
+            w[i] = v;
+        }
+        if (blk == nblocks - 1) {
+            w[14] = (u32)((unsigned long long)len >> 29);
+            w[15] = (u32)(len << 3);
+        }
+        u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        ECB_NOUNROLL
+        for (int t = 0; t < 64; t++) {
+            u32 wt;
+            if (t < 16) {
+                wt = w[t];
+            } else {
+                u32 w15 = w[(t - 15) & 15], w2 = w[(t - 2) & 15];
+                u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+                u32 s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+                wt = w[t & 15] + s0 + w[(t - 7) & 15] + s1;
+                w[t & 15] = wt;
+            }
+            u32 S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+            u32 ch = (e & f) ^ (~e & g);
+            u32 t1 = hh + S1 + ch + SHA256_K[t] + wt;
+            u32 S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+            u32 mj = (a & b) ^ (a & c) ^ (b & c);
+            u32 t2 = S0 + mj;
+            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
+        }
+        h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
+    }
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        digest[4 * i] = (unsigned char)(h[i] >> 24);
+        digest[4 * i + 1] = (unsigned char)(h[i] >> 16);
+        digest[4 * i + 2] = (unsigned char)(h[i] >> 8);
+        digest[4 * i + 3] = (unsigned char)h[i];
     }
 }
 

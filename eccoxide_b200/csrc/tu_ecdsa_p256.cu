@@ -3,4 +3,5 @@
 #define ECB_TU_FN dev_ecdsa_p256
 #define ECB_TU_CURVE_INDEX 0
 #define ECB_TU_TABLE_FN dev_wei_table_p256
+#define ECB_TU_MSG_FN dev_ecdsa_msgs_p256
 #include "tu_ecdsa.inc"

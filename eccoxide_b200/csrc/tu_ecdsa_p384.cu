@@ -3,4 +3,5 @@
 #define ECB_TU_FN dev_ecdsa_p384
 #define ECB_TU_CURVE_INDEX 1
 #define ECB_TU_TABLE_FN dev_wei_table_p384
+#define ECB_TU_MSG_FN dev_ecdsa_msgs_p384
 #include "tu_ecdsa.inc"

@@ -117,6 +117,12 @@ int ecb_wei_mul_base(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, size_t n, 
 int ecb_ecdsa_verify_hashed(ecb_ctx* ctx, int curve_id, const uint8_t* q_xy_be, const uint8_t* z_be,
                             const uint8_t* rs_be, size_t n, uint8_t* ok, size_t* bad_index);
 
+/* ecdsa::verify::<O>(public, message, signature)   (src/protocol/ecdsa.rs:228; O::hash_to_scalar :288):
+ * z = digest_to_scalar(SHA-2(message)) is computed on the device.  hash = 256, 384 or 512 (the
+ * P256R1_Sha256 / _Sha384 / _Sha512 and P384R1_* marker types); messages as in ecb_ed25519_verify. */
+int ecb_ecdsa_verify(ecb_ctx* ctx, int curve_id, int hash, const uint8_t* q_xy_be, const uint8_t* msgs, const uint64_t* msg_off,
+                     const uint8_t* rs_be, size_t n, uint8_t* ok, size_t* bad_index);
+
 /* ---- device-resident variants (inputs/outputs already in HBM of device `dev_index`) ------ */
 int ecb_ed25519_mul_base_dev(ecb_ctx* ctx, int dev_index, const void* d_k_le, size_t n, void* d_xy_le, void* stream);
 int ecb_ed25519_mul_dev(ecb_ctx* ctx, int dev_index, const void* d_k_le, const void* d_xy_in, size_t n, void* d_xy_out,

@@ -118,6 +118,9 @@ void hs_x448(const u32* k, const u32* u, size_t n, u32* out) {
 void hs_sha512(const unsigned char* msg, size_t len, unsigned char* digest) {
     sha512_bytes(digest, len, [&](size_t pos) -> unsigned char { return msg[pos]; });
 }
+void hs_ecdsa_hash_z(const unsigned char* msgs, const unsigned long long* off, size_t n, int hash, int SB, unsigned char* z) {
+    for (size_t i = 0; i < n; i++) ecdsa_hash_z_body(i, msgs, off, hash, SB, z);
+}
 void hs_ed25519_hash_k(const unsigned char* a, const unsigned char* sig, const unsigned char* msgs, const unsigned long long* off,
                        size_t n, u32* r, u32* s, u32* k) {
     for (size_t i = 0; i < n; i++) ed25519_hash_k_body(i, a, sig, msgs, off, r, s, k);

@@ -506,6 +506,38 @@ def test_ed25519_verify_raw_messages(ctx, golden, coracle):
     assert np.array_equal(got, ctx.ed25519_verify_prehashed(rows(pubs), sg[:, :32].copy(), sg[:, 32:].copy(), ks))
 
 
+@pytest.mark.parametrize("curve", ["p256r1", "p384r1"])
+def test_ecdsa_verify_raw_messages(ctx, golden, coracle, curve):
+    """ecdsa::verify(public, message, sig): SHA-2 + bits2int on the device, all three hash sizes."""
+    c, v = R.WCURVES[curve], golden["ecdsa_rfc6979"][curve]
+    Q = c.enc((int(v["qx"], 16), int(v["qy"], 16)))
+    for kat in v["kats"]:
+        bits = int(kat["alg"][3:])
+        rs = int(kat["r"], 16).to_bytes(c.sbytes, "big") + int(kat["s"], 16).to_bytes(c.sbytes, "big")
+        msg = kat["message"].encode()
+        got = ctx.ecdsa_verify(curve, bits, rows([Q, Q, Q]), [msg, msg + b".", msg], rows([rs, rs, rs[:-1] + bytes([rs[-1] ^ 1])]))
+        assert got.tolist() == [True, False, False], kat
+    g = rng(6979)
+    n = 600
+    d = int.from_bytes(g.bytes(40), "little") % (c.n - 1) + 1
+    q = c.enc(c.mul(d, c.G))
+    lens = [0, 1, 55, 56, 63, 64, 65, 111, 112, 127, 128, 129, 400] + [int(x) for x in g.integers(0, 200, size=n - 13)]
+    msgs = [g.bytes(l) if l else b"" for l in lens]
+    for bits, hname in ((256, "sha256"), (384, "sha384"), (512, "sha512")):
+        zs, rss = [], []
+        for i, m in enumerate(msgs):
+            z = R.ecdsa_digest_to_scalar(c, hashlib.new(hname, m).digest())
+            k = int.from_bytes(g.bytes(60), "little") % (c.n - 1) + 1
+            rs = bytearray(R.ecdsa_sign_hashed(c, d, k, int.from_bytes(z, "big"))) if i < 60 else bytearray(rss[i % 60])
+            if i % 5 == 2:
+                rs[7] ^= 4
+            zs.append(z); rss.append(bytes(rs))
+        got = ctx.ecdsa_verify(curve, bits, rows([q] * n), msgs, rows(rss))
+        want = coracle.ecdsa_verify_hashed(curve, rows([q] * n), rows(zs), rows(rss), threads(coracle))
+        assert np.array_equal(got, want) and got[:60].sum() >= 40 and not got[60:].any()
+        assert np.array_equal(got, ctx.ecdsa_verify_hashed(curve, rows([q] * n), rows(zs), rows(rss)))
+
+
 # ---- device-resident entry points ---------------------------------------------------------------------
 def test_device_resident_entry_points_match_host_entry_points(ctx):
     torch = pytest.importorskip("torch")

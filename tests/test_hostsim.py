@@ -275,3 +275,28 @@ def test_sha512_and_ed25519_challenge(hs):
     for i in range(n):
         assert kk[i].tobytes() == R.ed25519_hash_k(sig[i, :32].tobytes(), a[i].tobytes(), msgs[i]), i
     assert np.array_equal(r, sig[:, :32]) and np.array_equal(s, sig[:, 32:])
+
+
+def test_ecdsa_digest_to_scalar_on_device_code(hs):
+    """SHA-256 / SHA-384 / SHA-512 + bits2int (left-pad or keep the leading bytes) vs hashlib / the oracle."""
+    import hashlib
+
+    _, k = hs
+    g = rng(256)
+    lens = [0, 1, 55, 56, 63, 64, 65, 111, 112, 119, 120, 127, 128, 129, 500] + [int(x) for x in g.integers(0, 300, size=25)]
+    n = len(lens)
+    msgs = [g.bytes(l) if l else b"" for l in lens]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum(lens)
+    blob = np.frombuffer(b"".join(msgs) + b"\0", dtype=np.uint8).copy()
+    for curve, sb in (("p256r1", 32), ("p384r1", 48)):
+        c = R.WCURVES[curve]
+        for hname, hid in (("sha256", 256), ("sha384", 384), ("sha512", 512)):
+            z = np.zeros((n, sb), dtype=np.uint8)
+            k.hs_ecdsa_hash_z(p(blob), p(off), ctypes.c_size_t(n), hid, sb, p(z))
+            for i in range(n):
+                d = hashlib.new(hname, msgs[i]).digest()
+                want = d[:sb] if len(d) >= sb else bytes(sb - len(d)) + d
+                assert z[i].tobytes() == want, (curve, hname, i)
+                # after the reduction mod n this is the reference's digest_to_scalar
+                assert (int.from_bytes(want, "big") % c.n).to_bytes(sb, "big") == R.ecdsa_digest_to_scalar(c, d)
