@@ -15,6 +15,9 @@
  *     (blocking); *_dev entry points take device pointers on device `dev_index` of the context and
  *     enqueue on `stream` (a cudaStream_t) without synchronising
  *   - a batch is sharded by contiguous slice over the devices of the context; no collective
+ *   - threading: host entry points may be called concurrently on one context (calls are serialised
+ *     per device); the *_dev entry points use the context's slot-0 work buffers without locking, so
+ *     issue them from one thread per device and do not mix them with concurrent host calls
  *   - input validation mirrors the reference's Option/CtOption results: a non-canonical scalar
  *     (Scalar::from_bytes -> None, src/curve/fiat/field_macros.rs:645) or an off-curve /
  *     non-canonical point (PointAffine::from_coordinate -> None, src/curve/affine.rs:77;
