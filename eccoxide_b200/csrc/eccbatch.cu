@@ -116,6 +116,11 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
         for (DevCtx* d : ctx->devs) d->inv_per_thread = (size_t)value;
         return ECB_OK;
     }
+    if (!strcmp(key, "inv_fill_per_sm")) {
+        if (value < 32 || value > 2048) return set_err(ctx, ECB_ERR_INVALID_ARG, "inv_fill_per_sm must be in 32..2048");
+        for (DevCtx* d : ctx->devs) d->inv_fill_per_sm = (size_t)value;
+        return ECB_OK;
+    }
     if (!strcmp(key, "chunk")) {
         if (value < 1) return set_err(ctx, ECB_ERR_INVALID_ARG, "chunk must be >= 1");
         ctx->opt_chunk = (size_t)value;

@@ -13,6 +13,7 @@
 // to_bytes emits.  mul = 64 + 8 IMAD.WIDE.U32, sqr = 36 + 8.
 #pragma once
 #include "limb.cuh"
+#include "modinv.cuh"
 
 namespace ecb {
 
@@ -202,12 +203,19 @@ struct F25519 {
         sqr_n(t, t, 50);
         mul(t250, t, z_50_0);
     }
-    // a^(p-2); 0 -> 0 (curve25519.rs:191 invert_or_zero)
-    ECB_DEV static void invert(el& r, const el& a) {
+    // a^(p-2); 0 -> 0 (curve25519.rs:191 invert_or_zero): the reference's Fermat chain
+    ECB_DEV static void invert_fermat(el& r, const el& a) {
         el t, z11;
         pow_2_250_m1(t, z11, a);
         sqr_n(t, t, 5);
         mul(r, t, z11);
+    }
+    // same value by safegcd divsteps (modinv.cuh): what the batch-inversion kernels use; 0 -> 0
+    ECB_DEV static void invert(el& r, const el& a) {
+        el c;
+        freeze(c, a);
+        const u32 p[8] = {0xffffffedu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x7fffffffu};
+        sg_modinv<8, 9, 22>(r.v, c.v, p);
     }
     // a^((p-5)/8) (curve25519.rs:185)
     ECB_DEV static void pow_p58(el& r, const el& a) {

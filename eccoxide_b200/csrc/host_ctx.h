@@ -49,6 +49,7 @@ struct DevCtx {
     cudaStream_t stream = nullptr;            // = slots[0].stream: table builds, probes
     Slot slots[ECB_NSLOT];
     cudaEvent_t ev_fork = nullptr;
+    size_t inv_fill_per_sm = 256;             // lower bound on batch-inversion threads per SM (option "inv_fill_per_sm")
     int dev_slots_used = 1;                   // slots whose status words the last *_dev call wrote
     size_t inv_per_thread = 32;               // batch-inversion chain length (option "inv_per_thread"; 8: 0.31 ms, 16: 0.24, 32: 0.20, 64: 0.20 at n = 2^20)
     Slot* cur = &slots[0];                    // slot whose buffers the dev_* functions use (calls are serialised by `mu`)
@@ -120,7 +121,7 @@ static inline unsigned grid_for(size_t n) { return (unsigned)((n + ECB_TPB - 1) 
 static inline size_t inv_threads(const DevCtx& d, size_t n) {
     size_t per = d.inv_per_thread ? d.inv_per_thread : 32;
     size_t T = (n + per - 1) / per;
-    size_t fill = (size_t)d.sm_count * 256;
+    size_t fill = (size_t)d.sm_count * (d.inv_fill_per_sm ? d.inv_fill_per_sm : 256);
     if (T < fill) T = fill;
     if (T > n) T = n;
     return T ? T : 1;

@@ -153,8 +153,17 @@ struct F448 {
         sqr(r, a);
         for (int i = 1; i < n; i++) sqr(r, r);
     }
-    // a^(p-2) = a^(2^448 - 2^224 - 3); 0 -> 0
+    // safegcd (modinv.cuh); 0 -> 0
     ECB_DEV static void invert(el& r, const el& a) {
+        el c;
+        freeze(c, a);
+        u32 p[14];
+        ECB_UNROLL
+        for (int i = 0; i < 14; i++) p[i] = (i == 7) ? 0xfffffffeu : 0xffffffffu;
+        sg_modinv<14, 15, 37>(r.v, c.v, p);
+    }
+    // a^(p-2) = a^(2^448 - 2^224 - 3); 0 -> 0
+    ECB_DEV static void invert_fermat(el& r, const el& a) {
         el x2, x3, x6, x12, x24, x27, x54, x108, x111, x222, x223, t;
         sqr(t, a);           mul(x2, t, a);
         sqr(t, x2);          mul(x3, t, a);

@@ -12,6 +12,7 @@
 // done by renaming registers.
 #pragma once
 #include "limb.cuh"
+#include "modinv.cuh"
 
 namespace ecb {
 
@@ -442,7 +443,19 @@ struct Mont {
     // The result is the field inverse, so any correct chain gives the same bits as
     // the reference's Fermat chains (p256r1.rs:49-65, p384r1.rs:50-69) and safegcd
     // (bls12_381/fp.rs:55-57).
+    // Montgomery-domain inverse by safegcd (modinv.cuh): (aR)^-1 = a^-1 R^-1, then two products with
+    // R^2 bring it back to a^-1 R.  0 -> 0.  This is what the batch-inversion kernels use.
     ECB_DEV static void invert(el& r, const el& a) {
+        el c, t, r2;
+        canon(c, a);
+        u32 p[N];
+        ECB_UNROLL
+        for (int i = 0; i < N; i++) { p[i] = P::mod(i); r2.v[i] = P::r2(i); }
+        sg_modinv<N, (32 * N + 2 + 29) / 30, (N <= 8 ? 22 : 32)>(t.v, c.v, p);
+        mul(t, t, r2);
+        mul(r, t, r2);
+    }
+    ECB_DEV static void invert_fermat(el& r, const el& a) {
         el acc;
         set_one(acc);
         for (int i = N - 1; i >= 0; i--) {

@@ -300,3 +300,35 @@ def test_ecdsa_digest_to_scalar_on_device_code(hs):
                 assert z[i].tobytes() == want, (curve, hname, i)
                 # after the reduction mod n this is the reference's digest_to_scalar
                 assert (int.from_bytes(want, "big") % c.n).to_bytes(sb, "big") == R.ecdsa_digest_to_scalar(c, d)
+
+
+@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (1, R.P256.n, 8), (2, R.P384.p, 12), (3, R.P384.n, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
+def test_safegcd_inversion_montgomery_fields(hs, field, mod, n):
+    """Field inverses come from safegcd divsteps (csrc/modinv.cuh), not from a Fermat chain: check
+    the whole range of operand shapes, including 0 -> 0."""
+    f, _ = hs
+    g = rng(300 + field)
+    Rm = 1 << (32 * n)
+    r = np.zeros(n, dtype=np.uint32)
+    vals = [1, 2, 3, mod - 1, mod - 2, (mod + 1) // 2, 1 << 200, (1 << (32 * n - 1)) % mod, Rm % mod]
+    vals += [_structured(g, n) % mod for _ in range(150)] + [int.from_bytes(g.bytes(64), "little") % mod for _ in range(150)]
+    for a in vals:
+        if a == 0:
+            continue
+        f.hs_mont(field, 6, p(words(a * Rm % mod, n)), p(words(0, n)), p(r))
+        assert val(r) % mod == pow(a, -1, mod) * Rm % mod, hex(a)
+    f.hs_mont(field, 6, p(words(0, n)), p(words(0, n)), p(r))
+    assert val(r) == 0
+
+
+def test_safegcd_inversion_25519_and_448(hs):
+    f, k = hs
+    g = rng(400)
+    r8, r14 = np.zeros(8, dtype=np.uint32), np.zeros(14, dtype=np.uint32)
+    P, Q = R.P25519, R.P448
+    for a in [1, 2, P - 1, P, P + 1, 2**256 - 1, 19, 38, 2**255] + [_structured(g, 8) for _ in range(150)] + [int.from_bytes(g.bytes(32), "little") for _ in range(150)]:
+        f.hs_fe25519(6, p(words(a, 8)), p(words(0, 8)), p(r8))
+        assert val(r8) % P == (pow(a % P, -1, P) if a % P else 0), hex(a)
+    for a in [1, 2, Q - 1, Q, Q + 1, 2**448 - 1, 2**224, 2**447] + [_structured(g, 14) for _ in range(100)] + [int.from_bytes(g.bytes(56), "little") for _ in range(100)]:
+        k.hs_fe448(6, p(words(a, 14)), p(words(0, 14)), p(r14))
+        assert val(r14) % Q == (pow(a % Q, -1, Q) if a % Q else 0), hex(a)
