@@ -116,6 +116,11 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
         for (DevCtx* d : ctx->devs) d->inv_per_thread = (size_t)value;
         return ECB_OK;
     }
+    if (!strcmp(key, "inv_block")) {
+        if (value < 0 || value > 2) return set_err(ctx, ECB_ERR_INVALID_ARG, "inv_block must be 0, 1 or 2");
+        for (DevCtx* d : ctx->devs) d->inv_block = (int)value;
+        return ECB_OK;
+    }
     if (!strcmp(key, "inv_fill_per_sm")) {
         if (value < 32 || value > 2048) return set_err(ctx, ECB_ERR_INVALID_ARG, "inv_fill_per_sm must be in 32..2048");
         for (DevCtx* d : ctx->devs) d->inv_fill_per_sm = (size_t)value;

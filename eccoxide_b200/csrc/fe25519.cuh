@@ -24,6 +24,7 @@ struct fe25519 {
 struct F25519 {
     typedef fe25519 el;
     static constexpr int N = 8;
+    static constexpr bool BLOCK_INV = true;   // k_batch_inv (one inversion per block) measured faster for this field
 
     ECB_DEV static void set_zero(el& r) {
         ECB_UNROLL

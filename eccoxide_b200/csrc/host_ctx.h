@@ -51,6 +51,7 @@ struct DevCtx {
     cudaEvent_t ev_fork = nullptr;
     size_t inv_fill_per_sm = 256;             // lower bound on batch-inversion threads per SM (option "inv_fill_per_sm")
     int dev_slots_used = 1;                   // slots whose status words the last *_dev call wrote
+    int inv_block = 1;                        // batch inversion, one safegcd per block instead of per thread: 0 never, 1 where measured faster (2^255-19), 2 every field (option "inv_block")
     size_t inv_per_thread = 32;               // batch-inversion chain length (option "inv_per_thread"; 8: 0.31 ms, 16: 0.24, 32: 0.20, 64: 0.20 at n = 2^20)
     Slot* cur = &slots[0];                    // slot whose buffers the dev_* functions use (calls are serialised by `mu`)
     u32* ed_table = nullptr;

@@ -368,20 +368,20 @@ ECB_DEV void x25519_body(size_t idx, size_t n, const u32* scalars, const u32* us
 //   X25519 z2 = 0 -> output 0 as invert_or_zero does, curve25519.rs:191, :512).
 // Cost per element: 3 M + the finisher's (2 M for x,y), plus one inversion per thread.
 // =======================================================================================
-template <class FT, class FIN>
-ECB_DEV void batch_inv_body(size_t t, size_t T, size_t n, const u32* planes, u32* pf, FIN fin) {
+// forward pass: running products of the thread's elements (t, t+T, t+2T, ...) into `pf`, two
+// interleaved chains (elements t, t+2T, ... and t+T, t+3T, ...): the two running products are
+// independent, so the dependent multiplication chains overlap; returns the two chain totals.
+template <class FT>
+ECB_DEV void batch_inv_forward(size_t t, size_t T, size_t n, const u32* planes, u32* pf,
+                               typename FT::el& accA, typename FT::el& accB) {
     typedef typename FT::el fe;
     constexpr int N = FT::N;
-    if (t >= n) return;
     const u32* zp = planes + 2 * (size_t)N * n;
-    // Two interleaved chains per thread (elements t, t+2T, ... and t+T, t+3T, ...): the two
-    // running products are independent, so the long dependent multiplication chains overlap
-    // (the kernel is latency-bound: few warps, each a serial chain); one inversion serves both.
-    fe accA, accB, zA, zB, one;
+    fe zA, zB, one;
     FT::set_one(one);
     FT::set_one(accA);
     FT::set_one(accB);
-    size_t cnt = (n - t + T - 1) / T;            // elements owned by this thread
+    size_t cnt = t < n ? (n - t + T - 1) / T : 0;  // elements owned by this thread
     size_t pairs = cnt / 2;
     for (size_t j = 0; j < pairs; j++) {
         size_t ia = t + (2 * j) * T, ib = ia + T;
@@ -407,11 +407,18 @@ ECB_DEV void batch_inv_body(size_t t, size_t T, size_t n, const u32* planes, u32
         plane_st<N>(pf, n, ia, accA.v);
         FT::mul(accA, accA, zA);
     }
-    fe inv, invA, invB;
-    FT::mul(inv, accA, accB);
-    FT::invert(inv, inv);
-    FT::mul(invA, inv, accB);
-    FT::mul(invB, inv, accA);
+}
+// backward pass: invA / invB are the inverses of the two chain totals
+template <class FT, class FIN>
+ECB_DEV void batch_inv_backward(size_t t, size_t T, size_t n, const u32* planes, const u32* pf, FIN fin,
+                                typename FT::el invA, typename FT::el invB) {
+    typedef typename FT::el fe;
+    constexpr int N = FT::N;
+    const u32* zp = planes + 2 * (size_t)N * n;
+    fe zA, zB, one;
+    FT::set_one(one);
+    size_t cnt = t < n ? (n - t + T - 1) / T : 0;
+    size_t pairs = cnt / 2;
     if (cnt & 1) {
         size_t ia = t + (cnt - 1) * T;
         plane_ld<N>(zA.v, zp, n, ia);
@@ -449,6 +456,20 @@ ECB_DEV void batch_inv_body(size_t t, size_t T, size_t n, const u32* planes, u32
         fin(ia, zinvA, zeroA);
         fin(ib, zinvB, zeroB);
     }
+}
+// one inversion per thread (the host simulation and option inv_block = 0 use this form; the
+// block-cooperative kernel in tu_common.cuh shares the two passes and inverts once per block)
+template <class FT, class FIN>
+ECB_DEV void batch_inv_body(size_t t, size_t T, size_t n, const u32* planes, u32* pf, FIN fin) {
+    typedef typename FT::el fe;
+    if (t >= n) return;
+    fe accA, accB, inv, invA, invB;
+    batch_inv_forward<FT>(t, T, n, planes, pf, accA, accB);
+    FT::mul(inv, accA, accB);
+    FT::invert(inv, inv);
+    FT::mul(invA, inv, accB);
+    FT::mul(invB, inv, accA);
+    batch_inv_backward<FT, FIN>(t, T, n, planes, pf, fin, invA, invB);
 }
 
 // finishers ------------------------------------------------------------------------------

@@ -19,6 +19,7 @@ struct fe448 {
 struct F448 {
     typedef fe448 el;
     static constexpr int N = 14;
+    static constexpr bool BLOCK_INV = false;
 
     ECB_DEV static void set_zero(el& r) {
         ECB_UNROLL

@@ -38,6 +38,7 @@ struct MontKind {
 template <class P>
 struct Mont {
     static constexpr int N = P::N;
+    static constexpr bool BLOCK_INV = false;  // wider fields: the per-thread form of the batch inversion is faster (registers)
     typedef P P_;
     typedef fe_mont<P::N> el;
 

@@ -59,7 +59,7 @@ const char* ecb_last_error(ecb_ctx* ctx);
 int ecb_device_count(ecb_ctx* ctx);
 /* tunables, before first use: "ed25519_comb_w" (window width of the fixed-base comb, 4..24; 0 = by free memory),
  * "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w" (generator combs of the Weierstrass curves, 4..22),
- * "chunk" (elements per pipeline chunk), "inv_per_thread" (batch-inversion chain length), "profile" (1: record CUDA events around the kernels of
+ * "chunk" (elements per pipeline chunk), "inv_per_thread" (batch-inversion chain length), "inv_block" (batch inversion: 0 one inversion per thread, 2 one per block, 1 (default) per field as measured), "profile" (1: record CUDA events around the kernels of
  * every call on the launching stream, read back with ecb_profile_collect) */
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */

@@ -656,10 +656,38 @@ def test_host_entry_points_across_pipeline_chunks(ctx, coracle):
         ctx.set_option("chunk", 189440)
 
 
+@pytest.mark.parametrize("mode", [0, 2])
+def test_batch_inversion_forms_agree(ctx, coracle, mode):
+    """Option inv_block: one inversion per thread (0) or one per block (2) for EVERY field — the
+    default picks per field; both forms must give the reference's bytes, including Z = 0 elements
+    (zero scalars -> infinity) and ragged sizes that leave threads of the last block without work."""
+    g = rng(4242 + mode)
+    ctx.set_option("inv_block", mode)
+    try:
+        for n in (1, 130, 5000):
+            kb = scalars_mod(g, n, R.L25519, 32, "little")
+            kb[0] = 0
+            assert np.array_equal(ctx.ed25519_mul_base(kb), coracle.ed25519_mul_base(kb))
+            k, u = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
+            u[n // 2] = 0                                    # z2 = 0 -> output 0
+            assert np.array_equal(ctx.x25519(k, u), coracle.x25519(k, u))
+        for curve in CURVES:
+            c = R.WCURVES[curve]
+            ks = scalars_mod(g, 300, c.n, c.sbytes, "big")
+            ks[3] = 0
+            want, winf = coracle.wei_mul_base(curve, ks)
+            got, inf = ctx.wei_mul_base(curve, ks)
+            assert np.array_equal(inf, winf) and np.array_equal(got, want), curve
+        k, u = rand_bytes(g, 200, 56), rand_bytes(g, 200, 56)
+        assert np.array_equal(ctx.x448(k, u), coracle.x448(k, u))
+    finally:
+        ctx.set_option("inv_block", 1)
+
+
 def test_options_are_validated(ctx):
     from eccoxide_b200 import EccBatchError
 
-    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 25), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0)):
+    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 25), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0), ("inv_block", 3)):
         with pytest.raises(EccBatchError) as e:
             ctx.set_option(key, val)
         assert e.value.code == -2
