@@ -427,6 +427,21 @@ def pcie_bandwidth(torch, nbytes=64 << 20):
         e1.record()
         torch.cuda.synchronize()
         out[nm] = 4 * nbytes / (e0.elapsed_time(e1) * 1e-3) / 1e9
+    # both directions at once (what the pipelined host path asks of the link): 1 part in, 2 parts out,
+    # the byte ratio of the affine-output operations
+    h2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+    d2 = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(4):
+        with torch.cuda.stream(s_in):
+            d[: nbytes // 2].copy_(h[: nbytes // 2], non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h2.copy_(d2, non_blocking=True)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    out["duplex_1in_2out_gbs_total"] = 4 * (nbytes + nbytes // 2) / dt / 1e9
     return out
 
 
@@ -566,6 +581,11 @@ def main():
     e2e_s, e2e_out = measure_e2e(torch, ctx, name, n, 1 if args.profile_run else max(3, min(args.steps, 10)), args.warmup, r["ins_h"], dist)
 
     line = None
+    pcie = pcie_bandwidth(torch) if rank == 0 else None
+    if pcie:
+        # the host path moves in + out bytes over one link; with both directions busy the link's TOTAL is what counts
+        pcie["link_floor_ms_per_step"] = (r["in_bytes"] + r["out_bytes"]) / (pcie["duplex_1in_2out_gbs_total"] * 1e9) * 1e3
+        pcie["e2e_ms_per_step"] = e2e_s * 1e3
     if rank == 0:
         # parity spot check of this very run (never in the timed region): device output vs the oracle
         check = None
@@ -601,7 +621,7 @@ def main():
                        "parallelism": "%d x contiguous batch slice, no collective" % world},
             "e2e": {"value": world * n / e2e_s, "unit": "scalar-mults/s", "h2d_bytes_per_step": r["in_bytes"], "d2h_bytes_per_step": r["out_bytes"],
                     "path": "ecb_* host entry point, pinned host buffers, chunks pipelined over 4 stream slots",
-                    "pcie": pcie_bandwidth(torch)},
+                    "pcie": pcie},
             "gpu_launches": int(r["launches"]),
             "roofline": {"bound": "imad", "achieved": achieved, "peak": peak, "unit": "T MAC32/s (32x32->64 multiply-accumulates)", "frac": achieved / peak if peak else None,
                          "traffic": traffic, "mac32_per_op": W,
@@ -623,6 +643,8 @@ def main():
             wl[x] = {"value": v, "ms_per_step": rx["ms_per_step"], "batch_per_gpu": nx, "mac32_per_op": work_of(x),
                      "roofline_frac": (nx * work_of(x) / (rx["ms_per_step"] * 1e-3) / 1e12) / peak if peak else None,
                      "kernels_ms": {"scalar_mult": rx["main_ms"], "batch_inversion_encode": rx["fin_ms"]}}
+            ex_s, _ = measure_e2e(torch, ctx, x, nx, 1 if args.profile_run else 5, 2, rx["ins_h"], dist)
+            wl[x]["e2e"] = world * nx / ex_s
             del rx
             torch.cuda.empty_cache()
         except Exception as e:  # keep the headline line even if an extra fails

@@ -60,6 +60,7 @@ SIGNATURES = {
     "ecb_profile_collect": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_int)]),
     "ecb_dev_status": (_int, [_vp, _int, _szp]),
     "ecb_imad_probe": (_int, [_vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "ecb_debug_chunk_plan": (ctypes.c_long, [_sz, _sz, _sz, ctypes.c_long, _vp, _sz]),
     "ecb_debug_ed25519_table": (ctypes.c_long, [_vp, _int, _vp, _sz, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
 }
 

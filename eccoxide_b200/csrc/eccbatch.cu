@@ -131,6 +131,11 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
         ctx->opt_chunk = (size_t)value;
         return ECB_OK;
     }
+    if (!strcmp(key, "ramp")) {
+        if (value < 0 || value > 4) return set_err(ctx, ECB_ERR_INVALID_ARG, "ramp must be in 0..4");
+        ctx->opt_ramp = value;
+        return ECB_OK;
+    }
     if (!strcmp(key, "inv_hi")) {
         ctx->opt_inv_hi = value ? 1 : 0;
         return ECB_OK;
@@ -168,6 +173,39 @@ struct HostOut {
 };
 
 // op(d, stream, din[], dout[], n) enqueues the kernels for one chunk
+// Chunk schedule of one device's slice [lo, hi): the first chunks ramp up from chunk / 2^ramp and the
+// last ones ramp back down, so that the pipeline (copy in | kernels | copy out, ECB_NSLOT chunks in
+// flight) fills and drains on small chunks: the first copy-in and the last copy-out, which nothing
+// can overlap, shrink with the chunk they belong to.  The middle is cut into equal chunks <= chunk.
+static void chunk_plan(size_t lo, size_t hi, size_t chunk, long ramp, std::vector<size_t>& bounds) {
+    bounds.clear();
+    bounds.push_back(lo);
+    size_t len = hi - lo;
+    std::vector<size_t> up;
+    size_t used = 0;
+    for (long r = ramp; r >= 1; r--) {
+        size_t c = chunk >> r;
+        if (c < 4096) continue;
+        up.push_back(c);
+        used += 2 * c;
+    }
+    if (used + chunk > len) {  // short batch: no ramp
+        up.clear();
+        used = 0;
+    }
+    size_t pos = lo;
+    for (size_t c : up) bounds.push_back(pos += c);
+    size_t mid = len - used;
+    size_t nmid = (mid + chunk - 1) / chunk;
+    if (up.empty() && ramp > 0) {  // short batch: still ECB_NSLOT chunks (>= 16384 elements each) to overlap copies and kernels
+        size_t want = len / 16384 < (size_t)ECB_NSLOT ? len / 16384 : (size_t)ECB_NSLOT;
+        if (nmid < want) nmid = want;
+    }
+    for (size_t i = 1; i <= nmid; i++) bounds.push_back(pos + mid * i / nmid);
+    pos += mid;
+    for (size_t i = up.size(); i-- > 0;) bounds.push_back(pos += up[i]);
+}
+
 template <class OP>
 static int run_sharded(ecb_ctx* ctx, size_t n, const std::vector<HostArg>& ins, const std::vector<HostOut>& outs,
                        bool has_status, size_t* bad_index, OP op) {
@@ -198,8 +236,10 @@ static int run_sharded(ecb_ctx* ctx, size_t n, const std::vector<HostArg>& ins, 
             };
             int rcb = ECB_OK;
             size_t ci = 0;
-            for (size_t c0 = lo; c0 < hi && rcb == ECB_OK && bad[di] == ~0ull; c0 += ctx->opt_chunk, ci++) {
-                size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
+            std::vector<size_t> bounds;
+            chunk_plan(lo, hi, ctx->opt_chunk, ctx->opt_ramp, bounds);
+            for (; ci + 1 < bounds.size() && rcb == ECB_OK && bad[di] == ~0ull; ci++) {
+                size_t c0 = bounds[ci], cn = bounds[ci + 1] - c0;
                 Slot& sl = d.slots[ci % ECB_NSLOT];
                 auto one = [&]() -> int {
                     TRY(retire(sl));
@@ -700,6 +740,14 @@ int ecb_imad_probe(ecb_ctx* ctx, int di, int variant, int iters, double* macs_pe
     return dev_imad_probe(ctx, *d, variant, iters, macs_per_s, ms_out);
 }
 
+long ecb_debug_chunk_plan(size_t lo, size_t hi, size_t chunk, long ramp, size_t* bounds, size_t cap) {
+    if (hi < lo || chunk == 0 || ramp < 0 || ramp > 4) return -1;
+    std::vector<size_t> b;
+    chunk_plan(lo, hi, chunk, ramp, b);
+    if (bounds)
+        for (size_t i = 0; i < b.size() && i < cap; i++) bounds[i] = b[i];
+    return (long)b.size();
+}
 long ecb_debug_ed25519_table(ecb_ctx* ctx, int di, uint8_t* out, size_t cap, int* w, int* nwin) {
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;

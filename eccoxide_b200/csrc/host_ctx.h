@@ -78,6 +78,7 @@ struct ecb_ctx {
     size_t opt_chunk = 189440;  // elements per pipeline chunk = 148 SMs x 1280 (ECB_NSLOT chunks in flight per device; measured best of 2^16..2^19)
     long opt_profile = 0;
     long opt_inv_hi = 1;                      // run batch inversions on the slot's high-priority side stream
+    long opt_ramp = 2;                        // pipeline chunk schedule: this many halvings of the chunk size at both ends of a batch (option "ramp")
     long opt_dev_split = 0;                   // 1: split large device-resident batches over the slot streams (measured: no gain, the
                                               // shorter inversion chains cost what the overlap saves; kept as an option)
     std::atomic<unsigned long long> launches{0};

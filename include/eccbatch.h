@@ -59,7 +59,7 @@ const char* ecb_last_error(ecb_ctx* ctx);
 int ecb_device_count(ecb_ctx* ctx);
 /* tunables, before first use: "ed25519_comb_w" (window width of the fixed-base comb, 4..24; 0 = by free memory),
  * "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w" (generator combs of the Weierstrass curves, 4..22),
- * "chunk" (elements per pipeline chunk), "inv_per_thread" (batch-inversion chain length), "inv_block" (batch inversion: 0 one inversion per thread, 2 one per block, 1 (default) per field as measured), "profile" (1: record CUDA events around the kernels of
+ * "chunk" (elements per pipeline chunk), "ramp" (halvings of the chunk size at both ends of a batch, 0..4), "inv_per_thread" (batch-inversion chain length), "inv_block" (batch inversion: 0 one inversion per thread, 2 one per block, 1 (default) per field as measured), "profile" (1: record CUDA events around the kernels of
  * every call on the launching stream, read back with ecb_profile_collect) */
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
@@ -152,6 +152,9 @@ int ecb_imad_probe(ecb_ctx* ctx, int dev_index, int variant, int iters, double* 
 /* with option "profile" = 1: sum over the calls since the last collect of the device time (ms) of
  * the scalar-multiplication kernel(s) and of the batch-inversion / encoding kernel; synchronises. */
 int ecb_profile_collect(ecb_ctx* ctx, int dev_index, double* main_ms, double* finish_ms, int* calls);
+/* debug (no device needed): the pipeline chunk schedule the host entry points use for one device's
+ * slice [lo, hi) — writes the chunk boundaries (first = lo, last = hi) and returns how many */
+long ecb_debug_chunk_plan(size_t lo, size_t hi, size_t chunk, long ramp, size_t* bounds, size_t cap);
 /* debug: copy the device's Ed25519 comb table (niels entries, 96 B each) to host; returns entries */
 long ecb_debug_ed25519_table(ecb_ctx* ctx, int dev_index, uint8_t* out, size_t cap_bytes, int* w, int* nwin);
 

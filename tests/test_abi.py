@@ -60,3 +60,35 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".inc")):
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "oracle" not in txt.replace("test oracle", "").lower() or f in (), "%s mentions the oracle" % f
+
+
+def test_pipeline_chunk_schedule_covers_every_slice_exactly():
+    """Host logic of the pipelined entry points (run_sharded, eccbatch.cu): the chunk boundaries of a
+    device's slice are strictly increasing from lo to hi, no chunk exceeds the configured size, long
+    batches start and end on ramped (halved) chunks, short ones are still cut for overlap."""
+    import numpy as np
+
+    from eccoxide_b200 import _lib
+
+    lib = _lib.load()
+    C = 189440
+
+    def plan(lo, hi, chunk=C, ramp=2):
+        cnt = lib.ecb_debug_chunk_plan(lo, hi, chunk, ramp, None, 0)
+        assert cnt >= 2
+        b = np.zeros(cnt, dtype=np.uint64)
+        assert lib.ecb_debug_chunk_plan(lo, hi, chunk, ramp, b.ctypes.data_as(ctypes.c_void_p), cnt) == cnt
+        return b.astype(np.int64)
+
+    for lo, hi in ((0, 1), (0, 1000), (7, 7 + 65536), (0, C), (0, C + 1), (0, 473600), (0, 473601), (5, 5 + (1 << 20)), (0, 569097), (0, 1 << 24)):
+        for ramp in range(5):
+            for chunk in (1000, C):
+                b = plan(lo, hi, chunk, ramp)
+                sizes = np.diff(b)
+                assert b[0] == lo and b[-1] == hi and (sizes > 0).all() and sizes.max() <= chunk, (lo, hi, ramp, chunk)
+    sizes = np.diff(plan(0, 1 << 20))
+    assert list(sizes[:2]) == [C // 4, C // 2] and list(sizes[-2:]) == [C // 2, C // 4]
+    assert len(np.diff(plan(0, 1 << 16))) == 4          # short batch: four chunks in flight
+    assert len(np.diff(plan(0, 1 << 16, ramp=0))) == 1  # ramp 0: plain equal chunks
+    assert len(np.diff(plan(0, 1000))) == 1
+    assert lib.ecb_debug_chunk_plan(10, 5, C, 2, None, 0) == -1

@@ -640,8 +640,13 @@ def test_host_entry_points_across_pipeline_chunks(ctx, coracle):
     kb = rand_bytes(g, n, 32)
     kb[:, 31] &= 0x0F
     got = ctx.ed25519_mul_base(kb)
-    idx = np.concatenate([np.arange(32)] + [np.arange(c * 189440 - 16, c * 189440 + 16) for c in (1, 2, 3)] + [np.arange(n - 32, n)])
-    assert np.array_equal(got[idx], coracle.ed25519_mul_base(kb[idx], threads(coracle)))
+    # every element: the chunk borders move with the schedule (ramped chunk sizes, option "ramp")
+    assert np.array_equal(got, coracle.ed25519_mul_base(kb, threads(coracle)))
+    ctx.set_option("ramp", 0)
+    try:
+        assert np.array_equal(ctx.ed25519_mul_base(kb), got)
+    finally:
+        ctx.set_option("ramp", 2)
     kb[2 * 189440 + 5] = 0xFF
     kb[3 * 189440 + 9] = 0xFF
     with pytest.raises(EccBatchError) as e:
@@ -687,7 +692,7 @@ def test_batch_inversion_forms_agree(ctx, coracle, mode):
 def test_options_are_validated(ctx):
     from eccoxide_b200 import EccBatchError
 
-    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 25), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0), ("inv_block", 3)):
+    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 25), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0), ("inv_block", 3), ("ramp", 5)):
         with pytest.raises(EccBatchError) as e:
             ctx.set_option(key, val)
         assert e.value.code == -2
