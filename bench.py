@@ -48,6 +48,11 @@ WORK = {
     "p384_mul": 864666,
     "bls12_381_g1_mul": 984276,
     "x448": 715596,
+    # wire formats, reference algorithm: sqrt chain p256r1.rs:68 (253 S + 11 M) + x^3 + a x + b;
+    # BLS: Fp::sqrt = power((p+1)/4) by square-and-multiply (~380 S + ~190 M) + is_in_subgroup
+    # (2 x mul_by_abs_x = 126 doublings (7 M + 2 S... counted 9 M) + 10 additions (14 M))
+    "p256_decompress": 254 * 36 + 13 * 64,
+    "bls12_381_g1_from_compressed": 380 * 234 + 192 * 300 + (126 * 9 + 10 * 14) * 300,
 }
 # name -> (log2 n per GPU, bytes in per op, bytes out per op, BASELINE.json config it belongs to)
 WORKLOADS = {
@@ -64,6 +69,8 @@ WORKLOADS = {
     "ed25519_verify": (20, 128, 1, "north star: batched ed25519 verify (k = SHA-512(R||A||M) mod l precomputed by the caller)"),
     "p256_mul_base": (20, 32, 65, "north star: fixed-base p256r1 Point::mul_base (comb)"),
     "bls12_381_g1_mul_base": (20, 32, 97, "north star: fixed-base BLS12-381 G1 Point::mul_base (comb)"),
+    "p256_decompress": (20, 33, 65, "SURVEY 8 f.1: PointAffine::decompress (SEC1 point decompression) on p256r1"),
+    "bls12_381_g1_from_compressed": (20, 48, 97, "SURVEY 8 f.1: BLS12-381 G1 from_compressed with the prime-order-subgroup check"),
 }
 HEADLINE = "ed25519_mul_base"
 EXTRA_DEFAULT = ["ed25519_mul_base_2p16", "x25519", "p256_mul", "p256_ecdsa_verify", "bls12_381_g1_mul"]
@@ -127,6 +134,15 @@ def make_inputs(name, n, ctx, seed):
         return [rand_scalars(g, n, 32, 1, "big")]
     if base == "bls12_381_g1_mul_base":
         return [rand_scalars(g, n, 32, 2, "big")]
+    if base == "p256_decompress":
+        pts, _ = ctx.wei_mul_base("p256r1", rand_scalars(g, uniq, 32, 1, "big"))
+        x = np.ascontiguousarray(pts[:, :32])
+        x[5::16] = g.integers(0, 256, size=x[5::16].shape, dtype=np.uint8)   # 1/16 random field elements (half of them no x-coordinate)
+        x[5::16, 0] &= 0x7F
+        return [tile(x), np.ascontiguousarray(np.tile(g.integers(0, 2, size=uniq, dtype=np.uint8), n // uniq))]
+    if base == "bls12_381_g1_from_compressed":
+        pts, _ = ctx.wei_mul_base("bls12_381_g1", rand_scalars(g, uniq, 32, 2, "big"))
+        return [tile(ctx.bls12_381_g1_to_compressed(pts))]
     if base == "p256_ecdsa_verify":
         from oracle import pyref as R
 
@@ -157,6 +173,7 @@ OUT_SHAPES = {
     "ed25519_mul_base": [64], "ed25519_mul": [64], "x25519": [32], "x25519_base": [32], "x448": [56],
     "p256_mul": [64, 1], "p384_mul": [96, 1], "bls12_381_g1_mul": [96, 1], "p256_ecdsa_verify": [1],
     "p256_mul_base": [64, 1], "bls12_381_g1_mul_base": [96, 1], "ed25519_verify": [1],
+    "p256_decompress": [64, 1], "bls12_381_g1_from_compressed": [96, 1],
 }
 
 
@@ -184,6 +201,10 @@ def dev_launch(ctx, name, ins, outs, n, stream):
         ctx.dev_call("ecb_wei_mul_base_dev", 0, 0 if base == "p256_mul_base" else 2, p[0], n, o[0], o[1], stream)
     elif base == "p256_ecdsa_verify":
         ctx.dev_call("ecb_ecdsa_verify_hashed_dev", 0, 0, p[0], p[1], p[2], n, o[0], stream)
+    elif base == "p256_decompress":
+        ctx.dev_call("ecb_wei_decompress_dev", 0, 0, p[0], p[1], n, o[0], o[1], stream)
+    elif base == "bls12_381_g1_from_compressed":
+        ctx.dev_call("ecb_bls12_381_g1_from_compressed_dev", 0, p[0], n, 1, o[0], o[1], stream)
     else:
         raise ValueError(name)
 
@@ -211,6 +232,10 @@ def host_call(ctx, name, ins, outs=None):
         return list(ctx.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], out=o[0], out_inf=o[1]))
     if base == "p256_ecdsa_verify":
         return [ctx.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], out=o[0])]
+    if base == "p256_decompress":
+        return list(ctx.wei_decompress("p256r1", ins[0], ins[1], out=o[0], out_ok=o[1]))
+    if base == "bls12_381_g1_from_compressed":
+        return list(ctx.bls12_381_g1_from_compressed(ins[0], True, out=o[0], out_ok=o[1]))
     raise ValueError(name)
 
 
@@ -236,6 +261,10 @@ def oracle_call(C, name, ins, nthreads):
         return list(C.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], nthreads))
     if base == "p256_ecdsa_verify":
         return [C.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], nthreads)]
+    if base == "p256_decompress":
+        return list(C.wei_decompress("p256r1", ins[0], ins[1], nthreads))
+    if base == "bls12_381_g1_from_compressed":
+        return list(C.bls12_381_g1_from_compressed(ins[0], True, nthreads))
     raise ValueError(name)
 
 

@@ -198,6 +198,41 @@ class Context:
         self._check(self._lib.ecb_wei_mul_base(self._ctx, cid, _p(k), n, _p(out), _p(inf), ctypes.byref(bad)), bad)
         return out, inf.astype(bool)
 
+    def wei_decompress(self, curve, x_be, sign, out=None, out_ok=None):
+        """PointAffine::decompress over a batch (affine.rs:48): (x || y rows, present)."""
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+        fb = FIELD_BYTES[cid]
+        x = _rows(x_be, fb, "x_be")
+        n = x.shape[0]
+        sg = np.ascontiguousarray(sign, dtype=np.uint8).reshape(-1)
+        if sg.shape[0] != n:
+            raise ValueError("count mismatch")
+        out = _out(out, (n, 2 * fb))
+        ok = _out(out_ok, (n,))
+        self._check(self._lib.ecb_wei_decompress(self._ctx, cid, _p(x), _p(sg), n, _p(out), _p(ok)))
+        return out, ok.astype(bool)
+
+    def bls12_381_g1_from_compressed(self, enc, check_subgroup=True, out=None, out_ok=None):
+        """PointAffine::from_compressed / from_compressed_oncurve_only (bls12_381/serialize.rs:286, :310)."""
+        e = _rows(enc, 48, "enc")
+        n = e.shape[0]
+        out = _out(out, (n, 96))
+        ok = _out(out_ok, (n,))
+        self._check(self._lib.ecb_bls12_381_g1_from_compressed(self._ctx, _p(e), n, 1 if check_subgroup else 0, _p(out), _p(ok)))
+        return out, ok.astype(bool)
+
+    def bls12_381_g1_to_compressed(self, xy_be, inf=None, out=None):
+        """Point::to_compressed (bls12_381/serialize.rs:400)."""
+        p = _rows(xy_be, 96, "xy_be")
+        n = p.shape[0]
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8).reshape(-1)
+            if inf.shape[0] != n:
+                raise ValueError("count mismatch")
+        out = _out(out, (n, 48))
+        self._check(self._lib.ecb_bls12_381_g1_to_compressed(self._ctx, _p(p), _p(inf), n, _p(out)))
+        return out
+
     def ecdsa_verify_hashed(self, curve, q_xy_be, z_be, rs_be, out=None):
         cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
         fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]

@@ -23,6 +23,12 @@ int dev_wei_mul_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, con
 int dev_wei_mul_base_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
 int dev_wei_mul_base_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
 int dev_wei_mul_base_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
+// wire formats (kernels3.cuh): PointAffine::decompress per curve, BLS12-381 G1 standard encodings
+int dev_wei_decompress_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_x, const unsigned char* d_sign, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
+int dev_wei_decompress_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_x, const unsigned char* d_sign, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
+int dev_wei_decompress_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_x, const unsigned char* d_sign, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
+int dev_bls_g1_from_compressed(ecb_ctx* ctx, DevCtx& d, const u32* d_enc, size_t n, int check, u32* d_out, unsigned char* d_ok, cudaStream_t s);
+int dev_bls_g1_to_compressed(ecb_ctx* ctx, DevCtx& d, const u32* d_xy, const unsigned char* d_inf, size_t n, u32* d_enc, cudaStream_t s);
 int dev_wei_table_p256(ecb_ctx* ctx, DevCtx& d);
 int dev_wei_table_p384(ecb_ctx* ctx, DevCtx& d);
 int dev_wei_table_bls(ecb_ctx* ctx, DevCtx& d);

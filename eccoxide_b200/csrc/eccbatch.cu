@@ -589,6 +589,43 @@ int ecb_wei_mul_base(ecb_ctx* ctx, int curve, const uint8_t* k_be, size_t n, uin
                            return dev_wei_mul_base(ctx, d, curve, (const u32*)in[0], cn, (u32*)o[0], (unsigned char*)o[1], s);
                        });
 }
+int ecb_wei_decompress(ecb_ctx* ctx, int curve, const uint8_t* x_be, const uint8_t* sign, size_t n, uint8_t* out_xy, uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb)) return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
+    if (n && (!x_be || !sign || !out_xy || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{x_be, fb}, {sign, 1}}, {{out_xy, 2 * fb}, {ok, 1}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           switch (curve) {
+                               case ECB_CURVE_P256R1:
+                                   return dev_wei_decompress_p256(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0],
+                                                                  (unsigned char*)o[1], s);
+                               case ECB_CURVE_P384R1:
+                                   return dev_wei_decompress_p384(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0],
+                                                                  (unsigned char*)o[1], s);
+                               default:
+                                   return dev_wei_decompress_bls(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0],
+                                                                 (unsigned char*)o[1], s);
+                           }
+                       });
+}
+int ecb_bls12_381_g1_from_compressed(ecb_ctx* ctx, const uint8_t* enc, size_t n, int check_subgroup, uint8_t* out_xy, uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!enc || !out_xy || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{enc, 48}}, {{out_xy, 96}, {ok, 1}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_bls_g1_from_compressed(ctx, d, (const u32*)in[0], cn, check_subgroup ? 1 : 0, (u32*)o[0],
+                                                             (unsigned char*)o[1], s);
+                       });
+}
+int ecb_bls12_381_g1_to_compressed(ecb_ctx* ctx, const uint8_t* xy_be, const uint8_t* inf, size_t n, uint8_t* enc) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!xy_be || !enc)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{xy_be, 96}, {inf, 1}}, {{enc, 48}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_bls_g1_to_compressed(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0], s);
+                       });
+}
 int ecb_ecdsa_verify_hashed(ecb_ctx* ctx, int curve, const uint8_t* q_xy, const uint8_t* z_be, const uint8_t* rs_be,
                             size_t n, uint8_t* ok, size_t* bad_index) {
     if (!ctx) return ECB_ERR_CUDA;
@@ -662,6 +699,34 @@ int ecb_wei_mul_base_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, size_
         return dev_wei_mul_base(ctx, *d, curve, (const u32*)d_k + lo * (sb / 4), cnt, (u32*)d_out + lo * (fb / 2),
                                 d_inf ? (unsigned char*)d_inf + lo : nullptr, st);
     });
+}
+int ecb_wei_decompress_dev(ecb_ctx* ctx, int di, int curve, const void* d_x, const void* d_sign, size_t n, void* d_out, void* d_ok,
+                           void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    single_slot(d);
+    switch (curve) {
+        case ECB_CURVE_P256R1:
+            return dev_wei_decompress_p256(ctx, *d, (const u32*)d_x, (const unsigned char*)d_sign, n, (u32*)d_out, (unsigned char*)d_ok,
+                                           (cudaStream_t)stream);
+        case ECB_CURVE_P384R1:
+            return dev_wei_decompress_p384(ctx, *d, (const u32*)d_x, (const unsigned char*)d_sign, n, (u32*)d_out, (unsigned char*)d_ok,
+                                           (cudaStream_t)stream);
+        case ECB_CURVE_BLS12_381_G1:
+            return dev_wei_decompress_bls(ctx, *d, (const u32*)d_x, (const unsigned char*)d_sign, n, (u32*)d_out, (unsigned char*)d_ok,
+                                          (cudaStream_t)stream);
+    }
+    return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
+}
+int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int di, const void* d_enc, size_t n, int check_subgroup, void* d_out, void* d_ok,
+                                         void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    single_slot(d);
+    return dev_bls_g1_from_compressed(ctx, *d, (const u32*)d_enc, n, check_subgroup ? 1 : 0, (u32*)d_out, (unsigned char*)d_ok,
+                                      (cudaStream_t)stream);
 }
 int ecb_x448_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);

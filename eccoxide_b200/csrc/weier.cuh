@@ -27,6 +27,7 @@ struct CurveP256 {
     ECB_DEV static u32 b3(int i) { return P256_B3[i]; }
     ECB_DEV static u32 gx(int i) { return P256_GX[i]; }
     ECB_DEV static u32 gy(int i) { return P256_GY[i]; }
+    ECB_DEV static u32 sqrt_e(int i) { return P256_SQRT_E[i]; }
 };
 struct CurveP384 {
     typedef Mont<P384_FP> F;
@@ -38,6 +39,7 @@ struct CurveP384 {
     ECB_DEV static u32 b3(int i) { return P384_B3[i]; }
     ECB_DEV static u32 gx(int i) { return P384_GX[i]; }
     ECB_DEV static u32 gy(int i) { return P384_GY[i]; }
+    ECB_DEV static u32 sqrt_e(int i) { return P384_SQRT_E[i]; }
 };
 struct CurveBLSG1 {
     typedef Mont<BLS_FP> F;
@@ -49,6 +51,8 @@ struct CurveBLSG1 {
     ECB_DEV static u32 b3(int i) { return BLSG1_B3[i]; }
     ECB_DEV static u32 gx(int i) { return BLSG1_GX[i]; }
     ECB_DEV static u32 gy(int i) { return BLSG1_GY[i]; }
+    ECB_DEV static u32 sqrt_e(int i) { return BLSG1_SQRT_E[i]; }
+    ECB_DEV static u32 beta(int i) { return BLSG1_BETA[i]; }
 };
 
 template <class C>

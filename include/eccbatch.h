@@ -114,6 +114,28 @@ int ecb_wei_mul(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, const uint8_t* 
 /* Point::mul_base(&Scalar) -> to_affine   (fiat/curve_macros.rs:55 -> projective.rs:965/:945) */
 int ecb_wei_mul_base(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, size_t n, uint8_t* out_xy_be, uint8_t* out_inf,
                      size_t* bad_index);
+/* ---- wire formats either side of the Weierstrass path --------------------------------------------------
+ * PointAffine::decompress(&FieldElement, Sign) -> CtOption<PointAffine> (src/curve/affine.rs:48,
+ * src/curve/fiat/curve_macros.rs:221; square roots src/curve/sec2/p256r1.rs:68, p384r1.rs:71,
+ * src/curve/bls12_381/fp.rs:64), batched.  x_be: n x FB bytes; sign: n bytes, 0 = Sign::Positive (the
+ * root whose canonical value is even), non-zero = Sign::Negative (odd) (field_macros.rs:557).
+ * out_xy_be: n x 2FB bytes x || y; ok[i] = 1 when the reference returns a present value, else 0 and
+ * the output bytes are zero: x >= p (FieldElement::from_bytes -> None, field_macros.rs:15) or
+ * x^3 + a x + b not a square. */
+int ecb_wei_decompress(ecb_ctx* ctx, int curve_id, const uint8_t* x_be, const uint8_t* sign, size_t n, uint8_t* out_xy_be,
+                       uint8_t* ok);
+/* BLS12-381 G1 standard (zcash / IETF) encodings, src/curve/bls12_381/serialize.rs.
+ * from_compressed: PointAffine::from_compressed (serialize.rs:286; check_subgroup != 0, the
+ * prime-order-subgroup test is PointAffine::is_in_subgroup, g1.rs:105) or from_compressed_oncurve_only
+ * (serialize.rs:310; check_subgroup == 0).  enc: n x 48 bytes; out_xy_be: n x 96 bytes; ok[i] = 0 (None,
+ * output zero) for a clear compression flag, the identity (the affine type cannot hold it), flag
+ * misuse, x >= p, x^3 + 4 not a square, and - when checking - points outside the subgroup.
+ * to_compressed: Point::to_compressed (serialize.rs:400): x with flag bits 7 (compressed) and 5 (y is the
+ * larger root, y > (p-1)/2); inf (n bytes, may be NULL) marks identities, encoded 0xc0 00 .. 00. */
+int ecb_bls12_381_g1_from_compressed(ecb_ctx* ctx, const uint8_t* enc, size_t n, int check_subgroup, uint8_t* out_xy_be,
+                                     uint8_t* ok);
+int ecb_bls12_381_g1_to_compressed(ecb_ctx* ctx, const uint8_t* xy_be, const uint8_t* inf, size_t n, uint8_t* enc);
+
 /* ecdsa::verify_hashed (src/protocol/ecdsa.rs:205-222) after Signature::from_bytes (:399).
  * q_xy_be: n x 2FB public keys; z_be: n x SB message scalars (any value, reduced mod n as
  * digest_to_scalar :340 does); rs_be: n x 2SB r || s (zero or >= n => ok = 0); ok: n x 1 B. */
@@ -136,6 +158,10 @@ int ecb_wei_mul_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_k_b
                     void* d_out_xy_be, void* d_out_inf, void* stream);
 int ecb_wei_mul_base_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_k_be, size_t n, void* d_out_xy_be,
                          void* d_out_inf, void* stream);
+int ecb_wei_decompress_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_x_be, const void* d_sign, size_t n,
+                           void* d_out_xy_be, void* d_ok, void* stream);
+int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int dev_index, const void* d_enc, size_t n, int check_subgroup,
+                                         void* d_out_xy_be, void* d_ok, void* stream);
 int ecb_x448_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);
 int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int dev_index, const void* d_a_enc, const void* d_r_enc, const void* d_s_le,
                                      const void* d_k_le, size_t n, void* d_ok, void* stream);

@@ -43,7 +43,8 @@ def load():
         lib = ctypes.CDLL(LIB_PATH)
         lib.orc_init.restype = None
         for name in ("orc_ed25519_mul_base", "orc_ed25519_mul", "orc_ed25519_verify_prehashed", "orc_x25519", "orc_x448",
-                     "orc_wei_mul", "orc_ecdsa_verify_hashed"):
+                     "orc_wei_mul", "orc_ecdsa_verify_hashed", "orc_wei_decompress", "orc_bls12_381_g1_from_compressed",
+                     "orc_bls12_381_g1_to_compressed"):
             getattr(lib, name).restype = ctypes.c_long
         lib.orc_init()
         _lib = lib
@@ -127,6 +128,44 @@ def wei_mul(curve, k_be, xy_be=None, inf_in=None, mode=MODE_WINDOW, nthreads=1):
 
 def wei_mul_base(curve, k_be, nthreads=1):
     return wei_mul(curve, k_be, None, None, MODE_COMB, nthreads)
+
+
+def wei_decompress(curve, x_be, sign, nthreads=1):
+    """PointAffine::decompress over a batch -> (x || y rows, present)."""
+    cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+    fb = FIELD_BYTES[cid]
+    x = _rows(x_be, fb)
+    n = x.shape[0]
+    sg = np.ascontiguousarray(sign, dtype=np.uint8).reshape(n)
+    out = np.zeros((n, 2 * fb), dtype=np.uint8)
+    ok = np.zeros(n, dtype=np.uint8)
+    load().orc_wei_decompress(cid, _p(x), _p(sg), ctypes.c_size_t(n), _p(out), _p(ok), nthreads)
+    return out, ok.astype(bool)
+
+
+def bls12_381_g1_from_compressed(enc, check_subgroup=True, nthreads=1):
+    e = _rows(enc, 48)
+    n = e.shape[0]
+    out = np.zeros((n, 96), dtype=np.uint8)
+    ok = np.zeros(n, dtype=np.uint8)
+    load().orc_bls12_381_g1_from_compressed(_p(e), ctypes.c_size_t(n), 1 if check_subgroup else 0, _p(out), _p(ok), nthreads)
+    return out, ok.astype(bool)
+
+
+def bls12_381_g1_to_compressed(xy_be, inf=None, nthreads=1):
+    p = _rows(xy_be, 96)
+    n = p.shape[0]
+    if inf is not None:
+        inf = np.ascontiguousarray(inf, dtype=np.uint8).reshape(n)
+    out = np.zeros((n, 48), dtype=np.uint8)
+    load().orc_bls12_381_g1_to_compressed(_p(p), _p(inf), ctypes.c_size_t(n), _p(out), nthreads)
+    return out
+
+
+def bls12_381_beta():
+    out = np.zeros(48, dtype=np.uint8)
+    load().orc_bls12_381_beta(_p(out))
+    return out.tobytes()
 
 
 def ecdsa_verify_hashed(curve, q_xy_be, z_be, rs_be, nthreads=1):

@@ -690,6 +690,7 @@ DEFINE_ECDSA(6)
  * init
  * ========================================================================================= */
 static pthread_once_t g_once = PTHREAD_ONCE_INIT;
+static void bls_extra_init(void);
 static void do_init(void) {
     u8 b[32];
     fe_set_u64(&FE_ONE, 1);
@@ -782,6 +783,7 @@ static void do_init(void) {
     hex2be(gx, "17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb", 48);
     hex2be(gy, "08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1", 48);
     curve_init6(&BLSG1, p, nn, bb, gx, gy, 48, 32, 1);
+    bls_extra_init();
 }
 void orc_init(void) { pthread_once(&g_once, do_init); }
 
@@ -899,6 +901,139 @@ static void j_wei(job* j, size_t lo, size_t hi) {
         case 2: WEI_BODY(6, &BLSG1, mode) break;
     }
 }
+/* PointAffine::decompress over a batch: a = x (fb bytes BE), b = sign bytes, o = x || y, o2 = present */
+#define DECOMP_BODY(NLV, CURVE)                                                                            \
+    {                                                                                                      \
+        const curve##NLV* c = (CURVE);                                                                     \
+        int fb = c->fbytes;                                                                                \
+        for (size_t i = lo; i < hi; i++) {                                                                 \
+            u8* out = j->o + (size_t)2 * fb * i;                                                           \
+            memset(out, 0, (size_t)2 * fb);                                                                \
+            j->o2[i] = 0;                                                                                  \
+            fe##NLV x, y;                                                                                  \
+            if (!f_from_be##NLV(&c->fp, &x, j->a + (size_t)fb * i, fb)) continue;                          \
+            if (!pt_decompress##NLV(c, &y, &x, j->b[i] != 0)) continue;                                    \
+            f_to_be##NLV(&c->fp, out, &x, fb);                                                             \
+            f_to_be##NLV(&c->fp, out + fb, &y, fb);                                                        \
+            j->o2[i] = 1;                                                                                  \
+        }                                                                                                  \
+    }
+static void j_decompress(job* j, size_t lo, size_t hi) {
+    switch (j->curve) {
+        case 0: DECOMP_BODY(4, &P256) break;
+        case 1: DECOMP_BODY(6, &P384) break;
+        case 2: DECOMP_BODY(6, &BLSG1) break;
+    }
+}
+
+/* ---- BLS12-381 G1 wire format and subgroup test -------------------------------------------
+ * bls12_381/serialize.rs: flags in the top three bits of byte 0 (0x80 compressed, 0x40 infinity,
+ * 0x20 y is the larger root: y > (p-1)/2); g1.rs:55-108: sigma(x, y) = (beta x, y),
+ * mul_by_abs_x = double-and-add over |x| = 0xd201000000010000, P in G1 <=> sigma(P) = -[x^2]P. */
+static fe6 BLS_BETA;          /* set in do_init from the cube roots of unity: the one with sigma(G) = [-x^2]G */
+static u64 BLS_HALF_P[6];     /* (p - 1) / 2 */
+#define BLS_ABS_X 0xd201000000010000ULL
+static void bls_mul_by_abs_x(pt6* r, const pt6* p) {
+    pt6 acc = *p;
+    for (int i = 62; i >= 0; i--) {
+        pt_dbl6(&BLSG1, &acc, &acc);
+        if ((BLS_ABS_X >> i) & 1) pt_add6(&BLSG1, &acc, &acc, p);
+    }
+    *r = acc;
+}
+static int bls_pt_equiv(const pt6* a, const pt6* b) { /* projective equality (projective.rs:133) */
+    const field6* F = &BLSG1.fp;
+    fe6 l, r;
+    f_mul6(F, &l, &a->X, &b->Z); f_mul6(F, &r, &b->X, &a->Z);
+    if (!f_eq6(&l, &r)) return 0;
+    f_mul6(F, &l, &a->Y, &b->Z); f_mul6(F, &r, &b->Y, &a->Z);
+    return f_eq6(&l, &r);
+}
+static int bls_in_subgroup(const pt6* p) {
+    pt6 t, u, s = *p;
+    bls_mul_by_abs_x(&t, p);
+    bls_mul_by_abs_x(&u, &t);
+    f_neg6(&BLSG1.fp, &u.Y, &u.Y);
+    f_mul6(&BLSG1.fp, &s.X, &s.X, &BLS_BETA);
+    return bls_pt_equiv(&s, &u);
+}
+/* beta and (p-1)/2 are derived, not embedded: beta = g^((p-1)/3) != 1 for the first small g, then the
+ * one of {beta, beta^2} that makes the generator pass the test (g1.rs:440-450 pins it the same way);
+ * tests/test_oracle_golden.py compares it with the reference's BETA_BYTES */
+static void bls_extra_init(void) {
+    const field6* F = &BLSG1.fp;
+    u64 e[6], pm1[6], one[6] = {1, 0, 0, 0, 0, 0};
+    sub_raw6(pm1, F->p, one);
+    for (int i = 0; i < 6; i++) BLS_HALF_P[i] = (pm1[i] >> 1) | (i + 1 < 6 ? pm1[i + 1] << 63 : 0);
+    unsigned __int128 rem = 0;
+    for (int i = 5; i >= 0; i--) {
+        unsigned __int128 cur = (rem << 64) | pm1[i];
+        e[i] = (u64)(cur / 3);
+        rem = cur % 3;
+    }
+    for (u64 g = 2; g < 32; g++) {
+        fe6 base, acc = F->r1;
+        memset(&base, 0, sizeof base);
+        base.v[0] = g;
+        f_mul6(F, &base, &base, &F->r2);
+        for (int i = 6 * 64 - 1; i >= 0; i--) {
+            f_sqr6(F, &acc, &acc);
+            if ((e[i / 64] >> (i % 64)) & 1) f_mul6(F, &acc, &acc, &base);
+        }
+        if (f_eq6(&acc, &F->r1)) continue;
+        BLS_BETA = acc;
+        if (!bls_in_subgroup(&BLSG1.G)) f_sqr6(F, &BLS_BETA, &acc);
+        break;
+    }
+}
+void orc_bls12_381_beta(u8* out48) {
+    orc_init();
+    f_to_be6(&BLSG1.fp, out48, &BLS_BETA, 48);
+}
+static int bls_y_is_largest(const fe6* y) {
+    u64 w[6];
+    f_to_raw6(&BLSG1.fp, w, y);
+    return !ge_raw6(BLS_HALF_P, w);   /* w > (p-1)/2 */
+}
+/* a = 48-byte encodings, mode = check_subgroup; o = x || y (96 B), o2 = Some/None */
+static void j_bls_from_compressed(job* j, size_t lo, size_t hi) {
+    const curve6* c = &BLSG1;
+    for (size_t i = lo; i < hi; i++) {
+        const u8* enc = j->a + 48 * i;
+        u8* out = j->o + 96 * i;
+        memset(out, 0, 96);
+        j->o2[i] = 0;
+        u8 flags = enc[0] & 0xE0;
+        if (!(flags & 0x80) || (flags & 0x40)) continue;   /* not compressed / the identity: None */
+        u8 buf[48];
+        memcpy(buf, enc, 48);
+        buf[0] &= 0x1F;
+        fe6 x, y;
+        if (!f_from_be6(&c->fp, &x, buf, 48)) continue;
+        if (!pt_decompress6(c, &y, &x, 0)) continue;
+        if (bls_y_is_largest(&y) != ((flags & 0x20) ? 1 : 0)) f_neg6(&c->fp, &y, &y);
+        if (j->mode) {
+            pt6 P;
+            P.X = x; P.Y = y; P.Z = c->fp.r1;
+            if (!bls_in_subgroup(&P)) continue;
+        }
+        f_to_be6(&c->fp, out, &x, 48);
+        f_to_be6(&c->fp, out + 48, &y, 48);
+        j->o2[i] = 1;
+    }
+}
+/* a = x || y (96 B), c = infinity flags (may be null); o = 48-byte encodings (Point::to_compressed) */
+static void j_bls_to_compressed(job* j, size_t lo, size_t hi) {
+    for (size_t i = lo; i < hi; i++) {
+        u8* out = j->o + 48 * i;
+        if (j->c && j->c[i]) { memset(out, 0, 48); out[0] = 0xC0; continue; }
+        memcpy(out, j->a + 96 * i, 48);
+        u64 w[6];
+        raw_from_be6(w, j->a + 96 * i + 48, 48);
+        out[0] |= 0x80 | (ge_raw6(BLS_HALF_P, w) ? 0 : 0x20);
+    }
+}
+
 static void j_ecdsa(job* j, size_t lo, size_t hi) {
     for (size_t i = lo; i < hi; i++) {
         int bad = 0;
@@ -952,6 +1087,22 @@ long orc_ecdsa_verify_hashed(int curve, const u8* q_xy, const u8* z_be, const u8
     return run_jobs(&t, n, nthreads, code);
 }
 /* comb-table entry (window i, digit j) as affine bytes, for pinning against params/comb/*.rs */
+/* PointAffine::decompress batch: sign[i] = 0 Positive (even y) / 1 Negative (odd y); ok[i] = present */
+long orc_wei_decompress(int curve, const u8* x_be, const u8* sign, size_t n, u8* out_xy, u8* ok, int nthreads) {
+    job j = {0};
+    j.fn = j_decompress; j.curve = curve; j.a = x_be; j.b = sign; j.o = out_xy; j.o2 = ok;
+    return run_jobs(&j, n, nthreads, 0);
+}
+long orc_bls12_381_g1_from_compressed(const u8* enc, size_t n, int check_subgroup, u8* out_xy, u8* ok, int nthreads) {
+    job j = {0};
+    j.fn = j_bls_from_compressed; j.mode = check_subgroup; j.a = enc; j.o = out_xy; j.o2 = ok;
+    return run_jobs(&j, n, nthreads, 0);
+}
+long orc_bls12_381_g1_to_compressed(const u8* xy, const u8* inf, size_t n, u8* enc, int nthreads) {
+    job j = {0};
+    j.fn = j_bls_to_compressed; j.a = xy; j.c = inf; j.o = enc;
+    return run_jobs(&j, n, nthreads, 0);
+}
 void orc_ed25519_comb_entry(int i, int j, u8* xy_le) {
     orc_init();
     ge_to_affine_bytes(xy_le, &ED_COMB[i][j]);

@@ -402,6 +402,46 @@ static int T(pt_from_xy_be)(const T(curve)* c, T(pt)* r, const u8* xy) {
     T(f_add)(F, &rr, &rr, &c->b);
     return T(f_eq)(&l, &rr);
 }
+/* FieldElement::sqrt (p256r1.rs:68, p384r1.rs:71, bls12_381/fp.rs:64): candidate = a^((p+1)/4)
+ * (all three primes are 3 mod 4; the reference walks per-prime addition chains / `power`, the
+ * value is the same), present iff candidate^2 == a. */
+static int T(f_sqrt)(const T(field)* f, T(fe)* r, const T(fe)* a) {
+    u64 e[NL], one[NL];
+    for (int i = 0; i < NL; i++) one[i] = 0;
+    one[0] = 1;
+    T(add_raw)(e, f->p, one);                  /* p + 1 < 2^(64 NL) for these primes */
+    for (int i = 0; i < NL; i++) e[i] = (e[i] >> 2) | (i + 1 < NL ? e[i + 1] << 62 : 0);
+    T(fe) acc = f->r1, chk;
+    for (int i = NL * 64 - 1; i >= 0; i--) {
+        T(f_sqr)(f, &acc, &acc);
+        if ((e[i / 64] >> (i % 64)) & 1) T(f_mul)(f, &acc, &acc, a);
+    }
+    T(f_sqr)(f, &chk, &acc);
+    *r = acc;
+    return T(f_eq)(&chk, a);
+}
+/* FieldElement::sign (field_macros.rs:557): bit 0 of the canonical value */
+static int T(f_odd)(const T(field)* f, const T(fe)* a) {
+    u64 w[NL];
+    T(f_to_raw)(f, w, a);
+    return (int)(w[0] & 1);
+}
+/* affine::Point::decompress (affine.rs:48-60): y^2 = x^3 + a x + b, root of the requested parity */
+static int T(pt_decompress)(const T(curve)* c, T(fe)* y, const T(fe)* x, int want_odd) {
+    const T(field)* F = &c->fp;
+    T(fe) rr, t;
+    T(f_mul)(F, &rr, x, x);
+    T(f_mul)(F, &rr, &rr, x);
+    if (!c->a0) {
+        T(f_add)(F, &t, x, x);
+        T(f_add)(F, &t, &t, x);
+        T(f_sub)(F, &rr, &rr, &t);
+    }
+    T(f_add)(F, &rr, &rr, &c->b);
+    int present = T(f_sqrt)(F, y, &rr);
+    if (T(f_odd)(F, y) != (want_odd ? 1 : 0)) T(f_neg)(F, y, y);
+    return present;
+}
 static void T(curve_init)(T(curve)* c, const u8* p_be, const u8* n_be, const u8* b_be, const u8* gx_be, const u8* gy_be,
                           int fbytes, int sbytes, int a0) {
     memset(c, 0, sizeof *c);

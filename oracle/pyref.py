@@ -322,6 +322,72 @@ def wei_mul_base(curve, k_be):
     return wei_mul(c, k_be, c.enc(c.G))
 
 
+def wei_decompress(curve, x_be, sign):
+    """PointAffine::decompress(&x, sign) (src/curve/affine.rs:48, fiat/curve_macros.rs:221):
+    y = sqrt(x^3 + a x + b) = (..)^((p+1)/4) (p256r1.rs:68, p384r1.rs:71, bls12_381/fp.rs:64; all three
+    primes are 3 mod 4), present iff y^2 is the right-hand side; the root with the requested parity
+    (Sign::Positive = even, Negative = odd of the canonical value, field_macros.rs:557).
+    x_be must be canonical (FieldElement::from_bytes -> None otherwise, field_macros.rs:15).
+    Returns x || y bytes, or None."""
+    c = WCURVES[curve] if isinstance(curve, str) else curve
+    x = int.from_bytes(x_be, "big")
+    if x >= c.p:
+        return None
+    yy = (x * x * x + c.a * x + c.b) % c.p
+    y = pow(yy, (c.p + 1) // 4, c.p)
+    if y * y % c.p != yy:
+        return None
+    if (y & 1) != (1 if sign else 0):
+        y = (-y) % c.p
+    return c.enc((x, y))
+
+
+BLS_X_ABS = 0xd201000000010000  # |x|, the BLS12-381 seed (params/bls12_381.rs)
+
+
+def bls_g1_in_subgroup(P):
+    """PointAffine::is_in_subgroup (bls12_381/g1.rs:105), by the DEFINITION [r]P = infinity rather
+    than the reference's endomorphism test: same predicate, independent computation."""
+    return BLSG1.mul(BLSG1.n, P) is None
+
+
+def bls_g1_from_compressed(enc, check_subgroup=True):
+    """PointAffine::from_compressed / from_compressed_oncurve_only (bls12_381/serialize.rs:286-321 with
+    read_compressed_flags :117 and read_compressed_affine :172): 48 bytes -> x || y (96 bytes) or None.
+    The identity encoding is None as well (the affine type cannot hold it)."""
+    c = BLSG1
+    flags = enc[0] & 0xE0
+    if not flags & 0x80:
+        return None
+    if flags & 0x40:
+        return None  # infinity (canonical or not): no affine point either way
+    sort = 1 if flags & 0x20 else 0
+    x = int.from_bytes(bytes([enc[0] & 0x1F]) + bytes(enc[1:]), "big")
+    if x >= c.p:
+        return None
+    yy = (x * x * x + c.b) % c.p
+    y = pow(yy, (c.p + 1) // 4, c.p)
+    if y * y % c.p != yy:
+        return None
+    if (1 if y > (c.p - 1) // 2 else 0) != sort:
+        y = (-y) % c.p
+    if check_subgroup and not bls_g1_in_subgroup((x, y)):
+        return None
+    return c.enc((x, y))
+
+
+def bls_g1_to_compressed(xy_be, inf=0):
+    """Point::to_compressed (serialize.rs:400-420): x with the compression flag and the sort flag
+    (y > (p-1)/2); the identity is 0xc0 followed by zeros."""
+    c = BLSG1
+    if inf:
+        return bytes([0xC0]) + bytes(47)
+    x, y = c.dec(xy_be)
+    out = bytearray(x.to_bytes(48, "big"))
+    out[0] |= 0x80 | (0x20 if y > (c.p - 1) // 2 else 0)
+    return bytes(out)
+
+
 def ecdsa_verify_hashed(curve, q_xy_be, z_be, rs_be):
     """verify_hashed (protocol/ecdsa.rs:205-222); Signature::from_bytes (:399) rejects zero or
     non-canonical r, s; z is reduced mod n as digest_to_scalar (:340) would."""

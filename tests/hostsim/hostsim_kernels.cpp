@@ -187,3 +187,21 @@ extern "C" unsigned long long hs_ecdsa_verify(int curve, const u32* q, const u32
     if (curve == 0) return ecdsa_run<CurveP256>(q, z, rs, n, ok);
     return ecdsa_run<CurveP384>(q, z, rs, n, ok);
 }
+
+// ---- kernels3: PointAffine::decompress, BLS12-381 G1 standard encodings ---------------------
+#include "../../eccoxide_b200/csrc/kernels3.cuh"
+extern "C" void hs_wei_decompress(int curve, const u32* x, const unsigned char* sign, size_t n, u32* out, unsigned char* ok) {
+    for (size_t i = 0; i < n; i++) {
+        switch (curve) {
+            case 0: wei_decompress_body<CurveP256>(i, x, sign, out, ok); break;
+            case 1: wei_decompress_body<CurveP384>(i, x, sign, out, ok); break;
+            case 2: wei_decompress_body<CurveBLSG1>(i, x, sign, out, ok); break;
+        }
+    }
+}
+extern "C" void hs_bls_g1_from_compressed(const u32* enc, size_t n, int check, u32* out, unsigned char* ok) {
+    for (size_t i = 0; i < n; i++) bls_g1_from_compressed_body(i, enc, check, out, ok);
+}
+extern "C" void hs_bls_g1_to_compressed(const u32* xy, const unsigned char* inf, size_t n, u32* enc) {
+    for (size_t i = 0; i < n; i++) bls_g1_to_compressed_body(i, xy, inf, enc);
+}

@@ -661,6 +661,93 @@ def test_host_entry_points_across_pipeline_chunks(ctx, coracle):
         ctx.set_option("chunk", 189440)
 
 
+# ---- wire formats either side of the path -------------------------------------------
+@pytest.mark.parametrize("curve", CURVES)
+def test_wei_decompress(ctx, coracle, golden, curve):
+    """PointAffine::decompress (affine.rs:48) through the C ABI: x-coordinates of random points with
+    both parities, the NIST KAT points, random field elements (about half are not x-coordinates),
+    x = 0, x = p, x = 2^(8 FB) - 1; bit-exact with the oracle, zero bytes where the reference gives None."""
+    c = R.WCURVES[curve]
+    g = rng(SEEDS["p256"] + 31 + len(curve))
+    n = 3000
+    pts = wei_points(curve, g, n)
+    x = np.ascontiguousarray(pts[:, : c.fbytes])
+    sign = g.integers(0, 2, n).astype(np.uint8)
+    rnd = rows([(int.from_bytes(g.bytes(c.fbytes + 8), "big") % c.p).to_bytes(c.fbytes, "big") for _ in range(200)])
+    x[100:300] = rnd
+    x[0] = 0
+    x[1] = np.frombuffer(c.p.to_bytes(c.fbytes, "big"), dtype=np.uint8)
+    x[2] = 0xFF
+    if curve != "bls12_381_g1":
+        kat = golden["nist_p256" if curve == "p256r1" else "nist_p384"]
+        for i, e in enumerate(kat[:20]):
+            x[10 + i] = np.frombuffer(bytes.fromhex(e["x"]), dtype=np.uint8)
+            sign[10 + i] = int(e["y"], 16) & 1
+    got, ok = ctx.wei_decompress(curve, x, sign)
+    exp, eok = coracle.wei_decompress(curve, x, sign, threads(coracle))
+    assert np.array_equal(ok, eok) and np.array_equal(got, exp)
+    assert not ok[1] and not ok[2] and not got[1].any() and 40 < int((~ok[100:300]).sum()) < 160
+    if curve != "bls12_381_g1":
+        for i, e in enumerate(kat[:20]):
+            assert ok[10 + i] and got[10 + i].tobytes().hex() == e["x"] + e["y"]
+    # the points the library itself produces decompress back to themselves
+    assert ok[300:].all() and np.array_equal(got[300:][sign[300:] == (pts[300:, -1] & 1)], pts[300:][sign[300:] == (pts[300:, -1] & 1)])
+    assert ctx.wei_decompress(curve, np.zeros((0, c.fbytes), dtype=np.uint8), np.zeros(0, dtype=np.uint8))[0].shape == (0, 2 * c.fbytes)
+
+
+def test_bls_g1_standard_encodings(ctx, coracle, golden):
+    """bls12_381/serialize.rs through the C ABI: the reference's compressed KATs (g1.rs:605-680) and
+    OFF_SUBGROUP encodings (:313-368), flag misuse, and a batch of library-produced points mixed with
+    raw curve points outside G1: to_compressed -> from_compressed round trip, subgroup check on/off."""
+    c = R.BLSG1
+    v = golden["bls12_381_g1"]
+    kat = [bytes.fromhex(e["bytes"]) for e in v["compressed"]]
+    off_c = [bytes.fromhex(o["compressed"]) for o in v["off_subgroup"]]
+    off_u = [bytes.fromhex(o["uncompressed"]) for o in v["off_subgroup"]]
+    g0 = kat[0]
+    bad = [bytes([g0[0] & 0x7F]) + g0[1:], bytes([0xC0]) + bytes(47), bytes([0xE0]) + bytes(47), bytes([0xC0]) + bytes(46) + b"\x01",
+           bytes([0x80 | (c.p >> 376)]) + (c.p & ((1 << 376) - 1)).to_bytes(47, "big")]
+    enc = rows(kat + off_c + bad)
+    out, ok = ctx.bls12_381_g1_from_compressed(enc, True)
+    assert list(ok) == [True] * 5 + [False] * (3 + len(bad)) and not out[5:].any()
+    for i, e in enumerate(v["compressed"]):
+        assert out[i].tobytes() == R.wei_mul_base(c, e["k"].to_bytes(32, "big"))[0]
+    out, ok = ctx.bls12_381_g1_from_compressed(enc, False)
+    assert list(ok) == [True] * 8 + [False] * len(bad)
+    assert [out[5 + i].tobytes() for i in range(3)] == off_u
+    assert [r.tobytes() for r in ctx.bls12_381_g1_to_compressed(rows(off_u))] == off_c
+    # batch: k*G from the comb (in G1), every 7th replaced by a raw curve point (outside G1 almost surely)
+    g = rng(4711)
+    n = 2000
+    ks = scalars_mod(g, n, c.n, 32, "big")
+    ks[3] = 0
+    pts, inf = ctx.wei_mul_base("bls12_381_g1", ks)
+    raw = []
+    x = 1000
+    while len(raw) < (n + 6) // 7:
+        x += 1
+        rhs = (x**3 + 4) % c.p
+        y = pow(rhs, (c.p + 1) // 4, c.p)
+        if y * y % c.p == rhs:
+            raw.append(c.enc((x, y if len(raw) & 1 else c.p - y)))
+    pts[::7] = rows(raw)
+    inf[::7] = False
+    inf[3] = True
+    enc = ctx.bls12_381_g1_to_compressed(pts, inf)
+    assert np.array_equal(enc, coracle.bls12_381_g1_to_compressed(pts, inf, threads(coracle)))
+    assert enc[3].tobytes() == bytes([0xC0]) + bytes(47)
+    for check in (True, False):
+        got, ok = ctx.bls12_381_g1_from_compressed(enc, check)
+        exp, eok = coracle.bls12_381_g1_from_compressed(enc, check, threads(coracle))
+        assert np.array_equal(ok, eok) and np.array_equal(got, exp), check
+        fin = ~inf
+        assert not ok[3]
+        if check:
+            assert not ok[::7].any() and ok[fin & (np.arange(n) % 7 != 0)].all()
+        else:
+            assert ok[fin].all() and np.array_equal(got[fin], pts[fin])
+
+
 @pytest.mark.parametrize("mode", [0, 2])
 def test_batch_inversion_forms_agree(ctx, coracle, mode):
     """Option inv_block: one inversion per thread (0) or one per block (2) for EVERY field — the

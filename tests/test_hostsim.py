@@ -172,6 +172,75 @@ def test_wei_mul(hs, golden, coracle, cid, curve):
         assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
 
 
+@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1"), (2, "bls12_381_g1")])
+def test_wei_decompress(hs, coracle, cid, curve):
+    """Device code of PointAffine::decompress (kernels3.cuh) against the oracle: both parities, an x
+    with a non-square right-hand side, x = 0, x >= p."""
+    _, k = hs
+    c = R.WCURVES[curve]
+    g = rng(60 + cid)
+    n = 40
+    pts = wei_points(curve, g, n)
+    x = np.ascontiguousarray(pts[:, : c.fbytes])
+    sign = (g.integers(0, 2, n)).astype(np.uint8)
+    x[n - 3] = 0
+    x[n - 2] = np.frombuffer(c.p.to_bytes(c.fbytes, "big"), dtype=np.uint8)
+    x[n - 1] = 0xFF
+    for i in range(0, 12):  # random field elements: about half are not x-coordinates
+        x[i] = np.frombuffer((int.from_bytes(g.bytes(c.fbytes + 8), "big") % c.p).to_bytes(c.fbytes, "big"), dtype=np.uint8)
+    out = np.zeros((n, 2 * c.fbytes), dtype=np.uint8)
+    ok = np.zeros(n, dtype=np.uint8)
+    k.hs_wei_decompress(cid, p(x), p(sign), ctypes.c_size_t(n), p(out), p(ok))
+    exp, eok = coracle.wei_decompress(curve, x, sign)
+    assert np.array_equal(ok.astype(bool), eok) and np.array_equal(out, exp)
+    assert eok.any() and not eok.all()
+    for i in (0, 5, 20):
+        want = R.wei_decompress(curve, x[i].tobytes(), int(sign[i]))
+        assert (out[i].tobytes() if ok[i] else None) == want
+
+
+def test_bls_g1_encodings(hs, coracle, golden):
+    """Device code of from_compressed / to_compressed / is_in_subgroup against the reference's KATs
+    (g1.rs:605-680, OFF_SUBGROUP :313-368) and the oracle on random curve points inside and outside G1."""
+    _, k = hs
+    c = R.BLSG1
+    v = golden["bls12_381_g1"]
+    encs = [bytes.fromhex(e["bytes"]) for e in v["compressed"]] + [bytes.fromhex(o["compressed"]) for o in v["off_subgroup"]]
+    x = 300
+    while len(encs) < 16:  # raw curve points (outside G1) and their cofactor-cleared images (inside)
+        x += 1
+        rhs = (x**3 + 4) % c.p
+        y = pow(rhs, (c.p + 1) // 4, c.p)
+        if y * y % c.p == rhs:
+            encs.append(R.bls_g1_to_compressed(c.enc((x, y))))
+            encs.append(R.bls_g1_to_compressed(c.enc(c.mul(0xd201000000010001, (x, y)))))
+    g0 = encs[0]
+    encs += [bytes([g0[0] & 0x7F]) + g0[1:], bytes([0xC0]) + bytes(47), bytes([0xE0]) + bytes(47), bytes([g0[0] ^ 0x20]) + g0[1:],
+             bytes([0x80 | (c.p >> 376)]) + (c.p & ((1 << 376) - 1)).to_bytes(47, "big")]
+    e = rows(encs)
+    n = e.shape[0]
+    for check in (1, 0):
+        out = np.zeros((n, 96), dtype=np.uint8)
+        ok = np.zeros(n, dtype=np.uint8)
+        k.hs_bls_g1_from_compressed(p(e), ctypes.c_size_t(n), check, p(out), p(ok))
+        exp, eok = coracle.bls12_381_g1_from_compressed(e, bool(check))
+        assert np.array_equal(ok.astype(bool), eok) and np.array_equal(out, exp), check
+        for i in range(n):
+            assert (out[i].tobytes() if ok[i] else None) == R.bls_g1_from_compressed(encs[i], bool(check)), (i, check)
+    assert list(ok[5:8]) == [1, 1, 1]                    # OFF_SUBGROUP decodes with _oncurve_only ...
+    uncompressed = [bytes.fromhex(o["uncompressed"]) for o in v["off_subgroup"]]
+    assert [out[5 + i].tobytes() for i in range(3)] == uncompressed
+    # to_compressed inverts it, identity included
+    good = ok.astype(bool)
+    inf = np.zeros(n, dtype=np.uint8)
+    inf[-1] = 1
+    enc2 = np.zeros((n, 48), dtype=np.uint8)
+    k.hs_bls_g1_to_compressed(p(out), p(inf), ctypes.c_size_t(n), p(enc2))
+    assert np.array_equal(enc2[good], e[good])
+    assert enc2[-1].tobytes() == bytes([0xC0]) + bytes(47)
+    assert np.array_equal(enc2, coracle.bls12_381_g1_to_compressed(out, inf))
+
+
 @pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1")])
 def test_ecdsa(hs, coracle, cid, curve):
     _, k = hs

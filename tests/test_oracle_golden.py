@@ -294,6 +294,108 @@ def test_bls_off_subgroup_points(coracle):
         assert (out[i].tobytes(), int(inf[i])) == R.wei_mul(c, ks[i], c.enc(p))
 
 
+# ---- wire formats either side of the path -------------------------------------------
+def _non_residue_x(c, start=2):
+    x = start
+    while pow((x**3 + c.a * x + c.b) % c.p, (c.p - 1) // 2, c.p) != c.p - 1:
+        x += 1
+    return x
+
+
+@pytest.mark.parametrize("curve", CURVES)
+def test_decompress_roundtrip_and_rejects(golden, coracle, curve):
+    """compress_decompress_roundtrip / decompress_rejects_invalid_x (fiat/curve_macros.rs:429-475):
+    both parities recover the point and its negation; an x whose right-hand side is not a square and a
+    non-canonical x give None.  The NIST KAT points pin the byte values for the SEC curves."""
+    c = R.WCURVES[curve]
+    g = rng(77 + len(curve))
+    pts = [c.mul(int.from_bytes(g.bytes(40), "little") % c.n, c.G) for _ in range(12)]
+    if curve != "bls12_381_g1":
+        kat = golden["nist_p256" if curve == "p256r1" else "nist_p384"]
+        pts += [(int(e["x"], 16), int(e["y"], 16)) for e in kat[:10]]
+    xs, signs, want = [], [], []
+    for P in pts:
+        for Q in (P, c.neg(P)):
+            xs.append(Q[0].to_bytes(c.fbytes, "big"))
+            signs.append(Q[1] & 1)
+            want.append(c.enc(Q))
+    bad_x = _non_residue_x(c)
+    xs += [bad_x.to_bytes(c.fbytes, "big"), c.p.to_bytes(c.fbytes, "big"), b"\xff" * c.fbytes]
+    signs += [0, 1, 0]
+    out, ok = coracle.wei_decompress(curve, rows(xs), np.array(signs, dtype=np.uint8))
+    assert ok[: len(want)].all() and not ok[len(want):].any() and not out[len(want):].any()
+    for i, w in enumerate(want):
+        assert out[i].tobytes() == w == R.wei_decompress(curve, xs[i], signs[i])
+    for i in range(len(want), len(xs)):
+        assert R.wei_decompress(curve, xs[i], signs[i]) is None
+
+
+def test_bls_g1_compressed_format_kats(golden, coracle):
+    """serialization_kat (g1.rs:605-680) and off_subgroup_kat (:313-368, :481-520): to_compressed of k*G
+    is the reference's bytes, from_compressed inverts it; the OFF_SUBGROUP encodings decode with
+    _oncurve_only to the listed uncompressed bytes and are refused by the checking decoder; flag
+    misuse, the identity and non-canonical x are None (serialize.rs:117-136, :172-190)."""
+    v = golden["bls12_381_g1"]
+    c = R.BLSG1
+    encs = [bytes.fromhex(e["bytes"]) for e in v["compressed"]]
+    xy = [R.wei_mul_base(c, e["k"].to_bytes(32, "big"))[0] for e in v["compressed"]]
+    assert [coracle.bls12_381_g1_to_compressed(rows(xy))[i].tobytes() for i in range(len(xy))] == encs
+    out, ok = coracle.bls12_381_g1_from_compressed(rows(encs), True)
+    assert ok.all() and [out[i].tobytes() for i in range(len(xy))] == xy
+    inf_enc = coracle.bls12_381_g1_to_compressed(np.zeros((1, 96), dtype=np.uint8), np.ones(1, dtype=np.uint8))[0].tobytes()
+    assert inf_enc == bytes([0xC0]) + bytes(47) == R.bls_g1_to_compressed(bytes(96), 1)
+    off_c = [bytes.fromhex(o["compressed"]) for o in v["off_subgroup"]]
+    off_u = [bytes.fromhex(o["uncompressed"]) for o in v["off_subgroup"]]
+    out, ok = coracle.bls12_381_g1_from_compressed(rows(off_c), False)
+    assert ok.all() and [out[i].tobytes() for i in range(len(off_u))] == off_u
+    out, ok = coracle.bls12_381_g1_from_compressed(rows(off_c), True)
+    assert not ok.any() and not out.any()
+    assert [coracle.bls12_381_g1_to_compressed(rows(off_u))[i].tobytes() for i in range(len(off_u))] == off_c
+    for i, e in enumerate(off_c):
+        assert R.bls_g1_from_compressed(e, False) == off_u[i] and R.bls_g1_from_compressed(e, True) is None
+    g0 = bytearray(encs[0])
+    bad = [bytes([g0[0] & 0x7F]) + bytes(g0[1:]),            # compression flag clear
+           inf_enc,                                          # the identity: no affine point
+           bytes([0xE0]) + bytes(47),                        # infinity with the sort flag
+           bytes([0xC0]) + bytes(46) + b"\x01",              # infinity with a payload
+           bytes([0x80 | (c.p >> 376)]) + (c.p & ((1 << 376) - 1)).to_bytes(47, "big"),   # x = p
+           bytes([0x80]) + _non_residue_x(c).to_bytes(48, "big")[1:]]
+    out, ok = coracle.bls12_381_g1_from_compressed(rows(bad), True)
+    assert not ok.any() and not out.any()
+    assert all(R.bls_g1_from_compressed(b, True) is None for b in bad)
+    # the sort flag picks the other root
+    flipped = bytes([g0[0] ^ 0x20]) + bytes(g0[1:])
+    out, ok = coracle.bls12_381_g1_from_compressed(rows([flipped]), True)
+    assert ok[0] and out[0].tobytes() == c.enc(c.neg(c.G)) == R.bls_g1_from_compressed(flipped, True)
+    # beta is derived in the oracle; the reference's constant pins it (params/bls12_381.rs:100)
+    assert coracle.bls12_381_beta().hex() == golden["params"]["bls12_381_g1"]["beta"]
+
+
+def test_bls_g1_subgroup_check_agrees_with_the_definition(coracle):
+    """is_in_subgroup (g1.rs:105, endomorphism test in the C oracle) against [r]P = infinity (big-int
+    oracle) on random curve points: cofactor-cleared ones are in, raw ones (almost surely) are not."""
+    c = R.BLSG1
+    h_eff = 0xd201000000010001
+    encs, want = [], []
+    x = 100
+    while len(encs) < 10:
+        x += 1
+        rhs = (x**3 + 4) % c.p
+        y = pow(rhs, (c.p + 1) // 4, c.p)
+        if y * y % c.p != rhs:
+            continue
+        for P in ((x, y), c.mul(h_eff, (x, y))):
+            encs.append(R.bls_g1_to_compressed(c.enc(P)))
+            want.append(R.bls_g1_in_subgroup(P))
+    assert any(want) and not all(want)
+    out, ok = coracle.bls12_381_g1_from_compressed(rows(encs), True)
+    assert list(ok) == want
+    out2, ok2 = coracle.bls12_381_g1_from_compressed(rows(encs), False)
+    assert ok2.all()
+    for i, e in enumerate(encs):
+        assert out2[i].tobytes() == R.bls_g1_from_compressed(e, False)
+
+
 # ---- Weierstrass edge scalars, identity handling, cross-algorithm agreement ----------------------
 @pytest.mark.parametrize("curve", CURVES)
 def test_weierstrass_edge_scalars(golden, coracle, curve):

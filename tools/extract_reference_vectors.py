@@ -14,7 +14,7 @@ Sources (paths relative to /root/reference):
   src/curve/curve25519.rs:1629-1643 ladder u-coordinates of k*(u=9), k = 2, 5, 7
   src/protocol/ed25519.rs:271-290   RFC 8032 §7.1 TEST 1-3
   src/protocol/ecdsa.rs:808-878     RFC 6979 A.2.5 (P-256), A.2.6 (P-384)
-  src/curve/bls12_381/g1.rs:605-680 compressed / uncompressed k*G
+  src/curve/bls12_381/g1.rs:605-680 compressed / uncompressed k*G; :313-368 OFF_SUBGROUP encodings
   src/protocol/x448.rs:116-160      RFC 7748 §5.2 / §6.2
   src/params/comb/*.rs              generator comb tables: SHA-256 of the whole table + sample entries
   src/params/sec2.rs, bls12_381.rs  domain parameters
@@ -124,6 +124,17 @@ def kv_pairs(s):
 
 out["bls12_381_g1"] = {"compressed": kv_pairs(comp_seg), "uncompressed": kv_pairs(uncomp_seg)}
 assert len(out["bls12_381_g1"]["compressed"]) == 5 and len(out["bls12_381_g1"]["uncompressed"]) == 2
+# points of the curve outside the prime-order subgroup: (compressed, uncompressed) pairs (g1.rs:313-368 OFF_SUBGROUP)
+i1 = g1.index("const OFF_SUBGROUP")
+i1 = g1.index("= &[", i1) + 4
+off_seg = g1[i1:g1.index("\n        ];", i1)]
+offs = []
+for m in re.finditer(r"\(\s*\[(.*?)\],\s*\[(.*?)\],\s*\)", off_seg, re.S):
+    c, u = bytes_of(m.group(1)), bytes_of(m.group(2))
+    assert len(c) == 48 and len(u) == 96
+    offs.append({"compressed": c.hex(), "uncompressed": u.hex()})
+assert len(offs) >= 2
+out["bls12_381_g1"]["off_subgroup"] = offs
 
 # ---- X448 ----------------------------------------------------------------------------------
 x4 = read("src/protocol/x448.rs")
@@ -156,7 +167,7 @@ for curve in ("p256r1", "p384r1"):
     at = sec2.index("pub mod %s {" % curve)
     params[curve] = {n.lower().replace("_bytes", ""): const_bytes(sec2, n, at).hex() for n in ("P_BYTES", "ORDER_BYTES", "B_BYTES", "GX_BYTES", "GY_BYTES")}
 bl = read("src/params/bls12_381.rs")
-params["bls12_381_g1"] = {n.lower().replace("_bytes", ""): const_bytes(bl, n).hex() for n in ("P_BYTES", "ORDER_BYTES", "B_BYTES", "GX_BYTES", "GY_BYTES")}
+params["bls12_381_g1"] = {n.lower().replace("_bytes", ""): const_bytes(bl, n).hex() for n in ("P_BYTES", "ORDER_BYTES", "B_BYTES", "GX_BYTES", "GY_BYTES", "BETA_BYTES")}
 out["params"] = params
 
 os.makedirs(os.path.dirname(OUT), exist_ok=True)

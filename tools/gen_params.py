@@ -87,6 +87,46 @@ def mont(x, p, n):
     return (x << (32 * n)) % p
 
 
+def bls_beta():
+    """The cube root of unity beta in Fp with (beta x, y) = [-x^2](x, y) on G1 (x = the curve seed):
+    the reference pins its BETA the same way (bls12_381/g1.rs:440-450); tests compare the bytes."""
+    p, r = BLS_P, BLS_R
+
+    def add(P, Q):
+        if P is None:
+            return Q
+        if Q is None:
+            return P
+        if P[0] == Q[0]:
+            if (P[1] + Q[1]) % p == 0:
+                return None
+            lam = 3 * P[0] * P[0] * pow(2 * P[1], -1, p) % p
+        else:
+            lam = (Q[1] - P[1]) * pow(Q[0] - P[0], -1, p) % p
+        x = (lam * lam - P[0] - Q[0]) % p
+        return (x, (lam * (P[0] - x) - P[1]) % p)
+
+    def mul(k, P):
+        R = None
+        while k:
+            if k & 1:
+                R = add(R, P)
+            P = add(P, P)
+            k >>= 1
+        return R
+
+    G = (BLS_GX, BLS_GY)
+    target = mul((-(0xd201000000010000 ** 2)) % r, G)
+    g = 2
+    while pow(g, (p - 1) // 3, p) == 1:
+        g += 1
+    beta = pow(g, (p - 1) // 3, p)
+    for cand in (beta, beta * beta % p):
+        if (cand * G[0] % p, G[1]) == target:
+            return cand
+    raise AssertionError("no cube root of unity acts as [-x^2] on G1")
+
+
 def main():
     out = ("// GENERATED by tools/gen_params.py — do not edit.\n"
            "// Montgomery-domain constants for the Weierstrass curves of the batch path\n"
@@ -114,6 +154,12 @@ def main():
         out += arr(cname + "_B3", mont(3 * b % p, p, n), n)
         out += arr(cname + "_GX", mont(gx, p, n), n)
         out += arr(cname + "_GY", mont(gy, p, n), n)
+        assert p % 4 == 3
+        out += "// (p + 1) / 4: the square-root exponent (p = 3 mod 4)\n"
+        out += arr(cname + "_SQRT_E", (p + 1) // 4, n)
+        if cname == "BLSG1":
+            out += "// beta: (beta x, y) = [-x^2](x, y) on G1 (subgroup test, bls12_381/g1.rs:55, :105), Montgomery domain\n"
+            out += arr("BLSG1_BETA", mont(bls_beta(), p, n), n)
         out += "\n"
     out += "}  // namespace ecb\n"
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "eccoxide_b200", "csrc", "params_gen.cuh")
