@@ -5,9 +5,12 @@
 //! Intended location in the reference crate: `src/batch/mod.rs` (feature `gpu-batch`).
 use super::ffi::*;
 use crate::curve::curve25519::{FieldElement as Fe25519, Point as EdPoint, Scalar as EdScalar};
+use crate::curve::bls12_381::g1;
+use crate::curve::field::Sign;
 use crate::curve::sec2::p256r1;
 use crate::protocol::ecdsa;
 use std::ffi::CStr;
+use std::os::raw::c_int;
 use std::ptr;
 
 #[derive(Debug)]
@@ -116,6 +119,53 @@ impl BatchContext {
                 let y = p256r1::FieldElement::from_bytes(c[32..].try_into().unwrap())?;
                 p256r1::PointAffine::from_coordinate(&x, &y)
             })
+            .collect())
+    }
+
+    /// Batch sibling of `p256r1::PointAffine::decompress(&x, sign)` (src/curve/fiat/curve_macros.rs:221 ->
+    /// src/curve/affine.rs:48).  `None` where the reference's `CtOption` is empty.
+    pub fn p256r1_decompress_batch(&self, xs: &[p256r1::FieldElement], signs: &[Sign]) -> Result<Vec<Option<p256r1::PointAffine>>, BatchError> {
+        if xs.len() != signs.len() {
+            return Err(BatchError::InvalidArgument("length mismatch".into()));
+        }
+        let n = xs.len();
+        let mut xb = Vec::with_capacity(32 * n);
+        for x in xs {
+            xb.extend_from_slice(&x.to_bytes());
+        }
+        let sg: Vec<u8> = signs.iter().map(|s| matches!(s, Sign::Negative) as u8).collect();
+        let (mut out, mut ok) = (vec![0u8; 64 * n], vec![0u8; n]);
+        let rc = unsafe { ecb_wei_decompress(self.ctx, ECB_CURVE_P256R1, xb.as_ptr(), sg.as_ptr(), n, out.as_mut_ptr(), ok.as_mut_ptr()) };
+        self.check(rc, usize::MAX)?;
+        Ok(out
+            .chunks_exact(64)
+            .zip(ok)
+            .map(|(c, present)| {
+                if present == 0 {
+                    return None;
+                }
+                let x = p256r1::FieldElement::from_bytes(c[..32].try_into().unwrap())?;
+                let y = p256r1::FieldElement::from_bytes(c[32..].try_into().unwrap())?;
+                p256r1::PointAffine::from_coordinate(&x, &y)
+            })
+            .collect())
+    }
+
+    /// Batch sibling of `bls12_381::g1::PointAffine::from_compressed` (src/curve/bls12_381/serialize.rs:286;
+    /// `check_subgroup = false`: `from_compressed_oncurve_only`, :310).  The device has already validated
+    /// flags, canonicity, the curve equation and (optionally) subgroup membership, so the accepted
+    /// coordinates are rebuilt with the unchecked constructor path (`from_uncompressed_oncurve_only`).
+    pub fn g1_from_compressed_batch(&self, encodings: &[[u8; 48]], check_subgroup: bool) -> Result<Vec<Option<g1::PointAffine>>, BatchError> {
+        let n = encodings.len();
+        let (mut out, mut ok) = (vec![0u8; 96 * n], vec![0u8; n]);
+        let rc = unsafe {
+            ecb_bls12_381_g1_from_compressed(self.ctx, encodings.as_ptr() as *const u8, n, check_subgroup as c_int, out.as_mut_ptr(), ok.as_mut_ptr())
+        };
+        self.check(rc, usize::MAX)?;
+        Ok(out
+            .chunks_exact(96)
+            .zip(ok)
+            .map(|(c, present)| if present == 0 { None } else { g1::PointAffine::from_uncompressed_oncurve_only(c.try_into().unwrap()) })
             .collect())
     }
 
