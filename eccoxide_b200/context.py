@@ -141,6 +141,33 @@ class Context:
         self._check(self._lib.ecb_ed25519_verify(self._ctx, _p(a), _p(blob), _p(off), _p(s), n, _p(ok)))
         return ok.astype(bool)
 
+    def ed25519_public_from_seed(self, seeds, out=None):
+        """ed25519 SecretKey::public_key over a batch of 32-byte seeds (not constant-time)."""
+        sd = _rows(seeds, 32, "seeds")
+        n = sd.shape[0]
+        out = _out(out, (n, 32))
+        self._check(self._lib.ecb_ed25519_public_from_seed(self._ctx, _p(sd), n, _p(out)))
+        return out
+
+    def ed25519_sign(self, seeds, msgs, pub=None, out=None):
+        """ed25519 Keypair::sign (pub given) / SecretKey::sign (pub None) on raw, ragged messages
+        (not constant-time): n x 64 bytes R || S."""
+        sd = _rows(seeds, 32, "seeds")
+        n = sd.shape[0]
+        if len(msgs) != n:
+            raise ValueError("count mismatch")
+        pb = None
+        if pub is not None:
+            pb = _rows(pub, 32, "pub")
+            if pb.shape[0] != n:
+                raise ValueError("count mismatch")
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(bytes(m) for m in msgs) + b"\0", dtype=np.uint8)
+        out = _out(out, (n, 64))
+        self._check(self._lib.ecb_ed25519_sign(self._ctx, _p(sd), _p(pb), _p(blob), _p(off), n, _p(out)))
+        return out
+
     # -- X25519 / X448 ------------------------------------------------------------------------
     def x25519(self, k, u, out=None):
         k = _rows(k, 32, "k")

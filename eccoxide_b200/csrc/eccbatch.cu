@@ -460,6 +460,79 @@ int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, 
         if (rc[i] != ECB_OK) return rc[i];
     return ECB_OK;
 }
+int ecb_ed25519_public_from_seed(ecb_ctx* ctx, const uint8_t* seeds, size_t n, uint8_t* pub) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!seeds || !pub)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{seeds, 32}}, {{pub, 32}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** out, size_t cn) {
+                           return dev_ed25519_public_from_seed(ctx, d, (const unsigned char*)in[0], cn, (u32*)out[0], s);
+                       });
+}
+// Ed25519 signing of raw messages (ragged input): the chunk loop of ecb_ed25519_verify with seeds and
+// (optional) public keys in, signatures out.
+int ecb_ed25519_sign(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
+                     uint8_t* sig) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!seeds || !msg_off || !sig)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    if (n == 0) return ECB_OK;
+    for (size_t i = 0; i < n; i++)
+        if (msg_off[i + 1] < msg_off[i]) return set_err(ctx, ECB_ERR_INVALID_ARG, "message offsets must be non-decreasing");
+    if (msg_off[n] > msg_off[0] && !msgs) return set_err(ctx, ECB_ERR_INVALID_ARG, "null message buffer");
+    int nd = (int)ctx->devs.size();
+    std::vector<int> rc(nd, ECB_OK);
+    auto worker = [&](int di) {
+        DevCtx& d = *ctx->devs[di];
+        size_t lo = n * (size_t)di / nd, hi = n * (size_t)(di + 1) / nd;
+        if (lo == hi) return;
+        std::lock_guard<std::mutex> g(d.mu);
+        auto body = [&]() -> int {
+            CU(cudaSetDevice(d.dev));
+            size_t ci = 0;
+            for (size_t c0 = lo; c0 < hi; c0 += ctx->opt_chunk, ci++) {
+                size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
+                Slot& sl = d.slots[ci % ECB_NSLOT];
+                if (sl.busy) {
+                    sl.busy = false;
+                    CU(cudaStreamSynchronize(sl.stream));
+                }
+                d.cur = &sl;
+                size_t mbytes = (size_t)(msg_off[c0 + cn] - msg_off[c0]);
+                TRY(ensure(ctx, sl.in[0], cn * 32));
+                if (pub) TRY(ensure(ctx, sl.in[1], cn * 32));
+                TRY(ensure(ctx, sl.in[2], (cn + 1) * sizeof(uint64_t)));
+                TRY(ensure(ctx, sl.in[3], mbytes + 16));
+                TRY(ensure(ctx, sl.out[0], cn * 64));
+                CU(cudaMemcpyAsync(sl.in[0].p, seeds + c0 * 32, cn * 32, cudaMemcpyHostToDevice, sl.stream));
+                if (pub) CU(cudaMemcpyAsync(sl.in[1].p, pub + c0 * 32, cn * 32, cudaMemcpyHostToDevice, sl.stream));
+                CU(cudaMemcpyAsync(sl.in[2].p, msg_off + c0, (cn + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, sl.stream));
+                if (mbytes) CU(cudaMemcpyAsync(sl.in[3].p, msgs + msg_off[c0], mbytes, cudaMemcpyHostToDevice, sl.stream));
+                const unsigned char* d_msgs = (const unsigned char*)sl.in[3].p - msg_off[c0];
+                TRY(dev_ed25519_sign(ctx, d, (const unsigned char*)sl.in[0].p, pub ? (const unsigned char*)sl.in[1].p : nullptr, d_msgs,
+                                     (const unsigned long long*)sl.in[2].p, cn, (unsigned char*)sl.out[0].p, sl.stream));
+                CU(cudaMemcpyAsync(sig + c0 * 64, sl.out[0].p, cn * 64, cudaMemcpyDeviceToHost, sl.stream));
+                sl.busy = true;
+            }
+            for (Slot& sl : d.slots) {
+                if (!sl.busy) continue;
+                sl.busy = false;
+                CU(cudaStreamSynchronize(sl.stream));
+            }
+            d.cur = &d.slots[0];
+            return ECB_OK;
+        };
+        rc[di] = body();
+    };
+    if (nd == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nd; i++) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < nd; i++)
+        if (rc[i] != ECB_OK) return rc[i];
+    return ECB_OK;
+}
 // ECDSA verification on raw messages (ragged input); layout of a chunk in the slot buffers:
 // in[0] = Q, in[1] = r || s, in[2] = offsets, aux2 (in[3]) = z, message bytes in `scratch2` (out[1]).
 int ecb_ecdsa_verify(ecb_ctx* ctx, int curve, int hash, const uint8_t* q_xy, const uint8_t* msgs, const uint64_t* msg_off,

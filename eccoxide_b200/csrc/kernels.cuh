@@ -488,8 +488,8 @@ struct FinEdXY {  // out: x_le || y_le, canonical (Point::to_affine + to_bytes_l
         st_words<8>(out + idx * 16 + 8, y.v);
     }
 };
-struct FinEdCompressed {  // out: encode_point (protocol/ed25519.rs:27)
-    const u32* planes; size_t n; u32* out;
+struct FinEdCompressed {  // out: encode_point (protocol/ed25519.rs:27); element idx at out + idx * stride words
+    const u32* planes; size_t n; u32* out; size_t stride = 8;
     ECB_DEV void pre(size_t idx) const { plane_prefetch<8>(planes, n, idx); plane_prefetch<8>(planes + 8 * n, n, idx); }
     ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
         fe25519 X, Y, x, y;
@@ -500,7 +500,7 @@ struct FinEdCompressed {  // out: encode_point (protocol/ed25519.rs:27)
         F::freeze(x, x);
         F::freeze(y, y);
         y.v[7] |= (x.v[0] & 1u) << 31;
-        st_words<8>(out + idx * 8, y.v);
+        st_words<8>(out + idx * stride, y.v);
     }
 };
 struct FinEdMontU {  // out: u = (1 + y) / (1 - y) = (Z + Y) / (Z - Y), little-endian canonical; 0 for the identity

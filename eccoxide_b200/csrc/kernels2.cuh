@@ -469,24 +469,9 @@ ECB_DEV u32 ed25519_decode(fe25519& x, fe25519& y, const u32* enc) {
     return ok;
 }
 
-// =======================================================================================
-// k = reduce_wide_le(SHA-512(R || A || M))  (src/protocol/ed25519.rs:21 reduce_wide_le, :139) and the
-// split of the 64-byte signature into R and S: the prologue of verification on raw messages.
-//   sig : n x 64 bytes R || S ; a_enc : n x 32 ; msgs + off : concatenated messages, message i is
-//   bytes [off[i], off[i+1]) ; outputs r_out, s_out, k_out : n x 32 bytes each
-// The 512-bit digest d = d_lo + 2^256 d_hi (little-endian) is reduced with three Montgomery products
-// in GF(l): d_hi 2^256 = mont(d_hi, R^2), d_lo = mont(mont(d_lo, R^2), 1) — CIOS accepts any 256-bit
-// first operand.
-// =======================================================================================
-ECB_DEV void ed25519_hash_k_body(size_t idx, const unsigned char* a_enc, const unsigned char* sig, const unsigned char* msgs,
-                                 const unsigned long long* off, u32* r_out, u32* s_out, u32* k_out) {
+// 64 little-endian bytes -> canonical scalar mod l (reduce_wide_le / init_from_wide_bytes_le)
+ECB_DEV void ed25519_reduce_wide(u32* out8, const unsigned char* dg) {
     typedef Mont<ED_FN> FL;
-    const unsigned char* R = sig + idx * 64;
-    const unsigned char* A = a_enc + idx * 32;
-    const unsigned char* M = msgs + off[idx];
-    size_t mlen = (size_t)(off[idx + 1] - off[idx]);
-    unsigned char dg[64];
-    sha512_bytes(dg, 64 + mlen, [&](size_t pos) -> unsigned char { return pos < 32 ? R[pos] : (pos < 64 ? A[pos - 32] : M[pos - 64]); });
     FL::el lo, hi, r2, one, t;
     ECB_UNROLL
     for (int i = 0; i < 8; i++) {
@@ -500,11 +485,101 @@ ECB_DEV void ed25519_hash_k_body(size_t idx, const unsigned char* a_enc, const u
     FL::mul(lo, t, one);       // d_lo mod l
     FL::add(t, lo, hi);
     ECB_UNROLL
+    for (int i = 0; i < 8; i++) out8[i] = t.v[i];
+}
+
+// =======================================================================================
+// k = reduce_wide_le(SHA-512(R || A || M))  (src/protocol/ed25519.rs:21 reduce_wide_le, :139) and the
+// split of the 64-byte signature into R and S: the prologue of verification on raw messages.
+//   sig : n x 64 bytes R || S ; a_enc : n x 32 ; msgs + off : concatenated messages, message i is
+//   bytes [off[i], off[i+1]) ; outputs r_out, s_out, k_out : n x 32 bytes each
+// The 512-bit digest d = d_lo + 2^256 d_hi (little-endian) is reduced with three Montgomery products
+// in GF(l): d_hi 2^256 = mont(d_hi, R^2), d_lo = mont(mont(d_lo, R^2), 1) — CIOS accepts any 256-bit
+// first operand.
+// =======================================================================================
+ECB_DEV void ed25519_hash_k_body(size_t idx, const unsigned char* a_enc, const unsigned char* sig, const unsigned char* msgs,
+                                 const unsigned long long* off, u32* r_out, u32* s_out, u32* k_out) {
+    const unsigned char* R = sig + idx * 64;
+    const unsigned char* A = a_enc + idx * 32;
+    const unsigned char* M = msgs + off[idx];
+    size_t mlen = (size_t)(off[idx + 1] - off[idx]);
+    unsigned char dg[64];
+    sha512_bytes(dg, 64 + mlen, [&](size_t pos) -> unsigned char { return pos < 32 ? R[pos] : (pos < 64 ? A[pos - 32] : M[pos - 64]); });
+    u32 kw[8];
+    ed25519_reduce_wide(kw, dg);
+    ECB_UNROLL
     for (int i = 0; i < 8; i++) {
-        k_out[idx * 8 + i] = t.v[i];
+        k_out[idx * 8 + i] = kw[i];
         r_out[idx * 8 + i] = (u32)R[4 * i] | ((u32)R[4 * i + 1] << 8) | ((u32)R[4 * i + 2] << 16) | ((u32)R[4 * i + 3] << 24);
         s_out[idx * 8 + i] = (u32)R[32 + 4 * i] | ((u32)R[32 + 4 * i + 1] << 8) | ((u32)R[32 + 4 * i + 2] << 16) | ((u32)R[32 + 4 * i + 3] << 24);
     }
+}
+
+// =======================================================================================
+// Ed25519 key generation and signing (src/protocol/ed25519.rs:61-110).
+// NOT constant-time: secret-dependent table addresses in the comb kernel.
+//   expand : h = SHA-512(seed); a = clamp(h[0..32]) mod l (init_from_wide_bytes_le of the clamped
+//            value, ed25519.rs:71-74); prefix = h[32..64]
+//   nonce  : r = reduce_wide_le(SHA-512(prefix || M))                              (ed25519.rs:96)
+//   [comb kernel + FinEdCompressed: R = encode_point(r B), A = encode_point(a B)]
+//   finish : k = reduce_wide_le(SHA-512(R || A || M)); S = r + k a mod l; sig = R || S   (:100-109)
+// =======================================================================================
+ECB_DEV void ed25519_expand_body(size_t idx, const unsigned char* seeds, u32* a_out, u32* prefix_out) {
+    const unsigned char* S = seeds + idx * 32;
+    unsigned char dg[64], wide[64];
+    sha512_bytes(dg, 32, [&](size_t pos) -> unsigned char { return S[pos]; });
+    ECB_UNROLL
+    for (int i = 0; i < 32; i++) { wide[i] = dg[i]; wide[32 + i] = 0; }
+    wide[0] &= 248;
+    wide[31] &= 127;
+    wide[31] |= 64;
+    u32 a[8];
+    ed25519_reduce_wide(a, wide);
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        a_out[idx * 8 + i] = a[i];
+        prefix_out[idx * 8 + i] = (u32)dg[32 + 4 * i] | ((u32)dg[32 + 4 * i + 1] << 8) | ((u32)dg[32 + 4 * i + 2] << 16) | ((u32)dg[32 + 4 * i + 3] << 24);
+    }
+}
+ECB_DEV void ed25519_sign_nonce_body(size_t idx, const u32* prefix, const unsigned char* msgs, const unsigned long long* off, u32* r_out) {
+    const u32* P = prefix + idx * 8;
+    const unsigned char* M = msgs + off[idx];
+    size_t mlen = (size_t)(off[idx + 1] - off[idx]);
+    unsigned char dg[64];
+    sha512_bytes(dg, 32 + mlen, [&](size_t pos) -> unsigned char { return pos < 32 ? (unsigned char)(P[pos >> 2] >> (8 * (pos & 3))) : M[pos - 32]; });
+    u32 r[8];
+    ed25519_reduce_wide(r, dg);
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) r_out[idx * 8 + i] = r[i];
+}
+// sig holds R in bytes [0, 32) of element idx on entry; S is written to bytes [32, 64)
+ECB_DEV void ed25519_sign_finish_body(size_t idx, unsigned char* sig, const unsigned char* a_pub, const unsigned char* msgs,
+                                      const unsigned long long* off, const u32* a_red, const u32* r_red) {
+    typedef Mont<ED_FN> FL;
+    const unsigned char* R = sig + idx * 64;
+    const unsigned char* A = a_pub + idx * 32;
+    const unsigned char* M = msgs + off[idx];
+    size_t mlen = (size_t)(off[idx + 1] - off[idx]);
+    unsigned char dg[64];
+    sha512_bytes(dg, 64 + mlen, [&](size_t pos) -> unsigned char { return pos < 32 ? R[pos] : (pos < 64 ? A[pos - 32] : M[pos - 64]); });
+    u32 kw[8];
+    ed25519_reduce_wide(kw, dg);
+    FL::el k, a, r, r2, one, t;
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        k.v[i] = kw[i];
+        a.v[i] = a_red[idx * 8 + i];
+        r.v[i] = r_red[idx * 8 + i];
+        r2.v[i] = ED_FN::r2(i);
+        one.v[i] = i == 0 ? 1u : 0u;
+    }
+    FL::mul(k, k, r2);         // k R
+    FL::mul(t, k, a);          // k a   (one Montgomery factor cancels)
+    FL::add(t, t, r);          // S = r + k a mod l
+    FL::canon(t, t);
+    u32* out = reinterpret_cast<u32*>(sig + idx * 64 + 32);
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) out[i] = t.v[i];
 }
 
 ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,

@@ -61,7 +61,8 @@ int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
     return ECB_OK;
 }
 
-int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s) {
+int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s,
+                         size_t enc_stride_words) {
     if (!d.ed_table || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
     TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
@@ -74,7 +75,7 @@ int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32*
     prof_mark(ctx, d, s, 1);
     int rc;
     if (compressed) {
-        FinEdCompressed fin{planes, n, d_out};
+        FinEdCompressed fin{planes, n, d_out, enc_stride_words ? enc_stride_words : 8};
         rc = launch_batch_inv<F25519, FinEdCompressed>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     } else {
         FinEdXY fin{planes, n, d_out};
@@ -164,4 +165,55 @@ int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, cons
     int rc = launch_batch_inv<F25519, FinEdVerify>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     prof_mark(ctx, d, s, 2);
     return rc;
+}
+
+// ---- key generation and signing (ed25519.rs:61-110).  Not constant-time. ------------
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_expand(size_t n, const unsigned char* seeds, u32* a_out, u32* prefix_out) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) ed25519_expand_body(idx, seeds, a_out, prefix_out);
+}
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_sign_nonce(size_t n, const u32* prefix, const unsigned char* msgs,
+                                                                 const unsigned long long* off, u32* r_out) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) ed25519_sign_nonce_body(idx, prefix, msgs, off, r_out);
+}
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_sign_finish(size_t n, unsigned char* sig, const unsigned char* a_pub,
+                                                                  const unsigned char* msgs, const unsigned long long* off,
+                                                                  const u32* a_red, const u32* r_red) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) ed25519_sign_finish_body(idx, sig, a_pub, msgs, off, a_red, r_red);
+}
+// SecretKey::public_key (ed25519.rs:81 public_from_seed): seeds n x 32 -> encode_point(a B) n x 32
+int dev_ed25519_public_from_seed(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, size_t n, u32* d_pub, cudaStream_t s) {
+    TRY(ensure(ctx, d.cur->aux, n * 4 * 32));
+    u32* a = (u32*)d.cur->aux.p;
+    u32* prefix = a + n * 8;
+    k_ed25519_expand<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_seeds, a, prefix);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return dev_ed25519_mul_base(ctx, d, a, n, d_pub, true, s, 0);
+}
+// Keypair::sign / sign_with_public (ed25519.rs:94): d_pub may be null (SecretKey::sign, :112: A is derived first)
+int dev_ed25519_sign(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, const unsigned char* d_pub, const unsigned char* d_msgs,
+                     const unsigned long long* d_off, size_t n, unsigned char* d_sig, cudaStream_t s) {
+    TRY(ensure(ctx, d.cur->aux, n * 4 * 32));
+    u32* a = (u32*)d.cur->aux.p;
+    u32* prefix = a + n * 8;
+    u32* r = prefix + n * 8;
+    u32* pub_tmp = r + n * 8;
+    k_ed25519_expand<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_seeds, a, prefix);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    if (!d_pub) {
+        TRY(dev_ed25519_mul_base(ctx, d, a, n, pub_tmp, true, s, 0));
+        d_pub = (const unsigned char*)pub_tmp;
+    }
+    k_ed25519_sign_nonce<<<grid_for(n), ECB_TPB, 0, s>>>(n, prefix, d_msgs, d_off, r);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    TRY(dev_ed25519_mul_base(ctx, d, r, n, (u32*)d_sig, true, s, 16));   // R = encode_point(r B) into bytes [0, 32) of each signature
+    k_ed25519_sign_finish<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_sig, d_pub, d_msgs, d_off, a, r);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ECB_OK;
 }

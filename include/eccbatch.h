@@ -93,6 +93,17 @@ int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, 
 
 /* ---- X25519 / X448 --------------------------------------------------------------------- */
 
+/* ---- Ed25519 key generation and signing.  NOT constant-time (see the note at the top of
+ * this header and DESIGN.md section 8): the comb kernel addresses its table by secret digits.
+ * SecretKey::public_key (src/protocol/ed25519.rs:81 public_from_seed, :61 expand_secret): seeds n x 32 bytes ->
+ * pub n x 32 bytes = encode_point([clamp(SHA-512(seed)[0..32]) mod l] B).
+ * Keypair::sign / sign_with_public (ed25519.rs:94-110; SecretKey::sign :112 when pub is NULL: A is derived on
+ * the device first): r = SHA-512(prefix || M) mod l, R = encode_point(r B), k = SHA-512(R || A || M) mod l,
+ * S = r + k a mod l; sig: n x 64 bytes R || S.  Messages as in ecb_ed25519_verify (concatenated, n + 1 offsets). */
+int ecb_ed25519_public_from_seed(ecb_ctx* ctx, const uint8_t* seeds, size_t n, uint8_t* pub);
+int ecb_ed25519_sign(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
+                     uint8_t* sig);
+
 /* protocol::x25519::x25519(scalar, u)   (src/protocol/x25519.rs:36): clamps inside, masks bit 255
  * of u, accepts non-canonical u, returns 0 for low-order inputs.  k, u, out: n x 32 B. */
 int ecb_x25519(ecb_ctx* ctx, const uint8_t* k, const uint8_t* u, size_t n, uint8_t* out);

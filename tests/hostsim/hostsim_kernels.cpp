@@ -205,3 +205,28 @@ extern "C" void hs_bls_g1_from_compressed(const u32* enc, size_t n, int check, u
 extern "C" void hs_bls_g1_to_compressed(const u32* xy, const unsigned char* inf, size_t n, u32* enc) {
     for (size_t i = 0; i < n; i++) bls_g1_to_compressed_body(i, xy, inf, enc);
 }
+
+// ---- Ed25519 key generation and signing (kernels2.cuh) ---------------------------------------
+extern "C" void hs_ed25519_public_from_seed(const unsigned char* seeds, size_t n, int W, const u32* table, u32* pub) {
+    int nwin = (254 + W - 1) / W;
+    std::vector<u32> a(8 * n), prefix(8 * n), planes(3 * 8 * n), pf(8 * n);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) ed25519_expand_body(i, seeds, a.data(), prefix.data());
+    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, a.data(), table, W, nwin, planes.data(), &st);
+    size_t T = inv_threads(n);
+    FinEdCompressed fin{planes.data(), n, pub};
+    for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
+}
+extern "C" void hs_ed25519_sign(const unsigned char* seeds, const unsigned char* pub, const unsigned char* msgs,
+                                const unsigned long long* off, size_t n, int W, const u32* table, unsigned char* sig) {
+    int nwin = (254 + W - 1) / W;
+    std::vector<u32> a(8 * n), prefix(8 * n), r(8 * n), planes(3 * 8 * n), pf(8 * n);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) ed25519_expand_body(i, seeds, a.data(), prefix.data());
+    for (size_t i = 0; i < n; i++) ed25519_sign_nonce_body(i, prefix.data(), msgs, off, r.data());
+    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, r.data(), table, W, nwin, planes.data(), &st);
+    size_t T = inv_threads(n);
+    FinEdCompressed fin{planes.data(), n, (u32*)sig, 16};
+    for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
+    for (size_t i = 0; i < n; i++) ed25519_sign_finish_body(i, sig, pub, msgs, off, a.data(), r.data());
+}

@@ -172,6 +172,39 @@ def test_wei_mul(hs, golden, coracle, cid, curve):
         assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
 
 
+def test_ed25519_keygen_and_sign(hs, golden):
+    """Device code of expand_secret / public_from_seed / sign_with_public (ed25519.rs:61-110) against
+    RFC 8032 TEST 1-3 (seed, public key, message, signature: ed25519.rs:271-290) and the big-int oracle
+    on random seeds with message lengths around the SHA-512 padding boundaries."""
+    _, k = hs
+    W = 6
+    table = np.zeros((k.hs_ed25519_table_entries(W), 24), dtype=np.uint32)
+    k.hs_ed25519_build_table(W, p(table))
+    g = rng(70)
+    seeds = [bytes.fromhex(v["seed"]) for v in golden["ed25519_rfc8032"]]
+    msgs = [bytes.fromhex(v["message"]) for v in golden["ed25519_rfc8032"]]
+    for ln in (0, 1, 47, 48, 79, 80, 111, 112, 175, 176, 300):
+        seeds.append(g.bytes(32))
+        msgs.append(g.bytes(ln))
+    n = len(seeds)
+    sd = rows(seeds)
+    pub = np.zeros((n, 32), dtype=np.uint8)
+    k.hs_ed25519_public_from_seed(p(sd), ctypes.c_size_t(n), W, p(table), p(pub))
+    for i, v in enumerate(golden["ed25519_rfc8032"]):
+        assert pub[i].tobytes().hex() == v["public"]
+    assert [r.tobytes() for r in pub] == [R.ed25519_public_from_seed(s) for s in seeds]
+    off = np.zeros(n + 1, dtype=np.uint64)
+    off[1:] = np.cumsum([len(m) for m in msgs])
+    blob = np.frombuffer(b"".join(msgs) + b"\0", dtype=np.uint8).copy()
+    sig = np.zeros((n, 64), dtype=np.uint8)
+    k.hs_ed25519_sign(p(sd), p(pub), p(blob), p(off), ctypes.c_size_t(n), W, p(table), p(sig))
+    for i, v in enumerate(golden["ed25519_rfc8032"]):
+        assert sig[i].tobytes().hex() == v["signature"]
+    for i in range(n):
+        assert sig[i].tobytes() == R.ed25519_sign(seeds[i], msgs[i])
+        assert R.ed25519_verify(pub[i].tobytes(), msgs[i], sig[i].tobytes())
+
+
 @pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1"), (2, "bls12_381_g1")])
 def test_wei_decompress(hs, coracle, cid, curve):
     """Device code of PointAffine::decompress (kernels3.cuh) against the oracle: both parities, an x
