@@ -51,6 +51,10 @@ WORK = {
     # wire formats, reference algorithm: sqrt chain p256r1.rs:68 (253 S + 11 M) + x^3 + a x + b;
     # BLS: Fp::sqrt = power((p+1)/4) by square-and-multiply (~380 S + ~190 M) + is_in_subgroup
     # (2 x mul_by_abs_x = 126 doublings (7 M + 2 S... counted 9 M) + 10 additions (14 M))
+    # Ed25519 keygen / sign as the reference does them: mul_base (comb, 579 M) + encode; the hashes and the
+    # scalar-field arithmetic are not multiplier work worth counting
+    "ed25519_keygen": 41688,
+    "ed25519_sign": 41688,
     "p256_decompress": 254 * 36 + 13 * 64,
     "bls12_381_g1_from_compressed": 380 * 234 + 192 * 300 + (126 * 9 + 10 * 14) * 300,
 }
@@ -69,6 +73,8 @@ WORKLOADS = {
     "ed25519_verify": (20, 128, 1, "north star: batched ed25519 verify (k = SHA-512(R||A||M) mod l precomputed by the caller)"),
     "p256_mul_base": (20, 32, 65, "north star: fixed-base p256r1 Point::mul_base (comb)"),
     "bls12_381_g1_mul_base": (20, 32, 97, "north star: fixed-base BLS12-381 G1 Point::mul_base (comb)"),
+    "ed25519_keygen": (20, 32, 32, "SURVEY 8 f.3: ed25519 SecretKey::public_key (seed -> public key)"),
+    "ed25519_sign": (20, 128, 64, "SURVEY 8 f.3: ed25519 Keypair::sign of 64-byte messages (seed, public key, message -> R || S)"),
     "p256_decompress": (20, 33, 65, "SURVEY 8 f.1: PointAffine::decompress (SEC1 point decompression) on p256r1"),
     "bls12_381_g1_from_compressed": (20, 48, 97, "SURVEY 8 f.1: BLS12-381 G1 from_compressed with the prime-order-subgroup check"),
 }
@@ -134,6 +140,11 @@ def make_inputs(name, n, ctx, seed):
         return [rand_scalars(g, n, 32, 1, "big")]
     if base == "bls12_381_g1_mul_base":
         return [rand_scalars(g, n, 32, 2, "big")]
+    if base == "ed25519_keygen":
+        return [g.integers(0, 256, size=(n, 32), dtype=np.uint8)]
+    if base == "ed25519_sign":
+        seeds = g.integers(0, 256, size=(uniq, 32), dtype=np.uint8)
+        return [tile(seeds), tile(ctx.ed25519_public_from_seed(seeds)), g.integers(0, 256, size=(n, 64), dtype=np.uint8)]
     if base == "p256_decompress":
         pts, _ = ctx.wei_mul_base("p256r1", rand_scalars(g, uniq, 32, 1, "big"))
         x = np.ascontiguousarray(pts[:, :32])
@@ -173,8 +184,21 @@ OUT_SHAPES = {
     "ed25519_mul_base": [64], "ed25519_mul": [64], "x25519": [32], "x25519_base": [32], "x448": [56],
     "p256_mul": [64, 1], "p384_mul": [96, 1], "bls12_381_g1_mul": [96, 1], "p256_ecdsa_verify": [1],
     "p256_mul_base": [64, 1], "bls12_381_g1_mul_base": [96, 1], "ed25519_verify": [1],
-    "p256_decompress": [64, 1], "bls12_381_g1_from_compressed": [96, 1],
+    "p256_decompress": [64, 1], "bls12_381_g1_from_compressed": [96, 1], "ed25519_keygen": [32], "ed25519_sign": [64],
 }
+
+
+_OFFSETS = {}
+
+
+def _msg_offsets(msgs):
+    """Device offsets 0, w, 2w, ... for n fixed-width messages (cached; not part of the rotated inputs)."""
+    import torch
+
+    key = (msgs.shape[0], msgs.shape[1])
+    if key not in _OFFSETS:
+        _OFFSETS[key] = (torch.arange(key[0] + 1, dtype=torch.int64, device=msgs.device) * key[1]).contiguous()
+    return _OFFSETS[key]
 
 
 def dev_launch(ctx, name, ins, outs, n, stream):
@@ -201,6 +225,10 @@ def dev_launch(ctx, name, ins, outs, n, stream):
         ctx.dev_call("ecb_wei_mul_base_dev", 0, 0 if base == "p256_mul_base" else 2, p[0], n, o[0], o[1], stream)
     elif base == "p256_ecdsa_verify":
         ctx.dev_call("ecb_ecdsa_verify_hashed_dev", 0, 0, p[0], p[1], p[2], n, o[0], stream)
+    elif base == "ed25519_keygen":
+        ctx.dev_call("ecb_ed25519_public_from_seed_dev", 0, p[0], n, o[0], stream)
+    elif base == "ed25519_sign":
+        ctx.dev_call("ecb_ed25519_sign_dev", 0, p[0], p[1], p[2], _msg_offsets(ins[2]).data_ptr(), n, o[0], stream)
     elif base == "p256_decompress":
         ctx.dev_call("ecb_wei_decompress_dev", 0, 0, p[0], p[1], n, o[0], o[1], stream)
     elif base == "bls12_381_g1_from_compressed":
@@ -232,6 +260,10 @@ def host_call(ctx, name, ins, outs=None):
         return list(ctx.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], out=o[0], out_inf=o[1]))
     if base == "p256_ecdsa_verify":
         return [ctx.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], out=o[0])]
+    if base == "ed25519_keygen":
+        return [ctx.ed25519_public_from_seed(ins[0], out=o[0])]
+    if base == "ed25519_sign":
+        return [ctx.ed25519_sign_fixed(ins[0], ins[2], pub=ins[1], out=o[0])]
     if base == "p256_decompress":
         return list(ctx.wei_decompress("p256r1", ins[0], ins[1], out=o[0], out_ok=o[1]))
     if base == "bls12_381_g1_from_compressed":
@@ -261,6 +293,13 @@ def oracle_call(C, name, ins, nthreads):
         return list(C.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], nthreads))
     if base == "p256_ecdsa_verify":
         return [C.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], nthreads)]
+    if base in ("ed25519_keygen", "ed25519_sign"):
+        # the C oracle carries no SHA-512: the big-int oracle restates these two (pinned to RFC 8032 and OpenSSL in tests/)
+        from oracle import pyref as R
+
+        if base == "ed25519_keygen":
+            return [np.frombuffer(b"".join(R.ed25519_public_from_seed(r.tobytes()) for r in ins[0]), dtype=np.uint8).reshape(-1, 32)]
+        return [np.frombuffer(b"".join(R.ed25519_sign(ins[0][i].tobytes(), ins[2][i].tobytes()) for i in range(len(ins[0]))), dtype=np.uint8).reshape(-1, 64)]
     if base == "p256_decompress":
         return list(C.wei_decompress("p256r1", ins[0], ins[1], nthreads))
     if base == "bls12_381_g1_from_compressed":

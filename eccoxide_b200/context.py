@@ -168,6 +168,19 @@ class Context:
         self._check(self._lib.ecb_ed25519_sign(self._ctx, _p(sd), _p(pb), _p(blob), _p(off), n, _p(out)))
         return out
 
+    def ed25519_sign_fixed(self, seeds, msgs, pub=None, out=None):
+        """ed25519_sign for n messages of one length given as an (n, w) byte array (no per-message objects)."""
+        sd = _rows(seeds, 32, "seeds")
+        n = sd.shape[0]
+        m = np.ascontiguousarray(msgs, dtype=np.uint8)
+        if m.ndim != 2 or m.shape[0] != n:
+            raise ValueError("msgs must be (n, w) bytes")
+        pb = None if pub is None else _rows(pub, 32, "pub")
+        off = np.arange(n + 1, dtype=np.uint64) * np.uint64(m.shape[1])
+        out = _out(out, (n, 64))
+        self._check(self._lib.ecb_ed25519_sign(self._ctx, _p(sd), _p(pb), _p(m), _p(off), n, _p(out)))
+        return out
+
     # -- X25519 / X448 ------------------------------------------------------------------------
     def x25519(self, k, u, out=None):
         k = _rows(k, 32, "k")

@@ -801,6 +801,22 @@ int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int di, const void* d_enc
     return dev_bls_g1_from_compressed(ctx, *d, (const u32*)d_enc, n, check_subgroup ? 1 : 0, (u32*)d_out, (unsigned char*)d_ok,
                                       (cudaStream_t)stream);
 }
+int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int di, const void* d_seeds, size_t n, void* d_pub, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    single_slot(d);
+    return dev_ed25519_public_from_seed(ctx, *d, (const unsigned char*)d_seeds, n, (u32*)d_pub, (cudaStream_t)stream);
+}
+int ecb_ed25519_sign_dev(ecb_ctx* ctx, int di, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off, size_t n,
+                         void* d_sig, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    single_slot(d);
+    return dev_ed25519_sign(ctx, *d, (const unsigned char*)d_seeds, (const unsigned char*)d_pub, (const unsigned char*)d_msgs,
+                            (const unsigned long long*)d_msg_off, n, (unsigned char*)d_sig, (cudaStream_t)stream);
+}
 int ecb_x448_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
     if (!d) return ECB_ERR_INVALID_ARG;

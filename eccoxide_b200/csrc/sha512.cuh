@@ -22,25 +22,27 @@ struct Sha512 {
     // one 128-byte block given as 16 big-endian words
     ECB_DEV void compress(w64* w) {
         w64 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
+        // 5 passes of 16 rounds, the 16 rounds unrolled: every index into the schedule window is a
+        // compile-time constant, so w[] stays in registers (a rolled loop indexes it dynamically and
+        // sends it to local memory: 5 local accesses per round)
         ECB_NOUNROLL
-        for (int t = 0; t < 80; t++) {
-            w64 wt;
-            if (t < 16) {
-                wt = w[t];
-            } else {
-                w64 w15 = w[(t - 15) & 15], w2 = w[(t - 2) & 15];
-                w64 s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
-                w64 s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
-                wt = w[t & 15] + s0 + w[(t - 7) & 15] + s1;
-                w[t & 15] = wt;
+        for (int t0 = 0; t0 < 80; t0 += 16) {
+            ECB_UNROLL
+            for (int i = 0; i < 16; i++) {
+                if (t0 != 0) {
+                    w64 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                    w64 s0 = rotr64(w15, 1) ^ rotr64(w15, 8) ^ (w15 >> 7);
+                    w64 s1 = rotr64(w2, 19) ^ rotr64(w2, 61) ^ (w2 >> 6);
+                    w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
+                }
+                w64 S1 = rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41);
+                w64 ch = (e & f) ^ (~e & g);
+                w64 t1 = hh + S1 + ch + SHA512_K[t0 + i] + w[i];
+                w64 S0 = rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39);
+                w64 mj = (a & b) ^ (a & c) ^ (b & c);
+                w64 t2 = S0 + mj;
+                hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
             }
-            w64 S1 = rotr64(e, 14) ^ rotr64(e, 18) ^ rotr64(e, 41);
-            w64 ch = (e & f) ^ (~e & g);
-            w64 t1 = hh + S1 + ch + SHA512_K[t] + wt;
-            w64 S0 = rotr64(a, 28) ^ rotr64(a, 34) ^ rotr64(a, 39);
-            w64 mj = (a & b) ^ (a & c) ^ (b & c);
-            w64 t2 = S0 + mj;
-            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
         }
         h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
     }
@@ -56,7 +58,7 @@ ECB_DEV void sha512_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at, bo
     size_t nblocks = (len + 17 + 127) / 128;  // 0x80 marker + 16-byte length field
     ECB_NOUNROLL
     for (size_t blk = 0; blk < nblocks; blk++) {
-        ECB_NOUNROLL
+        ECB_UNROLL
         for (int i = 0; i < 16; i++) {
             w64 v = 0;
             ECB_NOUNROLL
@@ -90,7 +92,7 @@ ECB_DEV void sha256_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at) {
     size_t nblocks = (len + 9 + 63) / 64;
     ECB_NOUNROLL
     for (size_t blk = 0; blk < nblocks; blk++) {
-        ECB_NOUNROLL
+        ECB_UNROLL
         for (int i = 0; i < 16; i++) {
             u32 v = 0;
             ECB_NOUNROLL
@@ -107,24 +109,23 @@ ECB_DEV void sha256_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at) {
         }
         u32 a = h[0], b = h[1], c = h[2], d = h[3], e = h[4], f = h[5], g = h[6], hh = h[7];
         ECB_NOUNROLL
-        for (int t = 0; t < 64; t++) {
-            u32 wt;
-            if (t < 16) {
-                wt = w[t];
-            } else {
-                u32 w15 = w[(t - 15) & 15], w2 = w[(t - 2) & 15];
-                u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
-                u32 s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
-                wt = w[t & 15] + s0 + w[(t - 7) & 15] + s1;
-                w[t & 15] = wt;
+        for (int t0 = 0; t0 < 64; t0 += 16) {      // as in Sha512::compress: static schedule indices
+            ECB_UNROLL
+            for (int i = 0; i < 16; i++) {
+                if (t0 != 0) {
+                    u32 w15 = w[(i + 1) & 15], w2 = w[(i + 14) & 15];
+                    u32 s0 = rotr32(w15, 7) ^ rotr32(w15, 18) ^ (w15 >> 3);
+                    u32 s1 = rotr32(w2, 17) ^ rotr32(w2, 19) ^ (w2 >> 10);
+                    w[i] = w[i] + s0 + w[(i + 9) & 15] + s1;
+                }
+                u32 S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
+                u32 ch = (e & f) ^ (~e & g);
+                u32 t1 = hh + S1 + ch + SHA256_K[t0 + i] + w[i];
+                u32 S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
+                u32 mj = (a & b) ^ (a & c) ^ (b & c);
+                u32 t2 = S0 + mj;
+                hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
             }
-            u32 S1 = rotr32(e, 6) ^ rotr32(e, 11) ^ rotr32(e, 25);
-            u32 ch = (e & f) ^ (~e & g);
-            u32 t1 = hh + S1 + ch + SHA256_K[t] + wt;
-            u32 S0 = rotr32(a, 2) ^ rotr32(a, 13) ^ rotr32(a, 22);
-            u32 mj = (a & b) ^ (a & c) ^ (b & c);
-            u32 t2 = S0 + mj;
-            hh = g; g = f; f = e; e = d + t1; d = c; c = b; b = a; a = t1 + t2;
         }
         h[0] += a; h[1] += b; h[2] += c; h[3] += d; h[4] += e; h[5] += f; h[6] += g; h[7] += hh;
     }

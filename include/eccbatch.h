@@ -173,6 +173,9 @@ int ecb_wei_decompress_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void
                            void* d_out_xy_be, void* d_ok, void* stream);
 int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int dev_index, const void* d_enc, size_t n, int check_subgroup,
                                          void* d_out_xy_be, void* d_ok, void* stream);
+int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, size_t n, void* d_pub, void* stream);
+int ecb_ed25519_sign_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off,
+                         size_t n, void* d_sig, void* stream);
 int ecb_x448_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);
 int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int dev_index, const void* d_a_enc, const void* d_r_enc, const void* d_s_le,
                                      const void* d_k_le, size_t n, void* d_ok, void* stream);
