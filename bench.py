@@ -53,6 +53,7 @@ WORK = {
     # (2 x mul_by_abs_x = 126 doublings (7 M + 2 S... counted 9 M) + 10 additions (14 M))
     # Ed25519 keygen / sign as the reference does them: mul_base (comb, 579 M) + encode; the hashes and the
     # scalar-field arithmetic are not multiplier work worth counting
+    "p256_ecdsa_sign": 896 * 64 + 3 * 64 + 5 * 136,   # reference: comb mul_base + x affine share + scalar-field products (n256 generic Montgomery)
     "ed25519_keygen": 41688,
     "ed25519_sign": 41688,
     "p256_decompress": 254 * 36 + 13 * 64,
@@ -73,6 +74,7 @@ WORKLOADS = {
     "ed25519_verify": (20, 128, 1, "north star: batched ed25519 verify (k = SHA-512(R||A||M) mod l precomputed by the caller)"),
     "p256_mul_base": (20, 32, 65, "north star: fixed-base p256r1 Point::mul_base (comb)"),
     "bls12_381_g1_mul_base": (20, 32, 97, "north star: fixed-base BLS12-381 G1 Point::mul_base (comb)"),
+    "p256_ecdsa_sign": (20, 96, 65, "SURVEY 8 f.3: ecdsa::sign_hashed on p256r1 (secret, nonce, message scalar -> r || s)"),
     "ed25519_keygen": (20, 32, 32, "SURVEY 8 f.3: ed25519 SecretKey::public_key (seed -> public key)"),
     "ed25519_sign": (20, 128, 64, "SURVEY 8 f.3: ed25519 Keypair::sign of 64-byte messages (seed, public key, message -> R || S)"),
     "p256_decompress": (20, 33, 65, "SURVEY 8 f.1: PointAffine::decompress (SEC1 point decompression) on p256r1"),
@@ -140,6 +142,9 @@ def make_inputs(name, n, ctx, seed):
         return [rand_scalars(g, n, 32, 1, "big")]
     if base == "bls12_381_g1_mul_base":
         return [rand_scalars(g, n, 32, 2, "big")]
+    if base == "p256_ecdsa_sign":
+        mk = lambda: np.bitwise_or(rand_scalars(g, n, 32, 1, "big"), np.eye(1, 32, 31, dtype=np.uint8))   # non-zero, < n
+        return [mk(), mk(), rand_scalars(g, n, 32, 1, "big")]
     if base == "ed25519_keygen":
         return [g.integers(0, 256, size=(n, 32), dtype=np.uint8)]
     if base == "ed25519_sign":
@@ -184,7 +189,7 @@ OUT_SHAPES = {
     "ed25519_mul_base": [64], "ed25519_mul": [64], "x25519": [32], "x25519_base": [32], "x448": [56],
     "p256_mul": [64, 1], "p384_mul": [96, 1], "bls12_381_g1_mul": [96, 1], "p256_ecdsa_verify": [1],
     "p256_mul_base": [64, 1], "bls12_381_g1_mul_base": [96, 1], "ed25519_verify": [1],
-    "p256_decompress": [64, 1], "bls12_381_g1_from_compressed": [96, 1], "ed25519_keygen": [32], "ed25519_sign": [64],
+    "p256_decompress": [64, 1], "bls12_381_g1_from_compressed": [96, 1], "ed25519_keygen": [32], "ed25519_sign": [64], "p256_ecdsa_sign": [64, 1],
 }
 
 
@@ -225,6 +230,8 @@ def dev_launch(ctx, name, ins, outs, n, stream):
         ctx.dev_call("ecb_wei_mul_base_dev", 0, 0 if base == "p256_mul_base" else 2, p[0], n, o[0], o[1], stream)
     elif base == "p256_ecdsa_verify":
         ctx.dev_call("ecb_ecdsa_verify_hashed_dev", 0, 0, p[0], p[1], p[2], n, o[0], stream)
+    elif base == "p256_ecdsa_sign":
+        ctx.dev_call("ecb_ecdsa_sign_hashed_dev", 0, 0, p[0], p[1], p[2], n, o[0], o[1], stream)
     elif base == "ed25519_keygen":
         ctx.dev_call("ecb_ed25519_public_from_seed_dev", 0, p[0], n, o[0], stream)
     elif base == "ed25519_sign":
@@ -260,6 +267,8 @@ def host_call(ctx, name, ins, outs=None):
         return list(ctx.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], out=o[0], out_inf=o[1]))
     if base == "p256_ecdsa_verify":
         return [ctx.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], out=o[0])]
+    if base == "p256_ecdsa_sign":
+        return list(ctx.ecdsa_sign_hashed("p256r1", ins[0], ins[1], ins[2], out=o[0], out_ok=o[1]))
     if base == "ed25519_keygen":
         return [ctx.ed25519_public_from_seed(ins[0], out=o[0])]
     if base == "ed25519_sign":
@@ -293,6 +302,12 @@ def oracle_call(C, name, ins, nthreads):
         return list(C.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], nthreads))
     if base == "p256_ecdsa_verify":
         return [C.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], nthreads)]
+    if base == "p256_ecdsa_sign":
+        from oracle import pyref as R
+
+        ib = lambda r: int.from_bytes(r.tobytes(), "big")
+        rs = b"".join(R.ecdsa_sign_hashed(R.P256, ib(ins[0][i]), ib(ins[1][i]), ib(ins[2][i])) for i in range(len(ins[0])))
+        return [np.frombuffer(rs, dtype=np.uint8).reshape(-1, 64), np.ones((len(ins[0]), 1), dtype=np.uint8)]
     if base in ("ed25519_keygen", "ed25519_sign"):
         # the C oracle carries no SHA-512: the big-int oracle restates these two (pinned to RFC 8032 and OpenSSL in tests/)
         from oracle import pyref as R

@@ -238,6 +238,21 @@ class Context:
         self._check(self._lib.ecb_wei_mul_base(self._ctx, cid, _p(k), n, _p(out), _p(inf), ctypes.byref(bad)), bad)
         return out, inf.astype(bool)
 
+    def ecdsa_sign_hashed(self, curve, d_be, k_be, z_be, out=None, out_ok=None):
+        """ecdsa::sign_hashed over a batch (not constant-time): (r || s rows, present)."""
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+        sb = SCALAR_BYTES[cid]
+        d = _rows(d_be, sb, "d_be")
+        k = _rows(k_be, sb, "k_be")
+        z = _rows(z_be, sb, "z_be")
+        n = d.shape[0]
+        if not (k.shape[0] == z.shape[0] == n):
+            raise ValueError("count mismatch")
+        out = _out(out, (n, 2 * sb))
+        ok = _out(out_ok, (n,))
+        self._check(self._lib.ecb_ecdsa_sign_hashed(self._ctx, cid, _p(d), _p(k), _p(z), n, _p(out), _p(ok)))
+        return out, ok.astype(bool)
+
     def wei_decompress(self, curve, x_be, sign, out=None, out_ok=None):
         """PointAffine::decompress over a batch (affine.rs:48): (x || y rows, present)."""
         cid = CURVE_IDS[curve] if isinstance(curve, str) else curve

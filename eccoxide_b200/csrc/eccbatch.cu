@@ -662,6 +662,21 @@ int ecb_wei_mul_base(ecb_ctx* ctx, int curve, const uint8_t* k_be, size_t n, uin
                            return dev_wei_mul_base(ctx, d, curve, (const u32*)in[0], cn, (u32*)o[0], (unsigned char*)o[1], s);
                        });
 }
+int ecb_ecdsa_sign_hashed(ecb_ctx* ctx, int curve, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n, uint8_t* rs_be,
+                          uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb) || curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+    if (n && (!d_be || !k_be || !z_be || !rs_be || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{d_be, sb}, {k_be, sb}, {z_be, sb}}, {{rs_be, 2 * sb}, {ok, 1}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           if (curve == ECB_CURVE_P256R1)
+                               return dev_ecdsa_sign_p256(ctx, d, (const u32*)in[0], (const u32*)in[1], (const u32*)in[2], cn, (u32*)o[0],
+                                                          (unsigned char*)o[1], s);
+                           return dev_ecdsa_sign_p384(ctx, d, (const u32*)in[0], (const u32*)in[1], (const u32*)in[2], cn, (u32*)o[0],
+                                                      (unsigned char*)o[1], s);
+                       });
+}
 int ecb_wei_decompress(ecb_ctx* ctx, int curve, const uint8_t* x_be, const uint8_t* sign, size_t n, uint8_t* out_xy, uint8_t* ok) {
     if (!ctx) return ECB_ERR_CUDA;
     size_t fb, sb;
@@ -800,6 +815,20 @@ int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int di, const void* d_enc
     single_slot(d);
     return dev_bls_g1_from_compressed(ctx, *d, (const u32*)d_enc, n, check_subgroup ? 1 : 0, (u32*)d_out, (unsigned char*)d_ok,
                                       (cudaStream_t)stream);
+}
+int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_d, const void* d_k, const void* d_z, size_t n, void* d_rs,
+                              void* d_ok, void* stream) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    single_slot(d);
+    if (curve == ECB_CURVE_P256R1)
+        return dev_ecdsa_sign_p256(ctx, *d, (const u32*)d_d, (const u32*)d_k, (const u32*)d_z, n, (u32*)d_rs, (unsigned char*)d_ok,
+                                   (cudaStream_t)stream);
+    if (curve == ECB_CURVE_P384R1)
+        return dev_ecdsa_sign_p384(ctx, *d, (const u32*)d_d, (const u32*)d_k, (const u32*)d_z, n, (u32*)d_rs, (unsigned char*)d_ok,
+                                   (cudaStream_t)stream);
+    return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
 }
 int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int di, const void* d_seeds, size_t n, void* d_pub, void* stream) {
     DevCtx* d = get_dev(ctx, di);

@@ -417,6 +417,77 @@ struct FinEcdsa {  // x_mod_n(R) == r (ecdsa.rs:382, :218-221); identity => reje
 };
 
 // =======================================================================================
+// ECDSA sign_hashed, batched (src/protocol/ecdsa.rs:165-184).  NOT constant-time.
+//   prep   : d, k, z decoded; valid = canonical & d != 0 & k != 0; k (or 1) -> Montgomery form in GF(n)
+//            into the "Z" plane of `sp` for the scalar-field batch inversion
+//   [batch_inv<FN> + FinScalarInv -> k^-1; generator comb on k + affine conversion -> x || y of k G]
+//   finish : r = x mod n (field_to_scalar, ecdsa.rs:363); s = k^-1 (z + r d) mod n;
+//            valid &= k G finite & r != 0 & s != 0; rs = r || s big-endian (zero when not valid)
+// =======================================================================================
+template <class C>
+ECB_DEV void ecdsa_sign_prep_body(size_t idx, size_t n, const u32* d_be, const u32* k_be, const u32* z_be, u32* sp, unsigned char* valid) {
+    typedef typename C::FN FN;
+    constexpr int NS = FN::N;
+    u32 d[NS], k[NS], z[NS];
+    ld_words_be<NS>(d, d_be + idx * NS);
+    ld_words_be<NS>(k, k_be + idx * NS);
+    ld_words_be<NS>(z, z_be + idx * NS);
+    u32 dz = 0, kz = 0;
+    ECB_UNROLL
+    for (int i = 0; i < NS; i++) { dz |= d[i]; kz |= k[i]; }
+    u32 ok = (dz != 0) & (kz != 0) & FN::is_canonical_words(d) & FN::is_canonical_words(k) & FN::is_canonical_words(z);
+    if (!ok) {
+        ECB_UNROLL
+        for (int i = 0; i < NS; i++) k[i] = 0;
+        k[0] = 1;
+    }
+    typename FN::el km;
+    FN::to_mont(km, k);
+    plane_st<NS>(sp + 2 * (size_t)NS * n, n, idx, km.v);
+    valid[idx] = (unsigned char)ok;
+}
+template <class C>
+ECB_DEV void ecdsa_sign_finish_body(size_t idx, size_t n, const u32* d_be, const u32* z_be, const u32* kg_xy_be, const unsigned char* kg_inf,
+                                    const u32* sp, u32* rs_be, unsigned char* valid) {
+    typedef typename C::F FT;
+    typedef typename C::FN FN;
+    constexpr int N = FT::N;
+    constexpr int NS = FN::N;
+    u32 xw[N], d[NS], z[NS], r[NS], sw[NS];
+    ld_words_be<N>(xw, kg_xy_be + idx * 2 * N);
+    ld_words_be<NS>(d, d_be + idx * NS);
+    ld_words_be<NS>(z, z_be + idx * NS);
+    // field_to_scalar: FB == SB for p256r1 / p384r1 and p < 2n: one conditional subtraction
+    u32 t[NS];
+    t[0] = sub_cc(xw[0], FN::P_::mod(0));
+    ECB_UNROLL
+    for (int i = 1; i < NS; i++) t[i] = subc_cc(xw[i], FN::P_::mod(i));
+    u32 borrow = subc(0, 0) & 1;
+    u32 rz = 0;
+    ECB_UNROLL
+    for (int i = 0; i < NS; i++) { r[i] = borrow ? xw[i] : t[i]; rz |= r[i]; }
+    typename FN::el rm, dm, zm, kinv, acc;
+    FN::to_mont(rm, r);
+    FN::to_mont(dm, d);
+    FN::to_mont(zm, z);
+    plane_ld<NS>(kinv.v, sp, n, idx);
+    FN::mul(acc, rm, dm);
+    FN::add(acc, acc, zm);
+    FN::mul(acc, acc, kinv);
+    FN::from_mont(sw, acc);
+    u32 sz = 0;
+    ECB_UNROLL
+    for (int i = 0; i < NS; i++) sz |= sw[i];
+    u32 ok = (valid[idx] != 0) & (kg_inf[idx] == 0) & (rz != 0) & (sz != 0);
+    u32 m = ok ? 0xffffffffu : 0u;
+    ECB_UNROLL
+    for (int i = 0; i < NS; i++) { r[i] &= m; sw[i] &= m; }
+    st_words_be<NS>(rs_be + idx * 2 * NS, r);
+    st_words_be<NS>(rs_be + idx * 2 * NS + NS, sw);
+    valid[idx] = (unsigned char)ok;
+}
+
+// =======================================================================================
 // Ed25519 verification, batched (src/protocol/ed25519.rs:119-147) with k = H(R||A||M) mod l
 // supplied by the caller.  One kernel, no inversion: the final comparison is projective
 // exactly like Point::eq (curve25519.rs:1200).

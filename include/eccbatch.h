@@ -125,6 +125,13 @@ int ecb_wei_mul(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, const uint8_t* 
 /* Point::mul_base(&Scalar) -> to_affine   (fiat/curve_macros.rs:55 -> projective.rs:965/:945) */
 int ecb_wei_mul_base(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, size_t n, uint8_t* out_xy_be, uint8_t* out_inf,
                      size_t* bad_index);
+/* ecdsa::sign_hashed::<O>(&secret, &nonce, hashed) -> CtOption<Signature> (src/protocol/ecdsa.rs:165-184), batched
+ * (NOT constant-time).  d_be (secret), k_be (nonce), z_be (message scalar): n x SB bytes each;
+ * rs_be: n x 2SB bytes r || s; ok[i] = 0 (and zero output) where the reference reports no signature: secret or
+ * nonce zero, r = 0 or s = 0 - and for a non-canonical scalar (Scalar::from_bytes -> None). */
+int ecb_ecdsa_sign_hashed(ecb_ctx* ctx, int curve_id, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n,
+                          uint8_t* rs_be, uint8_t* ok);
+
 /* ---- wire formats either side of the Weierstrass path --------------------------------------------------
  * PointAffine::decompress(&FieldElement, Sign) -> CtOption<PointAffine> (src/curve/affine.rs:48,
  * src/curve/fiat/curve_macros.rs:221; square roots src/curve/sec2/p256r1.rs:68, p384r1.rs:71,
@@ -173,6 +180,8 @@ int ecb_wei_decompress_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void
                            void* d_out_xy_be, void* d_ok, void* stream);
 int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int dev_index, const void* d_enc, size_t n, int check_subgroup,
                                          void* d_out_xy_be, void* d_ok, void* stream);
+int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_d_be, const void* d_k_be, const void* d_z_be,
+                              size_t n, void* d_rs_be, void* d_ok, void* stream);
 int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, size_t n, void* d_pub, void* stream);
 int ecb_ed25519_sign_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off,
                          size_t n, void* d_sig, void* stream);

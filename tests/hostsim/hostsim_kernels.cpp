@@ -230,3 +230,22 @@ extern "C" void hs_ed25519_sign(const unsigned char* seeds, const unsigned char*
     for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
     for (size_t i = 0; i < n; i++) ed25519_sign_finish_body(i, sig, pub, msgs, off, a.data(), r.data());
 }
+
+// ---- ECDSA sign_hashed (kernels2.cuh) -------------------------------------------------------
+template <class C>
+static void ecdsa_sign_run(const u32* d, const u32* k, const u32* z, size_t n, u32* rs, unsigned char* ok) {
+    constexpr int N = C::F::N;
+    constexpr int NS = C::FN::N;
+    std::vector<u32> sp(3 * NS * n), pf((N > NS ? N : NS) * n), kg(2 * N * n);
+    std::vector<unsigned char> kinf(n);
+    for (size_t i = 0; i < n; i++) ecdsa_sign_prep_body<C>(i, n, d, k, z, sp.data(), ok);
+    size_t T = inv_threads(n);
+    FinScalarInv<C> fin1{sp.data(), n};
+    for (size_t t = 0; t < T; t++) batch_inv_body<typename C::FN>(t, T, n, sp.data(), pf.data(), fin1);
+    wei_mul_base_run<C>(k, n, 5, kg.data(), kinf.data());
+    for (size_t i = 0; i < n; i++) ecdsa_sign_finish_body<C>(i, n, d, z, kg.data(), kinf.data(), sp.data(), rs, ok);
+}
+extern "C" void hs_ecdsa_sign(int curve, const u32* d, const u32* k, const u32* z, size_t n, u32* rs, unsigned char* ok) {
+    if (curve == 0) ecdsa_sign_run<CurveP256>(d, k, z, n, rs, ok);
+    else ecdsa_sign_run<CurveP384>(d, k, z, n, rs, ok);
+}

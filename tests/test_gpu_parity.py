@@ -701,6 +701,61 @@ def test_ed25519_keygen_and_sign(ctx, golden):
     assert ctx.ed25519_public_from_seed(np.zeros((0, 32), dtype=np.uint8)).shape == (0, 32)
 
 
+@pytest.mark.parametrize("curve", ["p256r1", "p384r1"])
+def test_ecdsa_sign_hashed(ctx, golden, coracle, curve):
+    """ecdsa::sign_hashed (ecdsa.rs:165-184) through the C ABI: RFC 6979 A.2.5 / A.2.6 (d, k, message ->
+    r, s), 2000 random (d, k, z) bit-exact with the big-int oracle (sampled) and accepted by the
+    library's verification, the C oracle and OpenSSL; zero / non-canonical secrets and nonces refused."""
+    c = R.WCURVES[curve]
+    v = golden["ecdsa_rfc6979"][curve]
+    d0 = int(v["d"], 16)
+    ds, ks, zs, want = [], [], [], []
+    for kat in v["kats"]:
+        dg = hashlib.new(kat["alg"], kat["message"].encode()).digest()
+        ds.append(d0)
+        ks.append(int(kat["k"], 16))
+        zs.append(int.from_bytes(R.ecdsa_digest_to_scalar(c, dg), "big"))
+        want.append(kat["r"].rjust(2 * c.sbytes, "0") + kat["s"].rjust(2 * c.sbytes, "0"))
+    nk = len(want)
+    g = rng(6979 + c.sbytes)
+    n_rand = 2000
+    for _ in range(n_rand):
+        ds.append(int.from_bytes(g.bytes(c.sbytes + 8), "big") % (c.n - 1) + 1)
+        ks.append(int.from_bytes(g.bytes(c.sbytes + 8), "big") % (c.n - 1) + 1)
+        zs.append(int.from_bytes(g.bytes(c.sbytes + 8), "big") % c.n)
+    bad = [(0, 5, 7), (5, 0, 7), (c.n, 5, 7), (5, c.n, 7), (5, 6, c.n), (2**(8 * c.sbytes) - 1, 3, 3)]
+    for d, kk, z in bad:
+        ds.append(d)
+        ks.append(kk)
+        zs.append(z)
+    tob = lambda xs: rows([x.to_bytes(c.sbytes, "big") for x in xs])
+    db, kb, zb = tob(ds), tob(ks), tob(zs)
+    rs, ok = ctx.ecdsa_sign_hashed(curve, db, kb, zb)
+    m = nk + n_rand
+    assert ok[:m].all() and not ok[m:].any() and not rs[m:].any()
+    for i in range(nk):
+        assert rs[i].tobytes().hex() == want[i]
+    for i in list(range(nk, nk + 40)) + [m - 1]:
+        assert rs[i].tobytes() == R.ecdsa_sign_hashed(c, ds[i], ks[i], zs[i])
+    q, inf = ctx.wei_mul_base(curve, db[:m])
+    assert not inf.any()
+    assert ctx.ecdsa_verify_hashed(curve, q, zb[:m], rs[:m]).all()
+    assert coracle.ecdsa_verify_hashed(curve, q, zb[:m], rs[:m], threads(coracle)).all()
+    zb2 = zb[:m].copy()
+    zb2[:, -1] ^= 1
+    assert not ctx.ecdsa_verify_hashed(curve, q, zb2, rs[:m]).any()
+    ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
+    from cryptography.hazmat.primitives import hashes
+    from cryptography.hazmat.primitives.asymmetric.utils import Prehashed, encode_dss_signature
+
+    crv, alg = (ec.SECP256R1(), hashes.SHA256()) if curve == "p256r1" else (ec.SECP384R1(), hashes.SHA384())
+    for i in range(nk, nk + 64):
+        x, y = c.dec(q[i].tobytes())
+        pub = ec.EllipticCurvePublicNumbers(x, y, crv).public_key()
+        r_, s_ = int.from_bytes(rs[i, : c.sbytes].tobytes(), "big"), int.from_bytes(rs[i, c.sbytes:].tobytes(), "big")
+        pub.verify(encode_dss_signature(r_, s_), zb[i].tobytes(), ec.ECDSA(Prehashed(alg)))   # raises on a bad signature
+
+
 # ---- wire formats either side of the path (SURVEY §8 f.1) -------------------------------------------
 @pytest.mark.parametrize("curve", CURVES)
 def test_wei_decompress(ctx, coracle, golden, curve):

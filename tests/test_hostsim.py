@@ -172,6 +172,52 @@ def test_wei_mul(hs, golden, coracle, cid, curve):
         assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
 
 
+@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1")])
+def test_ecdsa_sign(hs, golden, coracle, cid, curve):
+    """Device code of sign_hashed (ecdsa.rs:165-184) against the RFC 6979 vectors (d, k, message -> r, s;
+    ecdsa.rs:808-878), the big-int oracle on random (d, k, z), and the refusals: zero secret, zero nonce,
+    non-canonical scalars.  Every produced signature verifies (C oracle)."""
+    import hashlib
+
+    _, k = hs
+    c = R.WCURVES[curve]
+    v = golden["ecdsa_rfc6979"][curve]
+    d0 = int(v["d"], 16)
+    ds, ks, zs, want = [], [], [], []
+    for kat in v["kats"]:
+        dg = hashlib.new(kat["alg"], kat["message"].encode()).digest()
+        z = int.from_bytes(R.ecdsa_digest_to_scalar(c, dg), "big")
+        ds.append(d0)
+        ks.append(int(kat["k"], 16))
+        zs.append(z)
+        want.append(kat["r"].rjust(2 * c.sbytes, "0") + kat["s"].rjust(2 * c.sbytes, "0"))
+    g = rng(90 + cid)
+    for _ in range(12):
+        ds.append(int.from_bytes(g.bytes(c.sbytes + 8), "big") % (c.n - 1) + 1)
+        ks.append(int.from_bytes(g.bytes(c.sbytes + 8), "big") % (c.n - 1) + 1)
+        zs.append(int.from_bytes(g.bytes(c.sbytes + 8), "big") % c.n)
+    nk = len(v["kats"])
+    bad = [(0, 5, 7), (5, 0, 7), (c.n, 5, 7), (5, c.n, 7), (5, 6, c.n)]
+    for d, kk, z in bad:
+        ds.append(d)
+        ks.append(kk)
+        zs.append(z)
+    n = len(ds)
+    tob = lambda xs: rows([x.to_bytes(c.sbytes, "big") for x in xs])
+    db, kb, zb = tob(ds), tob(ks), tob(zs)
+    rs = np.zeros((n, 2 * c.sbytes), dtype=np.uint8)
+    ok = np.zeros(n, dtype=np.uint8)
+    k.hs_ecdsa_sign(cid, p(db), p(kb), p(zb), ctypes.c_size_t(n), p(rs), p(ok))
+    assert list(ok) == [1] * (n - len(bad)) + [0] * len(bad) and not rs[n - len(bad):].any()
+    for i in range(nk):
+        assert rs[i].tobytes().hex() == want[i]
+    for i in range(n - len(bad)):
+        assert rs[i].tobytes() == R.ecdsa_sign_hashed(c, ds[i], ks[i], zs[i])
+    m = n - len(bad)
+    q = rows([c.enc(c.mul(d, c.G)) for d in ds[:m]])
+    assert coracle.ecdsa_verify_hashed(curve, q, zb[:m], rs[:m]).all()
+
+
 def test_ed25519_keygen_and_sign(hs, golden):
     """Device code of expand_secret / public_from_seed / sign_with_public (ed25519.rs:61-110) against
     RFC 8032 TEST 1-3 (seed, public key, message, signature: ed25519.rs:271-290) and the big-int oracle
