@@ -122,6 +122,38 @@ impl BatchContext {
             .collect())
     }
 
+    /// Batch sibling of `ed25519::SecretKey::sign` (src/protocol/ed25519.rs:112) on raw messages.
+    /// NOT constant-time on the device.
+    pub fn ed25519_sign_batch(&self, seeds: &[[u8; 32]], messages: &[&[u8]]) -> Result<Vec<[u8; 64]>, BatchError> {
+        if seeds.len() != messages.len() {
+            return Err(BatchError::InvalidArgument("length mismatch".into()));
+        }
+        let n = seeds.len();
+        let mut off = Vec::with_capacity(n + 1);
+        let mut blob = Vec::new();
+        off.push(0u64);
+        for m in messages {
+            blob.extend_from_slice(m);
+            off.push(blob.len() as u64);
+        }
+        blob.push(0);
+        let mut sig = vec![[0u8; 64]; n];
+        let rc = unsafe {
+            ecb_ed25519_sign(self.ctx, seeds.as_ptr() as *const u8, ptr::null(), blob.as_ptr(), off.as_ptr(), n, sig.as_mut_ptr() as *mut u8)
+        };
+        self.check(rc, usize::MAX)?;
+        Ok(sig)
+    }
+
+    /// Batch sibling of `ed25519::SecretKey::public_key` (src/protocol/ed25519.rs:81).
+    pub fn ed25519_public_key_batch(&self, seeds: &[[u8; 32]]) -> Result<Vec<[u8; 32]>, BatchError> {
+        let n = seeds.len();
+        let mut out = vec![[0u8; 32]; n];
+        let rc = unsafe { ecb_ed25519_public_from_seed(self.ctx, seeds.as_ptr() as *const u8, n, out.as_mut_ptr() as *mut u8) };
+        self.check(rc, usize::MAX)?;
+        Ok(out)
+    }
+
     /// Batch sibling of `p256r1::PointAffine::decompress(&x, sign)` (src/curve/fiat/curve_macros.rs:221 ->
     /// src/curve/affine.rs:48).  `None` where the reference's `CtOption` is empty.
     pub fn p256r1_decompress_batch(&self, xs: &[p256r1::FieldElement], signs: &[Sign]) -> Result<Vec<Option<p256r1::PointAffine>>, BatchError> {
