@@ -575,7 +575,10 @@ ECB_DEV void ed25519_hash_k_body(size_t idx, const unsigned char* a_enc, const u
     const unsigned char* M = msgs + off[idx];
     size_t mlen = (size_t)(off[idx + 1] - off[idx]);
     unsigned char dg[64];
-    sha512_bytes(dg, 64 + mlen, [&](size_t pos) -> unsigned char { return pos < 32 ? R[pos] : (pos < 64 ? A[pos - 32] : M[pos - 64]); });
+    u32 pw[16];                 // R || A as sixteen little-endian words (both 16-byte aligned)
+    ld_words<8>(pw, reinterpret_cast<const u32*>(R));
+    ld_words<8>(pw + 8, reinterpret_cast<const u32*>(A));
+    sha512_prefixed<16>(dg, [&](int i) -> u32 { return pw[i]; }, M, mlen);
     u32 kw[8];
     ed25519_reduce_wide(kw, dg);
     ECB_UNROLL
@@ -598,7 +601,9 @@ ECB_DEV void ed25519_hash_k_body(size_t idx, const unsigned char* a_enc, const u
 ECB_DEV void ed25519_expand_body(size_t idx, const unsigned char* seeds, u32* a_out, u32* prefix_out) {
     const unsigned char* S = seeds + idx * 32;
     unsigned char dg[64], wide[64];
-    sha512_bytes(dg, 32, [&](size_t pos) -> unsigned char { return S[pos]; });
+    u32 sw[8];
+    ld_words<8>(sw, reinterpret_cast<const u32*>(S));
+    sha512_prefixed<8>(dg, [&](int i) -> u32 { return sw[i]; }, nullptr, 0);
     ECB_UNROLL
     for (int i = 0; i < 32; i++) { wide[i] = dg[i]; wide[32 + i] = 0; }
     wide[0] &= 248;
@@ -617,7 +622,9 @@ ECB_DEV void ed25519_sign_nonce_body(size_t idx, const u32* prefix, const unsign
     const unsigned char* M = msgs + off[idx];
     size_t mlen = (size_t)(off[idx + 1] - off[idx]);
     unsigned char dg[64];
-    sha512_bytes(dg, 32 + mlen, [&](size_t pos) -> unsigned char { return pos < 32 ? (unsigned char)(P[pos >> 2] >> (8 * (pos & 3))) : M[pos - 32]; });
+    u32 pw[8];
+    ld_words<8>(pw, P);
+    sha512_prefixed<8>(dg, [&](int i) -> u32 { return pw[i]; }, M, mlen);
     u32 r[8];
     ed25519_reduce_wide(r, dg);
     ECB_UNROLL
@@ -632,7 +639,10 @@ ECB_DEV void ed25519_sign_finish_body(size_t idx, unsigned char* sig, const unsi
     const unsigned char* M = msgs + off[idx];
     size_t mlen = (size_t)(off[idx + 1] - off[idx]);
     unsigned char dg[64];
-    sha512_bytes(dg, 64 + mlen, [&](size_t pos) -> unsigned char { return pos < 32 ? R[pos] : (pos < 64 ? A[pos - 32] : M[pos - 64]); });
+    u32 pw[16];
+    ld_words<8>(pw, reinterpret_cast<const u32*>(R));
+    ld_words<8>(pw + 8, reinterpret_cast<const u32*>(A));
+    sha512_prefixed<16>(dg, [&](int i) -> u32 { return pw[i]; }, M, mlen);
     u32 kw[8];
     ed25519_reduce_wide(kw, dg);
     FL::el k, a, r, r2, one, t;

@@ -82,6 +82,63 @@ ECB_DEV void sha512_bytes(unsigned char* digest, size_t len, BYTE_AT byte_at, bo
     }
 }
 
+// The same hash with the first 4 NPW bytes given as NPW little-endian 32-bit words held in registers
+// (pre(i), i a compile-time constant after unrolling: R || A of a signature, a seed, a nonce prefix)
+// followed by the message bytes M[0, mlen): block 0 is assembled from registers, message words come
+// from 8-byte loads when the address allows it.  Byte-for-byte the digest of sha512_bytes.
+ECB_DEV u32 sha_bswap32(u32 x) { return (x >> 24) | ((x >> 8) & 0xff00u) | ((x << 8) & 0xff0000u) | (x << 24); }
+ECB_DEV w64 sha_msg_w64(const unsigned char* M, size_t mlen, size_t off) {
+    if (off + 8 <= mlen) {
+        const unsigned char* p = M + off;
+        if ((reinterpret_cast<size_t>(p) & 7u) == 0) {
+            w64 v = *reinterpret_cast<const w64*>(p);
+            return ((w64)sha_bswap32((u32)v) << 32) | (w64)sha_bswap32((u32)(v >> 32));
+        }
+    }
+    w64 v = 0;
+    ECB_NOUNROLL
+    for (int j = 0; j < 8; j++) {
+        size_t pos = off + (size_t)j;
+        unsigned b = pos < mlen ? (unsigned)M[pos] : (pos == mlen ? 0x80u : 0u);
+        v = (v << 8) | b;
+    }
+    return v;
+}
+template <int NPW, class PRE>
+ECB_DEV void sha512_prefixed(unsigned char* digest, PRE pre, const unsigned char* M, size_t mlen) {
+    static_assert(NPW % 2 == 0 && NPW <= 28, "prefix must be whole 64-bit words inside the first block");
+    const size_t len = 4 * (size_t)NPW + mlen;
+    Sha512 st;
+    st.init(false);
+    w64 w[16];
+    const size_t nblocks = (len + 17 + 127) / 128;
+    ECB_UNROLL
+    for (int i = 0; i < 16; i++) {
+        if (i < NPW / 2) w[i] = ((w64)sha_bswap32(pre(2 * i)) << 32) | (w64)sha_bswap32(pre(2 * i + 1));
+        else w[i] = sha_msg_w64(M, mlen, (size_t)(8 * i - 4 * NPW));
+    }
+    if (nblocks == 1) {
+        w[14] = (w64)(len >> 61);
+        w[15] = (w64)len << 3;
+    }
+    st.compress(w);
+    ECB_NOUNROLL
+    for (size_t blk = 1; blk < nblocks; blk++) {
+        ECB_UNROLL
+        for (int i = 0; i < 16; i++) w[i] = sha_msg_w64(M, mlen, blk * 128 + (size_t)(8 * i) - 4 * (size_t)NPW);
+        if (blk == nblocks - 1) {
+            w[14] = (w64)(len >> 61);
+            w[15] = (w64)len << 3;
+        }
+        st.compress(w);
+    }
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) {
+        ECB_UNROLL
+        for (int j = 0; j < 8; j++) digest[8 * i + j] = (unsigned char)(st.h[i] >> (56 - 8 * j));
+    }
+}
+
 // ---- SHA-256 (ECDSA over p256r1: src/protocol/ecdsa.rs:288-292 hash_to_scalar) --------------------
 ECB_DEV u32 rotr32(u32 x, int n) { return (x >> n) | (x << (32 - n)); }
 template <class BYTE_AT>
