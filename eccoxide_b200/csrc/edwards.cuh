@@ -116,6 +116,39 @@ ECB_DEV void ge_madd(ge_p3& r, const ge_p3& p, const ge_niels& q) {
     if (WITH_T) F::mul(r.T, E, H);
 }
 
+// the same with the T output decided at run time (one code body for every window of the comb loop)
+ECB_DEV void ge_madd_rt(ge_p3& r, const ge_p3& p, const ge_niels& q, bool with_t) {
+    fe25519 A, B, C, D, E, Fv, G, H;
+    F::sub(A, p.Y, p.X);
+    F::mul(A, A, q.ym);
+    F::add(B, p.Y, p.X);
+    F::mul(B, B, q.yp);
+    F::mul(C, p.T, q.t2d);
+    F::dbl(D, p.Z);
+    F::sub(E, B, A);
+    F::sub(Fv, D, C);
+    F::add(G, D, C);
+    F::add(H, B, A);
+    F::mul(r.X, E, Fv);
+    F::mul(r.Y, G, H);
+    F::mul(r.Z, Fv, G);
+    if (with_t) F::mul(r.T, E, H);
+}
+// r = identity + q: the addition formulas with (X, Y, Z, T) = (0, 1, 1, 0) leave
+// E = yp - ym, H = yp + ym, F = G = 2, so r = (2E : 2H : 4 : E H) — one product instead of seven.
+// The niels identity (1, 1, 0) gives (0 : 4 : 4 : 0), the identity again.
+ECB_DEV void ge_from_niels(ge_p3& r, const ge_niels& q) {
+    fe25519 E, H, two;
+    F::sub(E, q.yp, q.ym);
+    F::add(H, q.yp, q.ym);
+    F::dbl(r.X, E);
+    F::dbl(r.Y, H);
+    F::set_one(two);
+    F::dbl(two, two);
+    F::dbl(r.Z, two);
+    F::mul(r.T, E, H);
+}
+
 // r = p + q, q projective cached. 8M
 template <bool WITH_T, bool NI = false>
 ECB_DEV void ge_add_cached(ge_p3& r, const ge_p3& p, const ge_cached& q) {

@@ -178,7 +178,9 @@ ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, con
             ld_words<8>(e.t2d.v, src + 16);
         }
         ge_niels_cneg(e, neg);
-        ge_madd<true>(acc, acc, e);
+        // first window: identity + entry needs one product; last window: nobody reads T
+        if (i == 0) ge_from_niels(acc, e);
+        else ge_madd_rt(acc, acc, e, i != nwin - 1);
     }
     plane_st<8>(planes + 0 * 8 * n, n, idx, acc.X.v);
     plane_st<8>(planes + 1 * 8 * n, n, idx, acc.Y.v);
