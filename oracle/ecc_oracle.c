@@ -1086,7 +1086,7 @@ long orc_ecdsa_verify_hashed(int curve, const u8* q_xy, const u8* z_be, const u8
     t.fn = j_ecdsa; t.curve = curve; t.a = q_xy; t.b = z_be; t.c = rs_be; t.o = ok;
     return run_jobs(&t, n, nthreads, code);
 }
-/* comb-table entry (window i, digit j) as affine bytes, for pinning against params/comb/*.rs */
+/* comb-table entry (window i, digit j) as affine bytes, for pinning against params/comb/<curve>.rs */
 /* PointAffine::decompress batch: sign[i] = 0 Positive (even y) / 1 Negative (odd y); ok[i] = present */
 long orc_wei_decompress(int curve, const u8* x_be, const u8* sign, size_t n, u8* out_xy, u8* ok, int nthreads) {
     job j = {0};

@@ -467,13 +467,13 @@ static void T(curve_init)(T(curve)* c, const u8* p_be, const u8* n_be, const u8*
         w[1] = base;
         for (int j = 2; j < 16; j++) T(pt_add)(c, &w[j], &w[j - 1], &base);
         for (int j = 1; j < 16; j++) {
-            T(fe) x, y;
+            T(fe) x = c->fp.r1, y = c->fp.r1;   /* multiples of G below the group order are finite */
             T(pt_to_affine)(c, &x, &y, &w[j]);
             w[j].X = x; w[j].Y = y; w[j].Z = c->fp.r1;
         }
         T(pt) nb;
         T(pt_add)(c, &nb, &w[15], &base); /* 16 * base */
-        T(fe) x, y;
+        T(fe) x = c->fp.r1, y = c->fp.r1;
         T(pt_to_affine)(c, &x, &y, &nb);
         base.X = x; base.Y = y; base.Z = c->fp.r1;
     }
