@@ -41,6 +41,9 @@ struct Mont {
     static constexpr bool BLOCK_INV = false;  // wider fields: the per-thread form of the batch inversion is faster (registers)
     typedef P P_;
     typedef fe_mont<P::N> el;
+    // p256r1 and p384r1 keep elements "loose": any representative below 2^(32 N), not necessarily
+    // below p (see the note above add()); the generic primes stay canonical
+    static constexpr bool LOOSE = MontKind<P>::kind == 1 || MontKind<P>::kind == 2;
 
     ECB_DEV static void set_zero(el& r) {
         ECB_UNROLL
@@ -111,6 +114,17 @@ struct Mont {
     // r = t + c * (2^256 - p) mod 2^256 for c in {0, 1};  2^256 - p = 2^224 - 2^192 - 2^96 + 1
     ECB_DEV static u32 fold_carry(el& r, const u32* t, u32 c) {
         const u32 m = 0u - c;
+        if constexpr (MontKind<P>::kind == 2) {
+            // 2^384 - p = 2^128 + 2^96 - 2^32 + 1 = limbs {1, ffffffff, ffffffff, 0, 1, 0, ...}
+            r.v[0] = add_cc(t[0], c);
+            r.v[1] = addc_cc(t[1], m);
+            r.v[2] = addc_cc(t[2], m);
+            r.v[3] = addc_cc(t[3], 0u);
+            r.v[4] = addc_cc(t[4], c);
+            ECB_UNROLL
+            for (int i = 5; i < N; i++) r.v[i] = addc_cc(t[i], 0u);
+            return addc(0u, 0u);
+        }
         r.v[0] = add_cc(t[0], c);
         r.v[1] = addc_cc(t[1], 0u);
         r.v[2] = addc_cc(t[2], 0u);
@@ -124,6 +138,16 @@ struct Mont {
     // r = t - c * (2^256 - p) mod 2^256 ; returns the borrow
     ECB_DEV static u32 fold_borrow(el& r, const u32* t, u32 c) {
         const u32 m = 0u - c;
+        if constexpr (MontKind<P>::kind == 2) {
+            r.v[0] = sub_cc(t[0], c);
+            r.v[1] = subc_cc(t[1], m);
+            r.v[2] = subc_cc(t[2], m);
+            r.v[3] = subc_cc(t[3], 0u);
+            r.v[4] = subc_cc(t[4], c);
+            ECB_UNROLL
+            for (int i = 5; i < N; i++) r.v[i] = subc_cc(t[i], 0u);
+            return subc(0u, 0u) & 1u;
+        }
         r.v[0] = sub_cc(t[0], c);
         r.v[1] = subc_cc(t[1], 0u);
         r.v[2] = subc_cc(t[2], 0u);
@@ -184,13 +208,14 @@ struct Mont {
         for (int j = O + 15; j <= 24; j++) T[j] = addc_cc(T[j], 0u);
         (void)addc(0u, 0u);
     }
-    // T: 25 limbs, T[24] = 0 on entry, value < p^2.  r = T / 2^384 mod p, canonical.
+    // T: 25 limbs, T[24] = 0 on entry, value < 2^768.  r = T / 2^384 mod p, loose (< 2^384).
     ECB_DEV static void p384_reduce(el& r, u32* T) {
         p384_round<0>(T);
         p384_round<3>(T);
         p384_round<6>(T);
         p384_round<9>(T);
-        final_sub(r, T + 12, T[24]);
+        // T[12..24] < 2^384 + p: fold the carry word by adding 2^384 - p once; the result is < 2^384 (loose)
+        fold_carry(r, T + 12, T[24]);
     }
 
     ECB_DEV static void mul(el& r, const el& a, const el& b) {
@@ -343,7 +368,7 @@ struct Mont {
     ECB_DEV static void add(el& r, const el& a, const el& b) {
         u32 t[N];
         u32 c = add_n<N>(t, a.v, b.v);
-        if constexpr (MontKind<P>::kind == 1) {
+        if constexpr (LOOSE) {
             u32 c2 = fold_carry(r, t, c);
             if (c2) fold_carry(r, r.v, 1u);
             return;
@@ -353,7 +378,7 @@ struct Mont {
     ECB_DEV static void sub(el& r, const el& a, const el& b) {
         u32 t[N];
         u32 bw = sub_n<N>(t, a.v, b.v);
-        if constexpr (MontKind<P>::kind == 1) {
+        if constexpr (LOOSE) {
             u32 b2 = fold_borrow(r, t, bw);
             if (b2) fold_borrow(r, r.v, 1u);
             return;
@@ -370,7 +395,7 @@ struct Mont {
     }
     // canonical representative (< p) of a possibly loose value
     ECB_DEV static void canon(el& r, const el& a) {
-        if constexpr (MontKind<P>::kind == 1) {
+        if constexpr (LOOSE) {
             final_sub(r, a.v, 0u);
             return;
         }
@@ -382,7 +407,7 @@ struct Mont {
         u32 o = 0;
         ECB_UNROLL
         for (int i = 0; i < N; i++) o |= a.v[i];
-        if constexpr (MontKind<P>::kind == 1) {  // loose: 0 or p
+        if constexpr (LOOSE) {  // loose: 0 or p
             u32 q = 0;
             ECB_UNROLL
             for (int i = 0; i < N; i++) q |= a.v[i] ^ P::mod(i);
@@ -391,7 +416,7 @@ struct Mont {
         return o == 0 ? 1u : 0u;
     }
     ECB_DEV static u32 eq(const el& a, const el& b) {
-        if constexpr (MontKind<P>::kind == 1) {
+        if constexpr (LOOSE) {
             el d;
             sub(d, a, b);
             return is_zero(d);
@@ -419,7 +444,7 @@ struct Mont {
         set_zero(one);
         one.v[0] = 1;
         mul(t, a, one);
-        if constexpr (MontKind<P>::kind == 1) final_sub(t, t.v, 0u);  // canonical representative
+        if constexpr (LOOSE) final_sub(t, t.v, 0u);  // canonical representative
         ECB_UNROLL
         for (int i = 0; i < N; i++) w[i] = t.v[i];
     }

@@ -70,10 +70,16 @@ def test_montgomery_fields(hs, field, mod, n):
     r = np.zeros(n, dtype=np.uint32)
     cases = [(0, 0), (1, mod - 1), (mod - 1, mod - 1), (Rm % mod, 1)]
     cases += [(int.from_bytes(g.bytes(48), "little") % mod, int.from_bytes(g.bytes(48), "little") % mod) for _ in range(100)]
-    loose = field == 0  # p256 field elements are kept "loose" (< 2^256, congruent): see mont.cuh
-    if loose:  # any 256-bit value is a valid operand, including the ones that need a second fold
-        cases += [(Rm - 1, Rm - 1), (Rm - 1, mod), (mod, mod), (Rm - 2**200, Rm - 5), (0, Rm - 1), (3, Rm - 2), (mod + 1, 2)]
-        cases += [(int.from_bytes(g.bytes(32), "little"), int.from_bytes(g.bytes(32), "little")) for _ in range(100)]
+    loose = field in (0, 2)  # p256r1 / p384r1 field elements are kept "loose" (< 2^(32 n), congruent): see mont.cuh
+    if loose:  # any n-limb value is a valid operand, including the ones that need a second fold
+        K = Rm - mod
+        cases += [(Rm - 1, Rm - 1), (Rm - 1, mod), (mod, mod), (Rm - 2**200, Rm - 5), (0, Rm - 1), (3, Rm - 2), (mod + 1, 2),
+                  (Rm - 1, Rm - K), (Rm - K, Rm - K), (K - 1, K), (0, K), (K, Rm - 1), (Rm - K - 1, K + 1)]
+        cases += [(int.from_bytes(g.bytes(4 * n), "little"), int.from_bytes(g.bytes(4 * n), "little")) for _ in range(150)]
+        # structured limbs (all-ones / all-zero words) exercise the carry paths of the multiplication-free reduction
+        for _ in range(150):
+            pick = lambda: sum([0, 0xFFFFFFFF, 1, 0xFFFFFFFE, int(g.integers(0, 2**32))][int(g.integers(0, 5))] << (32 * i) for i in range(n))
+            cases.append((pick(), pick()))
     for a, b in cases:
         aw, bw = words(a, n), words(b, n)
         for op, exp in ((0, a * b * Ri), (1, a * a * Ri), (2, a + b), (3, a - b), (4, -a), (5, a * Rm), (7, a * Ri)):
