@@ -2,7 +2,7 @@
 #include "tu_common.cuh"
 #include "dev_ops.h"
 
-static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul_base(size_t n, const u32* scalars, const u32* table, int W,
+static __global__ void __launch_bounds__(ECB_TPB, 5) k_ed25519_mul_base(size_t n, const u32* scalars, const u32* table, int W,
                                                                int nwin, u32* planes, unsigned long long* status) {
     size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
     if (idx < n) ed25519_mul_base_body<false>(idx, n, scalars, table, W, nwin, planes, status);
@@ -85,7 +85,7 @@ int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32*
     return rc;
 }
 
-static __global__ void __launch_bounds__(ECB_TPB) k_x25519_base(size_t n, const u32* scalars, const u32* table, int W, int nwin,
+static __global__ void __launch_bounds__(ECB_TPB, 5) k_x25519_base(size_t n, const u32* scalars, const u32* table, int W, int nwin,
                                                           u32* planes) {
     size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
     if (idx < n) x25519_base_body(idx, n, scalars, table, W, nwin, planes);
