@@ -102,12 +102,12 @@ unsigned long long ecb_launch_count(ecb_ctx* ctx) { return ctx ? ctx->launches.l
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
     if (!ctx || !key) return ECB_ERR_INVALID_ARG;
     if (!strcmp(key, "ed25519_comb_w")) {
-        if (value < 4 || value > 24) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_comb_w must be in 4..24");
+        if (value != 0 && (value < 4 || value > 26)) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_comb_w must be 0 or in 4..26");
         ctx->opt_ed_w = value;
         return ECB_OK;
     }
     if (!strcmp(key, "p256r1_comb_w") || !strcmp(key, "p384r1_comb_w") || !strcmp(key, "bls12_381_g1_comb_w")) {
-        if (value < 4 || value > 22) return set_err(ctx, ECB_ERR_INVALID_ARG, "comb width must be in 4..22");
+        if (value != 0 && (value < 4 || value > 24)) return set_err(ctx, ECB_ERR_INVALID_ARG, "comb width must be 0 or in 4..24");
         ctx->opt_wei_w[key[1] == '2' ? 0 : (key[1] == '3' ? 1 : 2)] = value;
         return ECB_OK;
     }

@@ -69,7 +69,7 @@ struct ecb_ctx {
     std::vector<DevCtx*> devs;
     std::string err;
     std::mutex err_mu;
-    long opt_wei_w[3] = {20, 18, 20};  // generator comb widths: 13 / 22 / 13 windows, 436 MB / 277 MB / 654 MB tables
+    long opt_wei_w[3] = {0, 0, 0};     // generator comb widths (p256r1, p384r1, bls12_381 g1); 0 = by free memory: 24 / 22 / 24 (11 / 18 / 11 windows, 5.9 / 3.6 / 8.9 GB) above 100 GB free, else 20 / 18 / 20
     // Ed25519 comb width; 0 = pick by free device memory (24: 11 windows, 8.9 GB table; 20: 13 windows, 0.65 GB;
     // 16: 16 windows, 50 MB).  Measured at n = 2^20: w=16 772 M/s, 20 907, 22 969, 24 1041 M/s — the kernel is
     // integer-pipe-bound, so time follows the window count; the random table reads (96 B per window) stay

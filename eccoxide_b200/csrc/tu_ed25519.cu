@@ -31,7 +31,8 @@ static int ed_pick_w(ecb_ctx* ctx) {
     if (ctx->opt_ed_w) return (int)ctx->opt_ed_w;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 16;
-    if (free_b > ((size_t)64 << 30)) return 24;
+    if (free_b > ((size_t)110 << 30)) return 26;   // 10 windows, 32 GB table (+ 43 GB while it is built)
+    if (free_b > ((size_t)40 << 30)) return 24;
     if (free_b > ((size_t)8 << 30)) return 20;
     return 16;
 }

@@ -57,8 +57,8 @@ int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out);
 void ecb_destroy(ecb_ctx* ctx);
 const char* ecb_last_error(ecb_ctx* ctx);
 int ecb_device_count(ecb_ctx* ctx);
-/* tunables, before first use: "ed25519_comb_w" (window width of the fixed-base comb, 4..24; 0 = by free memory),
- * "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w" (generator combs of the Weierstrass curves, 4..22),
+/* tunables, before first use: "ed25519_comb_w" (window width of the fixed-base comb, 4..26; 0 = by free memory),
+ * "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w" (generator combs of the Weierstrass curves, 4..24; 0 = by free memory),
  * "chunk" (elements per pipeline chunk), "ramp" (halvings of the chunk size at both ends of a batch, 0..4), "inv_per_thread" (batch-inversion chain length), "inv_block" (batch inversion: 0 one inversion per thread, 2 one per block, 1 (default) per field as measured), "profile" (1: record CUDA events around the kernels of
  * every call on the launching stream, read back with ecb_profile_collect) */
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value);

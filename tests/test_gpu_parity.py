@@ -874,7 +874,7 @@ def test_batch_inversion_forms_agree(ctx, coracle, mode):
 def test_options_are_validated(ctx):
     from eccoxide_b200 import EccBatchError
 
-    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 25), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0), ("inv_block", 3), ("ramp", 5)):
+    for key, val in (("no_such_option", 1), ("ed25519_comb_w", 3), ("ed25519_comb_w", 27), ("chunk", 0), ("p256r1_comb_w", 99), ("inv_per_thread", 0), ("inv_block", 3), ("ramp", 5)):
         with pytest.raises(EccBatchError) as e:
             ctx.set_option(key, val)
         assert e.value.code == -2
