@@ -36,7 +36,25 @@ static int ed_pick_w(ecb_ctx* ctx) {
     if (free_b > ((size_t)8 << 30)) return 20;
     return 16;
 }
+static int ed25519_build_table_w(ecb_ctx* ctx, DevCtx& d, int W);
+// In automatic mode (option 0) a width whose table or build buffers cannot be allocated falls back
+// to the next narrower even width instead of failing the call.
 int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
+    for (;;) {
+        int rc = ed25519_build_table_w(ctx, d, W);
+        if (rc == ECB_OK || ctx->opt_ed_w != 0 || W <= 16) return rc;
+        (void)cudaGetLastError();
+        if (d.ed_table) cudaFree(d.ed_table);
+        d.ed_table = nullptr;
+        for (DevBuf* b : {&d.cur->planes, &d.cur->pf}) {
+            if (b->p) cudaFree(b->p);
+            b->p = nullptr;
+            b->cap = 0;
+        }
+        W -= 2;
+    }
+}
+static int ed25519_build_table_w(ecb_ctx* ctx, DevCtx& d, int W) {
     int nwin = (254 + W - 1) / W;
     size_t ntab = (size_t)nwin << (W - 1);
     if (d.ed_table) CU(cudaFree(d.ed_table));
