@@ -45,3 +45,29 @@ def test_product_arm_refuses_to_run_without_a_gpu():
         pytest.skip("a CUDA device is present")
     r = _run(["--steps", "1", "--warmup", "1", "--no-cpu"])
     assert r.returncode != 0 and "no CPU fallback" in r.stderr and not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+@pytest.mark.gpu
+def test_product_arm_prints_the_contract_line_on_a_gpu():
+    """One short run of the default workload on cuda:0: one JSON line with the base contract's keys plus
+    roofline / cpu_baseline / e2e / clocks / gpu_launches, a green parity check of that very run, and
+    kernel launches counted (a zero would mean a fallback)."""
+    r = _run(["--steps", "3", "--warmup", "3", "--extra", ""], timeout=600)
+    assert r.returncode == 0, r.stderr[-800:]
+    lines = [ln for ln in r.stdout.strip().splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
+    assert d["config"]["workload"] == "ed25519_mul_base" and d["parity_check"] is True
+    assert d["gpu_launches"] >= 2 * d["steps"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in d["roofline"], key
+    assert d["roofline"]["peak"] > 1 and abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
+    e = d["e2e"]
+    assert e["h2d_bytes_per_step"] == 32 << 20 and e["d2h_bytes_per_step"] == 64 << 20 and 0 < e["value"] < d["value"]
+    c = d["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and 0 < c["value"] < d["value"] / 10
+    assert d["clocks"]["sm_mhz"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
