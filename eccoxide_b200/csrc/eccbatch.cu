@@ -173,6 +173,22 @@ struct HostOut {
 };
 
 // op(d, stream, din[], dout[], n) enqueues the kernels for one chunk
+// On an error path a host entry point must not return while copies it enqueued still read or write
+// the caller's buffers: drain every slot stream of the device and reset the slot state.
+struct SlotDrain {
+    DevCtx& d;
+    bool armed = true;
+    ~SlotDrain() {
+        if (!armed) return;
+        for (Slot& sl : d.slots) {
+            if (sl.stream) cudaStreamSynchronize(sl.stream);
+            if (sl.hi) cudaStreamSynchronize(sl.hi);
+            sl.busy = false;
+        }
+        d.cur = &d.slots[0];
+    }
+};
+
 // Chunk schedule of one device's slice [lo, hi): the first chunks ramp up from chunk / 2^ramp and the
 // last ones ramp back down, so that the pipeline (copy in | kernels | copy out, ECB_NSLOT chunks in
 // flight) fills and drains on small chunks: the first copy-in and the last copy-out, which nothing
@@ -222,6 +238,7 @@ static int run_sharded(ecb_ctx* ctx, size_t n, const std::vector<HostArg>& ins, 
         std::lock_guard<std::mutex> g(d.mu);
         auto body = [&]() -> int {
             CU(cudaSetDevice(d.dev));
+            SlotDrain drain{d};
             // retire the chunk in flight on `sl`: wait, then look at its status word
             auto retire = [&](Slot& sl) -> int {
                 if (!sl.busy) return ECB_OK;
@@ -274,6 +291,7 @@ static int run_sharded(ecb_ctx* ctx, size_t n, const std::vector<HostArg>& ins, 
                 if (rcb == ECB_OK) rcb = r2;
             }
             d.cur = &d.slots[0];
+            drain.armed = rcb != ECB_OK;
             return rcb;
         };
         rc[di] = body();
@@ -413,6 +431,7 @@ int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, 
         std::lock_guard<std::mutex> g(d.mu);
         auto body = [&]() -> int {
             CU(cudaSetDevice(d.dev));
+            SlotDrain drain{d};
             size_t ci = 0;
             for (size_t c0 = lo; c0 < hi; c0 += ctx->opt_chunk, ci++) {
                 size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
@@ -445,6 +464,7 @@ int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, 
                 CU(cudaStreamSynchronize(sl.stream));
             }
             d.cur = &d.slots[0];
+            drain.armed = false;
             return ECB_OK;
         };
         rc[di] = body();
@@ -487,6 +507,7 @@ int ecb_ed25519_sign(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, con
         std::lock_guard<std::mutex> g(d.mu);
         auto body = [&]() -> int {
             CU(cudaSetDevice(d.dev));
+            SlotDrain drain{d};
             size_t ci = 0;
             for (size_t c0 = lo; c0 < hi; c0 += ctx->opt_chunk, ci++) {
                 size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
@@ -518,6 +539,7 @@ int ecb_ed25519_sign(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, con
                 CU(cudaStreamSynchronize(sl.stream));
             }
             d.cur = &d.slots[0];
+            drain.armed = false;
             return ECB_OK;
         };
         rc[di] = body();
@@ -567,6 +589,7 @@ int ecb_ecdsa_verify(ecb_ctx* ctx, int curve, int hash, const uint8_t* q_xy, con
         };
         auto body = [&]() -> int {
             CU(cudaSetDevice(d.dev));
+            SlotDrain drain{d};
             size_t ci = 0;
             for (size_t c0 = lo; c0 < hi && bad[di] == ~0ull; c0 += ctx->opt_chunk, ci++) {
                 size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
@@ -601,6 +624,7 @@ int ecb_ecdsa_verify(ecb_ctx* ctx, int curve, int hash, const uint8_t* q_xy, con
                 if (r2 == ECB_OK) r2 = r3;
             }
             d.cur = &d.slots[0];
+            drain.armed = r2 != ECB_OK;
             return r2;
         };
         rc[di] = body();

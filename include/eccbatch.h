@@ -13,7 +13,8 @@
  *     encodings (curve25519: little-endian; Weierstrass curves: big-endian), element i at i*size
  *   - host entry points copy host->device, run the kernels and copy back before returning
  *     (blocking); *_dev entry points take device pointers on device `dev_index` of the context and
- *     enqueue on `stream` (a cudaStream_t) without synchronising
+ *     enqueue on `stream` (a cudaStream_t) without synchronising; device pointers must be 16-byte
+ *     aligned (the kernels move elements with 128-bit loads and stores; cudaMalloc gives 256)
  *   - a batch is sharded by contiguous slice over the devices of the context; no collective
  *   - threading: host entry points may be called concurrently on one context (calls are serialised
  *     per device); the *_dev entry points use the context's slot-0 work buffers without locking, so
