@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(256) k_imad_probe(u32* out, int iters) {
         for (int i = 0; i < 8; i++) s ^= a[i];
         out[tid] = s;
     } else if (V == 1) {
-        unsigned long long a[8], cadd = ((unsigned long long)x[0] << 32) | y;
+        unsigned long long a[8];
         for (int i = 0; i < 8; i++) a[i] = ((unsigned long long)x[i] << 32) | (tid + i + 1);
         for (int it = 0; it < iters; it++) {
 #pragma unroll
