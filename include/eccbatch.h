@@ -58,10 +58,18 @@ int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out);
 void ecb_destroy(ecb_ctx* ctx);
 const char* ecb_last_error(ecb_ctx* ctx);
 int ecb_device_count(ecb_ctx* ctx);
-/* tunables, before first use: "ed25519_comb_w" (window width of the fixed-base comb, 4..26; 0 = by free memory),
- * "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w" (generator combs of the Weierstrass curves, 4..24; 0 = by free memory),
- * "chunk" (elements per pipeline chunk), "ramp" (halvings of the chunk size at both ends of a batch, 0..4), "inv_per_thread" (batch-inversion chain length), "inv_block" (batch inversion: 0 one inversion per thread, 2 one per block, 1 (default) per field as measured), "profile" (1: record CUDA events around the kernels of
- * every call on the launching stream, read back with ecb_profile_collect) */
+/* Tunables (set before first use; unknown keys and out-of-range values give ECB_ERR_INVALID_ARG):
+ *   "ed25519_comb_w"        window width of the Ed25519 fixed-base comb, 4..26; 0 = by free device memory
+ *   "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w"
+ *                           generator combs of the Weierstrass curves, 4..24; 0 = by free device memory
+ *   "chunk"                 elements per pipeline chunk of the host entry points
+ *   "ramp"                  halvings of the chunk size at both ends of a batch, 0..4
+ *   "inv_per_thread"        batch-inversion chain length;  "inv_fill_per_sm": minimum inversion threads per SM
+ *   "inv_block"             batch inversion: 0 one inversion per thread, 2 one per block, 1 (default) per field as measured
+ *   "inv_hi"                1 (default): batch inversions of pipelined chunks run on a high-priority side stream
+ *   "dev_split"             1: split large device-resident batches over the slot streams (default 0)
+ *   "profile"               1: record CUDA events around the kernels of every call on the launching stream,
+ *                           read back with ecb_profile_collect */
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value);
 /* number of kernel launches issued by this context so far (bench.py's gpu_launches) */
 unsigned long long ecb_launch_count(ecb_ctx* ctx);
