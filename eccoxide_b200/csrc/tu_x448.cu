@@ -2,7 +2,7 @@
 #include "tu_common.cuh"
 #include "dev_ops.h"
 
-static __global__ void __launch_bounds__(ECB_TPB) k_x448(size_t n, const u32* scalars, const u32* us, u32* planes) {
+static __global__ void __launch_bounds__(ECB_TPB, 3) k_x448(size_t n, const u32* scalars, const u32* us, u32* planes) {
     size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
     if (idx < n) x448_body(idx, n, scalars, us, planes);
 }
