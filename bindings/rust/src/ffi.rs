@@ -49,6 +49,8 @@ extern "C" {
                             sig: *mut u8) -> c_int;
     pub fn ecb_ecdsa_sign_hashed(ctx: *mut ecb_ctx, curve_id: c_int, d_be: *const u8, k_be: *const u8, z_be: *const u8, n: usize,
                                  rs_be: *mut u8, ok: *mut u8) -> c_int;
+    pub fn ecb_ecdsa_sign(ctx: *mut ecb_ctx, curve_id: c_int, hash: c_int, d_be: *const u8, k_be: *const u8, msgs: *const u8,
+                          msg_off: *const u64, n: usize, rs_be: *mut u8, ok: *mut u8) -> c_int;
     pub fn ecb_wei_decompress(ctx: *mut ecb_ctx, curve_id: c_int, x_be: *const u8, sign: *const u8, n: usize, out_xy_be: *mut u8,
                               ok: *mut u8) -> c_int;
     pub fn ecb_bls12_381_g1_from_compressed(ctx: *mut ecb_ctx, enc: *const u8, n: usize, check_subgroup: c_int, out_xy_be: *mut u8,

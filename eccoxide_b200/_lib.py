@@ -71,6 +71,7 @@ SIGNATURES = {
     "ecb_ed25519_sign_dev": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_sign_hashed": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_sign_hashed_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "ecb_ecdsa_sign": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_debug_chunk_plan": (ctypes.c_long, [_sz, _sz, _sz, ctypes.c_long, _vp, _sz]),
     "ecb_debug_ed25519_table": (ctypes.c_long, [_vp, _int, _vp, _sz, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
 }

@@ -253,6 +253,25 @@ class Context:
         self._check(self._lib.ecb_ecdsa_sign_hashed(self._ctx, cid, _p(d), _p(k), _p(z), n, _p(out), _p(ok)))
         return out, ok.astype(bool)
 
+    def ecdsa_sign(self, curve, d_be, k_be, msgs, hash_bits=None, out=None, out_ok=None):
+        """ecdsa::sign on raw, ragged messages (hash on the device; not constant-time): (r || s rows, present)."""
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+        sb = SCALAR_BYTES[cid]
+        d = _rows(d_be, sb, "d_be")
+        k = _rows(k_be, sb, "k_be")
+        n = d.shape[0]
+        if k.shape[0] != n or len(msgs) != n:
+            raise ValueError("count mismatch")
+        if hash_bits is None:
+            hash_bits = 256 if sb == 32 else 384
+        off = np.zeros(n + 1, dtype=np.uint64)
+        off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
+        blob = np.frombuffer(b"".join(bytes(m) for m in msgs) + b"\0", dtype=np.uint8)
+        out = _out(out, (n, 2 * sb))
+        ok = _out(out_ok, (n,))
+        self._check(self._lib.ecb_ecdsa_sign(self._ctx, cid, int(hash_bits), _p(d), _p(k), _p(blob), _p(off), n, _p(out), _p(ok)))
+        return out, ok.astype(bool)
+
     def wei_decompress(self, curve, x_be, sign, out=None, out_ok=None):
         """PointAffine::decompress over a batch (affine.rs:48): (x || y rows, present)."""
         cid = CURVE_IDS[curve] if isinstance(curve, str) else curve

@@ -49,4 +49,8 @@ int dev_ecdsa_sign_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k,
                         cudaStream_t s);
 int dev_ecdsa_sign_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k, const u32* d_z, size_t n, u32* d_rs, unsigned char* d_ok,
                         cudaStream_t s);
+int dev_ecdsa_sign_msgs_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k, const unsigned char* d_msgs, const unsigned long long* d_off,
+                             int hash, size_t n, u32* d_rs, unsigned char* d_ok, cudaStream_t s);
+int dev_ecdsa_sign_msgs_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k, const unsigned char* d_msgs, const unsigned long long* d_off,
+                             int hash, size_t n, u32* d_rs, unsigned char* d_ok, cudaStream_t s);
 int dev_imad_probe(ecb_ctx* ctx, DevCtx& d, int variant, int iters, double* macs_per_s, double* ms_out);

@@ -701,6 +701,82 @@ int ecb_ecdsa_sign_hashed(ecb_ctx* ctx, int curve, const uint8_t* d_be, const ui
                                                       (unsigned char*)o[1], s);
                        });
 }
+// ecdsa::sign on raw messages (ragged input): the chunk loop of ecb_ecdsa_verify; per chunk the slot holds
+// d in in[0], k in in[1], the offsets in in[2], z (device-made) in in[3], the message bytes in `scratch`.
+int ecb_ecdsa_sign(ecb_ctx* ctx, int curve, int hash, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* msgs, const uint64_t* msg_off,
+                   size_t n, uint8_t* rs_be, uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb) || curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+    if (hash != 256 && hash != 384 && hash != 512) return set_err(ctx, ECB_ERR_INVALID_ARG, "hash must be 256, 384 or 512");
+    if (n && (!d_be || !k_be || !msg_off || !rs_be || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    if (n == 0) return ECB_OK;
+    for (size_t i = 0; i < n; i++)
+        if (msg_off[i + 1] < msg_off[i]) return set_err(ctx, ECB_ERR_INVALID_ARG, "message offsets must be non-decreasing");
+    if (msg_off[n] > msg_off[0] && !msgs) return set_err(ctx, ECB_ERR_INVALID_ARG, "null message buffer");
+    int nd = (int)ctx->devs.size();
+    std::vector<int> rc(nd, ECB_OK);
+    auto worker = [&](int di) {
+        DevCtx& d = *ctx->devs[di];
+        size_t lo = n * (size_t)di / nd, hi = n * (size_t)(di + 1) / nd;
+        if (lo == hi) return;
+        std::lock_guard<std::mutex> g(d.mu);
+        auto body = [&]() -> int {
+            CU(cudaSetDevice(d.dev));
+            SlotDrain drain{d};
+            size_t ci = 0;
+            for (size_t c0 = lo; c0 < hi; c0 += ctx->opt_chunk, ci++) {
+                size_t cn = hi - c0 < ctx->opt_chunk ? hi - c0 : ctx->opt_chunk;
+                Slot& sl = d.slots[ci % ECB_NSLOT];
+                if (sl.busy) {
+                    sl.busy = false;
+                    CU(cudaStreamSynchronize(sl.stream));
+                }
+                d.cur = &sl;
+                size_t mbytes = (size_t)(msg_off[c0 + cn] - msg_off[c0]);
+                TRY(ensure(ctx, sl.in[0], cn * sb));
+                TRY(ensure(ctx, sl.in[1], cn * sb));
+                TRY(ensure(ctx, sl.in[2], (cn + 1) * sizeof(uint64_t)));
+                TRY(ensure(ctx, sl.scratch, mbytes + 16));
+                TRY(ensure(ctx, sl.out[0], cn * 2 * sb));
+                TRY(ensure(ctx, sl.out[1], cn));
+                CU(cudaMemcpyAsync(sl.in[0].p, d_be + c0 * sb, cn * sb, cudaMemcpyHostToDevice, sl.stream));
+                CU(cudaMemcpyAsync(sl.in[1].p, k_be + c0 * sb, cn * sb, cudaMemcpyHostToDevice, sl.stream));
+                CU(cudaMemcpyAsync(sl.in[2].p, msg_off + c0, (cn + 1) * sizeof(uint64_t), cudaMemcpyHostToDevice, sl.stream));
+                if (mbytes) CU(cudaMemcpyAsync(sl.scratch.p, msgs + msg_off[c0], mbytes, cudaMemcpyHostToDevice, sl.stream));
+                const unsigned char* d_msgs = (const unsigned char*)sl.scratch.p - msg_off[c0];
+                if (curve == ECB_CURVE_P256R1)
+                    TRY(dev_ecdsa_sign_msgs_p256(ctx, d, (const u32*)sl.in[0].p, (const u32*)sl.in[1].p, d_msgs, (const unsigned long long*)sl.in[2].p,
+                                                 hash, cn, (u32*)sl.out[0].p, (unsigned char*)sl.out[1].p, sl.stream));
+                else
+                    TRY(dev_ecdsa_sign_msgs_p384(ctx, d, (const u32*)sl.in[0].p, (const u32*)sl.in[1].p, d_msgs, (const unsigned long long*)sl.in[2].p,
+                                                 hash, cn, (u32*)sl.out[0].p, (unsigned char*)sl.out[1].p, sl.stream));
+                CU(cudaMemcpyAsync(rs_be + c0 * 2 * sb, sl.out[0].p, cn * 2 * sb, cudaMemcpyDeviceToHost, sl.stream));
+                CU(cudaMemcpyAsync(ok + c0, sl.out[1].p, cn, cudaMemcpyDeviceToHost, sl.stream));
+                sl.busy = true;
+            }
+            for (Slot& sl : d.slots) {
+                if (!sl.busy) continue;
+                sl.busy = false;
+                CU(cudaStreamSynchronize(sl.stream));
+            }
+            d.cur = &d.slots[0];
+            drain.armed = false;
+            return ECB_OK;
+        };
+        rc[di] = body();
+    };
+    if (nd == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nd; i++) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < nd; i++)
+        if (rc[i] != ECB_OK) return rc[i];
+    return ECB_OK;
+}
 int ecb_wei_decompress(ecb_ctx* ctx, int curve, const uint8_t* x_be, const uint8_t* sign, size_t n, uint8_t* out_xy, uint8_t* ok) {
     if (!ctx) return ECB_ERR_CUDA;
     size_t fb, sb;

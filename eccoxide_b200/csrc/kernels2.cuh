@@ -424,8 +424,11 @@ struct FinEcdsa {  // x_mod_n(R) == r (ecdsa.rs:382, :218-221); identity => reje
 //   finish : r = x mod n (field_to_scalar, ecdsa.rs:363); s = k^-1 (z + r d) mod n;
 //            valid &= k G finite & r != 0 & s != 0; rs = r || s big-endian (zero when not valid)
 // =======================================================================================
+// z_any: z is bits2int of a digest (raw-message signing): any SB-byte value, reduced mod n by the
+// Montgomery conversion in the finish step; otherwise z is a Scalar and must be canonical
 template <class C>
-ECB_DEV void ecdsa_sign_prep_body(size_t idx, size_t n, const u32* d_be, const u32* k_be, const u32* z_be, u32* sp, unsigned char* valid) {
+ECB_DEV void ecdsa_sign_prep_body(size_t idx, size_t n, const u32* d_be, const u32* k_be, const u32* z_be, u32* sp, unsigned char* valid,
+                                  bool z_any = false) {
     typedef typename C::FN FN;
     constexpr int NS = FN::N;
     u32 d[NS], k[NS], z[NS];
@@ -435,7 +438,7 @@ ECB_DEV void ecdsa_sign_prep_body(size_t idx, size_t n, const u32* d_be, const u
     u32 dz = 0, kz = 0;
     ECB_UNROLL
     for (int i = 0; i < NS; i++) { dz |= d[i]; kz |= k[i]; }
-    u32 ok = (dz != 0) & (kz != 0) & FN::is_canonical_words(d) & FN::is_canonical_words(k) & FN::is_canonical_words(z);
+    u32 ok = (dz != 0) & (kz != 0) & FN::is_canonical_words(d) & FN::is_canonical_words(k) & (z_any ? 1u : FN::is_canonical_words(z));
     if (!ok) {
         ECB_UNROLL
         for (int i = 0; i < NS; i++) k[i] = 0;

@@ -140,6 +140,10 @@ int ecb_wei_mul_base(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, size_t n, 
  * nonce zero, r = 0 or s = 0 - and for a non-canonical scalar (Scalar::from_bytes -> None). */
 int ecb_ecdsa_sign_hashed(ecb_ctx* ctx, int curve_id, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n,
                           uint8_t* rs_be, uint8_t* ok);
+/* ecdsa::sign::<O>(&secret, &nonce, message) (src/protocol/ecdsa.rs:192): z = O::hash_to_scalar(message) on the device
+ * (hash = 256 / 384 / 512, as ecb_ecdsa_verify), then sign_hashed.  Messages concatenated, n + 1 offsets. */
+int ecb_ecdsa_sign(ecb_ctx* ctx, int curve_id, int hash, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* msgs,
+                   const uint64_t* msg_off, size_t n, uint8_t* rs_be, uint8_t* ok);
 
 /* ---- wire formats either side of the Weierstrass path --------------------------------------------------
  * PointAffine::decompress(&FieldElement, Sign) -> CtOption<PointAffine> (src/curve/affine.rs:48,

@@ -756,6 +756,33 @@ def test_ecdsa_sign_hashed(ctx, golden, coracle, curve):
         pub.verify(encode_dss_signature(r_, s_), zb[i].tobytes(), ec.ECDSA(Prehashed(alg)))   # raises on a bad signature
 
 
+@pytest.mark.parametrize("curve", ["p256r1", "p384r1"])
+def test_ecdsa_sign_raw_messages(ctx, golden, curve):
+    """ecdsa::sign (ecdsa.rs:192) with the hash on the device: the RFC 6979 vectors straight from their
+    messages for SHA-256 / 384 / 512 (ecdsa.rs:808-878), ragged random messages against hashlib + the
+    big-int oracle, and acceptance by the library's raw-message verification."""
+    c = R.WCURVES[curve]
+    v = golden["ecdsa_rfc6979"][curve]
+    d0 = int(v["d"], 16)
+    g = rng(1979 + c.sbytes)
+    assert len([k for k in v["kats"] if k["alg"] in ("sha256", "sha384", "sha512")]) == len(v["kats"]) >= 3
+    for bits in (256, 384, 512):
+        kats = [k for k in v["kats"] if k["alg"] == "sha%d" % bits]   # (a curve's vectors need not use every hash)
+        msgs = [k["message"].encode() for k in kats] + [g.bytes(int(g.integers(0, 200))) for _ in range(300)] + [b""]
+        ds = [d0] * len(kats) + [int.from_bytes(g.bytes(c.sbytes + 8), "big") % (c.n - 1) + 1 for _ in range(301)]
+        ks = [int(k["k"], 16) for k in kats] + [int.from_bytes(g.bytes(c.sbytes + 8), "big") % (c.n - 1) + 1 for _ in range(301)]
+        tob = lambda xs: rows([x.to_bytes(c.sbytes, "big") for x in xs])
+        rs, ok = ctx.ecdsa_sign(curve, tob(ds), tob(ks), msgs, hash_bits=bits)
+        assert ok.all()
+        for i, k in enumerate(kats):
+            assert rs[i].tobytes().hex() == k["r"].rjust(2 * c.sbytes, "0") + k["s"].rjust(2 * c.sbytes, "0")
+        for i in range(len(msgs)):
+            z = int.from_bytes(R.ecdsa_digest_to_scalar(c, hashlib.new("sha%d" % bits, msgs[i]).digest()), "big")
+            assert rs[i].tobytes() == R.ecdsa_sign_hashed(c, ds[i], ks[i], z), (bits, i)
+        q, _ = ctx.wei_mul_base(curve, tob(ds))
+        assert ctx.ecdsa_verify(curve, bits, q, msgs, rs).all()
+
+
 # ---- wire formats either side of the path (SURVEY §8 f.1) -------------------------------------------
 @pytest.mark.parametrize("curve", CURVES)
 def test_wei_decompress(ctx, coracle, golden, curve):
