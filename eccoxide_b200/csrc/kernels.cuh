@@ -203,35 +203,42 @@ ECB_DEV void x25519_base_body(size_t idx, size_t n, const u32* scalars, const u3
     plane_st<8>(planes + 2 * 8 * n, n, idx, d.v);
 }
 
-// comb-table builder: entry (i, j) = j * 2^(W*i) * B by plain double-and-add on the 256-bit
-// integer s = j << (W*i); output projective planes (4*8 words: X,Y,Z) over ntab entries.
-ECB_DEV void ed25519_table_point_body(size_t e, size_t ntab, int W, int nwin, u32* planes) {
-    const u32 half = 1u << (W - 1);
-    u32 i = (u32)(e / half), j = (u32)(e % half) + 1;
-    u32 s[9];
-    ECB_UNROLL
-    for (int t = 0; t < 9; t++) s[t] = 0;
-    int sh = W * (int)i;
-    int wd = sh >> 5, b = sh & 31;
-    // j < 2^16, may straddle two words
-    u32 lo = j << b, hi = b ? (j >> (32 - b)) : 0u;
-    for (int t = 0; t < 9; t++) {
-        if (t == wd) s[t] |= lo;
-        if (t == wd + 1) s[t] |= hi;
-    }
+// comb-table builder, two steps:
+//   window bases  B_i = 2^(W i) * B, one thread per window (W i doublings), stored in cached form
+//                 (Y+X, Y-X, Z, 2dT: 32 words) so that no inversion is needed in between;
+//   entries       (i, j) = j * B_i by double-and-add over the W bits of j only (the first version
+//                 walked all W * nwin bits of j << (W i) for every entry: ~10x the work).
+// Output: projective planes (X, Y, Z) over ntab entries, made affine by the batch inversion.
+ECB_DEV void ed25519_window_base_body(int i, int W, u32* bases) {
     fe25519 bx, by;
     F::from_words(bx, ED25519_BX);
     F::from_words(by, ED25519_BY);
-    ge_niels nb;
-    ge_niels_from_affine(nb, bx, by);
+    ge_p3 acc;
+    ge_from_affine(acc, bx, by);
+    for (int s = 0; s < W * i; s++) ge_double<true>(acc, acc);
+    ge_cached c;
+    ge_to_cached(c, acc);
+    u32* dst = bases + (size_t)i * 32;
+    st_words<8>(dst, c.yp.v);
+    st_words<8>(dst + 8, c.ym.v);
+    st_words<8>(dst + 16, c.Z.v);
+    st_words<8>(dst + 24, c.t2d.v);
+}
+ECB_DEV void ed25519_table_point_body(size_t e, size_t ntab, int W, int nwin, const u32* bases, u32* planes) {
+    const u32 half = 1u << (W - 1);
+    u32 i = (u32)(e / half), j = (u32)(e % half) + 1;
+    (void)nwin;
+    ge_cached c;
+    const u32* src = bases + (size_t)i * 32;
+    ld_words<8>(c.yp.v, src);
+    ld_words<8>(c.ym.v, src + 8);
+    ld_words<8>(c.Z.v, src + 16);
+    ld_words<8>(c.t2d.v, src + 24);
     ge_p3 acc;
     ge_identity(acc);
-    for (int bit = W * nwin - 1; bit >= 0; bit--) {  // W*nwin <= 288 bits
+    for (int bit = W - 1; bit >= 0; bit--) {  // j <= 2^(W-1)
         ge_double<true>(acc, acc);
-        u32 wv = 0;
-        for (int t = 0; t < 9; t++)
-            if (t == (bit >> 5)) wv = s[t];
-        if ((wv >> (bit & 31)) & 1) ge_madd<true>(acc, acc, nb);
+        if ((j >> bit) & 1) ge_add_cached<true>(acc, acc, c);
     }
     plane_st<8>(planes + 0 * 8 * ntab, ntab, e, acc.X.v);
     plane_st<8>(planes + 1 * 8 * ntab, ntab, e, acc.Y.v);
@@ -702,37 +709,49 @@ ECB_DEV void wei_mul_base_body(size_t idx, size_t n, const u32* scalars, const u
     plane_st<N>(planes + 1 * (size_t)N * n, n, idx, acc.Y.v);
     plane_st<N>(planes + 2 * (size_t)N * n, n, idx, acc.Z.v);
 }
-// comb-table builder: entry (i, j) = j * 2^(W i) * G by double-and-add on s = j << (W i)
+// comb-table builder, as for Ed25519: window bases G_i = 2^(W i) * G (Jacobian with cached Z^2, Z^3:
+// 5N words each), then entry (i, j) = j * G_i over the W bits of j.
 template <class C>
-ECB_DEV void wei_table_point_body(size_t e, size_t ntab, int W, int nwin, u32* planes) {
+ECB_DEV void wei_window_base_body(int i, int W, u32* bases) {
     typedef WeiJ<C> J;
     typedef typename C::F FT;
     constexpr int N = FT::N;
-    constexpr int SW = 14;  // scalar words: W * nwin <= 448 bits
+    typename J::pt acc;
+    ECB_UNROLL
+    for (int t = 0; t < N; t++) { acc.X.v[t] = C::gx(t); acc.Y.v[t] = C::gy(t); }
+    FT::set_one(acc.Z);
+    ECB_NOUNROLL
+    for (int s = 0; s < W * i; s++) J::dbl(acc, acc);
+    typename J::cached c;
+    J::to_cached(c, acc);
+    u32* dst = bases + (size_t)i * 5 * N;
+    st_words<N>(dst, c.X.v);
+    st_words<N>(dst + N, c.Y.v);
+    st_words<N>(dst + 2 * N, c.Z.v);
+    st_words<N>(dst + 3 * N, c.ZZ.v);
+    st_words<N>(dst + 4 * N, c.ZZZ.v);
+}
+template <class C>
+ECB_DEV void wei_table_point_body(size_t e, size_t ntab, int W, int nwin, const u32* bases, u32* planes) {
+    typedef WeiJ<C> J;
+    typedef typename C::F FT;
+    constexpr int N = FT::N;
     const u32 half = 1u << (W - 1);
     u32 i = (u32)(e / half), j = (u32)(e % half) + 1;
-    u32 s[SW];
-    ECB_UNROLL
-    for (int t = 0; t < SW; t++) s[t] = 0;
-    int sh = W * (int)i;
-    int wd = sh >> 5, b = sh & 31;
-    u32 lo = j << b, hi = b ? (j >> (32 - b)) : 0u;
-    for (int t = 0; t < SW; t++) {
-        if (t == wd) s[t] |= lo;
-        if (t == wd + 1) s[t] |= hi;
-    }
+    (void)nwin;
     typename J::cached g;
-    ECB_UNROLL
-    for (int t = 0; t < N; t++) { g.X.v[t] = C::gx(t); g.Y.v[t] = C::gy(t); }
+    const u32* src = bases + (size_t)i * 5 * N;
+    ld_words<N>(g.X.v, src);
+    ld_words<N>(g.Y.v, src + N);
+    ld_words<N>(g.Z.v, src + 2 * N);
+    ld_words<N>(g.ZZ.v, src + 3 * N);
+    ld_words<N>(g.ZZZ.v, src + 4 * N);
     typename J::pt acc;
     J::set_inf(acc);
     ECB_NOUNROLL
-    for (int bit = W * nwin - 1; bit >= 0; bit--) {
+    for (int bit = W - 1; bit >= 0; bit--) {  // j <= 2^(W-1)
         J::dbl(acc, acc);
-        u32 wv = 0;
-        for (int t = 0; t < SW; t++)
-            if (t == (bit >> 5)) wv = s[t];
-        if ((wv >> (bit & 31)) & 1) J::template add<true>(acc, acc, g);
+        if ((j >> bit) & 1) J::template add<false>(acc, acc, g);
     }
     plane_st<N>(planes + 0 * (size_t)N * ntab, ntab, e, acc.X.v);
     plane_st<N>(planes + 1 * (size_t)N * ntab, ntab, e, acc.Y.v);

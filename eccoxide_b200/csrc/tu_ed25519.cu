@@ -7,9 +7,13 @@ static __global__ void __launch_bounds__(ECB_TPB, 5) k_ed25519_mul_base(size_t n
     size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
     if (idx < n) ed25519_mul_base_body<false>(idx, n, scalars, table, W, nwin, planes, status);
 }
-static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_table_points(size_t ntab, int W, int nwin, u32* planes) {
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_window_bases(int nwin, int W, u32* bases) {
+    int i = (int)(blockIdx.x * ECB_TPB + threadIdx.x);
+    if (i < nwin) ed25519_window_base_body(i, W, bases);
+}
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_table_points(size_t ntab, int W, int nwin, const u32* bases, u32* planes) {
     size_t e = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
-    if (e < ntab) ed25519_table_point_body(e, ntab, W, nwin, planes);
+    if (e < ntab) ed25519_table_point_body(e, ntab, W, nwin, bases, planes);
 }
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul(size_t n, const u32* scalars, const u32* points, u32* scratch,
                                                           u32* planes, unsigned long long* status) {
@@ -62,12 +66,21 @@ static int ed25519_build_table_w(ecb_ctx* ctx, DevCtx& d, int W) {
     CU(cudaMalloc(&d.ed_table, ntab * 24 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->planes, ntab * 3 * 8 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->pf, ntab * 8 * sizeof(u32)));
-    k_ed25519_table_points<<<grid_for(ntab), ECB_TPB, 0, d.stream>>>(ntab, W, nwin, (u32*)d.cur->planes.p);
-    ctx->launches++;
-    CU(cudaGetLastError());
+    u32* bases = nullptr;   // 2^(W i) * B per window, cached form (32 words each)
+    CU(cudaMalloc(&bases, (size_t)nwin * 32 * sizeof(u32)));
+    k_ed25519_window_bases<<<grid_for((size_t)nwin), ECB_TPB, 0, d.stream>>>(nwin, W, bases);
+    k_ed25519_table_points<<<grid_for(ntab), ECB_TPB, 0, d.stream>>>(ntab, W, nwin, bases, (u32*)d.cur->planes.p);
+    ctx->launches += 2;
+    cudaError_t le = cudaGetLastError();
+    if (le != cudaSuccess) {
+        cudaFree(bases);
+        CU(le);
+    }
     FinEdNiels fin{(const u32*)d.cur->planes.p, ntab, d.ed_table};
     TRY((launch_batch_inv<F25519, FinEdNiels>(ctx, d, ntab, (const u32*)d.cur->planes.p, (u32*)d.cur->pf.p, fin, d.stream)));
-    CU(cudaStreamSynchronize(d.stream));
+    cudaError_t se = cudaStreamSynchronize(d.stream);
+    cudaFree(bases);
+    CU(se);
     if (ntab * 96 > ((size_t)256 << 20)) {  // give the build buffers of a large table back
         for (DevBuf* b : {&d.cur->planes, &d.cur->pf}) {
             if (b->p) CU(cudaFree(b->p));

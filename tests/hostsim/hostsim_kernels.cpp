@@ -18,7 +18,9 @@ void hs_ed25519_build_table(int W, u32* table) {
     int nwin = (254 + W - 1) / W;
     size_t ntab = (size_t)nwin << (W - 1);
     std::vector<u32> planes(3 * 8 * ntab), pf(8 * ntab);
-    for (size_t e = 0; e < ntab; e++) ed25519_table_point_body(e, ntab, W, nwin, planes.data());
+    std::vector<u32> bases((size_t)nwin * 32);
+    for (int i = 0; i < nwin; i++) ed25519_window_base_body(i, W, bases.data());
+    for (size_t e = 0; e < ntab; e++) ed25519_table_point_body(e, ntab, W, nwin, bases.data(), planes.data());
     size_t T = inv_threads(ntab);
     FinEdNiels fin{planes.data(), ntab, table};
     for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, ntab, planes.data(), pf.data(), fin);
@@ -140,7 +142,9 @@ static std::vector<u32> wei_build_comb(int W, int nwin) {
     constexpr int N = C::F::N;
     size_t ntab = (size_t)nwin << (W - 1);
     std::vector<u32> planes(3 * N * ntab), pf(N * ntab), table(2 * N * ntab);
-    for (size_t e = 0; e < ntab; e++) wei_table_point_body<C>(e, ntab, W, nwin, planes.data());
+    std::vector<u32> bases((size_t)nwin * 5 * N);
+    for (int i = 0; i < nwin; i++) wei_window_base_body<C>(i, W, bases.data());
+    for (size_t e = 0; e < ntab; e++) wei_table_point_body<C>(e, ntab, W, nwin, bases.data(), planes.data());
     size_t T = inv_threads(ntab);
     FinWeiTable<C> fin{planes.data(), ntab, table.data()};
     for (size_t t = 0; t < T; t++) batch_inv_body<typename C::F>(t, T, ntab, planes.data(), pf.data(), fin);
