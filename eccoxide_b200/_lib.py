@@ -60,6 +60,7 @@ SIGNATURES = {
     "ecb_profile_collect": (_int, [_vp, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_int)]),
     "ecb_dev_status": (_int, [_vp, _int, _szp]),
     "ecb_imad_probe": (_int, [_vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "ecb_latency_probe": (_int, [_vp, _int, _int, _int, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "ecb_wei_decompress": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_bls12_381_g1_from_compressed": (_int, [_vp, _vp, _sz, _int, _vp, _vp]),
     "ecb_bls12_381_g1_to_compressed": (_int, [_vp, _vp, _vp, _sz, _vp]),

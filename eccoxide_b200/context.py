@@ -360,6 +360,11 @@ class Context:
         self._check(self._lib.ecb_imad_probe(self._ctx, dev_index, variant, iters, ctypes.byref(macs), ctypes.byref(ms)))
         return macs.value, ms.value
 
+    def latency_probe(self, variant, threads=32, reps=16, dev_index=0):
+        cyc, mhz = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.ecb_latency_probe(self._ctx, dev_index, variant, threads, reps, ctypes.byref(cyc), ctypes.byref(mhz)))
+        return cyc.value, mhz.value
+
     def debug_ed25519_table(self, dev_index=0):
         w = ctypes.c_int()
         nwin = ctypes.c_int()

@@ -4,6 +4,7 @@
 #include "host_ctx.h"
 
 int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W);
+int dev_ed25519_table(ecb_ctx* ctx, DevCtx& d);   // build the comb of the configured shape if the device does not hold it
 // enc_stride_words: distance between compressed outputs in 32-bit words (0 = packed, 8)
 int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s,
                          size_t enc_stride_words = 0);
@@ -54,3 +55,4 @@ int dev_ecdsa_sign_msgs_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32*
 int dev_ecdsa_sign_msgs_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k, const unsigned char* d_msgs, const unsigned long long* d_off,
                              int hash, size_t n, u32* d_rs, unsigned char* d_ok, cudaStream_t s);
 int dev_imad_probe(ecb_ctx* ctx, DevCtx& d, int variant, int iters, double* macs_per_s, double* ms_out);
+int dev_latency_probe(ecb_ctx* ctx, DevCtx& d, int variant, int threads, int reps, double* cycles, double* mhz);

@@ -59,11 +59,6 @@ int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out) {
         }
         d->stream = d->slots[0].stream;
     }
-    const char* w = getenv("ECB_ED25519_COMB_W");
-    if (w) {
-        long v = atol(w);
-        if (v >= 4 && v <= 24) ctx->opt_ed_w = v;
-    }
     *out = ctx;
     return ECB_OK;
 }
@@ -104,6 +99,21 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
     if (!strcmp(key, "ed25519_comb_w")) {
         if (value != 0 && (value < 4 || value > 26)) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_comb_w must be 0 or in 4..26");
         ctx->opt_ed_w = value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "ed25519_entry_stride")) {
+        if (value != 24 && value != 32) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_entry_stride must be 24 or 32 (32-bit words)");
+        ctx->opt_ed_stride = value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "ed25519_fused")) {
+        if (value < 0 || value > 2) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_fused must be 0, 1 or 2");
+        ctx->opt_ed_fused = value;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "ed25519_lanes")) {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8) return set_err(ctx, ECB_ERR_INVALID_ARG, "ed25519_lanes must be 0, 1, 2, 4 or 8");
+        ctx->opt_ed_lanes = value;
         return ECB_OK;
     }
     if (!strcmp(key, "p256r1_comb_w") || !strcmp(key, "p384r1_comb_w") || !strcmp(key, "bls12_381_g1_comb_w")) {
@@ -1023,6 +1033,13 @@ int ecb_imad_probe(ecb_ctx* ctx, int di, int variant, int iters, double* macs_pe
     return dev_imad_probe(ctx, *d, variant, iters, macs_per_s, ms_out);
 }
 
+int ecb_latency_probe(ecb_ctx* ctx, int di, int variant, int threads, int reps, double* cycles, double* sm_mhz) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_latency_probe(ctx, *d, variant, threads, reps, cycles, sm_mhz);
+}
+
 long ecb_debug_chunk_plan(size_t lo, size_t hi, size_t chunk, long ramp, size_t* bounds, size_t cap) {
     if (hi < lo || chunk == 0 || ramp < 0 || ramp > 4) return -1;
     std::vector<size_t> b;
@@ -1036,17 +1053,16 @@ long ecb_debug_ed25519_table(ecb_ctx* ctx, int di, uint8_t* out, size_t cap, int
     if (!d) return ECB_ERR_INVALID_ARG;
     std::lock_guard<std::mutex> g(d->mu);
     if (cudaSetDevice(d->dev) != cudaSuccess) return ECB_ERR_CUDA;
-    if (!d->ed_table || (ctx->opt_ed_w && d->ed_w != (int)ctx->opt_ed_w)) {
+    if (!d->ed_table || (ctx->opt_ed_w && d->ed_w != (int)ctx->opt_ed_w) || d->ed_stride != (int)ctx->opt_ed_stride) {
         int r = dev_ed25519_build_table(ctx, *d, ctx->opt_ed_w ? (int)ctx->opt_ed_w : 16);
         if (r != ECB_OK) return r;
     }
     size_t ntab = (size_t)d->ed_nwin << (d->ed_w - 1);
     if (w) *w = d->ed_w;
     if (nwin) *nwin = d->ed_nwin;
-    size_t bytes = ntab * 96;
-    if (out) {
-        if (bytes > cap) bytes = cap - cap % 96;
-        if (cudaMemcpy(out, d->ed_table, bytes, cudaMemcpyDeviceToHost) != cudaSuccess) return ECB_ERR_CUDA;
+    if (out) {   // always handed out packed (96 B per entry), whatever the device stride
+        size_t cnt = cap / 96 < ntab ? cap / 96 : ntab;
+        if (cudaMemcpy2D(out, 96, d->ed_table, (size_t)d->ed_stride * 4, 96, cnt, cudaMemcpyDeviceToHost) != cudaSuccess) return ECB_ERR_CUDA;
     }
     return (long)ntab;
 }

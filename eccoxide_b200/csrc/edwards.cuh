@@ -170,6 +170,32 @@ ECB_DEV void ge_add_cached(ge_p3& r, const ge_p3& p, const ge_cached& q) {
     if (WITH_T) { if (NI) F::mul_ni(r.T, E, H); else F::mul(r.T, E, H); }
 }
 
+// r = p + q, both extended (Point::add, curve25519.rs:695: 9M, 8M when !WITH_T).  Used by the
+// lane-split comb: the partial sums of the lanes of one scalar are added pairwise.
+template <bool WITH_T>
+ECB_DEV void ge_add_p3(ge_p3& r, const ge_p3& p, const ge_p3& q) {
+    fe25519 A, B, C, D, E, Fv, G, H, d2;
+    F::from_words(d2, ED25519_D2);
+    F::sub(A, p.Y, p.X);
+    F::sub(B, q.Y, q.X);
+    F::mul(A, A, B);
+    F::add(B, p.Y, p.X);
+    F::add(C, q.Y, q.X);
+    F::mul(B, B, C);
+    F::mul(C, p.T, q.T);
+    F::mul(C, C, d2);
+    F::mul(D, p.Z, q.Z);
+    F::dbl(D, D);
+    F::sub(E, B, A);
+    F::sub(Fv, D, C);
+    F::add(G, D, C);
+    F::add(H, B, A);
+    F::mul(r.X, E, Fv);
+    F::mul(r.Y, G, H);
+    F::mul(r.Z, Fv, G);
+    if (WITH_T) F::mul(r.T, E, H);
+}
+
 ECB_DEV void ge_to_cached(ge_cached& r, const ge_p3& p) {
     fe25519 d2;
     F::from_words(d2, ED25519_D2);
@@ -230,6 +256,42 @@ ECB_DEV u32 booth_digit(const u32* k, int nwords, int W, int i, u32& neg) {
     u32 s = view >> W;       // top bit = sign
     u32 d = (view + 1u) >> 1;
     // if sign: d = 2^W - d  (in units after the +1>>1 trick)
+    u32 dn = (1u << W) - d;
+    neg = s;
+    u32 r = s ? dn : d;
+    if (r == 0) neg = 0;
+    return r;
+}
+
+
+// The comb kernels walk their windows in order, so instead of indexing k[] by a run-time word number
+// (which sends the scalar to local memory) they keep v = 2k in a shift register: the (W+1)-bit Booth
+// view of the current window is the low bits of v[0], and moving to the next window is a static
+// multi-word funnel shift by W.  NV words hold 2k (the callers' scalars leave the top bit of the last
+// word clear, or pass one word more).
+ECB_DEV u32 funnel_r(u32 lo, u32 hi, int s) {   // low word of (hi:lo) >> s, 0 < s < 32
+#ifdef ECB_HOSTSIM
+    return (lo >> s) | (hi << (32 - s));
+#else
+    return __funnelshift_r(lo, hi, s);
+#endif
+}
+template <int NV>
+ECB_DEV void booth_reg_init(u32* v, const u32* k) {   // v = 2k
+    v[0] = k[0] << 1;
+    ECB_UNROLL
+    for (int j = 1; j < NV; j++) v[j] = funnel_r(k[j - 1], k[j], 31);
+}
+template <int NV>
+ECB_DEV void booth_reg_shift(u32* v, int W) {          // v >>= W, 0 < W < 32
+    ECB_UNROLL
+    for (int j = 0; j < NV - 1; j++) v[j] = funnel_r(v[j], v[j + 1], W);
+    v[NV - 1] >>= W;
+}
+ECB_DEV u32 booth_from_view(u32 view, int W, u32& neg) {
+    view &= (2u << W) - 1u;
+    u32 s = view >> W;
+    u32 d = (view + 1u) >> 1;
     u32 dn = (1u << W) - d;
     neg = s;
     u32 r = s ? dn : d;

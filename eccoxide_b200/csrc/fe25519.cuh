@@ -69,6 +69,13 @@ struct F25519 {
         sqr_full<8>(t, a.v);
         fold(r, t);
     }
+    // r1 = a1 * b1 and r2 = a2 * b2, rows interleaved (limb.cuh mul_full2): for latency-bound callers
+    ECB_DEV static void mul2(el& r1, const el& a1, const el& b1, el& r2, const el& a2, const el& b2) {
+        u32 t1[16], t2[16];
+        mul_full2<8>(t1, a1.v, b1.v, t2, a2.v, b2.v);
+        fold(r1, t1);
+        fold(r2, t2);
+    }
     // out-of-line copies (operands by value, so they stay in registers) for the kernels whose window
     // loop would not fit the instruction cache with every product inlined
     ECB_DEVNI static el mul_v(el a, el b) {

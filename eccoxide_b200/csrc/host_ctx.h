@@ -55,7 +55,7 @@ struct DevCtx {
     size_t inv_per_thread = 32;               // batch-inversion chain length (option "inv_per_thread"; 8: 0.31 ms, 16: 0.24, 32: 0.20, 64: 0.20 at n = 2^20)
     Slot* cur = &slots[0];                    // slot whose buffers the dev_* functions use (calls are serialised by `mu`)
     u32* ed_table = nullptr;
-    int ed_w = 0, ed_nwin = 0;
+    int ed_w = 0, ed_nwin = 0, ed_stride = 24;  // comb width, windows, words between entries (24 packed, 32 = 128-byte aligned)
     u32* wei_table[3] = {nullptr, nullptr, nullptr};  // generator combs of p256r1, p384r1, bls12_381 G1
     int wei_w[3] = {0, 0, 0}, wei_nwin[3] = {0, 0, 0};
     std::mutex mu;
@@ -75,6 +75,9 @@ struct ecb_ctx {
     // integer-pipe-bound, so time follows the window count; the random table reads (96 B per window) stay
     // far below HBM bandwidth.
     long opt_ed_w = 0;
+    long opt_ed_stride = 24;                  // words between comb entries: 24 (packed, 96 B) or 32 (one entry per 128-byte line)
+    long opt_ed_fused = 1;                    // small-batch fused kernel (fused.cuh): 0 never, 1 when the batch fits one wave, 2 always
+    long opt_ed_lanes = 0;                    // lanes per scalar in the fused kernel: 0 = by batch size, or 1 / 2 / 4 / 8
     size_t opt_chunk = 189440;  // elements per pipeline chunk = 148 SMs x 1280 (ECB_NSLOT chunks in flight per device; measured best of 2^16..2^19)
     long opt_profile = 0;
     long opt_inv_hi = 1;                      // run batch inversions on the slot's high-priority side stream

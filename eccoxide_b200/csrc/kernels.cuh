@@ -7,7 +7,8 @@
 //   inputs / outputs : the reference's wire encodings, AoS, contiguous (32/48/56-byte elements)
 //   intermediates    : structure-of-arrays "planes": plane[limb * n + idx], so a warp reading limb
 //                      `l` of 32 consecutive elements touches one 128-byte line
-//   tables           : fixed-base comb tables as arrays of 96-byte niels entries (L2-resident)
+//   tables           : fixed-base comb tables as arrays of niels entries (96 B, packed or on a 128-byte
+//                      stride) in HBM: 0.65-43 GB depending on the window width
 //                      per-thread window tables of variable-base kernels in a scratch arena,
 //                      one contiguous block per resident thread
 #pragma once
@@ -150,38 +151,55 @@ ECB_DEV u32 lt_words8(const u32* a, const u32* m) {  // a < m ?
 // CLAMP: the scalar is an X25519 secret (protocol/x25519.rs:15 clamp, :49 x25519_base): any 32 bytes,
 // clamped here, up to 255 bits — the comb covers W * nwin >= 256 bits and k*B = (k mod l)*B.
 template <bool CLAMP>
-ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin,
-                                   u32* planes, unsigned long long* status) {
-    u32 k[9];
+ECB_DEV void ed25519_load_scalar(u32* k, size_t idx, const u32* scalars, unsigned long long* status) {
     ld_words<8>(k, scalars + idx * 8);
     k[8] = 0;
     if (CLAMP) {
         k[0] &= 0xfffffff8u;
         k[7] = (k[7] & 0x7fffffffu) | 0x40000000u;
     } else if (!lt_words8(k, ED25519_L)) {
-        report_bad(status, idx, ST_NONCANONICAL_SCALAR);
+        if (status) report_bad(status, idx, ST_NONCANONICAL_SCALAR);
         ECB_UNROLL
         for (int i = 0; i < 8; i++) k[i] = 0;
     }
+}
+// acc = sum of d_i * 2^(W i) * B over the windows i = first, first + step, ... < nwin (d_i = signed
+// Booth digit of k).  The reference adds its 64 window entries in one chain (curve25519.rs:844-849);
+// they are independent, so a scalar's windows can be split over `step` lanes and the partial sums
+// added afterwards.  T of the result is computed only when want_t (a further addition follows).
+// Entry (i, j) sits at table + (i * half + j - 1) * stride words (stride 24 packed, 32 = 128-byte aligned).
+ECB_DEV void ed25519_comb_partial(ge_p3& acc, const u32* k, const u32* table, int W, int nwin, int stride, int first, int step,
+                                  bool want_t) {
     const u32 half = 1u << (W - 1);
-    ge_p3 acc;
     ge_identity(acc);
-    for (int i = 0; i < nwin; i++) {
+    u32 v[8];                      // 2k as a shift register (k < 2^255, so 2k fits 256 bits)
+    booth_reg_init<8>(v, k);
+    for (int j = 0; j < first; j++) booth_reg_shift<8>(v, W);
+    for (int i = first; i < nwin; i += step) {
         u32 neg;
-        u32 d = booth_digit(k, 9, W, i, neg);
+        u32 d = booth_from_view(v[0], W, neg);
+        for (int j = 0; j < step; j++) booth_reg_shift<8>(v, W);
         ge_niels e;
         ge_niels_identity(e);
         if (d != 0) {
-            const u32* src = table + ((size_t)i * half + (d - 1)) * 24;
+            const u32* src = table + ((size_t)i * half + (d - 1)) * (size_t)stride;
             ld_words<8>(e.yp.v, src);
             ld_words<8>(e.ym.v, src + 8);
             ld_words<8>(e.t2d.v, src + 16);
         }
         ge_niels_cneg(e, neg);
-        // first window: identity + entry needs one product; last window: nobody reads T
-        if (i == 0) ge_from_niels(acc, e);
-        else ge_madd_rt(acc, acc, e, i != nwin - 1);
+        // first window: identity + entry needs one product; last window: T only if somebody reads it
+        if (i == first) ge_from_niels(acc, e);
+        else ge_madd_rt(acc, acc, e, want_t || (i + step < nwin));
     }
+}
+template <bool CLAMP>
+ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin, int stride,
+                                   u32* planes, unsigned long long* status) {
+    u32 k[9];
+    ed25519_load_scalar<CLAMP>(k, idx, scalars, status);
+    ge_p3 acc;
+    ed25519_comb_partial(acc, k, table, W, nwin, stride, 0, 1, false);
     plane_st<8>(planes + 0 * 8 * n, n, idx, acc.X.v);
     plane_st<8>(planes + 1 * 8 * n, n, idx, acc.Y.v);
     plane_st<8>(planes + 2 * 8 * n, n, idx, acc.Z.v);
@@ -192,8 +210,8 @@ ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, con
 // (u = (1 + y) / (1 - y), curve25519.rs:1668 tests this map), so the fixed-base comb replaces 255
 // ladder steps.  Writes Z + Y -> plane 0, Z - Y -> plane 2; FinEdMontU divides (0 when Z = Y, as the
 // ladder's z2 = 0 case gives).
-ECB_DEV void x25519_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin, u32* planes) {
-    ed25519_mul_base_body<true>(idx, n, scalars, table, W, nwin, planes, nullptr);
+ECB_DEV void x25519_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin, int stride, u32* planes) {
+    ed25519_mul_base_body<true>(idx, n, scalars, table, W, nwin, stride, planes, nullptr);
     fe25519 Y, Z, s, d;
     plane_ld<8>(Y.v, planes + 1 * 8 * n, n, idx);
     plane_ld<8>(Z.v, planes + 2 * 8 * n, n, idx);
@@ -526,8 +544,8 @@ struct FinEdMontU {  // out: u = (1 + y) / (1 - y) = (Z + Y) / (Z - Y), little-e
         st_words<8>(out + idx * 8, u.v);
     }
 };
-struct FinEdNiels {  // out: comb-table entry (y+x, y-x, 2dxy), 24 words
-    const u32* planes; size_t n; u32* out;
+struct FinEdNiels {  // out: comb-table entry (y+x, y-x, 2dxy), 24 words at out + idx * stride
+    const u32* planes; size_t n; u32* out; size_t stride = 24;
     ECB_DEV void pre(size_t idx) const { plane_prefetch<8>(planes, n, idx); plane_prefetch<8>(planes + 8 * n, n, idx); }
     ECB_DEV void operator()(size_t idx, const fe25519& zinv, u32) const {
         fe25519 X, Y, x, y;
@@ -540,9 +558,9 @@ struct FinEdNiels {  // out: comb-table entry (y+x, y-x, 2dxy), 24 words
         F::freeze(e.yp, e.yp);
         F::freeze(e.ym, e.ym);
         F::freeze(e.t2d, e.t2d);
-        st_words<8>(out + idx * 24, e.yp.v);
-        st_words<8>(out + idx * 24 + 8, e.ym.v);
-        st_words<8>(out + idx * 24 + 16, e.t2d.v);
+        st_words<8>(out + idx * stride, e.yp.v);
+        st_words<8>(out + idx * stride + 8, e.ym.v);
+        st_words<8>(out + idx * stride + 16, e.t2d.v);
     }
 };
 struct FinX25519 {  // out: u' = x2 / z2 little-endian canonical, 0 when z2 == 0
@@ -673,10 +691,15 @@ ECB_DEV void wei_comb_accumulate(typename WeiJ<C>::pt& acc, const u32* k, int nw
     typedef typename C::F FT;
     constexpr int N = FT::N;
     const u32 half = 1u << (W - 1);
+    constexpr int NV = C::SB / 4 + 1;   // callers pass k[NS + 1] with a zero top word
+    (void)nwords;
+    u32 v[NV];
+    booth_reg_init<NV>(v, k);
     ECB_NOUNROLL
     for (int i = 0; i < nwin; i++) {
         u32 neg;
-        u32 d = booth_digit(k, nwords, W, i, neg);
+        u32 d = booth_from_view(v[0], W, neg);
+        booth_reg_shift<NV>(v, W);
         if (d != 0) {
             typename J::cached e;
             const u32* src = table + ((size_t)i * half + (d - 1)) * 2 * N;

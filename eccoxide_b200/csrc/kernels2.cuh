@@ -667,7 +667,7 @@ ECB_DEV void ed25519_sign_finish_body(size_t idx, unsigned char* sig, const unsi
 }
 
 ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,
-                                 const u32* table, int W, int nwin, u32* tbl, u32* planes, unsigned char* out_ok) {
+                                 const u32* table, int W, int nwin, int stride, u32* tbl, u32* planes, unsigned char* out_ok) {
     u32 aw[8], s[8], k[8];
     ld_words<8>(aw, a_enc + idx * 8);
     ld_words<8>(s, s_le + idx * 8);
@@ -688,7 +688,7 @@ ECB_DEV void ed25519_verify_body(size_t idx, size_t n, const u32* a_enc, const u
             u32 d = booth_digit(s, 8, W, i, neg);
             if (d != 0) {
                 ge_niels e;
-                const u32* src = table + ((size_t)i * half + (d - 1)) * 24;
+                const u32* src = table + ((size_t)i * half + (d - 1)) * (size_t)stride;
                 ld_words<8>(e.yp.v, src);
                 ld_words<8>(e.ym.v, src + 8);
                 ld_words<8>(e.t2d.v, src + 16);

@@ -141,6 +141,41 @@ ECB_DEV void mul_full(u32* t, const u32* a, const u32* b) {
     (void)addc(0, 0);
 }
 
+// Two independent full products with their rows interleaved in program order: four carry chains in
+// flight instead of two.  One warp alone runs a product as a ~500-cycle dependent chain (the assembler
+// keeps the `volatile` carry-chain statements in order); latency-bound code with two products ready
+// (the prefix and suffix scans of fused.cuh) overlaps them this way.
+template <int N>
+ECB_DEV void mul_full2(u32* t1, const u32* a1, const u32* b1, u32* t2, const u32* a2, const u32* b2) {
+    u32 E1[2 * N + 2], O1[2 * N + 2], E2[2 * N + 2], O2[2 * N + 2];
+    ECB_UNROLL
+    for (int i = 0; i < 2 * N + 2; i++) { E1[i] = 0; O1[i] = 0; E2[i] = 0; O2[i] = 0; }
+    ECB_UNROLL
+    for (int i = 0; i < N; i++) {
+        if ((i & 1) == 0) {
+            mac_chain<N / 2, true>(E1 + i, a1, b1[i]);
+            mac_chain<N / 2, true>(E2 + i, a2, b2[i]);
+            mac_chain<N / 2, true>(O1 + i + 1, a1 + 1, b1[i]);
+            mac_chain<N / 2, true>(O2 + i + 1, a2 + 1, b2[i]);
+        } else {
+            mac_chain<N / 2, true>(E1 + i + 1, a1 + 1, b1[i]);
+            mac_chain<N / 2, true>(E2 + i + 1, a2 + 1, b2[i]);
+            mac_chain<N / 2, true>(O1 + i, a1, b1[i]);
+            mac_chain<N / 2, true>(O2 + i, a2, b2[i]);
+        }
+    }
+    t1[0] = E1[0];
+    t1[1] = add_cc(E1[1], O1[1]);
+    ECB_UNROLL
+    for (int i = 2; i < 2 * N; i++) t1[i] = addc_cc(E1[i], O1[i]);
+    (void)addc(0, 0);
+    t2[0] = E2[0];
+    t2[1] = add_cc(E2[1], O2[1]);
+    ECB_UNROLL
+    for (int i = 2; i < 2 * N; i++) t2[i] = addc_cc(E2[i], O2[i]);
+    (void)addc(0, 0);
+}
+
 // Full square t[0..2N) = a*a: off-diagonal products once, doubled, plus the
 // diagonal.  N(N-1)/2 + N IMAD.WIDE.
 template <int N>

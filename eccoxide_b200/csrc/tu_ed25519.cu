@@ -1,11 +1,21 @@
 // tu_ed25519.cu — edwards25519 kernels: fixed-base comb (+ table builder), variable base, verify.
 #include "tu_common.cuh"
 #include "dev_ops.h"
+#include "fused.cuh"
 
 static __global__ void __launch_bounds__(ECB_TPB, 5) k_ed25519_mul_base(size_t n, const u32* scalars, const u32* table, int W,
-                                                               int nwin, u32* planes, unsigned long long* status) {
+                                                               int nwin, int stride, u32* planes, unsigned long long* status) {
     size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
-    if (idx < n) ed25519_mul_base_body<false>(idx, n, scalars, table, W, nwin, planes, status);
+    if (idx < n) ed25519_mul_base_body<false>(idx, n, scalars, table, W, nwin, stride, planes, status);
+}
+// small-batch form (fused.cuh): LANES lanes per scalar, affine conversion in the same launch.
+// <512, 1>: one block of up to 512 threads per SM, the whole batch in one wave; <128, 4>: the same
+// body with the large-batch launch shape (option ed25519_fused = 2, for measurement).
+template <int LANES, bool CLAMP, class FIN, int MAXT, int MINB>
+static __global__ void __launch_bounds__(MAXT, MINB) k_ed25519_mul_base_fused(size_t n, const u32* scalars, const u32* table, int W, int nwin,
+                                                                      int stride, FIN fin, unsigned long long* status) {
+    __shared__ u32 sh[2 * FUSED_MAXW * 8];
+    ed25519_mul_base_fused_block<LANES, CLAMP, FIN>(n, scalars, table, W, nwin, stride, fin, status, sh);
 }
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_window_bases(int nwin, int W, u32* bases) {
     int i = (int)(blockIdx.x * ECB_TPB + threadIdx.x);
@@ -22,11 +32,11 @@ static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul(size_t n, const 
     for (size_t idx = t; idx < n; idx += T) ed25519_mul_body(idx, n, scalars, points, tbl, planes, status);
 }
 static __global__ void __launch_bounds__(ECB_TPB, 3) k_ed25519_verify(size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,
-                                                             const u32* table, int W, int nwin, u32* scratch, u32* planes,
+                                                             const u32* table, int W, int nwin, int stride, u32* scratch, u32* planes,
                                                              unsigned char* ok) {
     size_t T = (size_t)gridDim.x * ECB_TPB, t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
     u32* tbl = scratch + t * (8 * 32);
-    for (size_t idx = t; idx < n; idx += T) ed25519_verify_body(idx, n, a_enc, s_le, k_le, table, W, nwin, tbl, planes, ok);
+    for (size_t idx = t; idx < n; idx += T) ed25519_verify_body(idx, n, a_enc, s_le, k_le, table, W, nwin, stride, tbl, planes, ok);
 }
 
 // comb width actually used on this device: the option, or (option 0) the widest whose table and
@@ -41,15 +51,19 @@ static int ed_pick_w(ecb_ctx* ctx) {
     return 16;
 }
 static int ed25519_build_table_w(ecb_ctx* ctx, DevCtx& d, int W);
+static void ed_drop_table(DevCtx& d) {
+    if (d.ed_table) cudaFree(d.ed_table);
+    d.ed_table = nullptr;
+    d.ed_w = d.ed_nwin = 0;
+}
 // In automatic mode (option 0) a width whose table or build buffers cannot be allocated falls back
-// to the next narrower even width instead of failing the call.
+// to the next narrower even width instead of failing the call.  On failure the context holds NO table
+// (ed_table == nullptr, ed_w == ed_nwin == 0): the next call rebuilds or fails again, loudly.
 int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
     for (;;) {
         int rc = ed25519_build_table_w(ctx, d, W);
         if (rc == ECB_OK || ctx->opt_ed_w != 0 || W <= 16) return rc;
         (void)cudaGetLastError();
-        if (d.ed_table) cudaFree(d.ed_table);
-        d.ed_table = nullptr;
         for (DevBuf* b : {&d.cur->planes, &d.cur->pf}) {
             if (b->p) cudaFree(b->p);
             b->p = nullptr;
@@ -58,50 +72,124 @@ int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
         W -= 2;
     }
 }
+// The new table is built into a local buffer and published (table, width, window count, stride together)
+// only when every step succeeded; any failure frees it and leaves the context without a table.
 static int ed25519_build_table_w(ecb_ctx* ctx, DevCtx& d, int W) {
-    int nwin = (254 + W - 1) / W;
-    size_t ntab = (size_t)nwin << (W - 1);
-    if (d.ed_table) CU(cudaFree(d.ed_table));
-    d.ed_table = nullptr;
-    CU(cudaMalloc(&d.ed_table, ntab * 24 * sizeof(u32)));
-    TRY(ensure(ctx, d.cur->planes, ntab * 3 * 8 * sizeof(u32)));
-    TRY(ensure(ctx, d.cur->pf, ntab * 8 * sizeof(u32)));
+    const int nwin = (254 + W - 1) / W;
+    const size_t ntab = (size_t)nwin << (W - 1);
+    const int stride = (int)ctx->opt_ed_stride;
+    ed_drop_table(d);
+    u32* table = nullptr;
     u32* bases = nullptr;   // 2^(W i) * B per window, cached form (32 words each)
-    CU(cudaMalloc(&bases, (size_t)nwin * 32 * sizeof(u32)));
-    k_ed25519_window_bases<<<grid_for((size_t)nwin), ECB_TPB, 0, d.stream>>>(nwin, W, bases);
-    k_ed25519_table_points<<<grid_for(ntab), ECB_TPB, 0, d.stream>>>(ntab, W, nwin, bases, (u32*)d.cur->planes.p);
-    ctx->launches += 2;
-    cudaError_t le = cudaGetLastError();
-    if (le != cudaSuccess) {
-        cudaFree(bases);
-        CU(le);
+    auto build = [&]() -> int {
+        CU(cudaMalloc(&table, ntab * (size_t)stride * sizeof(u32)));
+        TRY(ensure(ctx, d.cur->planes, ntab * 3 * 8 * sizeof(u32)));
+        TRY(ensure(ctx, d.cur->pf, ntab * 8 * sizeof(u32)));
+        CU(cudaMalloc(&bases, (size_t)nwin * 32 * sizeof(u32)));
+        if (stride != 24) CU(cudaMemsetAsync(table, 0, ntab * (size_t)stride * sizeof(u32), d.stream));
+        k_ed25519_window_bases<<<grid_for((size_t)nwin), ECB_TPB, 0, d.stream>>>(nwin, W, bases);
+        k_ed25519_table_points<<<grid_for(ntab), ECB_TPB, 0, d.stream>>>(ntab, W, nwin, bases, (u32*)d.cur->planes.p);
+        ctx->launches += 2;
+        CU(cudaGetLastError());
+        FinEdNiels fin{(const u32*)d.cur->planes.p, ntab, table, (size_t)stride};
+        TRY((launch_batch_inv<F25519, FinEdNiels>(ctx, d, ntab, (const u32*)d.cur->planes.p, (u32*)d.cur->pf.p, fin, d.stream)));
+        CU(cudaStreamSynchronize(d.stream));
+        return ECB_OK;
+    };
+    int rc = build();
+    if (rc != ECB_OK) cudaStreamSynchronize(d.stream);   // nothing may still write into buffers about to be freed
+    if (bases) cudaFree(bases);
+    if (rc != ECB_OK) {
+        if (table) cudaFree(table);
+        return rc;
     }
-    FinEdNiels fin{(const u32*)d.cur->planes.p, ntab, d.ed_table};
-    TRY((launch_batch_inv<F25519, FinEdNiels>(ctx, d, ntab, (const u32*)d.cur->planes.p, (u32*)d.cur->pf.p, fin, d.stream)));
-    cudaError_t se = cudaStreamSynchronize(d.stream);
-    cudaFree(bases);
-    CU(se);
     if (ntab * 96 > ((size_t)256 << 20)) {  // give the build buffers of a large table back
         for (DevBuf* b : {&d.cur->planes, &d.cur->pf}) {
-            if (b->p) CU(cudaFree(b->p));
+            if (b->p) cudaFree(b->p);
             b->p = nullptr;
             b->cap = 0;
         }
     }
+    d.ed_table = table;
     d.ed_w = W;
     d.ed_nwin = nwin;
+    d.ed_stride = stride;
+    return ECB_OK;
+}
+static inline bool ed_table_stale(ecb_ctx* ctx, const DevCtx& d) {
+    return !d.ed_table || d.ed_nwin <= 0 || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w) || d.ed_stride != (int)ctx->opt_ed_stride;
+}
+// make sure the device holds a comb table of the configured shape (ecb_warm and the host entry points)
+int dev_ed25519_table(ecb_ctx* ctx, DevCtx& d) {
+    if (ed_table_stale(ctx, d)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
+    return ECB_OK;
+}
+
+// Launch shape of the fused small-batch kernel: LANES lanes per scalar and a block size such that the
+// whole batch is one wave of one block (<= 512 threads) per SM.  false: the batch is too large for it.
+static bool fused_shape(const DevCtx& d, size_t n, long force_lanes, int& lanes, int& tpb, unsigned& grid) {
+    const size_t cap = (size_t)d.sm_count * 512;
+    if (force_lanes) {
+        lanes = (int)force_lanes;
+    } else {   // measured (profiles/r02_tune_ed25519.jsonl): extra lanes pay while they add warps to idle schedulers, i.e. up to ~4 warps per SM
+        lanes = 8;
+        while (lanes > 1 && n * lanes > (size_t)d.sm_count * 128) lanes >>= 1;
+    }
+    size_t threads = n * lanes;
+    if (threads > cap) return false;
+    size_t per_sm = (threads + d.sm_count - 1) / d.sm_count;
+    tpb = (int)((per_sm + 31) / 32 * 32);
+    if (tpb < 32) tpb = 32;
+    grid = (unsigned)((threads + tpb - 1) / tpb);
+    return true;
+}
+template <bool CLAMP, class FIN>
+static int launch_fused(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, FIN fin, unsigned long long* status, cudaStream_t s, bool& done) {
+    done = false;
+    if (!ctx->opt_ed_fused || n == 0) return ECB_OK;
+    int lanes, tpb;
+    unsigned grid;
+    const bool fits = fused_shape(d, n, ctx->opt_ed_lanes, lanes, tpb, grid);
+    if (!fits && ctx->opt_ed_fused != 2) return ECB_OK;
+    prof_mark(ctx, d, s, 0);
+    if (fits) {
+        switch (lanes) {
+            case 1: k_ed25519_mul_base_fused<1, CLAMP, FIN, 512, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status); break;
+            case 2: k_ed25519_mul_base_fused<2, CLAMP, FIN, 512, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status); break;
+            case 4: k_ed25519_mul_base_fused<4, CLAMP, FIN, 512, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status); break;
+            default: k_ed25519_mul_base_fused<8, CLAMP, FIN, 512, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status); break;
+        }
+    } else {
+        k_ed25519_mul_base_fused<1, CLAMP, FIN, ECB_TPB, 4><<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status);
+    }
+    ctx->launches++;
+    CU(cudaGetLastError());
+    prof_mark(ctx, d, s, 1);   // one kernel: the whole step is booked as "scalar_mult", the finisher share is 0
+    prof_mark(ctx, d, s, 2);
+    done = true;
     return ECB_OK;
 }
 
 int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s,
                          size_t enc_stride_words) {
-    if (!d.ed_table || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
+    TRY(dev_ed25519_table(ctx, d));
+    TRY(reset_status(ctx, d, s));
+    {
+        bool done = false;
+        if (compressed) {
+            FusedEdCompressed fin{d_out, enc_stride_words ? enc_stride_words : 8};
+            TRY((launch_fused<false, FusedEdCompressed>(ctx, d, d_k, n, fin, d.cur->d_status, s, done)));
+        } else {
+            FusedEdXY fin{d_out};
+            TRY((launch_fused<false, FusedEdXY>(ctx, d, d_k, n, fin, d.cur->d_status, s, done)));
+        }
+        if (done) return ECB_OK;
+    }
     TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
-    TRY(reset_status(ctx, d, s));
     u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
-    k_ed25519_mul_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, planes, d.cur->d_status);
+    k_ed25519_mul_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, planes, d.cur->d_status);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);
@@ -118,19 +206,25 @@ int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32*
 }
 
 static __global__ void __launch_bounds__(ECB_TPB, 5) k_x25519_base(size_t n, const u32* scalars, const u32* table, int W, int nwin,
-                                                          u32* planes) {
+                                                          int stride, u32* planes) {
     size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
-    if (idx < n) x25519_base_body(idx, n, scalars, table, W, nwin, planes);
+    if (idx < n) x25519_base_body(idx, n, scalars, table, W, nwin, stride, planes);
 }
 int dev_x25519_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, cudaStream_t s) {
-    if (!d.ed_table || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
+    TRY(dev_ed25519_table(ctx, d));
     if (d.ed_w * d.ed_nwin < 256) return set_err(ctx, ECB_ERR_INVALID_ARG, "x25519_base needs a comb covering 256 bits (ed25519_comb_w)");
+    TRY(reset_status(ctx, d, s));
+    {
+        bool done = false;
+        FusedEdMontU fin{d_out};
+        TRY((launch_fused<true, FusedEdMontU>(ctx, d, d_k, n, fin, nullptr, s, done)));
+        if (done) return ECB_OK;
+    }
     TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
-    TRY(reset_status(ctx, d, s));
     u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
-    k_x25519_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, planes);
+    k_x25519_base<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, planes);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);
@@ -180,7 +274,7 @@ int dev_ed25519_verify_msgs(ecb_ctx* ctx, DevCtx& d, const unsigned char* a, con
 
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
                        unsigned char* ok, cudaStream_t s) {
-    if (!d.ed_table || (ctx->opt_ed_w && d.ed_w != (int)ctx->opt_ed_w)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
+    TRY(dev_ed25519_table(ctx, d));
     TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
     TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
     unsigned g = persistent_grid(d, k_ed25519_verify, n);
@@ -188,7 +282,7 @@ int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, cons
     TRY(reset_status(ctx, d, s));
     u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
-    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, (u32*)d.cur->scratch.p, planes, ok);
+    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, (u32*)d.cur->scratch.p, planes, ok);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);

@@ -1,7 +1,84 @@
 // tu_probe.cu — integer-pipe (IMAD) peak probe: the denominator of every roofline fraction.
 #include "host_ctx.h"
 #include "dev_ops.h"
+#include "fused.cuh"
 using namespace ecb;
+
+// latency probe -------------------------------------------------------------------------------
+// One block per SM; lane 0 of warp 0 reports clock64() cycles per operation of a dependent chain
+// (what a latency-bound small batch pays), plus the SM clock it ran at (clock64 vs %globaltimer).
+//   0: F25519::mul      1: F25519::sqr      2: F25519::invert (safegcd)      3: F25519::invert_fermat
+//   4: block_invert<F25519> with the launch's block size (whole scan + one inversion + peel)
+//   5: fe_shfl_up round trip (8 shuffles)                6: ge_madd_rt     7: ge_add_p3     8: mul2 (two interleaved products)
+template <int V>
+__global__ void __launch_bounds__(512, 1) k_latency_probe(int reps, double* out_cycles, double* out_mhz, u32* sink) {
+    __shared__ u32 sh[2 * FUSED_MAXW * 8];
+    fe25519 x, y;
+#pragma unroll
+    for (int i = 0; i < 8; i++) { x.v[i] = 0x9e3779b9u * (threadIdx.x + 1 + i) + blockIdx.x; y.v[i] = 0x85ebca6bu * (threadIdx.x + 3 + i) ^ 0x1234567u; }
+    x.v[7] &= 0x7fffffffu;
+    ge_p3 P;
+    ge_niels e;
+    P.X = x; P.Y = y; F::set_one(P.Z); F::mul(P.T, x, y);
+    e.yp = y; e.ym = x; e.t2d = P.T;
+    unsigned long long g0, g1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g0));
+    long long t0 = clock64();
+#pragma unroll 1
+    for (int r = 0; r < reps; r++) {
+        if (V == 0) F::mul(x, x, y);
+        else if (V == 1) F::sqr(x, x);
+        else if (V == 2) { F::invert(x, x); x.v[0] ^= 5u; }
+        else if (V == 3) { F::invert_fermat(x, x); x.v[0] ^= 5u; }
+        else if (V == 4) { u32 z; fe25519 o; block_invert<F25519>(o, x, z, sh, 0); x = o; x.v[0] ^= 5u; }
+        else if (V == 5) { fe25519 o; fe_shfl_up<F25519>(o, x, 1); x = o; x.v[0] += 1u; }
+        else if (V == 6) ge_madd_rt(P, P, e, true);
+        else if (V == 8) F::mul2(x, x, y, P.X, P.X, y);
+        else ge_add_p3<true>(P, P, P);
+    }
+    long long t1 = clock64();
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(g1));
+    u32 acc = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) acc ^= x.v[i] ^ P.X.v[i] ^ P.T.v[i];
+    sink[blockIdx.x * blockDim.x + threadIdx.x] = acc;
+    if (threadIdx.x == 0) {
+        out_cycles[blockIdx.x] = (double)(t1 - t0) / reps;
+        out_mhz[blockIdx.x] = g1 > g0 ? (double)(t1 - t0) / (double)(g1 - g0) * 1e3 : 0.0;
+    }
+}
+int dev_latency_probe(ecb_ctx* ctx, DevCtx& d, int variant, int threads, int reps, double* cycles, double* mhz) {
+    if (variant < 0 || variant > 8 || reps < 1 || threads < 32 || threads > 512 || threads % 32) return ECB_ERR_INVALID_ARG;
+    unsigned blocks = (unsigned)d.sm_count;
+    TRY(ensure(ctx, d.cur->aux, (size_t)blocks * 512 * sizeof(u32) + 2 * blocks * sizeof(double)));
+    double* dc = (double*)d.cur->aux.p;
+    double* dm = dc + blocks;
+    u32* sink = (u32*)(dm + blocks);
+    for (int rep = 0; rep < 2; rep++) {
+        switch (variant) {
+            case 0: k_latency_probe<0><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 1: k_latency_probe<1><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 2: k_latency_probe<2><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 3: k_latency_probe<3><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 4: k_latency_probe<4><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 5: k_latency_probe<5><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 6: k_latency_probe<6><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 7: k_latency_probe<7><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            default: k_latency_probe<8><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+        }
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaStreamSynchronize(d.stream));
+    }
+    std::vector<double> hc(blocks), hm(blocks);
+    CU(cudaMemcpy(hc.data(), dc, blocks * sizeof(double), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(hm.data(), dm, blocks * sizeof(double), cudaMemcpyDeviceToHost));
+    double sc = 0, sm = 0;
+    for (unsigned i = 0; i < blocks; i++) { sc += hc[i]; sm += hm[i]; }
+    if (cycles) *cycles = sc / blocks;
+    if (mhz) *mhz = sm / blocks;
+    return ECB_OK;
+}
 
 // integer-pipe probe -----------------------------------------------------------------------
 // Every variant keeps 8 independent dependency chains per thread whose multiplicand is the

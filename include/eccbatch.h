@@ -211,6 +211,11 @@ int ecb_dev_status(ecb_ctx* ctx, int dev_index, size_t* bad_index);
  * chains (the field kernels' instruction), 3 = IMAD.HI.U32, 4 = DFMA, 5 = integer add/logic.  Returns multiply-accumulates per second
  * on device `dev_index` and the kernel time. */
 int ecb_imad_probe(ecb_ctx* ctx, int dev_index, int variant, int iters, double* macs_per_s, double* ms);
+/* Latency probe: cycles per operation of a DEPENDENT chain in one warp per SM (what a small batch pays) and the
+ * SM clock the probe ran at.  variant: 0 field mul, 1 field square (GF(2^255-19)), 2 safegcd inversion, 3 Fermat
+ * inversion, 4 block-cooperative inversion of `threads` elements (fused.cuh), 5 one 8-word shuffle, 6 mixed
+ * extended addition, 7 complete extended addition.  threads: block size, multiple of 32, <= 512. */
+int ecb_latency_probe(ecb_ctx* ctx, int dev_index, int variant, int threads, int reps, double* cycles, double* sm_mhz);
 /* with option "profile" = 1: sum over the calls since the last collect of the device time (ms) of
  * the scalar-multiplication kernel(s) and of the batch-inversion / encoding kernel; synchronises. */
 int ecb_profile_collect(ecb_ctx* ctx, int dev_index, double* main_ms, double* finish_ms, int* calls);

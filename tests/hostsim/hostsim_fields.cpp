@@ -44,6 +44,8 @@ void hs_fe25519(int op, const u32* a, const u32* b, u32* r) {
         case 6: F25519::invert(z, x); break;
         case 7: F25519::mul_small(z, x, b[0]); break;
         case 8: F25519::pow_p58(z, x); break;
+        case 9: { fe25519 w; F25519::mul2(z, x, y, w, y, y); } break;    // first product of the interleaved pair
+        case 10: { fe25519 w; F25519::mul2(w, x, y, z, y, y); } break;   // second product
     }
     memcpy(r, z.v, 32);
 }

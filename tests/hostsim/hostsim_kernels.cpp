@@ -30,7 +30,7 @@ unsigned long long hs_ed25519_mul_base(const u32* k, size_t n, int W, const u32*
     int nwin = (254 + W - 1) / W;
     std::vector<u32> planes(3 * 8 * n), pf(8 * n);
     unsigned long long st = ~0ull;
-    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, k, table, W, nwin, planes.data(), &st);
+    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, k, table, W, nwin, 24, planes.data(), &st);
     size_t T = inv_threads(n);
     if (compressed) {
         FinEdCompressed fin{planes.data(), n, out};
@@ -42,10 +42,36 @@ unsigned long long hs_ed25519_mul_base(const u32* k, size_t n, int W, const u32*
     return st;
 }
 
+// lane-split comb of the fused small-batch kernel (fused.cuh), without the warp: the partial sums of
+// `lanes` lanes are added in the butterfly's order, then the usual affine finish
+unsigned long long hs_ed25519_mul_base_lanes(const u32* k, size_t n, int W, const u32* table, int lanes, u32* out) {
+    int nwin = (254 + W - 1) / W;
+    std::vector<u32> planes(3 * 8 * n), pf(8 * n);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) {
+        u32 kk[9];
+        ed25519_load_scalar<false>(kk, i, k, &st);
+        std::vector<ge_p3> part(lanes);
+        for (int l = 0; l < lanes; l++) ed25519_comb_partial(part[l], kk, table, W, nwin, 24, l, lanes, lanes > 1);
+        for (int d = 1; d < lanes; d <<= 1) {
+            std::vector<ge_p3> nxt(lanes);
+            for (int l = 0; l < lanes; l++) ge_add_p3<true>(nxt[l], part[l], part[l ^ d]);
+            part = nxt;
+        }
+        plane_st<8>(planes.data() + 0 * 8 * n, n, i, part[0].X.v);
+        plane_st<8>(planes.data() + 1 * 8 * n, n, i, part[0].Y.v);
+        plane_st<8>(planes.data() + 2 * 8 * n, n, i, part[0].Z.v);
+    }
+    size_t T = inv_threads(n);
+    FinEdXY fin{planes.data(), n, out};
+    for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
+    return st;
+}
+
 void hs_x25519_base(const u32* k, size_t n, int W, const u32* table, u32* out) {
     int nwin = (254 + W - 1) / W;
     std::vector<u32> planes(3 * 8 * n), pf(8 * n);
-    for (size_t i = 0; i < n; i++) x25519_base_body(i, n, k, table, W, nwin, planes.data());
+    for (size_t i = 0; i < n; i++) x25519_base_body(i, n, k, table, W, nwin, 24, planes.data());
     size_t T = inv_threads(n);
     FinEdMontU fin{planes.data(), n, out};
     for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
@@ -131,7 +157,7 @@ void hs_ed25519_verify(const u32* a, const u32* r, const u32* s, const u32* k, s
                        unsigned char* ok) {
     int nwin = (254 + W - 1) / W;
     std::vector<u32> tbl(8 * 32), planes(3 * 8 * n), pf(8 * n);
-    for (size_t i = 0; i < n; i++) ed25519_verify_body(i, n, a, s, k, table, W, nwin, tbl.data(), planes.data(), ok);
+    for (size_t i = 0; i < n; i++) ed25519_verify_body(i, n, a, s, k, table, W, nwin, 24, tbl.data(), planes.data(), ok);
     size_t T = inv_threads(n);
     FinEdVerify fin{planes.data(), n, r, ok};
     for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
@@ -216,7 +242,7 @@ extern "C" void hs_ed25519_public_from_seed(const unsigned char* seeds, size_t n
     std::vector<u32> a(8 * n), prefix(8 * n), planes(3 * 8 * n), pf(8 * n);
     unsigned long long st = ~0ull;
     for (size_t i = 0; i < n; i++) ed25519_expand_body(i, seeds, a.data(), prefix.data());
-    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, a.data(), table, W, nwin, planes.data(), &st);
+    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, a.data(), table, W, nwin, 24, planes.data(), &st);
     size_t T = inv_threads(n);
     FinEdCompressed fin{planes.data(), n, pub};
     for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
@@ -228,7 +254,7 @@ extern "C" void hs_ed25519_sign(const unsigned char* seeds, const unsigned char*
     unsigned long long st = ~0ull;
     for (size_t i = 0; i < n; i++) ed25519_expand_body(i, seeds, a.data(), prefix.data());
     for (size_t i = 0; i < n; i++) ed25519_sign_nonce_body(i, prefix.data(), msgs, off, r.data());
-    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, r.data(), table, W, nwin, planes.data(), &st);
+    for (size_t i = 0; i < n; i++) ed25519_mul_base_body<false>(i, n, r.data(), table, W, nwin, 24, planes.data(), &st);
     size_t T = inv_threads(n);
     FinEdCompressed fin{planes.data(), n, (u32*)sig, 16};
     for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);

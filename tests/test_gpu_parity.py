@@ -80,6 +80,77 @@ def test_ed25519_mul_base_every_comb_width(w, coracle, golden):
             assert table[i * (1 << (w - 1)) + j - 1].tobytes() == exp
 
 
+@pytest.mark.parametrize("lanes", [0, 1, 2, 4, 8])
+def test_ed25519_mul_base_fused_small_batch_every_lane_count(lanes, coracle, golden):
+    """The small-batch kernel (fused.cuh: windows split over lanes, block-level inversion in the same launch)
+    against the C oracle at 2^10 ... 2^17 and ragged sizes, for every lane count, plus the edge scalars;
+    the two-kernel large-batch form (ed25519_fused = 0) must give the same bytes."""
+    from eccoxide_b200 import Context
+
+    g = rng(SEEDS["ed25519"] + 100 + lanes)
+    edge = rows([v.to_bytes(32, "little") for v in ed_edge_scalars(golden)])
+    big = scalars_mod(g, (1 << 17) + 77, R.L25519, 32, "little")
+    exp_big = coracle.ed25519_mul_base(big, threads(coracle))
+    with Context() as c:
+        c.set_option("ed25519_lanes", lanes)
+        c.ed25519_mul_base(edge[:2])                  # builds the comb table (its launches are not the call's)
+        cap = 148 * 512 // max(lanes, 1)
+        for n in (1, 31, 33, 1 << 10, 1 << 12, (1 << 13) + 5, 1 << 14, 1 << 15, 1 << 16, 75776, (1 << 17) + 77):
+            kb = big[:n].copy()
+            m = min(n, edge.shape[0])
+            kb[:m] = edge[:m]
+            exp = exp_big[:n].copy()
+            exp[:m] = coracle.ed25519_mul_base(edge[:m])
+            c.set_option("ed25519_fused", 1)
+            l0 = c.launch_count()
+            got = c.ed25519_mul_base(kb)
+            used_fused = c.launch_count() - l0 == 1
+            assert np.array_equal(got, exp), (lanes, n)
+            if lanes and n <= cap and n < 16384:       # below one pipeline chunk the host path is a single launch
+                assert used_fused, (lanes, n)
+            enc = c.ed25519_mul_base(kb, compressed=True)
+            assert np.array_equal(enc[:, :31], exp[:, 32:63]) and np.array_equal(enc[:, 31] & 0x7F, exp[:, 63]) and np.array_equal(enc[:, 31] >> 7, exp[:, 0] & 1)
+            if lanes == 0:
+                c.set_option("ed25519_fused", 0)
+                assert np.array_equal(c.ed25519_mul_base(kb), exp), ("split", n)
+                c.set_option("ed25519_fused", 2)   # the fused body with the large-batch launch shape
+                assert np.array_equal(c.ed25519_mul_base(kb), exp), ("fused2", n)
+        # non-canonical scalar is still reported with its index
+        bad = big[:5000].copy()
+        bad[4321] = np.frombuffer(R.L25519.to_bytes(32, "little"), dtype=np.uint8)
+        c.set_option("ed25519_fused", 1)
+        with pytest.raises(Exception) as ei:
+            c.ed25519_mul_base(bad)
+        assert getattr(ei.value, "bad_index", None) == 4321
+
+
+def test_x25519_base_fused_small_batch(ctx, coracle):
+    g = rng(SEEDS["x25519"] + 9)
+    for n in (1, 100, 4096, 1 << 15, 1 << 16):
+        ks = rand_bytes(g, n, 32)
+        nine = np.tile(np.frombuffer((9).to_bytes(32, "little"), dtype=np.uint8), (n, 1))
+        assert np.array_equal(ctx.x25519_base(ks), coracle.x25519(ks, nine, threads(coracle))), n
+
+
+@pytest.mark.parametrize("stride", [24, 32])
+def test_ed25519_comb_entry_stride(stride, coracle):
+    """Comb entries packed (96 B) or one per 128-byte line: same results, same table contents."""
+    from eccoxide_b200 import Context
+
+    g = rng(SEEDS["ed25519"] + 7)
+    kb = scalars_mod(g, 3000, R.L25519, 32, "little")
+    with Context(ed25519_comb_w=9) as c:
+        c.set_option("ed25519_entry_stride", stride)
+        exp = coracle.ed25519_mul_base(kb, threads(coracle))
+        assert np.array_equal(c.ed25519_mul_base(kb), exp)
+        c.set_option("ed25519_fused", 0)
+        assert np.array_equal(c.ed25519_mul_base(kb), exp)
+        table, tw, nwin = c.debug_ed25519_table()
+        x, y = R.ed_mul(3 << 9, R.ED_B)
+        p = R.P25519
+        assert table[(1 << 8) + 2].tobytes() == ((y + x) % p).to_bytes(32, "little") + ((y - x) % p).to_bytes(32, "little") + (2 * R.ED_D * x * y % p).to_bytes(32, "little")
+
+
 def test_ed25519_mul_base_config1_full_batch(ctx, coracle):
     """Config 1 at full size (2^16 random scalars): 100 % against the C oracle, plus libsodium sample."""
     g = rng(SEEDS["ed25519"])

@@ -21,7 +21,7 @@ def hs():
     subprocess.check_call(["make", "-s", "-j4", "-C", HS])
     f = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_fields.so"))
     k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
-    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_ecdsa_verify"):
+    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_ecdsa_verify"):
         getattr(k, fn).restype = ctypes.c_ulonglong
     return f, k
 
@@ -47,7 +47,7 @@ def test_fe25519_ops(hs):
     r = np.zeros(8, dtype=np.uint32)
     for a, b in cases:
         aw, bw = words(a, 8), words(b, 8)
-        for op, exp in ((0, a * b), (1, a * a), (2, a + b), (3, a - b), (4, -a)):
+        for op, exp in ((0, a * b), (1, a * a), (2, a + b), (3, a - b), (4, -a), (9, a * b), (10, b * b)):
             f.hs_fe25519(op, p(aw), p(bw), p(r))
             assert val(r) % P == exp % P, (op, a, b)
         f.hs_fe25519(5, p(aw), p(bw), p(r))
@@ -108,6 +108,11 @@ def test_ed25519_mul_base_and_table(hs, golden, coracle):
         out = np.zeros((n, 64), dtype=np.uint8)
         st = k.hs_ed25519_mul_base(p(kb), ctypes.c_size_t(n), W, p(table), p(out), 0)
         assert st == 2**64 - 1 and np.array_equal(out, exp)
+        # the fused small-batch kernel's lane split: windows l, l + lanes, ... per lane, butterfly of complete additions
+        for lanes in (1, 2, 4, 8):
+            out2 = np.zeros((n, 64), dtype=np.uint8)
+            st = k.hs_ed25519_mul_base_lanes(p(kb), ctypes.c_size_t(n), W, p(table), lanes, p(out2))
+            assert st == 2**64 - 1 and np.array_equal(out2, exp), (W, lanes)
     bad = kb.copy()
     bad[3] = np.frombuffer(R.L25519.to_bytes(32, "little"), dtype=np.uint8)
     st = k.hs_ed25519_mul_base(p(bad), ctypes.c_size_t(n), W, p(table), p(out), 0)
