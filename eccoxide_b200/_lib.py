@@ -61,6 +61,7 @@ SIGNATURES = {
     "ecb_dev_status": (_int, [_vp, _int, _szp]),
     "ecb_imad_probe": (_int, [_vp, _int, _int, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "ecb_latency_probe": (_int, [_vp, _int, _int, _int, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
+    "ecb_fieldmul_probe": (_int, [_vp, _int, _int, _int, _int, _int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]),
     "ecb_wei_decompress": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_bls12_381_g1_from_compressed": (_int, [_vp, _vp, _sz, _int, _vp, _vp]),
     "ecb_bls12_381_g1_to_compressed": (_int, [_vp, _vp, _vp, _sz, _vp]),
@@ -73,6 +74,7 @@ SIGNATURES = {
     "ecb_ecdsa_sign_hashed": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_sign_hashed_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "ecb_ecdsa_sign": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ecb_debug_fused_trace": (ctypes.c_long, [_vp, _int, _vp, _sz]),
     "ecb_debug_chunk_plan": (ctypes.c_long, [_sz, _sz, _sz, ctypes.c_long, _vp, _sz]),
     "ecb_debug_ed25519_table": (ctypes.c_long, [_vp, _int, _vp, _sz, ctypes.POINTER(_int), ctypes.POINTER(_int)]),
 }

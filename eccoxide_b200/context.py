@@ -365,6 +365,19 @@ class Context:
         self._check(self._lib.ecb_latency_probe(self._ctx, dev_index, variant, threads, reps, ctypes.byref(cyc), ctypes.byref(mhz)))
         return cyc.value, mhz.value
 
+    def fieldmul_probe(self, fp64_num, fp64_den, blocks_per_sm=4, reps=512, dev_index=0):
+        v, chk = ctypes.c_double(), ctypes.c_double()
+        self._check(self._lib.ecb_fieldmul_probe(self._ctx, dev_index, fp64_num, fp64_den, blocks_per_sm, reps, ctypes.byref(v), ctypes.byref(chk)))
+        return v.value, int(chk.value)
+
+    def debug_fused_trace(self, dev_index=0):
+        nb = int(self._lib.ecb_debug_fused_trace(self._ctx, dev_index, None, 0))
+        if nb < 0:
+            self._check(nb)
+        out = np.zeros((max(nb, 1), 4), dtype=np.uint64)
+        self._lib.ecb_debug_fused_trace(self._ctx, dev_index, _p(out), nb)
+        return out[:nb]
+
     def debug_ed25519_table(self, dev_index=0):
         w = ctypes.c_int()
         nwin = ctypes.c_int()

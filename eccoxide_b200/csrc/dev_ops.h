@@ -56,3 +56,4 @@ int dev_ecdsa_sign_msgs_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32*
                              int hash, size_t n, u32* d_rs, unsigned char* d_ok, cudaStream_t s);
 int dev_imad_probe(ecb_ctx* ctx, DevCtx& d, int variant, int iters, double* macs_per_s, double* ms_out);
 int dev_latency_probe(ecb_ctx* ctx, DevCtx& d, int variant, int threads, int reps, double* cycles, double* mhz);
+int dev_fieldmul_probe(ecb_ctx* ctx, DevCtx& d, int num, int den, int blocks_per_sm, int reps, double* muls_per_s, double* check);

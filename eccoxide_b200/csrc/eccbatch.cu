@@ -82,6 +82,7 @@ void ecb_destroy(ecb_ctx* ctx) {
         }
         for (auto& r : d->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); cudaEventDestroy(r.c); }
         if (d->ed_table) cudaFree(d->ed_table);
+        if (d->trace.p) cudaFree(d->trace.p);
         if (d->ev_fork) cudaEventDestroy(d->ev_fork);
         for (u32* t : d->wei_table)
             if (t) cudaFree(t);
@@ -152,6 +153,10 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
     }
     if (!strcmp(key, "dev_split")) {
         ctx->opt_dev_split = value ? 1 : 0;
+        return ECB_OK;
+    }
+    if (!strcmp(key, "trace")) {
+        ctx->opt_trace = value ? 1 : 0;
         return ECB_OK;
     }
     if (!strcmp(key, "profile")) {
@@ -1038,6 +1043,22 @@ int ecb_latency_probe(ecb_ctx* ctx, int di, int variant, int threads, int reps, 
     if (!d) return ECB_ERR_INVALID_ARG;
     CU(cudaSetDevice(d->dev));
     return dev_latency_probe(ctx, *d, variant, threads, reps, cycles, sm_mhz);
+}
+
+int ecb_fieldmul_probe(ecb_ctx* ctx, int di, int fp64_num, int fp64_den, int blocks_per_sm, int reps, double* muls_per_s, double* check) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    CU(cudaSetDevice(d->dev));
+    return dev_fieldmul_probe(ctx, *d, fp64_num, fp64_den, blocks_per_sm, reps, muls_per_s, check);
+}
+
+long ecb_debug_fused_trace(ecb_ctx* ctx, int di, unsigned long long* out, size_t cap_blocks) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d) return ECB_ERR_INVALID_ARG;
+    if (cudaSetDevice(d->dev) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess) return ECB_ERR_CUDA;
+    size_t nb = d->trace_blocks < cap_blocks ? d->trace_blocks : cap_blocks;
+    if (out && nb && cudaMemcpy(out, d->trace.p, nb * 4 * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return ECB_ERR_CUDA;
+    return (long)d->trace_blocks;
 }
 
 long ecb_debug_chunk_plan(size_t lo, size_t hi, size_t chunk, long ramp, size_t* bounds, size_t cap) {

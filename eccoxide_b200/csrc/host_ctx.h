@@ -58,6 +58,8 @@ struct DevCtx {
     int ed_w = 0, ed_nwin = 0, ed_stride = 24;  // comb width, windows, words between entries (24 packed, 32 = 128-byte aligned)
     u32* wei_table[3] = {nullptr, nullptr, nullptr};  // generator combs of p256r1, p384r1, bls12_381 G1
     int wei_w[3] = {0, 0, 0}, wei_nwin[3] = {0, 0, 0};
+    DevBuf trace;                             // option "trace": per-block timestamps of the last fused launch
+    size_t trace_blocks = 0;
     std::mutex mu;
     // optional per-kernel timing (ecb_set_option "profile"): events recorded on the launching stream
     // around the scalar-mult kernel(s) [a,b] and the batch-inversion finisher [b,c] of every call
@@ -80,6 +82,7 @@ struct ecb_ctx {
     long opt_ed_lanes = 0;                    // lanes per scalar in the fused kernel: 0 = by batch size, or 1 / 2 / 4 / 8
     size_t opt_chunk = 189440;  // elements per pipeline chunk = 148 SMs x 1280 (ECB_NSLOT chunks in flight per device; measured best of 2^16..2^19)
     long opt_profile = 0;
+    long opt_trace = 0;                       // 1: the fused kernels record per-block phase timestamps (measurement only)
     long opt_inv_hi = 1;                      // run batch inversions on the slot's high-priority side stream
     long opt_ramp = 2;                        // pipeline chunk schedule: this many halvings of the chunk size at both ends of a batch (option "ramp")
     long opt_dev_split = 0;                   // 1: split large device-resident batches over the slot streams (measured: no gain, the

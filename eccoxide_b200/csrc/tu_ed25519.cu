@@ -9,13 +9,16 @@ static __global__ void __launch_bounds__(ECB_TPB, 5) k_ed25519_mul_base(size_t n
     if (idx < n) ed25519_mul_base_body<false>(idx, n, scalars, table, W, nwin, stride, planes, status);
 }
 // small-batch form (fused.cuh): LANES lanes per scalar, affine conversion in the same launch.
-// <512, 1>: one block of up to 512 threads per SM, the whole batch in one wave; <128, 4>: the same
-// body with the large-batch launch shape (option ed25519_fused = 2, for measurement).
+// <FUSED_WIDE_T, 1>: one block of up to 448 threads per SM (65536 / 448 = 146 registers per thread: room for the
+// software-pipelined table loads), the whole batch in one wave — 148 x 448 = 66304 >= 2^16 scalars, BASELINE
+// configs[0]; <128, 4>: the same body with the large-batch launch shape (option ed25519_fused = 2, for measurement).
+#define FUSED_WIDE_T 448
 template <int LANES, bool CLAMP, class FIN, int MAXT, int MINB>
 static __global__ void __launch_bounds__(MAXT, MINB) k_ed25519_mul_base_fused(size_t n, const u32* scalars, const u32* table, int W, int nwin,
-                                                                      int stride, FIN fin, unsigned long long* status) {
+                                                                      int stride, FIN fin, unsigned long long* status,
+                                                                      unsigned long long* trace) {
     __shared__ u32 sh[2 * FUSED_MAXW * 8];
-    ed25519_mul_base_fused_block<LANES, CLAMP, FIN>(n, scalars, table, W, nwin, stride, fin, status, sh);
+    ed25519_mul_base_fused_block<LANES, CLAMP, FIN>(n, scalars, table, W, nwin, stride, fin, status, sh, trace);
 }
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_window_bases(int nwin, int W, u32* bases) {
     int i = (int)(blockIdx.x * ECB_TPB + threadIdx.x);
@@ -126,9 +129,9 @@ int dev_ed25519_table(ecb_ctx* ctx, DevCtx& d) {
 }
 
 // Launch shape of the fused small-batch kernel: LANES lanes per scalar and a block size such that the
-// whole batch is one wave of one block (<= 512 threads) per SM.  false: the batch is too large for it.
+// whole batch is one wave of one block (<= FUSED_WIDE_T threads) per SM.  false: the batch is too large for it.
 static bool fused_shape(const DevCtx& d, size_t n, long force_lanes, int& lanes, int& tpb, unsigned& grid) {
-    const size_t cap = (size_t)d.sm_count * 512;
+    const size_t cap = (size_t)d.sm_count * FUSED_WIDE_T;
     if (force_lanes) {
         lanes = (int)force_lanes;
     } else {   // measured (profiles/r02_tune_ed25519.jsonl): extra lanes pay while they add warps to idle schedulers, i.e. up to ~4 warps per SM
@@ -151,16 +154,23 @@ static int launch_fused(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, FIN f
     unsigned grid;
     const bool fits = fused_shape(d, n, ctx->opt_ed_lanes, lanes, tpb, grid);
     if (!fits && ctx->opt_ed_fused != 2) return ECB_OK;
+    unsigned long long* trace = nullptr;
+    if (ctx->opt_trace) {   // measurement only: 4 timestamps per block of the last fused launch (ecb_debug_fused_trace)
+        size_t blocks = fits ? grid : grid_for(n);
+        TRY(ensure(ctx, d.trace, blocks * 4 * sizeof(unsigned long long)));
+        trace = (unsigned long long*)d.trace.p;
+        d.trace_blocks = blocks;
+    }
     prof_mark(ctx, d, s, 0);
     if (fits) {
         switch (lanes) {
-            case 1: k_ed25519_mul_base_fused<1, CLAMP, FIN, 512, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status); break;
-            case 2: k_ed25519_mul_base_fused<2, CLAMP, FIN, 512, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status); break;
-            case 4: k_ed25519_mul_base_fused<4, CLAMP, FIN, 512, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status); break;
-            default: k_ed25519_mul_base_fused<8, CLAMP, FIN, 512, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status); break;
+            case 1: k_ed25519_mul_base_fused<1, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
+            case 2: k_ed25519_mul_base_fused<2, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
+            case 4: k_ed25519_mul_base_fused<4, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
+            default: k_ed25519_mul_base_fused<8, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
         }
     } else {
-        k_ed25519_mul_base_fused<1, CLAMP, FIN, ECB_TPB, 4><<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status);
+        k_ed25519_mul_base_fused<1, CLAMP, FIN, ECB_TPB, 4><<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace);
     }
     ctx->launches++;
     CU(cudaGetLastError());

@@ -2,7 +2,68 @@
 #include "host_ctx.h"
 #include "dev_ops.h"
 #include "fused.cuh"
+#include "fe43.cuh"
 using namespace ecb;
+
+// field-multiplication throughput on the two multiplier pipes -----------------------------------
+// Every thread runs a dependent chain of `reps` GF(2^255-19) products; warps with (warp % den) < num use the
+// FP64-pipe field (fe43.cuh), the others the integer field (fe25519.cuh).  num/den = 0/1: integer only,
+// 1/1: FP64 only, 1/2: every other warp.  Reports products per second over the whole chip.
+__global__ void __launch_bounds__(128) k_fieldmul_probe(int reps, int num, int den, u32* sink) {
+    const u32 tid = blockIdx.x * 128 + threadIdx.x;
+    const int warp = threadIdx.x >> 5;
+    u32 w[8], yw[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { w[i] = 0x9e3779b9u * (tid + 1 + i); yw[i] = 0x85ebca6bu * (tid + 3 + i) ^ 0x1234567u; }
+    u32 acc = 0;
+    if ((warp % den) < num) {
+        fe43 x, y;
+        F43::from_words(x, w);
+        F43::from_words(y, yw);
+#pragma unroll 1
+        for (int r = 0; r < reps; r++) F43::mul(x, x, y);
+        fe25519 o;
+        F43::to_fe25519(o, x);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc ^= o.v[i];
+    } else {
+        fe25519 x, y;
+        F25519::from_words(x, w);
+        F25519::from_words(y, yw);
+#pragma unroll 1
+        for (int r = 0; r < reps; r++) F25519::mul(x, x, y);
+#pragma unroll
+        for (int i = 0; i < 8; i++) acc ^= x.v[i];
+    }
+    sink[tid] = acc;
+}
+int dev_fieldmul_probe(ecb_ctx* ctx, DevCtx& d, int num, int den, int blocks_per_sm, int reps, double* muls_per_s, double* check) {
+    if (den < 1 || num < 0 || num > den || blocks_per_sm < 1 || blocks_per_sm > 16 || reps < 1) return ECB_ERR_INVALID_ARG;
+    unsigned blocks = (unsigned)(d.sm_count * blocks_per_sm);
+    TRY(ensure(ctx, d.cur->aux, (size_t)blocks * 128 * sizeof(u32)));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    for (int rep = 0; rep < 2; rep++) {
+        CU(cudaEventRecord(e0, d.stream));
+        k_fieldmul_probe<<<blocks, 128, 0, d.stream>>>(reps, num, den, (u32*)d.cur->aux.p);
+        ctx->launches++;
+        CU(cudaGetLastError());
+        CU(cudaEventRecord(e1, d.stream));
+        CU(cudaEventSynchronize(e1));
+    }
+    float ms = 0;
+    CU(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (muls_per_s) *muls_per_s = (double)blocks * 128.0 * reps / (ms * 1e-3);
+    if (check) {   // both fields compute the same chain from the same words: XOR of thread 0's result words
+        u32 v = 0;
+        CU(cudaMemcpy(&v, d.cur->aux.p, sizeof(u32), cudaMemcpyDeviceToHost));
+        *check = (double)v;
+    }
+    return ECB_OK;
+}
 
 // latency probe -------------------------------------------------------------------------------
 // One block per SM; lane 0 of warp 0 reports clock64() cycles per operation of a dependent chain

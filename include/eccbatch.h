@@ -68,6 +68,11 @@ int ecb_device_count(ecb_ctx* ctx);
  *   "inv_block"             batch inversion: 0 one inversion per thread, 2 one per block, 1 (default) per field as measured
  *   "inv_hi"                1 (default): batch inversions of pipelined chunks run on a high-priority side stream
  *   "dev_split"             1: split large device-resident batches over the slot streams (default 0)
+ *   "ed25519_entry_stride"  32-bit words between Ed25519 comb entries: 24 (packed, 96 B) or 32 (one entry per 128-byte line)
+ *   "ed25519_fused"         small-batch kernel (lanes share a scalar, affine conversion in the same launch): 0 never,
+ *                           1 (default) when the batch fits one wave of the device, 2 always
+ *   "ed25519_lanes"         lanes per scalar in that kernel: 0 (default) by batch size, or 1, 2, 4, 8
+ *   "trace"                 1: the fused kernel records per-block phase timestamps (ecb_debug_fused_trace)
  *   "profile"               1: record CUDA events around the kernels of every call on the launching stream,
  *                           read back with ecb_profile_collect */
 int ecb_set_option(ecb_ctx* ctx, const char* key, long value);
@@ -216,12 +221,21 @@ int ecb_imad_probe(ecb_ctx* ctx, int dev_index, int variant, int iters, double* 
  * inversion, 4 block-cooperative inversion of `threads` elements (fused.cuh), 5 one 8-word shuffle, 6 mixed
  * extended addition, 7 complete extended addition.  threads: block size, multiple of 32, <= 512. */
 int ecb_latency_probe(ecb_ctx* ctx, int dev_index, int variant, int threads, int reps, double* cycles, double* sm_mhz);
+/* Field-multiplication throughput on the two multiplier pipes: every thread runs a dependent chain of `reps`
+ * GF(2^255-19) products; warps with (warp % fp64_den) < fp64_num use the FP64-pipe field (csrc/fe43.cuh), the
+ * others the integer field (csrc/fe25519.cuh); blocks_per_sm blocks of 128 threads per SM.  Returns products per
+ * second over the chip and a checksum word (the same for every split: both fields compute the same values). */
+int ecb_fieldmul_probe(ecb_ctx* ctx, int dev_index, int fp64_num, int fp64_den, int blocks_per_sm, int reps, double* muls_per_s,
+                       double* check);
 /* with option "profile" = 1: sum over the calls since the last collect of the device time (ms) of
  * the scalar-multiplication kernel(s) and of the batch-inversion / encoding kernel; synchronises. */
 int ecb_profile_collect(ecb_ctx* ctx, int dev_index, double* main_ms, double* finish_ms, int* calls);
 /* debug (no device needed): the pipeline chunk schedule the host entry points use for one device's
  * slice [lo, hi) — writes the chunk boundaries (first = lo, last = hi) and returns how many */
 long ecb_debug_chunk_plan(size_t lo, size_t hi, size_t chunk, long ramp, size_t* bounds, size_t cap);
+/* debug (option "trace" = 1): per block of the last fused small-batch launch four %globaltimer values in ns —
+ * start, comb done, inversion done, end.  Synchronises the device; returns the number of blocks recorded. */
+long ecb_debug_fused_trace(ecb_ctx* ctx, int dev_index, unsigned long long* out, size_t cap_blocks);
 /* debug: copy the device's Ed25519 comb table (niels entries, 96 B each) to host; returns entries */
 long ecb_debug_ed25519_table(ecb_ctx* ctx, int dev_index, uint8_t* out, size_t cap_bytes, int* w, int* nwin);
 

@@ -4,6 +4,7 @@
 #define ECB_HOSTSIM 1
 #include "../../eccoxide_b200/csrc/fe25519.cuh"
 #include "../../eccoxide_b200/csrc/mont_kinds.cuh"
+#include "../../eccoxide_b200/csrc/fe43.cuh"
 #include <string.h>
 using namespace ecb;
 
@@ -48,6 +49,37 @@ void hs_fe25519(int op, const u32* a, const u32* b, u32* r) {
         case 10: { fe25519 w; F25519::mul2(w, x, y, z, y, y); } break;   // second product
     }
     memcpy(r, z.v, 32);
+}
+// FP64-pipe field (fe43.cuh): operands given as 8 words (converted with from_words), optionally loosened by
+// adding `loosen` copies of the operand to itself (limbs up to (loosen + 1) * 2^43); result converted back with to_fe25519.
+// op: 0 mul 1 sqr 2 add 3 sub 4 neg-then-mul (signed limbs) 5 conversion round trip
+void hs_fe43(int op, const u32* a, const u32* b, int loosen, u32* r) {
+    fe43 x, y, z;
+    F43::from_words(x, a); F43::from_words(y, b);
+    fe43 x0 = x, y0 = y;
+    for (int i = 0; i < loosen; i++) { F43::add(x, x, x0); F43::add(y, y, y0); }
+    switch (op) {
+        case 0: F43::mul(z, x, y); break;
+        case 1: F43::sqr(z, x); break;
+        case 2: F43::add(z, x, y); break;
+        case 3: F43::sub(z, x, y); break;
+        case 4: { fe43 n; F43::neg(n, x); F43::sub(n, n, y0); F43::mul(z, n, y); } break;   // (-x - y0) * y
+        case 5: z = x; break;
+    }
+    // chained use: feed the tight result through another product to exercise signed limbs
+    fe25519 o;
+    F43::to_fe25519(o, z);
+    memcpy(r, o.v, 32);
+}
+double hs_fe43_maxlimb(int op, const u32* a, const u32* b, int loosen) {
+    fe43 x, y, z;
+    F43::from_words(x, a); F43::from_words(y, b);
+    fe43 x0 = x, y0 = y;
+    for (int i = 0; i < loosen; i++) { F43::add(x, x, x0); F43::add(y, y, y0); }
+    if (op == 0) F43::mul(z, x, y); else F43::sqr(z, x);
+    double m = 0;
+    for (int i = 0; i < 6; i++) { double t = z.v[i] < 0 ? -z.v[i] : z.v[i]; if (t > m) m = t; }
+    return m;
 }
 u32 hs_fe25519_is_canonical(const u32* a) { return F25519::is_canonical_words(a); }
 

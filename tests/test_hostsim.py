@@ -61,6 +61,31 @@ def test_fe25519_ops(hs):
         assert val(r) % P == pow(a, (P - 5) // 8, P)
 
 
+def test_fe43_fp64_field(hs):
+    """GF(2^255-19) on the FP64 pipe (csrc/fe43.cuh: 6 signed 43-bit limbs in doubles, products split by FMA):
+    exact for every operand shape incl. all-ones limbs, loosened (unreduced sums) inputs and negative limbs,
+    and the outputs stay inside the tight bound the exactness argument needs."""
+    f, _ = hs
+    f.hs_fe43_maxlimb.restype = ctypes.c_double
+    g = rng(43)
+    P = R.P25519
+    top = 2**256 - 1
+    cases = [(0, 0), (1, 1), (P - 1, P - 1), (top, top), (2**255 - 1, top), (P, 2), (2**43 - 1, 2**215 * (2**41 - 1))]
+    cases += [(sum((2**43 - 1) << (43 * i) for i in range(0, 6, 2)) & top, sum((2**43 - 1) << (43 * i) for i in range(1, 6, 2)) & top)]
+    cases += [(_structured(g, 8), _structured(g, 8)) for _ in range(150)]
+    cases += [(int.from_bytes(g.bytes(32), "little"), int.from_bytes(g.bytes(32), "little")) for _ in range(300)]
+    r = np.zeros(8, dtype=np.uint32)
+    tight = 2.0**42 + 2.0**16
+    for a, b in cases:
+        aw, bw = words(a, 8), words(b, 8)
+        for loosen in (0, 1, 4):
+            k = loosen + 1
+            for op, exp in ((0, k * a * k * b), (1, k * a * k * a), (2, k * a + k * b), (3, k * a - k * b), (4, (-k * a - b) * k * b), (5, k * a)):
+                f.hs_fe43(op, p(aw), p(bw), loosen, p(r))
+                assert val(r) % P == exp % P, (op, loosen, hex(a), hex(b))
+            assert f.hs_fe43_maxlimb(0, p(aw), p(bw), loosen) <= tight and f.hs_fe43_maxlimb(1, p(aw), p(bw), loosen) <= tight
+
+
 @pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (1, R.P256.n, 8), (2, R.P384.p, 12), (3, R.P384.n, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
 def test_montgomery_fields(hs, field, mod, n):
     f, _ = hs
