@@ -225,6 +225,16 @@ struct F25519 {
         const u32 p[8] = {0xffffffedu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x7fffffffu};
         sg_modinv<8, 9, 22>(r.v, c.v, p);
     }
+#ifndef ECB_HOSTSIM
+    // the same inverse by one whole warp (every lane passes the same a): ~3x shorter latency, for the
+    // block-level batch inversions where one inversion runs while the rest of the block waits
+    __device__ __forceinline__ static void invert_warp(el& r, const el& a) {
+        el c;
+        freeze(c, a);
+        const u32 p[8] = {0xffffffedu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x7fffffffu};
+        sg_modinv_warp<8, 9, 22>(r.v, c.v, p);
+    }
+#endif
     // a^((p-5)/8) (curve25519.rs:185)
     ECB_DEV static void pow_p58(el& r, const el& a) {
         el t, z11;

@@ -44,77 +44,91 @@ __device__ __forceinline__ void fe_shfl_xor(typename FT::el& r, const typename F
     for (int k = 0; k < FT::N; k++) r.v[k] = __shfl_xor_sync(0xffffffffu, a.v[k], m);
 }
 
-// Block-cooperative inversion: every thread of the block passes one element z and receives z^-1
-// (z = 0 -> treated as 1, `zero` set).  blockDim.x must be a multiple of 32, at most 32 * FUSED_MAXW.
-// sh: 2 * FUSED_MAXW * N words of shared memory.  inv_warp: the warp that runs the safegcd (callers
-// rotate it with blockIdx so that co-resident blocks do not pile their inversions on one scheduler).
+// Block-cooperative inversion: every WORK thread of the block passes one element z and receives z^-1
+// (z = 0 -> treated as 1, `zero` set).  The block is nww <= FUSED_MAXW - 1 work warps plus ONE more warp
+// (the last) that holds no element and does nothing but the inversion, so that everything which does
+// not need the inverse happens beside it instead of before or after it:
+//   all work warps   inclusive prefix products over their lanes; lane 31 publishes the warp total   | barrier
+//   inversion warp   product of the warp totals (butterfly), ONE inverse by the 32 lanes (sg_modinv_warp)
+//   work warps       meanwhile: suffix products, the product of the OTHER warps' totals, and from those
+//                    E = product of every other element of the block                                  | barrier
+//   work threads     z^-1 = E * inverse: one product after the inverse is known.
+// sh: (FUSED_MAXW + 1) * N words of shared memory.
 #define FUSED_MAXW 16
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 template <class FT>
-__device__ __forceinline__ void block_invert(typename FT::el& zinv, typename FT::el z, u32& zero, u32* sh, int inv_warp) {
+__device__ __forceinline__ void block_invert(typename FT::el& zinv, typename FT::el z, u32& zero, u32* sh) {
     typedef typename FT::el fe;
     constexpr int N = FT::N;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nww = (int)(blockDim.x >> 5) - 1;
+    const bool inv_role = warp >= nww;
     u32* sh_tot = sh;
-    u32* sh_c = sh + FUSED_MAXW * N;
+    u32* sh_inv = sh + FUSED_MAXW * N;
     fe one;
     FT::set_one(one);
     zero = FT::is_zero(z);
     FT::select(z, zero, one, z);
-    fe P = z, S = z, o, m;
-    fe o2, m2;
+    fe P = z, o, m;
+    if (!inv_role) {
 #pragma unroll 1
-    for (int d = 1; d < 32; d <<= 1) {   // the two scans are independent: their products run interleaved (mul2)
-        fe_shfl_up<FT>(o, P, d);
-        fe_shfl_down<FT>(o2, S, d);
-        FT::mul2(m, P, o, m2, S, o2);
-        if (lane >= d) P = m;
-        if (lane + d < 32) S = m2;
-    }
-    if (lane == 31) {
+        for (int d = 1; d < 32; d <<= 1) {
+            fe_shfl_up<FT>(o, P, d);
+            FT::mul(m, P, o);
+            if (lane >= d) P = m;
+        }
+        if (lane == 31) {
 #pragma unroll
-        for (int k = 0; k < N; k++) sh_tot[k * FUSED_MAXW + warp] = P.v[k];
+            for (int k = 0; k < N; k++) sh_tot[k * FUSED_MAXW + warp] = P.v[k];
+        }
     }
     __syncthreads();
-    if (warp == inv_warp) {
-        fe t = one;
-        if (lane < nw) {
+    // both halves of a warp load the same 16 slots, so four butterfly levels leave the product in every lane
+    fe t = one, E = one;
+    const int slot = lane & 15;
+    if (slot < nww && (inv_role || slot != warp)) {
 #pragma unroll
-            for (int k = 0; k < N; k++) t.v[k] = sh_tot[k * FUSED_MAXW + lane];
-        }
-        fe WP = t, WS = t;
+        for (int k = 0; k < N; k++) t.v[k] = sh_tot[k * FUSED_MAXW + slot];
+    }
+    if (inv_role) {
 #pragma unroll 1
-        for (int d = 1; d < FUSED_MAXW; d <<= 1) {
-            fe_shfl_up<FT>(o, WP, d);
-            fe_shfl_down<FT>(o2, WS, d);
-            FT::mul2(m, WP, o, m2, WS, o2);
-            if (lane >= d) WP = m;
-            if (lane + d < 32) WS = m2;
+        for (int d = 1; d < 16; d <<= 1) {
+            fe_shfl_xor<FT>(o, t, d);
+            FT::mul(t, t, o);
         }
-        fe total, tinv, exP, exS;
-        fe_shfl_idx<FT>(total, WP, FUSED_MAXW - 1);   // lanes >= nw hold 1
-        FT::invert(tinv, total);                       // same value in every lane: no divergence
-        fe_shfl_up<FT>(exP, WP, 1);
-        fe_shfl_down<FT>(exS, WS, 1);
+        FT::invert_warp(m, t);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < N; k++) sh_inv[k] = m.v[k];
+        }
+    } else {
+        fe S = z, exP, exS;
+#pragma unroll 1
+        for (int d = 1; d < 32; d <<= 1) {
+            fe_shfl_down<FT>(o, S, d);
+            FT::mul(m, S, o);
+            if (lane + d < 32) S = m;
+        }
+#pragma unroll 1
+        for (int d = 1; d < 16; d <<= 1) {   // product of the other warps' totals
+            fe_shfl_xor<FT>(o, t, d);
+            FT::mul(t, t, o);
+        }
+        fe_shfl_up<FT>(exP, P, 1);
+        fe_shfl_down<FT>(exS, S, 1);
         if (lane == 0) exP = one;
-        // lanes >= FUSED_MAXW were scanned with wrapped partners: only lanes < nw <= FUSED_MAXW are read,
-        // and for those lane + d < 32 always held, so WS[lane] = t[lane] * ... * t[lane + 15] ⊇ every warp total
+        if (lane == 31) exS = one;
         FT::mul(m, exP, exS);
-        FT::mul(m, m, tinv);
-        if (lane < nw) {
-#pragma unroll
-            for (int k = 0; k < N; k++) sh_c[k * FUSED_MAXW + lane] = m.v[k];
-        }
+        FT::mul(E, m, t);
     }
     __syncthreads();
-    fe c, exP, exS;
+    fe tinv;
 #pragma unroll
-    for (int k = 0; k < N; k++) c.v[k] = sh_c[k * FUSED_MAXW + warp];
-    fe_shfl_up<FT>(exP, P, 1);
-    fe_shfl_down<FT>(exS, S, 1);
-    if (lane == 0) exP = one;
-    if (lane == 31) exS = one;
-    FT::mul(m, exP, exS);
-    FT::mul(zinv, m, c);
+    for (int k = 0; k < N; k++) tinv.v[k] = sh_inv[k];
+    FT::mul(zinv, E, tinv);
     __syncthreads();   // sh is reused by the next tile
 }
 
@@ -160,17 +174,20 @@ struct FusedEdMontU {       // x25519_base: u = (Z + Y) / (Z - Y), 0 when Z = Y 
     }
 };
 
-// One tile = blockDim.x / LANES scalars; a block walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...
+// One tile = (blockDim.x - 32) / LANES scalars (the last warp is the inversion warp of block_invert); a block
+// walks the tiles blockIdx.x, blockIdx.x + gridDim.x, ...
 template <int LANES, bool CLAMP, class FIN>
 __device__ __forceinline__ void ed25519_mul_base_fused_block(size_t n, const u32* scalars, const u32* table, int W, int nwin,
-                                                             int stride, FIN fin, unsigned long long* status, u32* sh) {
+                                                             int stride, FIN fin, unsigned long long* status, u32* sh,
+                                                             unsigned long long* trace) {
     const int tid = threadIdx.x;
+    if (trace && tid == 0) trace[(size_t)blockIdx.x * 4 + 0] = globaltimer_ns();
+    const int work = (int)blockDim.x - 32;
     const int l = tid % LANES;
-    const size_t per_tile = blockDim.x / LANES;
-    const int nwarps = blockDim.x >> 5;
+    const size_t per_tile = work / LANES;
     for (size_t tile = blockIdx.x; tile * per_tile < n; tile += gridDim.x) {
         const size_t idx = tile * per_tile + tid / LANES;
-        const bool live = idx < n;
+        const bool live = tid < work && idx < n;
         ge_p3 acc;
         if (live) {
             u32 k[9];
@@ -179,22 +196,27 @@ __device__ __forceinline__ void ed25519_mul_base_fused_block(size_t n, const u32
         } else {
             ge_identity(acc);
         }
+        if (tid < work) {
 #pragma unroll 1
-        for (int d = 1; d < LANES; d <<= 1) {   // butterfly: afterwards every lane of the group holds the sum
-            ge_p3 o;
-            fe_shfl_xor<F25519>(o.X, acc.X, d);
-            fe_shfl_xor<F25519>(o.Y, acc.Y, d);
-            fe_shfl_xor<F25519>(o.Z, acc.Z, d);
-            fe_shfl_xor<F25519>(o.T, acc.T, d);
-            ge_add_p3<true>(acc, acc, o);
+            for (int d = 1; d < LANES; d <<= 1) {   // butterfly: afterwards every lane of the group holds the sum
+                ge_p3 o;
+                fe_shfl_xor<F25519>(o.X, acc.X, d);
+                fe_shfl_xor<F25519>(o.Y, acc.Y, d);
+                fe_shfl_xor<F25519>(o.Z, acc.Z, d);
+                fe_shfl_xor<F25519>(o.T, acc.T, d);
+                ge_add_p3<true>(acc, acc, o);
+            }
         }
         fe25519 den, dinv;
         F::set_one(den);
         if (live && l == 0) fin.den(den, acc);
         u32 zero;
-        block_invert<F25519>(dinv, den, zero, sh, (int)(blockIdx.x % (unsigned)nwarps));
+        if (trace && tid == 0) trace[(size_t)blockIdx.x * 4 + 1] = globaltimer_ns();
+        block_invert<F25519>(dinv, den, zero, sh);
+        if (trace && tid == 0) trace[(size_t)blockIdx.x * 4 + 2] = globaltimer_ns();
         if (live && l == 0) fin(idx, acc, dinv, zero);
     }
+    if (trace && tid == 0) trace[(size_t)blockIdx.x * 4 + 3] = globaltimer_ns();
 }
 
 }  // namespace ecb

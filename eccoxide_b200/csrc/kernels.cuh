@@ -193,47 +193,6 @@ ECB_DEV void ed25519_comb_partial(ge_p3& acc, const u32* k, const u32* table, in
         else ge_madd_rt(acc, acc, e, want_t || (i + step < nwin));
     }
 }
-// The same sum with the table entry of the NEXT window requested before the current addition starts
-// (software pipelining, 24 more live registers): the small-batch kernel runs 3-4 warps per scheduler, too
-// few to hide ten dependent DRAM + TLB misses per scalar behind other warps' arithmetic.
-ECB_DEV void ed25519_comb_load(ge_niels& e, u32 d, const u32* table, u32 half, int stride, int i) {
-    ge_niels_identity(e);
-    if (d != 0) {
-        const u32* src = table + ((size_t)i * half + (d - 1)) * (size_t)stride;
-        ld_words<8>(e.yp.v, src);
-        ld_words<8>(e.ym.v, src + 8);
-        ld_words<8>(e.t2d.v, src + 16);
-    }
-}
-ECB_DEV void ed25519_comb_partial_pipelined(ge_p3& acc, const u32* k, const u32* table, int W, int nwin, int stride, int first,
-                                            int step, bool want_t) {
-    const u32 half = 1u << (W - 1);
-    ge_identity(acc);
-    u32 v[8];
-    booth_reg_init<8>(v, k);
-    for (int j = 0; j < first; j++) booth_reg_shift<8>(v, W);
-    if (first >= nwin) return;
-    u32 neg, neg_next = 0;
-    u32 d = booth_from_view(v[0], W, neg);
-    for (int j = 0; j < step; j++) booth_reg_shift<8>(v, W);
-    ge_niels e, e_next;
-    ed25519_comb_load(e, d, table, half, stride, first);
-    for (int i = first; i < nwin; i += step) {
-        const bool more = i + step < nwin;
-        if (more) {
-            u32 dn = booth_from_view(v[0], W, neg_next);
-            for (int j = 0; j < step; j++) booth_reg_shift<8>(v, W);
-            ed25519_comb_load(e_next, dn, table, half, stride, i + step);
-        }
-        ge_niels_cneg(e, neg);
-        if (i == first) ge_from_niels(acc, e);
-        else ge_madd_rt(acc, acc, e, want_t || more);
-        if (more) {
-            e = e_next;
-            neg = neg_next;
-        }
-    }
-}
 template <bool CLAMP>
 ECB_DEV void ed25519_mul_base_body(size_t idx, size_t n, const u32* scalars, const u32* table, int W, int nwin, int stride,
                                    u32* planes, unsigned long long* status) {

@@ -90,6 +90,7 @@ ECB_DEV s32 sg_divsteps30_var(s32 zeta, u32 f0, u32 g0, s32& tu, s32& tv, s32& t
     return zeta;
 }
 
+
 // NW 32-bit words (little-endian, value < 2^(32 NW)) <-> NL signed 30-bit limbs (30 NL >= 32 NW + 2)
 template <int NW, int NL>
 ECB_DEV void sg_from_words(s32* l, const u32* w) {
@@ -203,5 +204,94 @@ ECB_DEV void sg_modinv(u32* r, const u32* a, const u32* p) {
     }
     sg_to_words<NW, NL>(r, d);
 }
+
+#ifndef ECB_HOSTSIM
+// ---------------------------------------------------------------------------------------------------
+// The same inverse computed by ONE WARP for ONE element (every lane passes the same a and receives the
+// same result).  The batch-inversion kernels run a single inversion per block while every other warp
+// waits, so its latency — not its instruction count — is what a small batch pays.  In sg_modinv one
+// thread spends about half of each batch of 30 divsteps in four serial NL-limb carry chains.  Here
+//   lanes 0 .. NL-1        hold limb j of (f, g),
+//   lanes 16 .. 16+NL-1    hold limb j of (d, e)          (NL <= 16),
+// every lane derives the transition matrix from the broadcast low limbs (identical work, no divergence),
+// multiplies its own limb pair, and the carries move ONE lane per batch: limbs stay signed and only
+// partially normalised (in [-8, 2^30 + 8]; the low limb is exact mod 2^30, which is all the divsteps
+// read).  The sign of d, e is then read from the top limb alone; a wrong guess within 2^-40 of zero
+// loosens the (-2p, p) bound by one p, which the final reduction absorbs.  Ranges and results are
+// checked lane for lane in tools/models/safegcd_warp_model.py.
+// ---------------------------------------------------------------------------------------------------
+template <int NW, int NL, int MAXB>
+__device__ __forceinline__ void sg_modinv_warp(u32* r, const u32* a, const u32* p) {
+    static_assert(NL <= 16, "one limb per lane: NL <= 16");
+    const unsigned FULL = 0xffffffffu;
+    const int lane = (int)(threadIdx.x & 31u), j = lane & 15;
+    const bool de = lane >= 16, live = j < NL, top = j == NL - 1;
+    const s32 M30 = 0x3fffffff;
+    s32 ml[NL], al[NL];
+    sg_from_words<NW, NL>(ml, p);
+    sg_from_words<NW, NL>(al, a);
+    s32 mj = 0, x = 0, y = 0;   // this lane's limb of the modulus, of f | d, of g | e
+    ECB_UNROLL
+    for (int i = 0; i < NL; i++) {
+        if (j == i) { mj = ml[i]; x = de ? 0 : ml[i]; y = de ? (i == 0 ? 1 : 0) : al[i]; }
+    }
+    if (!de) mj = 0;            // the multiple of p only enters (d, e)
+    u32 pinv = (u32)ml[0];
+    ECB_UNROLL
+    for (int i = 0; i < 5; i++) pinv *= 2u - (u32)ml[0] * pinv;
+    pinv &= 0x3fffffffu;
+    s32 zeta = -1;
+    ECB_NOUNROLL
+    for (int b = 0; b < MAXB; b++) {
+        const u32 f0 = (u32)__shfl_sync(FULL, x, 0), g0 = (u32)__shfl_sync(FULL, y, 0);
+        const s32 d0 = __shfl_sync(FULL, x, 16), e0 = __shfl_sync(FULL, y, 16);
+        const s32 sd = __shfl_sync(FULL, x, 16 + NL - 1) >> 31, se = __shfl_sync(FULL, y, 16 + NL - 1) >> 31;
+        s32 u, v, q, rr;
+        zeta = sg_divsteps30_var(zeta, f0, g0, u, v, q, rr);
+        s32 md = (u & sd) + (v & se), me = (q & sd) + (rr & se);
+        const u32 cd = (u32)u * (u32)d0 + (u32)v * (u32)e0, ce = (u32)q * (u32)d0 + (u32)rr * (u32)e0;
+        md -= (s32)((pinv * cd + (u32)md) & (u32)M30);
+        me -= (s32)((pinv * ce + (u32)me) & (u32)M30);
+        const s64 tx = (s64)u * x + (s64)v * y + (s64)mj * md;
+        const s64 ty = (s64)q * x + (s64)rr * y + (s64)mj * me;
+        // divide by 2^30: limb j of the quotient = high part of product j + low 30 bits of product j + 1
+        s32 lox = __shfl_down_sync(FULL, (s32)tx & M30, 1), loy = __shfl_down_sync(FULL, (s32)ty & M30, 1);
+        if (top || !live) { lox = 0; loy = 0; }
+        const s64 nx = (tx >> 30) + lox, ny = (ty >> 30) + loy;
+        s32 cx = top ? 0 : (s32)(nx >> 30), cy = top ? 0 : (s32)(ny >> 30);
+        x = top ? (s32)nx : ((s32)nx & M30);
+        y = top ? (s32)ny : ((s32)ny & M30);
+        cx = __shfl_up_sync(FULL, cx, 1);
+        cy = __shfl_up_sync(FULL, cy, 1);
+        if (j > 0 && live) { x += cx; y += cy; }
+        if (!live) { x = 0; y = 0; }
+        if (__ballot_sync(FULL, !de && y != 0) == 0u) break;   // every limb of g is zero: g = 0
+    }
+    // f = +-1 (its low limb is exact: 1 or 2^30 - 1); d = +-a^-1 somewhere in (-3p, 2p), limbs loose
+    const s32 fneg = ((u32)__shfl_sync(FULL, x, 0) == 1u) ? 0 : -1;
+    s32 d[NL];
+    ECB_UNROLL
+    for (int i = 0; i < NL; i++) d[i] = __shfl_sync(FULL, x, 16 + i);
+    ECB_UNROLL
+    for (int i = 0; i < NL; i++) d[i] = (d[i] ^ fneg) - fneg;
+    ECB_UNROLL
+    for (int rep = 0; rep < 6; rep++) {
+        // rep 0: carry only; rep 1-3: add p while negative; rep 4-5: subtract p while >= p (tested as d - p >= 0)
+        s32 t[NL], c = 0;
+        const s32 neg = d[NL - 1] >> 31;
+        ECB_UNROLL
+        for (int i = 0; i < NL; i++) {
+            s32 w = d[i] + c;
+            if (rep >= 1 && rep <= 3) w += ml[i] & neg;
+            if (rep >= 4) w -= ml[i];
+            if (i < NL - 1) { t[i] = w & M30; c = w >> 30; } else t[i] = w;
+        }
+        const s32 keep = (rep >= 4) ? ~(t[NL - 1] >> 31) : -1;   // a subtraction that went negative is dropped
+        ECB_UNROLL
+        for (int i = 0; i < NL; i++) d[i] = (t[i] & keep) | (d[i] & ~keep);
+    }
+    sg_to_words<NW, NL>(r, d);
+}
+#endif
 
 }  // namespace ecb

@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(ECB_TPB) k_batch_inv(size_t T, size_t n, const
         }
         fe total, tinv, exP, exS;
         fe_shfl<FT>(total, P, 31);
-        FT::invert(tinv, total);                   // same value in every lane: no divergence
+        FT::invert_warp(tinv, total);              // the 32 lanes compute ONE inverse together (modinv.cuh)
         fe_shfl<FT>(exP, P, lane > 0 ? lane - 1 : 0);
         fe_shfl<FT>(exS, S, lane < 31 ? lane + 1 : 31);
         if (lane == 0) exP = one;

@@ -9,15 +9,17 @@ static __global__ void __launch_bounds__(ECB_TPB, 5) k_ed25519_mul_base(size_t n
     if (idx < n) ed25519_mul_base_body<false>(idx, n, scalars, table, W, nwin, stride, planes, status);
 }
 // small-batch form (fused.cuh): LANES lanes per scalar, affine conversion in the same launch.
-// <FUSED_WIDE_T, 1>: one block of up to 448 threads per SM (65536 / 448 = 146 registers per thread: room for the
-// software-pipelined table loads), the whole batch in one wave — 148 x 448 = 66304 >= 2^16 scalars, BASELINE
-// configs[0]; <128, 4>: the same body with the large-batch launch shape (option ed25519_fused = 2, for measurement).
-#define FUSED_WIDE_T 448
+// <FUSED_WIDE_T, 1>: one block per SM of up to 15 work warps + the inversion warp (512 threads, 128 registers:
+// the register file is split over four schedulers, so 14 or 15 warps get no more registers than 16), the whole
+// batch in one wave — 148 x 480 = 71040 >= 2^16 scalars, BASELINE configs[0]; <160, 3>: the same body with a
+// large-batch launch shape (option ed25519_fused = 2, for measurement).
+#define FUSED_WIDE_T 512
+#define FUSED_WORK_T (FUSED_WIDE_T - 32)
 template <int LANES, bool CLAMP, class FIN, int MAXT, int MINB>
 static __global__ void __launch_bounds__(MAXT, MINB) k_ed25519_mul_base_fused(size_t n, const u32* scalars, const u32* table, int W, int nwin,
                                                                       int stride, FIN fin, unsigned long long* status,
                                                                       unsigned long long* trace) {
-    __shared__ u32 sh[2 * FUSED_MAXW * 8];
+    __shared__ u32 sh[(FUSED_MAXW + 1) * 8];
     ed25519_mul_base_fused_block<LANES, CLAMP, FIN>(n, scalars, table, W, nwin, stride, fin, status, sh, trace);
 }
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_window_bases(int nwin, int W, u32* bases) {
@@ -129,9 +131,10 @@ int dev_ed25519_table(ecb_ctx* ctx, DevCtx& d) {
 }
 
 // Launch shape of the fused small-batch kernel: LANES lanes per scalar and a block size such that the
-// whole batch is one wave of one block (<= FUSED_WIDE_T threads) per SM.  false: the batch is too large for it.
+// whole batch is one wave of one block (<= FUSED_WORK_T work threads) per SM.  tpb counts the work threads; the
+// launch adds the inversion warp.  false: the batch is too large for it.
 static bool fused_shape(const DevCtx& d, size_t n, long force_lanes, int& lanes, int& tpb, unsigned& grid) {
-    const size_t cap = (size_t)d.sm_count * FUSED_WIDE_T;
+    const size_t cap = (size_t)d.sm_count * FUSED_WORK_T;
     if (force_lanes) {
         lanes = (int)force_lanes;
     } else {   // measured (profiles/r02_tune_ed25519.jsonl): extra lanes pay while they add warps to idle schedulers, i.e. up to ~4 warps per SM
@@ -163,14 +166,15 @@ static int launch_fused(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, FIN f
     }
     prof_mark(ctx, d, s, 0);
     if (fits) {
+        const int T = tpb + 32;   // + the inversion warp
         switch (lanes) {
-            case 1: k_ed25519_mul_base_fused<1, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
-            case 2: k_ed25519_mul_base_fused<2, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
-            case 4: k_ed25519_mul_base_fused<4, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
-            default: k_ed25519_mul_base_fused<8, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, tpb, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
+            case 1: k_ed25519_mul_base_fused<1, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, T, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
+            case 2: k_ed25519_mul_base_fused<2, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, T, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
+            case 4: k_ed25519_mul_base_fused<4, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, T, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
+            default: k_ed25519_mul_base_fused<8, CLAMP, FIN, FUSED_WIDE_T, 1><<<grid, T, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace); break;
         }
     } else {
-        k_ed25519_mul_base_fused<1, CLAMP, FIN, ECB_TPB, 4><<<grid_for(n), ECB_TPB, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace);
+        k_ed25519_mul_base_fused<1, CLAMP, FIN, ECB_TPB + 32, 3><<<grid_for(n), ECB_TPB + 32, 0, s>>>(n, d_k, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, fin, status, trace);
     }
     ctx->launches++;
     CU(cudaGetLastError());

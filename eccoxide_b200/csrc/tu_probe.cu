@@ -69,11 +69,12 @@ int dev_fieldmul_probe(ecb_ctx* ctx, DevCtx& d, int num, int den, int blocks_per
 // One block per SM; lane 0 of warp 0 reports clock64() cycles per operation of a dependent chain
 // (what a latency-bound small batch pays), plus the SM clock it ran at (clock64 vs %globaltimer).
 //   0: F25519::mul      1: F25519::sqr      2: F25519::invert (safegcd)      3: F25519::invert_fermat
-//   4: block_invert<F25519> with the launch's block size (whole scan + one inversion + peel)
+//   4: block_invert<F25519> with the launch's block size + the inversion warp (threads <= 480)
 //   5: fe_shfl_up round trip (8 shuffles)                6: ge_madd_rt     7: ge_add_p3     8: mul2 (two interleaved products)
+//   9: F25519::invert_warp (one inversion by the 32 lanes of a warp; every warp of the block runs its own)
 template <int V>
 __global__ void __launch_bounds__(512, 1) k_latency_probe(int reps, double* out_cycles, double* out_mhz, u32* sink) {
-    __shared__ u32 sh[2 * FUSED_MAXW * 8];
+    __shared__ u32 sh[(FUSED_MAXW + 1) * 8];
     fe25519 x, y;
 #pragma unroll
     for (int i = 0; i < 8; i++) { x.v[i] = 0x9e3779b9u * (threadIdx.x + 1 + i) + blockIdx.x; y.v[i] = 0x85ebca6bu * (threadIdx.x + 3 + i) ^ 0x1234567u; }
@@ -91,10 +92,11 @@ __global__ void __launch_bounds__(512, 1) k_latency_probe(int reps, double* out_
         else if (V == 1) F::sqr(x, x);
         else if (V == 2) { F::invert(x, x); x.v[0] ^= 5u; }
         else if (V == 3) { F::invert_fermat(x, x); x.v[0] ^= 5u; }
-        else if (V == 4) { u32 z; fe25519 o; block_invert<F25519>(o, x, z, sh, 0); x = o; x.v[0] ^= 5u; }
+        else if (V == 4) { u32 z; fe25519 o; block_invert<F25519>(o, x, z, sh); x = o; x.v[0] ^= 5u; }
         else if (V == 5) { fe25519 o; fe_shfl_up<F25519>(o, x, 1); x = o; x.v[0] += 1u; }
         else if (V == 6) ge_madd_rt(P, P, e, true);
         else if (V == 8) F::mul2(x, x, y, P.X, P.X, y);
+        else if (V == 9) { fe25519 o; fe_shfl_idx<F25519>(o, x, 0); F::invert_warp(x, o); x.v[0] ^= 5u; }
         else ge_add_p3<true>(P, P, P);
     }
     long long t1 = clock64();
@@ -109,7 +111,7 @@ __global__ void __launch_bounds__(512, 1) k_latency_probe(int reps, double* out_
     }
 }
 int dev_latency_probe(ecb_ctx* ctx, DevCtx& d, int variant, int threads, int reps, double* cycles, double* mhz) {
-    if (variant < 0 || variant > 8 || reps < 1 || threads < 32 || threads > 512 || threads % 32) return ECB_ERR_INVALID_ARG;
+    if (variant < 0 || variant > 9 || reps < 1 || threads < 32 || threads > 512 || threads % 32) return ECB_ERR_INVALID_ARG;
     unsigned blocks = (unsigned)d.sm_count;
     TRY(ensure(ctx, d.cur->aux, (size_t)blocks * 512 * sizeof(u32) + 2 * blocks * sizeof(double)));
     double* dc = (double*)d.cur->aux.p;
@@ -121,11 +123,12 @@ int dev_latency_probe(ecb_ctx* ctx, DevCtx& d, int variant, int threads, int rep
             case 1: k_latency_probe<1><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
             case 2: k_latency_probe<2><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
             case 3: k_latency_probe<3><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
-            case 4: k_latency_probe<4><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 4: k_latency_probe<4><<<blocks, (threads <= 480 ? threads : 480) + 32, 0, d.stream>>>(reps, dc, dm, sink); break;
             case 5: k_latency_probe<5><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
             case 6: k_latency_probe<6><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
             case 7: k_latency_probe<7><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
-            default: k_latency_probe<8><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            case 8: k_latency_probe<8><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
+            default: k_latency_probe<9><<<blocks, threads, 0, d.stream>>>(reps, dc, dm, sink); break;
         }
         ctx->launches++;
         CU(cudaGetLastError());

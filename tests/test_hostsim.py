@@ -516,3 +516,32 @@ def test_safegcd_inversion_25519_and_448(hs):
     for a in [1, 2, Q - 1, Q, Q + 1, 2**448 - 1, 2**224, 2**447] + [_structured(g, 14) for _ in range(100)] + [int.from_bytes(g.bytes(56), "little") for _ in range(100)]:
         k.hs_fe448(6, p(words(a, 14)), p(words(0, 14)), p(r14))
         assert val(r14) % Q == (pow(a % Q, -1, Q) if a % Q else 0), hex(a)
+
+
+def test_divsteps_variants_agree(hs):
+    """The two forms of 30 divsteps (modinv.cuh: one step at a time, and zero runs shifted out by ctz with up to four
+    bits cancelled per trip) give the same transition matrix and the same zeta — on random words and along the
+    trajectories of real inversions, where zeta hovers around zero and nearly every odd step swaps."""
+    f, _ = hs
+    g = rng(77)
+    t = [np.zeros(4, dtype=np.int32) for _ in range(2)]
+    cases = []
+    for _ in range(3000):
+        z = int(g.integers(-40, 40))
+        cases.append((z, int(g.integers(0, 1 << 30)) | 1, int(g.integers(0, 1 << 30))))
+    for z in (-31, -30, -2, -1, 0, 1, 29, 30, 31):
+        for g0 in (0, 1, 2, 4, 8, 1 << 29, (1 << 30) - 1, (1 << 30) - 2):
+            cases.append((z, (1 << 30) - 19, g0))
+    P = R.P25519
+    for _ in range(40):
+        a, fv, zeta = int.from_bytes(g.bytes(32), "little") % P, P, -1
+        while a:
+            f0, g0 = fv & 0x3FFFFFFF, a & 0x3FFFFFFF
+            cases.append((zeta, f0, g0))
+            zeta = f.hs_divsteps30(0, zeta, f0, g0, p(t[0]))
+            u, v, q, r = (int(x) for x in t[0])
+            fv, a = (u * fv + v * a) >> 30, (q * fv + r * a) >> 30
+    for z, f0, g0 in cases:
+        zs = [f.hs_divsteps30(k, z, f0, g0, p(t[k])) for k in range(2)]
+        assert zs[0] == zs[1], (z, f0, g0)
+        assert np.array_equal(t[0], t[1]), (z, f0, g0)

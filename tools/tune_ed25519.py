@@ -51,9 +51,9 @@ def main():
                 out = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
                 variants = [("split", 0, 0)]
                 for lanes in (1, 2, 4, 8):
-                    if n * lanes <= 148 * 512:
+                    if n * lanes <= 148 * 480:
                         variants.append(("fused_l%d" % lanes, 1, lanes))
-                if n > 148 * 512:
+                if n > 148 * 480:
                     variants.append(("fused_128x4", 2, 0))
                 for label, fused, lanes in variants:
                     ctx.set_option("ed25519_fused", fused)
