@@ -4,14 +4,21 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One JSON line on stdout (rank 0).  A "step" is one pass of the hot path over one batch:
+One JSON line on stdout (rank 0).  The headline workload is BASELINE.json configs[0] exactly — Ed25519
+Point::mul_base on batches of 2^16 scalars; the 2^20 batch, P-256 Point::mul and the other configs are
+measured the same way and reported under "workloads".  A "step" is `batches_per_step` back-to-back passes
+of the hot path over distinct batches (a single 2^16 pass is ~90 us; the inner repetition makes the timed
+region of K steps last >= 0.5 s):
   value    device-resident inputs (HBM), CUDA-event time of K steps on the launching stream, max over ranks
   e2e      the same op through the host C-ABI entry point with pinned HOST buffers (H2D + kernels + D2H
            inside the timed region)
-  roofline IMAD-pipe bound (BASELINE.json north star: not HBM, not tensor): algorithmic MAC32 per op
-           (fixed across rounds) x ops / device time, over the integer multiply-add
-           peak measured live by the probe kernel; per-kernel times from CUDA events recorded by the
-           library on the launching stream
+  roofline IMAD-pipe bound (BASELINE.json north star: not HBM, not tensor).  Three fractions per workload:
+           frac          algorithmic MAC32 per op of the REFERENCE's algorithm (fixed across
+                         rounds) x ops / device time / peak — comparable across rounds, can exceed 1
+           frac_executed MAC32 the kernels actually execute per op / kernel time / peak — a utilisation
+           hbm_frac      DRAM bytes per launch (ncu) / kernel time / MEASURED_PEAKS.json hbm_gbs
+           peak = integer multiply-add rate measured live by the probe kernel; kernel times from CUDA
+           events recorded by the library on the launching stream in a second pass of the same steps
   cpu_baseline  oracle/ecc_oracle.c (C restatement of the reference's algorithms — the reference is
            Rust and cannot be built here) on all host cores, bounded sample, rank 0 only
 Multi-GPU: every element is independent — each rank processes its own contiguous slice of the
@@ -59,6 +66,39 @@ WORK = {
     "p256_decompress": 254 * 36 + 13 * 64,
     "bls12_381_g1_from_compressed": 380 * 234 + 192 * 300 + (126 * 9 + 10 * 14) * 300,
 }
+# Field products the kernels EXECUTE per operation (M = product, S = square, in 32-bit-limb MAC32: 2^255-19
+# M 72 / S 44; P-256 M 64 / S 36; P-384 M 144 / S 78; BLS12-381 Fp M 288 / S 222; p448 M 196 / S 105), counted
+# from the kernels' formulas — the numerator of roofline.frac_executed.  The Ed25519 fixed-base count depends
+# on the comb in use (nwin windows) and on the kernel form, see executed_mac32().
+EXEC = {
+    "x25519": 255 * (5 * 72 + 4 * 44 + 8) + 5 * 72,                        # ladder step 5 M + 4 S + a24 product; batched inverse 3 M + 2 M
+    "p256_mul": 260 * (3 * 64 + 5 * 36) + 72 * (10 * 64 + 4 * 36) + 5 * 64,  # 65 windows x 4 doublings, 65 + 7 (table) Jacobian additions
+    "p256_ecdsa_verify": 260 * (3 * 64 + 5 * 36) + 72 * (10 * 64 + 4 * 36) + 11 * (7 * 64 + 4 * 36) + 14 * 64 + 5 * 136 + 5 * 64,
+    "p384_mul": 388 * (3 * 144 + 5 * 78) + 104 * (10 * 144 + 4 * 78) + 5 * 144,
+    "bls12_381_g1_mul": 256 * (2 * 288 + 5 * 222) + 71 * (10 * 288 + 4 * 222) + 5 * 288,
+    "x448": 448 * (5 * 196 + 4 * 105 + 14) + 5 * 196,
+    "ed25519_mul": 256 * (3 * 72 + 4 * 44) + 72 * 8 * 72 + 5 * 72,
+}
+ORDERS = {   # group orders: scalars are 64 uniform bytes reduced mod the order, as init_from_wide_bytes does
+    "ed25519": 2**252 + 27742317777372353535851937790883648493,
+    "p256r1": 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551,
+    "p384r1": 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973,
+    "bls12_381_g1": 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
+}
+
+
+def executed_mac32(name, ctx, n):
+    base = name.replace("_2p16", "")
+    if base in ("ed25519_mul_base", "x25519_base", "ed25519_keygen", "ed25519_sign"):
+        nwin = ctx.get_info("ed25519_comb_windows") or 11
+        comb = 1 + 7 * (nwin - 2) + 6              # first window: one product; last: no T
+        fused = n <= ctx.get_info("sm_count") * 480
+        # fused kernel: prefix + suffix scans (5 + 5), other-warp product (4), E (2), inverse (1), finisher (2);
+        # two-kernel form: Montgomery's trick 3 M + finisher 2 M
+        return (comb + (19 if fused else 5)) * 72
+    return EXEC.get(base)
+
+
 # name -> (log2 n per GPU, bytes in per op, bytes out per op, BASELINE.json config it belongs to)
 WORKLOADS = {
     "ed25519_mul_base": (20, 32, 64, "configs[0] op (Ed25519 Point::mul_base) at the 2^20 batch of configs[1..3]"),
@@ -80,8 +120,16 @@ WORKLOADS = {
     "p256_decompress": (20, 33, 65, "SURVEY 8 f.1: PointAffine::decompress (SEC1 point decompression) on p256r1"),
     "bls12_381_g1_from_compressed": (20, 48, 97, "SURVEY 8 f.1: BLS12-381 G1 from_compressed with the prime-order-subgroup check"),
 }
-HEADLINE = "ed25519_mul_base"
-EXTRA_DEFAULT = ["ed25519_mul_base_2p16", "x25519", "p256_mul", "p256_ecdsa_verify", "bls12_381_g1_mul"]
+HEADLINE = "ed25519_mul_base_2p16"
+EXTRA_DEFAULT = ["ed25519_mul_base", "p256_mul", "x25519", "p256_ecdsa_verify", "bls12_381_g1_mul"]
+# op name and curve for ecb_warm (the *_dev entry points never allocate)
+WARM = {"ed25519_mul_base": ("ed25519_mul_base", None), "ed25519_mul": ("ed25519_mul", None), "x25519": ("x25519", None),
+        "x25519_base": ("x25519_base", None), "x448": ("x448", None), "p256_mul": ("wei_mul", "p256r1"), "p384_mul": ("wei_mul", "p384r1"),
+        "bls12_381_g1_mul": ("wei_mul", "bls12_381_g1"), "ed25519_verify": ("ed25519_verify_prehashed", None),
+        "p256_mul_base": ("wei_mul_base", "p256r1"), "bls12_381_g1_mul_base": ("wei_mul_base", "bls12_381_g1"),
+        "p256_ecdsa_verify": ("ecdsa_verify_hashed", "p256r1"), "p256_ecdsa_sign": ("ecdsa_sign_hashed", "p256r1"),
+        "ed25519_keygen": ("ed25519_public_from_seed", None), "ed25519_sign": ("ed25519_sign", None),
+        "p256_decompress": ("wei_decompress", "p256r1"), "bls12_381_g1_from_compressed": ("bls12_381_g1_from_compressed", None)}
 
 
 def work_of(name):
@@ -89,12 +137,19 @@ def work_of(name):
 
 
 # ---- synthetic inputs (seeded) ----------------------------------------------------
+_CLEAR = {(32, 4): "ed25519", (32, 1): "p256r1", (48, 1): "p384r1", (32, 2): "bls12_381_g1"}
+
+
 def rand_scalars(g, n, nbytes, clear_top_bits, endian):
-    """Uniform scalars below 2^(8*nbytes - clear_top_bits) (< group order for every curve used)."""
-    a = g.integers(0, 256, size=(n, nbytes), dtype=np.uint8)
-    top = nbytes - 1 if endian == "little" else 0
-    a[:, top] &= 0xFF >> clear_top_bits
-    return a
+    """Canonical scalars as SURVEY §8d asks: 64 uniform bytes reduced mod the group order (the reference's
+    init_from_wide_bytes_le, field_macros.rs:314), stored in the curve's wire order.  (nbytes, clear_top_bits)
+    names the curve, as the callers did when this drew uniform values below a power of two."""
+    order = ORDERS[_CLEAR[(nbytes, clear_top_bits)]]
+    wide = g.integers(0, 256, size=(n, 64), dtype=np.uint8)
+    out = bytearray(n * nbytes)
+    for i in range(n):
+        out[i * nbytes:(i + 1) * nbytes] = (int.from_bytes(wide[i].tobytes(), "little") % order).to_bytes(nbytes, endian)
+    return np.frombuffer(bytes(out), dtype=np.uint8).reshape(n, nbytes).copy()
 
 
 def make_inputs(name, n, ctx, seed):
@@ -418,81 +473,113 @@ class ClockSampler:
 
 
 # ---- measurement ---------------------------------------------------------------------------------
-def measure_device(torch, ctx, name, n, steps, warmup, seed, dist=None, sampler=None, nbuf=None):
-    """Device-resident throughput of `name`: returns dict with ms_per_step (max over ranks), kernel split."""
+L2_BYTES = 126 << 20
+MIN_TIMED_S = 0.5
+
+
+def measure_device(torch, ctx, name, n, steps, warmup, seed, dist=None, min_s=MIN_TIMED_S, inner=None):
+    """Device-resident throughput of `name`.  One step = `inner` back-to-back passes over distinct batches
+    (inner chosen so that the K timed steps last >= min_s).  The timed region carries no profiling events; the
+    per-kernel split comes from a second pass of the same steps with the library's event marks."""
     ins_h = make_inputs(name, n, ctx, seed)
     in_bytes = sum(a.nbytes for a in ins_h)
-    # rotate over enough distinct input batches that consecutive steps never re-read an L2-resident batch
-    if nbuf is None:
-        nbuf = max(2, int(np.ceil(160e6 / max(in_bytes, 1))))
-        nbuf = min(nbuf, 8)
+    # rotate over enough distinct input batches to exceed the L2, so no step re-reads an L2-resident batch
+    nbuf = max(2, min(96, int(np.ceil(1.3 * L2_BYTES / max(in_bytes, 1)))))
     bufs = []
     for b in range(nbuf):
-        if b == 0:
-            hb = ins_h
-        else:  # same elements in a rotated order: distinct buffers, same validity
-            hb = [np.roll(a, b * 977, axis=0) for a in ins_h]
+        hb = ins_h if b == 0 else [np.roll(a, b * 977, axis=0) for a in ins_h]   # same elements, rotated: distinct buffers, same validity
         bufs.append([torch.from_numpy(a).cuda() for a in hb])
     base = name.replace("_2p16", "")
     outs = [torch.empty((n, w), dtype=torch.uint8, device="cuda") for w in OUT_SHAPES[base]]
     stream = torch.cuda.current_stream().cuda_stream
-    for i in range(warmup):
-        dev_launch(ctx, name, bufs[i % nbuf], outs, n, stream)
+    op, curve = WARM[base]
+    ctx.warm(op, n, curve)
+    k = 0
+    for _ in range(max(warmup, 3)):
+        dev_launch(ctx, name, bufs[k % nbuf], outs, n, stream)
+        k += 1
     torch.cuda.synchronize()
     rc, bad = ctx.dev_status(0)
     if rc != 0:
         raise RuntimeError("%s: invalid synthetic input at %s (rc %d)" % (name, bad, rc))
-    ctx.set_option("profile", 1)
-    l0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if inner is None:   # calibrate on a few passes
+        e0.record()
+        for _ in range(4):
+            dev_launch(ctx, name, bufs[k % nbuf], outs, n, stream)
+            k += 1
+        e1.record()
+        torch.cuda.synchronize()
+        per = e0.elapsed_time(e1) / 4 * 1e-3
+        inner = int(min(4096, max(1, np.ceil(1.1 * min_s / (steps * per)))))
+        if dist is not None:   # every rank must run the same step
+            t = torch.tensor([inner], dtype=torch.int64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            inner = int(t.item())
+    for _ in range(inner if inner > 1 else 0):   # one untimed full step
+        dev_launch(ctx, name, bufs[k % nbuf], outs, n, stream)
+        k += 1
+    l0 = ctx.launch_count()
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.time()
     e0.record()
-    for i in range(steps):
-        dev_launch(ctx, name, bufs[(warmup + i) % nbuf], outs, n, stream)
+    for _ in range(steps * inner):
+        dev_launch(ctx, name, bufs[k % nbuf], outs, n, stream)
+        k += 1
     e1.record()
     torch.cuda.synchronize()
     t1 = time.time()
+    last = (k - 1) % nbuf
+    got = [o[:PARITY_SAMPLE].cpu().numpy() for o in outs]   # result of the LAST timed pass, for the parity check
     if dist is not None:
         dist.barrier()
     ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count() - l0
+    # second pass, same steps, with the library's CUDA-event marks around its kernels (on the launching stream)
+    ctx.set_option("profile", 1)
+    pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    pcalls = min(steps * inner, 400)
+    pe0.record()
+    for _ in range(pcalls):
+        dev_launch(ctx, name, bufs[k % nbuf], outs, n, stream)
+        k += 1
+    pe1.record()
+    torch.cuda.synchronize()
     main_ms, fin_ms, calls = ctx.profile_collect(0)
     ctx.set_option("profile", 0)
-    launches = ctx.launch_count() - l0
+    prof_ms = pe0.elapsed_time(pe1) / pcalls
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    res = {"ms_per_step": ms / steps, "main_ms": main_ms / max(calls, 1), "fin_ms": fin_ms / max(calls, 1), "launches": launches,
-           "nbuf": nbuf, "in_bytes": in_bytes, "out_bytes": sum(int(o.numel()) for o in outs), "t0": t0, "t1": t1,
-           "ins_h": ins_h, "outs": outs}
-    return res
+    return {"ms_per_step": ms / steps, "ms_per_batch": ms / (steps * inner), "inner": inner, "timed_s": ms * 1e-3,
+            "main_ms": main_ms / max(calls, 1), "fin_ms": fin_ms / max(calls, 1), "ms_per_batch_profiled": prof_ms,
+            "launches": launches, "nbuf": nbuf, "in_bytes": in_bytes, "out_bytes": sum(int(o.numel()) for o in outs),
+            "t0": t0, "t1": t1, "ins_h": ins_h, "got": got, "last": last}
 
 
-def measure_e2e(torch, ctx, name, n, steps, warmup, ins_h, dist=None):
-    """Host-API throughput with pinned host buffers (the call a user of the C ABI makes)."""
-    pinned = []
-    for a in ins_h:
-        t = torch.from_numpy(a).pin_memory()
-        pinned.append(t.numpy())
+def measure_e2e(torch, ctx, name, n, steps, inner, ins_h, dist=None):
+    """Host-API throughput with pinned host buffers (the call a user of the C ABI makes): every pass copies
+    its inputs host -> device and its results device -> host inside the timed region."""
+    pinned = [torch.from_numpy(a).pin_memory().numpy() for a in ins_h]
     base = name.replace("_2p16", "")
     pouts = [torch.empty((n, w), dtype=torch.uint8).pin_memory().numpy() for w in OUT_SHAPES[base]]
-    for _ in range(max(1, min(warmup, 2))):
+    for _ in range(3):
         host_call(ctx, name, pinned, pouts)
     if dist is not None:
         dist.barrier()
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    for _ in range(steps):
+    for _ in range(steps * inner):
         out = host_call(ctx, name, pinned, pouts)
     dt = time.perf_counter() - t0
     if dist is not None:
         t = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dt = float(t.item())
-    return dt / steps, out
+    return dt / (steps * inner), out
 
 
 def pcie_bandwidth(torch, nbytes=64 << 20):
@@ -528,6 +615,9 @@ def pcie_bandwidth(torch, nbytes=64 << 20):
     return out
 
 
+PARITY_SAMPLE = 4096
+
+
 def cpu_baseline(name, ins_h, target_s, threads):
     """Time the C oracle (reference algorithms) on a bounded sample of the same inputs."""
     from oracle import coracle as C
@@ -541,15 +631,27 @@ def cpu_baseline(name, ins_h, target_s, threads):
     m = int(max(threads * 16, min(len(ins_h[0]), target_s / per * threads)))
     m -= m % threads
     sub = [a[:m] for a in ins_h]
+    oracle_call(C, name, [a[: max(threads * 16, m // 8)] for a in ins_h], threads)   # warm the threads and the tables
+    reps, dt = 0, 0.0
     t0 = time.perf_counter()
-    out = oracle_call(C, name, sub, threads)
-    dt = time.perf_counter() - t0
-    return {"value": m / dt, "unit": "scalar-mults/s", "cores": threads, "kind": "port",
-            "sample": "%d elements of the same batch, %.1f s, C restatement of the reference algorithm (oracle/ecc_oracle.c); reference is Rust, no toolchain here" % (m, dt)}, out, m
+    while dt < target_s * 0.8 and reps < 1000:   # a small batch (2^16) is repeated until the sample is ~10 s of CPU work
+        oracle_call(C, name, sub, threads)
+        reps += 1
+        dt = time.perf_counter() - t0
+    return {"value": m * reps / dt, "unit": "scalar-mults/s", "cores": threads, "kind": "port",
+            "sample": "%d elements of the same batch x %d passes, %.1f s, C restatement of the reference algorithm (oracle/ecc_oracle.c); reference is Rust, no toolchain here" % (m, reps, dt)}
+
+
+def config_of(name, world):
+    """The `config` object: identical in both arms (bench.py and bench.py --impl reference) for one workload."""
+    n = 1 << WORKLOADS[name][0]
+    return {"workload": name, "batch_per_gpu": n, "what": WORKLOADS[name][3],
+            "parallelism": "%d x contiguous batch slice, no collective" % world,
+            "inputs": "scalars = 64 uniform bytes mod the group order; seeded Philox; points = random multiples of the generator"}
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm (C port, all host threads) on bounded samples."""
+    """--impl reference: the reference's CPU algorithm (C port, all host threads) on the same workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -568,13 +670,14 @@ def run_reference_arm(args):
         def wei_mul_base(self, curve, k):
             return C.wei_mul_base(curve, k, threads)
 
-    # calibrate a per-step sample of ~2 s
+    # the whole batch when a step of it stays within ~10 s of CPU time, else a bounded sample of it
     n_small = 1 << 11
     ins = make_inputs(name, n_small, _NoCtx(), 0xECC00001)
     t0 = time.perf_counter()
     oracle_call(C, name, [a[:256] for a in ins], threads)
     rate = 256 / (time.perf_counter() - t0)
-    m = int(min(1 << logn, max(threads * 32, rate * 2.0)))
+    budget_s = 120.0 / max(args.steps + args.warmup / 8.0, 1)
+    m = int(min(1 << logn, max(threads * 32, rate * min(budget_s, 10.0))))
     m = 1 << int(np.floor(np.log2(m)))
     ins = make_inputs(name, max(m, 1 << 14) if m >= (1 << 14) else m, _NoCtx(), 0xECC00001)
     ins = [a[:m] for a in ins]
@@ -585,30 +688,98 @@ def run_reference_arm(args):
         oracle_call(C, name, ins, threads)
     dt = time.perf_counter() - t0
     v = m * args.steps / dt
+    whole = m == (1 << logn)
     line = {
         "impl": "reference", "metric": "scalar-mults/s", "value": v, "unit": "scalar-mults/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "u64 limbs (unsigned __int128 products)", "data": "synthetic",
-        "config": {"workload": name, "batch_per_step": m, "note": "bounded sample of the %s workload; reference (Rust) cannot be built in this image, C port of its algorithms" % name},
+        "dtype": "u32 limbs (32x32->64 integer multiply-add)", "data": "synthetic",
+        "config": config_of(name, int(os.environ.get("WORLD_SIZE", "1"))),
         "cpu_baseline": {"value": v, "unit": "scalar-mults/s", "cores": threads, "kind": "port",
-                         "sample": "%d elements per step x %d steps, all %d host threads" % (m, args.steps, threads)},
+                         "sample": "%s per step x %d steps, all %d host threads; C restatement of the reference's algorithm on u64 limbs with unsigned __int128 products (oracle/ecc_oracle.c) — the Rust reference cannot be built in this image" % (
+                             "the whole 2^%d batch" % logn if whole else "%d elements of the 2^%d batch" % (m, logn), args.steps, threads)},
         "e2e": {"value": v, "unit": "scalar-mults/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
+def load_json(path):
+    try:
+        return json.load(open(path))
+    except Exception:
+        return {}
+
+
+def run_workload(torch, ctx, name, steps, warmup, world, rank, dist, peak, probes, check=True, cpu=False, e2e_cap_s=6.0):
+    """Everything reported for one workload: device-resident value, e2e, the three roofline fractions, parity."""
+    n = 1 << WORKLOADS[name][0]
+    r = measure_device(torch, ctx, name, n, steps, warmup, 0xECC00001 + rank, dist)
+    ops_s = world * n / (r["ms_per_batch"] * 1e-3)
+    W, Wx = work_of(name), executed_mac32(name, ctx, n)
+    # e2e: the same number of passes, capped so that a slow host link does not stretch the run
+    e_inner = max(1, min(r["inner"], int(e2e_cap_s / max(steps * r["ms_per_batch"] * 2e-3, 1e-9))))
+    e_steps = steps if steps * e_inner * r["ms_per_batch"] * 2e-3 <= e2e_cap_s else max(3, int(e2e_cap_s / (r["ms_per_batch"] * 2e-3)))
+    e2e_s, e2e_out = measure_e2e(torch, ctx, name, n, e_steps, e_inner, r["ins_h"], dist)
+    if rank != 0:
+        return None
+    res = {"value": ops_s, "ms_per_step": r["ms_per_step"], "ms_per_batch": r["ms_per_batch"], "batches_per_step": r["inner"],
+           "timed_region_s": r["timed_s"], "steps": steps, "batch_per_gpu": n, "gpu_launches": int(r["launches"])}
+    parity = None
+    if check:
+        from oracle import coracle as C
+
+        C.build()
+        m = min(PARITY_SAMPLE, n)
+        ins_last = [np.roll(a, r["last"] * 977, axis=0) if r["last"] else a for a in r["ins_h"]]
+        exp = oracle_call(C, name, [a[:m] for a in ins_last], os.cpu_count() or 1)
+        parity = all(np.array_equal(np.asarray(g)[:m].reshape(m, -1), np.asarray(e).astype(np.uint8).reshape(m, -1)) for g, e in zip(r["got"], exp))
+        exp2 = oracle_call(C, name, [a[:m] for a in r["ins_h"]], os.cpu_count() or 1)
+        parity = parity and all(np.array_equal(np.asarray(g[:m]).astype(np.uint8).reshape(m, -1), np.asarray(e).astype(np.uint8).reshape(m, -1)) for g, e in zip(e2e_out, exp2))
+    res["parity_check"] = parity
+    res["parity_sample"] = "%d elements of the last timed device pass and of the last e2e pass, bit-exact vs the C oracle" % min(PARITY_SAMPLE, n) if check else None
+    static = load_json(os.path.join(ROOT, "profiles", "ncu_static.json")).get(name) or {}
+    peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
+    hbm_peak = peaks.get("hbm_gbs")
+    traffic = (static.get("dram_read_bytes") or 0) + (static.get("dram_write_bytes") or 0) or None
+    # the dominant kernel: the scalar-multiplication kernel (for the fused small-batch form it is the whole pass)
+    k_ms = r["main_ms"] if r["main_ms"] > 0 else r["ms_per_batch"]
+    achieved = n * W / (r["ms_per_batch"] * 1e-3) / 1e12
+    res["roofline"] = {
+        "bound": static.get("bound", "imad"), "achieved": achieved, "peak": peak, "unit": "T MAC32/s (32x32->64 multiply-accumulates)",
+        "frac": achieved / peak if peak else None,
+        "frac_executed": (n * Wx / ((r["main_ms"] + r["fin_ms"]) * 1e-3 if r["main_ms"] > 0 else r["ms_per_batch"] * 1e-3) / 1e12 / peak) if (peak and Wx) else None,
+        "hbm_frac": (traffic / (k_ms * 1e-3) / 1e9 / hbm_peak) if (traffic and hbm_peak) else None,
+        "traffic": traffic, "mac32_per_op": W, "mac32_executed_per_op": Wx,
+        "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json (burst copy bandwidth)" if hbm_peak else "absent",
+        "pipe_util_ncu": {"kernel": static.get("kernel"), "launch": static.get("launch"), "fmaheavy_pct": static.get("fmaheavy_pct"), "alu_pct": static.get("alu_pct"),
+                          "fp64_pct": static.get("fp64_pct"), "issue_pct": static.get("issue_pct"), "top_stall": static.get("top_stall"), "source": static.get("source")},
+        "kernels_ms": {"scalar_mult": r["main_ms"], "batch_inversion_encode": r["fin_ms"], "pass_with_event_marks": r["ms_per_batch_profiled"],
+                       "how": "CUDA events recorded by the library around its kernels on the launching stream, second pass of the same steps"},
+        "io_gbs": (r["in_bytes"] + r["out_bytes"]) / (r["ms_per_batch"] * 1e-3) / 1e9,
+        "note": "frac: the REFERENCE algorithm's MAC32 count (SURVEY 8d) x ops / time / peak — fixed across rounds, exceeds 1 when the kernels do less work than the reference (wider comb, mixed additions); frac_executed: MAC32 the kernels execute / kernel time / peak — a utilisation; hbm_frac: DRAM bytes per launch (ncu) / kernel time / measured HBM peak",
+        "peak_source": "live probe kernels on this GPU (T/s): %s; a MAC32 is two passes of the 32-bit multiplier" % json.dumps({k: (round(v, 3) if v else v) for k, v in probes.items()}),
+    }
+    res["e2e"] = {"value": world * n / e2e_s, "unit": "scalar-mults/s", "h2d_bytes_per_step": r["in_bytes"] * r["inner"], "d2h_bytes_per_step": r["out_bytes"] * r["inner"],
+                  "h2d_bytes_per_batch": r["in_bytes"], "d2h_bytes_per_batch": r["out_bytes"], "ms_per_batch": e2e_s * 1e3, "passes_timed": e_steps * e_inner,
+                  "path": "ecb_* host entry point, pinned host buffers, chunks pipelined over 4 stream slots"}
+    res["l2"] = "inputs rotate over %d distinct batches (%.0f MB, larger than the %d MB L2); the comb table reads are random over %s" % (
+        r["nbuf"], r["nbuf"] * r["in_bytes"] / 1e6, L2_BYTES >> 20, "GBs of HBM")
+    res["_r"] = r
+    if cpu:
+        res["cpu_baseline"] = cpu_baseline(name, r["ins_h"], 12.0, os.cpu_count() or 1)
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS))
     ap.add_argument("--extra", default=",".join(EXTRA_DEFAULT), help="comma list of further workloads reported under 'workloads' ('' = none)")
-    ap.add_argument("--extra-steps", type=int, default=4)
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--profile-run", action="store_true", help="1 warm-up + 1 step per workload, for ncu captures only (numbers are not bench values)")
+    ap.add_argument("--profile-run", action="store_true", help="minimal run of one workload for ncu captures only (numbers are not bench values)")
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--comb-w", type=int, default=None)
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (ecb_set_option)")
@@ -639,6 +810,13 @@ def main():
     for kv in args.opt:
         key, val = kv.split("=")
         ctx.set_option(key, int(val))
+    name = args.workload
+
+    if args.profile_run:   # two passes of one workload, nothing else: for ncu
+        n = 1 << WORKLOADS[name][0]
+        measure_device(torch, ctx, name, n, 1, 3, 0xECC00001, None, min_s=0.0, inner=1)
+        ctx.close()
+        return
 
     # IMAD peak, measured live: a 32x32->64 multiply-accumulate is two passes of the 32-bit multiplier
     # (IMAD.WIDE or IMAD.LO + IMAD.HI); take the best of the three ways of issuing it
@@ -646,89 +824,45 @@ def main():
     for v, nm in ((0, "imad_lo32"), (2, "imad_wide_carry_chain"), (3, "imad_hi32"), (1, "imad_wide"), (4, "dfma")):
         try:
             probes[nm] = ctx.imad_probe(v, 2048)[0] / 1e12
-        except Exception as e:  # pragma: no cover
+        except Exception:  # pragma: no cover
             probes[nm] = None
-    cand = [probes["imad_wide_carry_chain"] or 0, (probes["imad_lo32"] or 0) / 2, (probes["imad_hi32"] or 0) / 2]
-    peak = max(cand)
+    peak = max(probes["imad_wide_carry_chain"] or 0, (probes["imad_lo32"] or 0) / 2, (probes["imad_hi32"] or 0) / 2)
 
-    name = args.workload
-    n = 1 << WORKLOADS[name][0]
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
         time.sleep(0.3)
-    r = measure_device(torch, ctx, name, n, args.steps, args.warmup, 0xECC00001 + rank, dist)
-    clocks = sampler.summary(r["t0"], r["t1"]) if sampler else None
-    ops_s = world * n / (r["ms_per_step"] * 1e-3)
-    W = work_of(name)
-    e2e_s, e2e_out = measure_e2e(torch, ctx, name, n, 1 if args.profile_run else max(3, min(args.steps, 10)), args.warmup, r["ins_h"], dist)
-
+    head = run_workload(torch, ctx, name, args.steps, args.warmup, world, rank, dist, peak, probes, check=not args.no_check,
+                        cpu=(not args.no_cpu and world == 1))
     line = None
-    pcie = pcie_bandwidth(torch) if rank == 0 else None
-    if pcie:
-        # the host path moves in + out bytes over one link; with both directions busy the link's TOTAL is what counts
-        pcie["link_floor_ms_per_step"] = (r["in_bytes"] + r["out_bytes"]) / (pcie["duplex_1in_2out_gbs_total"] * 1e9) * 1e3
-        pcie["e2e_ms_per_step"] = e2e_s * 1e3
     if rank == 0:
-        # parity spot check of this very run (never in the timed region): device output vs the oracle
-        check = None
-        if not args.no_check:
-            from oracle import coracle as C
-
-            C.build()
-            m = 256
-            got = [o[:m].cpu().numpy() for o in r["outs"]]
-            # the device buffers hold the result of the LAST step: recompute that batch's inputs
-            last = (args.warmup + args.steps - 1) % r["nbuf"]
-            ins_last = [np.roll(a, last * 977, axis=0) if last else a for a in r["ins_h"]]
-            exp = oracle_call(C, name, [a[:m] for a in ins_last], os.cpu_count() or 1)
-            check = all(np.array_equal(np.asarray(g).reshape(m, -1), np.asarray(e).astype(np.uint8).reshape(m, -1)) for g, e in zip(got, exp))
-            exp2 = oracle_call(C, name, [a[:m] for a in r["ins_h"]], os.cpu_count() or 1)
-            check = check and all(np.array_equal(np.asarray(g[:m]).astype(np.uint8).reshape(m, -1), np.asarray(e).astype(np.uint8).reshape(m, -1)) for g, e in zip(e2e_out, exp2))
-        cpu = None
-        if not args.no_cpu and world == 1:  # CPU baseline: rank 0 at N = 1 only
-            cpu, _, _ = cpu_baseline(name, r["ins_h"], 12.0, os.cpu_count() or 1)
-        achieved = n * W / (r["ms_per_step"] * 1e-3) / 1e12
-        try:
-            static = json.load(open(os.path.join(ROOT, "profiles", "ncu_static.json"))).get(name) or {}
-        except Exception:
-            static = {}
-        traffic = (static.get("dram_read_bytes") or 0) + (static.get("dram_write_bytes") or 0) or None
+        r = head.pop("_r")
+        clocks = sampler.summary(r["t0"], r["t1"])
+        pcie = pcie_bandwidth(torch)
+        # the host path moves in + out bytes over one link; with both directions busy the link's TOTAL is what counts
+        pcie["link_floor_ms_per_batch"] = (r["in_bytes"] + r["out_bytes"]) / (pcie["duplex_1in_2out_gbs_total"] * 1e9) * 1e3
+        head["e2e"]["pcie"] = pcie
+        cfg = config_of(name, world)
         line = {
-            "metric": "scalar-mults/s", "value": ops_s, "unit": "scalar-mults/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "u32 limbs (32x32->64 integer multiply-add)", "data": "synthetic",
-            "config": {"workload": name, "batch_per_gpu": n, "what": WORKLOADS[name][3],
-                       "l2": "inputs rotate over %d distinct batches (%.0f MB) + %.0f MB of intermediates per step: larger than the 126 MB L2" % (
-                           r["nbuf"], r["nbuf"] * r["in_bytes"] / 1e6, n * 4 * 32 / 1e6),
-                       "parallelism": "%d x contiguous batch slice, no collective" % world},
-            "e2e": {"value": world * n / e2e_s, "unit": "scalar-mults/s", "h2d_bytes_per_step": r["in_bytes"], "d2h_bytes_per_step": r["out_bytes"],
-                    "path": "ecb_* host entry point, pinned host buffers, chunks pipelined over 4 stream slots",
-                    "pcie": pcie},
-            "gpu_launches": int(r["launches"]),
-            "roofline": {"bound": "imad", "achieved": achieved, "peak": peak, "unit": "T MAC32/s (32x32->64 multiply-accumulates)", "frac": achieved / peak if peak else None,
-                         "traffic": traffic, "mac32_per_op": W,
-                         "pipe_util_ncu": {"kernel": static.get("kernel"), "fmaheavy_pct": static.get("fmaheavy_pct"), "alu_pct": static.get("alu_pct"),
-                                           "issue_pct": static.get("issue_pct"), "source": static.get("source")},
-                         "note": "frac uses the reference algorithm's MAC32 count (SURVEY 8d); the kernels execute fewer (wider comb, mixed additions), so frac can exceed 1 while pipe_util_ncu (the integer-multiply pipe's busy cycles) stays below 100 %", "peak_source": "live probe kernels on this GPU (T/s): %s; a MAC32 is two passes of the 32-bit multiplier" % json.dumps({k: (round(v, 3) if v else v) for k, v in probes.items()}),
-                         "kernels_ms": {"scalar_mult": r["main_ms"], "batch_inversion_encode": r["fin_ms"]},
-                         "hbm_gbs": (r["in_bytes"] + r["out_bytes"]) / (r["ms_per_step"] * 1e-3) / 1e9},
-            "cpu_baseline": cpu, "clocks": clocks, "parity_check": check,
+            "metric": "scalar-mults/s", "value": head["value"], "unit": "scalar-mults/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u32 limbs (32x32->64 integer multiply-add)", "data": "synthetic", "config": cfg,
+            "step": {"batches_per_step": head["batches_per_step"], "ms_per_batch": head["ms_per_batch"], "timed_region_s": head["timed_region_s"],
+                     "why": "one pass over a 2^%d batch takes %.3f ms; a step is %d passes over distinct batches so that the timed region lasts >= %.1f s" % (
+                         WORKLOADS[name][0], head["ms_per_batch"], head["batches_per_step"], MIN_TIMED_S), "l2": head["l2"]},
+            "comb": {"ed25519_comb_w": ctx.get_info("ed25519_comb_w"), "ed25519_comb_windows": ctx.get_info("ed25519_comb_windows")},
+            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
+            "cpu_baseline": head.get("cpu_baseline"), "clocks": clocks, "parity_check": head["parity_check"], "parity_sample": head["parity_sample"],
         }
-    # further configs of BASELINE.json, a few steps each (device-resident), same line
-    extras = [x for x in args.extra.split(",") if x and x != name]
+    # the other BASELINE.json configs, measured the same way (>= 0.5 s timed, same step count), same line
     wl = {}
-    for x in extras:
-        nx = 1 << WORKLOADS[x][0]
+    for x in [x for x in args.extra.split(",") if x and x != name]:
         try:
-            rx = measure_device(torch, ctx, x, nx, args.extra_steps, 1 if args.profile_run else 3, 0xECC00002 + rank, dist)
-            v = world * nx / (rx["ms_per_step"] * 1e-3)
-            wl[x] = {"value": v, "ms_per_step": rx["ms_per_step"], "batch_per_gpu": nx, "mac32_per_op": work_of(x),
-                     "roofline_frac": (nx * work_of(x) / (rx["ms_per_step"] * 1e-3) / 1e12) / peak if peak else None,
-                     "kernels_ms": {"scalar_mult": rx["main_ms"], "batch_inversion_encode": rx["fin_ms"]}}
-            ex_s, _ = measure_e2e(torch, ctx, x, nx, 1 if args.profile_run else 5, 2, rx["ins_h"], dist)
-            wl[x]["e2e"] = world * nx / ex_s
-            del rx
+            rx = run_workload(torch, ctx, x, args.steps, args.warmup, world, rank, dist, peak, probes, check=not args.no_check, cpu=False)
+            if rank == 0:
+                rx.pop("_r")
+                rx["what"] = WORKLOADS[x][3]
+                wl[x] = rx
             torch.cuda.empty_cache()
         except Exception as e:  # keep the headline line even if an extra fails
             wl[x] = {"error": repr(e)}

@@ -16,6 +16,7 @@ ECB_ERR_INVALID_ARG = -2
 ECB_ERR_NONCANONICAL_SCALAR = -3
 ECB_ERR_POINT_NOT_ON_CURVE = -4
 ECB_ERR_OOM = -5
+ECB_ERR_NOT_READY = -6
 
 CURVE_P256R1 = 0
 CURVE_P384R1 = 1
@@ -74,6 +75,8 @@ SIGNATURES = {
     "ecb_ecdsa_sign_hashed": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_sign_hashed_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "ecb_ecdsa_sign": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ecb_warm": (_int, [_vp, ctypes.c_char_p, _int, _sz]),
+    "ecb_get_info": (_int, [_vp, _int, ctypes.c_char_p, ctypes.POINTER(ctypes.c_long)]),
     "ecb_debug_fused_trace": (ctypes.c_long, [_vp, _int, _vp, _sz]),
     "ecb_debug_chunk_plan": (ctypes.c_long, [_sz, _sz, _sz, ctypes.c_long, _vp, _sz]),
     "ecb_debug_ed25519_table": (ctypes.c_long, [_vp, _int, _vp, _sz, ctypes.POINTER(_int), ctypes.POINTER(_int)]),

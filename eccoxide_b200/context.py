@@ -338,7 +338,18 @@ class Context:
         self._check(self._lib.ecb_ecdsa_verify(self._ctx, cid, int(hash_bits), _p(q), _p(blob), _p(off), _p(rs), n, _p(ok), ctypes.byref(bad)), bad)
         return ok.astype(bool)
 
-    # -- device-resident variants (raw device pointers, enqueue on `stream`, no sync) -----------
+    # -- device-resident variants (raw device pointers, enqueue on `stream`, no sync, no allocation) ---
+    def warm(self, op, max_n, curve=None):
+        """ecb_warm: build the generator comb `op` needs and size its work buffers for batches up to max_n.
+        Required before dev_call (the *_dev entry points never allocate)."""
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else (-1 if curve is None else int(curve))
+        self._check(self._lib.ecb_warm(self._ctx, op.encode(), cid, int(max_n)))
+
+    def get_info(self, key, dev_index=0):
+        v = ctypes.c_long()
+        self._check(self._lib.ecb_get_info(self._ctx, dev_index, key.encode(), ctypes.byref(v)))
+        return int(v.value)
+
     def dev_call(self, name, *args):
         """Call a *_dev entry point: args are ints (device pointers, sizes, ids) in ABI order after ctx."""
         self._check(getattr(self._lib, name)(self._ctx, *args))

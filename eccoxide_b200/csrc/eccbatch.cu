@@ -853,49 +853,58 @@ static inline void single_slot(DevCtx* d) {  // *_dev calls that do not fork: on
     d->dev_slots_used = 1;
 }
 static DevCtx* get_dev(ecb_ctx* ctx, int i) { return (ctx && i >= 0 && i < (int)ctx->devs.size()) ? ctx->devs[i] : nullptr; }
+// *_dev entry points only enqueue: while one runs, ensure() and the table builders refuse to allocate
+// (ECB_ERR_NOT_READY) unless ecb_warm() is the caller.  Successive *_dev calls share the work buffers of
+// slot 0: enqueue them on ONE stream, or order streams with events.
+struct DevCallScope {
+    ecb_ctx* ctx;
+    bool prev;
+    explicit DevCallScope(ecb_ctx* c, bool warming) : ctx(c), prev(c->no_alloc) { ctx->no_alloc = !warming; }
+    ~DevCallScope() { ctx->no_alloc = prev; }
+};
+static thread_local bool g_warming = false;
+#define DEV_ENTER(n_)                          \
+    if (!d) return ECB_ERR_INVALID_ARG;        \
+    if ((n_) == 0) return ECB_OK;              \
+    CU(cudaSetDevice(d->dev));                 \
+    DevCallScope scope_(ctx, g_warming)
 
 int ecb_ed25519_mul_base_dev(ecb_ctx* ctx, int di, const void* d_k, size_t n, void* d_xy, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     return dev_forkjoin(ctx, *d, n, (cudaStream_t)stream, [&](size_t lo, size_t cnt, cudaStream_t st) {
         return dev_ed25519_mul_base(ctx, *d, (const u32*)d_k + lo * 8, cnt, (u32*)d_xy + lo * 16, false, st);
     });
 }
 int ecb_ed25519_mul_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_xy_in, size_t n, void* d_xy_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_ed25519_mul(ctx, *d, (const u32*)d_k, (const u32*)d_xy_in, n, (u32*)d_xy_out, (cudaStream_t)stream);
 }
 int ecb_x25519_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_x25519(ctx, *d, (const u32*)d_k, (const u32*)d_u, n, (u32*)d_out, (cudaStream_t)stream);
 }
 int ecb_x25519_base_dev(ecb_ctx* ctx, int di, const void* d_k, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_x25519_base(ctx, *d, (const u32*)d_k, n, (u32*)d_out, (cudaStream_t)stream);
 }
 int ecb_wei_mul_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, const void* d_xy, size_t n, void* d_out, void* d_inf,
                     void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_wei_mul(ctx, *d, curve, (const u32*)d_k, (const u32*)d_xy, nullptr, n, (u32*)d_out, (unsigned char*)d_inf,
                        (cudaStream_t)stream);
 }
 int ecb_wei_mul_base_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, size_t n, void* d_out, void* d_inf, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     size_t fb, sb;
     if (curve_sizes(curve, fb, sb)) return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
     return dev_forkjoin(ctx, *d, n, (cudaStream_t)stream, [&](size_t lo, size_t cnt, cudaStream_t st) {
@@ -906,8 +915,7 @@ int ecb_wei_mul_base_dev(ecb_ctx* ctx, int di, int curve, const void* d_k, size_
 int ecb_wei_decompress_dev(ecb_ctx* ctx, int di, int curve, const void* d_x, const void* d_sign, size_t n, void* d_out, void* d_ok,
                            void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     switch (curve) {
         case ECB_CURVE_P256R1:
@@ -925,8 +933,7 @@ int ecb_wei_decompress_dev(ecb_ctx* ctx, int di, int curve, const void* d_x, con
 int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int di, const void* d_enc, size_t n, int check_subgroup, void* d_out, void* d_ok,
                                          void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_bls_g1_from_compressed(ctx, *d, (const u32*)d_enc, n, check_subgroup ? 1 : 0, (u32*)d_out, (unsigned char*)d_ok,
                                       (cudaStream_t)stream);
@@ -934,8 +941,7 @@ int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int di, const void* d_enc
 int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_d, const void* d_k, const void* d_z, size_t n, void* d_rs,
                               void* d_ok, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     if (curve == ECB_CURVE_P256R1)
         return dev_ecdsa_sign_p256(ctx, *d, (const u32*)d_d, (const u32*)d_k, (const u32*)d_z, n, (u32*)d_rs, (unsigned char*)d_ok,
@@ -947,32 +953,28 @@ int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_d, 
 }
 int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int di, const void* d_seeds, size_t n, void* d_pub, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_ed25519_public_from_seed(ctx, *d, (const unsigned char*)d_seeds, n, (u32*)d_pub, (cudaStream_t)stream);
 }
 int ecb_ed25519_sign_dev(ecb_ctx* ctx, int di, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off, size_t n,
                          void* d_sig, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_ed25519_sign(ctx, *d, (const unsigned char*)d_seeds, (const unsigned char*)d_pub, (const unsigned char*)d_msgs,
                             (const unsigned long long*)d_msg_off, n, (unsigned char*)d_sig, (cudaStream_t)stream);
 }
 int ecb_x448_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_x448(ctx, *d, (const u32*)d_k, (const u32*)d_u, n, (u32*)d_out, (cudaStream_t)stream);
 }
 int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int di, const void* d_a, const void* d_r, const void* d_s, const void* d_k,
                                      size_t n, void* d_ok, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     return dev_ed25519_verify(ctx, *d, (const u32*)d_a, (const u32*)d_r, (const u32*)d_s, (const u32*)d_k, n,
                               (unsigned char*)d_ok, (cudaStream_t)stream);
@@ -980,8 +982,7 @@ int ecb_ed25519_verify_prehashed_dev(ecb_ctx* ctx, int di, const void* d_a, cons
 int ecb_ecdsa_verify_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_q, const void* d_z, const void* d_rs, size_t n,
                                 void* d_ok, void* stream) {
     DevCtx* d = get_dev(ctx, di);
-    if (!d) return ECB_ERR_INVALID_ARG;
-    CU(cudaSetDevice(d->dev));
+    DEV_ENTER(n);
     single_slot(d);
     if (curve == ECB_CURVE_P256R1)
         return dev_ecdsa_p256(ctx, *d, (const u32*)d_q, (const u32*)d_z, (const u32*)d_rs, n, (unsigned char*)d_ok, (cudaStream_t)stream);
@@ -1086,6 +1087,100 @@ long ecb_debug_ed25519_table(ecb_ctx* ctx, int di, uint8_t* out, size_t cap, int
         if (cudaMemcpy2D(out, 96, d->ed_table, (size_t)d->ed_stride * 4, 96, cnt, cudaMemcpyDeviceToHost) != cudaSuccess) return ECB_ERR_CUDA;
     }
     return (long)ntab;
+}
+
+// ---- explicit preparation -------------------------------------------------------------------------
+// ecb_warm runs `op` once per device on an all-zero batch of max_n elements with allocation allowed:
+// afterwards the generator comb the op needs is built and every work buffer is sized, so *_dev calls of
+// that op with n <= max_n (same options) only enqueue kernels.
+struct WarmOp { const char* name; size_t in_b[4]; size_t out_b[2]; };
+static const WarmOp* warm_lookup(const char* op, int curve, WarmOp& tmp) {
+    size_t fb = 0, sb = 0;
+    const bool wei = curve_sizes(curve, fb, sb) == ECB_OK;
+    static const WarmOp fixed[] = {
+        {"ed25519_mul_base", {32, 0, 0, 0}, {64, 0}},       {"ed25519_mul", {32, 64, 0, 0}, {64, 0}},
+        {"x25519", {32, 32, 0, 0}, {32, 0}},                {"x25519_base", {32, 0, 0, 0}, {32, 0}},
+        {"x448", {56, 56, 0, 0}, {56, 0}},                  {"ed25519_verify_prehashed", {32, 32, 32, 32}, {1, 0}},
+        {"ed25519_public_from_seed", {32, 0, 0, 0}, {32, 0}}, {"ed25519_sign", {32, 32, 64, 8}, {64, 0}},
+        {"bls12_381_g1_from_compressed", {48, 0, 0, 0}, {96, 1}},
+    };
+    for (const WarmOp& w : fixed)
+        if (!strcmp(op, w.name)) return &w;
+    if (!wei) return nullptr;
+    tmp.name = op;
+    if (!strcmp(op, "wei_mul")) tmp = WarmOp{op, {sb, 2 * fb, 0, 0}, {2 * fb, 1}};
+    else if (!strcmp(op, "wei_mul_base")) tmp = WarmOp{op, {sb, 0, 0, 0}, {2 * fb, 1}};
+    else if (!strcmp(op, "wei_decompress")) tmp = WarmOp{op, {fb, 1, 0, 0}, {2 * fb, 1}};
+    else if (!strcmp(op, "ecdsa_verify_hashed")) tmp = WarmOp{op, {2 * fb, sb, 2 * sb, 0}, {1, 0}};
+    else if (!strcmp(op, "ecdsa_sign_hashed")) tmp = WarmOp{op, {sb, sb, sb, 0}, {2 * sb, 1}};
+    else return nullptr;
+    return &tmp;
+}
+int ecb_warm(ecb_ctx* ctx, const char* op, int curve, size_t max_n) {
+    if (!ctx || !op) return ECB_ERR_INVALID_ARG;
+    WarmOp tmp{};
+    const WarmOp* w = warm_lookup(op, curve, tmp);
+    if (!w) return set_err(ctx, ECB_ERR_INVALID_ARG, std::string("ecb_warm: unknown op ") + op);
+    if (max_n == 0) max_n = 1;
+    for (int di = 0; di < (int)ctx->devs.size(); di++) {
+        DevCtx* d = ctx->devs[di];
+        CU(cudaSetDevice(d->dev));
+        void* in[4] = {nullptr, nullptr, nullptr, nullptr};
+        void* out[2] = {nullptr, nullptr};
+        int rc = ECB_OK;
+        auto body = [&]() -> int {
+            for (int k = 0; k < 4; k++)
+                if (w->in_b[k]) {
+                    size_t bytes = w->in_b[k] * (max_n + 1);
+                    CU(cudaMalloc(&in[k], bytes));
+                    CU(cudaMemset(in[k], 0, bytes));
+                }
+            for (int k = 0; k < 2; k++)
+                if (w->out_b[k]) CU(cudaMalloc(&out[k], w->out_b[k] * max_n));
+            void* st = (void*)d->stream;
+            g_warming = true;
+            int r;
+            if (!strcmp(op, "ed25519_mul_base")) r = ecb_ed25519_mul_base_dev(ctx, di, in[0], max_n, out[0], st);
+            else if (!strcmp(op, "ed25519_mul")) r = ecb_ed25519_mul_dev(ctx, di, in[0], in[1], max_n, out[0], st);
+            else if (!strcmp(op, "x25519")) r = ecb_x25519_dev(ctx, di, in[0], in[1], max_n, out[0], st);
+            else if (!strcmp(op, "x25519_base")) r = ecb_x25519_base_dev(ctx, di, in[0], max_n, out[0], st);
+            else if (!strcmp(op, "x448")) r = ecb_x448_dev(ctx, di, in[0], in[1], max_n, out[0], st);
+            else if (!strcmp(op, "ed25519_verify_prehashed")) r = ecb_ed25519_verify_prehashed_dev(ctx, di, in[0], in[1], in[2], in[3], max_n, out[0], st);
+            else if (!strcmp(op, "ed25519_public_from_seed")) r = ecb_ed25519_public_from_seed_dev(ctx, di, in[0], max_n, out[0], st);
+            else if (!strcmp(op, "ed25519_sign")) r = ecb_ed25519_sign_dev(ctx, di, in[0], in[1], in[2], in[3], max_n, out[0], st);   // all-zero offsets: empty messages
+            else if (!strcmp(op, "bls12_381_g1_from_compressed")) r = ecb_bls12_381_g1_from_compressed_dev(ctx, di, in[0], max_n, 1, out[0], out[1], st);
+            else if (!strcmp(op, "wei_mul")) r = ecb_wei_mul_dev(ctx, di, curve, in[0], in[1], max_n, out[0], out[1], st);
+            else if (!strcmp(op, "wei_mul_base")) r = ecb_wei_mul_base_dev(ctx, di, curve, in[0], max_n, out[0], out[1], st);
+            else if (!strcmp(op, "wei_decompress")) r = ecb_wei_decompress_dev(ctx, di, curve, in[0], in[1], max_n, out[0], out[1], st);
+            else if (!strcmp(op, "ecdsa_verify_hashed")) r = ecb_ecdsa_verify_hashed_dev(ctx, di, curve, in[0], in[1], in[2], max_n, out[0], st);
+            else r = ecb_ecdsa_sign_hashed_dev(ctx, di, curve, in[0], in[1], in[2], max_n, out[0], out[1], st);
+            g_warming = false;
+            TRY(r);
+            CU(cudaStreamSynchronize(d->stream));
+            return ECB_OK;
+        };
+        rc = body();
+        g_warming = false;
+        cudaStreamSynchronize(d->stream);
+        for (void* q : in) if (q) cudaFree(q);
+        for (void* q : out) if (q) cudaFree(q);
+        if (rc != ECB_OK) return rc;
+    }
+    return ECB_OK;
+}
+// what the context currently holds on device dev_index (0 when not built yet)
+int ecb_get_info(ecb_ctx* ctx, int di, const char* key, long* value) {
+    DevCtx* d = get_dev(ctx, di);
+    if (!d || !key || !value) return ECB_ERR_INVALID_ARG;
+    static const char* wn[3] = {"p256r1", "p384r1", "bls12_381_g1"};
+    if (!strcmp(key, "ed25519_comb_w")) { *value = d->ed_w; return ECB_OK; }
+    if (!strcmp(key, "ed25519_comb_windows")) { *value = d->ed_nwin; return ECB_OK; }
+    if (!strcmp(key, "sm_count")) { *value = d->sm_count; return ECB_OK; }
+    for (int c = 0; c < 3; c++) {
+        if (!strcmp(key, (std::string(wn[c]) + "_comb_w").c_str())) { *value = d->wei_w[c]; return ECB_OK; }
+        if (!strcmp(key, (std::string(wn[c]) + "_comb_windows").c_str())) { *value = d->wei_nwin[c]; return ECB_OK; }
+    }
+    return set_err(ctx, ECB_ERR_INVALID_ARG, std::string("ecb_get_info: unknown key ") + key);
 }
 
 }  // extern "C"

@@ -77,7 +77,10 @@ struct ecb_ctx {
     // integer-pipe-bound, so time follows the window count; the random table reads (96 B per window) stay
     // far below HBM bandwidth.
     long opt_ed_w = 0;
-    long opt_ed_stride = 24;                  // words between comb entries: 24 (packed, 96 B) or 32 (one entry per 128-byte line)
+    // words between comb entries: 32 (default: one 96-byte entry per 128-byte line) or 24 (packed).  Measured at W = 24,
+    // n = 2^20 (profiles/r02_l_*): same kernel time (0.79 vs 0.80 ms), DRAM reads 1.37 GB vs 2.03 GB per launch against a
+    // minimum of 1.11 GB — packed entries straddle DRAM atoms; the aligned table is 11.8 GB instead of 8.9 GB.
+    long opt_ed_stride = 32;
     long opt_ed_fused = 1;                    // small-batch fused kernel (fused.cuh): 0 never, 1 when the batch fits one wave, 2 always
     long opt_ed_lanes = 0;                    // lanes per scalar in the fused kernel: 0 = by batch size, or 1 / 2 / 4 / 8
     size_t opt_chunk = 189440;  // elements per pipeline chunk = 148 SMs x 1280 (ECB_NSLOT chunks in flight per device; measured best of 2^16..2^19)
@@ -88,6 +91,9 @@ struct ecb_ctx {
     long opt_dev_split = 0;                   // 1: split large device-resident batches over the slot streams (measured: no gain, the
                                               // shorter inversion chains cost what the overlap saves; kept as an option)
     std::atomic<unsigned long long> launches{0};
+    // set while a *_dev entry point runs: those enqueue only — no allocation, no table build, no synchronisation.
+    // Anything missing makes the call fail with ECB_ERR_NOT_READY; ecb_warm() provides it beforehand.
+    bool no_alloc = false;
 };
 
 static inline int set_err(ecb_ctx* ctx, int code, const std::string& msg) {
@@ -108,6 +114,7 @@ static inline int set_err(ecb_ctx* ctx, int code, const std::string& msg) {
 
 static inline int ensure(ecb_ctx* ctx, DevBuf& b, size_t bytes) {
     if (b.cap >= bytes) return ECB_OK;
+    if (ctx->no_alloc) return set_err(ctx, ECB_ERR_NOT_READY, "a *_dev call needs a larger work buffer: call ecb_warm(ctx, op, curve, max_n) first");
     if (b.p) CU(cudaFree(b.p));
     b.p = nullptr;
     b.cap = 0;

@@ -50,8 +50,8 @@ static int ed_pick_w(ecb_ctx* ctx) {
     if (ctx->opt_ed_w) return (int)ctx->opt_ed_w;
     size_t free_b = 0, total_b = 0;
     if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess) return 16;
-    if (free_b > ((size_t)110 << 30)) return 26;   // 10 windows, 32 GB table (+ 43 GB while it is built)
-    if (free_b > ((size_t)40 << 30)) return 24;
+    // W = 26 (10 windows, 32 GB table + 43 GB while it is built) is 7 % faster at 2^20 but is opt-in: ed25519_comb_w = 26
+    if (free_b > ((size_t)40 << 30)) return 24;    // 11 windows, 8.9 GB table
     if (free_b > ((size_t)8 << 30)) return 20;
     return 16;
 }
@@ -126,8 +126,9 @@ static inline bool ed_table_stale(ecb_ctx* ctx, const DevCtx& d) {
 }
 // make sure the device holds a comb table of the configured shape (ecb_warm and the host entry points)
 int dev_ed25519_table(ecb_ctx* ctx, DevCtx& d) {
-    if (ed_table_stale(ctx, d)) TRY(dev_ed25519_build_table(ctx, d, ed_pick_w(ctx)));
-    return ECB_OK;
+    if (!ed_table_stale(ctx, d)) return ECB_OK;
+    if (ctx->no_alloc) return set_err(ctx, ECB_ERR_NOT_READY, "Ed25519 comb table not built for the current options: call ecb_warm() first");
+    return dev_ed25519_build_table(ctx, d, ed_pick_w(ctx));
 }
 
 // Launch shape of the fused small-batch kernel: LANES lanes per scalar and a block size such that the

@@ -13,8 +13,12 @@
  *     encodings (curve25519: little-endian; Weierstrass curves: big-endian), element i at i*size
  *   - host entry points copy host->device, run the kernels and copy back before returning
  *     (blocking); *_dev entry points take device pointers on device `dev_index` of the context and
- *     enqueue on `stream` (a cudaStream_t) without synchronising; device pointers must be 16-byte
- *     aligned (the kernels move elements with 128-bit loads and stores; cudaMalloc gives 256)
+ *     enqueue on `stream` (a cudaStream_t) without synchronising and WITHOUT allocating: the generator
+ *     comb and the work buffers they need are provided beforehand by ecb_warm(ctx, op, curve, max_n);
+ *     a *_dev call that finds them missing or too small fails with ECB_ERR_NOT_READY; n == 0 is a
+ *     no-op; device pointers must be 16-byte aligned (the kernels move elements with 128-bit loads
+ *     and stores; cudaMalloc gives 256); successive *_dev calls share one set of work buffers, so
+ *     enqueue them on ONE stream or order the streams with events
  *   - a batch is sharded by contiguous slice over the devices of the context; no collective
  *   - threading: host entry points may be called concurrently on one context (calls are serialised
  *     per device); the *_dev entry points use the context's slot-0 work buffers without locking, so
@@ -43,6 +47,7 @@ extern "C" {
 #define ECB_ERR_NONCANONICAL_SCALAR (-3)
 #define ECB_ERR_POINT_NOT_ON_CURVE (-4)
 #define ECB_ERR_OOM (-5)
+#define ECB_ERR_NOT_READY (-6) /* a *_dev call found a table or work buffer missing: ecb_warm() first */
 
 /* Weierstrass curve ids (src/curve/sec2/p256r1.rs, p384r1.rs, src/curve/bls12_381/g1.rs) */
 #define ECB_CURVE_P256R1 0       /* field 32 B, scalar 32 B */
@@ -51,15 +56,28 @@ extern "C" {
 
 typedef struct ecb_ctx ecb_ctx;
 
-/* Create a context over `n_dev` CUDA devices (device_ids == NULL, n_dev == 0: device 0 only).
- * Builds the per-device generator comb tables — the role of the reference's OnceLock'd
- * generator_comb() (src/curve/curve25519.rs:881, src/curve/fiat/curve_macros.rs:168). */
+/* Create a context over `n_dev` CUDA devices (device_ids == NULL, n_dev == 0: device 0 only): streams,
+ * status words, nothing else.  The per-device generator comb tables — the role of the reference's
+ * OnceLock'd generator_comb() (src/curve/curve25519.rs:881, src/curve/fiat/curve_macros.rs:168) — are
+ * built on the device by the first HOST call that needs them (0.3 s for the default 8.9 GB Ed25519
+ * table) or explicitly by ecb_warm(). */
 int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out);
+/* Prepare every device of the context for `op` on batches of up to max_n elements: builds the generator
+ * comb the op uses (for the current options) and sizes its work buffers by running the op once on an
+ * all-zero batch.  Required before *_dev calls (which never allocate), optional before host calls.
+ * op: "ed25519_mul_base", "ed25519_mul", "x25519", "x25519_base", "x448", "ed25519_verify_prehashed",
+ * "ed25519_public_from_seed", "ed25519_sign", "bls12_381_g1_from_compressed", and with a curve_id
+ * "wei_mul", "wei_mul_base", "wei_decompress", "ecdsa_verify_hashed", "ecdsa_sign_hashed". */
+int ecb_warm(ecb_ctx* ctx, const char* op, int curve_id, size_t max_n);
+/* What device dev_index holds now: "ed25519_comb_w", "ed25519_comb_windows", "<curve>_comb_w",
+ * "<curve>_comb_windows" (0 = not built yet), "sm_count". */
+int ecb_get_info(ecb_ctx* ctx, int dev_index, const char* key, long* value);
 void ecb_destroy(ecb_ctx* ctx);
 const char* ecb_last_error(ecb_ctx* ctx);
 int ecb_device_count(ecb_ctx* ctx);
 /* Tunables (set before first use; unknown keys and out-of-range values give ECB_ERR_INVALID_ARG):
- *   "ed25519_comb_w"        window width of the Ed25519 fixed-base comb, 4..26; 0 = by free device memory
+ *   "ed25519_comb_w"        window width of the Ed25519 fixed-base comb, 4..26; 0 (default) = by free device memory, at
+ *                           most 24 (11 windows, 8.9 GB).  26 (10 windows, 32 GB + 43 GB while it is built) is opt-in.
  *   "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w"
  *                           generator combs of the Weierstrass curves, 4..24; 0 = by free device memory
  *   "chunk"                 elements per pipeline chunk of the host entry points
@@ -68,7 +86,7 @@ int ecb_device_count(ecb_ctx* ctx);
  *   "inv_block"             batch inversion: 0 one inversion per thread, 2 one per block, 1 (default) per field as measured
  *   "inv_hi"                1 (default): batch inversions of pipelined chunks run on a high-priority side stream
  *   "dev_split"             1: split large device-resident batches over the slot streams (default 0)
- *   "ed25519_entry_stride"  32-bit words between Ed25519 comb entries: 24 (packed, 96 B) or 32 (one entry per 128-byte line)
+ *   "ed25519_entry_stride"  32-bit words between Ed25519 comb entries: 32 (default, one entry per 128-byte line: 1.2x the minimum DRAM traffic) or 24 (packed, 96 B: 25 % smaller table, 1.8x the traffic, same speed)
  *   "ed25519_fused"         small-batch kernel (lanes share a scalar, affine conversion in the same launch): 0 never,
  *                           1 (default) when the batch fits one wave of the device, 2 always
  *   "ed25519_lanes"         lanes per scalar in that kernel: 0 (default) by batch size, or 1, 2, 4, 8

@@ -61,13 +61,18 @@ def test_product_arm_prints_the_contract_line_on_a_gpu():
                 "data", "config", "e2e", "gpu_launches", "roofline", "cpu_baseline", "clocks"):
         assert key in d, key
     assert d["n_gpus"] == 1 and d["steps"] == 3 and d["warmup"] >= 3 and d["scaling"] == "weak" and d["data"] == "synthetic"
-    assert d["config"]["workload"] == "ed25519_mul_base" and d["parity_check"] is True
-    assert d["gpu_launches"] >= 2 * d["steps"]
-    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+    # the headline is BASELINE.json configs[0] exactly: Ed25519 mul_base on 2^16 scalars, several passes per step
+    assert d["config"]["workload"] == "ed25519_mul_base_2p16" and d["config"]["batch_per_gpu"] == 1 << 16 and d["parity_check"] is True
+    bps = d["step"]["batches_per_step"]
+    assert bps >= 1 and d["step"]["timed_region_s"] > 0.4
+    assert d["gpu_launches"] >= bps * d["steps"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic", "frac_executed", "hbm_frac"):
         assert key in d["roofline"], key
+    assert 0 < d["roofline"]["frac_executed"] < 1
     assert d["roofline"]["peak"] > 1 and abs(d["roofline"]["frac"] - d["roofline"]["achieved"] / d["roofline"]["peak"]) < 1e-9
     e = d["e2e"]
-    assert e["h2d_bytes_per_step"] == 32 << 20 and e["d2h_bytes_per_step"] == 64 << 20 and 0 < e["value"] < d["value"]
+    assert e["h2d_bytes_per_batch"] == 2 << 20 and e["d2h_bytes_per_batch"] == 4 << 20 and 0 < e["value"] < d["value"]
+    assert e["h2d_bytes_per_step"] == bps * (2 << 20) and e["d2h_bytes_per_step"] == bps * (4 << 20)
     c = d["cpu_baseline"]
     assert c["kind"] == "port" and c["cores"] >= 1 and 0 < c["value"] < d["value"] / 10
     assert d["clocks"]["sm_mhz"] > 0 and not set(d["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}

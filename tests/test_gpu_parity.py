@@ -34,7 +34,12 @@ def test_native_library_is_loaded_and_counts_launches(ctx):
     assert L._lib is not None and L.LIB_PATH.endswith("libeccbatch.so")
     before = ctx.launch_count()
     ctx.ed25519_mul_base(rows([(5).to_bytes(32, "little")]))
-    assert ctx.launch_count() >= before + 2  # scalar-mult kernel + batch inversion
+    assert ctx.launch_count() >= before + 1  # small batch: ONE fused kernel (comb + block-level inversion + encoding)
+    ctx.set_option("ed25519_fused", 0)
+    before = ctx.launch_count()
+    ctx.ed25519_mul_base(rows([(5).to_bytes(32, "little")]))
+    ctx.set_option("ed25519_fused", 1)
+    assert ctx.launch_count() >= before + 2  # large-batch form: scalar-mult kernel + batch inversion
 
 
 def test_imad_probe_reports_a_plausible_peak(ctx):
@@ -618,10 +623,13 @@ def test_device_resident_entry_points_match_host_entry_points(ctx):
     d_k = torch.from_numpy(kb).cuda()
     d_out = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
+    ctx.warm("ed25519_mul_base", n)
+    ctx.warm("x25519", n)
     ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), n, d_out.data_ptr(), st)
     torch.cuda.synchronize()
     assert ctx.dev_status(0) == (0, None)
     assert np.array_equal(d_out.cpu().numpy(), ctx.ed25519_mul_base(kb))
+    ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), 0, d_out.data_ptr(), st)   # n = 0: a no-op, as the host path
     k, u = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
     d_o = torch.empty((n, 32), dtype=torch.uint8, device="cuda")
     d_kk, d_u = torch.from_numpy(k).cuda(), torch.from_numpy(u).cuda()  # keep alive: the allocator reuses freed blocks
@@ -636,6 +644,43 @@ def test_device_resident_entry_points_match_host_entry_points(ctx):
     assert ctx.dev_status(0) == (-3, 77)
 
 
+def test_device_resident_entry_points_never_allocate():
+    """*_dev calls only enqueue: without ecb_warm (no comb table, no work buffers) they fail with ECB_ERR_NOT_READY
+    instead of building a table inside a call documented as asynchronous; a warm for a smaller batch does not
+    cover a larger one; after ecb_warm they run, and ecb_get_info reports what was built."""
+    torch = pytest.importorskip("torch")
+    from eccoxide_b200 import Context, EccBatchError
+
+    g = rng(99)
+    n = 1 << 21   # the two-kernel form: 201 MB of projective planes, more than the W = 16 table build leaves behind
+    kb = np.tile(scalars_mod(g, 1 << 12, R.L25519, 32, "little"), (n >> 12, 1))
+    d_k = torch.from_numpy(kb).cuda()
+    d_out = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    with Context() as c:
+        c.set_option("ed25519_comb_w", 16)
+        assert c.get_info("ed25519_comb_w") == 0
+        with pytest.raises(EccBatchError) as e:
+            c.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), 1 << 12, d_out.data_ptr(), st)
+        assert e.value.code == -6
+        c.warm("ed25519_mul_base", 1 << 12)
+        assert c.get_info("ed25519_comb_w") == 16 and c.get_info("ed25519_comb_windows") == 16
+        c.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), 1 << 12, d_out.data_ptr(), st)
+        with pytest.raises(EccBatchError) as e:   # a warm for 2^12 does not cover 2^21
+            c.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), n, d_out.data_ptr(), st)
+        assert e.value.code == -6
+        c.warm("ed25519_mul_base", n)
+        c.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), n, d_out.data_ptr(), st)
+        torch.cuda.synchronize()
+        assert c.dev_status(0) == (0, None)
+        assert np.array_equal(d_out[:4096].cpu().numpy(), c.ed25519_mul_base(kb[:4096]))
+        with pytest.raises(EccBatchError) as e:
+            c.dev_call("ecb_wei_mul_base_dev", 0, 0, d_k.data_ptr(), 1024, d_out.data_ptr(), 0, st)
+        assert e.value.code == -6
+        with pytest.raises(EccBatchError):
+            c.warm("no_such_op", 16)
+
+
 def test_device_resident_large_batch_is_split_over_streams_and_stays_exact(ctx, coracle):
     """With option dev_split, n >= 3 * 2^16 takes the fork/join path (three sub-batches on the slot streams)."""
     torch = pytest.importorskip("torch")
@@ -646,6 +691,11 @@ def test_device_resident_large_batch_is_split_over_streams_and_stays_exact(ctx, 
     d_k = torch.from_numpy(kb).cuda()
     d_out = torch.empty((n, 64), dtype=torch.uint8, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
+    ctx.set_option("dev_split", 1)
+    ctx.warm("ed25519_mul_base", n)
+    ctx.warm("wei_mul_base", n, "p256r1")
+    ctx.set_option("dev_split", 0)
+    ctx.warm("ed25519_mul_base", n)
     ctx.set_option("dev_split", 1)
     ctx.dev_call("ecb_ed25519_mul_base_dev", 0, d_k.data_ptr(), n, d_out.data_ptr(), st)
     torch.cuda.synchronize()

@@ -59,6 +59,7 @@ def main():
                     ctx.set_option("ed25519_fused", fused)
                     ctx.set_option("ed25519_lanes", lanes)
                     try:
+                        ctx.warm("ed25519_mul_base", n)
                         for i in range(5):
                             ctx.dev_call("ecb_ed25519_mul_base_dev", 0, bufs[0].data_ptr(), n, out.data_ptr(), stream)
                         torch.cuda.synchronize()
