@@ -145,11 +145,13 @@ def rand_scalars(g, n, nbytes, clear_top_bits, endian):
     init_from_wide_bytes_le, field_macros.rs:314), stored in the curve's wire order.  (nbytes, clear_top_bits)
     names the curve, as the callers did when this drew uniform values below a power of two."""
     order = ORDERS[_CLEAR[(nbytes, clear_top_bits)]]
-    wide = g.integers(0, 256, size=(n, 64), dtype=np.uint8)
-    out = bytearray(n * nbytes)
-    for i in range(n):
+    u = min(n, 1 << 20)   # above 2^20 the same 2^20 scalars repeat (the sweep's 2^22 / 2^24 batches)
+    wide = g.integers(0, 256, size=(u, 64), dtype=np.uint8)
+    out = bytearray(u * nbytes)
+    for i in range(u):
         out[i * nbytes:(i + 1) * nbytes] = (int.from_bytes(wide[i].tobytes(), "little") % order).to_bytes(nbytes, endian)
-    return np.frombuffer(bytes(out), dtype=np.uint8).reshape(n, nbytes).copy()
+    a = np.frombuffer(bytes(out), dtype=np.uint8).reshape(u, nbytes)
+    return np.ascontiguousarray(np.tile(a, (n // u, 1))) if n > u else a.copy()
 
 
 def make_inputs(name, n, ctx, seed):
@@ -642,9 +644,9 @@ def cpu_baseline(name, ins_h, target_s, threads):
             "sample": "%d elements of the same batch x %d passes, %.1f s, C restatement of the reference algorithm (oracle/ecc_oracle.c); reference is Rust, no toolchain here" % (m, reps, dt)}
 
 
-def config_of(name, world):
+def config_of(name, world, strong=False):
     """The `config` object: identical in both arms (bench.py and bench.py --impl reference) for one workload."""
-    n = 1 << WORKLOADS[name][0]
+    n = (1 << WORKLOADS[name][0]) // (world if strong else 1)
     return {"workload": name, "batch_per_gpu": n, "what": WORKLOADS[name][3],
             "parallelism": "%d x contiguous batch slice, no collective" % world,
             "inputs": "scalars = 64 uniform bytes mod the group order; seeded Philox; points = random multiples of the generator"}
@@ -710,9 +712,10 @@ def load_json(path):
         return {}
 
 
-def run_workload(torch, ctx, name, steps, warmup, world, rank, dist, peak, probes, check=True, cpu=False, e2e_cap_s=6.0):
-    """Everything reported for one workload: device-resident value, e2e, the three roofline fractions, parity."""
-    n = 1 << WORKLOADS[name][0]
+def run_workload(torch, ctx, name, steps, warmup, world, rank, dist, peak, probes, check=True, cpu=False, e2e_cap_s=6.0, strong=False):
+    """Everything reported for one workload: device-resident value, e2e, the three roofline fractions, parity.
+    strong: the workload's batch is the WHOLE job and every rank takes its contiguous 1/world slice."""
+    n = (1 << WORKLOADS[name][0]) // (world if strong else 1)
     r = measure_device(torch, ctx, name, n, steps, warmup, 0xECC00001 + rank, dist)
     ops_s = world * n / (r["ms_per_batch"] * 1e-3)
     W, Wx = work_of(name), executed_mac32(name, ctx, n)
@@ -770,6 +773,64 @@ def run_workload(torch, ctx, name, steps, warmup, world, rank, dist, peak, probe
     return res
 
 
+def run_single_process(args):
+    """The library's own multi-device path: ONE process, ecb_init over N devices, every pass is ONE host
+    call on pinned host buffers; run_sharded gives device g the slice [g n/N, (g+1) n/N) on its own host thread
+    and stream slots.  Only an end-to-end number exists here (host buffers in, host buffers out)."""
+    import torch
+
+    from eccoxide_b200 import Context
+
+    ndev = args.gpus
+    if torch.cuda.device_count() < ndev:
+        raise SystemExit("bench.py --single-process: %d devices asked, %d visible" % (ndev, torch.cuda.device_count()))
+    ctx = Context(devices=list(range(ndev)))
+    for kv in args.opt:
+        key, val = kv.split("=")
+        ctx.set_option(key, int(val))
+    names = [args.workload] + [x for x in args.extra.split(",") if x and x != args.workload]
+    out = {}
+    for name in names:
+        n = (1 << WORKLOADS[name][0]) * (1 if args.scaling == "strong" else ndev)   # weak: 2^k per device
+        one = Context(devices=[0])   # inputs that need points come from a one-device context
+        ins = make_inputs(name, n, one, 0xECC00001)
+        one.close()
+        base = name.replace("_2p16", "")
+        pinned = [torch.from_numpy(a).pin_memory().numpy() for a in ins]
+        pouts = [torch.empty((n, w), dtype=torch.uint8).pin_memory().numpy() for w in OUT_SHAPES[base]]
+        for _ in range(3):
+            res = host_call(ctx, name, pinned, pouts)
+        t0 = time.perf_counter()
+        host_call(ctx, name, pinned, pouts)
+        per = time.perf_counter() - t0
+        passes = int(max(args.steps, min(2000, np.ceil(MIN_TIMED_S / per))))
+        t0 = time.perf_counter()
+        for _ in range(passes):
+            res = host_call(ctx, name, pinned, pouts)
+        dt = (time.perf_counter() - t0) / passes
+        parity = None
+        if not args.no_check:
+            from oracle import coracle as C
+
+            C.build()
+            m = min(PARITY_SAMPLE, n)
+            idx = np.unique(np.concatenate([np.arange(min(64, n)), np.random.Generator(np.random.Philox(5)).integers(0, n, size=m)]))
+            exp = oracle_call(C, name, [a[idx] for a in ins], os.cpu_count() or 1)
+            parity = all(np.array_equal(np.asarray(g)[idx].astype(np.uint8).reshape(len(idx), -1), np.asarray(e).astype(np.uint8).reshape(len(idx), -1)) for g, e in zip(res, exp))
+        out[name] = {"value": n / dt, "unit": "scalar-mults/s", "ms_per_pass": dt * 1e3, "batch_total": n, "passes_timed": passes,
+                     "h2d_bytes_per_pass": sum(a.nbytes for a in ins), "d2h_bytes_per_pass": sum(int(o.nbytes) for o in pouts), "parity_check": parity}
+    head = out[args.workload]
+    line = {"metric": "scalar-mults/s", "value": head["value"], "unit": "scalar-mults/s", "n_gpus": ndev, "steps": head["passes_timed"], "warmup": 3,
+            "ms_per_step": head["ms_per_pass"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "u32 limbs (32x32->64 integer multiply-add)", "data": "synthetic",
+            "mode": "single process: one ecb_init over %d devices, one host call per pass (run_sharded: a host thread and 4 stream slots per device, contiguous slices, no collective)" % ndev,
+            "config": config_of(args.workload, ndev, args.scaling == "strong"),
+            "e2e": {"value": head["value"], "unit": "scalar-mults/s", "h2d_bytes_per_step": head["h2d_bytes_per_pass"], "d2h_bytes_per_step": head["d2h_bytes_per_pass"]},
+            "gpu_launches": int(ctx.launch_count()), "parity_check": head["parity_check"], "workloads": {k: v for k, v in out.items() if k != args.workload}}
+    print(json.dumps(line), flush=True)
+    ctx.close()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -783,11 +844,17 @@ def main():
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--comb-w", type=int, default=None)
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (ecb_set_option)")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (the driver's contract): every rank its own batch; strong: ONE batch of the workload's size, sliced over the ranks")
+    ap.add_argument("--single-process", action="store_true",
+                    help="no torchrun: ONE context over --gpus devices (ecb_init(device_ids, N)), one host call per pass — the library's own multi-device path")
     args = ap.parse_args()
     if args.warmup < 3 and not args.profile_run:
         args.warmup = 3
     if args.impl == "reference":
         return run_reference_arm(args)
+    if args.single_process:
+        return run_single_process(args)
 
     import torch
 
@@ -832,20 +899,33 @@ def main():
     if sampler:
         sampler.start()
         time.sleep(0.3)
+    strong = args.scaling == "strong"
     head = run_workload(torch, ctx, name, args.steps, args.warmup, world, rank, dist, peak, probes, check=not args.no_check,
-                        cpu=(not args.no_cpu and world == 1))
+                        cpu=(not args.no_cpu and world == 1), strong=strong)
+    # plain pinned copies on every rank AT THE SAME TIME: what the box's host side gives each GPU when all are busy
+    if dist is not None:
+        dist.barrier()
+    pcie = pcie_bandwidth(torch)
+    pcie_ranks = None
+    if dist is not None:
+        t = torch.tensor([pcie["h2d_gbs"], pcie["d2h_gbs"], pcie["duplex_1in_2out_gbs_total"]], dtype=torch.float64, device="cuda")
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        pcie_ranks = [[round(float(x), 1) for x in a.tolist()] for a in allt]
     line = None
     if rank == 0:
         r = head.pop("_r")
         clocks = sampler.summary(r["t0"], r["t1"])
-        pcie = pcie_bandwidth(torch)
+        if pcie_ranks:
+            pcie["per_rank_simultaneous_h2d_d2h_duplex_gbs"] = pcie_ranks
+            pcie["all_ranks_duplex_total_gbs"] = round(sum(a[2] for a in pcie_ranks), 1)
         # the host path moves in + out bytes over one link; with both directions busy the link's TOTAL is what counts
         pcie["link_floor_ms_per_batch"] = (r["in_bytes"] + r["out_bytes"]) / (pcie["duplex_1in_2out_gbs_total"] * 1e9) * 1e3
         head["e2e"]["pcie"] = pcie
-        cfg = config_of(name, world)
+        cfg = config_of(name, world, strong)
         line = {
             "metric": "scalar-mults/s", "value": head["value"], "unit": "scalar-mults/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": head["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
             "dtype": "u32 limbs (32x32->64 integer multiply-add)", "data": "synthetic", "config": cfg,
             "step": {"batches_per_step": head["batches_per_step"], "ms_per_batch": head["ms_per_batch"], "timed_region_s": head["timed_region_s"],
                      "why": "one pass over a 2^%d batch takes %.3f ms; a step is %d passes over distinct batches so that the timed region lasts >= %.1f s" % (
@@ -858,7 +938,7 @@ def main():
     wl = {}
     for x in [x for x in args.extra.split(",") if x and x != name]:
         try:
-            rx = run_workload(torch, ctx, x, args.steps, args.warmup, world, rank, dist, peak, probes, check=not args.no_check, cpu=False)
+            rx = run_workload(torch, ctx, x, args.steps, args.warmup, world, rank, dist, peak, probes, check=not args.no_check, cpu=False, strong=strong)
             if rank == 0:
                 rx.pop("_r")
                 rx["what"] = WORKLOADS[x][3]
