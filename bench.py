@@ -831,6 +831,28 @@ def run_single_process(args):
     ctx.close()
 
 
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPUs NVML names as local to its GPU, BEFORE any pinned buffer is allocated: pinned pages
+    are placed by first touch, and a rank whose staging buffers sit on the other socket copies at half speed
+    (profiles/r02_n8_weak_8.json: four of eight ranks at 19 GB/s, the others at 40).  Returns what was done."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+        h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = [64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1]
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed or len(allowed) == len(os.sched_getaffinity(0)):
+            return {"bound": False, "why": "NVML reports no narrower CPU set for this GPU (%d CPUs)" % len(cpus)}
+        os.sched_setaffinity(0, allowed)
+        return {"bound": True, "cpus": "%d-%d (%d)" % (allowed[0], allowed[-1], len(allowed))}
+    except Exception as e:  # pragma: no cover
+        return {"bound": False, "why": repr(e)[:120]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -844,6 +866,7 @@ def main():
     ap.add_argument("--no-check", action="store_true")
     ap.add_argument("--comb-w", type=int, default=None)
     ap.add_argument("--opt", action="append", default=[], help="library option key=value (ecb_set_option)")
+    ap.add_argument("--no-bind", action="store_true", help="do not bind the rank to the CPUs local to its GPU")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (the driver's contract): every rank its own batch; strong: ONE batch of the workload's size, sliced over the ranks")
     ap.add_argument("--single-process", action="store_true",
@@ -864,6 +887,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
+    affinity = bind_to_gpu_numa_node(local) if not args.no_bind else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -932,7 +956,7 @@ def main():
                          WORKLOADS[name][0], head["ms_per_batch"], head["batches_per_step"], MIN_TIMED_S), "l2": head["l2"]},
             "comb": {"ed25519_comb_w": ctx.get_info("ed25519_comb_w"), "ed25519_comb_windows": ctx.get_info("ed25519_comb_windows")},
             "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "roofline": head["roofline"],
-            "cpu_baseline": head.get("cpu_baseline"), "clocks": clocks, "parity_check": head["parity_check"], "parity_sample": head["parity_sample"],
+            "cpu_affinity": affinity, "cpu_baseline": head.get("cpu_baseline"), "clocks": clocks, "parity_check": head["parity_check"], "parity_sample": head["parity_sample"],
         }
     # the other BASELINE.json configs, measured the same way (>= 0.5 s timed, same step count), same line
     wl = {}

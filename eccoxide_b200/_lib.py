@@ -71,6 +71,11 @@ SIGNATURES = {
     "ecb_ed25519_public_from_seed": (_int, [_vp, _vp, _sz, _vp]),
     "ecb_ed25519_sign": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "ecb_ed25519_public_from_seed_dev": (_int, [_vp, _int, _vp, _sz, _vp, _vp]),
+    "ecb_ed25519_public_from_seed_vartime": (_int, [_vp, _vp, _sz, _vp]),
+    "ecb_ed25519_sign_vartime": (_int, [_vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "ecb_ed25519_public_from_seed_vartime_dev": (_int, [_vp, _int, _vp, _sz, _vp, _vp]),
+    "ecb_ed25519_sign_vartime_dev": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ecb_ed25519_mul_base_ct": (_int, [_vp, _vp, _sz, _vp, _szp]),
     "ecb_ed25519_sign_dev": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_sign_hashed": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_sign_hashed_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),

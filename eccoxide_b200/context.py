@@ -141,17 +141,28 @@ class Context:
         self._check(self._lib.ecb_ed25519_verify(self._ctx, _p(a), _p(blob), _p(off), _p(s), n, _p(ok)))
         return ok.astype(bool)
 
-    def ed25519_public_from_seed(self, seeds, out=None):
-        """ed25519 SecretKey::public_key over a batch of 32-byte seeds (not constant-time)."""
+    def ed25519_mul_base_ct(self, k_le, out=None):
+        """Point::mul_base for SECRET scalars: the constant-time kernel (csrc/ct.cuh), same bytes as ed25519_mul_base."""
+        k = _rows(k_le, 32, "k_le")
+        n = k.shape[0]
+        out = _out(out, (n, 64))
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_ed25519_mul_base_ct(self._ctx, _p(k), n, _p(out), ctypes.byref(bad)), bad)
+        return out
+
+    def ed25519_public_from_seed(self, seeds, out=None, vartime=False):
+        """ed25519 SecretKey::public_key over a batch of 32-byte seeds.  Constant-time in the seeds by default;
+        vartime=True is the fast form (ecb_ed25519_public_from_seed_vartime)."""
         sd = _rows(seeds, 32, "seeds")
         n = sd.shape[0]
         out = _out(out, (n, 32))
-        self._check(self._lib.ecb_ed25519_public_from_seed(self._ctx, _p(sd), n, _p(out)))
+        fn = self._lib.ecb_ed25519_public_from_seed_vartime if vartime else self._lib.ecb_ed25519_public_from_seed
+        self._check(fn(self._ctx, _p(sd), n, _p(out)))
         return out
 
-    def ed25519_sign(self, seeds, msgs, pub=None, out=None):
-        """ed25519 Keypair::sign (pub given) / SecretKey::sign (pub None) on raw, ragged messages
-        (not constant-time): n x 64 bytes R || S."""
+    def ed25519_sign(self, seeds, msgs, pub=None, out=None, vartime=False):
+        """ed25519 Keypair::sign (pub given) / SecretKey::sign (pub None) on raw, ragged messages: n x 64 bytes
+        R || S.  Constant-time in the seeds by default; vartime=True is the fast form (ecb_ed25519_sign_vartime)."""
         sd = _rows(seeds, 32, "seeds")
         n = sd.shape[0]
         if len(msgs) != n:
@@ -165,10 +176,11 @@ class Context:
         off[1:] = np.cumsum([len(m) for m in msgs], dtype=np.uint64)
         blob = np.frombuffer(b"".join(bytes(m) for m in msgs) + b"\0", dtype=np.uint8)
         out = _out(out, (n, 64))
-        self._check(self._lib.ecb_ed25519_sign(self._ctx, _p(sd), _p(pb), _p(blob), _p(off), n, _p(out)))
+        fn = self._lib.ecb_ed25519_sign_vartime if vartime else self._lib.ecb_ed25519_sign
+        self._check(fn(self._ctx, _p(sd), _p(pb), _p(blob), _p(off), n, _p(out)))
         return out
 
-    def ed25519_sign_fixed(self, seeds, msgs, pub=None, out=None):
+    def ed25519_sign_fixed(self, seeds, msgs, pub=None, out=None, vartime=False):
         """ed25519_sign for n messages of one length given as an (n, w) byte array (no per-message objects)."""
         sd = _rows(seeds, 32, "seeds")
         n = sd.shape[0]
@@ -178,7 +190,8 @@ class Context:
         pb = None if pub is None else _rows(pub, 32, "pub")
         off = np.arange(n + 1, dtype=np.uint64) * np.uint64(m.shape[1])
         out = _out(out, (n, 64))
-        self._check(self._lib.ecb_ed25519_sign(self._ctx, _p(sd), _p(pb), _p(m), _p(off), n, _p(out)))
+        fn = self._lib.ecb_ed25519_sign_vartime if vartime else self._lib.ecb_ed25519_sign
+        self._check(fn(self._ctx, _p(sd), _p(pb), _p(m), _p(off), n, _p(out)))
         return out
 
     # -- X25519 / X448 ------------------------------------------------------------------------

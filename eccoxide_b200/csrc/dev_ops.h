@@ -8,9 +8,12 @@ int dev_ed25519_table(ecb_ctx* ctx, DevCtx& d);   // build the comb of the confi
 // enc_stride_words: distance between compressed outputs in 32-bit words (0 = packed, 8)
 int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s,
                          size_t enc_stride_words = 0);
-int dev_ed25519_public_from_seed(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, size_t n, u32* d_pub, cudaStream_t s);
+// ct: the scalar multiplications by secrets run the constant-time kernels (ct.cuh); false = the fast variable-time comb
+int dev_ed25519_mul_base_ct(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s,
+                            size_t enc_stride_words = 0);
+int dev_ed25519_public_from_seed(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, size_t n, u32* d_pub, cudaStream_t s, bool ct);
 int dev_ed25519_sign(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, const unsigned char* d_pub, const unsigned char* d_msgs,
-                     const unsigned long long* d_off, size_t n, unsigned char* d_sig, cudaStream_t s);
+                     const unsigned long long* d_off, size_t n, unsigned char* d_sig, cudaStream_t s, bool ct);
 int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_out, cudaStream_t s);
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
                        unsigned char* ok, cudaStream_t s);

@@ -71,7 +71,10 @@ void ecb_destroy(ecb_ctx* ctx) {
             if (sl.stream) cudaStreamSynchronize(sl.stream);
             DevBuf* bufs[] = {&sl.planes, &sl.pf, &sl.scratch, &sl.aux, &sl.in[0], &sl.in[1], &sl.in[2], &sl.in[3], &sl.out[0], &sl.out[1]};
             for (DevBuf* b : bufs)
-                if (b->p) cudaFree(b->p);
+                if (b->p) {
+                    cudaMemset(b->p, 0, b->cap);   // work buffers may hold key material of signing / key-generation calls
+                    cudaFree(b->p);
+                }
             if (sl.d_status) cudaFree(sl.d_status);
             if (sl.h_status) cudaFreeHost(sl.h_status);
             if (sl.ev_join) cudaEventDestroy(sl.ev_join);
@@ -83,6 +86,8 @@ void ecb_destroy(ecb_ctx* ctx) {
         for (auto& r : d->prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); cudaEventDestroy(r.c); }
         if (d->ed_table) cudaFree(d->ed_table);
         if (d->trace.p) cudaFree(d->trace.p);
+        if (d->ed_ct_table) cudaFree(d->ed_ct_table);
+        for (u32* t : d->wei_ct_table) if (t) cudaFree(t);
         if (d->ev_fork) cudaEventDestroy(d->ev_fork);
         for (u32* t : d->wei_table)
             if (t) cudaFree(t);
@@ -495,18 +500,43 @@ int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, 
         if (rc[i] != ECB_OK) return rc[i];
     return ECB_OK;
 }
-int ecb_ed25519_public_from_seed(ecb_ctx* ctx, const uint8_t* seeds, size_t n, uint8_t* pub) {
+static int ed25519_public_from_seed_impl(ecb_ctx* ctx, const uint8_t* seeds, size_t n, uint8_t* pub, bool ct) {
     if (!ctx) return ECB_ERR_CUDA;
     if (n && (!seeds || !pub)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
     return run_sharded(ctx, n, {{seeds, 32}}, {{pub, 32}}, false, nullptr,
                        [&](DevCtx& d, cudaStream_t s, const void** in, void** out, size_t cn) {
-                           return dev_ed25519_public_from_seed(ctx, d, (const unsigned char*)in[0], cn, (u32*)out[0], s);
+                           return dev_ed25519_public_from_seed(ctx, d, (const unsigned char*)in[0], cn, (u32*)out[0], s, ct);
+                       });
+}
+int ecb_ed25519_public_from_seed(ecb_ctx* ctx, const uint8_t* seeds, size_t n, uint8_t* pub) {
+    return ed25519_public_from_seed_impl(ctx, seeds, n, pub, true);
+}
+int ecb_ed25519_public_from_seed_vartime(ecb_ctx* ctx, const uint8_t* seeds, size_t n, uint8_t* pub) {
+    return ed25519_public_from_seed_impl(ctx, seeds, n, pub, false);
+}
+// Point::mul_base for SECRET scalars: the constant-time kernel (ct.cuh), same bytes as ecb_ed25519_mul_base
+int ecb_ed25519_mul_base_ct(ecb_ctx* ctx, const uint8_t* k_le, size_t n, uint8_t* xy_le, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k_le || !xy_le)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k_le, 32}}, {{xy_le, 64}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** out, size_t cn) {
+                           return dev_ed25519_mul_base_ct(ctx, d, (const u32*)in[0], cn, (u32*)out[0], false, s);
                        });
 }
 // Ed25519 signing of raw messages (ragged input): the chunk loop of ecb_ed25519_verify with seeds and
 // (optional) public keys in, signatures out.
+static int ed25519_sign_impl(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
+                             uint8_t* sig, bool ct);
 int ecb_ed25519_sign(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
                      uint8_t* sig) {
+    return ed25519_sign_impl(ctx, seeds, pub, msgs, msg_off, n, sig, true);
+}
+int ecb_ed25519_sign_vartime(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
+                             uint8_t* sig) {
+    return ed25519_sign_impl(ctx, seeds, pub, msgs, msg_off, n, sig, false);
+}
+static int ed25519_sign_impl(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
+                             uint8_t* sig, bool ct) {
     if (!ctx) return ECB_ERR_CUDA;
     if (n && (!seeds || !msg_off || !sig)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
     if (n == 0) return ECB_OK;
@@ -544,7 +574,7 @@ int ecb_ed25519_sign(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, con
                 if (mbytes) CU(cudaMemcpyAsync(sl.in[3].p, msgs + msg_off[c0], mbytes, cudaMemcpyHostToDevice, sl.stream));
                 const unsigned char* d_msgs = (const unsigned char*)sl.in[3].p - msg_off[c0];
                 TRY(dev_ed25519_sign(ctx, d, (const unsigned char*)sl.in[0].p, pub ? (const unsigned char*)sl.in[1].p : nullptr, d_msgs,
-                                     (const unsigned long long*)sl.in[2].p, cn, (unsigned char*)sl.out[0].p, sl.stream));
+                                     (const unsigned long long*)sl.in[2].p, cn, (unsigned char*)sl.out[0].p, sl.stream, ct));
                 CU(cudaMemcpyAsync(sig + c0 * 64, sl.out[0].p, cn * 64, cudaMemcpyDeviceToHost, sl.stream));
                 sl.busy = true;
             }
@@ -951,19 +981,33 @@ int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_d, 
                                    (cudaStream_t)stream);
     return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
 }
-int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int di, const void* d_seeds, size_t n, void* d_pub, void* stream) {
+static int ed25519_public_from_seed_dev_impl(ecb_ctx* ctx, int di, const void* d_seeds, size_t n, void* d_pub, void* stream, bool ct) {
     DevCtx* d = get_dev(ctx, di);
     DEV_ENTER(n);
     single_slot(d);
-    return dev_ed25519_public_from_seed(ctx, *d, (const unsigned char*)d_seeds, n, (u32*)d_pub, (cudaStream_t)stream);
+    return dev_ed25519_public_from_seed(ctx, *d, (const unsigned char*)d_seeds, n, (u32*)d_pub, (cudaStream_t)stream, ct);
 }
-int ecb_ed25519_sign_dev(ecb_ctx* ctx, int di, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off, size_t n,
-                         void* d_sig, void* stream) {
+int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int di, const void* d_seeds, size_t n, void* d_pub, void* stream) {
+    return ed25519_public_from_seed_dev_impl(ctx, di, d_seeds, n, d_pub, stream, true);
+}
+int ecb_ed25519_public_from_seed_vartime_dev(ecb_ctx* ctx, int di, const void* d_seeds, size_t n, void* d_pub, void* stream) {
+    return ed25519_public_from_seed_dev_impl(ctx, di, d_seeds, n, d_pub, stream, false);
+}
+static int ed25519_sign_dev_impl(ecb_ctx* ctx, int di, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off, size_t n,
+                                 void* d_sig, void* stream, bool ct) {
     DevCtx* d = get_dev(ctx, di);
     DEV_ENTER(n);
     single_slot(d);
     return dev_ed25519_sign(ctx, *d, (const unsigned char*)d_seeds, (const unsigned char*)d_pub, (const unsigned char*)d_msgs,
-                            (const unsigned long long*)d_msg_off, n, (unsigned char*)d_sig, (cudaStream_t)stream);
+                            (const unsigned long long*)d_msg_off, n, (unsigned char*)d_sig, (cudaStream_t)stream, ct);
+}
+int ecb_ed25519_sign_dev(ecb_ctx* ctx, int di, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off, size_t n,
+                         void* d_sig, void* stream) {
+    return ed25519_sign_dev_impl(ctx, di, d_seeds, d_pub, d_msgs, d_msg_off, n, d_sig, stream, true);
+}
+int ecb_ed25519_sign_vartime_dev(ecb_ctx* ctx, int di, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off,
+                                 size_t n, void* d_sig, void* stream) {
+    return ed25519_sign_dev_impl(ctx, di, d_seeds, d_pub, d_msgs, d_msg_off, n, d_sig, stream, false);
 }
 int ecb_x448_dev(ecb_ctx* ctx, int di, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream) {
     DevCtx* d = get_dev(ctx, di);
@@ -1102,6 +1146,7 @@ static const WarmOp* warm_lookup(const char* op, int curve, WarmOp& tmp) {
         {"x25519", {32, 32, 0, 0}, {32, 0}},                {"x25519_base", {32, 0, 0, 0}, {32, 0}},
         {"x448", {56, 56, 0, 0}, {56, 0}},                  {"ed25519_verify_prehashed", {32, 32, 32, 32}, {1, 0}},
         {"ed25519_public_from_seed", {32, 0, 0, 0}, {32, 0}}, {"ed25519_sign", {32, 32, 64, 8}, {64, 0}},
+        {"ed25519_public_from_seed_vartime", {32, 0, 0, 0}, {32, 0}}, {"ed25519_sign_vartime", {32, 32, 64, 8}, {64, 0}},
         {"bls12_381_g1_from_compressed", {48, 0, 0, 0}, {96, 1}},
     };
     for (const WarmOp& w : fixed)
@@ -1148,6 +1193,8 @@ int ecb_warm(ecb_ctx* ctx, const char* op, int curve, size_t max_n) {
             else if (!strcmp(op, "ed25519_verify_prehashed")) r = ecb_ed25519_verify_prehashed_dev(ctx, di, in[0], in[1], in[2], in[3], max_n, out[0], st);
             else if (!strcmp(op, "ed25519_public_from_seed")) r = ecb_ed25519_public_from_seed_dev(ctx, di, in[0], max_n, out[0], st);
             else if (!strcmp(op, "ed25519_sign")) r = ecb_ed25519_sign_dev(ctx, di, in[0], in[1], in[2], in[3], max_n, out[0], st);   // all-zero offsets: empty messages
+            else if (!strcmp(op, "ed25519_public_from_seed_vartime")) r = ecb_ed25519_public_from_seed_vartime_dev(ctx, di, in[0], max_n, out[0], st);
+            else if (!strcmp(op, "ed25519_sign_vartime")) r = ecb_ed25519_sign_vartime_dev(ctx, di, in[0], in[1], in[2], in[3], max_n, out[0], st);
             else if (!strcmp(op, "bls12_381_g1_from_compressed")) r = ecb_bls12_381_g1_from_compressed_dev(ctx, di, in[0], max_n, 1, out[0], out[1], st);
             else if (!strcmp(op, "wei_mul")) r = ecb_wei_mul_dev(ctx, di, curve, in[0], in[1], max_n, out[0], out[1], st);
             else if (!strcmp(op, "wei_mul_base")) r = ecb_wei_mul_base_dev(ctx, di, curve, in[0], max_n, out[0], out[1], st);

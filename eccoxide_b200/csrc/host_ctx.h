@@ -56,6 +56,8 @@ struct DevCtx {
     Slot* cur = &slots[0];                    // slot whose buffers the dev_* functions use (calls are serialised by `mu`)
     u32* ed_table = nullptr;
     int ed_w = 0, ed_nwin = 0, ed_stride = 24;  // comb width, windows, words between entries (24 packed, 32 = 128-byte aligned)
+    u32* ed_ct_table = nullptr;               // constant-time comb (ct.cuh): W = 4, 64 windows x 8 entries, 48 KB
+    u32* wei_ct_table[3] = {nullptr, nullptr, nullptr};   // constant-time generator combs of the Weierstrass curves (W = 4)
     u32* wei_table[3] = {nullptr, nullptr, nullptr};  // generator combs of p256r1, p384r1, bls12_381 G1
     int wei_w[3] = {0, 0, 0}, wei_nwin[3] = {0, 0, 0};
     DevBuf trace;                             // option "trace": per-block timestamps of the last fused launch

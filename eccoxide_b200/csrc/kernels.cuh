@@ -486,14 +486,16 @@ ECB_DEV void batch_inv_backward(size_t t, size_t T, size_t n, const u32* planes,
 }
 // one inversion per thread (the host simulation and option inv_block = 0 use this form; the
 // block-cooperative kernel in tu_common.cuh shares the two passes and inverts once per block)
-template <class FT, class FIN>
+// CT: the inverse in the middle is the fixed Fermat chain instead of the variable-time safegcd (secret data)
+template <class FT, class FIN, bool CT = false>
 ECB_DEV void batch_inv_body(size_t t, size_t T, size_t n, const u32* planes, u32* pf, FIN fin) {
     typedef typename FT::el fe;
     if (t >= n) return;
     fe accA, accB, inv, invA, invB;
     batch_inv_forward<FT>(t, T, n, planes, pf, accA, accB);
     FT::mul(inv, accA, accB);
-    FT::invert(inv, inv);
+    if (CT) FT::invert_fermat(inv, inv);
+    else FT::invert(inv, inv);
     FT::mul(invA, inv, accB);
     FT::mul(invB, inv, accA);
     batch_inv_backward<FT, FIN>(t, T, n, planes, pf, fin, invA, invB);

@@ -11,6 +11,21 @@ __global__ void __launch_bounds__(ECB_TPB) k_batch_inv_thread(size_t T, size_t n
     if (t < T) batch_inv_body<FT, FIN>(t, T, n, planes, pf, fin);
 }
 
+template <class FT, class FIN>
+__global__ void __launch_bounds__(ECB_TPB) k_batch_inv_thread_ct(size_t T, size_t n, const u32* planes, u32* pf, FIN fin) {
+    size_t t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (t < T) batch_inv_body<FT, FIN, true>(t, T, n, planes, pf, fin);
+}
+// constant-time batch inversion (ct.cuh): per-thread chains around the fixed Fermat chain, on the caller's stream
+template <class FT, class FIN>
+static int launch_batch_inv_ct(ecb_ctx* ctx, DevCtx& d, size_t n, const u32* planes, u32* pf, FIN fin, cudaStream_t s) {
+    size_t T = inv_threads(d, n);
+    k_batch_inv_thread_ct<FT, FIN><<<grid_for(T), ECB_TPB, 0, s>>>(T, n, planes, pf, fin);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ECB_OK;
+}
+
 // Block-cooperative batch inversion: every thread runs the forward pass over its own few elements,
 // the ECB_TPB chain totals of the block are inverted TOGETHER (shared memory, then a product scan
 // over the lanes of warp 0, ONE safegcd inversion per block), and every thread runs its backward

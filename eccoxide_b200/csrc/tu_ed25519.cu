@@ -2,6 +2,7 @@
 #include "tu_common.cuh"
 #include "dev_ops.h"
 #include "fused.cuh"
+#include "ct.cuh"
 
 static __global__ void __launch_bounds__(ECB_TPB, 5) k_ed25519_mul_base(size_t n, const u32* scalars, const u32* table, int W,
                                                                int nwin, int stride, u32* planes, unsigned long long* status) {
@@ -77,13 +78,10 @@ int dev_ed25519_build_table(ecb_ctx* ctx, DevCtx& d, int W) {
         W -= 2;
     }
 }
-// The new table is built into a local buffer and published (table, width, window count, stride together)
-// only when every step succeeded; any failure frees it and leaves the context without a table.
-static int ed25519_build_table_w(ecb_ctx* ctx, DevCtx& d, int W) {
+// Build a comb of width W into a fresh device buffer (entries `stride` words apart); the caller owns it.
+static int ed25519_build_table_raw(ecb_ctx* ctx, DevCtx& d, int W, int stride, u32** out_table, int* out_nwin) {
     const int nwin = (254 + W - 1) / W;
     const size_t ntab = (size_t)nwin << (W - 1);
-    const int stride = (int)ctx->opt_ed_stride;
-    ed_drop_table(d);
     u32* table = nullptr;
     u32* bases = nullptr;   // 2^(W i) * B per window, cached form (32 words each)
     auto build = [&]() -> int {
@@ -115,6 +113,18 @@ static int ed25519_build_table_w(ecb_ctx* ctx, DevCtx& d, int W) {
             b->cap = 0;
         }
     }
+    *out_table = table;
+    *out_nwin = nwin;
+    return ECB_OK;
+}
+// The new table is published (table, width, window count, stride together) only when every step succeeded;
+// any failure leaves the context without a table.
+static int ed25519_build_table_w(ecb_ctx* ctx, DevCtx& d, int W) {
+    const int stride = (int)ctx->opt_ed_stride;
+    ed_drop_table(d);
+    u32* table = nullptr;
+    int nwin = 0;
+    TRY(ed25519_build_table_raw(ctx, d, W, stride, &table, &nwin));
     d.ed_table = table;
     d.ed_w = W;
     d.ed_nwin = nwin;
@@ -215,6 +225,58 @@ int dev_ed25519_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32*
     } else {
         FinEdXY fin{planes, n, d_out};
         rc = launch_batch_inv<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
+    }
+    prof_mark(ctx, d, s, 2);
+    return rc;
+}
+
+
+// ---- constant-time fixed base (ct.cuh): secret scalars ------------------------------------------------
+// Persistent blocks: each stages the 48 KB W = 4 comb into shared memory once, then its threads walk the batch.
+static __global__ void __launch_bounds__(ECB_TPB, 4) k_ed25519_mul_base_ct(size_t n, const u32* scalars, const u32* table, u32* planes,
+                                                                       unsigned long long* status) {
+    __shared__ u32 tbl[ECB_CT_ED_WORDS];
+    for (int i = threadIdx.x; i < ECB_CT_ED_WORDS / 4; i += ECB_TPB)
+        reinterpret_cast<uint4*>(tbl)[i] = reinterpret_cast<const uint4*>(table)[i];
+    __syncthreads();
+    const size_t T = (size_t)gridDim.x * ECB_TPB;
+    for (size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x; idx < n; idx += T)
+        ed25519_mul_base_ct_body<false>(idx, n, scalars, tbl, planes, status);
+}
+static int dev_ed25519_ct_table(ecb_ctx* ctx, DevCtx& d) {
+    if (d.ed_ct_table) return ECB_OK;
+    if (ctx->no_alloc) return set_err(ctx, ECB_ERR_NOT_READY, "constant-time Ed25519 comb not built: call ecb_warm() first");
+    u32* table = nullptr;
+    int nwin = 0;
+    TRY(ed25519_build_table_raw(ctx, d, ECB_CT_W, 24, &table, &nwin));
+    if (nwin != ECB_CT_ED_NWIN) {
+        cudaFree(table);
+        return set_err(ctx, ECB_ERR_CUDA, "constant-time comb: unexpected window count");
+    }
+    d.ed_ct_table = table;
+    return ECB_OK;
+}
+// k * B for secret k: masked scans of a shared-memory comb, Fermat inversion.  ~9x the cost of the variable-time form.
+int dev_ed25519_mul_base_ct(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, bool compressed, cudaStream_t s,
+                            size_t enc_stride_words) {
+    TRY(dev_ed25519_ct_table(ctx, d));
+    TRY(reset_status(ctx, d, s));
+    TRY(ensure(ctx, d.cur->planes, n * 3 * 8 * sizeof(u32)));
+    TRY(ensure(ctx, d.cur->pf, n * 8 * sizeof(u32)));
+    u32* planes = (u32*)d.cur->planes.p;
+    unsigned g = persistent_grid(d, k_ed25519_mul_base_ct, n);
+    prof_mark(ctx, d, s, 0);
+    k_ed25519_mul_base_ct<<<g, ECB_TPB, 0, s>>>(n, d_k, d.ed_ct_table, planes, d.cur->d_status);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    prof_mark(ctx, d, s, 1);
+    int rc;
+    if (compressed) {
+        FinEdCompressed fin{planes, n, d_out, enc_stride_words ? enc_stride_words : 8};
+        rc = launch_batch_inv_ct<F25519, FinEdCompressed>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
+    } else {
+        FinEdXY fin{planes, n, d_out};
+        rc = launch_batch_inv_ct<F25519, FinEdXY>(ctx, d, n, planes, (u32*)d.cur->pf.p, fin, s);
     }
     prof_mark(ctx, d, s, 2);
     return rc;
@@ -325,18 +387,30 @@ static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_sign_finish(size_t n
     if (idx < n) ed25519_sign_finish_body(idx, sig, a_pub, msgs, off, a_red, r_red);
 }
 // SecretKey::public_key (ed25519.rs:81 public_from_seed): seeds n x 32 -> encode_point(a B) n x 32
-int dev_ed25519_public_from_seed(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, size_t n, u32* d_pub, cudaStream_t s) {
+// The working buffers of key generation and signing hold secrets (expanded scalar a, prefix, nonce r, and the
+// projective planes of a B / r B): they are cleared on the stream before the call's last kernel retires.
+static int wipe_secrets(ecb_ctx* ctx, DevCtx& d, size_t n, cudaStream_t s) {
+    if (d.cur->aux.p) CU(cudaMemsetAsync(d.cur->aux.p, 0, d.cur->aux.cap < n * 4 * 32 ? d.cur->aux.cap : n * 4 * 32, s));
+    if (d.cur->planes.p) CU(cudaMemsetAsync(d.cur->planes.p, 0, d.cur->planes.cap < n * 96 ? d.cur->planes.cap : n * 96, s));
+    if (d.cur->pf.p) CU(cudaMemsetAsync(d.cur->pf.p, 0, d.cur->pf.cap < n * 32 ? d.cur->pf.cap : n * 32, s));
+    return ECB_OK;
+}
+static int ed_secret_mul_base(ecb_ctx* ctx, DevCtx& d, bool ct, const u32* k, size_t n, u32* out, cudaStream_t s, size_t stride_words) {
+    return ct ? dev_ed25519_mul_base_ct(ctx, d, k, n, out, true, s, stride_words) : dev_ed25519_mul_base(ctx, d, k, n, out, true, s, stride_words);
+}
+int dev_ed25519_public_from_seed(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, size_t n, u32* d_pub, cudaStream_t s, bool ct) {
     TRY(ensure(ctx, d.cur->aux, n * 4 * 32));
     u32* a = (u32*)d.cur->aux.p;
     u32* prefix = a + n * 8;
     k_ed25519_expand<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_seeds, a, prefix);
     ctx->launches++;
     CU(cudaGetLastError());
-    return dev_ed25519_mul_base(ctx, d, a, n, d_pub, true, s, 0);
+    TRY(ed_secret_mul_base(ctx, d, ct, a, n, d_pub, s, 0));
+    return wipe_secrets(ctx, d, n, s);
 }
 // Keypair::sign / sign_with_public (ed25519.rs:94): d_pub may be null (SecretKey::sign, :112: A is derived first)
 int dev_ed25519_sign(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, const unsigned char* d_pub, const unsigned char* d_msgs,
-                     const unsigned long long* d_off, size_t n, unsigned char* d_sig, cudaStream_t s) {
+                     const unsigned long long* d_off, size_t n, unsigned char* d_sig, cudaStream_t s, bool ct) {
     TRY(ensure(ctx, d.cur->aux, n * 4 * 32));
     u32* a = (u32*)d.cur->aux.p;
     u32* prefix = a + n * 8;
@@ -346,15 +420,15 @@ int dev_ed25519_sign(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, cons
     ctx->launches++;
     CU(cudaGetLastError());
     if (!d_pub) {
-        TRY(dev_ed25519_mul_base(ctx, d, a, n, pub_tmp, true, s, 0));
+        TRY(ed_secret_mul_base(ctx, d, ct, a, n, pub_tmp, s, 0));
         d_pub = (const unsigned char*)pub_tmp;
     }
     k_ed25519_sign_nonce<<<grid_for(n), ECB_TPB, 0, s>>>(n, prefix, d_msgs, d_off, r);
     ctx->launches++;
     CU(cudaGetLastError());
-    TRY(dev_ed25519_mul_base(ctx, d, r, n, (u32*)d_sig, true, s, 16));   // R = encode_point(r B) into bytes [0, 32) of each signature
+    TRY(ed_secret_mul_base(ctx, d, ct, r, n, (u32*)d_sig, s, 16));   // R = encode_point(r B) into bytes [0, 32) of each signature
     k_ed25519_sign_finish<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_sig, d_pub, d_msgs, d_off, a, r);
     ctx->launches++;
     CU(cudaGetLastError());
-    return ECB_OK;
+    return wipe_secrets(ctx, d, n, s);
 }

@@ -125,16 +125,27 @@ int ecb_ed25519_verify(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* msgs, 
 
 /* ---- X25519 / X448 --------------------------------------------------------------------- */
 
-/* ---- Ed25519 key generation and signing.  NOT constant-time (see the note at the top of
- * this header and DESIGN.md section 8): the comb kernel addresses its table by secret digits.
+/* ---- Ed25519 key generation and signing -------------------------------------------------
  * SecretKey::public_key (src/protocol/ed25519.rs:81 public_from_seed, :61 expand_secret): seeds n x 32 bytes ->
  * pub n x 32 bytes = encode_point([clamp(SHA-512(seed)[0..32]) mod l] B).
  * Keypair::sign / sign_with_public (ed25519.rs:94-110; SecretKey::sign :112 when pub is NULL: A is derived on
  * the device first): r = SHA-512(prefix || M) mod l, R = encode_point(r B), k = SHA-512(R || A || M) mod l,
- * S = r + k a mod l; sig: n x 64 bytes R || S.  Messages as in ecb_ed25519_verify (concatenated, n + 1 offsets). */
+ * S = r + k a mod l; sig: n x 64 bytes R || S.  Messages as in ecb_ed25519_verify (concatenated, n + 1 offsets).
+ *
+ * The entry points under the reference's names are CONSTANT-TIME with respect to the seeds, as the reference is
+ * (select_from_table scans every entry, curve25519.rs:862-869; Fermat inverses :155-200): a B and r B come from
+ * csrc/ct.cuh — a 48 KB comb in shared memory, every window reads all 8 entries and keeps one by masks, the affine
+ * conversion is Montgomery's trick around the fixed Fermat chain — and the work buffers that held key material
+ * are cleared on the stream.  The *_vartime entry points are the fast forms (the large comb indexed by the
+ * scalar's digits, variable-time safegcd; ~7x the throughput): same bytes, for callers whose GPU is not shared
+ * with an adversary.  ecb_ed25519_mul_base_ct is Point::mul_base itself for secret scalars. */
 int ecb_ed25519_public_from_seed(ecb_ctx* ctx, const uint8_t* seeds, size_t n, uint8_t* pub);
 int ecb_ed25519_sign(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
                      uint8_t* sig);
+int ecb_ed25519_public_from_seed_vartime(ecb_ctx* ctx, const uint8_t* seeds, size_t n, uint8_t* pub);
+int ecb_ed25519_sign_vartime(ecb_ctx* ctx, const uint8_t* seeds, const uint8_t* pub, const uint8_t* msgs, const uint64_t* msg_off, size_t n,
+                             uint8_t* sig);
+int ecb_ed25519_mul_base_ct(ecb_ctx* ctx, const uint8_t* k_le, size_t n, uint8_t* xy_le, size_t* bad_index);
 
 /* protocol::x25519::x25519(scalar, u)   (src/protocol/x25519.rs:36): clamps inside, masks bit 255
  * of u, accepts non-canonical u, returns 0 for low-order inputs.  k, u, out: n x 32 B. */
@@ -219,6 +230,9 @@ int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int dev_index, const void
 int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_d_be, const void* d_k_be, const void* d_z_be,
                               size_t n, void* d_rs_be, void* d_ok, void* stream);
 int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, size_t n, void* d_pub, void* stream);
+int ecb_ed25519_public_from_seed_vartime_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, size_t n, void* d_pub, void* stream);
+int ecb_ed25519_sign_vartime_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off,
+                                 size_t n, void* d_sig, void* stream);
 int ecb_ed25519_sign_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, const void* d_pub, const void* d_msgs, const void* d_msg_off,
                          size_t n, void* d_sig, void* stream);
 int ecb_x448_dev(ecb_ctx* ctx, int dev_index, const void* d_k, const void* d_u, size_t n, void* d_out, void* stream);

@@ -4,6 +4,7 @@
 // batch inversion -> wire bytes).
 #define ECB_HOSTSIM 1
 #include "../../eccoxide_b200/csrc/kernels.cuh"
+#include "../../eccoxide_b200/csrc/ct.cuh"
 #include <vector>
 #include <string.h>
 using namespace ecb;
@@ -38,6 +39,22 @@ unsigned long long hs_ed25519_mul_base(const u32* k, size_t n, int W, const u32*
     } else {
         FinEdXY fin{planes.data(), n, out};
         for (size_t t = 0; t < T; t++) batch_inv_body<F25519>(t, T, n, planes.data(), pf.data(), fin);
+    }
+    return st;
+}
+
+// constant-time form (ct.cuh): masked scans of the W = 4 comb, Fermat inversion in the batch inversion
+unsigned long long hs_ed25519_mul_base_ct(const u32* k, size_t n, const u32* table_w4, u32* out, int compressed) {
+    std::vector<u32> planes(3 * 8 * n), pf(8 * n);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) ed25519_mul_base_ct_body<false>(i, n, k, table_w4, planes.data(), &st);
+    size_t T = inv_threads(n);
+    if (compressed) {
+        FinEdCompressed fin{planes.data(), n, out};
+        for (size_t t = 0; t < T; t++) batch_inv_body<F25519, FinEdCompressed, true>(t, T, n, planes.data(), pf.data(), fin);
+    } else {
+        FinEdXY fin{planes.data(), n, out};
+        for (size_t t = 0; t < T; t++) batch_inv_body<F25519, FinEdXY, true>(t, T, n, planes.data(), pf.data(), fin);
     }
     return st;
 }

@@ -822,6 +822,31 @@ def test_ed25519_keygen_and_sign(ctx, golden):
     tampered = [m + b"!" for m in msgs]
     assert not ctx.ed25519_verify(pub, tampered, sig).any()
     assert ctx.ed25519_public_from_seed(np.zeros((0, 32), dtype=np.uint8)).shape == (0, 32)
+    # the calls above ran the constant-time kernels (the entry points under the reference's names); the
+    # *_vartime forms — large comb indexed by the digits, safegcd — must give the same bytes
+    assert np.array_equal(ctx.ed25519_public_from_seed(sd, vartime=True), pub)
+    assert np.array_equal(ctx.ed25519_sign(sd, msgs, pub=pub, vartime=True), sig)
+    assert np.array_equal(ctx.ed25519_sign(sd, msgs, vartime=True), sig)
+
+
+def test_ed25519_mul_base_constant_time_kernel(ctx, coracle, golden):
+    """ecb_ed25519_mul_base_ct (csrc/ct.cuh: masked scans of a 48 KB comb staged in shared memory, Fermat
+    inversion): Point::mul_base bytes for the reference's edge scalars and a 2^16 batch, 100 % against the C oracle;
+    a non-canonical scalar is refused with its index as in the variable-time form."""
+    from eccoxide_b200 import EccBatchError
+
+    g = rng(0xC7)
+    kb = np.concatenate([rows([v.to_bytes(32, "little") for v in ed_edge_scalars(golden)]), scalars_mod(g, (1 << 16) - 7, R.L25519, 32, "little")])
+    got = ctx.ed25519_mul_base_ct(kb)
+    assert np.array_equal(got, coracle.ed25519_mul_base(kb, threads(coracle)))
+    assert np.array_equal(got[:5000], ctx.ed25519_mul_base(kb[:5000]))
+    for n in (1, 127, 129):
+        assert np.array_equal(ctx.ed25519_mul_base_ct(kb[:n]), got[:n])
+    bad = kb[:300].copy()
+    bad[211] = 0xFF
+    with pytest.raises(EccBatchError) as e:
+        ctx.ed25519_mul_base_ct(bad)
+    assert e.value.code == -3 and e.value.bad_index == 211
 
 
 @pytest.mark.parametrize("curve", ["p256r1", "p384r1"])

@@ -21,7 +21,7 @@ def hs():
     subprocess.check_call(["make", "-s", "-j4", "-C", HS])
     f = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_fields.so"))
     k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
-    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_ecdsa_verify"):
+    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_ecdsa_verify"):
         getattr(k, fn).restype = ctypes.c_ulonglong
     return f, k
 
@@ -142,6 +142,28 @@ def test_ed25519_mul_base_and_table(hs, golden, coracle):
     bad[3] = np.frombuffer(R.L25519.to_bytes(32, "little"), dtype=np.uint8)
     st = k.hs_ed25519_mul_base(p(bad), ctypes.c_size_t(n), W, p(table), p(out), 0)
     assert st == (3 << 8) | 1
+
+
+def test_ed25519_mul_base_constant_time_form(hs, golden, coracle):
+    """ct.cuh: every window scans all 8 entries of the W = 4 comb with masks (the reference's select_from_table,
+    curve25519.rs:862-869) and the inversion is the Fermat chain — same bytes as the variable-time comb, on the
+    reference's edge scalars (0, 1, l - 1, window boundaries) and random ones, affine and compressed."""
+    _, k = hs
+    g = rng(21)
+    kb = np.concatenate([rows([v.to_bytes(32, "little") for v in ed_edge_scalars(golden)]), scalars_mod(g, 60, R.L25519, 32, "little")])
+    n = kb.shape[0]
+    table = np.zeros((k.hs_ed25519_table_entries(4), 24), dtype=np.uint32)
+    assert table.shape[0] == 64 * 8
+    k.hs_ed25519_build_table(4, p(table))
+    out = np.zeros((n, 64), dtype=np.uint8)
+    st = k.hs_ed25519_mul_base_ct(p(kb), ctypes.c_size_t(n), p(table), p(out), 0)
+    exp = coracle.ed25519_mul_base(kb)
+    assert st == 2**64 - 1 and np.array_equal(out, exp)
+    enc = np.zeros((n, 32), dtype=np.uint8)
+    k.hs_ed25519_mul_base_ct(p(kb), ctypes.c_size_t(n), p(table), p(enc), 1)
+    want = exp[:, 32:].copy()
+    want[:, 31] |= (exp[:, 0] & 1) << 7
+    assert np.array_equal(enc, want)
 
 
 def test_x25519_base_via_comb(hs, golden, coracle):
