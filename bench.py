@@ -89,6 +89,11 @@ ORDERS = {   # group orders: scalars are 64 uniform bytes reduced mod the order 
 
 def executed_mac32(name, ctx, n):
     base = name.replace("_2p16", "")
+    if base in ("ed25519_keygen", "ed25519_sign"):   # constant-time comb: 64 windows x 7 M, Fermat chain shared by 32 elements, 5 M affine
+        return (64 * 7 + 5) * 72 + (254 * 44 + 11 * 72) // 32
+    if base == "p256_ecdsa_sign":                    # 65 complete additions (12 M + 2 m_b), Fermat chains in GF(p) and GF(n) shared by 32 elements
+        return 65 * 14 * 64 + 8 * 64 + 2 * (256 * 36 + 128 * 64) // 32 + 5 * 136
+    base = base.replace("_vartime", "")
     if base in ("ed25519_mul_base", "x25519_base", "ed25519_keygen", "ed25519_sign"):
         nwin = ctx.get_info("ed25519_comb_windows") or 11
         comb = 1 + 7 * (nwin - 2) + 6              # first window: one product; last: no T
@@ -114,9 +119,12 @@ WORKLOADS = {
     "ed25519_verify": (20, 128, 1, "north star: batched ed25519 verify (k = SHA-512(R||A||M) mod l precomputed by the caller)"),
     "p256_mul_base": (20, 32, 65, "north star: fixed-base p256r1 Point::mul_base (comb)"),
     "bls12_381_g1_mul_base": (20, 32, 97, "north star: fixed-base BLS12-381 G1 Point::mul_base (comb)"),
-    "p256_ecdsa_sign": (20, 96, 65, "SURVEY 8 f.3: ecdsa::sign_hashed on p256r1 (secret, nonce, message scalar -> r || s)"),
-    "ed25519_keygen": (20, 32, 32, "SURVEY 8 f.3: ed25519 SecretKey::public_key (seed -> public key)"),
-    "ed25519_sign": (20, 128, 64, "SURVEY 8 f.3: ed25519 Keypair::sign of 64-byte messages (seed, public key, message -> R || S)"),
+    "p256_ecdsa_sign": (20, 96, 65, "SURVEY 8 f.3: ecdsa::sign_hashed on p256r1 (secret, nonce, message scalar -> r || s), constant-time kernels"),
+    "ed25519_keygen": (20, 32, 32, "SURVEY 8 f.3: ed25519 SecretKey::public_key (seed -> public key), constant-time kernels"),
+    "ed25519_sign": (20, 128, 64, "SURVEY 8 f.3: ed25519 Keypair::sign of 64-byte messages (seed, public key, message -> R || S), constant-time kernels"),
+    "p256_ecdsa_sign_vartime": (20, 96, 65, "SURVEY 8 f.3: ecdsa::sign_hashed on p256r1, the fast variable-time form (ecb_ecdsa_sign_hashed_vartime)"),
+    "ed25519_keygen_vartime": (20, 32, 32, "SURVEY 8 f.3: ed25519 SecretKey::public_key, the fast variable-time form"),
+    "ed25519_sign_vartime": (20, 128, 64, "SURVEY 8 f.3: ed25519 Keypair::sign of 64-byte messages, the fast variable-time form"),
     "p256_decompress": (20, 33, 65, "SURVEY 8 f.1: PointAffine::decompress (SEC1 point decompression) on p256r1"),
     "bls12_381_g1_from_compressed": (20, 48, 97, "SURVEY 8 f.1: BLS12-381 G1 from_compressed with the prime-order-subgroup check"),
 }
@@ -129,11 +137,13 @@ WARM = {"ed25519_mul_base": ("ed25519_mul_base", None), "ed25519_mul": ("ed25519
         "p256_mul_base": ("wei_mul_base", "p256r1"), "bls12_381_g1_mul_base": ("wei_mul_base", "bls12_381_g1"),
         "p256_ecdsa_verify": ("ecdsa_verify_hashed", "p256r1"), "p256_ecdsa_sign": ("ecdsa_sign_hashed", "p256r1"),
         "ed25519_keygen": ("ed25519_public_from_seed", None), "ed25519_sign": ("ed25519_sign", None),
+        "ed25519_keygen_vartime": ("ed25519_public_from_seed_vartime", None), "ed25519_sign_vartime": ("ed25519_sign_vartime", None),
+        "p256_ecdsa_sign_vartime": ("ecdsa_sign_hashed_vartime", "p256r1"),
         "p256_decompress": ("wei_decompress", "p256r1"), "bls12_381_g1_from_compressed": ("bls12_381_g1_from_compressed", None)}
 
 
 def work_of(name):
-    return WORK[name.replace("_2p16", "")]
+    return WORK[name.replace("_2p16", "").replace("_vartime", "")]
 
 
 # ---- synthetic inputs (seeded) ----------------------------------------------------
@@ -158,7 +168,7 @@ def make_inputs(name, n, ctx, seed):
     """Host numpy inputs for one batch of `name`.  Points are produced by the library's own fixed-base
     entry points (outside any timed region) and spot-checked against the oracle by the caller."""
     g = np.random.Generator(np.random.Philox(seed))
-    base = name.replace("_2p16", "")
+    base = name.replace("_2p16", "").replace("_vartime", "")
     uniq = min(n, 1 << 14)
     tile = lambda a: np.ascontiguousarray(np.tile(a, (n // a.shape[0], 1)))
     if base == "ed25519_mul_base":
@@ -289,10 +299,16 @@ def dev_launch(ctx, name, ins, outs, n, stream):
         ctx.dev_call("ecb_ecdsa_verify_hashed_dev", 0, 0, p[0], p[1], p[2], n, o[0], stream)
     elif base == "p256_ecdsa_sign":
         ctx.dev_call("ecb_ecdsa_sign_hashed_dev", 0, 0, p[0], p[1], p[2], n, o[0], o[1], stream)
+    elif base == "p256_ecdsa_sign_vartime":
+        ctx.dev_call("ecb_ecdsa_sign_hashed_vartime_dev", 0, 0, p[0], p[1], p[2], n, o[0], o[1], stream)
     elif base == "ed25519_keygen":
         ctx.dev_call("ecb_ed25519_public_from_seed_dev", 0, p[0], n, o[0], stream)
+    elif base == "ed25519_keygen_vartime":
+        ctx.dev_call("ecb_ed25519_public_from_seed_vartime_dev", 0, p[0], n, o[0], stream)
     elif base == "ed25519_sign":
         ctx.dev_call("ecb_ed25519_sign_dev", 0, p[0], p[1], p[2], _msg_offsets(ins[2]).data_ptr(), n, o[0], stream)
+    elif base == "ed25519_sign_vartime":
+        ctx.dev_call("ecb_ed25519_sign_vartime_dev", 0, p[0], p[1], p[2], _msg_offsets(ins[2]).data_ptr(), n, o[0], stream)
     elif base == "p256_decompress":
         ctx.dev_call("ecb_wei_decompress_dev", 0, 0, p[0], p[1], n, o[0], o[1], stream)
     elif base == "bls12_381_g1_from_compressed":
@@ -324,12 +340,14 @@ def host_call(ctx, name, ins, outs=None):
         return list(ctx.wei_mul_base("p256r1" if base == "p256_mul_base" else "bls12_381_g1", ins[0], out=o[0], out_inf=o[1]))
     if base == "p256_ecdsa_verify":
         return [ctx.ecdsa_verify_hashed("p256r1", ins[0], ins[1], ins[2], out=o[0])]
+    vt = base.endswith("_vartime")
+    base = base.replace("_vartime", "")
     if base == "p256_ecdsa_sign":
-        return list(ctx.ecdsa_sign_hashed("p256r1", ins[0], ins[1], ins[2], out=o[0], out_ok=o[1]))
+        return list(ctx.ecdsa_sign_hashed("p256r1", ins[0], ins[1], ins[2], out=o[0], out_ok=o[1], vartime=vt))
     if base == "ed25519_keygen":
-        return [ctx.ed25519_public_from_seed(ins[0], out=o[0])]
+        return [ctx.ed25519_public_from_seed(ins[0], out=o[0], vartime=vt)]
     if base == "ed25519_sign":
-        return [ctx.ed25519_sign_fixed(ins[0], ins[2], pub=ins[1], out=o[0])]
+        return [ctx.ed25519_sign_fixed(ins[0], ins[2], pub=ins[1], out=o[0], vartime=vt)]
     if base == "p256_decompress":
         return list(ctx.wei_decompress("p256r1", ins[0], ins[1], out=o[0], out_ok=o[1]))
     if base == "bls12_381_g1_from_compressed":
@@ -338,7 +356,7 @@ def host_call(ctx, name, ins, outs=None):
 
 
 def oracle_call(C, name, ins, nthreads):
-    base = name.replace("_2p16", "")
+    base = name.replace("_2p16", "").replace("_vartime", "")
     if base == "ed25519_mul_base":
         return [C.ed25519_mul_base(ins[0], nthreads)]
     if base == "ed25519_mul":
@@ -492,7 +510,7 @@ def measure_device(torch, ctx, name, n, steps, warmup, seed, dist=None, min_s=MI
         hb = ins_h if b == 0 else [np.roll(a, b * 977, axis=0) for a in ins_h]   # same elements, rotated: distinct buffers, same validity
         bufs.append([torch.from_numpy(a).cuda() for a in hb])
     base = name.replace("_2p16", "")
-    outs = [torch.empty((n, w), dtype=torch.uint8, device="cuda") for w in OUT_SHAPES[base]]
+    outs = [torch.empty((n, w), dtype=torch.uint8, device="cuda") for w in OUT_SHAPES[base.replace("_vartime", "")]]
     stream = torch.cuda.current_stream().cuda_stream
     op, curve = WARM[base]
     ctx.warm(op, n, curve)
@@ -566,7 +584,7 @@ def measure_e2e(torch, ctx, name, n, steps, inner, ins_h, dist=None):
     """Host-API throughput with pinned host buffers (the call a user of the C ABI makes): every pass copies
     its inputs host -> device and its results device -> host inside the timed region."""
     pinned = [torch.from_numpy(a).pin_memory().numpy() for a in ins_h]
-    base = name.replace("_2p16", "")
+    base = name.replace("_2p16", "").replace("_vartime", "")
     pouts = [torch.empty((n, w), dtype=torch.uint8).pin_memory().numpy() for w in OUT_SHAPES[base]]
     for _ in range(3):
         host_call(ctx, name, pinned, pouts)
@@ -732,14 +750,15 @@ def run_workload(torch, ctx, name, steps, warmup, world, rank, dist, peak, probe
         from oracle import coracle as C
 
         C.build()
-        m = min(PARITY_SAMPLE, n)
+        # key generation / signing are checked by the big-integer Python oracle (the C oracle carries no SHA-512): smaller sample
+        m = min(256 if ("keygen" in name or "sign" in name) else PARITY_SAMPLE, n)
         ins_last = [np.roll(a, r["last"] * 977, axis=0) if r["last"] else a for a in r["ins_h"]]
         exp = oracle_call(C, name, [a[:m] for a in ins_last], os.cpu_count() or 1)
         parity = all(np.array_equal(np.asarray(g)[:m].reshape(m, -1), np.asarray(e).astype(np.uint8).reshape(m, -1)) for g, e in zip(r["got"], exp))
         exp2 = oracle_call(C, name, [a[:m] for a in r["ins_h"]], os.cpu_count() or 1)
         parity = parity and all(np.array_equal(np.asarray(g[:m]).astype(np.uint8).reshape(m, -1), np.asarray(e).astype(np.uint8).reshape(m, -1)) for g, e in zip(e2e_out, exp2))
     res["parity_check"] = parity
-    res["parity_sample"] = "%d elements of the last timed device pass and of the last e2e pass, bit-exact vs the C oracle" % min(PARITY_SAMPLE, n) if check else None
+    res["parity_sample"] = "%d elements of the last timed device pass and of the last e2e pass, bit-exact vs the oracle" % m if check else None
     static = load_json(os.path.join(ROOT, "profiles", "ncu_static.json")).get(name) or {}
     peaks = load_json(os.path.join(ROOT, "MEASURED_PEAKS.json"))
     hbm_peak = peaks.get("hbm_gbs")

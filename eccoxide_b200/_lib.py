@@ -78,6 +78,9 @@ SIGNATURES = {
     "ecb_ed25519_mul_base_ct": (_int, [_vp, _vp, _sz, _vp, _szp]),
     "ecb_ed25519_sign_dev": (_int, [_vp, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_sign_hashed": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ecb_ecdsa_sign_hashed_vartime": (_int, [_vp, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "ecb_ecdsa_sign_hashed_vartime_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
+    "ecb_ecdsa_sign_vartime": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_ecdsa_sign_hashed_dev": (_int, [_vp, _int, _int, _vp, _vp, _vp, _sz, _vp, _vp, _vp]),
     "ecb_ecdsa_sign": (_int, [_vp, _int, _int, _vp, _vp, _vp, _vp, _sz, _vp, _vp]),
     "ecb_warm": (_int, [_vp, ctypes.c_char_p, _int, _sz]),

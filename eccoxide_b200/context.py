@@ -251,7 +251,7 @@ class Context:
         self._check(self._lib.ecb_wei_mul_base(self._ctx, cid, _p(k), n, _p(out), _p(inf), ctypes.byref(bad)), bad)
         return out, inf.astype(bool)
 
-    def ecdsa_sign_hashed(self, curve, d_be, k_be, z_be, out=None, out_ok=None):
+    def ecdsa_sign_hashed(self, curve, d_be, k_be, z_be, out=None, out_ok=None, vartime=False):
         """ecdsa::sign_hashed over a batch (not constant-time): (r || s rows, present)."""
         cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
         sb = SCALAR_BYTES[cid]
@@ -263,11 +263,13 @@ class Context:
             raise ValueError("count mismatch")
         out = _out(out, (n, 2 * sb))
         ok = _out(out_ok, (n,))
-        self._check(self._lib.ecb_ecdsa_sign_hashed(self._ctx, cid, _p(d), _p(k), _p(z), n, _p(out), _p(ok)))
+        fn = self._lib.ecb_ecdsa_sign_hashed_vartime if vartime else self._lib.ecb_ecdsa_sign_hashed
+        self._check(fn(self._ctx, cid, _p(d), _p(k), _p(z), n, _p(out), _p(ok)))
         return out, ok.astype(bool)
 
-    def ecdsa_sign(self, curve, d_be, k_be, msgs, hash_bits=None, out=None, out_ok=None):
-        """ecdsa::sign on raw, ragged messages (hash on the device; not constant-time): (r || s rows, present)."""
+    def ecdsa_sign(self, curve, d_be, k_be, msgs, hash_bits=None, out=None, out_ok=None, vartime=False):
+        """ecdsa::sign on raw, ragged messages (hash on the device): (r || s rows, present).  Constant-time in the secret
+        and the nonce by default; vartime=True is the fast form."""
         cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
         sb = SCALAR_BYTES[cid]
         d = _rows(d_be, sb, "d_be")
@@ -282,7 +284,8 @@ class Context:
         blob = np.frombuffer(b"".join(bytes(m) for m in msgs) + b"\0", dtype=np.uint8)
         out = _out(out, (n, 2 * sb))
         ok = _out(out_ok, (n,))
-        self._check(self._lib.ecb_ecdsa_sign(self._ctx, cid, int(hash_bits), _p(d), _p(k), _p(blob), _p(off), n, _p(out), _p(ok)))
+        fn = self._lib.ecb_ecdsa_sign_vartime if vartime else self._lib.ecb_ecdsa_sign
+        self._check(fn(self._ctx, cid, int(hash_bits), _p(d), _p(k), _p(blob), _p(off), n, _p(out), _p(ok)))
         return out, ok.astype(bool)
 
     def wei_decompress(self, curve, x_be, sign, out=None, out_ok=None):

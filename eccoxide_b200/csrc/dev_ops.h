@@ -49,14 +49,17 @@ int dev_ecdsa_msgs_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const unsigned 
                         const u32* d_rs, size_t n, unsigned char* d_ok, cudaStream_t s);
 int dev_ecdsa_msgs_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_q, const unsigned char* d_msgs, const unsigned long long* d_off, int hash,
                         const u32* d_rs, size_t n, unsigned char* d_ok, cudaStream_t s);
+// ct: constant-time k G and k^-1 (ct.cuh); false = the fast variable-time forms
+int dev_wei_mul_base_ct_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_mul_base_ct_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
 int dev_ecdsa_sign_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k, const u32* d_z, size_t n, u32* d_rs, unsigned char* d_ok,
-                        cudaStream_t s);
+                        cudaStream_t s, bool ct);
 int dev_ecdsa_sign_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k, const u32* d_z, size_t n, u32* d_rs, unsigned char* d_ok,
-                        cudaStream_t s);
+                        cudaStream_t s, bool ct);
 int dev_ecdsa_sign_msgs_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k, const unsigned char* d_msgs, const unsigned long long* d_off,
-                             int hash, size_t n, u32* d_rs, unsigned char* d_ok, cudaStream_t s);
+                             int hash, size_t n, u32* d_rs, unsigned char* d_ok, cudaStream_t s, bool ct);
 int dev_ecdsa_sign_msgs_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_d, const u32* d_k, const unsigned char* d_msgs, const unsigned long long* d_off,
-                             int hash, size_t n, u32* d_rs, unsigned char* d_ok, cudaStream_t s);
+                             int hash, size_t n, u32* d_rs, unsigned char* d_ok, cudaStream_t s, bool ct);
 int dev_imad_probe(ecb_ctx* ctx, DevCtx& d, int variant, int iters, double* macs_per_s, double* ms_out);
 int dev_latency_probe(ecb_ctx* ctx, DevCtx& d, int variant, int threads, int reps, double* cycles, double* mhz);
 int dev_fieldmul_probe(ecb_ctx* ctx, DevCtx& d, int num, int den, int blocks_per_sm, int reps, double* muls_per_s, double* check);

@@ -731,8 +731,18 @@ int ecb_wei_mul_base(ecb_ctx* ctx, int curve, const uint8_t* k_be, size_t n, uin
                            return dev_wei_mul_base(ctx, d, curve, (const u32*)in[0], cn, (u32*)o[0], (unsigned char*)o[1], s);
                        });
 }
+static int ecdsa_sign_hashed_impl(ecb_ctx* ctx, int curve, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n, uint8_t* rs_be,
+                                  uint8_t* ok, bool ct);
 int ecb_ecdsa_sign_hashed(ecb_ctx* ctx, int curve, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n, uint8_t* rs_be,
                           uint8_t* ok) {
+    return ecdsa_sign_hashed_impl(ctx, curve, d_be, k_be, z_be, n, rs_be, ok, true);
+}
+int ecb_ecdsa_sign_hashed_vartime(ecb_ctx* ctx, int curve, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n, uint8_t* rs_be,
+                                  uint8_t* ok) {
+    return ecdsa_sign_hashed_impl(ctx, curve, d_be, k_be, z_be, n, rs_be, ok, false);
+}
+static int ecdsa_sign_hashed_impl(ecb_ctx* ctx, int curve, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n, uint8_t* rs_be,
+                                  uint8_t* ok, bool ct) {
     if (!ctx) return ECB_ERR_CUDA;
     size_t fb, sb;
     if (curve_sizes(curve, fb, sb) || curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
@@ -741,15 +751,25 @@ int ecb_ecdsa_sign_hashed(ecb_ctx* ctx, int curve, const uint8_t* d_be, const ui
                        [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
                            if (curve == ECB_CURVE_P256R1)
                                return dev_ecdsa_sign_p256(ctx, d, (const u32*)in[0], (const u32*)in[1], (const u32*)in[2], cn, (u32*)o[0],
-                                                          (unsigned char*)o[1], s);
+                                                          (unsigned char*)o[1], s, ct);
                            return dev_ecdsa_sign_p384(ctx, d, (const u32*)in[0], (const u32*)in[1], (const u32*)in[2], cn, (u32*)o[0],
-                                                      (unsigned char*)o[1], s);
+                                                      (unsigned char*)o[1], s, ct);
                        });
 }
 // ecdsa::sign on raw messages (ragged input): the chunk loop of ecb_ecdsa_verify; per chunk the slot holds
 // d in in[0], k in in[1], the offsets in in[2], z (device-made) in in[3], the message bytes in `scratch`.
+static int ecdsa_sign_impl(ecb_ctx* ctx, int curve, int hash, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* msgs, const uint64_t* msg_off,
+                           size_t n, uint8_t* rs_be, uint8_t* ok, bool ct);
 int ecb_ecdsa_sign(ecb_ctx* ctx, int curve, int hash, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* msgs, const uint64_t* msg_off,
                    size_t n, uint8_t* rs_be, uint8_t* ok) {
+    return ecdsa_sign_impl(ctx, curve, hash, d_be, k_be, msgs, msg_off, n, rs_be, ok, true);
+}
+int ecb_ecdsa_sign_vartime(ecb_ctx* ctx, int curve, int hash, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* msgs, const uint64_t* msg_off,
+                           size_t n, uint8_t* rs_be, uint8_t* ok) {
+    return ecdsa_sign_impl(ctx, curve, hash, d_be, k_be, msgs, msg_off, n, rs_be, ok, false);
+}
+static int ecdsa_sign_impl(ecb_ctx* ctx, int curve, int hash, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* msgs, const uint64_t* msg_off,
+                           size_t n, uint8_t* rs_be, uint8_t* ok, bool ct) {
     if (!ctx) return ECB_ERR_CUDA;
     size_t fb, sb;
     if (curve_sizes(curve, fb, sb) || curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
@@ -792,10 +812,10 @@ int ecb_ecdsa_sign(ecb_ctx* ctx, int curve, int hash, const uint8_t* d_be, const
                 const unsigned char* d_msgs = (const unsigned char*)sl.scratch.p - msg_off[c0];
                 if (curve == ECB_CURVE_P256R1)
                     TRY(dev_ecdsa_sign_msgs_p256(ctx, d, (const u32*)sl.in[0].p, (const u32*)sl.in[1].p, d_msgs, (const unsigned long long*)sl.in[2].p,
-                                                 hash, cn, (u32*)sl.out[0].p, (unsigned char*)sl.out[1].p, sl.stream));
+                                                 hash, cn, (u32*)sl.out[0].p, (unsigned char*)sl.out[1].p, sl.stream, ct));
                 else
                     TRY(dev_ecdsa_sign_msgs_p384(ctx, d, (const u32*)sl.in[0].p, (const u32*)sl.in[1].p, d_msgs, (const unsigned long long*)sl.in[2].p,
-                                                 hash, cn, (u32*)sl.out[0].p, (unsigned char*)sl.out[1].p, sl.stream));
+                                                 hash, cn, (u32*)sl.out[0].p, (unsigned char*)sl.out[1].p, sl.stream, ct));
                 CU(cudaMemcpyAsync(rs_be + c0 * 2 * sb, sl.out[0].p, cn * 2 * sb, cudaMemcpyDeviceToHost, sl.stream));
                 CU(cudaMemcpyAsync(ok + c0, sl.out[1].p, cn, cudaMemcpyDeviceToHost, sl.stream));
                 sl.busy = true;
@@ -968,18 +988,26 @@ int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int di, const void* d_enc
     return dev_bls_g1_from_compressed(ctx, *d, (const u32*)d_enc, n, check_subgroup ? 1 : 0, (u32*)d_out, (unsigned char*)d_ok,
                                       (cudaStream_t)stream);
 }
-int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_d, const void* d_k, const void* d_z, size_t n, void* d_rs,
-                              void* d_ok, void* stream) {
+static int ecdsa_sign_hashed_dev_impl(ecb_ctx* ctx, int di, int curve, const void* d_d, const void* d_k, const void* d_z, size_t n, void* d_rs,
+                                      void* d_ok, void* stream, bool ct) {
     DevCtx* d = get_dev(ctx, di);
     DEV_ENTER(n);
     single_slot(d);
     if (curve == ECB_CURVE_P256R1)
         return dev_ecdsa_sign_p256(ctx, *d, (const u32*)d_d, (const u32*)d_k, (const u32*)d_z, n, (u32*)d_rs, (unsigned char*)d_ok,
-                                   (cudaStream_t)stream);
+                                   (cudaStream_t)stream, ct);
     if (curve == ECB_CURVE_P384R1)
         return dev_ecdsa_sign_p384(ctx, *d, (const u32*)d_d, (const u32*)d_k, (const u32*)d_z, n, (u32*)d_rs, (unsigned char*)d_ok,
-                                   (cudaStream_t)stream);
+                                   (cudaStream_t)stream, ct);
     return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+}
+int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int di, int curve, const void* d_d, const void* d_k, const void* d_z, size_t n, void* d_rs,
+                              void* d_ok, void* stream) {
+    return ecdsa_sign_hashed_dev_impl(ctx, di, curve, d_d, d_k, d_z, n, d_rs, d_ok, stream, true);
+}
+int ecb_ecdsa_sign_hashed_vartime_dev(ecb_ctx* ctx, int di, int curve, const void* d_d, const void* d_k, const void* d_z, size_t n, void* d_rs,
+                                      void* d_ok, void* stream) {
+    return ecdsa_sign_hashed_dev_impl(ctx, di, curve, d_d, d_k, d_z, n, d_rs, d_ok, stream, false);
 }
 static int ed25519_public_from_seed_dev_impl(ecb_ctx* ctx, int di, const void* d_seeds, size_t n, void* d_pub, void* stream, bool ct) {
     DevCtx* d = get_dev(ctx, di);
@@ -1157,7 +1185,7 @@ static const WarmOp* warm_lookup(const char* op, int curve, WarmOp& tmp) {
     else if (!strcmp(op, "wei_mul_base")) tmp = WarmOp{op, {sb, 0, 0, 0}, {2 * fb, 1}};
     else if (!strcmp(op, "wei_decompress")) tmp = WarmOp{op, {fb, 1, 0, 0}, {2 * fb, 1}};
     else if (!strcmp(op, "ecdsa_verify_hashed")) tmp = WarmOp{op, {2 * fb, sb, 2 * sb, 0}, {1, 0}};
-    else if (!strcmp(op, "ecdsa_sign_hashed")) tmp = WarmOp{op, {sb, sb, sb, 0}, {2 * sb, 1}};
+    else if (!strcmp(op, "ecdsa_sign_hashed") || !strcmp(op, "ecdsa_sign_hashed_vartime")) tmp = WarmOp{op, {sb, sb, sb, 0}, {2 * sb, 1}};
     else return nullptr;
     return &tmp;
 }
@@ -1200,6 +1228,7 @@ int ecb_warm(ecb_ctx* ctx, const char* op, int curve, size_t max_n) {
             else if (!strcmp(op, "wei_mul_base")) r = ecb_wei_mul_base_dev(ctx, di, curve, in[0], max_n, out[0], out[1], st);
             else if (!strcmp(op, "wei_decompress")) r = ecb_wei_decompress_dev(ctx, di, curve, in[0], in[1], max_n, out[0], out[1], st);
             else if (!strcmp(op, "ecdsa_verify_hashed")) r = ecb_ecdsa_verify_hashed_dev(ctx, di, curve, in[0], in[1], in[2], max_n, out[0], st);
+            else if (!strcmp(op, "ecdsa_sign_hashed_vartime")) r = ecb_ecdsa_sign_hashed_vartime_dev(ctx, di, curve, in[0], in[1], in[2], max_n, out[0], out[1], st);
             else r = ecb_ecdsa_sign_hashed_dev(ctx, di, curve, in[0], in[1], in[2], max_n, out[0], out[1], st);
             g_warming = false;
             TRY(r);

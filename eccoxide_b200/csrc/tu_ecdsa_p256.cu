@@ -7,4 +7,5 @@
 #define ECB_TU_SIGN_FN dev_ecdsa_sign_p256
 #define ECB_TU_SIGN_MSG_FN dev_ecdsa_sign_msgs_p256
 #define ECB_TU_BASE_FN dev_wei_mul_base_p256
+#define ECB_TU_BASE_CT_FN dev_wei_mul_base_ct_p256
 #include "tu_ecdsa.inc"

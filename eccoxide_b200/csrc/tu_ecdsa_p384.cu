@@ -7,4 +7,5 @@
 #define ECB_TU_SIGN_FN dev_ecdsa_sign_p384
 #define ECB_TU_SIGN_MSG_FN dev_ecdsa_sign_msgs_p384
 #define ECB_TU_BASE_FN dev_wei_mul_base_p384
+#define ECB_TU_BASE_CT_FN dev_wei_mul_base_ct_p384
 #include "tu_ecdsa.inc"

@@ -29,8 +29,10 @@
  *     Point::from_coordinate, src/curve/curve25519.rs:649) fails the whole call with
  *     ECB_ERR_NONCANONICAL_SCALAR / ECB_ERR_POINT_NOT_ON_CURVE and *bad_index = first offender
  *   - there is no CPU fallback: without a CUDA device every call fails with ECB_ERR_CUDA
- *   - NOT constant time (indexed table loads, data-dependent skips): meant for public data
- *     (verification, public scalar multiplication); see DESIGN.md
+ *   - the scalar-multiplication and verification entry points are NOT constant time (indexed table loads,
+ *     data-dependent skips): they are meant for public data.  Key generation and signing, and
+ *     ecb_ed25519_mul_base_ct, run constant-time kernels (csrc/ct.cuh) unless their *_vartime form is
+ *     called; see DESIGN.md section 8
  */
 #ifndef ECCBATCH_H
 #define ECCBATCH_H
@@ -67,7 +69,8 @@ int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out);
  * all-zero batch.  Required before *_dev calls (which never allocate), optional before host calls.
  * op: "ed25519_mul_base", "ed25519_mul", "x25519", "x25519_base", "x448", "ed25519_verify_prehashed",
  * "ed25519_public_from_seed", "ed25519_sign", "bls12_381_g1_from_compressed", and with a curve_id
- * "wei_mul", "wei_mul_base", "wei_decompress", "ecdsa_verify_hashed", "ecdsa_sign_hashed". */
+ * "wei_mul", "wei_mul_base", "wei_decompress", "ecdsa_verify_hashed", "ecdsa_sign_hashed"; the *_vartime forms of
+ * the key-generation and signing ops are named with that suffix ("ed25519_sign_vartime", ...). */
 int ecb_warm(ecb_ctx* ctx, const char* op, int curve_id, size_t max_n);
 /* What device dev_index holds now: "ed25519_comb_w", "ed25519_comb_windows", "<curve>_comb_w",
  * "<curve>_comb_windows" (0 = not built yet), "sm_count". */
@@ -169,14 +172,22 @@ int ecb_wei_mul(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, const uint8_t* 
 int ecb_wei_mul_base(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, size_t n, uint8_t* out_xy_be, uint8_t* out_inf,
                      size_t* bad_index);
 /* ecdsa::sign_hashed::<O>(&secret, &nonce, hashed) -> CtOption<Signature> (src/protocol/ecdsa.rs:165-184), batched
- * (NOT constant-time).  d_be (secret), k_be (nonce), z_be (message scalar): n x SB bytes each;
+ * (SURVEY 8 f.3).  d_be (secret), k_be (nonce), z_be (message scalar): n x SB bytes each;
  * rs_be: n x 2SB bytes r || s; ok[i] = 0 (and zero output) where the reference reports no signature: secret or
- * nonce zero, r = 0 or s = 0 - and for a non-canonical scalar (Scalar::from_bytes -> None). */
+ * nonce zero, r = 0 or s = 0 - and for a non-canonical scalar (Scalar::from_bytes -> None).
+ * Under the reference's names the secret-dependent steps are CONSTANT-TIME, as the reference's are: k G by masked
+ * scans of a shared-memory comb with the complete projective addition (csrc/ct.cuh; projective.rs:340-423, :427),
+ * k^-1 by the fixed Fermat chain, work buffers cleared afterwards.  The *_vartime forms are ~6x faster (large comb
+ * indexed by the nonce's digits, Jacobian additions that branch on exceptional cases, safegcd): same bytes. */
 int ecb_ecdsa_sign_hashed(ecb_ctx* ctx, int curve_id, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n,
                           uint8_t* rs_be, uint8_t* ok);
+int ecb_ecdsa_sign_hashed_vartime(ecb_ctx* ctx, int curve_id, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* z_be, size_t n,
+                                  uint8_t* rs_be, uint8_t* ok);
 /* ecdsa::sign::<O>(&secret, &nonce, message) (src/protocol/ecdsa.rs:192): z = O::hash_to_scalar(message) on the device
  * (hash = 256 / 384 / 512, as ecb_ecdsa_verify), then sign_hashed.  Messages concatenated, n + 1 offsets. */
 int ecb_ecdsa_sign(ecb_ctx* ctx, int curve_id, int hash, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* msgs,
+                   const uint64_t* msg_off, size_t n, uint8_t* rs_be, uint8_t* ok);
+int ecb_ecdsa_sign_vartime(ecb_ctx* ctx, int curve_id, int hash, const uint8_t* d_be, const uint8_t* k_be, const uint8_t* msgs,
                    const uint64_t* msg_off, size_t n, uint8_t* rs_be, uint8_t* ok);
 
 /* ---- wire formats either side of the Weierstrass path --------------------------------------------------
@@ -228,6 +239,8 @@ int ecb_wei_decompress_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void
 int ecb_bls12_381_g1_from_compressed_dev(ecb_ctx* ctx, int dev_index, const void* d_enc, size_t n, int check_subgroup,
                                          void* d_out_xy_be, void* d_ok, void* stream);
 int ecb_ecdsa_sign_hashed_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_d_be, const void* d_k_be, const void* d_z_be,
+                              size_t n, void* d_rs_be, void* d_ok, void* stream);
+int ecb_ecdsa_sign_hashed_vartime_dev(ecb_ctx* ctx, int dev_index, int curve_id, const void* d_d_be, const void* d_k_be, const void* d_z_be,
                               size_t n, void* d_rs_be, void* d_ok, void* stream);
 int ecb_ed25519_public_from_seed_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, size_t n, void* d_pub, void* stream);
 int ecb_ed25519_public_from_seed_vartime_dev(ecb_ctx* ctx, int dev_index, const void* d_seeds, size_t n, void* d_pub, void* stream);

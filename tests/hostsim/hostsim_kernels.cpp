@@ -206,6 +206,23 @@ static unsigned long long wei_mul_base_run(const u32* k, size_t n, int W, u32* o
     for (size_t t = 0; t < T; t++) batch_inv_body<typename C::F>(t, T, n, planes.data(), pf.data(), fin);
     return st;
 }
+// constant-time form (ct.cuh): W = 4 comb scanned with masks, complete projective additions, Fermat inversion
+template <class C>
+static unsigned long long wei_mul_base_ct_run(const u32* k, size_t n, u32* out, unsigned char* inf) {
+    constexpr int N = C::F::N;
+    std::vector<u32> table = wei_build_comb<C>(ECB_CT_W, WeiCt<C>::NWIN);
+    std::vector<u32> planes(3 * N * n), pf(N * n);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) wei_mul_base_ct_body<C>(i, n, k, table.data(), planes.data(), &st);
+    size_t T = inv_threads(n);
+    FinWeiXY<C> fin{planes.data(), n, out, inf};
+    for (size_t t = 0; t < T; t++) batch_inv_body<typename C::F, FinWeiXY<C>, true>(t, T, n, planes.data(), pf.data(), fin);
+    return st;
+}
+extern "C" unsigned long long hs_wei_mul_base_ct(int curve, const u32* k, size_t n, u32* out, unsigned char* inf) {
+    if (curve == 0) return wei_mul_base_ct_run<CurveP256>(k, n, out, inf);
+    return wei_mul_base_ct_run<CurveP384>(k, n, out, inf);
+}
 extern "C" unsigned long long hs_wei_mul_base(int curve, const u32* k, size_t n, int W, u32* out, unsigned char* inf) {
     switch (curve) {
         case 0: return wei_mul_base_run<CurveP256>(k, n, W, out, inf);

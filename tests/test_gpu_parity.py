@@ -878,7 +878,9 @@ def test_ecdsa_sign_hashed(ctx, golden, coracle, curve):
         zs.append(z)
     tob = lambda xs: rows([x.to_bytes(c.sbytes, "big") for x in xs])
     db, kb, zb = tob(ds), tob(ks), tob(zs)
-    rs, ok = ctx.ecdsa_sign_hashed(curve, db, kb, zb)
+    rs, ok = ctx.ecdsa_sign_hashed(curve, db, kb, zb)          # the constant-time kernels (the reference's names)
+    rs_v, ok_v = ctx.ecdsa_sign_hashed(curve, db, kb, zb, vartime=True)
+    assert np.array_equal(rs, rs_v) and np.array_equal(ok, ok_v)
     m = nk + n_rand
     assert ok[:m].all() and not ok[m:].any() and not rs[m:].any()
     for i in range(nk):

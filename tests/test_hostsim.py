@@ -21,7 +21,7 @@ def hs():
     subprocess.check_call(["make", "-s", "-j4", "-C", HS])
     f = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_fields.so"))
     k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
-    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_ecdsa_verify"):
+    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_wei_mul_base_ct", "hs_ecdsa_verify"):
         getattr(k, fn).restype = ctypes.c_ulonglong
     return f, k
 
@@ -228,6 +228,26 @@ def test_wei_mul(hs, golden, coracle, cid, curve):
     for W in (4, 5):
         assert k.hs_wei_mul_base(cid, p(kb), ctypes.c_size_t(n), W, p(out), p(inf)) == 2**64 - 1
         assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
+
+
+@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1")])
+def test_weierstrass_mul_base_constant_time_form(hs, golden, coracle, cid, curve):
+    """ct.cuh on p256r1 / p384r1: masked scans of the W = 4 comb and the complete projective addition (RCB Algorithm 4,
+    the reference's own formulas, projective.rs:340-423) — same bytes as the reference's mul_base for the NIST KAT
+    scalars, the edge scalars (0 -> infinity, 1, n - 1, n - 2) and the scalars that hit the Jacobian exceptional
+    cases in a signed radix-16 comb (2^257 mod n and neighbours), plus random ones."""
+    _, k = hs
+    c = R.WCURVES[curve]
+    g = rng(400 + cid)
+    vals = [0, 1, 2, 15, 16, 17, c.n - 1, c.n - 2, (1 << (8 * c.sbytes + 1)) % c.n, ((1 << (8 * c.sbytes + 1)) + 1) % c.n, (1 << (8 * c.sbytes - 4)) % c.n]
+    vals += [v % c.n for v in wei_edge_scalars(golden, c.n)[:24]]
+    kb = np.concatenate([rows([v.to_bytes(c.sbytes, "big") for v in vals]), scalars_mod(g, 24, c.n, c.sbytes, "big")])
+    n = kb.shape[0]
+    out = np.zeros((n, 2 * c.fbytes), dtype=np.uint8)
+    inf = np.zeros(n, dtype=np.uint8)
+    assert k.hs_wei_mul_base_ct(cid, p(kb), ctypes.c_size_t(n), p(out), p(inf)) == 2**64 - 1
+    exp, einf = coracle.wei_mul_base(curve, kb)
+    assert np.array_equal(inf.astype(bool), einf) and np.array_equal(out, exp) and einf[0] and not einf[-24:].any()
 
 
 @pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1")])
