@@ -21,6 +21,7 @@ ECB_ERR_NOT_READY = -6
 CURVE_P256R1 = 0
 CURVE_P384R1 = 1
 CURVE_BLS12_381_G1 = 2
+CURVE_P256K1 = 3
 
 _vp = ctypes.c_void_p
 _sz = ctypes.c_size_t
@@ -66,6 +67,9 @@ SIGNATURES = {
     "ecb_wei_decompress": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp]),
     "ecb_bls12_381_g1_from_compressed": (_int, [_vp, _vp, _sz, _int, _vp, _vp]),
     "ecb_bls12_381_g1_to_compressed": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ecb_bls12_381_g1_from_uncompressed": (_int, [_vp, _vp, _sz, _int, _vp, _vp, _vp]),
+    "ecb_bls12_381_g1_to_uncompressed": (_int, [_vp, _vp, _vp, _sz, _vp]),
+    "ecb_ed25519_decompress": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "ecb_wei_decompress_dev": (_int, [_vp, _int, _int, _vp, _vp, _sz, _vp, _vp, _vp]),
     "ecb_bls12_381_g1_from_compressed_dev": (_int, [_vp, _int, _vp, _sz, _int, _vp, _vp, _vp]),
     "ecb_ed25519_public_from_seed": (_int, [_vp, _vp, _sz, _vp]),

@@ -10,9 +10,9 @@ import numpy as np
 from . import _lib
 from ._lib import EccBatchError
 
-FIELD_BYTES = {_lib.CURVE_P256R1: 32, _lib.CURVE_P384R1: 48, _lib.CURVE_BLS12_381_G1: 48}
-SCALAR_BYTES = {_lib.CURVE_P256R1: 32, _lib.CURVE_P384R1: 48, _lib.CURVE_BLS12_381_G1: 32}
-CURVE_IDS = {"p256r1": _lib.CURVE_P256R1, "p384r1": _lib.CURVE_P384R1, "bls12_381_g1": _lib.CURVE_BLS12_381_G1}
+FIELD_BYTES = {_lib.CURVE_P256R1: 32, _lib.CURVE_P384R1: 48, _lib.CURVE_BLS12_381_G1: 48, _lib.CURVE_P256K1: 32}
+SCALAR_BYTES = {_lib.CURVE_P256R1: 32, _lib.CURVE_P384R1: 48, _lib.CURVE_BLS12_381_G1: 32, _lib.CURVE_P256K1: 32}
+CURVE_IDS = {"p256r1": _lib.CURVE_P256R1, "p384r1": _lib.CURVE_P384R1, "bls12_381_g1": _lib.CURVE_BLS12_381_G1, "p256k1": _lib.CURVE_P256K1}
 
 
 def _rows(a, width, name):
@@ -309,6 +309,36 @@ class Context:
         out = _out(out, (n, 96))
         ok = _out(out_ok, (n,))
         self._check(self._lib.ecb_bls12_381_g1_from_compressed(self._ctx, _p(e), n, 1 if check_subgroup else 0, _p(out), _p(ok)))
+        return out, ok.astype(bool)
+
+    def bls12_381_g1_from_uncompressed(self, enc, check_subgroup=True, out=None, out_ok=None):
+        """PointAffine::from_uncompressed / from_uncompressed_oncurve_only (bls12_381/serialize.rs:330-380):
+        (x || y rows, present, was-the-identity-encoding)."""
+        e = _rows(enc, 96, "enc")
+        n = e.shape[0]
+        out = _out(out, (n, 96))
+        ok = _out(out_ok, (n,))
+        inf = np.zeros(n, dtype=np.uint8)
+        self._check(self._lib.ecb_bls12_381_g1_from_uncompressed(self._ctx, _p(e), n, 1 if check_subgroup else 0, _p(out), _p(inf), _p(ok)))
+        return out, ok.astype(bool), inf.astype(bool)
+
+    def bls12_381_g1_to_uncompressed(self, xy_be, inf=None, out=None):
+        """Point::to_uncompressed (bls12_381/serialize.rs:412)."""
+        p = _rows(xy_be, 96, "xy_be")
+        n = p.shape[0]
+        if inf is not None:
+            inf = np.ascontiguousarray(inf, dtype=np.uint8).reshape(-1)
+        out = _out(out, (n, 96))
+        self._check(self._lib.ecb_bls12_381_g1_to_uncompressed(self._ctx, _p(p), _p(inf), n, _p(out)))
+        return out
+
+    def ed25519_decompress(self, enc, out=None, out_ok=None):
+        """ed25519 decode_point / Point::decompress over a batch: (x || y rows, present)."""
+        e = _rows(enc, 32, "enc")
+        n = e.shape[0]
+        out = _out(out, (n, 64))
+        ok = _out(out_ok, (n,))
+        self._check(self._lib.ecb_ed25519_decompress(self._ctx, _p(e), n, _p(out), _p(ok)))
         return out, ok.astype(bool)
 
     def bls12_381_g1_to_compressed(self, xy_be, inf=None, out=None):

@@ -14,6 +14,7 @@ int dev_ed25519_mul_base_ct(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u
 int dev_ed25519_public_from_seed(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, size_t n, u32* d_pub, cudaStream_t s, bool ct);
 int dev_ed25519_sign(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, const unsigned char* d_pub, const unsigned char* d_msgs,
                      const unsigned long long* d_off, size_t n, unsigned char* d_sig, cudaStream_t s, bool ct);
+int dev_ed25519_decompress(ecb_ctx* ctx, DevCtx& d, const u32* d_enc, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
 int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_out, cudaStream_t s);
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
                        unsigned char* ok, cudaStream_t s);
@@ -28,6 +29,11 @@ int dev_wei_mul_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, co
                      u32* d_out, unsigned char* d_inf, cudaStream_t s);
 int dev_wei_mul_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, const unsigned char* d_inf_in, size_t n,
                     u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_mul_k256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, const unsigned char* d_inf_in, size_t n,
+                     u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_mul_base_k256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_decompress_k256(ecb_ctx* ctx, DevCtx& d, const u32* d_x, const unsigned char* d_sign, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
+int dev_wei_table_k256(ecb_ctx* ctx, DevCtx& d);
 // fixed base (comb): d_out / d_inf as dev_wei_mul_*; *_table makes sure the device comb exists
 int dev_wei_mul_base_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
 int dev_wei_mul_base_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
@@ -38,6 +44,9 @@ int dev_wei_decompress_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_x, const unsig
 int dev_wei_decompress_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_x, const unsigned char* d_sign, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
 int dev_bls_g1_from_compressed(ecb_ctx* ctx, DevCtx& d, const u32* d_enc, size_t n, int check, u32* d_out, unsigned char* d_ok, cudaStream_t s);
 int dev_bls_g1_to_compressed(ecb_ctx* ctx, DevCtx& d, const u32* d_xy, const unsigned char* d_inf, size_t n, u32* d_enc, cudaStream_t s);
+int dev_bls_g1_from_uncompressed(ecb_ctx* ctx, DevCtx& d, const u32* d_enc, size_t n, int check, u32* d_out, unsigned char* d_inf,
+                                 unsigned char* d_ok, cudaStream_t s);
+int dev_bls_g1_to_uncompressed(ecb_ctx* ctx, DevCtx& d, const u32* d_xy, const unsigned char* d_inf, size_t n, u32* d_enc, cudaStream_t s);
 int dev_wei_table_p256(ecb_ctx* ctx, DevCtx& d);
 int dev_wei_table_p384(ecb_ctx* ctx, DevCtx& d);
 int dev_wei_table_bls(ecb_ctx* ctx, DevCtx& d);

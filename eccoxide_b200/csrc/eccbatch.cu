@@ -10,6 +10,7 @@ static int dev_wei_mul(ecb_ctx* ctx, DevCtx& d, int curve, const u32* d_k, const
         case ECB_CURVE_P256R1: return dev_wei_mul_p256(ctx, d, d_k, d_p, d_inf_in, n, d_out, d_inf, s);
         case ECB_CURVE_P384R1: return dev_wei_mul_p384(ctx, d, d_k, d_p, d_inf_in, n, d_out, d_inf, s);
         case ECB_CURVE_BLS12_381_G1: return dev_wei_mul_bls(ctx, d, d_k, d_p, d_inf_in, n, d_out, d_inf, s);
+        case ECB_CURVE_P256K1: return dev_wei_mul_k256(ctx, d, d_k, d_p, d_inf_in, n, d_out, d_inf, s);
     }
     return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
 }
@@ -69,7 +70,7 @@ void ecb_destroy(ecb_ctx* ctx) {
         cudaSetDevice(d->dev);
         for (Slot& sl : d->slots) {
             if (sl.stream) cudaStreamSynchronize(sl.stream);
-            DevBuf* bufs[] = {&sl.planes, &sl.pf, &sl.scratch, &sl.aux, &sl.in[0], &sl.in[1], &sl.in[2], &sl.in[3], &sl.out[0], &sl.out[1]};
+            DevBuf* bufs[] = {&sl.planes, &sl.pf, &sl.scratch, &sl.aux, &sl.in[0], &sl.in[1], &sl.in[2], &sl.in[3], &sl.out[0], &sl.out[1], &sl.out[2]};
             for (DevBuf* b : bufs)
                 if (b->p) {
                     cudaMemset(b->p, 0, b->cap);   // work buffers may hold key material of signing / key-generation calls
@@ -122,9 +123,9 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
         ctx->opt_ed_lanes = value;
         return ECB_OK;
     }
-    if (!strcmp(key, "p256r1_comb_w") || !strcmp(key, "p384r1_comb_w") || !strcmp(key, "bls12_381_g1_comb_w")) {
+    if (!strcmp(key, "p256r1_comb_w") || !strcmp(key, "p384r1_comb_w") || !strcmp(key, "bls12_381_g1_comb_w") || !strcmp(key, "p256k1_comb_w")) {
         if (value != 0 && (value < 4 || value > 24)) return set_err(ctx, ECB_ERR_INVALID_ARG, "comb width must be 0 or in 4..24");
-        ctx->opt_wei_w[key[1] == '2' ? 0 : (key[1] == '3' ? 1 : 2)] = value;
+        ctx->opt_wei_w[!strcmp(key, "p256k1_comb_w") ? 3 : (key[1] == '2' ? 0 : (key[1] == '3' ? 1 : 2))] = value;
         return ECB_OK;
     }
     if (!strcmp(key, "inv_per_thread")) {
@@ -282,7 +283,7 @@ static int run_sharded(ecb_ctx* ctx, size_t n, const std::vector<HostArg>& ins, 
                     TRY(retire(sl));
                     d.cur = &sl;
                     const void* din[4] = {nullptr, nullptr, nullptr, nullptr};
-                    void* dout[2] = {nullptr, nullptr};
+                    void* dout[3] = {nullptr, nullptr, nullptr};
                     for (size_t i = 0; i < ins.size(); i++) {
                         if (!ins[i].src) continue;
                         TRY(ensure(ctx, sl.in[i], cn * ins[i].elem));
@@ -342,6 +343,7 @@ static int dev_wei_mul_base(ecb_ctx* ctx, DevCtx& d, int curve, const u32* d_k, 
         case ECB_CURVE_P256R1: return dev_wei_mul_base_p256(ctx, d, d_k, n, d_out, d_inf, s);
         case ECB_CURVE_P384R1: return dev_wei_mul_base_p384(ctx, d, d_k, n, d_out, d_inf, s);
         case ECB_CURVE_BLS12_381_G1: return dev_wei_mul_base_bls(ctx, d, d_k, n, d_out, d_inf, s);
+        case ECB_CURVE_P256K1: return dev_wei_mul_base_k256(ctx, d, d_k, n, d_out, d_inf, s);
     }
     return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
 }
@@ -384,6 +386,7 @@ static int curve_sizes(int curve, size_t& fb, size_t& sb) {
         case ECB_CURVE_P256R1: fb = 32; sb = 32; return ECB_OK;
         case ECB_CURVE_P384R1: fb = 48; sb = 48; return ECB_OK;
         case ECB_CURVE_BLS12_381_G1: fb = 48; sb = 32; return ECB_OK;
+        case ECB_CURVE_P256K1: fb = 32; sb = 32; return ECB_OK;
     }
     return ECB_ERR_INVALID_ARG;
 }
@@ -607,7 +610,7 @@ int ecb_ecdsa_verify(ecb_ctx* ctx, int curve, int hash, const uint8_t* q_xy, con
     if (!ctx) return ECB_ERR_CUDA;
     if (bad_index) *bad_index = (size_t)-1;
     size_t fb, sb;
-    if (curve_sizes(curve, fb, sb) || curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+    if (curve_sizes(curve, fb, sb) || (curve != ECB_CURVE_P256R1 && curve != ECB_CURVE_P384R1)) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
     if (hash != 256 && hash != 384 && hash != 512) return set_err(ctx, ECB_ERR_INVALID_ARG, "hash must be 256, 384 or 512 (SHA-2)");
     if (n && (!q_xy || !msg_off || !rs_be || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
     if (n == 0) return ECB_OK;
@@ -745,7 +748,7 @@ static int ecdsa_sign_hashed_impl(ecb_ctx* ctx, int curve, const uint8_t* d_be, 
                                   uint8_t* ok, bool ct) {
     if (!ctx) return ECB_ERR_CUDA;
     size_t fb, sb;
-    if (curve_sizes(curve, fb, sb) || curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+    if (curve_sizes(curve, fb, sb) || (curve != ECB_CURVE_P256R1 && curve != ECB_CURVE_P384R1)) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
     if (n && (!d_be || !k_be || !z_be || !rs_be || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
     return run_sharded(ctx, n, {{d_be, sb}, {k_be, sb}, {z_be, sb}}, {{rs_be, 2 * sb}, {ok, 1}}, false, nullptr,
                        [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
@@ -772,7 +775,7 @@ static int ecdsa_sign_impl(ecb_ctx* ctx, int curve, int hash, const uint8_t* d_b
                            size_t n, uint8_t* rs_be, uint8_t* ok, bool ct) {
     if (!ctx) return ECB_ERR_CUDA;
     size_t fb, sb;
-    if (curve_sizes(curve, fb, sb) || curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+    if (curve_sizes(curve, fb, sb) || (curve != ECB_CURVE_P256R1 && curve != ECB_CURVE_P384R1)) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
     if (hash != 256 && hash != 384 && hash != 512) return set_err(ctx, ECB_ERR_INVALID_ARG, "hash must be 256, 384 or 512");
     if (n && (!d_be || !k_be || !msg_off || !rs_be || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
     if (n == 0) return ECB_OK;
@@ -856,6 +859,9 @@ int ecb_wei_decompress(ecb_ctx* ctx, int curve, const uint8_t* x_be, const uint8
                                case ECB_CURVE_P384R1:
                                    return dev_wei_decompress_p384(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0],
                                                                   (unsigned char*)o[1], s);
+                               case ECB_CURVE_P256K1:
+                                   return dev_wei_decompress_k256(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0],
+                                                                  (unsigned char*)o[1], s);
                                default:
                                    return dev_wei_decompress_bls(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0],
                                                                  (unsigned char*)o[1], s);
@@ -871,6 +877,33 @@ int ecb_bls12_381_g1_from_compressed(ecb_ctx* ctx, const uint8_t* enc, size_t n,
                                                              (unsigned char*)o[1], s);
                        });
 }
+int ecb_bls12_381_g1_from_uncompressed(ecb_ctx* ctx, const uint8_t* enc, size_t n, int check_subgroup, uint8_t* out_xy, uint8_t* out_inf,
+                                       uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!enc || !out_xy || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{enc, 96}}, {{out_xy, 96}, {ok, 1}, {out_inf, 1}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_bls_g1_from_uncompressed(ctx, d, (const u32*)in[0], cn, check_subgroup ? 1 : 0, (u32*)o[0],
+                                                               (unsigned char*)o[2], (unsigned char*)o[1], s);
+                       });
+}
+int ecb_bls12_381_g1_to_uncompressed(ecb_ctx* ctx, const uint8_t* xy_be, const uint8_t* inf, size_t n, uint8_t* enc) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!xy_be || !enc)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{xy_be, 96}, {inf, 1}}, {{enc, 96}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_bls_g1_to_uncompressed(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0], s);
+                       });
+}
+// decode_point / Point::decompress over a batch (protocol/ed25519.rs:38-59, curve25519.rs:772)
+int ecb_ed25519_decompress(ecb_ctx* ctx, const uint8_t* enc, size_t n, uint8_t* xy_le, uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!enc || !xy_le || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{enc, 32}}, {{xy_le, 64}, {ok, 1}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_ed25519_decompress(ctx, d, (const u32*)in[0], cn, (u32*)o[0], (unsigned char*)o[1], s);
+                       });
+}
 int ecb_bls12_381_g1_to_compressed(ecb_ctx* ctx, const uint8_t* xy_be, const uint8_t* inf, size_t n, uint8_t* enc) {
     if (!ctx) return ECB_ERR_CUDA;
     if (n && (!xy_be || !enc)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
@@ -884,7 +917,7 @@ int ecb_ecdsa_verify_hashed(ecb_ctx* ctx, int curve, const uint8_t* q_xy, const 
     if (!ctx) return ECB_ERR_CUDA;
     size_t fb, sb;
     if (curve_sizes(curve, fb, sb)) return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
-    if (curve == ECB_CURVE_BLS12_381_G1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
+    if (curve != ECB_CURVE_P256R1 && curve != ECB_CURVE_P384R1) return set_err(ctx, ECB_ERR_INVALID_ARG, "ECDSA is defined for p256r1/p384r1 only");
     if (n && (!q_xy || !z_be || !rs_be || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
     return run_sharded(ctx, n, {{q_xy, 2 * fb}, {z_be, sb}, {rs_be, 2 * sb}}, {{ok, 1}}, true, bad_index,
                        [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
@@ -977,6 +1010,9 @@ int ecb_wei_decompress_dev(ecb_ctx* ctx, int di, int curve, const void* d_x, con
         case ECB_CURVE_BLS12_381_G1:
             return dev_wei_decompress_bls(ctx, *d, (const u32*)d_x, (const unsigned char*)d_sign, n, (u32*)d_out, (unsigned char*)d_ok,
                                           (cudaStream_t)stream);
+        case ECB_CURVE_P256K1:
+            return dev_wei_decompress_k256(ctx, *d, (const u32*)d_x, (const unsigned char*)d_sign, n, (u32*)d_out, (unsigned char*)d_ok,
+                                           (cudaStream_t)stream);
     }
     return set_err(ctx, ECB_ERR_INVALID_ARG, "unknown curve id");
 }
@@ -1248,11 +1284,11 @@ int ecb_warm(ecb_ctx* ctx, const char* op, int curve, size_t max_n) {
 int ecb_get_info(ecb_ctx* ctx, int di, const char* key, long* value) {
     DevCtx* d = get_dev(ctx, di);
     if (!d || !key || !value) return ECB_ERR_INVALID_ARG;
-    static const char* wn[3] = {"p256r1", "p384r1", "bls12_381_g1"};
+    static const char* wn[4] = {"p256r1", "p384r1", "bls12_381_g1", "p256k1"};
     if (!strcmp(key, "ed25519_comb_w")) { *value = d->ed_w; return ECB_OK; }
     if (!strcmp(key, "ed25519_comb_windows")) { *value = d->ed_nwin; return ECB_OK; }
     if (!strcmp(key, "sm_count")) { *value = d->sm_count; return ECB_OK; }
-    for (int c = 0; c < 3; c++) {
+    for (int c = 0; c < 4; c++) {
         if (!strcmp(key, (std::string(wn[c]) + "_comb_w").c_str())) { *value = d->wei_w[c]; return ECB_OK; }
         if (!strcmp(key, (std::string(wn[c]) + "_comb_windows").c_str())) { *value = d->wei_nwin[c]; return ECB_OK; }
     }

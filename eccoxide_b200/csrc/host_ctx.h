@@ -33,7 +33,7 @@ struct DevBuf {
 #define ECB_NSLOT 4
 struct Slot {
     cudaStream_t stream = nullptr;
-    DevBuf planes, pf, scratch, aux, in[4], out[2];
+    DevBuf planes, pf, scratch, aux, in[4], out[3];
     unsigned long long* d_status = nullptr;
     unsigned long long* h_status = nullptr;  // pinned
     bool busy = false;
@@ -57,9 +57,9 @@ struct DevCtx {
     u32* ed_table = nullptr;
     int ed_w = 0, ed_nwin = 0, ed_stride = 24;  // comb width, windows, words between entries (24 packed, 32 = 128-byte aligned)
     u32* ed_ct_table = nullptr;               // constant-time comb (ct.cuh): W = 4, 64 windows x 8 entries, 48 KB
-    u32* wei_ct_table[3] = {nullptr, nullptr, nullptr};   // constant-time generator combs of the Weierstrass curves (W = 4)
-    u32* wei_table[3] = {nullptr, nullptr, nullptr};  // generator combs of p256r1, p384r1, bls12_381 G1
-    int wei_w[3] = {0, 0, 0}, wei_nwin[3] = {0, 0, 0};
+    u32* wei_ct_table[4] = {nullptr, nullptr, nullptr, nullptr};   // constant-time generator combs of the Weierstrass curves (W = 4)
+    u32* wei_table[4] = {nullptr, nullptr, nullptr, nullptr};  // generator combs of p256r1, p384r1, bls12_381 G1, p256k1
+    int wei_w[4] = {0, 0, 0, 0}, wei_nwin[4] = {0, 0, 0, 0};
     DevBuf trace;                             // option "trace": per-block timestamps of the last fused launch
     size_t trace_blocks = 0;
     std::mutex mu;
@@ -73,7 +73,7 @@ struct ecb_ctx {
     std::vector<DevCtx*> devs;
     std::string err;
     std::mutex err_mu;
-    long opt_wei_w[3] = {0, 0, 0};     // generator comb widths (p256r1, p384r1, bls12_381 g1); 0 = by free memory: 24 / 22 / 24 (11 / 18 / 11 windows, 5.9 / 3.6 / 8.9 GB) above 100 GB free, else 20 / 18 / 20
+    long opt_wei_w[4] = {0, 0, 0, 0};  // generator comb widths (p256r1, p384r1, bls12_381 g1, p256k1); 0 = by free memory: 24 / 22 / 24 (11 / 18 / 11 windows, 5.9 / 3.6 / 8.9 GB) above 100 GB free, else 20 / 18 / 20
     // Ed25519 comb width; 0 = pick by free device memory (24: 11 windows, 8.9 GB table; 20: 13 windows, 0.65 GB;
     // 16: 16 windows, 50 MB).  Measured at n = 2^20: w=16 772 M/s, 20 907, 22 969, 24 1041 M/s — the kernel is
     // integer-pipe-bound, so time follows the window count; the random table reads (96 B per window) stay

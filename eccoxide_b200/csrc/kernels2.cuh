@@ -553,6 +553,24 @@ ECB_DEV u32 ed25519_decode(fe25519& x, fe25519& y, const u32* enc) {
     return ok;
 }
 
+// decode_point / Point::decompress over a batch (protocol/ed25519.rs:38-59, curve25519.rs:772): 32-byte encodings
+// -> canonical affine x || y (64 bytes LE) and a presence flag; zero bytes where the reference returns None
+// (non-canonical y, no square root, x = 0 with the sign bit set).
+ECB_DEV void ed25519_decompress_body(size_t idx, const u32* enc, u32* out_xy, unsigned char* ok) {
+    u32 w[8];
+    ld_words<8>(w, enc + idx * 8);
+    fe25519 x, y;
+    u32 good = ed25519_decode(x, y, w);
+    F::freeze(x, x);
+    F::freeze(y, y);
+    u32 m = good ? 0xffffffffu : 0u;
+    ECB_UNROLL
+    for (int i = 0; i < 8; i++) { x.v[i] &= m; y.v[i] &= m; }
+    st_words<8>(out_xy + idx * 16, x.v);
+    st_words<8>(out_xy + idx * 16 + 8, y.v);
+    ok[idx] = (unsigned char)good;
+}
+
 // 64 little-endian bytes -> canonical scalar mod l (reduce_wide_le / init_from_wide_bytes_le)
 ECB_DEV void ed25519_reduce_wide(u32* out8, const unsigned char* dg) {
     typedef Mont<ED_FN> FL;

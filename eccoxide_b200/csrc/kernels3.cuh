@@ -169,6 +169,53 @@ ECB_DEV void bls_g1_from_compressed_body(size_t idx, const u32* enc, int check, 
     ok[idx] = (unsigned char)good;
 }
 
+// PointAffine::from_uncompressed / from_uncompressed_oncurve_only (serialize.rs:330-380; flags :129-140,
+// coordinates :207-221): 96 bytes x || y big-endian, the three flag bits in the top of byte 0.  The compression
+// and sort bits must be clear; both coordinates canonical; on the curve; in G1 when `check`.  The identity
+// encoding (0x40 then zeros) is valid as an encoding but PointAffine cannot hold it: ok = 0 as the reference
+// returns None, and inf (optional) = 1 so that a caller working with projective points can tell it apart.
+ECB_DEV void bls_g1_from_uncompressed_body(size_t idx, const u32* enc, int check, u32* out_xy, unsigned char* inf, unsigned char* ok) {
+    typedef CurveBLSG1 C;
+    typedef C::F FT;
+    typedef FT::el fe;
+    constexpr int N = 12;
+    u32 xw[N], yw[N];
+    ld_words_be<N>(xw, enc + idx * 2 * N);
+    ld_words_be<N>(yw, enc + idx * 2 * N + N);
+    const u32 flags = xw[N - 1] >> 29;     // bit 2: compressed, bit 1: infinity, bit 0: sort
+    xw[N - 1] &= 0x1fffffffu;
+    u32 payload = 0;
+    ECB_UNROLL
+    for (int i = 0; i < N; i++) payload |= xw[i] | yw[i];
+    const u32 is_inf = ((flags & 5u) == 0u && (flags & 2u) && payload == 0u) ? 1u : 0u;
+    u32 good = (flags == 0u) ? 1u : 0u;
+    good &= FT::is_canonical_words(xw) & FT::is_canonical_words(yw);
+    fe x, y;
+    FT::to_mont(x, xw);
+    FT::to_mont(y, yw);
+    good &= Wei<C>::on_curve(x, y);
+    if (good && check) good = bls_g1_in_subgroup(x, y);
+    u32 m = good ? 0xffffffffu : 0u;
+    ECB_UNROLL
+    for (int i = 0; i < N; i++) { xw[i] &= m; yw[i] &= m; }
+    st_words_be<N>(out_xy + idx * 2 * N, xw);
+    st_words_be<N>(out_xy + idx * 2 * N + N, yw);
+    if (inf) inf[idx] = (unsigned char)is_inf;
+    ok[idx] = (unsigned char)good;
+}
+// Point::to_uncompressed (serialize.rs:412-): x || y as given, or 0x40 followed by zeros for the identity
+ECB_DEV void bls_g1_to_uncompressed_body(size_t idx, const u32* xy, const unsigned char* inf, u32* enc) {
+    constexpr int N = 12;
+    u32 w[2 * N];
+    ld_words<2 * N>(w, xy + idx * 2 * N);
+    if (inf && inf[idx]) {
+        ECB_UNROLL
+        for (int i = 0; i < 2 * N; i++) w[i] = 0;
+        w[0] = 0x40u;   // byte 0 of the big-endian encoding is the low byte of the first little-endian word
+    }
+    st_words<2 * N>(enc + idx * 2 * N, w);
+}
+
 // Point::to_compressed (serialize.rs:400-420): x with the compression flag and the sort flag; the
 // identity (inf[idx] != 0) is 0xc0 followed by zeros.  Coordinates are taken as given (canonical).
 ECB_DEV void bls_g1_to_compressed_body(size_t idx, const u32* xy, const unsigned char* inf, u32* enc) {

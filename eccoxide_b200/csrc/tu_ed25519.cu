@@ -329,6 +329,17 @@ int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, siz
     return rc;
 }
 
+static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_decompress(size_t n, const u32* enc, u32* out_xy, unsigned char* ok) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) ed25519_decompress_body(idx, enc, out_xy, ok);
+}
+int dev_ed25519_decompress(ecb_ctx* ctx, DevCtx& d, const u32* d_enc, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s) {
+    (void)d;
+    k_ed25519_decompress<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_enc, d_out, d_ok);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ECB_OK;
+}
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_hash_k(size_t n, const unsigned char* a_enc, const unsigned char* sig,
                                                              const unsigned char* msgs, const unsigned long long* off,
                                                              u32* r_out, u32* s_out, u32* k_out) {

@@ -22,6 +22,7 @@ struct CurveP256 {
     typedef Mont<P256_FN> FN;
     static constexpr bool A_M3 = true;
     static constexpr int FB = 32, SB = 32;          // field / scalar bytes
+    static constexpr bool COFACTOR = false;      // #E(Fp) != group order: small-order points exist
     static constexpr int SBITS = 256;
     ECB_DEV static u32 b(int i) { return P256_B[i]; }
     ECB_DEV static u32 b3(int i) { return P256_B3[i]; }
@@ -34,6 +35,7 @@ struct CurveP384 {
     typedef Mont<P384_FN> FN;
     static constexpr bool A_M3 = true;
     static constexpr int FB = 48, SB = 48;
+    static constexpr bool COFACTOR = false;      // #E(Fp) != group order: small-order points exist
     static constexpr int SBITS = 384;
     ECB_DEV static u32 b(int i) { return P384_B[i]; }
     ECB_DEV static u32 b3(int i) { return P384_B3[i]; }
@@ -46,6 +48,7 @@ struct CurveBLSG1 {
     typedef Mont<BLS_FR> FN;
     static constexpr bool A_M3 = false;
     static constexpr int FB = 48, SB = 32;
+    static constexpr bool COFACTOR = true;      // #E(Fp) != group order: small-order points exist
     static constexpr int SBITS = 255;
     ECB_DEV static u32 b(int i) { return BLSG1_B[i]; }
     ECB_DEV static u32 b3(int i) { return BLSG1_B3[i]; }
@@ -53,6 +56,22 @@ struct CurveBLSG1 {
     ECB_DEV static u32 gy(int i) { return BLSG1_GY[i]; }
     ECB_DEV static u32 sqrt_e(int i) { return BLSG1_SQRT_E[i]; }
     ECB_DEV static u32 beta(int i) { return BLSG1_BETA[i]; }
+};
+
+// secp256k1 (the reference's p256k1, src/curve/sec2/p256k1.rs): a = 0, b = 7 — the same a = 0 path as BLS12-381 G1
+// (projective.rs:268, :544, :842, :945), generic CIOS Montgomery fields on 8 limbs
+struct CurveK256 {
+    typedef Mont<K256_FP> F;
+    typedef Mont<K256_FN> FN;
+    static constexpr bool A_M3 = false;
+    static constexpr int FB = 32, SB = 32;
+    static constexpr bool COFACTOR = false;      // #E(Fp) != group order: small-order points exist
+    static constexpr int SBITS = 256;
+    ECB_DEV static u32 b(int i) { return K256_B[i]; }
+    ECB_DEV static u32 b3(int i) { return K256_B3[i]; }
+    ECB_DEV static u32 gx(int i) { return K256_GX[i]; }
+    ECB_DEV static u32 gy(int i) { return K256_GY[i]; }
+    ECB_DEV static u32 sqrt_e(int i) { return K256_SQRT_E[i]; }
 };
 
 template <class C>
@@ -206,6 +225,10 @@ struct WeiJ {
             if (QAFF) F::set_one(r.Z); else F::copy(r.Z, q.Z);
             return;
         }
+        if (!QAFF && C::COFACTOR && F::is_zero(q.Z)) {   // p + O (see add_mem)
+            F::copy(r.X, p.X); F::copy(r.Y, p.Y); F::copy(r.Z, p.Z);
+            return;
+        }
         fe Z1Z1, U1, U2, S1, S2, H, I, J, rr, V, t, X3, Y3, Z3;
         F::sqr_ni(Z1Z1, p.Z);
         if (QAFF) F::copy(U1, p.X); else F::mul_ni(U1, p.X, q.ZZ);
@@ -268,6 +291,16 @@ struct WeiJ {
             F::select(r.Y, neg, r.Y, q);
             ld(r.Z.v, e + 2 * N);
             return;
+        }
+        if (C::COFACTOR) {
+            // On a curve with cofactor > 1 a table entry j * P is the identity when ord(P) divides j (BLS12-381
+            // E(Fp) has points of order 3, and Point::mul accepts any curve point, g1.rs:375): p + O = p.
+            // The formulas below would give Z3 = 0 instead.  Prime-order curves never store such an entry.
+            ld(q.v, e + 2 * N);
+            if (F::is_zero(q)) {
+                F::copy(r.X, p.X); F::copy(r.Y, p.Y); F::copy(r.Z, p.Z);
+                return;
+            }
         }
         fe Z1Z1, U1, U2, S1, S2, H, I, J, rr, V, t, X3, Y3, Z3, HH;
         F::sqr_ni(Z1Z1, p.Z);

@@ -55,6 +55,7 @@ extern "C" {
 #define ECB_CURVE_P256R1 0       /* field 32 B, scalar 32 B */
 #define ECB_CURVE_P384R1 1       /* field 48 B, scalar 48 B */
 #define ECB_CURVE_BLS12_381_G1 2 /* field 48 B, scalar 32 B */
+#define ECB_CURVE_P256K1 3       /* secp256k1 (src/curve/sec2/p256k1.rs): field 32 B, scalar 32 B; mul, mul_base, decompress */
 
 typedef struct ecb_ctx ecb_ctx;
 
@@ -81,7 +82,7 @@ int ecb_device_count(ecb_ctx* ctx);
 /* Tunables (set before first use; unknown keys and out-of-range values give ECB_ERR_INVALID_ARG):
  *   "ed25519_comb_w"        window width of the Ed25519 fixed-base comb, 4..26; 0 (default) = by free device memory, at
  *                           most 24 (11 windows, 8.9 GB).  26 (10 windows, 32 GB + 43 GB while it is built) is opt-in.
- *   "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w"
+ *   "p256r1_comb_w" / "p384r1_comb_w" / "bls12_381_g1_comb_w" / "p256k1_comb_w"
  *                           generator combs of the Weierstrass curves, 4..24; 0 = by free device memory
  *   "chunk"                 elements per pipeline chunk of the host entry points
  *   "ramp"                  halvings of the chunk size at both ends of a batch, 0..4
@@ -114,6 +115,11 @@ int ecb_ed25519_mul_base_compressed(ecb_ctx* ctx, const uint8_t* k_le, size_t n,
  * xy_le_in: n x 64 B affine points (must satisfy Point::from_coordinate). */
 int ecb_ed25519_mul(ecb_ctx* ctx, const uint8_t* k_le, const uint8_t* xy_le_in, size_t n, uint8_t* xy_le_out,
                     size_t* bad_index);
+/* ed25519::decode_point / Point::decompress (src/protocol/ed25519.rs:38-59, src/curve/curve25519.rs:772), batched:
+ * enc: n x 32 B (y little-endian, sign of x in bit 255); xy_le: n x 64 B canonical affine x || y; ok[i] = 0 and zero
+ * bytes where the reference returns None (y >= p, x^2 not a square, x = 0 with the sign bit set).  The output feeds
+ * ecb_ed25519_mul directly. */
+int ecb_ed25519_decompress(ecb_ctx* ctx, const uint8_t* enc, size_t n, uint8_t* xy_le, uint8_t* ok);
 /* protocol::ed25519 verify with k = SHA-512(R||A||M) mod l computed by the caller
  * (src/protocol/ed25519.rs:119-147).  a_enc, r_enc, s_le, k_le: n x 32 B; ok: n x 1 B (0/1). */
 int ecb_ed25519_verify_prehashed(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* r_enc, const uint8_t* s_le,
@@ -211,6 +217,15 @@ int ecb_wei_decompress(ecb_ctx* ctx, int curve_id, const uint8_t* x_be, const ui
 int ecb_bls12_381_g1_from_compressed(ecb_ctx* ctx, const uint8_t* enc, size_t n, int check_subgroup, uint8_t* out_xy_be,
                                      uint8_t* ok);
 int ecb_bls12_381_g1_to_compressed(ecb_ctx* ctx, const uint8_t* xy_be, const uint8_t* inf, size_t n, uint8_t* enc);
+/* The uncompressed flavour (serialize.rs:22-28, :269, :330-380): 96 bytes x || y big-endian with the same flag bits.
+ * from_uncompressed = PointAffine::from_uncompressed (check_subgroup != 0) / from_uncompressed_oncurve_only (0): the
+ * compression and sort bits must be clear, both coordinates canonical, the point on the curve (and in G1);
+ * ok[i] = 0 and zero output where the reference gives None — which includes the identity encoding (0x40 then zeros),
+ * since PointAffine cannot hold it; out_inf (optional, n bytes) is 1 exactly for that encoding.
+ * to_uncompressed = Point::to_uncompressed: x || y as given, the identity (inf[i] != 0) as 0x40 then zeros. */
+int ecb_bls12_381_g1_from_uncompressed(ecb_ctx* ctx, const uint8_t* enc, size_t n, int check_subgroup, uint8_t* out_xy_be,
+                                       uint8_t* out_inf, uint8_t* ok);
+int ecb_bls12_381_g1_to_uncompressed(ecb_ctx* ctx, const uint8_t* xy_be, const uint8_t* inf, size_t n, uint8_t* enc);
 
 /* ecdsa::verify_hashed (src/protocol/ecdsa.rs:205-222) after Signature::from_bytes (:399).
  * q_xy_be: n x 2FB public keys; z_be: n x SB message scalars (any value, reduced mod n as

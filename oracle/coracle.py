@@ -14,9 +14,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_build", "libecc_oracle.so")
 _lib = None
 
-CURVE_IDS = {"p256r1": 0, "p384r1": 1, "bls12_381_g1": 2}
-FIELD_BYTES = {0: 32, 1: 48, 2: 48}
-SCALAR_BYTES = {0: 32, 1: 48, 2: 32}
+CURVE_IDS = {"p256r1": 0, "p384r1": 1, "bls12_381_g1": 2, "p256k1": 3}
+FIELD_BYTES = {0: 32, 1: 48, 2: 48, 3: 32}
+SCALAR_BYTES = {0: 32, 1: 48, 2: 32, 3: 32}
 MODE_WINDOW, MODE_COMB, MODE_WNAF = 0, 1, 2
 
 

@@ -628,7 +628,7 @@ static void x448_one(u8* out, const u8* scalar, const u8* ubytes) {
 #include "mont_tmpl.h"
 #undef NL
 
-static curve4 P256;
+static curve4 P256, K256;   /* K256 = secp256k1, the reference's p256k1 (src/curve/sec2/p256k1.rs; a = 0 path) */
 static curve6 P384, BLSG1;
 
 static void hex2be(u8* out, const char* hex, int len) {
@@ -783,6 +783,13 @@ static void do_init(void) {
     hex2be(gx, "17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb", 48);
     hex2be(gy, "08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1", 48);
     curve_init6(&BLSG1, p, nn, bb, gx, gy, 48, 32, 1);
+    /* secp256k1 (SEC 2 v2 2.4.1; src/params/sec2.rs:908-) */
+    hex2be(p, "fffffffffffffffffffffffffffffffffffffffffffffffffffffffefffffc2f", 32);
+    hex2be(nn, "fffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141", 32);
+    memset(bb, 0, 48); bb[31] = 7;
+    hex2be(gx, "79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798", 32);
+    hex2be(gy, "483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8", 32);
+    curve_init4(&K256, p, nn, bb, gx, gy, 32, 32, 1);
     bls_extra_init();
 }
 void orc_init(void) { pthread_once(&g_once, do_init); }
@@ -899,6 +906,7 @@ static void j_wei(job* j, size_t lo, size_t hi) {
         case 0: WEI_BODY(4, &P256, mode) break;
         case 1: WEI_BODY(6, &P384, mode) break;
         case 2: WEI_BODY(6, &BLSG1, mode) break;
+        case 3: WEI_BODY(4, &K256, mode) break;
     }
 }
 /* PointAffine::decompress over a batch: a = x (fb bytes BE), b = sign bytes, o = x || y, o2 = present */
@@ -923,6 +931,7 @@ static void j_decompress(job* j, size_t lo, size_t hi) {
         case 0: DECOMP_BODY(4, &P256) break;
         case 1: DECOMP_BODY(6, &P384) break;
         case 2: DECOMP_BODY(6, &BLSG1) break;
+        case 3: DECOMP_BODY(4, &K256) break;
     }
 }
 
@@ -1074,7 +1083,7 @@ long orc_x448(const u8* k, const u8* u, size_t n, u8* out, int nthreads) {
 /* mode: 0 fixed-window (Point * Scalar), 1 comb (mul_base; xy ignored), 2 wNAF (mul_vartime) */
 long orc_wei_mul(int curve, int mode, const u8* k_be, const u8* xy_be, const u8* inf_in, size_t n, u8* out_xy, u8* out_inf,
                  int nthreads, int* code) {
-    if (curve < 0 || curve > 2 || mode < 0 || mode > 2) return -2;
+    if (curve < 0 || curve > 3 || mode < 0 || mode > 2) return -2;
     job t = {0};
     t.fn = j_wei; t.curve = curve; t.mode = mode; t.a = k_be; t.b = xy_be; t.c = inf_in; t.o = out_xy; t.o2 = out_inf;
     return run_jobs(&t, n, nthreads, code);
@@ -1109,9 +1118,10 @@ void orc_ed25519_comb_entry(int i, int j, u8* xy_le) {
 }
 void orc_wei_comb_entry(int curve, int i, int j, u8* xy_be) {
     orc_init();
-    if (curve == 0) {
-        f_to_be4(&P256.fp, xy_be, &P256.comb[i * 16 + j].X, 32);
-        f_to_be4(&P256.fp, xy_be + 32, &P256.comb[i * 16 + j].Y, 32);
+    if (curve == 0 || curve == 3) {
+        const curve4* c4 = curve == 0 ? &P256 : &K256;
+        f_to_be4(&c4->fp, xy_be, &c4->comb[i * 16 + j].X, 32);
+        f_to_be4(&c4->fp, xy_be + 32, &c4->comb[i * 16 + j].Y, 32);
     } else {
         const curve6* c = curve == 1 ? &P384 : &BLSG1;
         f_to_be6(&c->fp, xy_be, &c->comb[i * 16 + j].X, 48);

@@ -301,7 +301,15 @@ BLSG1 = WCurve(
     0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb,
     0x08b3f481e3aaa0f1a09e30ed741d8ae4fcf5e095d5d00af600db18cb2c04b3edd03cc744a2888ae40caa232946c5e7e1,
     48, 32)
-WCURVES = {"p256r1": P256, "p384r1": P384, "bls12_381_g1": BLSG1}
+K256 = WCurve(   # secp256k1: the reference's p256k1 (src/curve/sec2/p256k1.rs, parameters src/params/sec2.rs:908-)
+    "p256k1",
+    2**256 - 2**32 - 977,
+    0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141,
+    0, 7,
+    0x79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798,
+    0x483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8,
+    32, 32)
+WCURVES = {"p256r1": P256, "p384r1": P384, "bls12_381_g1": BLSG1, "p256k1": K256}
 
 
 def wei_mul(curve, k_be, xy_be):
@@ -386,6 +394,27 @@ def bls_g1_to_compressed(xy_be, inf=0):
     out = bytearray(x.to_bytes(48, "big"))
     out[0] |= 0x80 | (0x20 if y > (c.p - 1) // 2 else 0)
     return bytes(out)
+
+
+def bls_g1_from_uncompressed(enc, check_subgroup=True):
+    """PointAffine::from_uncompressed / _oncurve_only (bls12_381/serialize.rs:330-380, flags :129-140): x || y or None."""
+    c = BLSG1
+    flags = enc[0] >> 5
+    if flags & 0b101:
+        return None
+    if flags & 0b010:
+        return None          # the identity (valid only with a zero payload) has no affine form either way
+    x, y = int.from_bytes(enc[:48], "big"), int.from_bytes(enc[48:], "big")
+    if x >= c.p or y >= c.p or not c.on_curve((x, y)):
+        return None
+    if check_subgroup and not bls_g1_in_subgroup((x, y)):
+        return None
+    return bytes(enc)
+
+
+def bls_g1_to_uncompressed(xy_be, inf=0):
+    """Point::to_uncompressed (bls12_381/serialize.rs:412)."""
+    return bytes([0x40]) + bytes(95) if inf else bytes(xy_be)
 
 
 def ecdsa_verify_hashed(curve, q_xy_be, z_be, rs_be):

@@ -58,12 +58,25 @@ def ed_points(g, n):
     return rows([x.to_bytes(32, "little") + y.to_bytes(32, "little") for x, y in pts])
 
 
+def bls_cofactor_points():
+    """Points of E(Fp): y^2 = x^3 + 4 outside the prime-order subgroup G1: the two points of order 3, (0, +-2), and
+    sums of them with subgroup points (order 3 r).  Point::mul accepts any curve point (g1.rs:375-377), and these
+    are the inputs an attacker would choose: j * P is the identity for small j."""
+    c = R.WCURVES["bls12_381_g1"]
+    t3 = [(0, 2), (0, c.p - 2)]
+    assert all(c.on_curve(P) and c.mul(3, P) is None for P in t3)
+    mixed = [c.add(c.mul(k, c.G), T) for k, T in ((5, t3[0]), (0xDEADBEEF, t3[1]))]
+    return t3 + mixed
+
+
 def wei_points(curve, g, n):
     c = R.WCURVES[curve]
     base = []
     for _ in range(min(n, 16)):
         k = int.from_bytes(g.bytes(60), "little") % c.n
         base.append(c.mul(k or 1, c.G))
+    if curve == "bls12_381_g1" and n >= 12:   # small-order and mixed-order inputs among the first rows
+        base[1:1] = bls_cofactor_points()
     return rows([c.enc(base[i % len(base)]) for i in range(n)])
 
 

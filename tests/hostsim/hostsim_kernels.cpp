@@ -132,6 +132,7 @@ extern "C" unsigned long long hs_wei_mul(int curve, const u32* k, const u32* pts
         case 0: return wei_mul_run<CurveP256>(k, pts, inf_in, n, out, inf);
         case 1: return wei_mul_run<CurveP384>(k, pts, inf_in, n, out, inf);
         case 2: return wei_mul_run<CurveBLSG1>(k, pts, inf_in, n, out, inf);
+        case 3: return wei_mul_run<CurveK256>(k, pts, inf_in, n, out, inf);
     }
     return 0;
 }
@@ -228,6 +229,7 @@ extern "C" unsigned long long hs_wei_mul_base(int curve, const u32* k, size_t n,
         case 0: return wei_mul_base_run<CurveP256>(k, n, W, out, inf);
         case 1: return wei_mul_base_run<CurveP384>(k, n, W, out, inf);
         case 2: return wei_mul_base_run<CurveBLSG1>(k, n, W, out, inf);
+        case 3: return wei_mul_base_run<CurveK256>(k, n, W, out, inf);
     }
     return 0;
 }
@@ -260,6 +262,7 @@ extern "C" void hs_wei_decompress(int curve, const u32* x, const unsigned char* 
             case 0: wei_decompress_body<CurveP256>(i, x, sign, out, ok); break;
             case 1: wei_decompress_body<CurveP384>(i, x, sign, out, ok); break;
             case 2: wei_decompress_body<CurveBLSG1>(i, x, sign, out, ok); break;
+            case 3: wei_decompress_body<CurveK256>(i, x, sign, out, ok); break;
         }
     }
 }

@@ -19,7 +19,7 @@ from oracle import pyref as R
 
 pytestmark = pytest.mark.gpu
 H = bytes.fromhex
-CURVES = ("p256r1", "p384r1", "bls12_381_g1")
+CURVES = ("p256r1", "p384r1", "bls12_381_g1", "p256k1")
 NT = None
 
 
@@ -382,11 +382,11 @@ def test_wei_mul_random_and_edges(ctx, golden, coracle, curve):
     # identity inputs
     out, oinf = ctx.wei_mul(curve, kb[:64], pts[:64], inf_in=np.ones(64, dtype=np.uint8))
     assert oinf.all() and not out.any()
-    # k = n - 1 gives -P
+    # k = n - 1 gives -P (for points of the prime-order subgroup: rows 5.. — rows 1-4 of the BLS batch have order 3 or 3 r)
     km1 = rows([(c.n - 1).to_bytes(c.sbytes, "big")] * 8)
-    out, _ = ctx.wei_mul(curve, km1, pts[:8])
+    out, _ = ctx.wei_mul(curve, km1, pts[5:13])
     for i in range(8):
-        x, y = c.dec(pts[i].tobytes())
+        x, y = c.dec(pts[5 + i].tobytes())
         assert out[i].tobytes() == c.enc((x, (-y) % c.p))
 
 
@@ -950,8 +950,8 @@ def test_wei_decompress(ctx, coracle, golden, curve):
     x[0] = 0
     x[1] = np.frombuffer(c.p.to_bytes(c.fbytes, "big"), dtype=np.uint8)
     x[2] = 0xFF
-    if curve != "bls12_381_g1":
-        kat = golden["nist_p256" if curve == "p256r1" else "nist_p384"]
+    kat = {"p256r1": golden["nist_p256"], "p384r1": golden["nist_p384"], "p256k1": golden["p256k1_sage"]}.get(curve)
+    if kat:
         for i, e in enumerate(kat[:20]):
             x[10 + i] = np.frombuffer(bytes.fromhex(e["x"]), dtype=np.uint8)
             sign[10 + i] = int(e["y"], 16) & 1
@@ -959,12 +959,120 @@ def test_wei_decompress(ctx, coracle, golden, curve):
     exp, eok = coracle.wei_decompress(curve, x, sign, threads(coracle))
     assert np.array_equal(ok, eok) and np.array_equal(got, exp)
     assert not ok[1] and not ok[2] and not got[1].any() and 40 < int((~ok[100:300]).sum()) < 160
-    if curve != "bls12_381_g1":
+    if kat:
         for i, e in enumerate(kat[:20]):
             assert ok[10 + i] and got[10 + i].tobytes().hex() == e["x"] + e["y"]
     # the points the library itself produces decompress back to themselves
     assert ok[300:].all() and np.array_equal(got[300:][sign[300:] == (pts[300:, -1] & 1)], pts[300:][sign[300:] == (pts[300:, -1] & 1)])
     assert ctx.wei_decompress(curve, np.zeros((0, c.fbytes), dtype=np.uint8), np.zeros(0, dtype=np.uint8))[0].shape == (0, 2 * c.fbytes)
+
+
+def test_p256k1_reference_kats(ctx, coracle, golden):
+    """secp256k1 — the reference's p256k1 (src/curve/sec2/p256k1.rs; the a = 0 path shared with BLS12-381 G1) — through
+    the C ABI: the reference's Sage-generated k G for k = 1..100 (src/tests/sage.rs) by the comb and by the
+    variable-base windows on G, 4000 random (k, P) against the C oracle, OpenSSL's secp256k1 public keys."""
+    c = R.WCURVES["p256k1"]
+    kats = golden["p256k1_sage"]
+    ks = rows([e["k"].to_bytes(32, "big") for e in kats])
+    want = rows([H(e["x"] + e["y"]) for e in kats])
+    got, inf = ctx.wei_mul_base("p256k1", ks)
+    assert not inf.any() and np.array_equal(got, want)
+    gen = np.tile(np.frombuffer(c.enc(c.G), dtype=np.uint8), (len(kats), 1))
+    got, inf = ctx.wei_mul("p256k1", ks, gen)
+    assert not inf.any() and np.array_equal(got, want)
+    g = rng(0x256C1)
+    kb = scalars_mod(g, 4000, c.n, 32, "big")
+    pts = wei_points("p256k1", g, 4000)
+    got, inf = ctx.wei_mul("p256k1", kb, pts)
+    exp, einf = coracle.wei_mul("p256k1", kb, pts, nthreads=threads(coracle))
+    assert np.array_equal(got, exp) and np.array_equal(inf, einf)
+    ec = pytest.importorskip("cryptography.hazmat.primitives.asymmetric.ec")
+    pub, _ = ctx.wei_mul_base("p256k1", kb[:64])
+    for i in range(64):
+        nums = ec.derive_private_key(int.from_bytes(kb[i].tobytes(), "big"), ec.SECP256K1()).public_key().public_numbers()
+        assert pub[i].tobytes() == nums.x.to_bytes(32, "big") + nums.y.to_bytes(32, "big")
+
+
+def test_bls_g1_small_order_and_mixed_order_inputs(ctx, coracle):
+    """Point::mul on BLS12-381 accepts any point of E(Fp) (g1.rs:375-377): the points of order 3, (0, +-2), and points of
+    order 3 r.  For those the per-thread table of multiples holds the identity (3 P = O), which the Jacobian addition
+    has to treat as such: every digit pattern, including scalars = 0, 1, 2 mod 3 and window digits 3 and 6."""
+    from helpers import bls_cofactor_points
+
+    c = R.BLSG1
+    g = rng(0xB153)
+    pts_list = bls_cofactor_points()
+    ks = [0, 1, 2, 3, 4, 6, 10, 0x33, 0x63, 0x123456789ABCDEF, c.n - 1, c.n - 2] + [int.from_bytes(g.bytes(40), "big") % c.n for _ in range(60)]
+    kb = rows([k.to_bytes(32, "big") for k in ks for _ in pts_list])
+    pts = rows([c.enc(P) for _ in ks for P in pts_list])
+    got, inf = ctx.wei_mul("bls12_381_g1", kb, pts)
+    exp, einf = coracle.wei_mul("bls12_381_g1", kb, pts, nthreads=threads(coracle))
+    assert np.array_equal(inf, einf) and np.array_equal(got, exp)
+    for i in (4, 5, 8, 9, 20, 41):     # the big-integer group law agrees: (k mod 3) P for the order-3 points
+        assert (got[i].tobytes(), int(inf[i])) == R.wei_mul(c, kb[i].tobytes(), pts[i].tobytes())
+    assert inf[:4].all() and inf[12] and inf[13]      # k = 0; 3 * (0, +-2) = O
+
+
+def test_ed25519_decompress(ctx, golden):
+    """decode_point / Point::decompress (ed25519.rs:38-59, curve25519.rs:772) as a batch entry point: encodings of
+    library-produced points round-trip, RFC 8032 public keys decode to points that satisfy the curve, random
+    32-byte strings (about half are not points), non-canonical y, x = 0 with the sign bit; bit-exact with the
+    big-integer oracle, zero bytes where the reference returns None; the output feeds ecb_ed25519_mul."""
+    g = rng(0xDEC0)
+    kb = scalars_mod(g, 600, R.L25519, 32, "little")
+    xy = ctx.ed25519_mul_base(kb)
+    enc = ctx.ed25519_mul_base(kb, compressed=True)
+    rnd = rand_bytes(g, 400, 32)
+    bad = [(R.P25519).to_bytes(32, "little"), (R.P25519 + 1).to_bytes(32, "little"), bytes([1] + [0] * 30 + [0x80]),
+           (R.P25519 - 1 | (1 << 255)).to_bytes(32, "little"), b"\xff" * 32]
+    kat = [bytes.fromhex(v["public"]) for v in golden["ed25519_rfc8032"]]
+    allenc = np.concatenate([enc, rnd, rows(bad), rows(kat)])
+    out, ok = ctx.ed25519_decompress(allenc)
+    assert ok[:600].all() and np.array_equal(out[:600], xy)
+    assert not ok[1000:1005].any() and not out[1000:1005].any() and ok[1005:].all()
+    for i in range(600, allenc.shape[0]):
+        P = R.ed_decode(allenc[i].tobytes())
+        if P is None:
+            assert not ok[i] and not out[i].any(), i
+        else:
+            assert ok[i] and out[i].tobytes() == P[0].to_bytes(32, "little") + P[1].to_bytes(32, "little"), i
+    assert 100 < int(ok[600:1000].sum()) < 300
+    k2 = scalars_mod(g, 600, R.L25519, 32, "little")
+    assert np.array_equal(ctx.ed25519_mul(k2, out[:600]), ctx.ed25519_mul(k2, xy))
+    assert ctx.ed25519_decompress(np.zeros((0, 32), dtype=np.uint8))[0].shape == (0, 64)
+
+
+def test_bls_g1_uncompressed_encodings(ctx, golden):
+    """The 96-byte flavour (serialize.rs:330-420): the reference's uncompressed KATs (g1.rs:605-680) and OFF_SUBGROUP
+    encodings (accepted by _oncurve_only, refused with the subgroup check), flag misuse, the identity encoding
+    (refused as the reference's PointAffine cannot hold it, reported in `inf`), non-canonical and off-curve
+    coordinates; to_uncompressed round trip including the identity."""
+    c = R.BLSG1
+    v = golden["bls12_381_g1"]
+    kat = [bytes.fromhex(e["bytes"]) for e in v["uncompressed"]]
+    off_u = [bytes.fromhex(o["uncompressed"]) for o in v["off_subgroup"]]
+    g0 = kat[0]
+    ident = bytes([0x40]) + bytes(95)
+    bad = [bytes([g0[0] | 0x80]) + g0[1:], bytes([g0[0] | 0x20]) + g0[1:], bytes([0x40]) + bytes(94) + b"\x01", bytes([0x60]) + bytes(95),
+           g0[:95] + bytes([g0[95] ^ 1]), c.p.to_bytes(48, "big") + g0[48:], g0[:48] + (c.p + 2).to_bytes(48, "big")]
+    enc = rows(kat + off_u + [ident] + bad)
+    nk, no = len(kat), len(off_u)
+    out, ok, inf = ctx.bls12_381_g1_from_uncompressed(enc, True)
+    assert list(ok) == [True] * nk + [False] * (no + 1 + len(bad)) and not out[nk:].any()
+    assert list(inf) == [False] * (nk + no) + [True] + [False] * len(bad)
+    out2, ok2, _ = ctx.bls12_381_g1_from_uncompressed(enc, False)
+    assert list(ok2) == [True] * (nk + no) + [False] * (1 + len(bad)) and np.array_equal(out2[: nk + no], enc[: nk + no])
+    for i in range(enc.shape[0]):
+        for chk, o, k in ((True, out, ok), (False, out2, ok2)):
+            want = R.bls_g1_from_uncompressed(enc[i].tobytes(), chk)
+            assert (want is not None) == bool(k[i]) and (want is None or o[i].tobytes() == want), (i, chk)
+    g = rng(0x96)
+    pts, pinf = ctx.wei_mul_base("bls12_381_g1", np.concatenate([np.zeros((1, 32), dtype=np.uint8), scalars_mod(g, 300, c.n, 32, "big")]))
+    assert pinf[0] and not pinf[1:].any()
+    u = ctx.bls12_381_g1_to_uncompressed(pts, pinf)
+    assert u[0].tobytes() == ident and np.array_equal(u[1:], pts[1:])
+    back, bok, binf = ctx.bls12_381_g1_from_uncompressed(u, True)
+    assert not bok[0] and binf[0] and bok[1:].all() and np.array_equal(back[1:], pts[1:])
 
 
 def test_bls_g1_standard_encodings(ctx, coracle, golden):

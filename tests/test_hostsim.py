@@ -210,7 +210,7 @@ def test_ed25519_mul_x25519_x448(hs, coracle):
     assert np.array_equal(o, coracle.x448(ks, us))
 
 
-@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1"), (2, "bls12_381_g1")])
+@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1"), (2, "bls12_381_g1"), (3, "p256k1")])
 def test_wei_mul(hs, golden, coracle, cid, curve):
     _, k = hs
     c = R.WCURVES[curve]
@@ -329,7 +329,7 @@ def test_ed25519_keygen_and_sign(hs, golden):
         assert R.ed25519_verify(pub[i].tobytes(), msgs[i], sig[i].tobytes())
 
 
-@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1"), (2, "bls12_381_g1")])
+@pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1"), (2, "bls12_381_g1"), (3, "p256k1")])
 def test_wei_decompress(hs, coracle, cid, curve):
     """Device code of PointAffine::decompress (kernels3.cuh) against the oracle: both parities, an x
     with a non-square right-hand side, x = 0, x >= p."""

@@ -14,7 +14,7 @@ from helpers import ed_edge_scalars, rng, rows, wei_edge_scalars
 from oracle import pyref as R
 
 H = bytes.fromhex
-CURVES = ("p256r1", "p384r1", "bls12_381_g1")
+CURVES = ("p256r1", "p384r1", "bls12_381_g1", "p256k1")
 
 
 # ---- domain parameters -------------------------------------------------------------------
@@ -38,7 +38,7 @@ def test_comb_table_ed25519_matches_reference(golden, coracle):
     assert coracle.ed25519_comb_entry(3, 0) == (0).to_bytes(32, "little") + (1).to_bytes(32, "little")
 
 
-@pytest.mark.parametrize("curve,name", [("p256r1", "p256r1"), ("p384r1", "p384r1"), ("bls12_381_g1", "bls12_381")])
+@pytest.mark.parametrize("curve,name", [("p256r1", "p256r1"), ("p384r1", "p384r1"), ("bls12_381_g1", "bls12_381"), ("p256k1", "p256k1")])
 def test_comb_table_weierstrass_matches_reference(golden, coracle, curve, name):
     t, c = golden["comb_tables"][name], R.WCURVES[curve]
     assert t["windows"] == 2 * c.sbytes
@@ -310,7 +310,9 @@ def test_decompress_roundtrip_and_rejects(golden, coracle, curve):
     c = R.WCURVES[curve]
     g = rng(77 + len(curve))
     pts = [c.mul(int.from_bytes(g.bytes(40), "little") % c.n, c.G) for _ in range(12)]
-    if curve != "bls12_381_g1":
+    if curve == "p256k1":
+        pts += [(int(e["x"], 16), int(e["y"], 16)) for e in golden["p256k1_sage"][:10]]
+    elif curve != "bls12_381_g1":
         kat = golden["nist_p256" if curve == "p256r1" else "nist_p384"]
         pts += [(int(e["x"], 16), int(e["y"], 16)) for e in kat[:10]]
     xs, signs, want = [], [], []
@@ -394,6 +396,24 @@ def test_bls_g1_subgroup_check_agrees_with_the_definition(coracle):
     assert ok2.all()
     for i, e in enumerate(encs):
         assert out2[i].tobytes() == R.bls_g1_from_compressed(e, False)
+
+
+# ---- p256k1 (secp256k1): the reference's Sage-generated k G for k = 1..100 (src/tests/sage.rs) ----------
+def test_p256k1_sage_kats(golden, coracle):
+    c = R.WCURVES["p256k1"]
+    kats = golden["p256k1_sage"]
+    ks = rows([e["k"].to_bytes(32, "big") for e in kats])
+    want = rows([H(e["x"] + e["y"]) for e in kats])
+    out, inf = coracle.wei_mul_base("p256k1", ks)
+    assert not inf.any() and np.array_equal(out, want)
+    g = np.tile(np.frombuffer(c.enc(c.G), dtype=np.uint8), (len(kats), 1))
+    for mode in (coracle.MODE_WINDOW, coracle.MODE_WNAF):
+        out, inf = coracle.wei_mul("p256k1", ks, g, mode=mode)
+        assert not inf.any() and np.array_equal(out, want)
+    for e in kats[:12]:
+        assert c.enc(c.mul(e["k"], c.G)).hex() == e["x"] + e["y"]
+    # add_same / add_different of src/tests/sage.rs:1331-1356 through the group law: (a + b) G = a G + b G
+    assert c.add(c.mul(7, c.G), c.mul(9, c.G)) == (int(kats[15]["x"], 16), int(kats[15]["y"], 16))
 
 
 # ---- Weierstrass edge scalars, identity handling, cross-algorithm agreement ----------------------

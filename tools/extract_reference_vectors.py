@@ -146,7 +146,7 @@ out["x448"] = {
 
 # ---- comb tables ---------------------------------------------------------------------------
 combs = {}
-for name, fs in (("curve25519", 32), ("p256r1", 32), ("p384r1", 48), ("bls12_381", 48)):
+for name, fs in (("curve25519", 32), ("p256r1", 32), ("p384r1", 48), ("bls12_381", 48), ("p256k1", 32)):
     src = read("src/params/comb/%s.rs" % name)
     i0 = src.index("pub static COMB_TABLE")
     i1 = src.find("pub const WNAF_BASE_W", i0)
@@ -160,10 +160,19 @@ for name, fs in (("curve25519", 32), ("p256r1", 32), ("p384r1", 48), ("bls12_381
     combs[name] = {"windows": nwin, "field_bytes": fs, "sha256": hashlib.sha256(raw).hexdigest(), "samples": samples}
 out["comb_tables"] = combs
 
+# ---- p256k1 (secp256k1): k * G for k = 1..100 (src/tests/sage.rs:9-1320, Sage-generated) ----------------
+sage = read("src/tests/sage.rs")
+seg = sage[sage.index("const KATS: [KAT; 100]"):sage.index("use crate::curve::sec2::p256k1")]
+k1 = []
+for m in re.finditer(r"KAT \{\s*n: (\d+),\s*x: \[(.*?)\],\s*y: \[(.*?)\],\s*\}", seg, re.S):
+    k1.append({"k": int(m.group(1)), "x": bytes_of(m.group(2)).hex(), "y": bytes_of(m.group(3)).hex()})
+assert len(k1) == 100 and k1[0]["k"] == 1 and k1[99]["k"] == 100
+out["p256k1_sage"] = k1
+
 # ---- domain parameters -----------------------------------------------------------------------
 sec2 = read("src/params/sec2.rs")
 params = {}
-for curve in ("p256r1", "p384r1"):
+for curve in ("p256r1", "p384r1", "p256k1"):
     at = sec2.index("pub mod %s {" % curve)
     params[curve] = {n.lower().replace("_bytes", ""): const_bytes(sec2, n, at).hex() for n in ("P_BYTES", "ORDER_BYTES", "B_BYTES", "GX_BYTES", "GY_BYTES")}
 bl = read("src/params/bls12_381.rs")

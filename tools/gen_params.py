@@ -24,6 +24,12 @@ P384_B = 0xb3312fa7e23ee7e4988e056be3f82d19181d9c6efe8141120314088f5013875ac6563
 P384_GX = 0xaa87ca22be8b05378eb1c71ef320ad746e1d3b628ba79b9859f741e082542a385502f25dbf55296c3a545e3872760ab7
 P384_GY = 0x3617de4a96262c6f5d9e98bf9292dc29f8f41dbd289a147ce9da3113b5f0b8c00a60b1ce1d7e819d7a431d7c90ea0e5f
 
+# secp256k1 (the reference's p256k1, src/params/sec2.rs:908-; SEC 2 v2 section 2.4.1)
+K256_P = 2**256 - 2**32 - 977
+K256_N = 0xfffffffffffffffffffffffffffffffebaaedce6af48a03bbfd25e8cd0364141
+K256_GX = 0x79be667ef9dcbbac55a06295ce870b07029bfcdb2dce28d959f2815b16f81798
+K256_GY = 0x483ada7726a3c4655da4fbfc0e1108a8fd17b448a68554199c47d08ffb10d4b8
+
 BLS_P = 0x1a0111ea397fe69a4b1ba7b6434bacd764774b84f38512bf6730d2a0f6b0f6241eabfffeb153ffffb9feffffffffaaab
 BLS_R = 0x73eda753299d7d483339d80809a1d80553bda402fffe5bfeffffffff00000001
 BLS_GX = 0x17f1d3a73197d7942695638c4fa9ac0fc3688c4f9774b905a14e3a3f171bac586c55e83ff97a1aeffb3af00adb22c6bb
@@ -139,6 +145,8 @@ def main():
     out += field("BLS_FP", BLS_P, 12)
     out += field("BLS_FR", BLS_R, 8)
     out += field("ED_FN", ED_L, 8)
+    out += field("K256_FP", K256_P, 8)
+    out += field("K256_FN", K256_N, 8)
     K, H0, H384, K256, H256 = sha512_constants()
     out += "// ---- SHA-512 (FIPS 180-4) round constants and initial hash value\n"
     out += "ECB_CONST unsigned long long SHA512_K[80] = {%s};\n" % ", ".join("0x%016xull" % k for k in K)
@@ -148,7 +156,8 @@ def main():
     out += "ECB_CONST u32 SHA256_H0[8] = {%s};\n\n" % ", ".join("0x%08xu" % h for h in H256)
     for cname, p, n, b, gx, gy in (("P256", P256_P, 8, P256_B, P256_GX, P256_GY),
                                    ("P384", P384_P, 12, P384_B, P384_GX, P384_GY),
-                                   ("BLSG1", BLS_P, 12, 4, BLS_GX, BLS_GY)):
+                                   ("BLSG1", BLS_P, 12, 4, BLS_GX, BLS_GY),
+                                   ("K256", K256_P, 8, 7, K256_GX, K256_GY)):
         out += "// ---- curve %s (Montgomery-domain constants)\n" % cname
         out += arr(cname + "_B", mont(b, p, n), n)
         out += arr(cname + "_B3", mont(3 * b % p, p, n), n)
