@@ -70,6 +70,10 @@ SIGNATURES = {
     "ecb_bls12_381_g1_from_uncompressed": (_int, [_vp, _vp, _sz, _int, _vp, _vp, _vp]),
     "ecb_bls12_381_g1_to_uncompressed": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "ecb_ed25519_decompress": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "ecb_ristretto255_decompress": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "ecb_ristretto255_compress": (_int, [_vp, _vp, _sz, _vp]),
+    "ecb_ristretto255_mul": (_int, [_vp, _vp, _vp, _sz, _vp, _szp]),
+    "ecb_ristretto255_mul_base": (_int, [_vp, _vp, _sz, _vp, _szp]),
     "ecb_wei_decompress_dev": (_int, [_vp, _int, _int, _vp, _vp, _sz, _vp, _vp, _vp]),
     "ecb_bls12_381_g1_from_compressed_dev": (_int, [_vp, _int, _vp, _sz, _int, _vp, _vp, _vp]),
     "ecb_ed25519_public_from_seed": (_int, [_vp, _vp, _sz, _vp]),

@@ -341,6 +341,44 @@ class Context:
         self._check(self._lib.ecb_ed25519_decompress(self._ctx, _p(e), n, _p(out), _p(ok)))
         return out, ok.astype(bool)
 
+    # -- ristretto255 ---------------------------------------------------------------------------
+    def ristretto255_decompress(self, enc, out=None, out_ok=None):
+        """RistrettoPoint::decompress over a batch: (Edwards representative x || y rows, present)."""
+        e = _rows(enc, 32, "enc")
+        n = e.shape[0]
+        out = _out(out, (n, 64))
+        ok = _out(out_ok, (n,))
+        self._check(self._lib.ecb_ristretto255_decompress(self._ctx, _p(e), n, _p(out), _p(ok)))
+        return out, ok.astype(bool)
+
+    def ristretto255_compress(self, xy_le, out=None):
+        """RistrettoPoint::compress of affine edwards25519 points."""
+        p = _rows(xy_le, 64, "xy_le")
+        n = p.shape[0]
+        out = _out(out, (n, 32))
+        self._check(self._lib.ecb_ristretto255_compress(self._ctx, _p(p), n, _p(out)))
+        return out
+
+    def ristretto255_mul(self, k_le, enc, out=None):
+        """RistrettoPoint::scale on encodings."""
+        k, e = _rows(k_le, 32, "k_le"), _rows(enc, 32, "enc")
+        n = k.shape[0]
+        if e.shape[0] != n:
+            raise ValueError("count mismatch")
+        out = _out(out, (n, 32))
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_ristretto255_mul(self._ctx, _p(k), _p(e), n, _p(out), ctypes.byref(bad)), bad)
+        return out
+
+    def ristretto255_mul_base(self, k_le, out=None):
+        """RistrettoPoint::mul_base, encoded."""
+        k = _rows(k_le, 32, "k_le")
+        n = k.shape[0]
+        out = _out(out, (n, 32))
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_ristretto255_mul_base(self._ctx, _p(k), n, _p(out), ctypes.byref(bad)), bad)
+        return out
+
     def bls12_381_g1_to_compressed(self, xy_be, inf=None, out=None):
         """Point::to_compressed (bls12_381/serialize.rs:400)."""
         p = _rows(xy_be, 96, "xy_be")

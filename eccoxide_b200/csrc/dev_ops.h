@@ -15,6 +15,10 @@ int dev_ed25519_public_from_seed(ecb_ctx* ctx, DevCtx& d, const unsigned char* d
 int dev_ed25519_sign(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, const unsigned char* d_pub, const unsigned char* d_msgs,
                      const unsigned long long* d_off, size_t n, unsigned char* d_sig, cudaStream_t s, bool ct);
 int dev_ed25519_decompress(ecb_ctx* ctx, DevCtx& d, const u32* d_enc, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
+int dev_ristretto255_decompress(ecb_ctx* ctx, DevCtx& d, const u32* d_enc, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
+int dev_ristretto255_compress(ecb_ctx* ctx, DevCtx& d, const u32* d_xy, size_t n, u32* d_enc, cudaStream_t s);
+int dev_ristretto255_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_enc, size_t n, u32* d_out, cudaStream_t s);
+int dev_ristretto255_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, cudaStream_t s);
 int dev_ed25519_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_out, cudaStream_t s);
 int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, const u32* sl, const u32* kl, size_t n,
                        unsigned char* ok, cudaStream_t s);

@@ -895,6 +895,39 @@ int ecb_bls12_381_g1_to_uncompressed(ecb_ctx* ctx, const uint8_t* xy_be, const u
                            return dev_bls_g1_to_uncompressed(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0], s);
                        });
 }
+// ristretto255 (src/curve/curve25519/ristretto255.rs): encodings and the scalar multiplications between them
+int ecb_ristretto255_decompress(ecb_ctx* ctx, const uint8_t* enc, size_t n, uint8_t* xy_le, uint8_t* ok) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!enc || !xy_le || !ok)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{enc, 32}}, {{xy_le, 64}, {ok, 1}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_ristretto255_decompress(ctx, d, (const u32*)in[0], cn, (u32*)o[0], (unsigned char*)o[1], s);
+                       });
+}
+int ecb_ristretto255_compress(ecb_ctx* ctx, const uint8_t* xy_le, size_t n, uint8_t* enc) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!xy_le || !enc)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{xy_le, 64}}, {{enc, 32}}, false, nullptr,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_ristretto255_compress(ctx, d, (const u32*)in[0], cn, (u32*)o[0], s);
+                       });
+}
+int ecb_ristretto255_mul(ecb_ctx* ctx, const uint8_t* k_le, const uint8_t* enc_in, size_t n, uint8_t* enc_out, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k_le || !enc_in || !enc_out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k_le, 32}, {enc_in, 32}}, {{enc_out, 32}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_ristretto255_mul(ctx, d, (const u32*)in[0], (const u32*)in[1], cn, (u32*)o[0], s);
+                       });
+}
+int ecb_ristretto255_mul_base(ecb_ctx* ctx, const uint8_t* k_le, size_t n, uint8_t* enc_out, size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (n && (!k_le || !enc_out)) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    return run_sharded(ctx, n, {{k_le, 32}}, {{enc_out, 32}}, true, bad_index,
+                       [&](DevCtx& d, cudaStream_t s, const void** in, void** o, size_t cn) {
+                           return dev_ristretto255_mul_base(ctx, d, (const u32*)in[0], cn, (u32*)o[0], s);
+                       });
+}
 // decode_point / Point::decompress over a batch (protocol/ed25519.rs:38-59, curve25519.rs:772)
 int ecb_ed25519_decompress(ecb_ctx* ctx, const uint8_t* enc, size_t n, uint8_t* xy_le, uint8_t* ok) {
     if (!ctx) return ECB_ERR_CUDA;

@@ -3,6 +3,7 @@
 #include "dev_ops.h"
 #include "fused.cuh"
 #include "ct.cuh"
+#include "ristretto.cuh"
 
 static __global__ void __launch_bounds__(ECB_TPB, 5) k_ed25519_mul_base(size_t n, const u32* scalars, const u32* table, int W,
                                                                int nwin, int stride, u32* planes, unsigned long long* status) {
@@ -442,4 +443,44 @@ int dev_ed25519_sign(ecb_ctx* ctx, DevCtx& d, const unsigned char* d_seeds, cons
     ctx->launches++;
     CU(cudaGetLastError());
     return wipe_secrets(ctx, d, n, s);
+}
+
+// ---- ristretto255 (ristretto.cuh; src/curve/curve25519/ristretto255.rs) ------------------------------------
+static __global__ void __launch_bounds__(ECB_TPB) k_ristretto255_decompress(size_t n, const u32* enc, u32* out_xy, unsigned char* ok) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) ristretto255_decompress_body(idx, enc, out_xy, ok);
+}
+static __global__ void __launch_bounds__(ECB_TPB) k_ristretto255_compress(size_t n, const u32* xy, u32* enc) {
+    size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    if (idx < n) ristretto255_compress_body(idx, xy, enc);
+}
+int dev_ristretto255_decompress(ecb_ctx* ctx, DevCtx& d, const u32* d_enc, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s) {
+    (void)d;
+    k_ristretto255_decompress<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_enc, d_out, d_ok);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ECB_OK;
+}
+int dev_ristretto255_compress(ecb_ctx* ctx, DevCtx& d, const u32* d_xy, size_t n, u32* d_enc, cudaStream_t s) {
+    (void)d;
+    k_ristretto255_compress<<<grid_for(n), ECB_TPB, 0, s>>>(n, d_xy, d_enc);
+    ctx->launches++;
+    CU(cudaGetLastError());
+    return ECB_OK;
+}
+// RistrettoPoint::scale (ristretto255.rs:152): decode -> k * P on edwards25519 -> encode.  An invalid encoding decodes
+// to (0, 0), which the Edwards kernel reports as a bad point with its index.
+int dev_ristretto255_mul(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_enc, size_t n, u32* d_out, cudaStream_t s) {
+    TRY(ensure(ctx, d.cur->aux, n * 64));
+    u32* xy = (u32*)d.cur->aux.p;
+    TRY(dev_ristretto255_decompress(ctx, d, d_enc, n, xy, nullptr, s));
+    TRY(dev_ed25519_mul(ctx, d, d_k, xy, n, xy, s));
+    return dev_ristretto255_compress(ctx, d, xy, n, d_out, s);
+}
+// RistrettoPoint::mul_base (ristretto255.rs:157)
+int dev_ristretto255_mul_base(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, cudaStream_t s) {
+    TRY(ensure(ctx, d.cur->aux, n * 64));
+    u32* xy = (u32*)d.cur->aux.p;
+    TRY(dev_ed25519_mul_base(ctx, d, d_k, n, xy, false, s));
+    return dev_ristretto255_compress(ctx, d, xy, n, d_out, s);
 }

@@ -120,6 +120,18 @@ int ecb_ed25519_mul(ecb_ctx* ctx, const uint8_t* k_le, const uint8_t* xy_le_in, 
  * bytes where the reference returns None (y >= p, x^2 not a square, x = 0 with the sign bit set).  The output feeds
  * ecb_ed25519_mul directly. */
 int ecb_ed25519_decompress(ecb_ctx* ctx, const uint8_t* enc, size_t n, uint8_t* xy_le, uint8_t* ok);
+/* ristretto255 (src/curve/curve25519/ristretto255.rs; RFC 9496).  A RistrettoPoint wraps an edwards25519 point and is
+ * observable only through its 32-byte encoding, so the batch forms work on encodings:
+ *   decompress   RistrettoPoint::decompress (:105): enc n x 32 B -> an Edwards representative, affine x || y (n x 64 B),
+ *                ok[i] = 0 and zero bytes for the encodings RFC 9496 rejects (non-canonical or negative s, non-square, ...)
+ *   compress     RistrettoPoint::compress (:73) of affine Edwards points: equal group elements give equal bytes
+ *   mul          RistrettoPoint::scale (:152): enc_out[i] = compress(k_i * decompress(enc_in[i])); an invalid encoding
+ *                fails the call with ECB_ERR_POINT_NOT_ON_CURVE and its index, a scalar >= l with ECB_ERR_NONCANONICAL_SCALAR
+ *   mul_base     RistrettoPoint::mul_base (:157): compress(k_i * B) */
+int ecb_ristretto255_decompress(ecb_ctx* ctx, const uint8_t* enc, size_t n, uint8_t* xy_le, uint8_t* ok);
+int ecb_ristretto255_compress(ecb_ctx* ctx, const uint8_t* xy_le, size_t n, uint8_t* enc);
+int ecb_ristretto255_mul(ecb_ctx* ctx, const uint8_t* k_le, const uint8_t* enc_in, size_t n, uint8_t* enc_out, size_t* bad_index);
+int ecb_ristretto255_mul_base(ecb_ctx* ctx, const uint8_t* k_le, size_t n, uint8_t* enc_out, size_t* bad_index);
 /* protocol::ed25519 verify with k = SHA-512(R||A||M) mod l computed by the caller
  * (src/protocol/ed25519.rs:119-147).  a_enc, r_enc, s_le, k_le: n x 32 B; ok: n x 1 B (0/1). */
 int ecb_ed25519_verify_prehashed(ecb_ctx* ctx, const uint8_t* a_enc, const uint8_t* r_enc, const uint8_t* s_le,

@@ -99,6 +99,88 @@ def ed_decode(b):
     return (x, y)
 
 
+# ---- ristretto255 (RFC 9496; src/curve/curve25519/ristretto255.rs:73-134) ---------------------------------
+def _fe_neg(x):
+    return x & 1   # is_negative: the low bit of the canonical representative
+
+
+def _sqrt_ratio_m1(u, v):
+    """RFC 9496 4.2 SQRT_RATIO_M1: (was_square, nonnegative r) with r = sqrt(u / v) or sqrt(i u / v)."""
+    p = P25519
+    r = u * pow(v, 3, p) * pow(u * pow(v, 7, p) % p, (p - 5) // 8, p) % p
+    check = v * r * r % p
+    correct = check == u % p
+    flipped = check == (-u) % p
+    flipped_i = check == (-u) * SQRT_M1 % p
+    if flipped or flipped_i:
+        r = r * SQRT_M1 % p
+    if _fe_neg(r):
+        r = p - r
+    return correct or flipped, r
+
+
+RISTRETTO_INVSQRT_A_MINUS_D = _sqrt_ratio_m1(1, (-1 - ED_D) % P25519)[1]   # RFC 9496 Appendix A; sign pinned by the KATs
+
+
+def ristretto255_decompress(b):
+    """RistrettoPoint::decompress (ristretto255.rs:105): an edwards25519 representative (x, y), or None."""
+    p = P25519
+    s = int.from_bytes(b, "little")
+    if s >= p or _fe_neg(s):
+        return None
+    ss = s * s % p
+    u1, u2 = (1 - ss) % p, (1 + ss) % p
+    u2_sq = u2 * u2 % p
+    v = (-(ED_D * u1 * u1) - u2_sq) % p
+    was_square, invsqrt = _sqrt_ratio_m1(1, v * u2_sq % p)
+    den_x = invsqrt * u2 % p
+    den_y = invsqrt * den_x * v % p
+    x = 2 * s * den_x % p
+    if _fe_neg(x):
+        x = p - x
+    y = u1 * den_y % p
+    t = x * y % p
+    if not was_square or _fe_neg(t) or y == 0:
+        return None
+    return (x, y)
+
+
+def ristretto255_compress(P):
+    """RistrettoPoint::compress (ristretto255.rs:73) of the affine edwards25519 point P = (x, y)."""
+    p = P25519
+    x0, y0 = P
+    z0, t0 = 1, x0 * y0 % p
+    u1 = (z0 + y0) * (z0 - y0) % p
+    u2 = x0 * y0 % p
+    _, invsqrt = _sqrt_ratio_m1(1, u1 * u2 * u2 % p)
+    den1, den2 = invsqrt * u1 % p, invsqrt * u2 % p
+    z_inv = den1 * den2 * t0 % p
+    ix, iy = x0 * SQRT_M1 % p, y0 * SQRT_M1 % p
+    ench = den1 * RISTRETTO_INVSQRT_A_MINUS_D % p
+    rotate = _fe_neg(t0 * z_inv % p)
+    x, y, den_inv = (iy, ix, ench) if rotate else (x0, y0, den2)
+    if _fe_neg(x * z_inv % p):
+        y = (-y) % p
+    s = den_inv * (z0 - y) % p
+    if _fe_neg(s):
+        s = p - s
+    return s.to_bytes(32, "little")
+
+
+def ristretto255_mul(k_le32, enc):
+    """RistrettoPoint::scale (ristretto255.rs:152): encoding of k * P, or None for an invalid encoding / scalar."""
+    k = int.from_bytes(k_le32, "little")
+    P = ristretto255_decompress(enc)
+    if P is None or k >= L25519:
+        return None
+    return ristretto255_compress(ed_mul(k, P))
+
+
+def ristretto255_mul_base(k_le32):
+    k = int.from_bytes(k_le32, "little")
+    return None if k >= L25519 else ristretto255_compress(ed_mul(k, ED_B))
+
+
 def ed25519_mul_base_xy(k_le32):
     """Point::mul_base(&Scalar) then to_affine, as 64 bytes x_le || y_le.  Scalar must be canonical."""
     k = int.from_bytes(k_le32, "little")

@@ -5,6 +5,7 @@
 #define ECB_HOSTSIM 1
 #include "../../eccoxide_b200/csrc/kernels.cuh"
 #include "../../eccoxide_b200/csrc/ct.cuh"
+#include "../../eccoxide_b200/csrc/ristretto.cuh"
 #include <vector>
 #include <string.h>
 using namespace ecb;
@@ -315,4 +316,12 @@ static void ecdsa_sign_run(const u32* d, const u32* k, const u32* z, size_t n, u
 extern "C" void hs_ecdsa_sign(int curve, const u32* d, const u32* k, const u32* z, size_t n, u32* rs, unsigned char* ok) {
     if (curve == 0) ecdsa_sign_run<CurveP256>(d, k, z, n, rs, ok);
     else ecdsa_sign_run<CurveP384>(d, k, z, n, rs, ok);
+}
+
+// ristretto255 encodings (ristretto.cuh)
+extern "C" void hs_ristretto255_decompress(const u32* enc, size_t n, u32* xy, unsigned char* ok) {
+    for (size_t i = 0; i < n; i++) ristretto255_decompress_body(i, enc, xy, ok);
+}
+extern "C" void hs_ristretto255_compress(const u32* xy, size_t n, u32* enc) {
+    for (size_t i = 0; i < n; i++) ristretto255_compress_body(i, xy, enc);
 }

@@ -1042,6 +1042,49 @@ def test_ed25519_decompress(ctx, golden):
     assert ctx.ed25519_decompress(np.zeros((0, 32), dtype=np.uint8))[0].shape == (0, 64)
 
 
+def test_ristretto255(ctx, golden):
+    """ristretto255 (src/curve/curve25519/ristretto255.rs; RFC 9496) through the C ABI: mul_base gives the RFC's
+    encodings of 0 B .. 15 B (:341-358), the 17 bad encodings are refused (:380-398) — by decompress with ok = 0 and
+    by mul with the offender's index —, scale on encodings agrees with the big-integer oracle for 300 random (k, P)
+    and with mul_base when P = B, and the encoding does not depend on the Edwards representative."""
+    from eccoxide_b200 import EccBatchError
+
+    v = golden["ristretto255"]
+    mult = rows([bytes.fromhex(x) for x in v["multiples"]])
+    bad = rows([bytes.fromhex(x) for x in v["bad"]])
+    ks = rows([i.to_bytes(32, "little") for i in range(16)])
+    assert np.array_equal(ctx.ristretto255_mul_base(ks), mult)
+    xy, ok = ctx.ristretto255_decompress(np.concatenate([mult, bad]))
+    assert ok[:16].all() and not ok[16:].any() and not xy[16:].any()
+    assert np.array_equal(ctx.ristretto255_compress(xy[:16]), mult)
+    g = rng(9496)
+    n = 300
+    kb = scalars_mod(g, n, R.L25519, 32, "little")
+    pk = scalars_mod(g, n, R.L25519, 32, "little")
+    enc = ctx.ristretto255_mul_base(pk)
+    out = ctx.ristretto255_mul(kb, enc)
+    for i in range(0, n, 7):
+        assert enc[i].tobytes() == R.ristretto255_mul_base(pk[i].tobytes())
+        assert out[i].tobytes() == R.ristretto255_mul(kb[i].tobytes(), enc[i].tobytes()), i
+    gen = np.tile(mult[1], (n, 1))
+    assert np.array_equal(ctx.ristretto255_mul(kb, gen), ctx.ristretto255_mul_base(kb))
+    # the same group element through another Edwards representative (P + a point of order 4) encodes identically
+    pts = ctx.ed25519_mul_base(pk[:64])
+    t4 = (R.SQRT_M1, 0)
+    moved = rows([b"".join(c.to_bytes(32, "little") for c in R.ed_add((int.from_bytes(r[:32].tobytes(), "little"), int.from_bytes(r[32:].tobytes(), "little")), t4)) for r in pts])
+    assert np.array_equal(ctx.ristretto255_compress(moved), enc[:64])
+    mixed = enc[:40].copy()
+    mixed[23] = bad[3]
+    with pytest.raises(EccBatchError) as e:
+        ctx.ristretto255_mul(kb[:40], mixed)
+    assert e.value.code == -4 and e.value.bad_index == 23
+    kbad = kb[:40].copy()
+    kbad[5] = 0xFF
+    with pytest.raises(EccBatchError) as e:
+        ctx.ristretto255_mul_base(kbad)
+    assert e.value.code == -3 and e.value.bad_index == 5
+
+
 def test_bls_g1_uncompressed_encodings(ctx, golden):
     """The 96-byte flavour (serialize.rs:330-420): the reference's uncompressed KATs (g1.rs:605-680) and OFF_SUBGROUP
     encodings (accepted by _oncurve_only, refused with the subgroup check), flag misuse, the identity encoding

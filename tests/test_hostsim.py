@@ -587,3 +587,33 @@ def test_divsteps_variants_agree(hs):
         zs = [f.hs_divsteps30(k, z, f0, g0, p(t[k])) for k in range(2)]
         assert zs[0] == zs[1], (z, f0, g0)
         assert np.array_equal(t[0], t[1]), (z, f0, g0)
+
+
+def test_ristretto255_encodings(hs, golden):
+    """ristretto.cuh against RFC 9496 as the reference holds it (ristretto255.rs:341-398): the encodings of 0 B .. 15 B,
+    the 17 encodings that must be refused, round trips, and compress(P + T) == compress(P) for the 8-torsion T
+    (equality independent of the representative, :466) — bit-exact with the big-integer oracle."""
+    _, k = hs
+    v = golden["ristretto255"]
+    mult = rows([bytes.fromhex(x) for x in v["multiples"]])
+    bad = rows([bytes.fromhex(x) for x in v["bad"]])
+    enc = np.concatenate([mult, bad])
+    n = enc.shape[0]
+    xy = np.zeros((n, 64), dtype=np.uint8)
+    ok = np.zeros(n, dtype=np.uint8)
+    k.hs_ristretto255_decompress(p(enc), ctypes.c_size_t(n), p(xy), p(ok))
+    assert ok[:16].all() and not ok[16:].any() and not xy[16:].any()
+    for i in range(16):
+        P = R.ristretto255_decompress(enc[i].tobytes())
+        assert xy[i].tobytes() == P[0].to_bytes(32, "little") + P[1].to_bytes(32, "little")
+    back = np.zeros((16, 32), dtype=np.uint8)
+    k.hs_ristretto255_compress(p(xy[:16].copy()), ctypes.c_size_t(16), p(back))
+    assert np.array_equal(back, mult)
+    # multiples of B computed on edwards25519 (any representative) compress to the RFC's encodings
+    pts = [R.ed_mul(i, R.ED_B) if i else R.ED_ID for i in range(16)]
+    t4 = (R.SQRT_M1, 0)                                        # a point of order 4
+    pts2 = [R.ed_add(P, t4) for P in pts] + [R.ed_add(P, (0, R.P25519 - 1)) for P in pts]
+    allp = rows([x.to_bytes(32, "little") + y.to_bytes(32, "little") for x, y in pts + pts2])
+    out = np.zeros((48, 32), dtype=np.uint8)
+    k.hs_ristretto255_compress(p(allp), ctypes.c_size_t(48), p(out))
+    assert np.array_equal(out[:16], mult) and np.array_equal(out[16:32], mult) and np.array_equal(out[32:], mult)

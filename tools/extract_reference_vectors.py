@@ -169,6 +169,17 @@ for m in re.finditer(r"KAT \{\s*n: (\d+),\s*x: \[(.*?)\],\s*y: \[(.*?)\],\s*\}",
 assert len(k1) == 100 and k1[0]["k"] == 1 and k1[99]["k"] == 100
 out["p256k1_sage"] = k1
 
+# ---- ristretto255: RFC 9496 vectors held by src/curve/curve25519/ristretto255.rs:341-398 -----------------
+rs = read("src/curve/curve25519/ristretto255.rs")
+def _strs(name):
+    seg = rs[rs.index("const %s:" % name):]
+    seg = seg[:seg.index("];")]
+    return re.findall(r'"([0-9a-f]+)"', seg)
+uni = _strs("UNIFORM")
+out["ristretto255"] = {"multiples": _strs("MULTIPLES"), "bad": _strs("BAD"),
+                       "uniform": [{"input": uni[2 * i], "encoding": uni[2 * i + 1]} for i in range(len(uni) // 2)]}
+assert len(out["ristretto255"]["multiples"]) == 16 and len(out["ristretto255"]["bad"]) == 17
+
 # ---- domain parameters -----------------------------------------------------------------------
 sec2 = read("src/params/sec2.rs")
 params = {}
