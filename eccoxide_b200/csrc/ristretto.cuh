@@ -6,13 +6,12 @@
 // multiplication in between is k_ed25519_mul / the comb.  Affine in, affine out: Z = 1, T = x y.
 #pragma once
 #include "kernels2.cuh"
+#include "params_gen.cuh"
 
 namespace ecb {
 
-// 1 / sqrt(a - d), a = -1 (RFC 9496 Appendix A; ristretto255.rs:31), little-endian limbs.  Generated:
-// tools/models / oracle/pyref.py RISTRETTO_INVSQRT_A_MINUS_D computes it, tests pin it to the reference's bytes.
-ECB_CONST u32 RISTRETTO_INVSQRT_A_MINUS_D[8] = {0x805d40eau, 0x99c8fdaau, 0x5a4172beu, 0x9d2f1617u,
-                                                0xfe01d840u, 0x16c27b91u, 0xcfaffca2u, 0x786c8905u};
+// RISTRETTO_INVSQRT_A_MINUS_D = 1 / sqrt(a - d), a = -1 (RFC 9496 Appendix A; ristretto255.rs:31) comes from params_gen.cuh:
+// computed by tools/gen_params.py, pinned to the reference's bytes by the parity tests.
 
 ECB_DEV u32 fe_is_negative(const fe25519& a) {   // low bit of the canonical representative (field_macros.rs:837)
     fe25519 f;

@@ -41,6 +41,17 @@ def test_python_binding_covers_the_header_exactly():
     _lib.load()
 
 
+def test_rust_ffi_lists_every_exported_symbol():
+    """bindings/rust/src/ffi.rs is generated from the header (tools/gen_rust_ffi.py): one extern item per exported
+    function, the error codes and the curve ids — the committed file must be what the generator prints."""
+    import subprocess
+    import sys
+
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "gen_rust_ffi.py")], capture_output=True, text=True, check=True).stdout
+    assert out == open(os.path.join(ROOT, "bindings", "rust", "src", "ffi.rs")).read()
+    assert sorted(re.findall(r"pub fn (ecb_[a-z0-9_]+)\(", out)) == header_functions()
+
+
 def test_no_cuda_device_means_error_not_fallback():
     """Without a GPU every entry point must fail loudly (ECB_ERR_CUDA); nothing is computed on the host."""
     import torch

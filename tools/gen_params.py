@@ -133,6 +133,21 @@ def bls_beta():
     raise AssertionError("no cube root of unity acts as [-x^2] on G1")
 
 
+def ristretto_invsqrt_a_minus_d():
+    """RFC 9496 Appendix A: 1 / sqrt(a - d) on edwards25519 (a = -1), the non-negative (even) root; the parity tests
+    compare it with the bytes the reference holds (src/curve/curve25519/ristretto255.rs:31)."""
+    p = 2**255 - 19
+    d = (-121665 * pow(121666, -1, p)) % p
+    v = (-1 - d) % p
+    sm1 = pow(2, (p - 1) // 4, p)
+    r = pow(v, 3, p) * pow(pow(v, 7, p), (p - 5) // 8, p) % p      # SQRT_RATIO_M1(1, v)
+    chk = v * r * r % p
+    assert chk in (1, p - 1)
+    if chk == p - 1:
+        r = r * sm1 % p
+    return p - r if r & 1 else r
+
+
 def main():
     out = ("// GENERATED by tools/gen_params.py — do not edit.\n"
            "// Montgomery-domain constants for the Weierstrass curves of the batch path\n"
@@ -170,7 +185,9 @@ def main():
             out += "// beta: (beta x, y) = [-x^2](x, y) on G1 (subgroup test, bls12_381/g1.rs:55, :105), Montgomery domain\n"
             out += arr("BLSG1_BETA", mont(bls_beta(), p, n), n)
         out += "\n"
-    out += "}  // namespace ecb\n"
+    out += "// ---- ristretto255 (RFC 9496 Appendix A): 1 / sqrt(a - d), little-endian limbs\n"
+    out += arr("RISTRETTO_INVSQRT_A_MINUS_D", ristretto_invsqrt_a_minus_d(), 8)
+    out += "\n}  // namespace ecb\n"
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "eccoxide_b200", "csrc", "params_gen.cuh")
     with open(dst, "w") as f:
         f.write(out)
