@@ -228,11 +228,11 @@ struct F25519 {
 #ifndef ECB_HOSTSIM
     // the same inverse by one whole warp (every lane passes the same a): ~3x shorter latency, for the
     // block-level batch inversions where one inversion runs while the rest of the block waits
-    __device__ __forceinline__ static void invert_warp(el& r, const el& a) {
+    __device__ __forceinline__ static void invert_warp(el& r, const el& a, const u32* jump) {
         el c;
         freeze(c, a);
         const u32 p[8] = {0xffffffedu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu, 0x7fffffffu};
-        sg_modinv_warp<8, 9, 22>(r.v, c.v, p);
+        sg_modinv_warp<8, 9, 22>(r.v, c.v, p, jump);
     }
 #endif
     // a^((p-5)/8) (curve25519.rs:185)

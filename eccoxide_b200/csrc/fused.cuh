@@ -53,7 +53,7 @@ __device__ __forceinline__ void fe_shfl_xor(typename FT::el& r, const typename F
 //   work warps       meanwhile: suffix products, the product of the OTHER warps' totals, and from those
 //                    E = product of every other element of the block                                  | barrier
 //   work threads     z^-1 = E * inverse: one product after the inverse is known.
-// sh: (FUSED_MAXW + 1) * N words of shared memory.
+// sh: (FUSED_MAXW + 1) * N words of shared memory; jump: the safegcd jump table (modinv.cuh) staged in shared memory.
 #define FUSED_MAXW 16
 __device__ __forceinline__ unsigned long long globaltimer_ns() {
     unsigned long long t;
@@ -61,7 +61,7 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 template <class FT>
-__device__ __forceinline__ void block_invert(typename FT::el& zinv, typename FT::el z, u32& zero, u32* sh) {
+__device__ __forceinline__ void block_invert(typename FT::el& zinv, typename FT::el z, u32& zero, u32* sh, const u32* jump) {
     typedef typename FT::el fe;
     constexpr int N = FT::N;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nww = (int)(blockDim.x >> 5) - 1;
@@ -99,7 +99,7 @@ __device__ __forceinline__ void block_invert(typename FT::el& zinv, typename FT:
             fe_shfl_xor<FT>(o, t, d);
             FT::mul(t, t, o);
         }
-        FT::invert_warp(m, t);
+        FT::invert_warp(m, t, jump);
         if (lane == 0) {
 #pragma unroll
             for (int k = 0; k < N; k++) sh_inv[k] = m.v[k];
@@ -179,8 +179,9 @@ struct FusedEdMontU {       // x25519_base: u = (Z + Y) / (Z - Y), 0 when Z = Y 
 template <int LANES, bool CLAMP, class FIN>
 __device__ __forceinline__ void ed25519_mul_base_fused_block(size_t n, const u32* scalars, const u32* table, int W, int nwin,
                                                              int stride, FIN fin, unsigned long long* status, u32* sh,
-                                                             unsigned long long* trace) {
+                                                             u32* jump, unsigned long long* trace) {
     const int tid = threadIdx.x;
+    sg_stage_jump_table(jump);   // read after the first __syncthreads() of block_invert, long after these loads
     if (trace && tid == 0) trace[(size_t)blockIdx.x * 4 + 0] = globaltimer_ns();
     const int work = (int)blockDim.x - 32;
     const int l = tid % LANES;
@@ -212,7 +213,7 @@ __device__ __forceinline__ void ed25519_mul_base_fused_block(size_t n, const u32
         if (live && l == 0) fin.den(den, acc);
         u32 zero;
         if (trace && tid == 0) trace[(size_t)blockIdx.x * 4 + 1] = globaltimer_ns();
-        block_invert<F25519>(dinv, den, zero, sh);
+        block_invert<F25519>(dinv, den, zero, sh, jump);
         if (trace && tid == 0) trace[(size_t)blockIdx.x * 4 + 2] = globaltimer_ns();
         if (live && l == 0) fin(idx, acc, dinv, zero);
     }

@@ -164,13 +164,13 @@ struct F448 {
         sg_modinv<14, 15, 37>(r.v, c.v, p);
     }
 #ifndef ECB_HOSTSIM
-    __device__ __forceinline__ static void invert_warp(el& r, const el& a) {   // one warp, one element (modinv.cuh)
+    __device__ __forceinline__ static void invert_warp(el& r, const el& a, const u32* jump) {   // one warp, one element (modinv.cuh)
         el c;
         freeze(c, a);
         u32 p[14];
         ECB_UNROLL
         for (int i = 0; i < 14; i++) p[i] = (i == 7) ? 0xfffffffeu : 0xffffffffu;
-        sg_modinv_warp<14, 15, 37>(r.v, c.v, p);
+        sg_modinv_warp<14, 15, 37>(r.v, c.v, p, jump);
     }
 #endif
     // a^(p-2) = a^(2^448 - 2^224 - 3); 0 -> 0

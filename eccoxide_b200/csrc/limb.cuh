@@ -22,12 +22,14 @@
 #define ECB_UNROLL
 #define ECB_NOUNROLL
 #define ECB_CONST static const
+#define ECB_GTABLE static const
 #else
 #define ECB_DEV __device__ __forceinline__
 #define ECB_DEVNI __device__ __noinline__
 #define ECB_UNROLL _Pragma("unroll")
 #define ECB_NOUNROLL _Pragma("unroll 1")
 #define ECB_CONST static __device__ __constant__ const
+#define ECB_GTABLE static __device__ const   /* a table in global memory: copied to shared memory by coalesced loads */
 #endif
 
 namespace ecb {

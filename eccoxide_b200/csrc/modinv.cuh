@@ -16,6 +16,7 @@
 // Plain integer C++: the same code runs in the host simulation.
 #pragma once
 #include "limb.cuh"
+#include "params_gen.cuh"
 
 namespace ecb {
 
@@ -90,6 +91,48 @@ ECB_DEV s32 sg_divsteps30_var(s32 zeta, u32 f0, u32 g0, s32& tu, s32& tv, s32& t
     return zeta;
 }
 
+
+// The same 30 divsteps, four at a time through a table.  Four steps depend only on the low four bits of f (odd)
+// and g and on where zeta sits relative to zero, so their combined transition matrix and the new zeta are
+// tabulated (SG_JUMP4, 1408 words, generated and documented by tools/gen_params.py: safegcd_jump_table): seven
+// lookups and two single steps replace ~10 data-dependent trips of sg_divsteps30_var.  With one warp per SM —
+// the block-level inversions — a trip of that loop costs ~120 cycles (BREV + FLO for the ctz, a dependent chain
+// of ~25 instructions); a lookup is one shared-memory load plus ~12 multiply-adds that do not wait on each other.
+// tbl: the table in shared memory (device) or SG_JUMP4 itself (host simulation).
+ECB_DEV s32 sg_divsteps30_jump(s32 zeta, u32 f0, u32 g0, s32& tu, s32& tv, s32& tq, s32& tr, const u32* tbl) {
+    u32 U = 1, V = 0, Q = 0, R = 1, f = f0, g = g0;
+    ECB_UNROLL
+    for (int it = 0; it < 7; it++) {
+        s32 zc = zeta < -6 ? -6 : (zeta > 4 ? 4 : zeta);
+        const u32 e = tbl[((u32)(zc + 6) * 8u + ((f >> 1) & 7u)) * 16u + (g & 15u)];
+        const u32 mu = (u32)((s32)(e << 26) >> 26), mv = (u32)((s32)(e << 20) >> 26);
+        const u32 mq = (u32)((s32)(e << 14) >> 26), mr = (u32)((s32)(e << 8) >> 26);
+        const s32 off = (s32)(e << 2) >> 26;
+        zeta = ((e >> 30) & 1u ? -zeta : zeta) + off;
+        const u32 nf = (mu * f + mv * g) >> 4, ng = (mq * f + mr * g) >> 4;
+        const u32 nU = mu * U + mv * Q, nV = mu * V + mv * R, nQ = mq * U + mr * Q, nR = mq * V + mr * R;
+        f = nf; g = ng; U = nU; V = nV; Q = nQ; R = nR;
+    }
+    ECB_UNROLL
+    for (int i = 0; i < 2; i++) {   // steps 29 and 30, one at a time (the loop body of sg_divsteps30)
+        u32 c1 = (u32)(zeta >> 31);
+        u32 c2 = 0u - (g & 1u);
+        u32 x = (f ^ c1) - c1, y = (U ^ c1) - c1, z = (V ^ c1) - c1;
+        g += x & c2;
+        Q += y & c2;
+        R += z & c2;
+        c1 &= c2;
+        zeta = (zeta ^ (s32)c1) - 1;
+        f += g & c1;
+        U += Q & c1;
+        V += R & c1;
+        g >>= 1;
+        U <<= 1;
+        V <<= 1;
+    }
+    tu = (s32)U; tv = (s32)V; tq = (s32)Q; tr = (s32)R;
+    return zeta;
+}
 
 // NW 32-bit words (little-endian, value < 2^(32 NW)) <-> NL signed 30-bit limbs (30 NL >= 32 NW + 2)
 template <int NW, int NL>
@@ -218,10 +261,15 @@ ECB_DEV void sg_modinv(u32* r, const u32* a, const u32* p) {
 // partially normalised (in [-8, 2^30 + 8]; the low limb is exact mod 2^30, which is all the divsteps
 // read).  The sign of d, e is then read from the top limb alone; a wrong guess within 2^-40 of zero
 // loosens the (-2p, p) bound by one p, which the final reduction absorbs.  Ranges and results are
-// checked lane for lane in tools/models/safegcd_warp_model.py.
+// checked lane for lane in tools/models/safegcd_warp_model.py.  The divsteps come from the jump table
+// (sg_divsteps30_jump), which the caller stages in shared memory with sg_stage_jump_table.
 // ---------------------------------------------------------------------------------------------------
+// every thread of the block copies its share of SG_JUMP4 into `sh` (SG_JUMP_WORDS words); the caller synchronises
+__device__ __forceinline__ void sg_stage_jump_table(u32* sh) {
+    for (int i = (int)threadIdx.x; i < SG_JUMP_WORDS; i += (int)blockDim.x) sh[i] = SG_JUMP4[i];
+}
 template <int NW, int NL, int MAXB>
-__device__ __forceinline__ void sg_modinv_warp(u32* r, const u32* a, const u32* p) {
+__device__ __forceinline__ void sg_modinv_warp(u32* r, const u32* a, const u32* p, const u32* jump) {
     static_assert(NL <= 16, "one limb per lane: NL <= 16");
     const unsigned FULL = 0xffffffffu;
     const int lane = (int)(threadIdx.x & 31u), j = lane & 15;
@@ -247,7 +295,7 @@ __device__ __forceinline__ void sg_modinv_warp(u32* r, const u32* a, const u32* 
         const s32 d0 = __shfl_sync(FULL, x, 16), e0 = __shfl_sync(FULL, y, 16);
         const s32 sd = __shfl_sync(FULL, x, 16 + NL - 1) >> 31, se = __shfl_sync(FULL, y, 16 + NL - 1) >> 31;
         s32 u, v, q, rr;
-        zeta = sg_divsteps30_var(zeta, f0, g0, u, v, q, rr);
+        zeta = sg_divsteps30_jump(zeta, f0, g0, u, v, q, rr, jump);   // jump: SG_JUMP4 staged in shared memory
         s32 md = (u & sd) + (v & se), me = (q & sd) + (rr & se);
         const u32 cd = (u32)u * (u32)d0 + (u32)v * (u32)e0, ce = (u32)q * (u32)d0 + (u32)rr * (u32)e0;
         md -= (s32)((pinv * cd + (u32)md) & (u32)M30);

@@ -482,13 +482,13 @@ struct Mont {
         mul(r, t, r2);
     }
 #ifndef ECB_HOSTSIM
-    __device__ __forceinline__ static void invert_warp(el& r, const el& a) {   // one warp, one element (modinv.cuh)
+    __device__ __forceinline__ static void invert_warp(el& r, const el& a, const u32* jump) {   // one warp, one element (modinv.cuh)
         el c, t, r2;
         canon(c, a);
         u32 p[N];
         ECB_UNROLL
         for (int i = 0; i < N; i++) { p[i] = P::mod(i); r2.v[i] = P::r2(i); }
-        sg_modinv_warp<N, (32 * N + 2 + 29) / 30, (N <= 8 ? 22 : 32)>(t.v, c.v, p);
+        sg_modinv_warp<N, (32 * N + 2 + 29) / 30, (N <= 8 ? 22 : 32)>(t.v, c.v, p, jump);
         mul(t, t, r2);
         mul(r, t, r2);
     }

@@ -53,6 +53,8 @@ __global__ void __launch_bounds__(ECB_TPB) k_batch_inv(size_t T, size_t n, const
     constexpr int PER_LANE = ECB_TPB / 32;
     __shared__ u32 sh_tot[N * ECB_TPB];   // chain totals, then their inverses (limb-major: conflict-free)
     __shared__ u32 sh_pre[N * ECB_TPB];   // running products inside a lane's PER_LANE entries
+    __shared__ u32 jump[SG_JUMP_WORDS];   // safegcd jump table (modinv.cuh), read after the __syncthreads() below
+    sg_stage_jump_table(jump);
     const int tid = threadIdx.x, lane = tid & 31;
     size_t t = (size_t)blockIdx.x * ECB_TPB + tid;
     fe accA, accB, inv;
@@ -83,7 +85,7 @@ __global__ void __launch_bounds__(ECB_TPB) k_batch_inv(size_t T, size_t n, const
         }
         fe total, tinv, exP, exS;
         fe_shfl<FT>(total, P, 31);
-        FT::invert_warp(tinv, total);              // the 32 lanes compute ONE inverse together (modinv.cuh)
+        FT::invert_warp(tinv, total, jump);              // the 32 lanes compute ONE inverse together (modinv.cuh)
         fe_shfl<FT>(exP, P, lane > 0 ? lane - 1 : 0);
         fe_shfl<FT>(exS, S, lane < 31 ? lane + 1 : 31);
         if (lane == 0) exP = one;

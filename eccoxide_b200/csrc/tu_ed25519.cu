@@ -22,7 +22,8 @@ static __global__ void __launch_bounds__(MAXT, MINB) k_ed25519_mul_base_fused(si
                                                                       int stride, FIN fin, unsigned long long* status,
                                                                       unsigned long long* trace) {
     __shared__ u32 sh[(FUSED_MAXW + 1) * 8];
-    ed25519_mul_base_fused_block<LANES, CLAMP, FIN>(n, scalars, table, W, nwin, stride, fin, status, sh, trace);
+    __shared__ u32 jump[SG_JUMP_WORDS];
+    ed25519_mul_base_fused_block<LANES, CLAMP, FIN>(n, scalars, table, W, nwin, stride, fin, status, sh, jump, trace);
 }
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_window_bases(int nwin, int W, u32* bases) {
     int i = (int)(blockIdx.x * ECB_TPB + threadIdx.x);

@@ -75,6 +75,9 @@ int dev_fieldmul_probe(ecb_ctx* ctx, DevCtx& d, int num, int den, int blocks_per
 template <int V>
 __global__ void __launch_bounds__(512, 1) k_latency_probe(int reps, double* out_cycles, double* out_mhz, u32* sink) {
     __shared__ u32 sh[(FUSED_MAXW + 1) * 8];
+    __shared__ u32 jump[SG_JUMP_WORDS];
+    sg_stage_jump_table(jump);
+    __syncthreads();
     fe25519 x, y;
 #pragma unroll
     for (int i = 0; i < 8; i++) { x.v[i] = 0x9e3779b9u * (threadIdx.x + 1 + i) + blockIdx.x; y.v[i] = 0x85ebca6bu * (threadIdx.x + 3 + i) ^ 0x1234567u; }
@@ -92,11 +95,11 @@ __global__ void __launch_bounds__(512, 1) k_latency_probe(int reps, double* out_
         else if (V == 1) F::sqr(x, x);
         else if (V == 2) { F::invert(x, x); x.v[0] ^= 5u; }
         else if (V == 3) { F::invert_fermat(x, x); x.v[0] ^= 5u; }
-        else if (V == 4) { u32 z; fe25519 o; block_invert<F25519>(o, x, z, sh); x = o; x.v[0] ^= 5u; }
+        else if (V == 4) { u32 z; fe25519 o; block_invert<F25519>(o, x, z, sh, jump); x = o; x.v[0] ^= 5u; }
         else if (V == 5) { fe25519 o; fe_shfl_up<F25519>(o, x, 1); x = o; x.v[0] += 1u; }
         else if (V == 6) ge_madd_rt(P, P, e, true);
         else if (V == 8) F::mul2(x, x, y, P.X, P.X, y);
-        else if (V == 9) { fe25519 o; fe_shfl_idx<F25519>(o, x, 0); F::invert_warp(x, o); x.v[0] ^= 5u; }
+        else if (V == 9) { fe25519 o; fe_shfl_idx<F25519>(o, x, 0); F::invert_warp(x, o, jump); x.v[0] ^= 5u; }
         else ge_add_p3<true>(P, P, P);
     }
     long long t1 = clock64();

@@ -26,11 +26,12 @@ template <class P> static void mont_op(int op, const u32* a, const u32* b, u32* 
 }
 
 extern "C" {
-// 30 divsteps on the low words: variant 0 = one step at a time (constant time), 1 = zero runs by ctz (modinv.cuh)
+// 30 divsteps on the low words: variant 0 = one step at a time (constant time), 1 = zero runs by ctz, 2 = jump table (modinv.cuh)
 int hs_divsteps30(int variant, int zeta, u32 f0, u32 g0, int* t) {
     s32 u, v, q, r, z;
     if (variant == 0) z = sg_divsteps30(zeta, f0, g0, u, v, q, r);
-    else z = sg_divsteps30_var(zeta, f0, g0, u, v, q, r);
+    else if (variant == 1) z = sg_divsteps30_var(zeta, f0, g0, u, v, q, r);
+    else z = sg_divsteps30_jump(zeta, f0, g0, u, v, q, r, SG_JUMP4);
     t[0] = u; t[1] = v; t[2] = q; t[3] = r;
     return z;
 }

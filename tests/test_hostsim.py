@@ -561,17 +561,18 @@ def test_safegcd_inversion_25519_and_448(hs):
 
 
 def test_divsteps_variants_agree(hs):
-    """The two forms of 30 divsteps (modinv.cuh: one step at a time, and zero runs shifted out by ctz with up to four
-    bits cancelled per trip) give the same transition matrix and the same zeta — on random words and along the
-    trajectories of real inversions, where zeta hovers around zero and nearly every odd step swaps."""
+    """The three forms of 30 divsteps (modinv.cuh: one step at a time; zero runs shifted out by ctz with up to four
+    bits cancelled per trip; four steps per lookup in the generated jump table SG_JUMP4, which the warp-level
+    inversion uses) give the same transition matrix and the same zeta — on random words, at every zeta around the
+    clamp boundaries of the table, and along the trajectories of real inversions."""
     f, _ = hs
     g = rng(77)
-    t = [np.zeros(4, dtype=np.int32) for _ in range(2)]
+    t = [np.zeros(4, dtype=np.int32) for _ in range(3)]
     cases = []
     for _ in range(3000):
         z = int(g.integers(-40, 40))
         cases.append((z, int(g.integers(0, 1 << 30)) | 1, int(g.integers(0, 1 << 30))))
-    for z in (-31, -30, -2, -1, 0, 1, 29, 30, 31):
+    for z in (-31, -30, -8, -7, -6, -5, -4, -3, -2, -1, 0, 1, 2, 3, 4, 5, 6, 29, 30, 31):
         for g0 in (0, 1, 2, 4, 8, 1 << 29, (1 << 30) - 1, (1 << 30) - 2):
             cases.append((z, (1 << 30) - 19, g0))
     P = R.P25519
@@ -584,9 +585,9 @@ def test_divsteps_variants_agree(hs):
             u, v, q, r = (int(x) for x in t[0])
             fv, a = (u * fv + v * a) >> 30, (q * fv + r * a) >> 30
     for z, f0, g0 in cases:
-        zs = [f.hs_divsteps30(k, z, f0, g0, p(t[k])) for k in range(2)]
-        assert zs[0] == zs[1], (z, f0, g0)
-        assert np.array_equal(t[0], t[1]), (z, f0, g0)
+        zs = [f.hs_divsteps30(k, z, f0, g0, p(t[k])) for k in range(3)]
+        assert zs[0] == zs[1] == zs[2], (z, f0, g0)
+        assert np.array_equal(t[0], t[1]) and np.array_equal(t[0], t[2]), (z, f0, g0)
 
 
 def test_ristretto255_encodings(hs, golden):

@@ -133,6 +133,50 @@ def bls_beta():
     raise AssertionError("no cube root of unity acts as [-x^2] on G1")
 
 
+def safegcd_jump_table(K=4):
+    """Jump table of the safegcd divsteps (csrc/modinv.cuh sg_divsteps30_jump): K = 4 steps at a time.
+    K steps depend only on f mod 2^K (odd), g mod 2^K and on where zeta sits relative to zero, so they are tabulated:
+    index = ((clamp(zeta, -6, 4) + 6) * 8 + (f >> 1 & 7)) * 16 + (g & 15); entry = the K-step transition matrix
+    (u, v, q, r), [f', g'] = M [f, g] / 2^K, as four 6-bit signed fields, and the new zeta as sgn * zeta + off
+    (off: 6 bits signed at bit 24, sgn at bit 30).  The two clamped classes are affine in zeta: zeta >= 4 never
+    swaps within four steps, zeta <= -6 swaps at most once (at the first odd g) and stays positive afterwards.
+    The device function is checked against 30 single steps in tests/test_hostsim.py."""
+    M = 0xffffffff
+
+    def step(zeta, f, g, u, v, q, r):   # one divstep, as sg_divsteps30
+        c1, c2 = zeta < 0, g & 1
+        x, y, z = ((-f) & M, (-u) & M, (-v) & M) if c1 else (f, u, v)
+        if c2:
+            g, q, r = (g + x) & M, (q + y) & M, (r + z) & M
+        c = c1 and c2
+        zeta = (~zeta if c else zeta) - 1
+        if c:
+            f, u, v = (f + g) & M, (u + q) & M, (v + r) & M
+        return zeta, f, g >> 1, (u << 1) & M, (v << 1) & M, q, r
+
+    def run(zeta, f, g):
+        u, v, q, r = 1, 0, 0, 1
+        for _ in range(K):
+            zeta, f, g, u, v, q, r = step(zeta, f, g, u, v, q, r)
+        sg = lambda t: t - (1 << 32) if t >> 31 else t
+        return zeta, (sg(u), sg(v), sg(q), sg(r))
+
+    tbl = []
+    for zc in range(11):
+        zs = [zc - 6] if 0 < zc < 10 else ([-6, -7] if zc == 0 else [4, 5])
+        for fi in range(8):
+            for gi in range(16):
+                outs = [run(z, 2 * fi + 1, gi) for z in zs]
+                assert len({o[1] for o in outs}) == 1
+                sgn = (outs[0][0] - outs[1][0]) * (zs[0] - zs[1]) if len(zs) == 2 else 1
+                off = outs[0][0] - sgn * zs[0]
+                assert sgn in (1, -1) and all(o[0] == sgn * z + off for z, o in zip(zs, outs))
+                u, v, q, r = outs[0][1]
+                assert all(-32 <= t <= 31 for t in (u, v, q, r, off))
+                tbl.append((u & 63) | ((v & 63) << 6) | ((q & 63) << 12) | ((r & 63) << 18) | ((off & 63) << 24) | ((1 if sgn < 0 else 0) << 30))
+    return tbl
+
+
 def ristretto_invsqrt_a_minus_d():
     """RFC 9496 Appendix A: 1 / sqrt(a - d) on edwards25519 (a = -1), the non-negative (even) root; the parity tests
     compare it with the bytes the reference holds (src/curve/curve25519/ristretto255.rs:31)."""
@@ -187,6 +231,10 @@ def main():
         out += "\n"
     out += "// ---- ristretto255 (RFC 9496 Appendix A): 1 / sqrt(a - d), little-endian limbs\n"
     out += arr("RISTRETTO_INVSQRT_A_MINUS_D", ristretto_invsqrt_a_minus_d(), 8)
+    jt = safegcd_jump_table()
+    out += "\n// ---- safegcd jump table (csrc/modinv.cuh sg_divsteps30_jump): 4 divsteps per entry, see tools/gen_params.py\n"
+    out += "#define SG_JUMP_WORDS %d\n" % len(jt)
+    out += "ECB_GTABLE u32 SG_JUMP4[SG_JUMP_WORDS] = {%s};\n" % ", ".join("0x%08xu" % e for e in jt)
     out += "\n}  // namespace ecb\n"
     dst = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "eccoxide_b200", "csrc", "params_gen.cuh")
     with open(dst, "w") as f:
