@@ -99,7 +99,7 @@ def test_ed25519_mul_base_fused_small_batch_every_lane_count(lanes, coracle, gol
     with Context() as c:
         c.set_option("ed25519_lanes", lanes)
         c.ed25519_mul_base(edge[:2])                  # builds the comb table (its launches are not the call's)
-        cap = 148 * 512 // max(lanes, 1)
+        cap = 148 * 480 // max(lanes, 1)
         for n in (1, 31, 33, 1 << 10, 1 << 12, (1 << 13) + 5, 1 << 14, 1 << 15, 1 << 16, 75776, (1 << 17) + 77):
             kb = big[:n].copy()
             m = min(n, edge.shape[0])
