@@ -70,6 +70,7 @@ SIGNATURES = {
     "ecb_bls12_381_g1_from_uncompressed": (_int, [_vp, _vp, _sz, _int, _vp, _vp, _vp]),
     "ecb_bls12_381_g1_to_uncompressed": (_int, [_vp, _vp, _vp, _sz, _vp]),
     "ecb_ed25519_decompress": (_int, [_vp, _vp, _sz, _vp, _vp]),
+    "ecb_wei_msm": (_int, [_vp, _int, _vp, _vp, _sz, _vp, _vp, _szp]),
     "ecb_ristretto255_decompress": (_int, [_vp, _vp, _sz, _vp, _vp]),
     "ecb_ristretto255_compress": (_int, [_vp, _vp, _sz, _vp]),
     "ecb_ristretto255_mul": (_int, [_vp, _vp, _vp, _sz, _vp, _szp]),

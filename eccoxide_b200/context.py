@@ -341,6 +341,21 @@ class Context:
         self._check(self._lib.ecb_ed25519_decompress(self._ctx, _p(e), n, _p(out), _p(ok)))
         return out, ok.astype(bool)
 
+    def wei_msm(self, curve, k_be, xy_be):
+        """sum_i k_i * P_i (bucket method, csrc/msm.cuh) on bls12_381_g1 / p256k1: (x || y bytes, is_identity)."""
+        cid = CURVE_IDS[curve] if isinstance(curve, str) else curve
+        fb, sb = FIELD_BYTES[cid], SCALAR_BYTES[cid]
+        k = _rows(k_be, sb, "k_be")
+        p = _rows(xy_be, 2 * fb, "xy_be")
+        n = k.shape[0]
+        if p.shape[0] != n:
+            raise ValueError("scalar/point count mismatch")
+        out = np.zeros(2 * fb, dtype=np.uint8)
+        inf = np.zeros(1, dtype=np.uint8)
+        bad = ctypes.c_size_t()
+        self._check(self._lib.ecb_wei_msm(self._ctx, cid, _p(k), _p(p), n, _p(out), _p(inf), ctypes.byref(bad)), bad)
+        return out, bool(inf[0])
+
     # -- ristretto255 ---------------------------------------------------------------------------
     def ristretto255_decompress(self, enc, out=None, out_ok=None):
         """RistrettoPoint::decompress over a batch: (Edwards representative x || y rows, present)."""

@@ -38,6 +38,11 @@ int dev_wei_mul_k256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, co
 int dev_wei_mul_base_k256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
 int dev_wei_decompress_k256(ecb_ctx* ctx, DevCtx& d, const u32* d_x, const unsigned char* d_sign, size_t n, u32* d_out, unsigned char* d_ok, cudaStream_t s);
 int dev_wei_table_k256(ecb_ctx* ctx, DevCtx& d);
+// multi-scalar multiplication (msm.cuh): the device's partial sum of its slice, then the sum of the partials made affine
+int dev_wei_msm_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_partial, cudaStream_t s);
+int dev_wei_msm_finish_bls(ecb_ctx* ctx, DevCtx& d, const u32* d_partials, int np, u32* d_out, unsigned char* d_inf, cudaStream_t s);
+int dev_wei_msm_k256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, const u32* d_p, size_t n, u32* d_partial, cudaStream_t s);
+int dev_wei_msm_finish_k256(ecb_ctx* ctx, DevCtx& d, const u32* d_partials, int np, u32* d_out, unsigned char* d_inf, cudaStream_t s);
 // fixed base (comb): d_out / d_inf as dev_wei_mul_*; *_table makes sure the device comb exists
 int dev_wei_mul_base_p256(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);
 int dev_wei_mul_base_p384(ecb_ctx* ctx, DevCtx& d, const u32* d_k, size_t n, u32* d_out, unsigned char* d_inf, cudaStream_t s);

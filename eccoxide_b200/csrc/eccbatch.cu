@@ -895,6 +895,91 @@ int ecb_bls12_381_g1_to_uncompressed(ecb_ctx* ctx, const uint8_t* xy_be, const u
                            return dev_bls_g1_to_uncompressed(ctx, d, (const u32*)in[0], (const unsigned char*)in[1], cn, (u32*)o[0], s);
                        });
 }
+// Multi-scalar multiplication sum_i k_i P_i (csrc/msm.cuh): every device reduces its contiguous slice to one Jacobian
+// point, the partial sums are copied to the first device (the one cross-device step of this library) and added there.
+int ecb_wei_msm(ecb_ctx* ctx, int curve, const uint8_t* k_be, const uint8_t* xy_be, size_t n, uint8_t* out_xy, uint8_t* out_inf,
+                size_t* bad_index) {
+    if (!ctx) return ECB_ERR_CUDA;
+    if (bad_index) *bad_index = (size_t)-1;
+    size_t fb, sb;
+    if (curve_sizes(curve, fb, sb) || (curve != ECB_CURVE_BLS12_381_G1 && curve != ECB_CURVE_P256K1))
+        return set_err(ctx, ECB_ERR_INVALID_ARG, "ecb_wei_msm: bls12_381_g1 and p256k1 only");
+    if (!out_xy || !out_inf || (n && (!k_be || !xy_be))) return set_err(ctx, ECB_ERR_INVALID_ARG, "null buffer");
+    if (n >= ((size_t)1 << 31)) return set_err(ctx, ECB_ERR_INVALID_ARG, "ecb_wei_msm: n must be below 2^31");
+    if (n == 0) {   // the empty sum is the identity
+        memset(out_xy, 0, 2 * fb);
+        *out_inf = 1;
+        return ECB_OK;
+    }
+    const int nd_all = (int)ctx->devs.size();
+    const int nd = n < (size_t)nd_all * 1024 ? 1 : nd_all;   // tiny batches stay on one device
+    const size_t pw = 3 * (fb / 4) * sizeof(u32);
+    std::vector<int> rc(nd, ECB_OK);
+    std::vector<unsigned long long> bad(nd, ~0ull);
+    DevCtx& d0 = *ctx->devs[0];
+    {   // room for the partial sums on the first device
+        std::lock_guard<std::mutex> g(d0.mu);
+        if (cudaSetDevice(d0.dev) != cudaSuccess) return set_err(ctx, ECB_ERR_CUDA, "cudaSetDevice");
+        d0.cur = &d0.slots[0];
+        TRY(ensure(ctx, d0.slots[0].in[2], (size_t)nd * pw));
+    }
+    auto worker = [&](int di) {
+        DevCtx& d = *ctx->devs[di];
+        size_t lo = n * (size_t)di / nd, hi = n * (size_t)(di + 1) / nd, cn = hi - lo;
+        std::lock_guard<std::mutex> g(d.mu);
+        auto body = [&]() -> int {
+            CU(cudaSetDevice(d.dev));
+            Slot& sl = d.slots[0];
+            d.cur = &sl;
+            cudaStream_t s = sl.stream;
+            TRY(ensure(ctx, sl.in[0], cn * sb));
+            TRY(ensure(ctx, sl.in[1], cn * 2 * fb));
+            TRY(ensure(ctx, sl.out[0], pw));
+            CU(cudaMemcpyAsync(sl.in[0].p, k_be + lo * sb, cn * sb, cudaMemcpyHostToDevice, s));
+            CU(cudaMemcpyAsync(sl.in[1].p, xy_be + lo * 2 * fb, cn * 2 * fb, cudaMemcpyHostToDevice, s));
+            if (curve == ECB_CURVE_BLS12_381_G1) TRY(dev_wei_msm_bls(ctx, d, (const u32*)sl.in[0].p, (const u32*)sl.in[1].p, cn, (u32*)sl.out[0].p, s));
+            else TRY(dev_wei_msm_k256(ctx, d, (const u32*)sl.in[0].p, (const u32*)sl.in[1].p, cn, (u32*)sl.out[0].p, s));
+            CU(cudaMemcpyAsync(sl.h_status, sl.d_status, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s));
+            CU(cudaMemcpyPeerAsync((char*)d0.slots[0].in[2].p + (size_t)di * pw, d0.dev, sl.out[0].p, d.dev, pw, s));
+            CU(cudaStreamSynchronize(s));
+            if (*sl.h_status != ~0ull) bad[di] = (((*sl.h_status >> 8) + lo) << 8) | (*sl.h_status & 0xff);
+            return ECB_OK;
+        };
+        rc[di] = body();
+        if (rc[di] != ECB_OK) cudaStreamSynchronize(d.slots[0].stream);
+    };
+    if (nd == 1) {
+        worker(0);
+    } else {
+        std::vector<std::thread> th;
+        for (int i = 0; i < nd; i++) th.emplace_back(worker, i);
+        for (auto& t : th) t.join();
+    }
+    for (int i = 0; i < nd; i++)
+        if (rc[i] != ECB_OK) return rc[i];
+    unsigned long long first = ~0ull;
+    for (int i = 0; i < nd; i++)
+        if (bad[i] < first) first = bad[i];
+    if (first != ~0ull) {
+        if (bad_index) *bad_index = (size_t)(first >> 8);
+        int code = (first & 0xff) == ecb::ST_NONCANONICAL_SCALAR ? ECB_ERR_NONCANONICAL_SCALAR : ECB_ERR_POINT_NOT_ON_CURVE;
+        return set_err(ctx, code, code == ECB_ERR_NONCANONICAL_SCALAR ? "non-canonical scalar" : "point not on curve");
+    }
+    std::lock_guard<std::mutex> g(d0.mu);
+    CU(cudaSetDevice(d0.dev));
+    Slot& sl = d0.slots[0];
+    d0.cur = &sl;
+    TRY(ensure(ctx, sl.out[1], 2 * fb + 16));
+    u32* o = (u32*)sl.out[1].p;
+    unsigned char* oi = (unsigned char*)sl.out[1].p + 2 * fb;
+    if (curve == ECB_CURVE_BLS12_381_G1) TRY(dev_wei_msm_finish_bls(ctx, d0, (const u32*)sl.in[2].p, nd, o, oi, sl.stream));
+    else TRY(dev_wei_msm_finish_k256(ctx, d0, (const u32*)sl.in[2].p, nd, o, oi, sl.stream));
+    CU(cudaMemcpyAsync(out_xy, o, 2 * fb, cudaMemcpyDeviceToHost, sl.stream));
+    CU(cudaMemcpyAsync(out_inf, oi, 1, cudaMemcpyDeviceToHost, sl.stream));
+    CU(cudaStreamSynchronize(sl.stream));
+    if (sl.hi) CU(cudaStreamSynchronize(sl.hi));
+    return ECB_OK;
+}
 // ristretto255 (src/curve/curve25519/ristretto255.rs): encodings and the scalar multiplications between them
 int ecb_ristretto255_decompress(ecb_ctx* ctx, const uint8_t* enc, size_t n, uint8_t* xy_le, uint8_t* ok) {
     if (!ctx) return ECB_ERR_CUDA;

@@ -5,6 +5,8 @@
 #define ECB_TU_TABLE_FN dev_wei_table_bls
 #define ECB_TU_BASE_FN dev_wei_mul_base_bls
 #define ECB_TU_DECOMP_FN dev_wei_decompress_bls
+#define ECB_TU_MSM_FN dev_wei_msm_bls
+#define ECB_TU_MSM_FINISH_FN dev_wei_msm_finish_bls
 #include "tu_wei.inc"
 
 // ---- BLS12-381 G1 standard encodings (bls12_381/serialize.rs) ---------------------------------------

@@ -5,4 +5,6 @@
 #define ECB_TU_TABLE_FN dev_wei_table_k256
 #define ECB_TU_BASE_FN dev_wei_mul_base_k256
 #define ECB_TU_DECOMP_FN dev_wei_decompress_k256
+#define ECB_TU_MSM_FN dev_wei_msm_k256
+#define ECB_TU_MSM_FINISH_FN dev_wei_msm_finish_k256
 #include "tu_wei.inc"

@@ -189,6 +189,15 @@ int ecb_wei_mul(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, const uint8_t* 
 /* Point::mul_base(&Scalar) -> to_affine   (fiat/curve_macros.rs:55 -> projective.rs:965/:945) */
 int ecb_wei_mul_base(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, size_t n, uint8_t* out_xy_be, uint8_t* out_inf,
                      size_t* bad_index);
+/* Multi-scalar multiplication: sum_i k_i * P_i -> to_affine (the reference lists it as a wish, TODO.md:48, :99-100; the
+ * value is what folding its own `&P * &k` (projective.rs:842) with `+` (:268) over the batch gives).  Bucket method
+ * (csrc/msm.cuh): signed windows of up to 16 bits, counting sort of the digits, one thread per bucket.  curve_id:
+ * ECB_CURVE_BLS12_381_G1 or ECB_CURVE_P256K1.  k_be: n x SB canonical scalars; xy_be: n x 2FB affine points on the curve
+ * (any subgroup); out_xy_be: 2FB bytes (zeros for the identity), out_inf: 1 byte.  n == 0 gives the identity.  The
+ * batch is sliced over the devices of the context; each reduces its slice and the partial sums are added on the
+ * first device — the one operation of this library with a cross-device step. */
+int ecb_wei_msm(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, const uint8_t* xy_be, size_t n, uint8_t* out_xy_be, uint8_t* out_inf,
+                size_t* bad_index);
 /* ecdsa::sign_hashed::<O>(&secret, &nonce, hashed) -> CtOption<Signature> (src/protocol/ecdsa.rs:165-184), batched
  * (SURVEY 8 f.3).  d_be (secret), k_be (nonce), z_be (message scalar): n x SB bytes each;
  * rs_be: n x 2SB bytes r || s; ok[i] = 0 (and zero output) where the reference reports no signature: secret or

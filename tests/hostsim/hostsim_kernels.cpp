@@ -6,6 +6,8 @@
 #include "../../eccoxide_b200/csrc/kernels.cuh"
 #include "../../eccoxide_b200/csrc/ct.cuh"
 #include "../../eccoxide_b200/csrc/ristretto.cuh"
+static inline unsigned atomicAdd(unsigned* p, unsigned v) { unsigned o = *p; *p += v; return o; }   // one thread at a time here
+#include "../../eccoxide_b200/csrc/msm.cuh"
 #include <vector>
 #include <string.h>
 using namespace ecb;
@@ -324,4 +326,33 @@ extern "C" void hs_ristretto255_decompress(const u32* enc, size_t n, u32* xy, un
 }
 extern "C" void hs_ristretto255_compress(const u32* xy, size_t n, u32* enc) {
     for (size_t i = 0; i < n; i++) ristretto255_compress_body(i, xy, enc);
+}
+
+// multi-scalar multiplication (msm.cuh): the kernels' bodies in launch order, window width c given
+template <class C>
+static unsigned long long msm_run(const u32* k, const u32* pts, size_t n, int c, u32* out, unsigned char* inf) {
+    constexpr int N = C::F::N;
+    typedef Msm<C> M;
+    const int nwin = (C::SBITS + 1 + c - 1) / c;
+    const u32 NB = 1u << (c - 1);
+    const size_t nb = (size_t)nwin * NB;
+    std::vector<u32> pm(n * 2 * N), dig((size_t)nwin * n), idx((size_t)nwin * n), hist(nb, 0), offs(nb, 0), cursor(nb, 0), bsum(nb * M::PW), part(M::PW);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) msm_prepare_body<C>(i, n, k, pts, c, nwin, NB, pm.data(), dig.data(), hist.data(), &st);
+    u32 run = 0;
+    for (size_t b = 0; b < nb; b++) { offs[b] = run; run += hist[b]; }
+    for (size_t i = 0; i < n; i++) msm_scatter_body(i, n, nwin, NB, dig.data(), offs.data(), cursor.data(), idx.data());
+    for (size_t b = 0; b < nb; b++) msm_bucket_body<C>(b, NB, offs.data(), hist.data(), idx.data(), pm.data(), bsum.data());
+    for (u32 half = NB >> 1; half >= 1; half >>= 1)
+        for (size_t t = 0; t < (size_t)nwin * half; t++) msm_reduce_body<C>(t, NB, half, bsum.data());
+    msm_window_body<C>(c, nwin, NB, bsum.data(), part.data());
+    std::vector<u32> planes(3 * N), pf(N);
+    msm_combine_body<C>(1, part.data(), planes.data());
+    FinWeiXY<C> fin{planes.data(), 1, out, inf};
+    batch_inv_body<typename C::F>(0, 1, 1, planes.data(), pf.data(), fin);
+    return st;
+}
+extern "C" unsigned long long hs_wei_msm(int curve, const u32* k, const u32* pts, size_t n, int c, u32* out, unsigned char* inf) {
+    if (curve == 2) return msm_run<CurveBLSG1>(k, pts, n, c, out, inf);
+    return msm_run<CurveK256>(k, pts, n, c, out, inf);
 }

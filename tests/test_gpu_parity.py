@@ -746,6 +746,17 @@ def test_context_over_all_visible_devices_shards_by_contiguous_slice(coracle):
         assert np.array_equal(c.ed25519_mul_base(kb), coracle.ed25519_mul_base(kb, threads(coracle)))
         k, u = rand_bytes(g, n, 32), rand_bytes(g, n, 32)
         assert np.array_equal(c.x25519(k, u), coracle.x25519(k, u, threads(coracle)))
+        # multi-scalar multiplication: every device reduces its slice, the partial sums meet on the first device
+        cb = R.WCURVES["bls12_381_g1"]
+        m, period = 1 << 15, 256
+        tb = scalars_mod(g, period, cb.n, 32, "big")
+        basepts, _ = c.wei_mul_base("bls12_381_g1", tb)
+        km = scalars_mod(g, m, cb.n, 32, "big")
+        tv = [int.from_bytes(r.tobytes(), "big") for r in tb]
+        total = sum(int.from_bytes(km[i].tobytes(), "big") * tv[i % period] for i in range(m)) % cb.n
+        want, _ = c.wei_mul_base("bls12_381_g1", rows([total.to_bytes(32, "big")]))
+        got, ginf = c.wei_msm("bls12_381_g1", km, np.ascontiguousarray(np.tile(basepts, (m // period, 1))))
+        assert not ginf and got.tobytes() == want[0].tobytes()
         kb[n - 7] = 0xFF  # first offender reported with its global index whichever device owns it
         kb[n // 2 + 1] = 0xFF
         with pytest.raises(EccBatchError) as e:
@@ -1040,6 +1051,62 @@ def test_ed25519_decompress(ctx, golden):
     k2 = scalars_mod(g, 600, R.L25519, 32, "little")
     assert np.array_equal(ctx.ed25519_mul(k2, out[:600]), ctx.ed25519_mul(k2, xy))
     assert ctx.ed25519_decompress(np.zeros((0, 32), dtype=np.uint8))[0].shape == (0, 64)
+
+
+@pytest.mark.parametrize("curve", ["bls12_381_g1", "p256k1"])
+def test_wei_msm(ctx, coracle, curve):
+    """ecb_wei_msm (csrc/msm.cuh, the bucket method): sum_i k_i P_i.  Small batches against the big-integer group law
+    (duplicates, P and -P with equal scalars, zero scalars, n = 0 and 1, and on BLS12-381 points outside G1); 2^18
+    points P_i = t_i G against (sum k_i t_i mod n) G from the generator comb — an exact check of the whole sum;
+    invalid scalars / points are refused with their index."""
+    from eccoxide_b200 import EccBatchError
+    from helpers import bls_cofactor_points
+
+    c = R.WCURVES[curve]
+    g = rng(0x3530 + len(curve))
+    pts = [c.mul(int.from_bytes(g.bytes(40), "big") % c.n or 1, c.G) for _ in range(60)]
+    if curve == "bls12_381_g1":
+        pts += bls_cofactor_points()
+    ks = [int.from_bytes(g.bytes(40), "big") % c.n for _ in pts]
+    pts += [pts[0], pts[1], c.neg(pts[2]), pts[3]]
+    ks += [ks[0], ks[1], ks[2], 0]
+    want = None
+    for kk, P in zip(ks, pts):
+        want = c.add(want, c.mul(kk, P)) if kk else want
+    kb = rows([v.to_bytes(c.sbytes, "big") for v in ks])
+    pb = rows([c.enc(P) for P in pts])
+    out, inf = ctx.wei_msm(curve, kb, pb)
+    assert not inf and out.tobytes() == c.enc(want)
+    out, inf = ctx.wei_msm(curve, kb[:1], pb[:1])
+    assert not inf and out.tobytes() == c.enc(c.mul(ks[0], pts[0]))
+    out, inf = ctx.wei_msm(curve, kb[:0], pb[:0])
+    assert inf and not out.any()
+    out, inf = ctx.wei_msm(curve, rows([kb[0].tobytes()] * 2), rows([c.enc(pts[0]), c.enc(c.neg(pts[0]))]))
+    assert inf and not out.any()
+    # a large batch: P_i = t_(i mod period) G
+    n, period = 1 << 18, 1 << 10
+    tb = scalars_mod(g, period, c.n, c.sbytes, "big")
+    base, binf = ctx.wei_mul_base(curve, tb)
+    assert not binf.any()
+    kbig = g.integers(0, 256, size=(n, c.sbytes), dtype=np.uint8)
+    kbig[:, 0] &= 0x3F if curve == "bls12_381_g1" else 0x7F
+    tv = [int.from_bytes(r.tobytes(), "big") for r in tb]
+    total = sum(int.from_bytes(kbig[i].tobytes(), "big") * tv[i % period] for i in range(n)) % c.n
+    exp, einf = ctx.wei_mul_base(curve, rows([total.to_bytes(c.sbytes, "big")]))
+    out, inf = ctx.wei_msm(curve, kbig, np.ascontiguousarray(np.tile(base, (n // period, 1))))
+    assert inf == bool(einf[0]) and out.tobytes() == exp[0].tobytes()
+    assert out.tobytes() == coracle.wei_mul_base(curve, rows([total.to_bytes(c.sbytes, "big")]))[0][0].tobytes()
+    # refusals
+    kbad = kb.copy()
+    kbad[7] = 0xFF
+    with pytest.raises(EccBatchError) as e:
+        ctx.wei_msm(curve, kbad, pb)
+    assert e.value.code == -3 and e.value.bad_index == 7
+    pbad = pb.copy()
+    pbad[11, -1] ^= 1
+    with pytest.raises(EccBatchError) as e:
+        ctx.wei_msm(curve, kb, pbad)
+    assert e.value.code == -4 and e.value.bad_index == 11
 
 
 def test_ristretto255(ctx, golden):

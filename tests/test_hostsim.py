@@ -21,7 +21,7 @@ def hs():
     subprocess.check_call(["make", "-s", "-j4", "-C", HS])
     f = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_fields.so"))
     k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
-    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_wei_mul_base_ct", "hs_ecdsa_verify"):
+    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_wei_mul_base_ct", "hs_wei_msm", "hs_ecdsa_verify"):
         getattr(k, fn).restype = ctypes.c_ulonglong
     return f, k
 
@@ -618,3 +618,41 @@ def test_ristretto255_encodings(hs, golden):
     out = np.zeros((48, 32), dtype=np.uint8)
     k.hs_ristretto255_compress(p(allp), ctypes.c_size_t(48), p(out))
     assert np.array_equal(out[:16], mult) and np.array_equal(out[16:32], mult) and np.array_equal(out[32:], mult)
+
+
+@pytest.mark.parametrize("cid,curve", [(2, "bls12_381_g1"), (3, "p256k1")])
+def test_wei_msm_bucket_method(hs, cid, curve):
+    """msm.cuh (signed windows, counting sort, bucket sums, j * B, tree sum, Horner) against the big-integer group law:
+    sum_i k_i P_i for random (k, P), with the cases the Jacobian additions must survive inside a bucket — the same
+    point twice with the same digit (P + P), P and -P with the same scalar (cancel to the identity), zero scalars —
+    and, on BLS12-381, points outside the prime-order subgroup; window widths 4, 5 and 9."""
+    _, k = hs
+    c = R.WCURVES[curve]
+    g = rng(700 + cid)
+    pts = [c.mul(int.from_bytes(g.bytes(40), "big") % c.n or 1, c.G) for _ in range(40)]
+    if curve == "bls12_381_g1":
+        from helpers import bls_cofactor_points
+
+        pts += bls_cofactor_points()
+    ks = [int.from_bytes(g.bytes(40), "big") % c.n for _ in pts]
+    pts += [pts[0], pts[1], c.neg(pts[2]), pts[3]]          # duplicates / opposite points ...
+    ks += [ks[0], ks[1], ks[2], 0]                           # ... with equal scalars, and a zero scalar
+    ks[5] = c.n - 1
+    ks[6] = 1
+    want = None
+    for kk, P in zip(ks, pts):
+        want = c.add(want, c.mul(kk, P)) if kk else want
+    kb = rows([v.to_bytes(c.sbytes, "big") for v in ks])
+    pb = rows([c.enc(P) for P in pts])
+    for cw in (4, 5, 9):
+        out = np.zeros(2 * c.fbytes, dtype=np.uint8)
+        inf = np.zeros(1, dtype=np.uint8)
+        assert k.hs_wei_msm(cid, p(kb), p(pb), ctypes.c_size_t(len(ks)), cw, p(out), p(inf)) == 2**64 - 1
+        assert not inf[0] and out.tobytes() == c.enc(want), cw
+    # everything cancels: k P + k (-P) -> the identity
+    kb2 = rows([ks[0].to_bytes(c.sbytes, "big")] * 2)
+    pb2 = rows([c.enc(pts[0]), c.enc(c.neg(pts[0]))])
+    out = np.zeros(2 * c.fbytes, dtype=np.uint8)
+    inf = np.zeros(1, dtype=np.uint8)
+    k.hs_wei_msm(cid, p(kb2), p(pb2), ctypes.c_size_t(2), 4, p(out), p(inf))
+    assert inf[0] and not out.any()
