@@ -75,6 +75,15 @@ ECB_DEV u32 madc_hi_cc(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.cc.u3
 ECB_DEV u32 madc_hi(u32 a, u32 b, u32 c) { u32 r; asm volatile("madc.hi.u32 %0,%1,%2,%3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
 #endif
 
+// word i of a multi-word value shifted left by s (0 < s < 32): (hi << s) | (lo >> (32 - s)), one SHF.L.W
+ECB_DEV u32 shl_word(u32 lo, u32 hi, int s) {
+#ifdef ECB_HOSTSIM
+    return (hi << s) | (lo >> (32 - s));
+#else
+    return __funnelshift_l(lo, hi, s);
+#endif
+}
+
 // ---------------------------------------------------------------------------
 // Wide multiply-accumulate chains ("even/odd" column layout).
 //

@@ -146,7 +146,7 @@ struct Mont {
             r.v[4] = subc_cc(t[4], c);
             ECB_UNROLL
             for (int i = 5; i < N; i++) r.v[i] = subc_cc(t[i], 0u);
-            return subc(0u, 0u) & 1u;
+            return 0u - subc(0u, 0u);   // 0 or 1; written so that its range stays unknown to the compiler (refold_borrow must remain a loop)
         }
         r.v[0] = sub_cc(t[0], c);
         r.v[1] = subc_cc(t[1], 0u);
@@ -156,7 +156,69 @@ struct Mont {
         r.v[5] = subc_cc(t[5], m);
         r.v[6] = subc_cc(t[6], m << 1);
         r.v[7] = subc_cc(t[7], 0u);
-        return subc(0u, 0u) & 1u;
+        return 0u - subc(0u, 0u);   // 0 or 1; written so that its range stays unknown to the compiler (refold_borrow must remain a loop)
+    }
+
+    // ---- loose representation, small multiples.  r = t + c (2^(32N) - p) mod 2^(32N) for a small c (0 <= c < 2^16),
+    // returns the carry out.  The limbs of c (2^256 - p) = c 2^224 - c 2^192 - c 2^96 + c are
+    // {c, 0, 0, -c, ~0, ~0, ~c, c - 1} for c >= 1 (all zero for c = 0); of c (2^384 - p) = c 2^128 + c 2^96 - c 2^32 + c:
+    // {c, -c, ~0, c - 1, c, 0, ...}.
+    ECB_DEV static u32 fold_carry_small(el& r, const u32* t, u32 c) {
+        const u32 nz = 0u - (u32)(c != 0u);
+        if constexpr (MontKind<P>::kind == 2) {
+            r.v[0] = add_cc(t[0], c);
+            r.v[1] = addc_cc(t[1], 0u - c);
+            r.v[2] = addc_cc(t[2], nz);
+            r.v[3] = addc_cc(t[3], (c - 1u) & nz);
+            r.v[4] = addc_cc(t[4], c);
+            ECB_UNROLL
+            for (int i = 5; i < N; i++) r.v[i] = addc_cc(t[i], 0u);
+            return addc(0u, 0u);
+        }
+        r.v[0] = add_cc(t[0], c);
+        r.v[1] = addc_cc(t[1], 0u);
+        r.v[2] = addc_cc(t[2], 0u);
+        r.v[3] = addc_cc(t[3], 0u - c);
+        r.v[4] = addc_cc(t[4], nz);
+        r.v[5] = addc_cc(t[5], nz);
+        r.v[6] = addc_cc(t[6], ~c & nz);
+        r.v[7] = addc_cc(t[7], (c - 1u) & nz);
+        return addc(0u, 0u);
+    }
+    // r = t - c (2^(32N) - p) mod 2^(32N), returns the borrow
+    ECB_DEV static u32 fold_borrow_small(el& r, const u32* t, u32 c) {
+        const u32 nz = 0u - (u32)(c != 0u);
+        if constexpr (MontKind<P>::kind == 2) {
+            r.v[0] = sub_cc(t[0], c);
+            r.v[1] = subc_cc(t[1], 0u - c);
+            r.v[2] = subc_cc(t[2], nz);
+            r.v[3] = subc_cc(t[3], (c - 1u) & nz);
+            r.v[4] = subc_cc(t[4], c);
+            ECB_UNROLL
+            for (int i = 5; i < N; i++) r.v[i] = subc_cc(t[i], 0u);
+            return 0u - subc(0u, 0u);   // 0 or 1; written so that its range stays unknown to the compiler (refold_borrow must remain a loop)
+        }
+        r.v[0] = sub_cc(t[0], c);
+        r.v[1] = subc_cc(t[1], 0u);
+        r.v[2] = subc_cc(t[2], 0u);
+        r.v[3] = subc_cc(t[3], 0u - c);
+        r.v[4] = subc_cc(t[4], nz);
+        r.v[5] = subc_cc(t[5], nz);
+        r.v[6] = subc_cc(t[6], ~c & nz);
+        r.v[7] = subc_cc(t[7], (c - 1u) & nz);
+        return 0u - subc(0u, 0u);   // 0 or 1; written so that its range stays unknown to the compiler (refold_borrow must remain a loop)
+    }
+    // The fold itself can carry once more (t within c 2^224 of 2^(32N)): about one operand pair in 2^32.  The repeat
+    // is a LOOP so that the assembler keeps it a branch: written as `if`, it becomes eight predicated instructions
+    // that every field addition then issues for nothing (6 % of the issue slots of a P-256 doubling).  The second fold
+    // cannot carry (the value is below c 2^224 by then).
+    ECB_DEV static void refold_carry(el& r, u32 c2) {
+        ECB_NOUNROLL
+        for (; c2 != 0u; c2--) (void)fold_carry(r, r.v, 1u);
+    }
+    ECB_DEV static void refold_borrow(el& r, u32 b2) {
+        ECB_NOUNROLL
+        for (; b2 != 0u; b2--) (void)fold_borrow(r, r.v, 1u);
     }
 
     // ---- p384: one round at limb offset O.  t = T[O..O+3); m = t (1 + 2^32 + 2^64) mod 2^96;
@@ -369,8 +431,7 @@ struct Mont {
         u32 t[N];
         u32 c = add_n<N>(t, a.v, b.v);
         if constexpr (LOOSE) {
-            u32 c2 = fold_carry(r, t, c);
-            if (c2) fold_carry(r, r.v, 1u);
+            refold_carry(r, fold_carry(r, t, c));
             return;
         }
         final_sub(r, t, c);
@@ -379,8 +440,7 @@ struct Mont {
         u32 t[N];
         u32 bw = sub_n<N>(t, a.v, b.v);
         if constexpr (LOOSE) {
-            u32 b2 = fold_borrow(r, t, bw);
-            if (b2) fold_borrow(r, r.v, 1u);
+            refold_borrow(r, fold_borrow(r, t, bw));
             return;
         }
         u32 m = 0u - bw;
@@ -402,6 +462,66 @@ struct Mont {
         copy(r, a);
     }
     ECB_DEV static void dbl(el& r, const el& a) { add(r, a, a); }
+
+    // ---- merged forms for the point formulas.  On the loose fields each is ONE pass with a single fold of the
+    // accumulated carries / borrows (a separate add or sub costs 8 + 8 fold instructions and the alu pipe is as
+    // loaded as the multiplier in the P-256 kernels); on the canonical fields they are the plain sequences.
+    // r = K a, K in {2, 3, 4, 8}
+    template <int K>
+    ECB_DEV static void mul_small(el& r, const el& a) {
+        static_assert(K == 2 || K == 3 || K == 4 || K == 8, "small multiple");
+        if constexpr (LOOSE && K != 2) {
+            constexpr int S = (K == 8) ? 3 : (K == 4) ? 2 : 1;
+            u32 t[N];
+            u32 c = a.v[N - 1] >> (32 - S);
+            ECB_UNROLL
+            for (int i = N - 1; i > 0; i--) t[i] = shl_word(a.v[i - 1], a.v[i], S);
+            t[0] = a.v[0] << S;
+            if constexpr (K == 3) {
+                t[0] = add_cc(t[0], a.v[0]);
+                ECB_UNROLL
+                for (int i = 1; i < N; i++) t[i] = addc_cc(t[i], a.v[i]);
+                c += addc(0u, 0u);
+            }
+            refold_carry(r, fold_carry_small(r, t, c));
+            return;
+        }
+        if constexpr (K == 2) { add(r, a, a); return; }
+        el d;
+        add(d, a, a);
+        if constexpr (K == 3) { add(r, d, a); return; }
+        add(d, d, d);
+        if constexpr (K == 4) { copy(r, d); return; }
+        add(r, d, d);
+    }
+    // r = a - b - c
+    ECB_DEV static void sub2(el& r, const el& a, const el& b, const el& c) {
+        if constexpr (LOOSE) {
+            u32 t[N];
+            u32 bw = sub_n<N>(t, a.v, b.v);
+            bw += sub_n<N>(t, t, c.v);
+            refold_borrow(r, fold_borrow_small(r, t, bw));
+            return;
+        }
+        el d;
+        sub(d, a, b);
+        sub(r, d, c);
+    }
+    // r = a - b - 2c
+    ECB_DEV static void sub_2x(el& r, const el& a, const el& b, const el& c) {
+        if constexpr (LOOSE) {
+            u32 t[N];
+            u32 bw = sub_n<N>(t, a.v, b.v);
+            bw += sub_n<N>(t, t, c.v);
+            bw += sub_n<N>(t, t, c.v);
+            refold_borrow(r, fold_borrow_small(r, t, bw));
+            return;
+        }
+        el d;
+        sub(d, a, b);
+        sub(d, d, c);
+        sub(r, d, c);
+    }
 
     ECB_DEV static u32 is_zero(const el& a) {
         u32 o = 0;

@@ -152,23 +152,17 @@ struct WeiJ {
             F::sub(t0, p.X, delta);
             F::add(t1, p.X, delta);
             F::mul_ni(t0, t0, t1);
-            F::dbl(alpha, t0);
-            F::add(alpha, alpha, t0);   // 3 (X - delta)(X + delta)
+            F::template mul_small<3>(alpha, t0);   // 3 (X - delta)(X + delta)
             F::add(t1, p.Y, p.Z);
             F::sqr_ni(Z3, t1);
-            F::sub(Z3, Z3, gamma);
-            F::sub(Z3, Z3, delta);      // (Y + Z)^2 - gamma - delta
+            F::sub2(Z3, Z3, gamma, delta);         // (Y + Z)^2 - gamma - delta
             F::sqr_ni(X3, alpha);
-            F::dbl(t0, beta);
-            F::dbl(t0, t0);             // 4 beta
-            F::dbl(t1, t0);             // 8 beta
-            F::sub(X3, X3, t1);
+            F::template mul_small<4>(t0, beta);    // 4 beta
+            F::sub2(X3, X3, t0, t0);               // alpha^2 - 8 beta
             F::sub(t0, t0, X3);
             F::mul_ni(Y3, alpha, t0);
             F::sqr_ni(t1, gamma);
-            F::dbl(t1, t1);
-            F::dbl(t1, t1);
-            F::dbl(t1, t1);             // 8 gamma^2
+            F::template mul_small<8>(t1, t1);      // 8 gamma^2
             F::sub(Y3, Y3, t1);
             F::copy(r.X, X3);
             F::copy(r.Y, Y3);
@@ -180,21 +174,16 @@ struct WeiJ {
             F::sqr_ni(Cc, B);
             F::add(t, p.X, B);
             F::sqr_ni(D, t);
-            F::sub(D, D, A);
-            F::sub(D, D, Cc);
+            F::sub2(D, D, A, Cc);
             F::dbl(D, D);               // 2((X + B)^2 - A - C)
-            F::dbl(E, A);
-            F::add(E, E, A);            // 3A
+            F::template mul_small<3>(E, A);   // 3A
             F::sqr_ni(Fv, E);
-            F::dbl(t, D);
-            F::sub(X3, Fv, t);
+            F::sub2(X3, Fv, D, D);      // F - 2D
             F::mul_ni(Z3, p.Y, p.Z);
             F::dbl(Z3, Z3);
             F::sub(t, D, X3);
             F::mul_ni(Y3, E, t);
-            F::dbl(Cc, Cc);
-            F::dbl(Cc, Cc);
-            F::dbl(Cc, Cc);             // 8C
+            F::template mul_small<8>(Cc, Cc);   // 8C
             F::sub(Y3, Y3, Cc);
             F::copy(r.X, X3);
             F::copy(r.Y, Y3);
@@ -249,29 +238,23 @@ struct WeiJ {
         fe HH;
         F::dbl(rr, rr);             // r = 2 (S2 - S1)
         F::sqr_ni(HH, H);
-        F::dbl(I, HH);
-        F::dbl(I, I);               // I = 4 H^2
+        F::template mul_small<4>(I, HH);   // I = 4 H^2
         F::mul_ni(J, H, I);
         F::mul_ni(V, U1, I);
         F::sqr_ni(X3, rr);
-        F::sub(X3, X3, J);
-        F::sub(X3, X3, V);
-        F::sub(X3, X3, V);
+        F::sub_2x(X3, X3, J, V);    // r^2 - J - 2V
         F::sub(t, V, X3);
         F::mul_ni(Y3, rr, t);
         F::mul_ni(t, S1, J);
-        F::dbl(t, t);
-        F::sub(Y3, Y3, t);
+        F::sub2(Y3, Y3, t, t);      // r (V - X3) - 2 S1 J
         if (QAFF) {
             F::add(t, p.Z, H);      // Z3 = (Z1 + H)^2 - Z1Z1 - HH = 2 Z1 H
             F::sqr_ni(Z3, t);
-            F::sub(Z3, Z3, Z1Z1);
-            F::sub(Z3, Z3, HH);
+            F::sub2(Z3, Z3, Z1Z1, HH);
         } else {
             F::add(t, p.Z, q.Z);
             F::sqr_ni(Z3, t);
-            F::sub(Z3, Z3, Z1Z1);
-            F::sub(Z3, Z3, q.ZZ);
+            F::sub2(Z3, Z3, Z1Z1, q.ZZ);
             F::mul_ni(Z3, Z3, H);
         }
         F::copy(r.X, X3);
@@ -327,25 +310,20 @@ struct WeiJ {
         }
         F::dbl(rr, rr);
         F::sqr_ni(HH, H);
-        F::dbl(I, HH);
-        F::dbl(I, I);
+        F::template mul_small<4>(I, HH);
         F::mul_ni(J, H, I);
         F::mul_ni(V, U1, I);
         F::sqr_ni(X3, rr);
-        F::sub(X3, X3, J);
-        F::sub(X3, X3, V);
-        F::sub(X3, X3, V);
+        F::sub_2x(X3, X3, J, V);
         F::sub(t, V, X3);
         F::mul_ni(Y3, rr, t);
         F::mul_ni(t, S1, J);
-        F::dbl(t, t);
-        F::sub(Y3, Y3, t);
+        F::sub2(Y3, Y3, t, t);
         ld(q.v, e + 2 * N);                 // Z2
         F::add(t, p.Z, q);
         F::sqr_ni(Z3, t);
-        F::sub(Z3, Z3, Z1Z1);
         ld(q.v, e + 3 * N);                 // Z2^2 again
-        F::sub(Z3, Z3, q);
+        F::sub2(Z3, Z3, Z1Z1, q);
         F::mul_ni(Z3, Z3, H);
         F::copy(r.X, X3);
         F::copy(r.Y, Y3);

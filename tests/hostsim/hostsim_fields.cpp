@@ -21,6 +21,24 @@ template <class P> static void mont_op(int op, const u32* a, const u32* b, u32* 
         case 5: F::to_mont(z, a); break;
         case 6: F::invert(z, x); break;
         case 7: F::from_mont(z.v, x); break;
+        case 8: F::template mul_small<2>(z, x); break;
+        case 9: F::template mul_small<3>(z, x); break;
+        case 10: F::template mul_small<4>(z, x); break;
+        case 11: F::template mul_small<8>(z, x); break;
+        case 12: F::copy(z, x); F::template mul_small<8>(z, z); break;   // in place
+    }
+    memcpy(r, z.v, 4 * P::N);
+}
+// merged three-operand forms: op 0 = a - b - c, 1 = a - b - 2c, 2 = the same with the result aliasing a
+template <class P> static void mont_op3(int op, const u32* a, const u32* b, const u32* c, u32* r) {
+    typedef Mont<P> F;
+    typename F::el x, y, w, z;
+    memcpy(x.v, a, 4 * P::N); memcpy(y.v, b, 4 * P::N); memcpy(w.v, c, 4 * P::N);
+    switch (op) {
+        case 0: F::sub2(z, x, y, w); break;
+        case 1: F::sub_2x(z, x, y, w); break;
+        case 2: F::sub2(x, x, y, w); F::copy(z, x); break;
+        case 3: F::sub_2x(x, x, y, w); F::copy(z, x); break;
     }
     memcpy(r, z.v, 4 * P::N);
 }
@@ -101,6 +119,16 @@ void hs_mont(int field, int op, const u32* a, const u32* b, u32* r) {
         case 3: mont_op<P384_FN>(op, a, b, r); break;
         case 4: mont_op<BLS_FP>(op, a, b, r); break;
         case 5: mont_op<BLS_FR>(op, a, b, r); break;
+    }
+}
+void hs_mont3(int field, int op, const u32* a, const u32* b, const u32* c, u32* r) {
+    switch (field) {
+        case 0: mont_op3<P256_FP>(op, a, b, c, r); break;
+        case 1: mont_op3<P256_FN>(op, a, b, c, r); break;
+        case 2: mont_op3<P384_FP>(op, a, b, c, r); break;
+        case 3: mont_op3<P384_FN>(op, a, b, c, r); break;
+        case 4: mont_op3<BLS_FP>(op, a, b, c, r); break;
+        case 5: mont_op3<BLS_FR>(op, a, b, c, r); break;
     }
 }
 }

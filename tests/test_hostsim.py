@@ -457,6 +457,53 @@ def test_montgomery_fields_structured_operands(hs, field, mod, n):
                 assert val(r) == exp % mod, (field, op, hex(a), hex(b))
 
 
+@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (2, R.P384.p, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
+def test_montgomery_merged_forms(hs, field, mod, n):
+    """K a (K = 2, 3, 4, 8), a - b - c and a - b - 2c in one pass with a single fold of the accumulated carries /
+    borrows (mont.cuh: mul_small, sub2, sub_2x) — on the loose fields every n-limb operand is valid, including the
+    ones whose fold carries again; on the canonical fields the plain sequences must give canonical results."""
+    f, _ = hs
+    g = rng(300 + field)
+    Rm = 1 << (32 * n)
+    loose = field in (0, 2)
+    top = Rm if loose else mod
+    K = Rm - mod
+    r = np.zeros(n, dtype=np.uint32)
+    cases = []
+    if loose:
+        edge = [0, 1, K - 1, K, K + 1, mod - 1, mod, mod + 1, Rm - 1, Rm - 2, Rm - K, Rm - K - 1, Rm - K + 1, Rm - 2 * K, Rm - 3 * K, Rm - 8 * K,
+                (Rm >> 1) - 1, Rm >> 1, (Rm >> 2) + 1, (Rm >> 3) - 1, Rm - (Rm >> 3), Rm - (Rm >> 2), 2 * K, 3 * K, 7 * K, 8 * K]
+        # values for which K a mod 2^(32 n) lands within a few multiples of 2^256 - p of the top (second fold)
+        for k in (2, 3, 4, 8):
+            for j in range(1, k):
+                for d in (-2 * K, -K - 1, -K, -K + 1, -1, 0, 1):
+                    edge.append(((j * Rm + Rm + d) // k) % Rm)
+    else:
+        edge = [0, 1, 2, mod - 1, mod - 2, mod >> 1, (mod >> 1) + 1, mod // 3, mod // 3 + 1, mod // 8, mod - mod // 8]
+    for a in edge:
+        for b in edge[:12]:
+            cases.append((a, b, edge[(a + b) % len(edge)]))
+    for _ in range(400):
+        cases.append(tuple(_structured(g, n) % top for _ in range(3)))
+    for _ in range(400):
+        cases.append(tuple(int.from_bytes(g.bytes(4 * n), "little") % top for _ in range(3)))
+
+    def check(exp, what):
+        if loose:
+            assert val(r) % mod == exp % mod and val(r) < Rm, what
+        else:
+            assert val(r) == exp % mod, what
+
+    for a, b, c in cases:
+        aw, bw, cw = words(a, n), words(b, n), words(c, n)
+        for op, k in ((8, 2), (9, 3), (10, 4), (11, 8), (12, 8)):
+            f.hs_mont(field, op, p(aw), p(bw), p(r))
+            check(k * a, (field, op, hex(a)))
+        for op, exp in ((0, a - b - c), (1, a - b - 2 * c), (2, a - b - c), (3, a - b - 2 * c)):
+            f.hs_mont3(field, op, p(aw), p(bw), p(cw), p(r))
+            check(exp, (field, op, hex(a), hex(b), hex(c)))
+
+
 def test_fe25519_and_fe448_structured_operands(hs):
     f, k = hs
     g = rng(200)
