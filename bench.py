@@ -72,10 +72,11 @@ WORK = {
 # on the comb in use (nwin windows) and on the kernel form, see executed_mac32().
 EXEC = {
     "x25519": 255 * (5 * 72 + 4 * 44 + 8) + 5 * 72,                        # ladder step 5 M + 4 S + a24 product; batched inverse 3 M + 2 M
-    "p256_mul": 260 * (3 * 64 + 5 * 36) + 72 * (10 * 64 + 4 * 36) + 5 * 64,  # 65 windows x 4 doublings, 65 + 7 (table) Jacobian additions
-    "p256_ecdsa_verify": 260 * (3 * 64 + 5 * 36) + 72 * (10 * 64 + 4 * 36) + 11 * (7 * 64 + 4 * 36) + 14 * 64 + 5 * 136 + 5 * 64,
-    "p384_mul": 388 * (3 * 144 + 5 * 78) + 104 * (10 * 144 + 4 * 78) + 5 * 144,
-    "bls12_381_g1_mul": 256 * (2 * 288 + 5 * 222) + 71 * (10 * 288 + 4 * 222) + 5 * 288,
+    # signed 5-bit windows (weier.cuh C::WIN): 52 windows = 51 x 5 doublings + 52 additions, table of 16 multiples = 8 doublings + 7 additions
+    "p256_mul": 263 * (3 * 64 + 5 * 36) + 59 * (10 * 64 + 4 * 36) + 5 * 64,
+    "p256_ecdsa_verify": 263 * (3 * 64 + 5 * 36) + 59 * (10 * 64 + 4 * 36) + 11 * (7 * 64 + 4 * 36) + 14 * 64 + 5 * 136 + 5 * 64,
+    "p384_mul": 388 * (3 * 144 + 5 * 78) + 84 * (10 * 144 + 4 * 78) + 5 * 144,    # 77 windows
+    "bls12_381_g1_mul": 263 * (2 * 288 + 5 * 222) + 59 * (10 * 288 + 4 * 222) + 5 * 288,
     "x448": 448 * (5 * 196 + 4 * 105 + 14) + 5 * 196,
     "ed25519_mul": 256 * (3 * 72 + 4 * 44) + 72 * 8 * 72 + 5 * 72,
 }
@@ -890,7 +891,11 @@ def main():
                     help="weak (the driver's contract): every rank its own batch; strong: ONE batch of the workload's size, sliced over the ranks")
     ap.add_argument("--single-process", action="store_true",
                     help="no torchrun: ONE context over --gpus devices (ecb_init(device_ids, N)), one host call per pass — the library's own multi-device path")
+    ap.add_argument("--lib", default=None, help="A/B runs only: another build of libeccbatch.so (tools/tune_wei_lib.py); the default is the in-tree library")
     args = ap.parse_args()
+    if args.lib:
+        from eccoxide_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(args.lib)
     if args.warmup < 3 and not args.profile_run:
         args.warmup = 3
     if args.impl == "reference":

@@ -581,16 +581,16 @@ struct FinX25519 {  // out: u' = x2 / z2 little-endian canonical, 0 when z2 == 0
 };
 
 // =======================================================================================
-// Weierstrass variable base: k*P with signed 4-bit Booth windows over a per-thread table of
-// 8 Jacobian multiples (replaces &Point * &Scalar, fiat/curve_macros.rs:321 ->
+// Weierstrass variable base: k*P with signed Booth windows of C::WIN bits (4, or 5 on p256r1) over a per-thread
+// table of 2^(WIN - 1) Jacobian multiples (replaces &Point * &Scalar, fiat/curve_macros.rs:321 ->
 // projective.rs:871 scalar_mul_fixed_window_am3 / :842 _a0: same group element, different
 // coordinates and window recoding — only the canonical affine result is observable).
 //   scalars: n x SB bytes big-endian canonical (< group order)
 //   points : n x 2FB bytes big-endian affine (x, y), on the curve; inf_in (optional) marks
 //            identity inputs
-//   tbl    : this thread's scratch, 8 entries x 5N words (X, Y, Z, Z^2, Z^3)
+//   tbl    : this thread's scratch, 2^(C::WIN - 1) entries x 5N words (X, Y, Z, Z^2, Z^3)
 // =======================================================================================
-// tbl[j-1] = cached(j * (x, y)), j = 1..8: 4 doublings + 3 additions.  Entries are written to
+// tbl[j-1] = cached(j * (x, y)), j = 1..2^(WIN - 1): half of them doublings, the rest additions of P.  Entries are written to
 // the table as soon as they exist and re-read when needed, so a single point is live at a time.
 template <class C>
 ECB_DEV void wei_store_pt_cached(u32* d, const typename WeiJ<C>::pt& p) {
@@ -602,8 +602,9 @@ ECB_DEV void wei_store_pt_cached(u32* d, const typename WeiJ<C>::pt& p) {
     st_words<N>(d, p.X.v); st_words<N>(d + N, p.Y.v); st_words<N>(d + 2 * N, p.Z.v);
     st_words<N>(d + 3 * N, zz.v); st_words<N>(d + 4 * N, zzz.v);
 }
+// HALF = 2^(WIN - 1) entries, WIN = C::WIN the width of the signed windows (weier.cuh)
 template <class C>
-ECB_DEV void wei_build_table8(u32* tbl, const typename C::F::el& x, const typename C::F::el& y) {
+ECB_DEV void wei_build_table(u32* tbl, const typename C::F::el& x, const typename C::F::el& y) {
     typedef WeiJ<C> J;
     typedef typename C::F FT;
     constexpr int N = FT::N;
@@ -616,7 +617,7 @@ ECB_DEV void wei_build_table8(u32* tbl, const typename C::F::el& x, const typena
     J::dbl(cur, cur);                                   // 2P
     wei_store_pt_cached<C>(tbl + 1 * ES, cur);
     ECB_NOUNROLL
-    for (int j = 2; j <= 6; j += 2) {                   // (j+1)P = jP + P ; (j+2)P = 2 * ((j+2)/2)P
+    for (int j = 2; j <= WeiJ<C>::TBL - 2; j += 2) {    // (j+1)P = jP + P ; (j+2)P = 2 * ((j+2)/2)P
         J::add_mem(cur, cur, tbl, 0u, ld);
         wei_store_pt_cached<C>(tbl + j * ES, cur);
         const u32* h = tbl + (j / 2) * ES;              // ((j+2)/2) P sits in slot (j+2)/2 - 1 = j/2
@@ -661,16 +662,17 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
     typename J::pt acc;
     J::set_inf(acc);
     if (ok && !is_inf) {
-        wei_build_table8<C>(tbl, px, py);
-        constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
+        wei_build_table<C>(tbl, px, py);
+        constexpr int WIN = C::WIN;
+        constexpr int NWIN = (C::SBITS + 1 + WIN - 1) / WIN;
         ECB_NOUNROLL
         for (int i = NWIN - 1; i >= 0; i--) {
             if (i != NWIN - 1) {
                 ECB_NOUNROLL
-                for (int r = 0; r < 4; r++) J::dbl(acc, acc);
+                for (int r = 0; r < WIN; r++) J::dbl(acc, acc);
             }
             u32 neg;
-            u32 d = booth_digit(k, NS + 1, 4, i, neg);
+            u32 d = booth_digit(k, NS + 1, WIN, i, neg);
             if (d != 0) J::add_mem(acc, acc, tbl + (d - 1) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
         }
     }

@@ -366,17 +366,18 @@ ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z
         for (int i = 0; i < NS; i++) { u1[i] = u1e.v[i]; u2[i] = u2e.v[i]; }
         u1[NS] = 0;
         u2[NS] = 0;
-        // u2*Q: signed 4-bit windows over tbl[0..8) = j*Q (Jacobian, cached Z powers)
-        wei_build_table8<C>(tbl, qx, qy);
-        constexpr int NWIN = (C::SBITS + 1 + 3) / 4;
+        // u2*Q: signed windows of C::WIN bits over tbl[0..2^(WIN-1)) = j*Q (Jacobian, cached Z powers)
+        wei_build_table<C>(tbl, qx, qy);
+        constexpr int WIN = C::WIN;
+        constexpr int NWIN = (C::SBITS + 1 + WIN - 1) / WIN;
         ECB_NOUNROLL
         for (int i = NWIN - 1; i >= 0; i--) {
             if (i != NWIN - 1) {
                 ECB_NOUNROLL
-                for (int r = 0; r < 4; r++) J::dbl(acc, acc);
+                for (int r = 0; r < WIN; r++) J::dbl(acc, acc);
             }
             u32 neg;
-            u32 d = booth_digit(u2, NS + 1, 4, i, neg);
+            u32 d = booth_digit(u2, NS + 1, WIN, i, neg);
             // skipping a zero digit: verification is variable time like mul_vartime
             if (d != 0) J::add_mem(acc, acc, tbl + (d - 1) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
         }

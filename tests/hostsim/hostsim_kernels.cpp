@@ -120,7 +120,7 @@ template <class C>
 static unsigned long long wei_mul_run(const u32* k, const u32* pts, const unsigned char* inf_in, size_t n, u32* out,
                                       unsigned char* inf) {
     constexpr int N = C::F::N;
-    std::vector<u32> planes(3 * N * n), pf(N * n), tbl(8 * 5 * N);
+    std::vector<u32> planes(3 * N * n), pf(N * n), tbl(WeiJ<C>::TBL * 5 * N);
     unsigned long long st = ~0ull;
     for (size_t i = 0; i < n; i++) wei_mul_body<C>(i, n, k, pts, inf_in, tbl.data(), planes.data(), &st);
     size_t T = inv_threads(n);
@@ -239,7 +239,7 @@ extern "C" unsigned long long hs_wei_mul_base(int curve, const u32* k, size_t n,
 template <class C>
 static unsigned long long ecdsa_run(const u32* q, const u32* z, const u32* rs, size_t n, unsigned char* ok) {
     constexpr int N = C::F::N, NS = C::FN::N;
-    std::vector<u32> planes(3 * N * n), pf((N > NS ? N : NS) * n), aux(3 * NS * n), tbl(8 * 5 * N);
+    std::vector<u32> planes(3 * N * n), pf((N > NS ? N : NS) * n), aux(3 * NS * n), tbl(WeiJ<C>::TBL * 5 * N);
     unsigned long long st = ~0ull;
     for (size_t i = 0; i < n; i++) ecdsa_prep_body<C>(i, n, z, rs, aux.data(), ok);
     size_t T = inv_threads(n);
