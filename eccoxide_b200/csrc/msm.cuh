@@ -107,46 +107,138 @@ ECB_DEV void msm_scatter_body(size_t i, size_t n, int nwin, u32 NB, const u32* d
     }
 }
 
-// bucket b = (w, j): B = sum of its members, then j * B -> bsum[b] (Jacobian, PW words)
+// ---- bucket sums, balanced over the SORTED index array ------------------------------------------------------
+// The counting sort leaves idx[0 .. L) ordered by bucket.  A thread per bucket would make the running time follow the
+// LARGEST bucket: the top window of a 256-bit scalar holds one or two bits, so half of all points share one bucket
+// (a 2^18 batch on p256k1 took 0.79 s that way), and equal scalars put everything into one bucket per window.  So the
+// array is cut into segments of S entries, one thread each: every thread does S mixed additions whatever the
+// distribution.  A bucket that lies inside one segment is summed there and written to bsum[b]; a bucket cut by
+// segment boundaries leaves pieces — per segment at most a head piece (its first run: part[2t]) and a tail piece (its
+// last run: part[2t + 1]) — which msm_finish_body adds up.
+ECB_DEV size_t msm_bucket_of(const u32* offs, size_t nb, size_t pos) {   // last b with offs[b] <= pos
+    size_t lo = 0, hi = nb;                                              // invariant: offs[lo] <= pos < offs[hi] (offs[nb] = L)
+    while (hi - lo > 1) {
+        size_t mid = (lo + hi) >> 1;
+        if ((size_t)offs[mid] <= pos) lo = mid; else hi = mid;
+    }
+    return lo;
+}
 template <class C>
-ECB_DEV void msm_bucket_body(size_t b, u32 NB, const u32* offs, const u32* hist, const u32* idx, const u32* pm, u32* bsum) {
+ECB_DEV void msm_segment_body(size_t t, size_t S, size_t nb, const u32* offs, const u32* hist, const u32* idx, const u32* pm, u32* bsum,
+                              u32* part) {
     typedef Msm<C> M;
     typedef typename M::J J;
     typedef typename C::F FT;
     constexpr int N = FT::N;
-    const u32 j = (u32)(b % NB) + 1u;
-    const u32 cnt = hist[b];
-    const size_t start = offs[b];
+    const size_t L = (size_t)offs[nb - 1] + hist[nb - 1];
+    size_t pos = t * S;
+    if (pos >= L) return;
+    const size_t hi = pos + S < L ? pos + S : L;
+    // ONE loop over the segment's entries, the same trip count in every lane, so that the warp stays converged on the
+    // addition (the expensive part); the end of a bucket is a short divergent side step.  (Nested per-bucket loops let
+    // the lanes drift apart: the additions then ran with partial masks and a 2^20 batch took 30 % longer.)
+    size_t b = msm_bucket_of(offs, nb, pos);
+    size_t bs = offs[b], be = bs + hist[b], run_start = pos;
+    bool first = true;
     typename J::pt acc;
     J::set_inf(acc);
     ECB_NOUNROLL
-    for (u32 t = 0; t < cnt; t++) {
-        const u32 e = idx[start + t];
-        const u32* src = pm + (size_t)(e & 0x7fffffffu) * 2 * N;
+    for (size_t e = pos; e < hi; e++) {
+        if (e == be) {                                   // bucket b ends here: it is whole if this run began at its start
+            M::st_pt(run_start == bs ? bsum + b * M::PW : part + 2 * t * M::PW, acc);
+            do b++; while (hist[b] == 0);                // empty buckets share their offset with the next one
+            bs = e;
+            be = bs + hist[b];
+            run_start = e;
+            first = false;
+            J::set_inf(acc);
+        }
+        const u32 v = idx[e];
+        const u32* src = pm + (size_t)(v & 0x7fffffffu) * 2 * N;
         typename J::cached q;
         ld_words<N>(q.X.v, src);
         ld_words<N>(q.Y.v, src + N);
-        J::cached_cneg(q, e >> 31);
+        J::cached_cneg(q, v >> 31);
         J::template add<true>(acc, acc, q);
     }
-    typename J::pt r;
-    J::set_inf(r);
-    if (!J::is_inf(acc)) {
-        typename J::cached ca;
-        J::to_cached(ca, acc);
+    if (run_start == bs && hi == be) M::st_pt(bsum + b * M::PW, acc);      // the whole bucket
+    else M::st_pt(part + (2 * t + (first ? 0 : 1)) * M::PW, acc);          // a piece: the head of this segment, or its tail
+}
+// the pieces of bucket b, if it was cut: segment tf holds its beginning (as that segment's tail, or as its head when the
+// bucket starts exactly on the boundary), every later segment up to tl holds a head piece.  Pieces t in [lo, hi)
+// with stride `step` (one thread: lo = tf + 1, step = 1; a warp: lane-strided) are added to acc.
+template <class C>
+ECB_DEV void msm_pieces(typename WeiJ<C>::pt& acc, const u32* part, size_t lo, size_t hi, size_t step) {
+    typedef Msm<C> M;
+    typename M::J::pt p;
+    ECB_NOUNROLL
+    for (size_t t = lo; t < hi; t += step) {
+        M::ld_pt(p, part + 2 * t * M::PW);
+        M::add_pts(acc, acc, p);
+    }
+}
+// bucket b: B = its sum (unscaled) -> bsum[b].  Returns through (tf, tl) the segments it spans; the caller adds the
+// middle pieces of a HEAVY bucket (tl - tf > heavy) with a whole warp and passes them in `mid`; lighter ones are added here.
+template <class C>
+ECB_DEV void msm_finish_body(size_t b, size_t S, const u32* offs, const u32* hist, const u32* part, u32* bsum, const typename WeiJ<C>::pt* mid) {
+    typedef Msm<C> M;
+    typedef typename M::J J;
+    const u32 cnt = hist[b];
+    typename J::pt acc;
+    if (cnt == 0) {
+        J::set_inf(acc);
+        M::st_pt(bsum + b * M::PW, acc);
+        return;
+    }
+    const size_t bs = offs[b], be = bs + cnt, tf = bs / S, tl = (be - 1) / S;
+    if (tf == tl) return;                                   // summed inside one segment: bsum[b] is already there
+    M::ld_pt(acc, part + (2 * tf + (bs == tf * S ? 0 : 1)) * M::PW);
+    if (mid) M::add_pts(acc, acc, *mid);
+    else msm_pieces<C>(acc, part, tf + 1, tl + 1, 1);
+    M::st_pt(bsum + b * M::PW, acc);
+}
+// ---- sum_j j * B_j by running sums, CH buckets per thread ----------------------------------------------------
+// Chunk q of window w covers the buckets j = a + 1 .. a + CH (a = q CH):
+//     sum_j j B_j = sum_i (a + i) B_(a+i) = a * T + sum_i i B_(a+i),   T = sum_i B_(a+i).
+// Walking i = CH .. 1 with run += B, acc += run gives acc = sum_i i B_(a+i) and run = T: two additions per bucket
+// instead of a 15-bit double-and-add (232 field products), and ONE a * T per chunk.  The result replaces the chunk's
+// first slot; the tree sum then runs over the NB / CH chunk results of each window.
+template <class C>
+ECB_DEV void msm_chunk_body(size_t t, u32 NB, u32 CH, u32* bsum, u32* csum) {
+    typedef Msm<C> M;
+    typedef typename M::J J;
+    typedef typename C::F FT;
+    const u32 NC = NB / CH;
+    const size_t w = t / NC;
+    const u32 q = (u32)(t % NC), a = q * CH;
+    const u32* base = bsum + (w * NB + a) * M::PW;
+    typename J::pt run, acc, p;
+    J::set_inf(run);
+    J::set_inf(acc);
+    ECB_NOUNROLL
+    for (int i = (int)CH - 1; i >= 0; i--) {
+        M::ld_pt(p, base + (size_t)i * M::PW);
+        M::add_pts(run, run, p);
+        M::add_pts(acc, acc, run);
+    }
+    if (a != 0 && !J::is_inf(run)) {                         // acc += a * T
+        typename J::cached ct;
+        J::to_cached(ct, run);
         int top = 31;
-        while (!((j >> top) & 1u)) top--;
-        FT::copy(r.X, acc.X); FT::copy(r.Y, acc.Y); FT::copy(r.Z, acc.Z);
+        while (!((a >> top) & 1u)) top--;
+        typename J::pt r;
+        FT::copy(r.X, run.X); FT::copy(r.Y, run.Y); FT::copy(r.Z, run.Z);
         ECB_NOUNROLL
         for (int bit = top - 1; bit >= 0; bit--) {
             J::dbl(r, r);
-            if ((j >> bit) & 1u) J::template add<false>(r, r, ca);
+            if ((a >> bit) & 1u) J::template add<false>(r, r, ct);
         }
+        M::add_pts(acc, acc, r);
     }
-    M::st_pt(bsum + b * M::PW, r);
+    M::st_pt(csum + t * M::PW, acc);
 }
 
-// one level of the tree sum inside each window: slot s += slot s + half, s < half
+// one level of the tree sum inside each window: slot s += slot s + half, s < half  (NB slots per window)
 template <class C>
 ECB_DEV void msm_reduce_body(size_t t, u32 NB, u32 half, u32* bsum) {
     typedef Msm<C> M;

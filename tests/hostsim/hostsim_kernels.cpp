@@ -328,31 +328,61 @@ extern "C" void hs_ristretto255_compress(const u32* xy, size_t n, u32* enc) {
     for (size_t i = 0; i < n; i++) ristretto255_compress_body(i, xy, enc);
 }
 
-// multi-scalar multiplication (msm.cuh): the kernels' bodies in launch order, window width c given
+// multi-scalar multiplication (msm.cuh): the kernels' bodies in launch order, window width c, segment length S and
+// running-sum chunk CH given; the warp-level sum of a heavy bucket's pieces (k_msm_finish in tu_wei.inc) is replayed lane by lane
 template <class C>
-static unsigned long long msm_run(const u32* k, const u32* pts, size_t n, int c, u32* out, unsigned char* inf) {
+static unsigned long long msm_run(const u32* k, const u32* pts, size_t n, int c, size_t S, u32 CHmax, u32 heavy, u32* out, unsigned char* inf) {
     constexpr int N = C::F::N;
     typedef Msm<C> M;
+    typedef typename M::J J;
     const int nwin = (C::SBITS + 1 + c - 1) / c;
     const u32 NB = 1u << (c - 1);
     const size_t nb = (size_t)nwin * NB;
-    std::vector<u32> pm(n * 2 * N), dig((size_t)nwin * n), idx((size_t)nwin * n), hist(nb, 0), offs(nb, 0), cursor(nb, 0), bsum(nb * M::PW), part(M::PW);
+    const size_t nseg = ((size_t)nwin * n + S - 1) / S;
+    const u32 CH = NB < CHmax ? NB : CHmax, NC = NB / CH;
+    const size_t nc = (size_t)nwin * NC;
+    std::vector<u32> pm(n * 2 * N), dig((size_t)nwin * n), idx((size_t)nwin * n), hist(nb, 0), offs(nb, 0), cursor(nb, 0),
+        bsum(nb * M::PW, 0xdeadbeefu), csum(nc * M::PW), pieces(2 * nseg * M::PW, 0xdeadbeefu), part(M::PW);
     unsigned long long st = ~0ull;
     for (size_t i = 0; i < n; i++) msm_prepare_body<C>(i, n, k, pts, c, nwin, NB, pm.data(), dig.data(), hist.data(), &st);
     u32 run = 0;
     for (size_t b = 0; b < nb; b++) { offs[b] = run; run += hist[b]; }
     for (size_t i = 0; i < n; i++) msm_scatter_body(i, n, nwin, NB, dig.data(), offs.data(), cursor.data(), idx.data());
-    for (size_t b = 0; b < nb; b++) msm_bucket_body<C>(b, NB, offs.data(), hist.data(), idx.data(), pm.data(), bsum.data());
-    for (u32 half = NB >> 1; half >= 1; half >>= 1)
-        for (size_t t = 0; t < (size_t)nwin * half; t++) msm_reduce_body<C>(t, NB, half, bsum.data());
-    msm_window_body<C>(c, nwin, NB, bsum.data(), part.data());
+    for (size_t t = 0; t < nseg; t++) msm_segment_body<C>(t, S, nb, offs.data(), hist.data(), idx.data(), pm.data(), bsum.data(), pieces.data());
+    for (size_t b = 0; b < nb; b++) {
+        typename J::pt mid;
+        bool has_mid = false;
+        if (hist[b]) {
+            const size_t bs = offs[b], be = bs + hist[b], tf = bs / S, tl = (be - 1) / S;
+            if (tl - tf > heavy) {
+                typename J::pt lane[32];
+                for (int l = 0; l < 32; l++) {
+                    J::set_inf(lane[l]);
+                    msm_pieces<C>(lane[l], pieces.data(), tf + 1 + l, tl + 1, 32);
+                }
+                for (int d = 16; d >= 1; d >>= 1)
+                    for (int l = 0; l < d; l++) M::add_pts(lane[l], lane[l], lane[l + d]);
+                mid = lane[0];
+                has_mid = true;
+            }
+        }
+        msm_finish_body<C>(b, S, offs.data(), hist.data(), pieces.data(), bsum.data(), has_mid ? &mid : nullptr);
+    }
+    for (size_t t = 0; t < nc; t++) msm_chunk_body<C>(t, NB, CH, bsum.data(), csum.data());
+    for (u32 half = NC >> 1; half >= 1; half >>= 1)
+        for (size_t t = 0; t < (size_t)nwin * half; t++) msm_reduce_body<C>(t, NC, half, csum.data());
+    msm_window_body<C>(c, nwin, NC, csum.data(), part.data());
     std::vector<u32> planes(3 * N), pf(N);
     msm_combine_body<C>(1, part.data(), planes.data());
     FinWeiXY<C> fin{planes.data(), 1, out, inf};
     batch_inv_body<typename C::F>(0, 1, 1, planes.data(), pf.data(), fin);
     return st;
 }
+extern "C" unsigned long long hs_wei_msm2(int curve, const u32* k, const u32* pts, size_t n, int c, size_t S, u32 CH, u32 heavy, u32* out, unsigned char* inf) {
+    if (curve == 2) return msm_run<CurveBLSG1>(k, pts, n, c, S, CH, heavy, out, inf);
+    return msm_run<CurveK256>(k, pts, n, c, S, CH, heavy, out, inf);
+}
 extern "C" unsigned long long hs_wei_msm(int curve, const u32* k, const u32* pts, size_t n, int c, u32* out, unsigned char* inf) {
-    if (curve == 2) return msm_run<CurveBLSG1>(k, pts, n, c, out, inf);
-    return msm_run<CurveK256>(k, pts, n, c, out, inf);
+    if (curve == 2) return msm_run<CurveBLSG1>(k, pts, n, c, 8, 32, 16, out, inf);
+    return msm_run<CurveK256>(k, pts, n, c, 8, 32, 16, out, inf);
 }

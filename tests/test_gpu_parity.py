@@ -1109,6 +1109,39 @@ def test_wei_msm(ctx, coracle, curve):
     assert e.value.code == -4 and e.value.bad_index == 11
 
 
+@pytest.mark.parametrize("curve", ["bls12_381_g1", "p256k1"])
+def test_wei_msm_skewed_digit_distributions(ctx, coracle, curve):
+    """The bucket sums are balanced over segments of the sorted index array, so the running time and the result must not
+    depend on how the digits are distributed.  2^16 points P_i = t_i G with (a) scalars = 64 uniform bytes mod the order —
+    on p256k1 the top window of such a scalar holds one bit, so half of all points share ONE bucket (a thread per bucket
+    took 0.8 s on 2^18 points) —, (b) ONE scalar for every point (one bucket per window holds everything: the warp-level
+    sum of a heavy bucket's pieces), (c) sixteen distinct scalars; each against (sum k_i t_i) G from the generator comb."""
+    import time
+
+    c = R.WCURVES[curve]
+    g = rng(0x3541 + len(curve))
+    n, period = 1 << 16, 1 << 9
+    tb = scalars_mod(g, period, c.n, c.sbytes, "big")
+    base, binf = ctx.wei_mul_base(curve, tb)
+    assert not binf.any()
+    pts = np.ascontiguousarray(np.tile(base, (n // period, 1)))
+    tv = [int.from_bytes(r.tobytes(), "big") for r in tb]
+    uniform = scalars_mod(g, n, c.n, c.sbytes, "big")
+    one = np.ascontiguousarray(np.tile(scalars_mod(g, 1, c.n, c.sbytes, "big"), (n, 1)))
+    few = scalars_mod(g, 16, c.n, c.sbytes, "big")[g.integers(0, 16, size=n)]
+    times = {}
+    for name, kb in (("uniform", uniform), ("one", one), ("few", np.ascontiguousarray(few))):
+        total = sum(int.from_bytes(kb[i].tobytes(), "big") * tv[i % period] for i in range(n)) % c.n
+        exp, einf = ctx.wei_mul_base(curve, rows([total.to_bytes(c.sbytes, "big")]))
+        ctx.wei_msm(curve, kb, pts)
+        t0 = time.perf_counter()
+        out, inf = ctx.wei_msm(curve, kb, pts)
+        times[name] = time.perf_counter() - t0
+        assert inf == bool(einf[0]) and out.tobytes() == exp[0].tobytes(), name
+    # no distribution may cost an order of magnitude more than the uniform one (a thread per bucket: x100 and more)
+    assert max(times.values()) < 10 * times["uniform"] + 0.05, times
+
+
 def test_ristretto255(ctx, golden):
     """ristretto255 (src/curve/curve25519/ristretto255.rs; RFC 9496) through the C ABI: mul_base gives the RFC's
     encodings of 0 B .. 15 B (:341-358), the 17 bad encodings are refused (:380-398) — by decompress with ok = 0 and

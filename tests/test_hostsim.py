@@ -21,7 +21,7 @@ def hs():
     subprocess.check_call(["make", "-s", "-j4", "-C", HS])
     f = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_fields.so"))
     k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
-    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_wei_mul_base_ct", "hs_wei_msm", "hs_ecdsa_verify"):
+    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_wei_mul_base_ct", "hs_wei_msm", "hs_wei_msm2", "hs_ecdsa_verify"):
         getattr(k, fn).restype = ctypes.c_ulonglong
     return f, k
 
@@ -703,3 +703,41 @@ def test_wei_msm_bucket_method(hs, cid, curve):
     inf = np.zeros(1, dtype=np.uint8)
     k.hs_wei_msm(cid, p(kb2), p(pb2), ctypes.c_size_t(2), 4, p(out), p(inf))
     assert inf[0] and not out.any()
+
+
+@pytest.mark.parametrize("cid,curve", [(2, "bls12_381_g1"), (3, "p256k1")])
+def test_wei_msm_skewed_buckets(hs, cid, curve):
+    """The bucket sums are balanced over segments of the sorted index array (msm.cuh: msm_segment_body / msm_finish_body /
+    msm_chunk_body), so the distribution of the digits must not matter: equal scalars (every point in ONE bucket per
+    window), scalars with the top bit set (the short top window of a 256-bit scalar: half of the points share a bucket),
+    a few distinct scalars, and random ones — for segment lengths that cut buckets into many pieces, with the warp-level
+    sum of a heavy bucket's pieces replayed lane by lane (heavy threshold 0, 2, 16), and running-sum chunks of 1 .. 32."""
+    _, k = hs
+    c = R.WCURVES[curve]
+    g = rng(800 + cid)
+    base = [c.mul(int.from_bytes(g.bytes(40), "big") % c.n or 1, c.G) for _ in range(12)]
+    n = 150
+    pts = [base[int(g.integers(0, len(base)))] for _ in range(n)]
+    pts = [P if g.integers(0, 4) else c.neg(P) for P in pts]
+    pb = rows([c.enc(P) for P in pts])
+    top = 1 << (c.n.bit_length() - 1)
+    families = {
+        "equal": [int.from_bytes(g.bytes(40), "big") % c.n] * n,
+        "top_bit": [(top | int.from_bytes(g.bytes(40), "big")) % c.n for _ in range(n)],
+        "few": [[1, 2, c.n - 1, 0x10001, top][int(g.integers(0, 5))] for _ in range(n)],
+        "random": [int.from_bytes(g.bytes(40), "big") % c.n for _ in range(n)],
+    }
+    out = np.zeros(2 * c.fbytes, dtype=np.uint8)
+    inf = np.zeros(1, dtype=np.uint8)
+    for name, ks in families.items():
+        want = None
+        for kk, P in zip(ks, pts):
+            want = c.add(want, c.mul(kk, P)) if kk else want
+        kb = rows([v.to_bytes(c.sbytes, "big") for v in ks])
+        for cw, S, CH, heavy in ((4, 1, 1, 0), (5, 3, 2, 2), (7, 2, 32, 16), (6, 8, 4, 0), (9, 5, 32, 2), (4, 512, 8, 16)):
+            st = k.hs_wei_msm2(cid, p(kb), p(pb), ctypes.c_size_t(n), cw, ctypes.c_size_t(S), CH, heavy, p(out), p(inf))
+            assert st == 2**64 - 1
+            if want is None:
+                assert inf[0] and not out.any(), (name, cw, S, CH, heavy)
+            else:
+                assert not inf[0] and out.tobytes() == c.enc(want), (name, cw, S, CH, heavy)
