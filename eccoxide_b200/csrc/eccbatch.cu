@@ -165,6 +165,10 @@ int ecb_set_option(ecb_ctx* ctx, const char* key, long value) {
         ctx->opt_trace = value ? 1 : 0;
         return ECB_OK;
     }
+    if (!strcmp(key, "bls12_381_g1_glv")) {
+        ctx->opt_bls_glv = value ? 1 : 0;
+        return ECB_OK;
+    }
     if (!strcmp(key, "profile")) {
         ctx->opt_profile = value ? 1 : 0;
         return ECB_OK;

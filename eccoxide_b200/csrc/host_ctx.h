@@ -87,6 +87,7 @@ struct ecb_ctx {
     long opt_ed_lanes = 0;                    // lanes per scalar in the fused kernel: 0 = by batch size, or 1 / 2 / 4 / 8
     size_t opt_chunk = 189440;  // elements per pipeline chunk = 148 SMs x 1280 (ECB_NSLOT chunks in flight per device; measured best of 2^16..2^19)
     long opt_profile = 0;
+    long opt_bls_glv = 0;                     // 1: ecb_wei_mul on bls12_381_g1 takes its inputs to be in G1 and uses the endomorphism (kernels3.cuh)
     long opt_trace = 0;                       // 1: the fused kernels record per-block phase timestamps (measurement only)
     long opt_inv_hi = 1;                      // run batch inversions on the slot's high-priority side stream
     long opt_ramp = 2;                        // pipeline chunk schedule: this many halvings of the chunk size at both ends of a batch (option "ramp")

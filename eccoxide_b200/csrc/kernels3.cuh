@@ -237,4 +237,97 @@ ECB_DEV void bls_g1_to_compressed_body(size_t idx, const u32* xy, const unsigned
     st_words_be<N>(enc + idx * N, xw);
 }
 
+// =======================================================================================
+// BLS12-381 G1, inputs PROMISED to lie in the prime-order subgroup (option bls12_381_g1_glv): k P through the
+// endomorphism phi(x, y) = (beta x, y) = [-x^2] P (the map of the reference's subgroup test, g1.rs:55, :105).
+//     k = q x^2 + rem  (0 <= rem < x^2 < 2^128, q < 2^128)   =>   k P = rem P + q (x^2 P) = rem P - q phi(P),
+// two 128-bit scalars over ONE table of multiples (phi of an entry costs one product): 25 x 5 doublings instead of
+// 51 x 5.  Same result as wei_mul_body for every point of G1 — and only for those: phi is not a multiplication on
+// the cofactor part of E(Fp), which Point::mul (g1.rs:375) accepts, so this is never the default.
+// =======================================================================================
+// k (8 words, little-endian, below the group order) -> k1 = rem, k2 = q, 5 words each with a zero top word.
+// x^2 = 2^32 y, so q = (k >> 32) div y and rem = ((k >> 32) mod y) 2^32 + (k mod 2^32): a 224-by-96-bit restoring division.
+ECB_DEV void bls_glv_split(u32* k1, u32* k2, const u32* k) {
+    const u64 yl = ((u64)BLSG1_XSQ[2] << 32) | BLSG1_XSQ[1], yh = BLSG1_XSQ[3];
+    u64 rl = 0, rh = 0;
+    u32 q[7];
+    ECB_UNROLL
+    for (int w = 7; w >= 1; w--) {
+        u32 cur = k[w], qw = 0;
+        ECB_NOUNROLL
+        for (int b = 0; b < 32; b++) {
+            rh = (rh << 1) | (rl >> 63);
+            rl = (rl << 1) | (cur >> 31);
+            cur <<= 1;
+            const u32 ge = (rh > yh || (rh == yh && rl >= yl)) ? 1u : 0u;
+            if (ge) {
+                rh = rh - yh - (rl < yl ? 1u : 0u);
+                rl = rl - yl;
+            }
+            qw = (qw << 1) | ge;
+        }
+        q[w - 1] = qw;
+    }
+    k1[0] = k[0]; k1[1] = (u32)rl; k1[2] = (u32)(rl >> 32); k1[3] = (u32)rh; k1[4] = 0;
+    k2[0] = q[0]; k2[1] = q[1]; k2[2] = q[2]; k2[3] = q[3]; k2[4] = 0;   // q[4..6] = 0 for k < 2^256 / 2^127
+}
+template <class C>
+ECB_DEV void wei_mul_glv_body(size_t idx, size_t n, const u32* scalars, const u32* points, const unsigned char* inf_in,
+                              u32* tbl, u32* planes, unsigned long long* status) {
+    typedef WeiJ<C> J;
+    typedef Wei<C> W;
+    typedef typename C::F FT;
+    typedef typename C::FN FNT;
+    typedef typename FT::el fe;
+    constexpr int N = FT::N;
+    constexpr int NS = C::SB / 4;
+    constexpr int ES = 5 * N;
+    static_assert(NS == 8, "256-bit scalars");
+    u32 k[NS];
+    ld_words_be<NS>(k, scalars + idx * NS);
+    u32 ok = 1;
+    if (!FNT::is_canonical_words(k)) {
+        report_bad(status, idx, ST_NONCANONICAL_SCALAR);
+        ok = 0;
+    }
+    u32 is_inf = inf_in ? (inf_in[idx] ? 1u : 0u) : 0u;
+    fe px, py;
+    {
+        u32 xw[N], yw[N];
+        ld_words_be<N>(xw, points + idx * 2 * N);
+        ld_words_be<N>(yw, points + idx * 2 * N + N);
+        FT::to_mont(px, xw);
+        FT::to_mont(py, yw);
+        if (ok && !is_inf && !(FT::is_canonical_words(xw) && FT::is_canonical_words(yw) && W::on_curve(px, py))) {
+            report_bad(status, idx, ST_BAD_POINT);
+            ok = 0;
+        }
+    }
+    typename J::pt acc;
+    J::set_inf(acc);
+    if (ok && !is_inf) {
+        u32 k1[5], k2[5];
+        bls_glv_split(k1, k2, k);
+        wei_build_table<C>(tbl, px, py);
+        constexpr int WIN = C::WIN;
+        constexpr int NWIN = (128 + 1 + WIN - 1) / WIN;
+        auto ld = [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); };
+        ECB_NOUNROLL
+        for (int i = NWIN - 1; i >= 0; i--) {
+            if (i != NWIN - 1) {
+                ECB_NOUNROLL
+                for (int r = 0; r < WIN; r++) J::dbl(acc, acc);
+            }
+            u32 neg;
+            u32 d = booth_digit(k1, 5, WIN, i, neg);
+            if (d != 0) J::add_mem(acc, acc, tbl + (d - 1) * ES, neg, ld);
+            d = booth_digit(k2, 5, WIN, i, neg);                       // - q phi(P): the opposite sign
+            if (d != 0) J::template add_mem<decltype(ld), true>(acc, acc, tbl + (d - 1) * ES, neg ^ 1u, ld);
+        }
+    }
+    plane_st<N>(planes + 0 * (size_t)N * n, n, idx, acc.X.v);
+    plane_st<N>(planes + 1 * (size_t)N * n, n, idx, acc.Y.v);
+    plane_st<N>(planes + 2 * (size_t)N * n, n, idx, acc.Z.v);
+}
+
 }  // namespace ecb

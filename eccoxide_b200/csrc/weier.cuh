@@ -281,11 +281,17 @@ struct WeiJ {
     // r = p + (neg ? -q : q) with q = the cached entry stored at `e` (5N words: X, Y, Z, Z^2, Z^3).
     // Same formulas as add<false>; the entry's fields are loaded where they are consumed so that
     // only one of them is live at a time (the whole entry would cost 5N registers).
-    template <class LD>
+    // ENDO (BLS12-381 G1 only): the entry is read as phi(q) = (beta X2, Y2, Z2): one product more (GLV, kernels3.cuh).
+    template <class LD, bool ENDO = false>
     ECB_DEV static void add_mem(pt& r, const pt& p, const u32* e, u32 neg, LD ld) {
         fe q;
         if (F::is_zero(p.Z)) {  // infinity + q
             ld(r.X.v, e);
+            if constexpr (ENDO) {
+                ECB_UNROLL
+                for (int i = 0; i < N; i++) q.v[i] = C::beta(i);
+                F::mul_ni(r.X, r.X, q);
+            }
             ld(q.v, e + N);
             F::neg(r.Y, q);
             F::select(r.Y, neg, r.Y, q);
@@ -307,6 +313,11 @@ struct WeiJ {
         ld(q.v, e + 3 * N);                 // Z2^2
         F::mul_ni(U1, p.X, q);
         ld(q.v, e);                         // X2
+        if constexpr (ENDO) {
+            ECB_UNROLL
+            for (int i = 0; i < N; i++) U2.v[i] = C::beta(i);
+            F::mul_ni(q, q, U2);
+        }
         F::mul_ni(U2, q, Z1Z1);
         F::sub(H, U2, U1);
         ld(q.v, e + 4 * N);                 // Z2^3

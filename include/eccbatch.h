@@ -94,6 +94,11 @@ int ecb_device_count(ecb_ctx* ctx);
  *   "ed25519_fused"         small-batch kernel (lanes share a scalar, affine conversion in the same launch): 0 never,
  *                           1 (default) when the batch fits one wave of the device, 2 always
  *   "ed25519_lanes"         lanes per scalar in that kernel: 0 (default) by batch size, or 1, 2, 4, 8
+ *   "bls12_381_g1_glv"      1: ecb_wei_mul / ecb_wei_mul_dev on ECB_CURVE_BLS12_381_G1 take every input point to be in the
+ *                           prime-order subgroup G1 (e.g. outputs of ecb_bls12_381_g1_from_compressed with check_subgroup = 1,
+ *                           or of ecb_wei_mul_base) and split the scalar over the endomorphism (beta x, y) = [-x^2] P of the
+ *                           reference's subgroup test (g1.rs:105): half the doublings, 1.4x.  For points of E(Fp) OUTSIDE G1 —
+ *                           which Point::mul accepts — the result is then NOT k P; default 0 (bit-exact for every curve point).
  *   "trace"                 1: the fused kernel records per-block phase timestamps (ecb_debug_fused_trace)
  *   "profile"               1: record CUDA events around the kernels of every call on the launching stream,
  *                           read back with ecb_profile_collect */

@@ -259,6 +259,20 @@ extern "C" unsigned long long hs_ecdsa_verify(int curve, const u32* q, const u32
 
 // ---- kernels3: PointAffine::decompress, BLS12-381 G1 standard encodings ---------------------
 #include "../../eccoxide_b200/csrc/kernels3.cuh"
+
+// BLS12-381 G1 through the endomorphism (option bls12_381_g1_glv): the split and the two-scalar window loop
+extern "C" void hs_bls_glv_split(const u32* k, u32* k1, u32* k2) { bls_glv_split(k1, k2, k); }
+extern "C" unsigned long long hs_bls_g1_mul_glv(const u32* k, const u32* pts, const unsigned char* inf_in, size_t n, u32* out, unsigned char* inf) {
+    typedef CurveBLSG1 C;
+    constexpr int N = C::F::N;
+    std::vector<u32> planes(3 * N * n), pf(N * n), tbl(WeiJ<C>::TBL * 5 * N);
+    unsigned long long st = ~0ull;
+    for (size_t i = 0; i < n; i++) wei_mul_glv_body<C>(i, n, k, pts, inf_in, tbl.data(), planes.data(), &st);
+    size_t T = inv_threads(n);
+    FinWeiXY<C> fin{planes.data(), n, out, inf};
+    for (size_t t = 0; t < T; t++) batch_inv_body<typename C::F>(t, T, n, planes.data(), pf.data(), fin);
+    return st;
+}
 extern "C" void hs_wei_decompress(int curve, const u32* x, const unsigned char* sign, size_t n, u32* out, unsigned char* ok) {
     for (size_t i = 0; i < n; i++) {
         switch (curve) {

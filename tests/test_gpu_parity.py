@@ -9,6 +9,7 @@ cuda:0 and compares byte for byte with
 Bar: bit-exact (integer / byte work).
 """
 import hashlib
+import os
 
 import numpy as np
 import pytest
@@ -1051,6 +1052,48 @@ def test_ed25519_decompress(ctx, golden):
     k2 = scalars_mod(g, 600, R.L25519, 32, "little")
     assert np.array_equal(ctx.ed25519_mul(k2, out[:600]), ctx.ed25519_mul(k2, xy))
     assert ctx.ed25519_decompress(np.zeros((0, 32), dtype=np.uint8))[0].shape == (0, 64)
+
+
+def test_bls12_381_g1_mul_through_the_endomorphism(ctx, coracle):
+    """Option bls12_381_g1_glv: for points of G1 ecb_wei_mul gives the same bytes with and without it (2^15 random
+    pairs + edge scalars + identity inputs), equal to the C oracle on a sample; refusals keep their index; the option
+    is off by default and off again afterwards (off-subgroup inputs are only defined without it)."""
+    from eccoxide_b200 import EccBatchError
+
+    c = R.WCURVES["bls12_381_g1"]
+    g = rng(0x6171)
+    n = 1 << 15
+    xsq = 0xD201000000010000 ** 2
+    base, binf = ctx.wei_mul_base("bls12_381_g1", scalars_mod(g, 1 << 10, c.n, 32, "big"))
+    assert not binf.any()
+    pts = np.ascontiguousarray(np.tile(base, (n // base.shape[0], 1)))
+    kb = scalars_mod(g, n, c.n, 32, "big")
+    edge = [0, 1, c.n - 1, xsq - 1, xsq, xsq + 1, 2 * xsq, (xsq - 1) * xsq, (1 << 128) - 1, 1 << 128, (1 << 254) + 1]
+    for i, v in enumerate(edge):
+        kb[i] = np.frombuffer(v.to_bytes(32, "big"), dtype=np.uint8)
+    inf_in = np.zeros(n, dtype=np.uint8)
+    inf_in[40:44] = 1
+    plain, pinf = ctx.wei_mul("bls12_381_g1", kb, pts, inf_in=inf_in)
+    try:
+        ctx.set_option("bls12_381_g1_glv", 1)
+        fast, finf = ctx.wei_mul("bls12_381_g1", kb, pts, inf_in=inf_in)
+        bad = kb.copy()
+        bad[77] = 0xFF
+        with pytest.raises(EccBatchError) as e:
+            ctx.wei_mul("bls12_381_g1", bad, pts, inf_in=inf_in)
+        assert e.value.code == -3 and e.value.bad_index == 77
+        badp = pts.copy()
+        badp[91, -1] ^= 1
+        with pytest.raises(EccBatchError) as e:
+            ctx.wei_mul("bls12_381_g1", kb, badp, inf_in=inf_in)
+        assert e.value.code == -4 and e.value.bad_index == 91
+    finally:
+        ctx.set_option("bls12_381_g1_glv", 0)
+    assert np.array_equal(fast, plain) and np.array_equal(finf, pinf)
+    assert finf[0] and finf[40:44].all() and not finf[1:40].any()
+    m = 2048
+    exp, einf = coracle.wei_mul("bls12_381_g1", kb[:m], pts[:m], inf_in=inf_in[:m], nthreads=os.cpu_count() or 1)
+    assert np.array_equal(fast[:m], exp) and np.array_equal(finf[:m], einf)
 
 
 @pytest.mark.parametrize("curve", ["bls12_381_g1", "p256k1"])

@@ -21,7 +21,7 @@ def hs():
     subprocess.check_call(["make", "-s", "-j4", "-C", HS])
     f = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_fields.so"))
     k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
-    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_wei_mul_base_ct", "hs_wei_msm", "hs_wei_msm2", "hs_ecdsa_verify"):
+    for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_wei_mul_base_ct", "hs_wei_msm", "hs_wei_msm2", "hs_ecdsa_verify", "hs_bls_g1_mul_glv"):
         getattr(k, fn).restype = ctypes.c_ulonglong
     return f, k
 
@@ -665,6 +665,51 @@ def test_ristretto255_encodings(hs, golden):
     out = np.zeros((48, 32), dtype=np.uint8)
     k.hs_ristretto255_compress(p(allp), ctypes.c_size_t(48), p(out))
     assert np.array_equal(out[:16], mult) and np.array_equal(out[16:32], mult) and np.array_equal(out[32:], mult)
+
+
+def test_bls12_381_g1_mul_through_the_endomorphism(hs, coracle):
+    """Option bls12_381_g1_glv (kernels3.cuh): k = q x^2 + rem exactly, both parts below 2^128, for edge and random
+    scalars; k P = rem P - q phi(P) equals the plain window kernel, the C oracle and the big-integer group law for
+    points of G1 (edge scalars 0, 1, r - 1, x^2, x^2 +- 1, multiples of x^2, identity inputs); a non-canonical scalar
+    and an off-curve point are refused with their index as in the plain kernel."""
+    _, k = hs
+    c = R.WCURVES["bls12_381_g1"]
+    g = rng(910)
+    xsq = 0xD201000000010000 ** 2
+    ks = [0, 1, 2, c.n - 1, c.n - 2, xsq - 1, xsq, xsq + 1, 2 * xsq, xsq * xsq % c.n, (xsq - 1) * xsq, (1 << 128) - 1, 1 << 128, (1 << 254) + 1,
+          xsq * ((1 << 127) - 1) % c.n, 0xFFFFFFFF, 1 << 32, (1 << 32) - 1 + xsq]
+    ks += [int.from_bytes(g.bytes(40), "big") % c.n for _ in range(60)]
+    k1 = np.zeros(5, dtype=np.uint32)
+    k2 = np.zeros(5, dtype=np.uint32)
+    for kk in ks:
+        k.hs_bls_glv_split(p(words(kk, 8)), p(k1), p(k2))
+        rem, q = val(k1), val(k2)
+        assert q * xsq + rem == kk and rem < xsq and q < (1 << 128) and k1[4] == 0 and k2[4] == 0, hex(kk)
+    pts = [c.mul(int.from_bytes(g.bytes(40), "big") % c.n or 1, c.G) for _ in range(len(ks))]
+    pts[3] = c.G
+    kb = rows([v.to_bytes(32, "big") for v in ks])
+    pb = rows([c.enc(P) for P in pts])
+    n = len(ks)
+    inf_in = np.zeros(n, dtype=np.uint8)
+    inf_in[5] = 1
+    out = np.zeros((n, 96), dtype=np.uint8)
+    inf = np.zeros(n, dtype=np.uint8)
+    assert k.hs_bls_g1_mul_glv(p(kb), p(pb), p(inf_in), ctypes.c_size_t(n), p(out), p(inf)) == 2**64 - 1
+    out2 = np.zeros((n, 96), dtype=np.uint8)
+    inf2 = np.zeros(n, dtype=np.uint8)
+    assert k.hs_wei_mul(2, p(kb), p(pb), p(inf_in), ctypes.c_size_t(n), p(out2), p(inf2)) == 2**64 - 1
+    assert np.array_equal(out, out2) and np.array_equal(inf, inf2)
+    exp, einf = coracle.wei_mul("bls12_381_g1", kb, pb, inf_in=inf_in)
+    assert np.array_equal(out, exp) and np.array_equal(inf.astype(bool), einf)
+    for i in (0, 1, 3, 6, 20):
+        want = c.mul(ks[i], pts[i]) if ks[i] else None
+        assert (inf[i] == 1) == (want is None) and (want is None or out[i].tobytes() == c.enc(want))
+    bad = kb.copy()
+    bad[4] = 0xFF
+    assert k.hs_bls_g1_mul_glv(p(bad), p(pb), p(inf_in), ctypes.c_size_t(n), p(out), p(inf)) == (4 << 8) | 1
+    badp = pb.copy()
+    badp[9, -1] ^= 1
+    assert k.hs_bls_g1_mul_glv(p(kb), p(badp), p(inf_in), ctypes.c_size_t(n), p(out), p(inf)) == (9 << 8) | 2
 
 
 @pytest.mark.parametrize("cid,curve", [(2, "bls12_381_g1"), (3, "p256k1")])

@@ -228,6 +228,10 @@ def main():
         if cname == "BLSG1":
             out += "// beta: (beta x, y) = [-x^2](x, y) on G1 (subgroup test, bls12_381/g1.rs:55, :105), Montgomery domain\n"
             out += arr("BLSG1_BETA", mont(bls_beta(), p, n), n)
+            xsq = 0xd201000000010000 ** 2
+            assert (xsq ** 2 - xsq + 1) == BLS_R and xsq.bit_length() == 128
+            out += "// x^2 (x = the curve seed, r = x^4 - x^2 + 1): the GLV split k = q x^2 + rem, k P = rem P - q (beta x, y) on G1\n"
+            out += arr("BLSG1_XSQ", xsq, 4)
         out += "\n"
     out += "// ---- ristretto255 (RFC 9496 Appendix A): 1 / sqrt(a - d), little-endian limbs\n"
     out += arr("RISTRETTO_INVSQRT_A_MINUS_D", ristretto_invsqrt_a_minus_d(), 8)
