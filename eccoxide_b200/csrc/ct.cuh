@@ -100,20 +100,20 @@ ECB_DEV void wei_add_complete_am3(typename C::F::el& X3, typename C::F::el& Y3, 
     typename F::el t0, t1, t2, t3, t4, b, x3, y3, z3;
     Wei<C>::get_b(b);
     F::mul_ni(t0, X1, X2); F::mul_ni(t1, Y1, Y2); F::mul_ni(t2, Z1, Z2);
-    F::add(t3, X1, Y1); F::add(t4, X2, Y2); F::mul_ni(t3, t3, t4);
-    F::add(t4, t0, t1); F::sub(t3, t3, t4); F::add(t4, Y1, Z1);
-    F::add(x3, Y2, Z2); F::mul_ni(t4, t4, x3); F::add(x3, t1, t2);
-    F::sub(t4, t4, x3); F::add(x3, X1, Z1); F::add(y3, X2, Z2);
-    F::mul_ni(x3, x3, y3); F::add(y3, t0, t2); F::sub(y3, x3, y3);
-    F::mul_ni(z3, b, t2); F::sub(x3, y3, z3); F::add(z3, x3, x3);
-    F::add(x3, x3, z3); F::sub(z3, t1, x3); F::add(x3, t1, x3);
-    F::mul_ni(y3, b, y3); F::add(t1, t2, t2); F::add(t2, t1, t2);
-    F::sub(y3, y3, t2); F::sub(y3, y3, t0); F::add(t1, y3, y3);
-    F::add(y3, t1, y3); F::add(t1, t0, t0); F::add(t0, t1, t0);
-    F::sub(t0, t0, t2); F::mul_ni(t1, t4, y3); F::mul_ni(t2, t0, y3);
-    F::mul_ni(y3, x3, z3); F::add(y3, y3, t2); F::mul_ni(x3, t3, x3);
-    F::sub(x3, x3, t1); F::mul_ni(z3, t4, z3); F::mul_ni(t1, t3, t0);
-    F::add(z3, z3, t1);
+    F::add_ct(t3, X1, Y1); F::add_ct(t4, X2, Y2); F::mul_ni(t3, t3, t4);
+    F::add_ct(t4, t0, t1); F::sub_ct(t3, t3, t4); F::add_ct(t4, Y1, Z1);
+    F::add_ct(x3, Y2, Z2); F::mul_ni(t4, t4, x3); F::add_ct(x3, t1, t2);
+    F::sub_ct(t4, t4, x3); F::add_ct(x3, X1, Z1); F::add_ct(y3, X2, Z2);
+    F::mul_ni(x3, x3, y3); F::add_ct(y3, t0, t2); F::sub_ct(y3, x3, y3);
+    F::mul_ni(z3, b, t2); F::sub_ct(x3, y3, z3); F::add_ct(z3, x3, x3);
+    F::add_ct(x3, x3, z3); F::sub_ct(z3, t1, x3); F::add_ct(x3, t1, x3);
+    F::mul_ni(y3, b, y3); F::add_ct(t1, t2, t2); F::add_ct(t2, t1, t2);
+    F::sub_ct(y3, y3, t2); F::sub_ct(y3, y3, t0); F::add_ct(t1, y3, y3);
+    F::add_ct(y3, t1, y3); F::add_ct(t1, t0, t0); F::add_ct(t0, t1, t0);
+    F::sub_ct(t0, t0, t2); F::mul_ni(t1, t4, y3); F::mul_ni(t2, t0, y3);
+    F::mul_ni(y3, x3, z3); F::add_ct(y3, y3, t2); F::mul_ni(x3, t3, x3);
+    F::sub_ct(x3, x3, t1); F::mul_ni(z3, t4, z3); F::mul_ni(t1, t3, t0);
+    F::add_ct(z3, z3, t1);
     F::copy(X3, x3); F::copy(Y3, y3); F::copy(Z3, z3);
 }
 
@@ -167,7 +167,7 @@ ECB_DEV void wei_mul_base_ct_body(size_t idx, size_t n, const u32* scalars, cons
             }
         }
         const u32 z = ct_eq_mask(d, 0u) & 1u;
-        F::neg(ny, ey);
+        F::neg_ct(ny, ey);
         F::select(ey, neg, ny, ey);
         F::select(ey, z, one, ey);               // digit 0: (0 : 1 : 0)
         F::set_zero(ez);

@@ -453,6 +453,34 @@ struct Mont {
         set_zero(z);
         sub(r, z, a);
     }
+    // constant-time forms for secret operands (ct.cuh).  The loose add / sub above BRANCH on the carry of their fold
+    // (once in ~2^32 operand pairs); here the second fold is always executed with that carry as its operand.  The
+    // canonical fields are branch-free already (final_sub selects by masks).
+    ECB_DEV static void add_ct(el& r, const el& a, const el& b) {
+        if constexpr (LOOSE) {
+            u32 t[N];
+            u32 c = add_n<N>(t, a.v, b.v);
+            u32 c2 = fold_carry(r, t, c);
+            (void)fold_carry(r, r.v, c2);
+            return;
+        }
+        add(r, a, b);
+    }
+    ECB_DEV static void sub_ct(el& r, const el& a, const el& b) {
+        if constexpr (LOOSE) {
+            u32 t[N];
+            u32 bw = sub_n<N>(t, a.v, b.v);
+            u32 b2 = fold_borrow(r, t, bw);
+            (void)fold_borrow(r, r.v, b2);
+            return;
+        }
+        sub(r, a, b);
+    }
+    ECB_DEV static void neg_ct(el& r, const el& a) {
+        el z;
+        set_zero(z);
+        sub_ct(r, z, a);
+    }
     // canonical representative (< p) of a possibly loose value
     ECB_DEV static void canon(el& r, const el& a) {
         if constexpr (LOOSE) {

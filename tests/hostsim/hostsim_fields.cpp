@@ -26,6 +26,9 @@ template <class P> static void mont_op(int op, const u32* a, const u32* b, u32* 
         case 10: F::template mul_small<4>(z, x); break;
         case 11: F::template mul_small<8>(z, x); break;
         case 12: F::copy(z, x); F::template mul_small<8>(z, z); break;   // in place
+        case 13: F::add_ct(z, x, y); break;
+        case 14: F::sub_ct(z, x, y); break;
+        case 15: F::neg_ct(z, x); break;
     }
     memcpy(r, z.v, 4 * P::N);
 }

@@ -107,7 +107,7 @@ def test_montgomery_fields(hs, field, mod, n):
             cases.append((pick(), pick()))
     for a, b in cases:
         aw, bw = words(a, n), words(b, n)
-        for op, exp in ((0, a * b * Ri), (1, a * a * Ri), (2, a + b), (3, a - b), (4, -a), (5, a * Rm), (7, a * Ri)):
+        for op, exp in ((0, a * b * Ri), (1, a * a * Ri), (2, a + b), (3, a - b), (4, -a), (5, a * Rm), (7, a * Ri), (13, a + b), (14, a - b), (15, -a)):
             if op == 5 and a >= mod:
                 continue  # to_mont takes canonical wire values
             f.hs_mont(field, op, p(aw), p(bw), p(r))
