@@ -27,6 +27,9 @@ struct fe_mont {
 // m = T mod 2^96 — no multiplication at all; product = N^2, square = N(N+1)/2 IMAD.WIDE.
 // kind 2 = p384: -p^-1 = 1 + 2^32 + 2^64 (mod 2^96) and p = 2^384 - 2^128 - 2^96 + 2^32 - 1: four
 // rounds of 96 bits, each a handful of shifted additions / subtractions of m — again no multiply.
+// kind 3 = secp256k1's p = 2^256 - 2^32 - 977: NO Montgomery domain (the parameter class gives R = 1, so "to_mont" and
+// "r2" are identities): a 512-bit product folds as lo + hi (2^32 + 977) — eight IMAD.WIDE and a shifted addition —
+// product = N^2 + N + 1, square = N(N+1)/2 + N + 1 instead of the 2 N^2 / N(N+1)/2 + N^2 of the generic rows.
 template <class P>
 struct MontKind {
     static constexpr int kind = 0;
@@ -43,7 +46,7 @@ struct Mont {
     typedef fe_mont<P::N> el;
     // p256r1 and p384r1 keep elements "loose": any representative below 2^(32 N), not necessarily
     // below p (see the note above add()); the generic primes stay canonical
-    static constexpr bool LOOSE = MontKind<P>::kind == 1 || MontKind<P>::kind == 2;
+    static constexpr bool LOOSE = MontKind<P>::kind == 1 || MontKind<P>::kind == 2 || MontKind<P>::kind == 3;
 
     ECB_DEV static void set_zero(el& r) {
         ECB_UNROLL
@@ -114,6 +117,14 @@ struct Mont {
     // r = t + c * (2^256 - p) mod 2^256 for c in {0, 1};  2^256 - p = 2^224 - 2^192 - 2^96 + 1
     ECB_DEV static u32 fold_carry(el& r, const u32* t, u32 c) {
         const u32 m = 0u - c;
+        if constexpr (MontKind<P>::kind == 3) {
+            // 2^256 - p = 2^32 + 977 = limbs {977, 1, 0, ...}; valid for any small c (977 c < 2^32)
+            r.v[0] = add_cc(t[0], 977u * c);
+            r.v[1] = addc_cc(t[1], c);
+            ECB_UNROLL
+            for (int i = 2; i < N; i++) r.v[i] = addc_cc(t[i], 0u);
+            return addc(0u, 0u);
+        }
         if constexpr (MontKind<P>::kind == 2) {
             // 2^384 - p = 2^128 + 2^96 - 2^32 + 1 = limbs {1, ffffffff, ffffffff, 0, 1, 0, ...}
             r.v[0] = add_cc(t[0], c);
@@ -138,6 +149,13 @@ struct Mont {
     // r = t - c * (2^256 - p) mod 2^256 ; returns the borrow
     ECB_DEV static u32 fold_borrow(el& r, const u32* t, u32 c) {
         const u32 m = 0u - c;
+        if constexpr (MontKind<P>::kind == 3) {
+            r.v[0] = sub_cc(t[0], 977u * c);
+            r.v[1] = subc_cc(t[1], c);
+            ECB_UNROLL
+            for (int i = 2; i < N; i++) r.v[i] = subc_cc(t[i], 0u);
+            return 0u - subc(0u, 0u);
+        }
         if constexpr (MontKind<P>::kind == 2) {
             r.v[0] = sub_cc(t[0], c);
             r.v[1] = subc_cc(t[1], m);
@@ -164,6 +182,7 @@ struct Mont {
     // {c, 0, 0, -c, ~0, ~0, ~c, c - 1} for c >= 1 (all zero for c = 0); of c (2^384 - p) = c 2^128 + c 2^96 - c 2^32 + c:
     // {c, -c, ~0, c - 1, c, 0, ...}.
     ECB_DEV static u32 fold_carry_small(el& r, const u32* t, u32 c) {
+        if constexpr (MontKind<P>::kind == 3) return fold_carry(r, t, c);
         const u32 nz = 0u - (u32)(c != 0u);
         if constexpr (MontKind<P>::kind == 2) {
             r.v[0] = add_cc(t[0], c);
@@ -187,6 +206,7 @@ struct Mont {
     }
     // r = t - c (2^(32N) - p) mod 2^(32N), returns the borrow
     ECB_DEV static u32 fold_borrow_small(el& r, const u32* t, u32 c) {
+        if constexpr (MontKind<P>::kind == 3) return fold_borrow(r, t, c);
         const u32 nz = 0u - (u32)(c != 0u);
         if constexpr (MontKind<P>::kind == 2) {
             r.v[0] = sub_cc(t[0], c);
@@ -280,7 +300,44 @@ struct Mont {
         fold_carry(r, T + 12, T[24]);
     }
 
+    // ---- secp256k1: T (16 limbs) -> lo + hi (2^32 + 977), twice, loose result (< 2^256)
+    ECB_DEV static void k256_reduce(el& r, const u32* T) {
+        u32 R[10];
+        ECB_UNROLL
+        for (int i = 0; i < 8; i++) R[i] = T[i];
+        R[8] = 0;
+        R[9] = 0;
+        mac_chain<4, true>(R, T + 8, 977u);        // 977 * T[8, 10, 12, 14] at limbs 0, 2, 4, 6 (carry into R[8])
+        mac_chain<4, false>(R + 1, T + 9, 977u);   // 977 * T[9, 11, 13, 15] at limbs 1, 3, 5, 7: R[8] < 2^11, no carry out
+        R[1] = add_cc(R[1], T[8]);                 // + hi << 32
+        ECB_UNROLL
+        for (int i = 2; i <= 8; i++) R[i] = addc_cc(R[i], T[i + 7]);
+        R[9] = addc(0u, 0u);
+        // V = R[8] + 2^32 R[9] < 2^33:  V (2^32 + 977) = (977 R[8]) + 2^32 (977 R[9] + R[8]) + 2^64 R[9]
+        const u32 w0 = mul_lo(R[8], 977u);
+        const u64 a1 = (u64)mul_hi(R[8], 977u) + (u64)(977u * R[9]) + R[8];
+        u32 t[8];
+        t[0] = add_cc(R[0], w0);
+        t[1] = addc_cc(R[1], (u32)a1);
+        t[2] = addc_cc(R[2], (u32)(a1 >> 32) + R[9]);
+        ECB_UNROLL
+        for (int i = 3; i < 8; i++) t[i] = addc_cc(R[i], 0u);
+        const u32 c = addc(0u, 0u);
+        // a wrapped value is below 2^66: adding 2^32 + 977 once more cannot carry out of limb 2
+        r.v[0] = add_cc(t[0], 977u * c);
+        r.v[1] = addc_cc(t[1], c);
+        r.v[2] = addc(t[2], 0u);
+        ECB_UNROLL
+        for (int i = 3; i < 8; i++) r.v[i] = t[i];
+    }
+
     ECB_DEV static void mul(el& r, const el& a, const el& b) {
+        if constexpr (MontKind<P>::kind == 3) {
+            u32 T[16];
+            mul_full<N>(T, a.v, b.v);
+            k256_reduce(r, T);
+            return;
+        }
         if constexpr (MontKind<P>::kind == 2) {
             u32 T[25];
             mul_full<N>(T, a.v, b.v);
@@ -386,6 +443,12 @@ struct Mont {
     }
 
     ECB_DEV static void sqr(el& r, const el& a) {
+        if constexpr (MontKind<P>::kind == 3) {
+            u32 T[16];
+            sqr_full<N>(T, a.v);
+            k256_reduce(r, T);
+            return;
+        }
         if constexpr (MontKind<P>::kind == 0) {
             u32 T[2 * N];
             sqr_full<N>(T, a.v);

@@ -15,4 +15,9 @@ struct MontKind<P384_FP> {
     static constexpr int kind = 2;
 };
 
+template <>
+struct MontKind<K256_FP> {
+    static constexpr int kind = 3;
+};
+
 }  // namespace ecb

@@ -113,7 +113,7 @@ double hs_fe43_maxlimb(int op, const u32* a, const u32* b, int loosen) {
 }
 u32 hs_fe25519_is_canonical(const u32* a) { return F25519::is_canonical_words(a); }
 
-// field: 0 P256_FP 1 P256_FN 2 P384_FP 3 P384_FN 4 BLS_FP 5 BLS_FR
+// field: 0 P256_FP 1 P256_FN 2 P384_FP 3 P384_FN 4 BLS_FP 5 BLS_FR 6 K256_FP (plain, pseudo-Mersenne) 7 K256_FN
 void hs_mont(int field, int op, const u32* a, const u32* b, u32* r) {
     switch (field) {
         case 0: mont_op<P256_FP>(op, a, b, r); break;
@@ -122,6 +122,8 @@ void hs_mont(int field, int op, const u32* a, const u32* b, u32* r) {
         case 3: mont_op<P384_FN>(op, a, b, r); break;
         case 4: mont_op<BLS_FP>(op, a, b, r); break;
         case 5: mont_op<BLS_FR>(op, a, b, r); break;
+        case 6: mont_op<K256_FP>(op, a, b, r); break;
+        case 7: mont_op<K256_FN>(op, a, b, r); break;
     }
 }
 void hs_mont3(int field, int op, const u32* a, const u32* b, const u32* c, u32* r) {
@@ -132,6 +134,8 @@ void hs_mont3(int field, int op, const u32* a, const u32* b, const u32* c, u32* 
         case 3: mont_op3<P384_FN>(op, a, b, c, r); break;
         case 4: mont_op3<BLS_FP>(op, a, b, c, r); break;
         case 5: mont_op3<BLS_FR>(op, a, b, c, r); break;
+        case 6: mont_op3<K256_FP>(op, a, b, c, r); break;
+        case 7: mont_op3<K256_FN>(op, a, b, c, r); break;
     }
 }
 }

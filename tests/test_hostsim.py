@@ -86,16 +86,23 @@ def test_fe43_fp64_field(hs):
             assert f.hs_fe43_maxlimb(0, p(aw), p(bw), loosen) <= tight and f.hs_fe43_maxlimb(1, p(aw), p(bw), loosen) <= tight
 
 
-@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (1, R.P256.n, 8), (2, R.P384.p, 12), (3, R.P384.n, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
+K256_P, K256_N = 2**256 - 2**32 - 977, 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141
+MONT_FIELDS = [(0, R.P256.p, 8), (1, R.P256.n, 8), (2, R.P384.p, 12), (3, R.P384.n, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8), (6, K256_P, 8), (7, K256_N, 8)]
+LOOSE_FIELDS = (0, 2, 6)   # p256r1 / p384r1 / p256k1 field elements are kept "loose" (< 2^(32 n), congruent): see mont.cuh
+PLAIN_FIELDS = (6,)        # secp256k1's field has no Montgomery domain (R = 1): pseudo-Mersenne folding
+
+
+@pytest.mark.parametrize("field,mod,n", MONT_FIELDS)
 def test_montgomery_fields(hs, field, mod, n):
     f, _ = hs
     g = rng(field)
     Rm = 1 << (32 * n)
-    Ri = pow(Rm, -1, mod)
+    Rd = 1 if field in PLAIN_FIELDS else Rm      # the domain's radix
+    Ri = pow(Rd, -1, mod)
     r = np.zeros(n, dtype=np.uint32)
     cases = [(0, 0), (1, mod - 1), (mod - 1, mod - 1), (Rm % mod, 1)]
     cases += [(int.from_bytes(g.bytes(48), "little") % mod, int.from_bytes(g.bytes(48), "little") % mod) for _ in range(100)]
-    loose = field in (0, 2)  # p256r1 / p384r1 field elements are kept "loose" (< 2^(32 n), congruent): see mont.cuh
+    loose = field in LOOSE_FIELDS
     if loose:  # any n-limb value is a valid operand, including the ones that need a second fold
         K = Rm - mod
         cases += [(Rm - 1, Rm - 1), (Rm - 1, mod), (mod, mod), (Rm - 2**200, Rm - 5), (0, Rm - 1), (3, Rm - 2), (mod + 1, 2),
@@ -107,7 +114,7 @@ def test_montgomery_fields(hs, field, mod, n):
             cases.append((pick(), pick()))
     for a, b in cases:
         aw, bw = words(a, n), words(b, n)
-        for op, exp in ((0, a * b * Ri), (1, a * a * Ri), (2, a + b), (3, a - b), (4, -a), (5, a * Rm), (7, a * Ri), (13, a + b), (14, a - b), (15, -a)):
+        for op, exp in ((0, a * b * Ri), (1, a * a * Ri), (2, a + b), (3, a - b), (4, -a), (5, a * Rd), (7, a * Ri), (13, a + b), (14, a - b), (15, -a)):
             if op == 5 and a >= mod:
                 continue  # to_mont takes canonical wire values
             f.hs_mont(field, op, p(aw), p(bw), p(r))
@@ -116,8 +123,8 @@ def test_montgomery_fields(hs, field, mod, n):
             else:
                 assert val(r) == exp % mod, (field, op)
     a = cases[5][0]
-    f.hs_mont(field, 6, p(words(a * Rm % mod, n)), p(words(0, n)), p(r))
-    assert val(r) % mod == pow(a, -1, mod) * Rm % mod
+    f.hs_mont(field, 6, p(words(a * Rd % mod, n)), p(words(0, n)), p(r))
+    assert val(r) % mod == pow(a, -1, mod) * Rd % mod
 
 
 def test_ed25519_mul_base_and_table(hs, golden, coracle):
@@ -436,15 +443,15 @@ def _structured(g, n):
     return sum(int(choices[int(c)] if c < 4 else int(g.integers(0, 1 << 32))) << (32 * i) for i, c in enumerate(g.integers(0, 5, size=n)))
 
 
-@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (1, R.P256.n, 8), (2, R.P384.p, 12), (3, R.P384.n, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
+@pytest.mark.parametrize("field,mod,n", MONT_FIELDS)
 def test_montgomery_fields_structured_operands(hs, field, mod, n):
     """A dropped top carry in the p384 reduction only showed with limbs like (1, 1, ff..f): random
     operands never hit it.  Every field gets the structured stress."""
     f, _ = hs
     g = rng(100 + field)
     Rm = 1 << (32 * n)
-    Ri = pow(Rm, -1, mod)
-    loose = field == 0
+    Ri = pow(1 if field in PLAIN_FIELDS else Rm, -1, mod)
+    loose = field in (0, 6)
     r = np.zeros(n, dtype=np.uint32)
     for _ in range(1500):
         a = _structured(g, n) % (Rm if loose else mod)
@@ -457,7 +464,7 @@ def test_montgomery_fields_structured_operands(hs, field, mod, n):
                 assert val(r) == exp % mod, (field, op, hex(a), hex(b))
 
 
-@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (2, R.P384.p, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
+@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (2, R.P384.p, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8), (6, K256_P, 8)])
 def test_montgomery_merged_forms(hs, field, mod, n):
     """K a (K = 2, 3, 4, 8), a - b - c and a - b - 2c in one pass with a single fold of the accumulated carries /
     borrows (mont.cuh: mul_small, sub2, sub_2x) — on the loose fields every n-limb operand is valid, including the
@@ -465,7 +472,7 @@ def test_montgomery_merged_forms(hs, field, mod, n):
     f, _ = hs
     g = rng(300 + field)
     Rm = 1 << (32 * n)
-    loose = field in (0, 2)
+    loose = field in LOOSE_FIELDS
     top = Rm if loose else mod
     K = Rm - mod
     r = np.zeros(n, dtype=np.uint32)
@@ -575,7 +582,7 @@ def test_ecdsa_digest_to_scalar_on_device_code(hs):
                 assert (int.from_bytes(want, "big") % c.n).to_bytes(sb, "big") == R.ecdsa_digest_to_scalar(c, d)
 
 
-@pytest.mark.parametrize("field,mod,n", [(0, R.P256.p, 8), (1, R.P256.n, 8), (2, R.P384.p, 12), (3, R.P384.n, 12), (4, R.BLSG1.p, 12), (5, R.BLSG1.n, 8)])
+@pytest.mark.parametrize("field,mod,n", MONT_FIELDS)
 def test_safegcd_inversion_montgomery_fields(hs, field, mod, n):
     """Field inverses come from safegcd divsteps (csrc/modinv.cuh), not from a Fermat chain: check
     the whole range of operand shapes, including 0 -> 0."""
@@ -588,8 +595,9 @@ def test_safegcd_inversion_montgomery_fields(hs, field, mod, n):
     for a in vals:
         if a == 0:
             continue
-        f.hs_mont(field, 6, p(words(a * Rm % mod, n)), p(words(0, n)), p(r))
-        assert val(r) % mod == pow(a, -1, mod) * Rm % mod, hex(a)
+        Rd = 1 if field in PLAIN_FIELDS else Rm
+        f.hs_mont(field, 6, p(words(a * Rd % mod, n)), p(words(0, n)), p(r))
+        assert val(r) % mod == pow(a, -1, mod) * Rd % mod, hex(a)
     f.hs_mont(field, 6, p(words(0, n)), p(words(0, n)), p(r))
     assert val(r) == 0
 

@@ -75,8 +75,11 @@ def arr(name, x, n):
     return "ECB_CONST u32 %s[%d] = {%s};\n" % (name, n, ", ".join("0x%08xu" % w for w in limbs(x, n)))
 
 
+PLAIN_FIELDS = {"K256_FP"}   # no Montgomery domain: pseudo-Mersenne folding, R = 1 (mont.cuh kind 3)
+
+
 def field(name, p, n):
-    R = 1 << (32 * n)
+    R = 1 if name in PLAIN_FIELDS else 1 << (32 * n)
     inv = (-pow(p, -1, 1 << 32)) % (1 << 32)
     s = "// ---- field %s: p = 0x%x\n" % (name, p)
     s += arr(name + "_MOD", p, n)
@@ -90,6 +93,8 @@ def field(name, p, n):
 
 
 def mont(x, p, n):
+    if p == K256_P:   # plain field (PLAIN_FIELDS)
+        return x % p
     return (x << (32 * n)) % p
 
 
