@@ -54,6 +54,9 @@ WORK = {
     "p256_ecdsa_verify": 296900,
     "p384_mul": 864666,
     "bls12_381_g1_mul": 984276,
+    # p256k1 counted the way bls12_381_g1_mul was (a = 0 fixed window, projective.rs:842: 64 x (4 doublings of 7 M + 2 S, one addition
+    # of 14 M) + the table; word-by-word Montgomery on 8 limbs: M 136 / S 108)
+    "p256k1_mul": 256 * (7 * 136 + 2 * 108) + 72 * 14 * 136 + 5 * 136,
     "x448": 715596,
     # wire formats, reference algorithm: sqrt chain p256r1.rs:68 (253 S + 11 M) + x^3 + a x + b;
     # BLS: Fp::sqrt = power((p+1)/4) by square-and-multiply (~380 S + ~190 M) + is_in_subgroup
@@ -77,6 +80,9 @@ EXEC = {
     "p256_ecdsa_verify": 263 * (3 * 64 + 5 * 36) + 59 * (10 * 64 + 4 * 36) + 11 * (7 * 64 + 4 * 36) + 14 * 64 + 5 * 136 + 5 * 64,
     "p384_mul": 388 * (3 * 144 + 5 * 78) + 84 * (10 * 144 + 4 * 78) + 5 * 144,    # 77 windows
     "bls12_381_g1_mul": 263 * (2 * 288 + 5 * 222) + 59 * (10 * 288 + 4 * 222) + 5 * 288,
+    # through the endomorphism (option bls12_381_g1_glv): 26 windows of two 128-bit halves = 25 x 5 doublings, 52 additions + 26 beta products
+    "bls12_381_g1_mul_glv": 133 * (2 * 288 + 5 * 222) + 59 * (10 * 288 + 4 * 222) + 26 * 288 + 5 * 288,
+    "p256k1_mul": 263 * (2 * 73 + 5 * 45) + 59 * (10 * 73 + 4 * 45) + 5 * 73,   # pseudo-Mersenne field: M 64 + 9, S 36 + 9
     "x448": 448 * (5 * 196 + 4 * 105 + 14) + 5 * 196,
     "ed25519_mul": 256 * (3 * 72 + 4 * 44) + 72 * 8 * 72 + 5 * 72,
 }
@@ -85,11 +91,12 @@ ORDERS = {   # group orders: scalars are 64 uniform bytes reduced mod the order 
     "p256r1": 0xFFFFFFFF00000000FFFFFFFFFFFFFFFFBCE6FAADA7179E84F3B9CAC2FC632551,
     "p384r1": 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFC7634D81F4372DDF581A0DB248B0A77AECEC196ACCC52973,
     "bls12_381_g1": 0x73EDA753299D7D483339D80809A1D80553BDA402FFFE5BFEFFFFFFFF00000001,
+    "p256k1": 0xFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFFEBAAEDCE6AF48A03BBFD25E8CD0364141,
 }
 
 
 def executed_mac32(name, ctx, n):
-    base = name.replace("_2p16", "")
+    base = name.replace("_2p16", "").replace("_glv", "")
     if base in ("ed25519_keygen", "ed25519_sign"):   # constant-time comb: 64 windows x 7 M, Fermat chain shared by 32 elements, 5 M affine
         return (64 * 7 + 5) * 72 + (254 * 44 + 11 * 72) // 32
     if base == "p256_ecdsa_sign":                    # 65 complete additions (12 M + 2 m_b), Fermat chains in GF(p) and GF(n) shared by 32 elements
@@ -102,7 +109,7 @@ def executed_mac32(name, ctx, n):
         # fused kernel: prefix + suffix scans (5 + 5), other-warp product (4), E (2), inverse (1), finisher (2);
         # two-kernel form: Montgomery's trick 3 M + finisher 2 M
         return (comb + (19 if fused else 5)) * 72
-    return EXEC.get(base)
+    return EXEC.get(name.replace("_2p16", "")) or EXEC.get(base)
 
 
 # name -> (log2 n per GPU, bytes in per op, bytes out per op, BASELINE.json config it belongs to)
@@ -114,6 +121,8 @@ WORKLOADS = {
     "p256_mul": (20, 96, 65, "configs[2] variable-base Point::mul"),
     "p256_ecdsa_verify": (20, 160, 1, "configs[2] ecdsa verify_batch"),
     "bls12_381_g1_mul": (20, 128, 97, "configs[3]"),
+    "bls12_381_g1_mul_glv": (20, 128, 97, "configs[3] for points known to be in G1: option bls12_381_g1_glv (scalar split over the endomorphism)"),
+    "p256k1_mul": (20, 96, 65, "SURVEY 8 f.4: variable-base Point::mul on p256k1 (secp256k1)"),
     "p384_mul": (18, 144, 97, "configs[4] sweep member"),
     "x448": (18, 112, 56, "configs[4] sweep member (X448 stands in for edwards448)"),
     "ed25519_mul": (18, 96, 64, "north star: variable-base Ed25519 Point::mul"),
@@ -134,7 +143,7 @@ EXTRA_DEFAULT = ["ed25519_mul_base", "p256_mul", "x25519", "p256_ecdsa_verify", 
 # op name and curve for ecb_warm (the *_dev entry points never allocate)
 WARM = {"ed25519_mul_base": ("ed25519_mul_base", None), "ed25519_mul": ("ed25519_mul", None), "x25519": ("x25519", None),
         "x25519_base": ("x25519_base", None), "x448": ("x448", None), "p256_mul": ("wei_mul", "p256r1"), "p384_mul": ("wei_mul", "p384r1"),
-        "bls12_381_g1_mul": ("wei_mul", "bls12_381_g1"), "ed25519_verify": ("ed25519_verify_prehashed", None),
+        "bls12_381_g1_mul": ("wei_mul", "bls12_381_g1"), "p256k1_mul": ("wei_mul", "p256k1"), "ed25519_verify": ("ed25519_verify_prehashed", None),
         "p256_mul_base": ("wei_mul_base", "p256r1"), "bls12_381_g1_mul_base": ("wei_mul_base", "bls12_381_g1"),
         "p256_ecdsa_verify": ("ecdsa_verify_hashed", "p256r1"), "p256_ecdsa_sign": ("ecdsa_sign_hashed", "p256r1"),
         "ed25519_keygen": ("ed25519_public_from_seed", None), "ed25519_sign": ("ed25519_sign", None),
@@ -144,11 +153,11 @@ WARM = {"ed25519_mul_base": ("ed25519_mul_base", None), "ed25519_mul": ("ed25519
 
 
 def work_of(name):
-    return WORK[name.replace("_2p16", "").replace("_vartime", "")]
+    return WORK[name.replace("_2p16", "").replace("_vartime", "").replace("_glv", "")]
 
 
 # ---- synthetic inputs (seeded) ----------------------------------------------------
-_CLEAR = {(32, 4): "ed25519", (32, 1): "p256r1", (48, 1): "p384r1", (32, 2): "bls12_381_g1"}
+_CLEAR = {(32, 4): "ed25519", (32, 1): "p256r1", (48, 1): "p384r1", (32, 2): "bls12_381_g1", (32, 3): "p256k1"}
 
 
 def rand_scalars(g, n, nbytes, clear_top_bits, endian):
@@ -169,7 +178,7 @@ def make_inputs(name, n, ctx, seed):
     """Host numpy inputs for one batch of `name`.  Points are produced by the library's own fixed-base
     entry points (outside any timed region) and spot-checked against the oracle by the caller."""
     g = np.random.Generator(np.random.Philox(seed))
-    base = name.replace("_2p16", "").replace("_vartime", "")
+    base = name.replace("_2p16", "").replace("_vartime", "").replace("_glv", "")
     uniq = min(n, 1 << 14)
     tile = lambda a: np.ascontiguousarray(np.tile(a, (n // a.shape[0], 1)))
     if base == "ed25519_mul_base":
@@ -183,8 +192,8 @@ def make_inputs(name, n, ctx, seed):
     if base == "ed25519_mul":
         pts = ctx.ed25519_mul_base(rand_scalars(g, uniq, 32, 4, "little"))
         return [rand_scalars(g, n, 32, 4, "little"), tile(pts)]
-    if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
-        curve, sb, clr = {"p256_mul": ("p256r1", 32, 1), "p384_mul": ("p384r1", 48, 1), "bls12_381_g1_mul": ("bls12_381_g1", 32, 2)}[base]
+    if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul", "p256k1_mul"):
+        curve, sb, clr = {"p256_mul": ("p256r1", 32, 1), "p384_mul": ("p384r1", 48, 1), "bls12_381_g1_mul": ("bls12_381_g1", 32, 2), "p256k1_mul": ("p256k1", 32, 3)}[base]
         pts, inf = ctx.wei_mul_base(curve, rand_scalars(g, uniq, sb, clr, "big"))
         assert not inf.any()
         return [rand_scalars(g, n, sb, clr, "big"), tile(pts)]
@@ -255,7 +264,7 @@ def make_inputs(name, n, ctx, seed):
 
 OUT_SHAPES = {
     "ed25519_mul_base": [64], "ed25519_mul": [64], "x25519": [32], "x25519_base": [32], "x448": [56],
-    "p256_mul": [64, 1], "p384_mul": [96, 1], "bls12_381_g1_mul": [96, 1], "p256_ecdsa_verify": [1],
+    "p256_mul": [64, 1], "p384_mul": [96, 1], "bls12_381_g1_mul": [96, 1], "p256k1_mul": [64, 1], "p256_ecdsa_verify": [1],
     "p256_mul_base": [64, 1], "bls12_381_g1_mul_base": [96, 1], "ed25519_verify": [1],
     "p256_decompress": [64, 1], "bls12_381_g1_from_compressed": [96, 1], "ed25519_keygen": [32], "ed25519_sign": [64], "p256_ecdsa_sign": [64, 1],
 }
@@ -276,7 +285,7 @@ def _msg_offsets(msgs):
 
 def dev_launch(ctx, name, ins, outs, n, stream):
     """Enqueue one step on device-resident buffers (raw pointers) through the *_dev C-ABI entry points."""
-    base = name.replace("_2p16", "")
+    base = name.replace("_2p16", "").replace("_glv", "")
     p = [t.data_ptr() for t in ins]
     o = [t.data_ptr() for t in outs]
     if base == "ed25519_mul_base":
@@ -289,8 +298,8 @@ def dev_launch(ctx, name, ins, outs, n, stream):
         ctx.dev_call("ecb_x25519_base_dev", 0, p[0], n, o[0], stream)
     elif base == "x448":
         ctx.dev_call("ecb_x448_dev", 0, p[0], p[1], n, o[0], stream)
-    elif base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
-        cid = {"p256_mul": 0, "p384_mul": 1, "bls12_381_g1_mul": 2}[base]
+    elif base in ("p256_mul", "p384_mul", "bls12_381_g1_mul", "p256k1_mul"):
+        cid = {"p256_mul": 0, "p384_mul": 1, "bls12_381_g1_mul": 2, "p256k1_mul": 3}[base]
         ctx.dev_call("ecb_wei_mul_dev", 0, cid, p[0], p[1], n, o[0], o[1], stream)
     elif base == "ed25519_verify":
         ctx.dev_call("ecb_ed25519_verify_prehashed_dev", 0, p[0], p[1], p[2], p[3], n, o[0], stream)
@@ -320,7 +329,7 @@ def dev_launch(ctx, name, ins, outs, n, stream):
 
 def host_call(ctx, name, ins, outs=None):
     """One step through the host C-ABI entry point (host buffers in, host buffers out)."""
-    base = name.replace("_2p16", "")
+    base = name.replace("_2p16", "").replace("_glv", "")
     o = outs or [None, None]
     if base == "ed25519_mul_base":
         return [ctx.ed25519_mul_base(ins[0], out=o[0])]
@@ -332,8 +341,8 @@ def host_call(ctx, name, ins, outs=None):
         return [ctx.x25519_base(ins[0], out=o[0])]
     if base == "x448":
         return [ctx.x448(ins[0], ins[1], out=o[0])]
-    if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
-        curve = {"p256_mul": "p256r1", "p384_mul": "p384r1", "bls12_381_g1_mul": "bls12_381_g1"}[base]
+    if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul", "p256k1_mul"):
+        curve = {"p256_mul": "p256r1", "p384_mul": "p384r1", "bls12_381_g1_mul": "bls12_381_g1", "p256k1_mul": "p256k1"}[base]
         return list(ctx.wei_mul(curve, ins[0], ins[1], out=o[0], out_inf=o[1]))
     if base == "ed25519_verify":
         return [ctx.ed25519_verify_prehashed(ins[0], ins[1], ins[2], ins[3], out=o[0])]
@@ -357,7 +366,7 @@ def host_call(ctx, name, ins, outs=None):
 
 
 def oracle_call(C, name, ins, nthreads):
-    base = name.replace("_2p16", "").replace("_vartime", "")
+    base = name.replace("_2p16", "").replace("_vartime", "").replace("_glv", "")
     if base == "ed25519_mul_base":
         return [C.ed25519_mul_base(ins[0], nthreads)]
     if base == "ed25519_mul":
@@ -369,8 +378,8 @@ def oracle_call(C, name, ins, nthreads):
         return [C.x25519(ins[0], nine, nthreads)]
     if base == "x448":
         return [C.x448(ins[0], ins[1], nthreads)]
-    if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul"):
-        curve = {"p256_mul": "p256r1", "p384_mul": "p384r1", "bls12_381_g1_mul": "bls12_381_g1"}[base]
+    if base in ("p256_mul", "p384_mul", "bls12_381_g1_mul", "p256k1_mul"):
+        curve = {"p256_mul": "p256r1", "p384_mul": "p384r1", "bls12_381_g1_mul": "bls12_381_g1", "p256k1_mul": "p256k1"}[base]
         return list(C.wei_mul(curve, ins[0], ins[1], nthreads=nthreads))
     if base == "ed25519_verify":
         return [C.ed25519_verify_prehashed(ins[0], ins[1], ins[2], ins[3], nthreads)]
@@ -510,7 +519,7 @@ def measure_device(torch, ctx, name, n, steps, warmup, seed, dist=None, min_s=MI
     for b in range(nbuf):
         hb = ins_h if b == 0 else [np.roll(a, b * 977, axis=0) for a in ins_h]   # same elements, rotated: distinct buffers, same validity
         bufs.append([torch.from_numpy(a).cuda() for a in hb])
-    base = name.replace("_2p16", "")
+    base = name.replace("_2p16", "").replace("_glv", "")
     outs = [torch.empty((n, w), dtype=torch.uint8, device="cuda") for w in OUT_SHAPES[base.replace("_vartime", "")]]
     stream = torch.cuda.current_stream().cuda_stream
     op, curve = WARM[base]
@@ -585,7 +594,7 @@ def measure_e2e(torch, ctx, name, n, steps, inner, ins_h, dist=None):
     """Host-API throughput with pinned host buffers (the call a user of the C ABI makes): every pass copies
     its inputs host -> device and its results device -> host inside the timed region."""
     pinned = [torch.from_numpy(a).pin_memory().numpy() for a in ins_h]
-    base = name.replace("_2p16", "").replace("_vartime", "")
+    base = name.replace("_2p16", "").replace("_vartime", "").replace("_glv", "")
     pouts = [torch.empty((n, w), dtype=torch.uint8).pin_memory().numpy() for w in OUT_SHAPES[base]]
     for _ in range(3):
         host_call(ctx, name, pinned, pouts)
@@ -731,7 +740,18 @@ def load_json(path):
         return {}
 
 
-def run_workload(torch, ctx, name, steps, warmup, world, rank, dist, peak, probes, check=True, cpu=False, e2e_cap_s=6.0, strong=False):
+def run_workload(torch, ctx, name, *a, **kw):
+    """_run_workload with the library option a `_glv` workload stands for switched on around it."""
+    if not name.endswith("_glv"):
+        return _run_workload(torch, ctx, name, *a, **kw)
+    ctx.set_option("bls12_381_g1_glv", 1)
+    try:
+        return _run_workload(torch, ctx, name, *a, **kw)
+    finally:
+        ctx.set_option("bls12_381_g1_glv", 0)
+
+
+def _run_workload(torch, ctx, name, steps, warmup, world, rank, dist, peak, probes, check=True, cpu=False, e2e_cap_s=6.0, strong=False):
     """Everything reported for one workload: device-resident value, e2e, the three roofline fractions, parity.
     strong: the workload's batch is the WHOLE job and every rank takes its contiguous 1/world slice."""
     n = (1 << WORKLOADS[name][0]) // (world if strong else 1)
@@ -815,7 +835,7 @@ def run_single_process(args):
         one = Context(devices=[0])   # inputs that need points come from a one-device context
         ins = make_inputs(name, n, one, 0xECC00001)
         one.close()
-        base = name.replace("_2p16", "")
+        base = name.replace("_2p16", "").replace("_glv", "")
         pinned = [torch.from_numpy(a).pin_memory().numpy() for a in ins]
         pouts = [torch.empty((n, w), dtype=torch.uint8).pin_memory().numpy() for w in OUT_SHAPES[base]]
         for _ in range(3):
@@ -929,6 +949,8 @@ def main():
 
     if args.profile_run:   # two passes of one workload, nothing else: for ncu
         n = 1 << WORKLOADS[name][0]
+        if name.endswith("_glv"):
+            ctx.set_option("bls12_381_g1_glv", 1)
         measure_device(torch, ctx, name, n, 1, 3, 0xECC00001, None, min_s=0.0, inner=1)
         ctx.close()
         return

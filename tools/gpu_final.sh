@@ -5,7 +5,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?" >> gpurun_out/${TAG}_smoke.log
 timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${TAG}_pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${TAG}_pytest_gpu.log
 python bench.py --impl reference > gpurun_out/${TAG}_bench_ref.json 2> gpurun_out/${TAG}_bench_ref.err
-python bench.py --extra ed25519_mul_base_2p16,x25519,x25519_base,p256_mul,p256_ecdsa_verify,bls12_381_g1_mul,p384_mul,x448,ed25519_mul,ed25519_verify,p256_mul_base,bls12_381_g1_mul_base,p256_decompress,bls12_381_g1_from_compressed,ed25519_keygen,ed25519_sign,p256_ecdsa_sign > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err
+python bench.py --extra ed25519_mul_base_2p16,x25519,x25519_base,p256_mul,p256_ecdsa_verify,bls12_381_g1_mul,p384_mul,x448,ed25519_mul,ed25519_verify,p256_mul_base,bls12_381_g1_mul_base,p256_decompress,bls12_381_g1_from_compressed,ed25519_keygen,ed25519_sign,p256_ecdsa_sign,p256k1_mul,bls12_381_g1_mul_glv > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?" >> gpurun_out/${TAG}_bench.err
 for w in x25519 p256_mul; do python bench.py --workload $w --steps 5 --extra "" > gpurun_out/${TAG}_bench_$w.json 2> gpurun_out/${TAG}_bench_$w.err; python bench.py --impl reference --workload $w --steps 2 --warmup 1 > gpurun_out/${TAG}_bench_ref_$w.json 2>&1; done
 CMD="python bench.py --steps 3 --warmup 3 --no-cpu --no-check --extra x25519,p256_mul --extra-steps 1"
 eval $CMD > gpurun_out/${TAG}_plain.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file gpurun_out/${TAG}_launches.csv bash -c "$CMD" > gpurun_out/${TAG}_list.log 2>&1
