@@ -2,7 +2,7 @@
 # full capture of the P-256 variable-base kernel: bash tools/gpu_profile_p256.sh TAG [workload] [kernel-regex]
 TAG=$1; WL=${2:-p256_mul}; RX=${3:-k_wei_mul}; mkdir -p gpurun_out
 CMD2="python bench.py --workload $WL --profile-run --steps 1 --warmup 1 --no-cpu --no-check --extra ''"
-eval $CMD2 > gpurun_out/${TAG}_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"$RX" -s 1 -c 1 -o /tmp/${TAG}_prof bash -c "$CMD2" > gpurun_out/${TAG}_ncu.log 2>&1
+eval $CMD2 > gpurun_out/${TAG}_plain2.log 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"$RX" -s 2 -c 1 -o /tmp/${TAG}_prof bash -c "$CMD2" > gpurun_out/${TAG}_ncu.log 2>&1
 python tools/ncu_summary.py /tmp/${TAG}_prof.ncu-rep > gpurun_out/${TAG}_ncu_summary.txt 2>&1
 ncu -i /tmp/${TAG}_prof.ncu-rep --page source --csv > gpurun_out/${TAG}_source.csv 2>/dev/null
 ncu -i /tmp/${TAG}_prof.ncu-rep --page raw --csv 2>/dev/null | python -c "
