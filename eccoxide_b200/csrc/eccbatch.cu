@@ -50,9 +50,9 @@ int ecb_init(const int* device_ids, int n_dev, ecb_ctx** out) {
                  cudaStreamCreateWithPriority(&sl.hi, cudaStreamNonBlocking, hi_p) == cudaSuccess &&
                  cudaEventCreateWithFlags(&sl.ev_a, cudaEventDisableTiming) == cudaSuccess &&
                  cudaEventCreateWithFlags(&sl.ev_b, cudaEventDisableTiming) == cudaSuccess &&
-                 cudaMalloc(&sl.d_status, sizeof(unsigned long long)) == cudaSuccess &&
+                 cudaMalloc(&sl.d_status, 2 * sizeof(unsigned long long)) == cudaSuccess &&
                  cudaMallocHost(&sl.h_status, sizeof(unsigned long long)) == cudaSuccess &&
-                 cudaMemset(sl.d_status, 0xff, sizeof(unsigned long long)) == cudaSuccess;
+                 cudaMemset(sl.d_status, 0xff, 2 * sizeof(unsigned long long)) == cudaSuccess;
         }
         if (!ok) {
             ecb_destroy(ctx);

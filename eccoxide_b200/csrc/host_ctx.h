@@ -155,8 +155,10 @@ static inline unsigned persistent_grid(const DevCtx& d, K kernel, size_t n) {
     return (unsigned)(g ? g : 1);
 }
 
+// d_status[0]: the per-batch status word (~0 = no error); d_status[1]: the work counter of the persistent kernels
+// (tu_common.cuh warp_next_chunk), which starts at ~0 = "-1" so that ONE memset arms both
 static inline int reset_status(ecb_ctx* ctx, DevCtx& d, cudaStream_t s) {
-    CU(cudaMemsetAsync(d.cur->d_status, 0xff, sizeof(unsigned long long), s));
+    CU(cudaMemsetAsync(d.cur->d_status, 0xff, 2 * sizeof(unsigned long long), s));
     return ECB_OK;
 }
 

@@ -35,16 +35,22 @@ static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_table_points(size_t 
 }
 static __global__ void __launch_bounds__(ECB_TPB) k_ed25519_mul(size_t n, const u32* scalars, const u32* points, u32* scratch,
                                                           u32* planes, unsigned long long* status) {
-    size_t T = (size_t)gridDim.x * ECB_TPB, t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+    size_t t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
     u32* tbl = scratch + t * (8 * 32);
-    for (size_t idx = t; idx < n; idx += T) ed25519_mul_body(idx, n, scalars, points, tbl, planes, status);
+    for (size_t base = warp_next_chunk(status); base < n; base = warp_next_chunk(status)) {
+        const size_t idx = base + (threadIdx.x & 31u);
+        if (idx < n) ed25519_mul_body(idx, n, scalars, points, tbl, planes, status);
+    }
 }
 static __global__ void __launch_bounds__(ECB_TPB, 3) k_ed25519_verify(size_t n, const u32* a_enc, const u32* s_le, const u32* k_le,
                                                              const u32* table, int W, int nwin, int stride, u32* scratch, u32* planes,
-                                                             unsigned char* ok) {
-    size_t T = (size_t)gridDim.x * ECB_TPB, t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
+                                                             unsigned char* ok, unsigned long long* status) {
+    size_t t = (size_t)blockIdx.x * ECB_TPB + threadIdx.x;
     u32* tbl = scratch + t * (8 * 32);
-    for (size_t idx = t; idx < n; idx += T) ed25519_verify_body(idx, n, a_enc, s_le, k_le, table, W, nwin, stride, tbl, planes, ok);
+    for (size_t base = warp_next_chunk(status); base < n; base = warp_next_chunk(status)) {
+        const size_t idx = base + (threadIdx.x & 31u);
+        if (idx < n) ed25519_verify_body(idx, n, a_enc, s_le, k_le, table, W, nwin, stride, tbl, planes, ok);
+    }
 }
 
 // comb width actually used on this device: the option, or (option 0) the widest whose table and
@@ -372,7 +378,7 @@ int dev_ed25519_verify(ecb_ctx* ctx, DevCtx& d, const u32* a, const u32* r, cons
     TRY(reset_status(ctx, d, s));
     u32* planes = (u32*)d.cur->planes.p;
     prof_mark(ctx, d, s, 0);
-    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, (u32*)d.cur->scratch.p, planes, ok);
+    k_ed25519_verify<<<g, ECB_TPB, 0, s>>>(n, a, sl, kl, d.ed_table, d.ed_w, d.ed_nwin, d.ed_stride, (u32*)d.cur->scratch.p, planes, ok, d.cur->d_status);
     ctx->launches++;
     CU(cudaGetLastError());
     prof_mark(ctx, d, s, 1);
