@@ -247,9 +247,11 @@ static __global__ void __launch_bounds__(ECB_TPB, 4) k_ed25519_mul_base_ct(size_
     for (int i = threadIdx.x; i < ECB_CT_ED_WORDS / 4; i += ECB_TPB)
         reinterpret_cast<uint4*>(tbl)[i] = reinterpret_cast<const uint4*>(table)[i];
     __syncthreads();
-    const size_t T = (size_t)gridDim.x * ECB_TPB;
-    for (size_t idx = (size_t)blockIdx.x * ECB_TPB + threadIdx.x; idx < n; idx += T)
-        ed25519_mul_base_ct_body<false>(idx, n, scalars, tbl, planes, status);
+    // the order in which warps take their chunks depends on the progress of other warps, never on a scalar
+    for (size_t base = warp_next_chunk(status); base < n; base = warp_next_chunk(status)) {
+        const size_t idx = base + (threadIdx.x & 31u);
+        if (idx < n) ed25519_mul_base_ct_body<false>(idx, n, scalars, tbl, planes, status);
+    }
 }
 static int dev_ed25519_ct_table(ecb_ctx* ctx, DevCtx& d) {
     if (d.ed_ct_table) return ECB_OK;
