@@ -264,8 +264,8 @@ struct FinX448 {
 //   prep : decode r || s (Signature::from_bytes :399 — zero or >= n is invalid), s -> Montgomery
 //          form in GF(n) into the "Z" plane of `sp` for the scalar-field batch inversion
 //   inv  : batch_inv_body<FN> + FinScalarInv  -> s^-1 (Montgomery) in plane 0 of `sp`
-//   main : u1 = z s^-1, u2 = r s^-1, R = u1*G + u2*Q (Straus, signed 4-bit windows, shared
-//          doublings, complete formulas), projective result to the point planes
+//   main : u1 = z s^-1, u2 = r s^-1, R = u2*Q (signed windows of C::WIN bits over a per-thread table, Jacobian) +
+//          u1*G (generator comb, no doublings), one general addition; Jacobian result to the point planes
 //   fin  : x = X/Z by batch inversion in GF(p); accept iff Z != 0 and x mod n == r
 // =======================================================================================
 // z = digest_to_scalar(H(message)) before the reduction mod n (src/protocol/ecdsa.rs:288 hash_to_scalar,

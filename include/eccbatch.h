@@ -196,7 +196,9 @@ int ecb_wei_mul_base(ecb_ctx* ctx, int curve_id, const uint8_t* k_be, size_t n, 
                      size_t* bad_index);
 /* Multi-scalar multiplication: sum_i k_i * P_i -> to_affine (the reference lists it as a wish, TODO.md:48, :99-100; the
  * value is what folding its own `&P * &k` (projective.rs:842) with `+` (:268) over the batch gives).  Bucket method
- * (csrc/msm.cuh): signed windows of up to 16 bits, counting sort of the digits, one thread per bucket.  curve_id:
+ * (csrc/msm.cuh): signed windows of up to 16 bits, counting sort of the digits, bucket sums balanced over equal
+ * segments of the sorted array (the running time does not depend on how the digits are distributed), running sums
+ * over the buckets.  curve_id:
  * ECB_CURVE_BLS12_381_G1 or ECB_CURVE_P256K1.  k_be: n x SB canonical scalars; xy_be: n x 2FB affine points on the curve
  * (any subgroup); out_xy_be: 2FB bytes (zeros for the identity), out_inf: 1 byte.  n == 0 gives the identity.  The
  * batch is sliced over the devices of the context; each reduces its slice and the partial sums are added on the
