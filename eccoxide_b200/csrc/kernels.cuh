@@ -627,6 +627,34 @@ ECB_DEV void wei_build_table(u32* tbl, const typename C::F::el& x, const typenam
     }
 }
 
+// acc = k * P over the table of multiples at tbl: signed windows of C::WIN bits, most significant first
+template <class C, bool LZ>
+ECB_DEV void wei_window_loop(typename WeiJ<C>::pt& acc, const u32* k, const u32* tbl, typename C::F::lazy& z) {
+    typedef WeiJ<C> J;
+    constexpr int N = C::F::N;
+    constexpr int NS = C::SB / 4;
+    constexpr int ES = 5 * N;
+    constexpr int WIN = C::WIN;
+    constexpr int NWIN = (C::SBITS + 1 + WIN - 1) / WIN;
+    J::set_inf(acc);
+    ECB_NOUNROLL
+    for (int i = NWIN - 1; i >= 0; i--) {
+        if (i != NWIN - 1) {
+            ECB_NOUNROLL
+            for (int r = 0; r < WIN; r++) J::template dbl_z<LZ>(acc, acc, z);
+        }
+        u32 neg;
+        u32 d = booth_digit(k, NS + 1, WIN, i, neg);
+        if (d != 0) J::add_mem(acc, acc, tbl + (d - 1) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
+    }
+}
+template <class C>
+ECB_DEVNI typename WeiJ<C>::pt wei_window_loop_checked(const u32* k, const u32* tbl) {
+    typename WeiJ<C>::pt acc;
+    typename C::F::lazy z;
+    wei_window_loop<C, false>(acc, k, tbl, z);
+    return acc;
+}
 template <class C>
 ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* points, const unsigned char* inf_in,
                           u32* tbl, u32* planes, unsigned long long* status) {
@@ -663,18 +691,11 @@ ECB_DEV void wei_mul_body(size_t idx, size_t n, const u32* scalars, const u32* p
     J::set_inf(acc);
     if (ok && !is_inf) {
         wei_build_table<C>(tbl, px, py);
-        constexpr int WIN = C::WIN;
-        constexpr int NWIN = (C::SBITS + 1 + WIN - 1) / WIN;
-        ECB_NOUNROLL
-        for (int i = NWIN - 1; i >= 0; i--) {
-            if (i != NWIN - 1) {
-                ECB_NOUNROLL
-                for (int r = 0; r < WIN; r++) J::dbl(acc, acc);
-            }
-            u32 neg;
-            u32 d = booth_digit(k, NS + 1, WIN, i, neg);
-            if (d != 0) J::add_mem(acc, acc, tbl + (d - 1) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
-        }
+        // the doublings run on the lazy field forms (mont.cuh): a fold that carries again is only counted, and the whole
+        // window loop is then redone with the checked forms — about one element in 2^20 on the loose fields
+        typename FT::lazy z;
+        wei_window_loop<C, FT::LOOSE>(acc, k, tbl, z);
+        if (z.any()) acc = wei_window_loop_checked<C>(k, tbl);
     }
     plane_st<N>(planes + 0 * (size_t)N * n, n, idx, acc.X.v);
     plane_st<N>(planes + 1 * (size_t)N * n, n, idx, acc.Y.v);

@@ -368,18 +368,10 @@ ECB_DEV void ecdsa_main_body(size_t idx, size_t n, const u32* q_be, const u32* z
         u2[NS] = 0;
         // u2*Q: signed windows of C::WIN bits over tbl[0..2^(WIN-1)) = j*Q (Jacobian, cached Z powers)
         wei_build_table<C>(tbl, qx, qy);
-        constexpr int WIN = C::WIN;
-        constexpr int NWIN = (C::SBITS + 1 + WIN - 1) / WIN;
-        ECB_NOUNROLL
-        for (int i = NWIN - 1; i >= 0; i--) {
-            if (i != NWIN - 1) {
-                ECB_NOUNROLL
-                for (int r = 0; r < WIN; r++) J::dbl(acc, acc);
-            }
-            u32 neg;
-            u32 d = booth_digit(u2, NS + 1, WIN, i, neg);
-            // skipping a zero digit: verification is variable time like mul_vartime
-            if (d != 0) J::add_mem(acc, acc, tbl + (d - 1) * ES, neg, [](u32* dst, const u32* src) { ld_words_rw<N>(dst, src); });
+        {   // lazy doublings, redone with the checked forms if a fold carried again (kernels.cuh wei_window_loop)
+            typename FT::lazy z;
+            wei_window_loop<C, FT::LOOSE>(acc, u2, tbl, z);
+            if (z.any()) acc = wei_window_loop_checked<C>(u2, tbl);
         }
         // u1*G from the generator comb (Point::mul_base), then one general addition
         typename J::pt accg;

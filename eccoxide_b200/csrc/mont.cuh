@@ -115,7 +115,8 @@ struct Mont {
         fold_carry(r, T + 8, T[16]);
     }
     // r = t + c * (2^256 - p) mod 2^256 for c in {0, 1};  2^256 - p = 2^224 - 2^192 - 2^96 + 1
-    ECB_DEV static u32 fold_carry(el& r, const u32* t, u32 c) {
+    // acc (optional): the lazy forms below pass a counter; the carry is then ADDED to it instead of being returned alone
+    ECB_DEV static u32 fold_carry(el& r, const u32* t, u32 c, const u32* acc = nullptr) {
         const u32 m = 0u - c;
         if constexpr (MontKind<P>::kind == 3) {
             // 2^256 - p = 2^32 + 977 = limbs {977, 1, 0, ...}; valid for any small c (977 c < 2^32)
@@ -123,7 +124,7 @@ struct Mont {
             r.v[1] = addc_cc(t[1], c);
             ECB_UNROLL
             for (int i = 2; i < N; i++) r.v[i] = addc_cc(t[i], 0u);
-            return addc(0u, 0u);
+            return acc ? addc(*acc, 0u) : addc(0u, 0u);
         }
         if constexpr (MontKind<P>::kind == 2) {
             // 2^384 - p = 2^128 + 2^96 - 2^32 + 1 = limbs {1, ffffffff, ffffffff, 0, 1, 0, ...}
@@ -134,7 +135,7 @@ struct Mont {
             r.v[4] = addc_cc(t[4], c);
             ECB_UNROLL
             for (int i = 5; i < N; i++) r.v[i] = addc_cc(t[i], 0u);
-            return addc(0u, 0u);
+            return acc ? addc(*acc, 0u) : addc(0u, 0u);
         }
         r.v[0] = add_cc(t[0], c);
         r.v[1] = addc_cc(t[1], 0u);
@@ -144,17 +145,17 @@ struct Mont {
         r.v[5] = addc_cc(t[5], m);
         r.v[6] = addc_cc(t[6], m << 1);
         r.v[7] = addc_cc(t[7], 0u);
-        return addc(0u, 0u);
+        return acc ? addc(*acc, 0u) : addc(0u, 0u);
     }
     // r = t - c * (2^256 - p) mod 2^256 ; returns the borrow
-    ECB_DEV static u32 fold_borrow(el& r, const u32* t, u32 c) {
+    ECB_DEV static u32 fold_borrow(el& r, const u32* t, u32 c, const u32* acc = nullptr) {
         const u32 m = 0u - c;
         if constexpr (MontKind<P>::kind == 3) {
             r.v[0] = sub_cc(t[0], 977u * c);
             r.v[1] = subc_cc(t[1], c);
             ECB_UNROLL
             for (int i = 2; i < N; i++) r.v[i] = subc_cc(t[i], 0u);
-            return 0u - subc(0u, 0u);
+            return acc ? subc(*acc, 0u) : 0u - subc(0u, 0u);
         }
         if constexpr (MontKind<P>::kind == 2) {
             r.v[0] = sub_cc(t[0], c);
@@ -164,7 +165,7 @@ struct Mont {
             r.v[4] = subc_cc(t[4], c);
             ECB_UNROLL
             for (int i = 5; i < N; i++) r.v[i] = subc_cc(t[i], 0u);
-            return 0u - subc(0u, 0u);   // 0 or 1; written so that its range stays unknown to the compiler (refold_borrow must remain a loop)
+            return acc ? subc(*acc, 0u) : 0u - subc(0u, 0u);   // 0 or 1, written so that its range stays unknown to the compiler (refold_borrow must remain a loop); lazy: the counter runs DOWN
         }
         r.v[0] = sub_cc(t[0], c);
         r.v[1] = subc_cc(t[1], 0u);
@@ -174,15 +175,15 @@ struct Mont {
         r.v[5] = subc_cc(t[5], m);
         r.v[6] = subc_cc(t[6], m << 1);
         r.v[7] = subc_cc(t[7], 0u);
-        return 0u - subc(0u, 0u);   // 0 or 1; written so that its range stays unknown to the compiler (refold_borrow must remain a loop)
+        return acc ? subc(*acc, 0u) : 0u - subc(0u, 0u);   // 0 or 1, written so that its range stays unknown to the compiler (refold_borrow must remain a loop); lazy: the counter runs DOWN
     }
 
     // ---- loose representation, small multiples.  r = t + c (2^(32N) - p) mod 2^(32N) for a small c (0 <= c < 2^16),
     // returns the carry out.  The limbs of c (2^256 - p) = c 2^224 - c 2^192 - c 2^96 + c are
     // {c, 0, 0, -c, ~0, ~0, ~c, c - 1} for c >= 1 (all zero for c = 0); of c (2^384 - p) = c 2^128 + c 2^96 - c 2^32 + c:
     // {c, -c, ~0, c - 1, c, 0, ...}.
-    ECB_DEV static u32 fold_carry_small(el& r, const u32* t, u32 c) {
-        if constexpr (MontKind<P>::kind == 3) return fold_carry(r, t, c);
+    ECB_DEV static u32 fold_carry_small(el& r, const u32* t, u32 c, const u32* acc = nullptr) {
+        if constexpr (MontKind<P>::kind == 3) return fold_carry(r, t, c, acc);
         const u32 nz = 0u - (u32)(c != 0u);
         if constexpr (MontKind<P>::kind == 2) {
             r.v[0] = add_cc(t[0], c);
@@ -192,7 +193,7 @@ struct Mont {
             r.v[4] = addc_cc(t[4], c);
             ECB_UNROLL
             for (int i = 5; i < N; i++) r.v[i] = addc_cc(t[i], 0u);
-            return addc(0u, 0u);
+            return acc ? addc(*acc, 0u) : addc(0u, 0u);
         }
         r.v[0] = add_cc(t[0], c);
         r.v[1] = addc_cc(t[1], 0u);
@@ -202,11 +203,11 @@ struct Mont {
         r.v[5] = addc_cc(t[5], nz);
         r.v[6] = addc_cc(t[6], ~c & nz);
         r.v[7] = addc_cc(t[7], (c - 1u) & nz);
-        return addc(0u, 0u);
+        return acc ? addc(*acc, 0u) : addc(0u, 0u);
     }
     // r = t - c (2^(32N) - p) mod 2^(32N), returns the borrow
-    ECB_DEV static u32 fold_borrow_small(el& r, const u32* t, u32 c) {
-        if constexpr (MontKind<P>::kind == 3) return fold_borrow(r, t, c);
+    ECB_DEV static u32 fold_borrow_small(el& r, const u32* t, u32 c, const u32* acc = nullptr) {
+        if constexpr (MontKind<P>::kind == 3) return fold_borrow(r, t, c, acc);
         const u32 nz = 0u - (u32)(c != 0u);
         if constexpr (MontKind<P>::kind == 2) {
             r.v[0] = sub_cc(t[0], c);
@@ -216,7 +217,7 @@ struct Mont {
             r.v[4] = subc_cc(t[4], c);
             ECB_UNROLL
             for (int i = 5; i < N; i++) r.v[i] = subc_cc(t[i], 0u);
-            return 0u - subc(0u, 0u);   // 0 or 1; written so that its range stays unknown to the compiler (refold_borrow must remain a loop)
+            return acc ? subc(*acc, 0u) : 0u - subc(0u, 0u);   // 0 or 1, written so that its range stays unknown to the compiler (refold_borrow must remain a loop); lazy: the counter runs DOWN
         }
         r.v[0] = sub_cc(t[0], c);
         r.v[1] = subc_cc(t[1], 0u);
@@ -226,7 +227,7 @@ struct Mont {
         r.v[5] = subc_cc(t[5], nz);
         r.v[6] = subc_cc(t[6], ~c & nz);
         r.v[7] = subc_cc(t[7], (c - 1u) & nz);
-        return 0u - subc(0u, 0u);   // 0 or 1; written so that its range stays unknown to the compiler (refold_borrow must remain a loop)
+        return acc ? subc(*acc, 0u) : 0u - subc(0u, 0u);   // 0 or 1, written so that its range stays unknown to the compiler (refold_borrow must remain a loop); lazy: the counter runs DOWN
     }
     // The fold itself can carry once more (t within c 2^224 of 2^(32N)): about one operand pair in 2^32.  The repeat
     // is a LOOP so that the assembler keeps it a branch: written as `if`, it becomes eight predicated instructions
@@ -612,6 +613,68 @@ struct Mont {
         sub(d, a, b);
         sub(d, d, c);
         sub(r, d, c);
+    }
+
+    // ---- lazy forms for the doubling (weier.cuh WeiJ::dbl).  On the loose fields the carry out of a fold — the once-in-2^32
+    // event that add / sub answer with a second fold — is only COUNTED here (one instruction); the caller looks at the
+    // counters once per doubling and, if any is set, recomputes the doubling with the checked forms.  That removes a
+    // compare, a branch and a reconvergence point from every field addition.  LZ = false, or a canonical field: the
+    // checked forms.
+    struct lazy {
+        u32 c = 0, b = 0;   // carries counted up, borrows counted down
+        ECB_DEV bool any() const { return (c | b) != 0u; }
+    };
+    template <bool LZ>
+    ECB_DEV static void add_z(el& r, const el& a, const el& b, lazy& z) {
+        if constexpr (LZ && LOOSE) {
+            u32 t[N];
+            u32 c = add_n<N>(t, a.v, b.v);
+            z.c = fold_carry(r, t, c, &z.c);
+            return;
+        }
+        add(r, a, b);
+    }
+    template <bool LZ>
+    ECB_DEV static void sub_z(el& r, const el& a, const el& b, lazy& z) {
+        if constexpr (LZ && LOOSE) {
+            u32 t[N];
+            u32 bw = sub_n<N>(t, a.v, b.v);
+            z.b = fold_borrow(r, t, bw, &z.b);
+            return;
+        }
+        sub(r, a, b);
+    }
+    template <int K, bool LZ>
+    ECB_DEV static void mul_small_z(el& r, const el& a, lazy& z) {
+        if constexpr (LZ && LOOSE) {
+            if constexpr (K == 2) { add_z<true>(r, a, a, z); return; }
+            constexpr int S = (K == 8) ? 3 : (K == 4) ? 2 : 1;
+            u32 t[N];
+            u32 c = a.v[N - 1] >> (32 - S);
+            ECB_UNROLL
+            for (int i = N - 1; i > 0; i--) t[i] = shl_word(a.v[i - 1], a.v[i], S);
+            t[0] = a.v[0] << S;
+            if constexpr (K == 3) {
+                t[0] = add_cc(t[0], a.v[0]);
+                ECB_UNROLL
+                for (int i = 1; i < N; i++) t[i] = addc_cc(t[i], a.v[i]);
+                c += addc(0u, 0u);
+            }
+            z.c = fold_carry_small(r, t, c, &z.c);
+            return;
+        }
+        mul_small<K>(r, a);
+    }
+    template <bool LZ>
+    ECB_DEV static void sub2_z(el& r, const el& a, const el& b, const el& c, lazy& z) {
+        if constexpr (LZ && LOOSE) {
+            u32 t[N];
+            u32 bw = sub_n<N>(t, a.v, b.v);
+            bw += sub_n<N>(t, t, c.v);
+            z.b = fold_borrow_small(r, t, bw, &z.b);
+            return;
+        }
+        sub2(r, a, b, c);
     }
 
     ECB_DEV static u32 is_zero(const el& a) {

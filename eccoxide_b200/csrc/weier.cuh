@@ -160,27 +160,29 @@ struct WeiJ {
     ECB_DEV static u32 is_inf(const pt& p) { return F::is_zero(p.Z); }
 
     // dbl-2001-b (a = -3): 3M + 5S ; dbl-2009-l (a = 0): 2M + 5S.  Z = 0 stays Z = 0.
-    ECB_DEV static void dbl(pt& r, const pt& p) {
+    // LZ: the field additions only COUNT a carry out of their fold (mont.cuh lazy forms); dbl() checks the counters once.
+    template <bool LZ>
+    ECB_DEV static void dbl_impl(pt& r, const pt& p, typename F::lazy& z) {
         if (C::A_M3) {
             fe delta, gamma, beta, alpha, t0, t1, X3, Y3, Z3;
             F::sqr_ni(delta, p.Z);
             F::sqr_ni(gamma, p.Y);
             F::mul_ni(beta, p.X, gamma);
-            F::sub(t0, p.X, delta);
-            F::add(t1, p.X, delta);
+            F::template sub_z<LZ>(t0, p.X, delta, z);
+            F::template add_z<LZ>(t1, p.X, delta, z);
             F::mul_ni(t0, t0, t1);
-            F::template mul_small<3>(alpha, t0);   // 3 (X - delta)(X + delta)
-            F::add(t1, p.Y, p.Z);
+            F::template mul_small_z<3, LZ>(alpha, t0, z);   // 3 (X - delta)(X + delta)
+            F::template add_z<LZ>(t1, p.Y, p.Z, z);
             F::sqr_ni(Z3, t1);
-            F::sub2(Z3, Z3, gamma, delta);         // (Y + Z)^2 - gamma - delta
+            F::template sub2_z<LZ>(Z3, Z3, gamma, delta, z);   // (Y + Z)^2 - gamma - delta
             F::sqr_ni(X3, alpha);
-            F::template mul_small<4>(t0, beta);    // 4 beta
-            F::sub2(X3, X3, t0, t0);               // alpha^2 - 8 beta
-            F::sub(t0, t0, X3);
+            F::template mul_small_z<4, LZ>(t0, beta, z);    // 4 beta
+            F::template sub2_z<LZ>(X3, X3, t0, t0, z);      // alpha^2 - 8 beta
+            F::template sub_z<LZ>(t0, t0, X3, z);
             F::mul_ni(Y3, alpha, t0);
             F::sqr_ni(t1, gamma);
-            F::template mul_small<8>(t1, t1);      // 8 gamma^2
-            F::sub(Y3, Y3, t1);
+            F::template mul_small_z<8, LZ>(t1, t1, z);      // 8 gamma^2
+            F::template sub_z<LZ>(Y3, Y3, t1, z);
             F::copy(r.X, X3);
             F::copy(r.Y, Y3);
             F::copy(r.Z, Z3);
@@ -189,24 +191,31 @@ struct WeiJ {
             F::sqr_ni(A, p.X);
             F::sqr_ni(B, p.Y);
             F::sqr_ni(Cc, B);
-            F::add(t, p.X, B);
+            F::template add_z<LZ>(t, p.X, B, z);
             F::sqr_ni(D, t);
-            F::sub2(D, D, A, Cc);
-            F::dbl(D, D);               // 2((X + B)^2 - A - C)
-            F::template mul_small<3>(E, A);   // 3A
+            F::template sub2_z<LZ>(D, D, A, Cc, z);
+            F::template mul_small_z<2, LZ>(D, D, z);        // 2((X + B)^2 - A - C)
+            F::template mul_small_z<3, LZ>(E, A, z);        // 3A
             F::sqr_ni(Fv, E);
-            F::sub2(X3, Fv, D, D);      // F - 2D
+            F::template sub2_z<LZ>(X3, Fv, D, D, z);        // F - 2D
             F::mul_ni(Z3, p.Y, p.Z);
-            F::dbl(Z3, Z3);
-            F::sub(t, D, X3);
+            F::template mul_small_z<2, LZ>(Z3, Z3, z);
+            F::template sub_z<LZ>(t, D, X3, z);
             F::mul_ni(Y3, E, t);
-            F::template mul_small<8>(Cc, Cc);   // 8C
-            F::sub(Y3, Y3, Cc);
+            F::template mul_small_z<8, LZ>(Cc, Cc, z);      // 8C
+            F::template sub_z<LZ>(Y3, Y3, Cc, z);
             F::copy(r.X, X3);
             F::copy(r.Y, Y3);
             F::copy(r.Z, Z3);
         }
     }
+    ECB_DEV static void dbl(pt& r, const pt& p) {   // every fold checked
+        typename F::lazy z;
+        dbl_impl<false>(r, p, z);
+    }
+    // LZ = true: folds only counted in z — the CALLER must look at z.any() and redo its work with LZ = false if set
+    template <bool LZ>
+    ECB_DEV static void dbl_z(pt& r, const pt& p, typename F::lazy& z) { dbl_impl<LZ>(r, p, z); }
     ECB_DEV static void to_cached(cached& c, const pt& p) {
         F::copy(c.X, p.X);
         F::copy(c.Y, p.Y);

@@ -140,6 +140,38 @@ extern "C" unsigned long long hs_wei_mul(int curve, const u32* k, const u32* pts
     return 0;
 }
 
+// Jacobian doubling on arbitrary (loose) coordinate words: which = 0: dbl() (every fold checked); 1: dbl_z<false> (the same);
+// 2: dbl_z<true>, the lazy form, returning its carry / borrow counters (nonzero = the result must be discarded and redone)
+template <class C>
+static unsigned wei_dbl_run(const u32* in, u32* out, int which) {
+    typedef WeiJ<C> J;
+    constexpr int N = C::F::N;
+    typename J::pt p, r;
+    memcpy(p.X.v, in, 4 * N); memcpy(p.Y.v, in + N, 4 * N); memcpy(p.Z.v, in + 2 * N, 4 * N);
+    unsigned flags = 0;
+    if (which == 0) J::dbl(r, p);
+    else if (which == 1) {
+        typename C::F::lazy z;
+        J::template dbl_z<false>(r, p, z);
+        flags = z.c | z.b;   // the checked forms never count
+    } else {
+        typename C::F::lazy z;
+        J::template dbl_impl<true>(r, p, z);
+        flags = z.c | z.b;
+    }
+    memcpy(out, r.X.v, 4 * N); memcpy(out + N, r.Y.v, 4 * N); memcpy(out + 2 * N, r.Z.v, 4 * N);
+    return flags;
+}
+extern "C" unsigned hs_wei_dbl(int curve, const u32* in, u32* out, int which) {
+    switch (curve) {
+        case 0: return wei_dbl_run<CurveP256>(in, out, which);
+        case 1: return wei_dbl_run<CurveP384>(in, out, which);
+        case 2: return wei_dbl_run<CurveBLSG1>(in, out, which);
+        case 3: return wei_dbl_run<CurveK256>(in, out, which);
+    }
+    return 0;
+}
+
 // ---- kernels2: X448, ECDSA verify, Ed25519 verify ------------------------------------------
 #include "../../eccoxide_b200/csrc/kernels2.cuh"
 extern "C" {

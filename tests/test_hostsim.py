@@ -23,6 +23,7 @@ def hs():
     k = ctypes.CDLL(os.path.join(HS, "_build", "hostsim_kernels.so"))
     for fn in ("hs_ed25519_mul_base", "hs_ed25519_mul_base_ct", "hs_ed25519_mul_base_lanes", "hs_ed25519_mul", "hs_wei_mul", "hs_wei_mul_base", "hs_wei_mul_base_ct", "hs_wei_msm", "hs_wei_msm2", "hs_ecdsa_verify", "hs_bls_g1_mul_glv"):
         getattr(k, fn).restype = ctypes.c_ulonglong
+    k.hs_wei_dbl.restype = ctypes.c_uint
     return f, k
 
 
@@ -215,6 +216,65 @@ def test_ed25519_mul_x25519_x448(hs, coracle):
     o = np.zeros((n, 56), dtype=np.uint8)
     k.hs_x448(p(ks), p(us), ctypes.c_size_t(n), p(o))
     assert np.array_equal(o, coracle.x448(ks, us))
+
+
+@pytest.mark.parametrize("cid,curve,n,am3", [(0, "p256r1", 8, True), (1, "p384r1", 12, True), (2, "bls12_381_g1", 12, False), (3, "p256k1", 8, False)])
+def test_wei_doubling_lazy_folds(hs, cid, curve, n, am3):
+    """WeiJ::dbl_z<true> (weier.cuh): the field additions of a doubling only COUNT a carry out of their fold; the window
+    loop (kernels.cuh wei_window_loop) is redone with the checked forms if any counter is set at its end.  The formulas are
+    polynomial maps, so ANY coordinate words are valid inputs: random ones, and loose representatives at the top of the
+    range, where folds do carry.  The checked forms (dbl, dbl_z<false>) and the lazy one are compared with the formulas
+    evaluated on big integers: the lazy form must be right whenever its counters are zero, the cases must include some
+    where they are not, and the checked forms never count."""
+    _, k = hs
+    c = R.WCURVES[curve]
+    p_ = c.p
+    Rm = 1 << (32 * n)
+    loose = cid in (0, 1, 3)
+    Rd = 1 if cid == 3 else Rm                     # domain radix: products are a b / Rd
+    Ri = pow(Rd, -1, p_)
+    g = rng(930 + cid)
+
+    def expect(X, Y, Z):
+        m = lambda a, b: a * b * Ri % p_           # the field product in the domain
+        if am3:
+            delta, gamma = m(Z, Z), m(Y, Y)
+            beta = m(X, gamma)
+            alpha = 3 * m(X - delta, X + delta)
+            Z3 = m(Y + Z, Y + Z) - gamma - delta
+            X3 = m(alpha, alpha) - 8 * beta
+            Y3 = m(alpha, 4 * beta - X3) - 8 * m(gamma, gamma)
+        else:
+            A, B = m(X, X), m(Y, Y)
+            Cc = m(B, B)
+            D = 2 * (m(X + B, X + B) - A - Cc)
+            E = 3 * A
+            X3 = m(E, E) - 2 * D
+            Z3 = 2 * m(Y, Z)
+            Y3 = m(E, D - X3) - 8 * Cc
+        return X3 % p_, Y3 % p_, Z3 % p_
+
+    top = Rm if loose else p_
+    K = Rm - p_
+    edge = [top - 1, top - 2, 0, 1, p_ - 1, (top - K) % top, (top - K - 1) % top, (top - 2 * K) % top, top >> 1, (top >> 1) + 1, top - (top >> 3), (top >> 2) + 5]
+    cases = [(a, b, d) for a in edge[:8] for b in edge[:6] for d in edge[:6]]
+    cases += [tuple(edge[int(g.integers(0, len(edge)))] for _ in range(3)) for _ in range(300)]
+    cases += [tuple(int.from_bytes(g.bytes(4 * n), "little") % top for _ in range(3)) for _ in range(300)]
+    out = np.zeros(3 * n, dtype=np.uint32)
+    flagged = 0
+    for X, Y, Z in cases:
+        inp = np.concatenate([words(X, n), words(Y, n), words(Z, n)])
+        want = expect(X, Y, Z)
+        for which in (0, 1, 2):
+            fl = k.hs_wei_dbl(cid, p(inp), p(out), which)
+            got = tuple(val(out[i * n:(i + 1) * n]) for i in range(3))
+            if which == 2 and fl:
+                flagged += 1
+                continue
+            assert which == 2 or fl == 0
+            assert all(v < top for v in got), (which, hex(X), hex(Y), hex(Z))
+            assert tuple(v % p_ for v in got) == want, (which, hex(X), hex(Y), hex(Z))
+    assert (flagged > 0) == loose, flagged
 
 
 @pytest.mark.parametrize("cid,curve", [(0, "p256r1"), (1, "p384r1"), (2, "bls12_381_g1"), (3, "p256k1")])
