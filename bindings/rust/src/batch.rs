@@ -6,11 +6,12 @@
 use super::ffi::*;
 use crate::curve::curve25519::{FieldElement as Fe25519, Point as EdPoint, Scalar as EdScalar};
 use crate::curve::bls12_381::g1;
+use crate::curve::bls12_381::scalar::Scalar as BlsScalar;
 use crate::curve::field::Sign;
 use crate::curve::sec2::p256r1;
 use crate::protocol::ecdsa;
 use std::ffi::CStr;
-use std::os::raw::c_int;
+use std::os::raw::{c_char, c_int, c_long};
 use std::ptr;
 
 #[derive(Debug)]
@@ -198,6 +199,38 @@ impl BatchContext {
             .chunks_exact(96)
             .zip(ok)
             .map(|(c, present)| if present == 0 { None } else { g1::PointAffine::from_uncompressed_oncurve_only(c.try_into().unwrap()) })
+            .collect())
+    }
+
+    /// Batch sibling of `&g1::Point * &Scalar` on BLS12-381 G1 (src/curve/fiat/curve_macros.rs:321 ->
+    /// projective.rs:842).  `in_subgroup = false` is `Point::mul` as the crate defines it: any point of E(Fp).
+    /// `in_subgroup = true` is for points the caller KNOWS to be in the prime-order subgroup — everything that came
+    /// out of `g1_from_compressed_batch(.., true)` or of `mul_base` — and lets the device split the scalar over the
+    /// endomorphism of the crate's own subgroup test (g1.rs:105): the same group element for those points, 1.35x
+    /// faster; for a point outside G1 the result would NOT be `k * P`.  The option is scoped to this call.
+    pub fn g1_mul_batch(&self, points: &[g1::PointAffine], scalars: &[BlsScalar], in_subgroup: bool) -> Result<Vec<Option<g1::PointAffine>>, BatchError> {
+        if points.len() != scalars.len() {
+            return Err(BatchError::InvalidArgument("length mismatch".into()));
+        }
+        let n = points.len();
+        let (mut k, mut xy) = (Vec::with_capacity(32 * n), Vec::with_capacity(96 * n));
+        for (p, s) in points.iter().zip(scalars) {
+            k.extend_from_slice(&s.to_bytes());
+            xy.extend_from_slice(&p.to_uncompressed()); // x || y, 48 bytes each, big-endian (serialize.rs:269)
+        }
+        let (mut out, mut inf, mut bad) = (vec![0u8; 96 * n], vec![0u8; n], usize::MAX);
+        let key = b"bls12_381_g1_glv\0".as_ptr() as *const c_char;
+        let rc = unsafe {
+            ecb_set_option(self.ctx, key, in_subgroup as c_long);
+            let rc = ecb_wei_mul(self.ctx, ECB_CURVE_BLS12_381_G1, k.as_ptr(), xy.as_ptr(), ptr::null(), n, out.as_mut_ptr(), inf.as_mut_ptr(), &mut bad);
+            ecb_set_option(self.ctx, key, 0);
+            rc
+        };
+        self.check(rc, bad)?;
+        Ok(out
+            .chunks_exact(96)
+            .zip(inf)
+            .map(|(c, i)| if i != 0 { None } else { g1::PointAffine::from_uncompressed_oncurve_only(c.try_into().unwrap()) })
             .collect())
     }
 
