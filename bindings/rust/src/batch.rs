@@ -124,7 +124,7 @@ impl BatchContext {
     }
 
     /// Batch sibling of `ed25519::SecretKey::sign` (src/protocol/ed25519.rs:112) on raw messages.
-    /// NOT constant-time on the device.
+    /// Constant-time kernels on the device; `ecb_ed25519_sign_vartime` is the fast form.
     pub fn ed25519_sign_batch(&self, seeds: &[[u8; 32]], messages: &[&[u8]]) -> Result<Vec<[u8; 64]>, BatchError> {
         if seeds.len() != messages.len() {
             return Err(BatchError::InvalidArgument("length mismatch".into()));

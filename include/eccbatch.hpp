@@ -196,7 +196,7 @@ struct ecdsa {
     b.check(rc, bad);
         return std::vector<bool>(ok.begin(), ok.end());
     }
-    // NOT constant-time on the device
+    // constant-time kernels on the device; the ecb_*_vartime entry points are the fast forms for public data
     static std::vector<std::optional<Signature>> sign_hashed_batch(const Batch& b, const std::vector<typename W::Scalar>& secret,
                                                                    const std::vector<typename W::Scalar>& nonce,
                                                                    const std::vector<typename W::Scalar>& hashed) {
@@ -227,7 +227,7 @@ inline std::vector<bool> verify_batch(const Batch& b, const std::vector<PublicKe
     b.check(ecb_ed25519_verify(b.handle(), detail::flat(pk), r.blob.data(), r.off.data(), detail::flat(sig), pk.size(), ok.data()));
     return std::vector<bool>(ok.begin(), ok.end());
 }
-// NOT constant-time on the device
+// constant-time kernels on the device; the ecb_*_vartime entry points are the fast forms for public data
 inline std::vector<PublicKey> public_key_batch(const Batch& b, const std::vector<SecretKey>& seeds) {
     std::vector<PublicKey> out(seeds.size());
     b.check(ecb_ed25519_public_from_seed(b.handle(), detail::flat(seeds), seeds.size(), detail::flat(out)));
