@@ -1,5 +1,6 @@
 #!/bin/bash
-# round 2, step w: A/B of builds of the Weierstrass variable-base kernels (blocks per SM, window width); see tools/tune_wei_lib.py
+# round 2, step w: A/B of builds of the Weierstrass variable-base kernels (blocks per SM, window width); the variants/ libraries
+# come from tools/build_variant.sh (e.g. `build_variant.sh p256_mb6 tu_wei_p256 -DECB_WEI_MINBLOCKS=6`); see tools/tune_wei_lib.py
 mkdir -p gpurun_out
 D=eccoxide_b200/libeccbatch.so
 O=gpurun_out/r2w2_tune_wei_lib.jsonl; : > $O
